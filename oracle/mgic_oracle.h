@@ -1,0 +1,143 @@
+/*
+ * mgic_oracle.h -- C interface of the CPU ORACLE.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library, and only as the checker / the timed
+ * CPU arm.  The product (mg_ic_code_b200/) never links, imports or executes it.
+ *
+ * PARITY UNPINNED: the reference (eugenealim/MG_IC_code) ships no tests, no
+ * golden vectors and cannot be built here (needs Chombo 3.2 + Fortran + MPI +
+ * HDF5, none present).  This oracle is a line-faithful restatement of the
+ * reference sources cited at each function, plus a restatement of the
+ * Chombo 3.2 control flow the path leans on (MultiGrid::cycle,
+ * BiCGStabSolver::solve, DiriBC/NeumBC, CoarseAverage, FORT_PROLONG), which is
+ * NOT vendored under /root/reference and is restated from its published
+ * algorithm.  Its own pins are the known-answer tests in tests/ (trivial KAT,
+ * trace-free KAT, manufactured solution, decomposition invariance) and an
+ * independent numpy twin (tests/np_twin.py).
+ */
+#ifndef MGIC_ORACLE_H
+#define MGIC_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors PoissonParameters (Source/PoissonParameters.H:20-63) plus the solver
+ * knobs Main_PoissonSolver.cpp:106-126 and Source/SetBCs.cpp:42-58 read. */
+typedef struct orc_params {
+  double alpha, beta;
+  double G_Newton, phi_amplitude, phi_wavelength;
+  double bh1_bare_mass, bh1_spin, bh1_momentum, bh1_offset;
+  double bh2_bare_mass, bh2_spin, bh2_momentum, bh2_offset;
+  double L;           /* domain length of direction 0; dx = L / N[0]       */
+  double bc_value;
+  double tolerance;
+  int N[3];
+  int max_level;
+  int block_factor, max_grid_size;
+  int coefficient_average_type; /* 0 arithmetic, 1 harmonic (CoarseAverage enum) */
+  int is_periodic;
+  int bc_lo[3], bc_hi[3];       /* 0 Dirichlet, 1 Neumann, 2 periodic      */
+  int numMGsmooth, numMGIterations, preCondSolverDepth;
+  int max_iterations, max_NL_iterations;
+  int verbosity;
+} orc_params;
+
+/* ---- kernel level: Fortran calling convention of the .ChF routines ------
+ * FRA  = ptr, lo0,lo1,lo2, hi0,hi1,hi2, ncomp      (all by pointer)
+ * FRA1 = ptr, lo0,lo1,lo2, hi0,hi1,hi2
+ * BOX  = lo0,lo1,lo2, hi0,hi1,hi2                                          */
+#define ORC_FRA(a)  double *a, const int *a##lo0, const int *a##lo1, const int *a##lo2, \
+                    const int *a##hi0, const int *a##hi1, const int *a##hi2, const int *a##nc
+#define ORC_CFRA(a) const double *a, const int *a##lo0, const int *a##lo1, const int *a##lo2, \
+                    const int *a##hi0, const int *a##hi1, const int *a##hi2, const int *a##nc
+#define ORC_FRA1(a)  double *a, const int *a##lo0, const int *a##lo1, const int *a##lo2, \
+                     const int *a##hi0, const int *a##hi1, const int *a##hi2
+#define ORC_CFRA1(a) const double *a, const int *a##lo0, const int *a##lo1, const int *a##lo2, \
+                     const int *a##hi0, const int *a##hi1, const int *a##hi2
+#define ORC_BOX(b)  const int *b##lo0, const int *b##lo1, const int *b##lo2, \
+                    const int *b##hi0, const int *b##hi1, const int *b##hi2
+
+void orc_gsrbhelmholtzvc3d(ORC_FRA(dpsi), ORC_CFRA(rhs), ORC_BOX(region), const double *dx,
+                           const double *alpha, ORC_CFRA(aCoef), const double *beta,
+                           ORC_CFRA(bCoef), ORC_CFRA(lambda), const int *redBlack);
+void orc_vccomputeop3d(ORC_FRA(lofdpsi), ORC_CFRA(dpsi), const double *alpha, ORC_CFRA(aCoef),
+                       const double *beta, ORC_CFRA(bCoef), ORC_BOX(region), const double *dx);
+void orc_vccomputeres3d(ORC_FRA(res), ORC_CFRA(dpsi), ORC_CFRA(rhs), const double *alpha,
+                        ORC_CFRA(aCoef), const double *beta, ORC_CFRA(bCoef), ORC_BOX(region),
+                        const double *dx);
+void orc_restrictresvc3d(ORC_FRA(res), ORC_CFRA(dpsi), ORC_CFRA(rhs), const double *alpha,
+                         ORC_CFRA(aCoef), const double *beta, ORC_CFRA(bCoef), ORC_BOX(region),
+                         const double *dx);
+void orc_getlaplacianpsif(ORC_FRA1(lap), ORC_CFRA1(psi), const double *dx, ORC_BOX(box));
+void orc_getrhogradphif(ORC_FRA1(rho), ORC_CFRA1(phi), const double *dx, ORC_BOX(box));
+void orc_prolong(ORC_FRA(phi), ORC_CFRA(coarse), ORC_BOX(region), const int *m);
+
+/* ---- problem level -------------------------------------------------------
+ * Field ids for orc_get_field / orc_set_field (global, ghost-free arrays in
+ * Fortran order: idx = i + nx*(j + ny*k)).                                   */
+enum {
+  ORC_F_E = 0,      /* MG correction e[depth]   (depth 0: the vector being solved for) */
+  ORC_F_R = 1,      /* MG residual / rhs r[depth]                                      */
+  ORC_F_A = 2,      /* aCoef[depth]                                                    */
+  ORC_F_B = 3,      /* bCoef[depth]                                                    */
+  ORC_F_LAMBDA = 4, /* lambda[depth]                                                   */
+  ORC_F_TMP = 5,    /* scratch, output of residual/applyOp                             */
+  ORC_F_DPSI = 6,   /* level-0 only: dpsi                                              */
+  ORC_F_RHS = 7,    /* level-0 only: rhs from set_rhs                                  */
+  ORC_F_MGVAR0 = 16 /* + comp (0..7): multigrid_vars component                          */
+};
+
+typedef struct orc_problem orc_problem;
+
+orc_problem *orc_create(const orc_params *p);
+void orc_destroy(orc_problem *);
+int orc_num_threads(void);
+
+/* Main_PoissonSolver.cpp:79-95 */
+void orc_set_initial_conditions(orc_problem *);
+/* Main_PoissonSolver.cpp:154-160: set_a_coef, set_b_coef, set_rhs */
+void orc_set_coefs_and_rhs(orc_problem *, double constant_K);
+/* Main_PoissonSolver.cpp:163-170: factory + MG hierarchy (MGnewOp until NULL);
+ * returns the number of MG levels (depths). */
+int orc_define_solver(orc_problem *);
+int orc_mg_depths(const orc_problem *);
+void orc_level_dims(const orc_problem *, int depth, int n[3], double *dx);
+
+void orc_get_field(orc_problem *, int depth, int field, double *out);
+void orc_set_field(orc_problem *, int depth, int field, const double *in);
+/* ghosted read (ng ghost layers, array extents n+2*ng) of e/dpsi/mgvars */
+void orc_get_field_ghosted(orc_problem *, int depth, int field, int ng, double *out);
+
+/* operator methods on MG depth d (reference: VariableCoeffPoissonOperator.cpp) */
+void orc_op_relax(orc_problem *, int depth, int iterations);           /* e, r            */
+void orc_op_gsrb_color(orc_problem *, int depth, int whichPass);       /* one colour pass */
+void orc_op_residual(orc_problem *, int depth, int homogeneous);       /* tmp = r - L e   */
+void orc_op_apply(orc_problem *, int depth, int homogeneous);          /* tmp = L e       */
+void orc_op_restrict(orc_problem *, int depth);                        /* r[d+1] from e[d], r[d] */
+void orc_op_prolong(orc_problem *, int depth);                         /* e[d] += P e[d+1] */
+void orc_op_precond(orc_problem *, int depth);                         /* e = lambda*r; relax 2 */
+double orc_op_norm(orc_problem *, int depth, int field, int ord);
+double orc_op_dot(orc_problem *, int depth, int field1, int field2);
+
+/* MultiGrid::cycle(0, e[0], r[0]) incl. bottom solve; returns bottom BiCGStab iterations */
+int orc_vcycle(orc_problem *);
+/* bottom solver alone on depth = last: BiCGStab(e, r); returns iterations */
+int orc_bottom_solve(orc_problem *);
+/* copy level-0 rhs into r[0], zero e[0] */
+void orc_load_rhs_zero_e(orc_problem *);
+
+/* f1: solver.solve(dpsi, rhs): outer BiCGStab preconditioned by numMGIterations V-cycles.
+ * Returns iterations; fills exit status and final residual norm. */
+int orc_outer_solve(orc_problem *, int *exit_status, double *final_norm, double *norms, int max_norms);
+/* Main_PoissonSolver.cpp:189-205 + computeNorm :208 ; returns dpsi_norm */
+double orc_update_psi0(orc_problem *);
+/* full NL loop (Main_PoissonSolver.cpp:131-216); dpsi_norms[NL_iter]; returns #NL iterations */
+int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

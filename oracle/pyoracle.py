@@ -1,0 +1,231 @@
+"""ctypes binding of oracle/build/libmgic_oracle.so (test infrastructure only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "build", "libmgic_oracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ -O3 -fopenmp, no FMA contraction)."""
+    if force or not os.path.exists(_SO) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+        for f in ("mgic_oracle.cpp", "mgic_oracle.h", "Makefile")
+    ):
+        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("alpha", C.c_double), ("beta", C.c_double),
+        ("G_Newton", C.c_double), ("phi_amplitude", C.c_double), ("phi_wavelength", C.c_double),
+        ("bh1_bare_mass", C.c_double), ("bh1_spin", C.c_double), ("bh1_momentum", C.c_double), ("bh1_offset", C.c_double),
+        ("bh2_bare_mass", C.c_double), ("bh2_spin", C.c_double), ("bh2_momentum", C.c_double), ("bh2_offset", C.c_double),
+        ("L", C.c_double), ("bc_value", C.c_double), ("tolerance", C.c_double),
+        ("N", C.c_int * 3), ("max_level", C.c_int), ("block_factor", C.c_int), ("max_grid_size", C.c_int),
+        ("coefficient_average_type", C.c_int), ("is_periodic", C.c_int),
+        ("bc_lo", C.c_int * 3), ("bc_hi", C.c_int * 3),
+        ("numMGsmooth", C.c_int), ("numMGIterations", C.c_int), ("preCondSolverDepth", C.c_int),
+        ("max_iterations", C.c_int), ("max_NL_iterations", C.c_int), ("verbosity", C.c_int),
+    ]
+
+
+def default_params(**over):
+    """The reference's params.txt physics/solver block (params.txt:12-84) with max_level = 0."""
+    d = dict(
+        alpha=1.0, beta=-1.0, G_Newton=1.0, phi_amplitude=0.1, phi_wavelength=1.0,
+        bh1_bare_mass=0.5, bh1_spin=0.1, bh1_momentum=0.05, bh1_offset=10.0,
+        bh2_bare_mass=0.5, bh2_spin=0.1, bh2_momentum=-0.05, bh2_offset=-10.0,
+        L=100.0, bc_value=0.0, tolerance=1.0e-10, N=(64, 64, 64), max_level=0, block_factor=8,
+        max_grid_size=16, coefficient_average_type=1, is_periodic=0, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0),
+        numMGsmooth=4, numMGIterations=2, preCondSolverDepth=-1, max_iterations=100, max_NL_iterations=6,
+        verbosity=2,
+    )
+    d.update(over)
+    return d
+
+
+def to_struct(d):
+    p = OrcParams()
+    for k, v in d.items():
+        if k in ("N", "bc_lo", "bc_hi"):
+            setattr(p, k, (C.c_int * 3)(*[int(x) for x in v]))
+        else:
+            setattr(p, k, v)
+    return p
+
+
+FIELD = dict(E=0, R=1, A=2, B=3, LAMBDA=4, TMP=5, DPSI=6, RHS=7, MGVAR0=16)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(OrcParams)]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_num_threads.restype = C.c_int
+        for name in ("orc_set_initial_conditions",):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.orc_set_coefs_and_rhs.argtypes = [C.c_void_p, C.c_double]
+        L.orc_define_solver.argtypes = [C.c_void_p]
+        L.orc_define_solver.restype = C.c_int
+        L.orc_mg_depths.argtypes = [C.c_void_p]
+        L.orc_mg_depths.restype = C.c_int
+        L.orc_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.orc_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.orc_set_field.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.orc_get_field_ghosted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_op_relax.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_op_gsrb_color.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_op_residual.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_op_apply.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_op_restrict.argtypes = [C.c_void_p, C.c_int]
+        L.orc_op_prolong.argtypes = [C.c_void_p, C.c_int]
+        L.orc_op_precond.argtypes = [C.c_void_p, C.c_int]
+        L.orc_op_norm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_op_norm.restype = C.c_double
+        L.orc_op_dot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_op_dot.restype = C.c_double
+        L.orc_vcycle.argtypes = [C.c_void_p]
+        L.orc_vcycle.restype = C.c_int
+        L.orc_bottom_solve.argtypes = [C.c_void_p]
+        L.orc_bottom_solve.restype = C.c_int
+        L.orc_load_rhs_zero_e.argtypes = [C.c_void_p]
+        L.orc_outer_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), dp, C.c_int]
+        L.orc_outer_solve.restype = C.c_int
+        L.orc_update_psi0.argtypes = [C.c_void_p]
+        L.orc_update_psi0.restype = C.c_double
+        L.orc_nl_solve.argtypes = [C.c_void_p, dp, C.c_int]
+        L.orc_nl_solve.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """One reference problem (Main_PoissonSolver.cpp poissonSolve state) on the CPU oracle."""
+
+    def __init__(self, **over):
+        self.params = default_params(**over)
+        self._p = to_struct(self.params)
+        self.L = lib()
+        self.h = self.L.orc_create(C.byref(self._p))
+        if not self.h:
+            raise RuntimeError("orc_create failed")
+        self.depths = 0
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup ---------------------------------------------------------------
+    def set_initial_conditions(self):
+        self.L.orc_set_initial_conditions(self.h)
+
+    def set_coefs_and_rhs(self, constant_K=0.0):
+        self.L.orc_set_coefs_and_rhs(self.h, constant_K)
+
+    def define_solver(self):
+        self.depths = self.L.orc_define_solver(self.h)
+        return self.depths
+
+    def setup(self):
+        self.set_initial_conditions()
+        self.set_coefs_and_rhs()
+        return self.define_solver()
+
+    def dims(self, depth=0):
+        n = (C.c_int * 3)()
+        dx = C.c_double()
+        self.L.orc_level_dims(self.h, depth, n, C.byref(dx))
+        return (n[0], n[1], n[2]), dx.value
+
+    # -- fields (numpy arrays indexed [k, j, i]) -----------------------------
+    def get(self, field, depth=0, comp=0):
+        (nx, ny, nz), _ = self.dims(depth if field not in ("DPSI", "RHS", "MGVAR0") else 0)
+        out = np.empty((nz, ny, nx), dtype=np.float64)
+        self.L.orc_get_field(self.h, depth, FIELD[field] + comp, out)
+        return out
+
+    def get_ghosted(self, field, ng, depth=0, comp=0):
+        (nx, ny, nz), _ = self.dims(depth if field not in ("DPSI", "RHS", "MGVAR0") else 0)
+        out = np.zeros((nz + 2 * ng, ny + 2 * ng, nx + 2 * ng), dtype=np.float64)
+        self.L.orc_get_field_ghosted(self.h, depth, FIELD[field] + comp, ng, out)
+        return out
+
+    def set(self, field, arr, depth=0, comp=0):
+        self.L.orc_set_field(self.h, depth, FIELD[field] + comp, np.ascontiguousarray(arr, dtype=np.float64))
+
+    # -- operator -------------------------------------------------------------
+    def relax(self, depth, iterations):
+        self.L.orc_op_relax(self.h, depth, iterations)
+
+    def gsrb_color(self, depth, which):
+        self.L.orc_op_gsrb_color(self.h, depth, which)
+
+    def residual(self, depth, homogeneous=True):
+        self.L.orc_op_residual(self.h, depth, int(homogeneous))
+        return self.get("TMP", depth)
+
+    def apply(self, depth, homogeneous=True):
+        self.L.orc_op_apply(self.h, depth, int(homogeneous))
+        return self.get("TMP", depth)
+
+    def restrict(self, depth):
+        self.L.orc_op_restrict(self.h, depth)
+
+    def prolong(self, depth):
+        self.L.orc_op_prolong(self.h, depth)
+
+    def precond(self, depth):
+        self.L.orc_op_precond(self.h, depth)
+
+    def norm(self, depth, field, ord=0):
+        return self.L.orc_op_norm(self.h, depth, FIELD[field], ord)
+
+    def dot(self, depth, f1, f2):
+        return self.L.orc_op_dot(self.h, depth, FIELD[f1], FIELD[f2])
+
+    def vcycle(self):
+        return self.L.orc_vcycle(self.h)
+
+    def bottom_solve(self):
+        return self.L.orc_bottom_solve(self.h)
+
+    def load_rhs_zero_e(self):
+        self.L.orc_load_rhs_zero_e(self.h)
+
+    def outer_solve(self, max_norms=256):
+        st = C.c_int()
+        fn = C.c_double()
+        norms = np.zeros(max_norms)
+        it = self.L.orc_outer_solve(self.h, C.byref(st), C.byref(fn), norms, max_norms)
+        return it, st.value, fn.value, norms[: it + 1].copy()
+
+    def update_psi0(self):
+        return self.L.orc_update_psi0(self.h)
+
+    def nl_solve(self):
+        out = np.zeros(64)
+        n = self.L.orc_nl_solve(self.h, out, 64)
+        return out[:n].copy()
+
+    @property
+    def num_threads(self):
+        return self.L.orc_num_threads()
