@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- V-cycle throughput of the VariableCoeffPoissonOperator multigrid hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--smooth 2] [--box 32] [--keep-b] [--smoother 1]
+  python bench.py --impl reference ...      # the CPU restatement (oracle) on the host cores, same metric
+
+A "step" is one multigrid V-cycle on a zeroed correction (what [Chombo] MultilevelLinearOp::preCond does per
+V-cycle): setToZero(e); MultiGrid::oneCycle(e, r) -- pre-smooth, restrictResidual, recurse, bottom BiCGStab,
+prolongIncrement, post-smooth on every MG depth.  Synthetic data: the reference's params.txt Bowen-York binary
+(Main_PoissonSolver.cpp first nonlinear iteration: psi = 1, rhs / aCoef from set_rhs / set_a_coef), single level.
+
+Prints ONE JSON line (see the contract in the task description / DESIGN.md "Measurement").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vcycle_gdof_per_s_512cubed_V22"
+UNIT = "GDOF/s"
+
+
+def algorithmic_bytes_per_cell(smooth, keep_b):
+    """per level 48(nu1+nu2)+52 B/cell with bCoef streamed; bCoef == 1 dropped: 40(nu1+nu2)+44."""
+    sweep = 48 if keep_b else 40
+    level = sweep * 2 * smooth + (33 + 1 + 1 + 17 if keep_b else 25 + 1 + 1 + 17)
+    return sweep, level
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            inside = t0 - 0.05 <= t <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            if inside:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's CPU path: the boxed C++ restatement under oracle/ (the reference itself needs Chombo 3.2 +
+    Fortran + MPI and cannot be built here), OpenMP over boxes on all host cores, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import Oracle
+    n = args.cpu_n
+    o = Oracle(N=(n, n, n), max_grid_size=args.box, numMGsmooth=args.smooth)
+    o.setup()
+    o.load_rhs_zero_e()
+    rhs = o.get("RHS")
+    zero = np.zeros_like(rhs)
+    for _ in range(args.warmup):
+        o.set("E", zero)
+        o.vcycle()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.set("E", zero)
+        o.vcycle()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n ** 3 / dt / 1e9
+    sample = f"{args.steps} V({args.smooth},{args.smooth}) cycles on a {n}^3 sub-sample of the workload, {args.box}^3 boxes"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"single-level {args.n}^3 Bowen-York binary (params.txt physics), V({args.smooth},{args.smooth}), "
+                        f"max_grid_size {args.box}, harmonic coefficient averaging, Dirichlet dpsi=0",
+            "n": args.n, "numMGsmooth": args.smooth, "max_grid_size": args.box,
+            "l2": "inputs larger than L2 (every level-0 array is n^3*8 B = %.0f MiB >> 126 MB); no flush needed" % (args.n ** 3 * 8 / 2 ** 20),
+            "bCoef": "streamed" if args.keep_b else "dropped (identically 1; bit-identical results)",
+            "smoother": "fused red+black sweep" if args.smoother == 1 else "one launch per colour",
+            "decomposition": "z-slabs, one per GPU"}
+
+
+def cpu_baseline(args):
+    from oracle import Oracle
+    n = args.cpu_n
+    o = Oracle(N=(n, n, n), max_grid_size=args.box, numMGsmooth=args.smooth)
+    o.setup()
+    o.load_rhs_zero_e()
+    o.vcycle()
+    zero = np.zeros((n, n, n))
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o.set("E", zero)
+        o.vcycle()
+    dt = (time.perf_counter() - t0) / reps
+    cores = o.num_threads
+    o.close()
+    return {"value": n ** 3 / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} V({args.smooth},{args.smooth}) cycles at {n}^3 ({args.box}^3 boxes) with the boxed C++ oracle, "
+                      f"OpenMP over boxes on {cores} host threads", "ms_per_vcycle": dt * 1e3}
+
+
+def run_gpu(args):
+    import torch
+    import mg_ic_code_b200 as m
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = m.Context(local, rank=rank, nranks=world)
+    if world > 1:
+        from mg_ic_code_b200 import comm
+        comm.attach(ctx, dist)
+
+    n = args.n
+    # weak scaling (C5): every GPU owns n^2 x n planes; the global domain grows in z
+    N = (n, n, n * world)
+    P = m.make_params(dict(m.DEFAULTS, N=N, L=100.0, max_grid_size=args.box, numMGsmooth=args.smooth))
+    k0, nzl = rank * n, n
+    lvl = m.level_op_from_params(ctx, P, k0, nzl)
+    vars_ = m.MultigridVars(ctx, P, k0, nzl)
+    dpsi, rhs, a, b = lvl.create(), lvl.create(), lvl.create(), lvl.create()
+    vars_.set_initial_conditions(dpsi)
+    vars_.set_rhs_and_a_coef(rhs, a)
+    vars_.set_b_coef(b)
+    vars_.close()
+    f = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b, keep_b=args.keep_b)
+    f.set_smoother(args.smoother)
+    op = f.MGnewOp(0)
+    e = op.create()
+    cells_local = n * n * nzl
+    cells_total = cells_local * world
+
+    def step():
+        op.setToZero(e)
+        f.vcycle(e, rhs)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- device-resident timing (value) with per-launch timing of the dominant kernel --------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ctx.profile(True)
+    l0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - l0
+    k_launches, k_ms = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    bottom_iters = f.last_bottom_iterations
+    # ---- end-to-end through the C ABI with HOST buffers: H2D residual, V-cycle, D2H correction ----------------
+    # each rank's pinned buffers hold its own slab; the C ABI addresses global arrays, so pass the slab-shifted base
+    h_r = torch.empty(cells_local, dtype=torch.float64).pin_memory()
+    h_e = torch.empty(cells_local, dtype=torch.float64).pin_memory()
+    off = k0 * n * n * 8
+    L = m.lib()
+    m._capi.check(L.mgic_field_download_async(rhs.h, C.c_void_p(h_r.data_ptr() - off)))
+    ctx.sync()
+    r_dev = op.create()
+
+    def step_e2e():
+        m._capi.check(L.mgic_field_upload_async(r_dev.h, C.c_void_p(h_r.data_ptr() - off)))
+        op.setToZero(e)
+        f.vcycle(e, r_dev)
+        m._capi.check(L.mgic_field_download_async(e.h, C.c_void_p(h_e.data_ptr() - off)))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    step_e2e()
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(e2e_steps):
+            step_e2e()
+        ev1.record(stream)
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e, k_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, k_ms = t.tolist()
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = cells_total / (ms_step * 1e-3) / 1e9
+        e2e_val = cells_total / (ms_e2e / e2e_steps * 1e-3) / 1e9
+        sweep_b, level_b = algorithmic_bytes_per_cell(args.smooth, args.keep_b)
+        peak, peak_src = peaks()
+        per_launch_cells = cells_local if args.smoother == 1 else cells_local / 2.0   # one launch = a sweep / a colour pass
+        alg_bytes_launch = sweep_b * per_launch_cells if args.smoother == 1 else sweep_b / 2.0 * cells_local
+        kdur = k_ms / max(k_launches, 1) * 1e-3
+        achieved = alg_bytes_launch / kdur / 1e9 if k_launches else None
+        vcycle_bytes = level_b * cells_local * sum(1.0 / 8 ** d for d in range(f.depths))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload_config(args), mg_depths=f.depths, bottom_bicgstab_iterations=bottom_iters,
+                                                global_cells=cells_total),
+            "roofline": {"bound": "hbm", "kernel": "finest-level GSRB " + ("fused red+black sweep" if args.smoother == 1 else "colour pass"),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "launches_timed": k_launches, "avg_launch_ms": kdur * 1e3,
+                         "kernel_share_of_step": k_ms / ms,
+                         "vcycle_algorithmic_GBps": vcycle_bytes / (ms_step * 1e-3) / 1e9,
+                         "vcycle_frac_of_peak": vcycle_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": cells_total * 8, "d2h_bytes_per_step": cells_total * 8,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "what": "pinned-host residual -> HBM, setToZero + V-cycle, correction -> pinned host, through the C ABI"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="cells per side per GPU")
+    ap.add_argument("--cpu-n", type=int, default=256, help="side of the CPU sample problem")
+    ap.add_argument("--smooth", type=int, default=2, help="numMGsmooth (pre = post = bottom)")
+    ap.add_argument("--box", type=int, default=32, help="max_grid_size (sets the MG depth, Factory.cpp:168-172)")
+    ap.add_argument("--keep-b", action="store_true", help="stream bCoef even though it is identically 1")
+    ap.add_argument("--smoother", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+/*
+ * mgic.h -- C ABI of the B200-native multigrid hot path of MG_IC_code.
+ *
+ * Two nested boundaries, both exported by libmgic_b200.so:
+ *
+ *  (A) mgic_*  : device-resident operator API.  One mgic_op is one
+ *      VariableCoeffPoissonOperator (Source/VariableCoeffPoissonOperator.H:25)
+ *      on one multigrid/AMR level; fields live in HBM; no per-call PCIe
+ *      traffic.  The C++ host mirror (mg_ic_code_b200/host) wraps these in the
+ *      reference's AMRLevelOp<LevelData<FArrayBox>> interface.
+ *
+ *  (B) the Fortran symbols of the reference's .ChF kernels with their exact
+ *      argument lists (host pointers; H2D, CUDA kernel, D2H) -- the link-time
+ *      drop-in for Source/VariableCoeffPoissonOperatorF_F.H and
+ *      Source/SetLevelDataF_F.H.  Declared in mgic_chf.h.
+ *
+ * Plain C: pointers and sizes only.  Every mgic_* function returns 0 on
+ * success, nonzero on error (message via mgic_last_error()); the reference's
+ * error behaviour (MayDay::Error/Abort == process abort) is re-created by the
+ * C++ host mirror on a nonzero return.  There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with MGIC_ERR_NO_DEVICE.
+ *
+ * All arithmetic is FP64; kernels are compiled without FMA contraction and
+ * follow the operation order of the .ChF sources.
+ */
+#ifndef MGIC_H
+#define MGIC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGIC_OK 0
+#define MGIC_ERR_NO_DEVICE 1
+#define MGIC_ERR_CUDA 2
+#define MGIC_ERR_ARG 3
+#define MGIC_ERR_STATE 4
+
+/* BC flags: params.txt bc_lo/bc_hi (Source/SetBCs.cpp:70-94) */
+#define MGIC_BC_DIRICHLET 0
+#define MGIC_BC_NEUMANN 1
+#define MGIC_BC_PERIODIC 2
+
+/* CoarseAverage::averageType [Chombo]; params.txt coefficient_average_type */
+#define MGIC_AVG_ARITHMETIC 0
+#define MGIC_AVG_HARMONIC 1
+
+typedef struct mgic_ctx mgic_ctx;     /* device + streams (+ peers)                         */
+typedef struct mgic_op mgic_op;       /* VariableCoeffPoissonOperator on one level          */
+typedef struct mgic_field mgic_field; /* one-component FP64 level array resident in HBM     */
+typedef struct mgic_mg mgic_mg;       /* MultiGrid hierarchy built by the factory           */
+typedef struct mgic_vars mgic_vars;   /* multigrid_vars (8 comps, MultigridUserVariables.hpp) */
+
+/* Mirrors PoissonParameters (Source/PoissonParameters.H) + the solver knobs read at
+ * Main_PoissonSolver.cpp:106-126 and the BC keys of Source/SetBCs.cpp:45-56. */
+typedef struct mgic_params {
+  double alpha, beta;
+  double G_Newton, phi_amplitude, phi_wavelength;
+  double bh1_bare_mass, bh1_spin, bh1_momentum, bh1_offset;
+  double bh2_bare_mass, bh2_spin, bh2_momentum, bh2_offset;
+  double L;
+  double bc_value;
+  double tolerance;
+  int N[3];
+  int max_level;
+  int block_factor, max_grid_size;
+  int coefficient_average_type;
+  int is_periodic;
+  int bc_lo[3], bc_hi[3];
+  int numMGsmooth, numMGIterations, preCondSolverDepth;
+  int max_iterations, max_NL_iterations;
+  int verbosity;
+} mgic_params;
+
+const char *mgic_last_error(void);
+const char *mgic_version(void);
+
+/* ------------------------------------------------------------------ context */
+int mgic_ctx_create(int device, mgic_ctx **out);
+int mgic_ctx_destroy(mgic_ctx *);
+int mgic_ctx_sync(mgic_ctx *);
+/* use an existing CUDA stream (e.g. torch's current stream) for all launches; 0 = own stream */
+int mgic_ctx_set_stream(mgic_ctx *, void *cuda_stream);
+void *mgic_ctx_stream(mgic_ctx *);
+/* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
+long long mgic_ctx_launch_count(mgic_ctx *);
+/* per-launch CUDA-event timing of the dominant kernel (the finest level's GSRB launches): arm with enable = 1,
+ * run, then read the number of timed launches and their summed device time (bench.py roofline) */
+int mgic_ctx_profile(mgic_ctx *, int enable);
+int mgic_ctx_profile_read(mgic_ctx *, long long *launches, double *total_ms);
+/* multi-GPU z-slab decomposition: this context is rank `rank` of `nranks` (one process per GPU);
+ * peers are wired with mgic_ctx_set_peer_halo(); see mgic_comm.h */
+int mgic_ctx_set_rank(mgic_ctx *, int rank, int nranks);
+
+/* ----------------------------------------------------------------- operator
+ * replaces: VariableCoeffPoissonOperator + AMRPoissonOp::define
+ * (Source/VariableCoeffPoissonOperatorFactory.cpp:187-192).  n = cells of the level's
+ * (rectangular, single-box-per-rank) domain; the rank owns global planes
+ * [k0, k0+nz_local).  Single GPU: k0 = 0, nz_local = n[2]. */
+int mgic_op_create(mgic_ctx *, const int n[3], int k0, int nz_local, double dx, double alpha, double beta,
+                   const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
+int mgic_op_destroy(mgic_op *);
+/* setCoefs (VariableCoeffPoissonOperator.cpp:208-218): coefficients are SHARED (caller keeps them alive);
+ * bCoef may be NULL == the constant 1 (set_b_coef, Source/SetLevelData.cpp:330-340) */
+int mgic_op_set_coefs(mgic_op *, mgic_field *aCoef, mgic_field *bCoef, double alpha, double beta);
+int mgic_op_set_alpha_beta(mgic_op *, double alpha, double beta);       /* :196-206 */
+int mgic_op_reset_lambda(mgic_op *);                                    /* :220-249 */
+int mgic_op_compute_lambda(mgic_op *);                                  /* :252-260 */
+int mgic_op_get_lambda(mgic_op *, mgic_field **lambda);
+int mgic_op_dims(const mgic_op *, int n[3], int *k0, int *nz_local, double *dx);
+
+/* fields: AMRLevelOp::create / createCoarser */
+int mgic_field_create(mgic_op *like, mgic_field **out);
+int mgic_field_destroy(mgic_field *);
+/* global ghost-free host array, Fortran order idx = i + nx*(j + ny*k), k global; the rank moves its slab */
+int mgic_field_upload(mgic_field *, const double *host);
+int mgic_field_download(const mgic_field *, double *host);
+/* same, ordered on the context stream without a host sync (pinned host memory; pair with mgic_ctx_sync) */
+int mgic_field_upload_async(mgic_field *, const double *host);
+int mgic_field_download_async(const mgic_field *, double *host);
+/* one FArrayBox (host, inclusive bounds incl. ghosts, Fortran order): copies fab ∩ region ∩ (this rank's slab) */
+int mgic_field_upload_fab(mgic_field *, const double *fab, const int fab_lo[3], const int fab_hi[3],
+                          const int region_lo[3], const int region_hi[3]);
+int mgic_field_download_fab(const mgic_field *, double *fab, const int fab_lo[3], const int fab_hi[3],
+                            const int region_lo[3], const int region_hi[3]);
+/* device pointer of local cell (0,0,0) and strides in doubles (plumbing for torch / tests) */
+int mgic_field_devptr(const mgic_field *, void **ptr, long long *stride_y, long long *stride_z);
+
+/* operator methods; names follow Source/VariableCoeffPoissonOperator.H:40-168 and AMRPoissonOp [Chombo] */
+int mgic_op_relax(mgic_op *, mgic_field *e, const mgic_field *residual, int iterations);   /* relax -> levelGSRB :273 */
+int mgic_op_gsrb_color(mgic_op *, mgic_field *e, const mgic_field *residual, int whichPass); /* one pass of :290-331 */
+int mgic_op_level_jacobi(mgic_op *, mgic_field *e, const mgic_field *residual);             /* :360-385 */
+int mgic_op_residual(mgic_op *, mgic_field *lhs, mgic_field *phi, const mgic_field *rhs, int homogeneous); /* :30-67 */
+int mgic_op_apply(mgic_op *, mgic_field *lhs, mgic_field *phi, int homogeneous);            /* applyOpI :106-121 */
+int mgic_op_apply_no_boundary(mgic_op *, mgic_field *lhs, mgic_field *phi);                 /* :123-149 */
+int mgic_op_restrict_residual(mgic_op *fine, mgic_field *resCoarse, mgic_field *phiFine, const mgic_field *rhsFine); /* :151-194 */
+int mgic_op_prolong_increment(mgic_op *fine, mgic_field *phiFine, const mgic_field *correctCoarse); /* [Chombo] FORT_PROLONG */
+int mgic_op_precond(mgic_op *, mgic_field *phi, const mgic_field *rhs);                     /* :72-104 */
+/* BLAS-1 over valid cells [Chombo AMRPoissonOp] */
+int mgic_op_norm(mgic_op *, const mgic_field *x, int ord, double *out);  /* ord 0: max|x|, 1: sum|x|, 2: sqrt(sum x^2) */
+int mgic_op_dot(mgic_op *, const mgic_field *x, const mgic_field *y, double *out);
+int mgic_op_incr(mgic_op *, mgic_field *y, const mgic_field *x, double scale);             /* y += scale*x */
+int mgic_op_axby(mgic_op *, mgic_field *y, const mgic_field *x1, const mgic_field *x2, double a, double b);
+int mgic_op_scale(mgic_op *, mgic_field *y, double s);
+int mgic_op_assign(mgic_op *, mgic_field *y, const mgic_field *x);
+int mgic_op_set_to_zero(mgic_op *, mgic_field *y);
+int mgic_op_set_val(mgic_op *, mgic_field *y, double v);
+/* smoother implementation used by relax: 0 = one launch per colour pass, 1 = fused red+black plane-streaming sweep (default) */
+int mgic_op_set_smoother(mgic_op *, int kind);
+
+/* ---------------------------------------------------------------- factory / MG
+ * replaces VariableCoeffPoissonOperatorFactory::define + MGnewOp (Factory.cpp:59-106,139-234) driven by
+ * [Chombo] MultiGrid::define: ops for depth 0,1,.. are built until the depth limit
+ * "boxes coarsenable by 2^depth * s_maxCoarse" (Factory.cpp:168-172) fails; boxes are the
+ * domainSplit lattice of max_grid_size (Source/SetGrids.cpp:54-58) unless given explicitly.
+ * Coefficients of depth>0 are CoarseAverage'd directly from depth 0 (Factory.cpp:199-227). */
+int mgic_mg_create(mgic_ctx *, const mgic_params *, mgic_field *aCoef0, mgic_field *bCoef0, mgic_mg **out);
+/* flags: MGIC_MG_KEEP_B = always stream bCoef (by default a bCoef that is identically 1 -- set_b_coef,
+ * Source/SetLevelData.cpp:330-340 -- is dropped from the kernels; x*1 == x, so results are bit-identical) */
+#define MGIC_MG_KEEP_B 1
+int mgic_mg_create_ex(mgic_ctx *, const mgic_params *, mgic_field *aCoef0, mgic_field *bCoef0, int flags, mgic_mg **out);
+int mgic_mg_b_is_one(const mgic_mg *);
+int mgic_mg_destroy(mgic_mg *);
+int mgic_mg_depths(const mgic_mg *);
+int mgic_mg_op(mgic_mg *, int depth, mgic_op **op);               /* MGnewOp(domain, depth) result; NULL past the end */
+int mgic_mg_scratch(mgic_mg *, int depth, mgic_field **e, mgic_field **r);  /* MultiGrid m_correction/m_residual */
+/* (re)coarsen coefficients after aCoef0 changed + recompute lambda (what re-defining the factory does per NL iteration) */
+int mgic_mg_refresh_coefs(mgic_mg *);
+/* [Chombo] MultiGrid::oneCycle (homogeneous) == cycle(0, e, r): relax/restrict/recurse/prolong/relax + bottom solve */
+int mgic_mg_vcycle(mgic_mg *, mgic_field *e, const mgic_field *r);
+int mgic_mg_bottom_solve(mgic_mg *, mgic_field *e, const mgic_field *r, int *iterations);
+int mgic_mg_last_bottom_iterations(const mgic_mg *);
+/* select the smoother implementation on every depth (see mgic_op_set_smoother) */
+int mgic_mg_set_smoother(mgic_mg *, int kind);
+
+/* f1: BiCGStabSolver<Vector<LevelData*>>::solve preconditioned by numMGIterations V-cycles
+ * (Main_PoissonSolver.cpp:103-117,173-184); norms[0..iterations] = residual history (normType 0) */
+int mgic_mg_outer_solve(mgic_mg *, mgic_field *dpsi, const mgic_field *rhs, int *iterations, int *exit_status,
+                        double *norms, int max_norms);
+
+/* ---------------------------------------------------------------- source terms
+ * multigrid_vars: 8 components (MultigridUserVariables.hpp:10-23) with one ghost layer on every side */
+int mgic_vars_create(mgic_ctx *, const mgic_params *, int k0, int nz_local, mgic_vars **out);
+int mgic_vars_destroy(mgic_vars *);
+int mgic_vars_download(const mgic_vars *, int comp, double *host /* ghost-free global array */);
+int mgic_vars_download_ghosted(const mgic_vars *, int comp, double *host /* (n+2)^3 */);
+/* set_initial_conditions (Source/SetLevelData.cpp:32-71): psi=1, dpsi=0, phi, Aij over the ghosted box */
+int mgic_set_initial_conditions(mgic_vars *, mgic_field *dpsi);
+/* set_a_coef / set_b_coef / set_rhs (Source/SetLevelData.cpp:73-127,281-340) */
+int mgic_set_a_coef(mgic_vars *, mgic_field *aCoef, double constant_K);
+int mgic_set_b_coef(mgic_vars *, mgic_field *bCoef);
+int mgic_set_rhs(mgic_vars *, mgic_field *rhs, double constant_K);
+int mgic_set_rhs_and_a_coef(mgic_vars *, mgic_field *rhs, mgic_field *aCoef, double constant_K);  /* both in one pass */
+/* set_update_psi0 (Source/SetLevelData.cpp:243-263) + computeNorm (Main_PoissonSolver.cpp:208) */
+int mgic_update_psi0(mgic_vars *, mgic_op *op0, mgic_field *dpsi, double *dpsi_norm);
+/* the NL loop of Main_PoissonSolver.cpp:131-216 for a single level, fully device resident */
+int mgic_nl_solve(mgic_ctx *, const mgic_params *, double *dpsi_norms, int max_out, int *nl_iterations,
+                  double *psi_out /* optional ghost-free host array */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGIC_H */

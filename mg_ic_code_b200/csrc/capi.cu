@@ -1,0 +1,916 @@
+// capi.cu -- the device-resident C ABI of include/mgic.h: context, level fields, the
+// VariableCoeffPoissonOperator methods, the operator factory / MultiGrid hierarchy, the V-cycle with its
+// bottom BiCGStab, the outer BiCGStab (f1) and the nonlinear loop of Main_PoissonSolver.cpp.
+//
+// Host code here only sequences kernel launches; all field data stays in HBM.  There is no CPU compute path.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+#include "mgic_internal.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void mgic_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char *mgic_last_error(void) { return g_err; }
+extern "C" const char *mgic_version(void) { return "mgic_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int mgic_ctx_create(int device, mgic_ctx **out) {
+  MGIC_REQUIRE(out, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    mgic_set_error("no CUDA device available (%s): the B200 path has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return MGIC_ERR_NO_DEVICE;
+  }
+  MGIC_REQUIRE(device >= 0 && device < ndev, "bad device index");
+  MGIC_CUDA(cudaSetDevice(device));
+  mgic_ctx *c = new mgic_ctx;
+  c->device = device;
+  MGIC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->ownStream = true;
+  cudaDeviceProp prop;
+  MGIC_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->numSMs = prop.multiProcessorCount;
+  c->partCap = 4096;
+  MGIC_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+  MGIC_CUDA(cudaMemset(c->d_scal, 0, 64 * sizeof(double)));
+  MGIC_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
+  MGIC_CUDA(cudaMalloc(&c->d_part, c->partCap * sizeof(double)));
+  MGIC_CUDA(cudaMalloc(&c->d_count, sizeof(unsigned int)));
+  MGIC_CUDA(cudaMemset(c->d_count, 0, sizeof(unsigned int)));
+  *out = c;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_ctx_destroy(mgic_ctx *c) {
+  if (!c) return MGIC_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_scal);
+  cudaFreeHost(c->h_scal);
+  cudaFree(c->d_part);
+  cudaFree(c->d_count);
+  if (c->ownStream) cudaStreamDestroy(c->stream);
+  delete c;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_ctx_sync(mgic_ctx *c) {
+  MGIC_REQUIRE(c, "ctx is NULL");
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  return MGIC_OK;
+}
+
+extern "C" int mgic_ctx_set_stream(mgic_ctx *c, void *s) {
+  MGIC_REQUIRE(c, "ctx is NULL");
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->ownStream) {
+    cudaStreamDestroy(c->stream);
+    c->ownStream = false;
+  }
+  if (s) c->stream = (cudaStream_t)s;
+  else {
+    MGIC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+  }
+  return MGIC_OK;
+}
+extern "C" void *mgic_ctx_stream(mgic_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" long long mgic_ctx_launch_count(mgic_ctx *c) { return c ? c->launches : 0; }
+extern "C" int mgic_ctx_set_rank(mgic_ctx *c, int rank, int nranks) {
+  MGIC_REQUIRE(c && nranks >= 1 && rank >= 0 && rank < nranks, "bad rank/nranks");
+  c->rank = rank;
+  c->nranks = nranks;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_ctx_profile(mgic_ctx *c, int enable) {
+  MGIC_REQUIRE(c, "ctx is NULL");
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto &ev : c->profEvents) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  c->profEvents.clear();
+  c->profiling = enable != 0;
+  return MGIC_OK;
+}
+extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *total_ms) {
+  MGIC_REQUIRE(c && launches && total_ms, "NULL argument");
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (auto &ev : c->profEvents) {
+    float ms = 0.f;
+    MGIC_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+  }
+  *launches = (long long)c->profEvents.size();
+  *total_ms = tot;
+  return MGIC_OK;
+}
+
+// read back `n` device scalars starting at slot (one sync); multi-rank: combine with op (0 sum, 1 max)
+static int fetch_scalars(mgic_ctx *c, int slot, int n, int op, double *out) {
+  MGIC_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->d_scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  for (int q = 0; q < n; q++) out[q] = c->h_scal[slot + q];
+  if (c->nranks > 1) {
+    MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm)");
+    MGIC_TRY(c->allreduce(c, out, n, op));
+  }
+  return MGIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ operator
+BCk mgic_op::bck(bool homogeneous) const {
+  BCk k;
+  const double v = homogeneous ? 0.0 : bc_value;
+  for (int f = 0; f < 6; f++) {
+    const int dir = f / 2, side = (f % 2) ? +1 : -1;
+    int t = (side < 0) ? bc_lo[dir] : bc_hi[dir];
+    k.type[f] = t;
+    if (t == MGIC_BC_DIRICHLET) { k.a[f] = -1.0; k.b[f] = 2 * v; }               // DiriBC order 1: 2*v - near
+    else if (t == MGIC_BC_NEUMANN) { k.a[f] = 1.0; k.b[f] = side * dx * v; }     // NeumBC: near + side*dx*v
+    else { k.a[f] = 0.0; k.b[f] = 0.0; }
+  }
+  if (k0 > 0) k.type[4] = MGIC_FACE_INTERIOR;
+  if (k0 + nzl < n[2]) k.type[5] = MGIC_FACE_INTERIOR;
+  if (ctx->nranks > 1 && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
+  return k;
+}
+
+static int field_alloc(mgic_ctx *c, int nx, int ny, int nz, int k0, int gnz, mgic_field **out) {
+  mgic_field *f = new mgic_field;
+  f->ctx = c;
+  f->nx = nx; f->ny = ny; f->nz = nz;
+  f->sy = nx; f->sz = (long long)nx * ny;
+  f->k0 = k0; f->gnz = gnz;
+  f->bytes = (size_t)f->sz * (nz + 2 * MGIC_GZ) * sizeof(double);
+  cudaError_t e = cudaMalloc(&f->base, f->bytes);
+  if (e != cudaSuccess) {
+    mgic_set_error("cudaMalloc(%zu bytes) failed: %s", f->bytes, cudaGetErrorString(e));
+    delete f;
+    return MGIC_ERR_CUDA;
+  }
+  MGIC_CUDA(cudaMemsetAsync(f->base, 0, f->bytes, c->stream));
+  f->p = f->base + (long long)MGIC_GZ * f->sz;
+  *out = f;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_op_create(mgic_ctx *c, const int n[3], int k0, int nz_local, double dx, double alpha, double beta,
+                              const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out) {
+  MGIC_REQUIRE(c && n && out && bc_lo && bc_hi, "NULL argument");
+  MGIC_REQUIRE(n[0] >= 1 && n[1] >= 1 && n[2] >= 1, "bad dims");
+  MGIC_REQUIRE(k0 >= 0 && nz_local >= 1 && k0 + nz_local <= n[2], "bad slab");
+  for (int d = 0; d < 3; d++) {
+    if (bc_lo[d] < 0 || bc_lo[d] > 2) { mgic_set_error("bogus bc flag low side %d", bc_lo[d]); return MGIC_ERR_ARG; }    // SetBCs.cpp:94
+    if (bc_hi[d] < 0 || bc_hi[d] > 2) { mgic_set_error("bogus bc flag high side %d", bc_hi[d]); return MGIC_ERR_ARG; }   // SetBCs.cpp:123
+    MGIC_REQUIRE((bc_lo[d] == MGIC_BC_PERIODIC) == (bc_hi[d] == MGIC_BC_PERIODIC), "periodic must be set on both sides");
+  }
+  MGIC_CUDA(cudaSetDevice(c->device));
+  mgic_op *o = new mgic_op;
+  o->ctx = c;
+  for (int d = 0; d < 3; d++) { o->n[d] = n[d]; o->bc_lo[d] = bc_lo[d]; o->bc_hi[d] = bc_hi[d]; }
+  o->k0 = k0; o->nzl = nz_local; o->dx = dx; o->alpha = alpha; o->beta = beta; o->bc_value = bc_value;
+  *out = o;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_op_destroy(mgic_op *o) {
+  if (!o) return MGIC_OK;
+  mgic_field_destroy(o->lambda);
+  mgic_field_destroy(o->scratch);
+  delete o;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_op_dims(const mgic_op *o, int n[3], int *k0, int *nzl, double *dx) {
+  MGIC_REQUIRE(o, "op is NULL");
+  if (n) for (int d = 0; d < 3; d++) n[d] = o->n[d];
+  if (k0) *k0 = o->k0;
+  if (nzl) *nzl = o->nzl;
+  if (dx) *dx = o->dx;
+  return MGIC_OK;
+}
+
+static bool same_shape(const mgic_op *o, const mgic_field *f) {
+  return f && f->nx == o->n[0] && f->ny == o->n[1] && f->nz == o->nzl && f->k0 == o->k0;
+}
+#define REQ_SHAPE(o, f) MGIC_REQUIRE(same_shape(o, f), "field " #f " does not live on this operator's level")
+
+extern "C" int mgic_op_set_coefs(mgic_op *o, mgic_field *a, mgic_field *b, double alpha, double beta) {
+  MGIC_REQUIRE(o && a, "NULL argument");
+  REQ_SHAPE(o, a);
+  if (b) REQ_SHAPE(o, b);
+  o->a = a; o->b = b; o->alpha = alpha; o->beta = beta;
+  o->lambdaDirty = true;  // VariableCoeffPoissonOperator.cpp:216-217
+  return MGIC_OK;
+}
+extern "C" int mgic_op_set_alpha_beta(mgic_op *o, double alpha, double beta) {
+  MGIC_REQUIRE(o, "op is NULL");
+  o->alpha = alpha; o->beta = beta;
+  o->lambdaDirty = true;  // :204-205
+  return MGIC_OK;
+}
+extern "C" int mgic_op_reset_lambda(mgic_op *o) {
+  MGIC_REQUIRE(o && o->a, "operator has no coefficients (setCoefs)");
+  if (!o->lambda) MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
+  if (!o->lambdaDirty) return MGIC_OK;
+  MGIC_TRY(mgk::compute_lambda(o->ctx, o->geom(), o->lambda->p, o->a->p, o->alpha, o->beta, o->dx));
+  o->lambdaDirty = false;
+  return MGIC_OK;
+}
+extern "C" int mgic_op_compute_lambda(mgic_op *o) {
+  MGIC_REQUIRE(o, "op is NULL");
+  o->lambdaDirty = true;
+  return mgic_op_reset_lambda(o);
+}
+extern "C" int mgic_op_get_lambda(mgic_op *o, mgic_field **l) {
+  MGIC_REQUIRE(o && l, "NULL argument");
+  MGIC_TRY(mgic_op_reset_lambda(o));
+  *l = o->lambda;
+  return MGIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fields
+extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
+  MGIC_REQUIRE(like && out, "NULL argument");
+  MGIC_CUDA(cudaSetDevice(like->ctx->device));
+  return field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out);
+}
+extern "C" int mgic_field_destroy(mgic_field *f) {
+  if (!f) return MGIC_OK;
+  cudaFree(f->base);
+  delete f;
+  return MGIC_OK;
+}
+extern "C" int mgic_field_upload(mgic_field *f, const double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  const size_t n = (size_t)f->sz * f->nz;
+  MGIC_CUDA(cudaMemcpyAsync(f->p, host + (size_t)f->k0 * f->sz, n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+  MGIC_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return MGIC_OK;
+}
+extern "C" int mgic_field_download(const mgic_field *f, double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  const size_t n = (size_t)f->sz * f->nz;
+  MGIC_CUDA(cudaMemcpyAsync(host + (size_t)f->k0 * f->sz, f->p, n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+  MGIC_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return MGIC_OK;
+}
+// asynchronous variants for pinned buffers (e2e timing: copies ordered on the context stream)
+extern "C" int mgic_field_upload_async(mgic_field *f, const double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  const size_t n = (size_t)f->sz * f->nz;
+  MGIC_CUDA(cudaMemcpyAsync(f->p, host + (size_t)f->k0 * f->sz, n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+  return MGIC_OK;
+}
+extern "C" int mgic_field_download_async(const mgic_field *f, double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  const size_t n = (size_t)f->sz * f->nz;
+  MGIC_CUDA(cudaMemcpyAsync(host + (size_t)f->k0 * f->sz, f->p, n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+  return MGIC_OK;
+}
+
+// FArrayBox <-> level array: copies fab ∩ region ∩ slab with cudaMemcpy3D (strided, no staging)
+static int fab_copy(const mgic_field *f, double *fab, const int flo[3], const int fhi[3], const int rlo[3], const int rhi[3],
+                    bool toDevice) {
+  int lo[3], hi[3];
+  const int dlo[3] = {0, 0, f->k0}, dhi[3] = {f->nx - 1, f->ny - 1, f->k0 + f->nz - 1};
+  for (int d = 0; d < 3; d++) {
+    lo[d] = std::max(std::max(flo[d], rlo[d]), dlo[d]);
+    hi[d] = std::min(std::min(fhi[d], rhi[d]), dhi[d]);
+    if (hi[d] < lo[d]) return MGIC_OK;
+  }
+  const size_t fnx = fhi[0] - flo[0] + 1, fny = fhi[1] - flo[1] + 1;
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  cudaPitchedPtr hp = make_cudaPitchedPtr(fab, fnx * sizeof(double), fnx, fny);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(f->p, (size_t)f->nx * sizeof(double), f->nx, f->ny);
+  cudaPos hpos = make_cudaPos((size_t)(lo[0] - flo[0]) * sizeof(double), lo[1] - flo[1], lo[2] - flo[2]);
+  cudaPos dpos = make_cudaPos((size_t)lo[0] * sizeof(double), lo[1], lo[2] - f->k0);
+  p.extent = make_cudaExtent((size_t)(hi[0] - lo[0] + 1) * sizeof(double), hi[1] - lo[1] + 1, hi[2] - lo[2] + 1);
+  if (toDevice) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+  else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+  MGIC_CUDA(cudaMemcpy3DAsync(&p, f->ctx->stream));
+  return MGIC_OK;
+}
+extern "C" int mgic_field_upload_fab(mgic_field *f, const double *fab, const int flo[3], const int fhi[3], const int rlo[3],
+                                     const int rhi[3]) {
+  MGIC_REQUIRE(f && fab && flo && fhi && rlo && rhi, "NULL argument");
+  return fab_copy(f, const_cast<double *>(fab), flo, fhi, rlo, rhi, true);
+}
+extern "C" int mgic_field_download_fab(const mgic_field *f, double *fab, const int flo[3], const int fhi[3], const int rlo[3],
+                                       const int rhi[3]) {
+  MGIC_REQUIRE(f && fab && flo && fhi && rlo && rhi, "NULL argument");
+  return fab_copy(f, fab, flo, fhi, rlo, rhi, false);
+}
+extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy, long long *sz) {
+  MGIC_REQUIRE(f && ptr, "NULL argument");
+  *ptr = f->p;
+  if (sy) *sy = f->sy;
+  if (sz) *sz = f->sz;
+  return MGIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ op methods
+static int halo(mgic_op *o, mgic_field *f, int planes) {
+  if (o->ctx->nranks > 1) {
+    MGIC_REQUIRE(o->ctx->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
+    return o->ctx->halo_exchange(o->ctx, f, planes);
+  }
+  return MGIC_OK;
+}
+static inline const double *bptr(const mgic_op *o) { return o->b ? o->b->p : nullptr; }
+
+// one colour pass of levelGSRB (VariableCoeffPoissonOperator.cpp:290-331): exchange, BC (folded in), kernel
+extern "C" int mgic_op_gsrb_color(mgic_op *o, mgic_field *e, const mgic_field *r, int whichPass) {
+  MGIC_REQUIRE(o && e && r, "NULL argument");
+  REQ_SHAPE(o, e); REQ_SHAPE(o, r);
+  MGIC_TRY(mgic_op_reset_lambda(o));  // :283
+  MGIC_TRY(halo(o, e, 1));            // :301
+  ProfScope ps(o->ctx, o->profTag);
+  return mgk::gsrb_color(o->ctx, o->geom(), o->bck(true), e->p, r->p, o->a->p, bptr(o), o->lambda->p, o->alpha, o->beta, o->dx,
+                         whichPass);
+}
+
+// relax -> levelGSRB x iterations ([Chombo] AMRPoissonOp::relax, s_relaxMode == 1)
+extern "C" int mgic_op_relax(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations) {
+  MGIC_REQUIRE(o && e && r, "NULL argument");
+  REQ_SHAPE(o, e); REQ_SHAPE(o, r);
+  MGIC_TRY(mgic_op_reset_lambda(o));
+  if (o->smoother == 1 && o->ctx->nranks == 1) return mgk::gsrb_fused(o, e, r, iterations);
+  for (int it = 0; it < iterations; it++)
+    for (int pass = 0; pass <= 1; pass++) MGIC_TRY(mgic_op_gsrb_color(o, e, r, pass));
+  return MGIC_OK;
+}
+
+extern "C" int mgic_op_residual(mgic_op *o, mgic_field *lhs, mgic_field *phi, const mgic_field *rhs, int homogeneous) {
+  MGIC_REQUIRE(o && lhs && phi && rhs && o->a, "NULL argument");
+  REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
+  MGIC_TRY(halo(o, phi, 1));  // :48
+  return mgk::residual(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, rhs->p, o->a->p, bptr(o), o->alpha, o->beta,
+                       o->dx);
+}
+extern "C" int mgic_op_apply(mgic_op *o, mgic_field *lhs, mgic_field *phi, int homogeneous) {
+  MGIC_REQUIRE(o && lhs && phi && o->a, "NULL argument");
+  REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi);
+  MGIC_TRY(halo(o, phi, 1));  // :131
+  return mgk::apply_op(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, o->a->p, bptr(o), o->alpha, o->beta, o->dx);
+}
+// applyOpNoBoundary (:123-149): the stencil on whatever the ghost cells hold.  With ghosts folded into the
+// kernels the only ghost state a caller can have produced through this API is the last BC fill, which for
+// every call site in the reference's solver stack is the homogeneous one.
+extern "C" int mgic_op_apply_no_boundary(mgic_op *o, mgic_field *lhs, mgic_field *phi) { return mgic_op_apply(o, lhs, phi, 1); }
+
+extern "C" int mgic_op_level_jacobi(mgic_op *o, mgic_field *e, const mgic_field *r) {
+  MGIC_REQUIRE(o && e && r, "NULL argument");
+  REQ_SHAPE(o, e); REQ_SHAPE(o, r);
+  MGIC_TRY(mgic_op_reset_lambda(o));                                       // :367
+  if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
+  MGIC_TRY(mgic_op_residual(o, o->scratch, e, r, 1));                      // :373
+  MGIC_TRY(mgk::jacobi_update(o->ctx, o->geom(), e->p, o->scratch->p, o->lambda->p, 0.5));  // :376-381
+  return halo(o, e, 1);                                                    // :384
+}
+
+extern "C" int mgic_op_restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, const mgic_field *rhs) {
+  MGIC_REQUIRE(o && resC && phi && rhs && o->a, "NULL argument");
+  REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
+  MGIC_REQUIRE(o->n[0] % 2 == 0 && o->n[1] % 2 == 0 && o->nzl % 2 == 0 && o->k0 % 2 == 0, "level is not coarsenable by 2");
+  MGIC_REQUIRE(resC->nx == o->n[0] / 2 && resC->ny == o->n[1] / 2 && resC->nz == o->nzl / 2, "coarse residual has the wrong shape");
+  MGIC_TRY(halo(o, phi, 1));  // :163
+  return mgk::restrict_res(o->ctx, o->geom(), o->bck(true), resC->p, resC->sy, resC->sz, phi->p, rhs->p, o->a->p, bptr(o),
+                           o->alpha, o->beta, o->dx);
+}
+extern "C" int mgic_op_prolong_increment(mgic_op *o, mgic_field *phi, const mgic_field *coarse) {
+  MGIC_REQUIRE(o && phi && coarse, "NULL argument");
+  REQ_SHAPE(o, phi);
+  MGIC_REQUIRE(coarse->nx == o->n[0] / 2 && coarse->ny == o->n[1] / 2 && coarse->nz == o->nzl / 2 && o->n[0] % 2 == 0,
+               "coarse correction has the wrong shape");
+  return mgk::prolong(o->ctx, o->geom(), phi->p, coarse->p, coarse->sy, coarse->sz);
+}
+// preCond (:72-104): phi = rhs * lambda, then relax(phi, rhs, 2)
+extern "C" int mgic_op_precond(mgic_op *o, mgic_field *phi, const mgic_field *rhs) {
+  MGIC_REQUIRE(o && phi && rhs, "NULL argument");
+  REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
+  MGIC_TRY(mgic_op_reset_lambda(o));
+  MGIC_TRY(mgk::mult(o->ctx, o->geom(), phi->p, rhs->p, o->lambda->p));
+  return mgic_op_relax(o, phi, rhs, 2);
+}
+
+// BLAS-1 [Chombo AMRPoissonOp]
+static int local_reduce(mgic_op *o, const mgic_field *x, const mgic_field *y, int kind, double *out) {
+  MGIC_TRY(mgk::reduce(o->ctx, o->geom(), x->p, y ? y->p : nullptr, kind, 0));
+  return fetch_scalars(o->ctx, 0, 1, kind == 0 ? 1 : 0, out);
+}
+extern "C" int mgic_op_norm(mgic_op *o, const mgic_field *x, int ord, double *out) {
+  MGIC_REQUIRE(o && x && out, "NULL argument");
+  REQ_SHAPE(o, x);
+  MGIC_REQUIRE(ord >= 0 && ord <= 2, "norm order must be 0, 1 or 2");
+  double v;
+  MGIC_TRY(local_reduce(o, x, nullptr, ord, &v));
+  *out = (ord == 2) ? sqrt(v) : v;
+  return MGIC_OK;
+}
+extern "C" int mgic_op_dot(mgic_op *o, const mgic_field *x, const mgic_field *y, double *out) {
+  MGIC_REQUIRE(o && x && y && out, "NULL argument");
+  REQ_SHAPE(o, x); REQ_SHAPE(o, y);
+  return local_reduce(o, x, y, 3, out);
+}
+extern "C" int mgic_op_incr(mgic_op *o, mgic_field *y, const mgic_field *x, double s) {
+  MGIC_REQUIRE(o && x && y, "NULL argument");
+  REQ_SHAPE(o, x); REQ_SHAPE(o, y);
+  return mgk::incr(o->ctx, o->geom(), y->p, x->p, s);
+}
+extern "C" int mgic_op_axby(mgic_op *o, mgic_field *y, const mgic_field *x1, const mgic_field *x2, double a, double b) {
+  MGIC_REQUIRE(o && x1 && x2 && y, "NULL argument");
+  REQ_SHAPE(o, x1); REQ_SHAPE(o, x2); REQ_SHAPE(o, y);
+  return mgk::axby(o->ctx, o->geom(), y->p, x1->p, x2->p, a, b);
+}
+extern "C" int mgic_op_scale(mgic_op *o, mgic_field *y, double s) {
+  MGIC_REQUIRE(o && y, "NULL argument");
+  REQ_SHAPE(o, y);
+  return mgk::scale(o->ctx, o->geom(), y->p, s);
+}
+extern "C" int mgic_op_assign(mgic_op *o, mgic_field *y, const mgic_field *x) {
+  MGIC_REQUIRE(o && x && y, "NULL argument");
+  REQ_SHAPE(o, x); REQ_SHAPE(o, y);
+  return mgk::assign(o->ctx, o->geom(), y->p, x->p);
+}
+extern "C" int mgic_op_set_to_zero(mgic_op *o, mgic_field *y) { return mgic_op_set_val(o, y, 0.0); }
+extern "C" int mgic_op_set_val(mgic_op *o, mgic_field *y, double v) {
+  MGIC_REQUIRE(o && y, "NULL argument");
+  REQ_SHAPE(o, y);
+  return mgk::set_val(o->ctx, o->geom(), y->p, v);
+}
+extern "C" int mgic_op_set_smoother(mgic_op *o, int kind) {
+  MGIC_REQUIRE(o && (kind == 0 || kind == 1), "smoother kind must be 0 or 1");
+  o->smoother = kind;
+  return MGIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BiCGStab
+// [Chombo 3.2] BiCGStabSolver<T>::solve on device-resident vectors.  `Lin` supplies
+// residual / applyOp / preCond; vector ops go to the level operator.
+struct BiCGParams {
+  int imax = 80;
+  double eps = 1.0e-6, reps = 1.0e-12, hang = 1.0e-8, small = 1.0e-30;
+  int numRestarts = 5, normType = 2;
+  bool homogeneous = false;
+};
+
+struct LinOp {
+  mgic_op *op;
+  virtual int preCond(mgic_field *cor, mgic_field *res) = 0;
+  virtual ~LinOp() {}
+};
+
+struct BiCGWork {
+  mgic_field *v[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int alloc(mgic_op *op) {
+    for (auto &f : v) if (!f) MGIC_TRY(mgic_field_create(op, &f));
+    return MGIC_OK;
+  }
+  void release() {
+    for (auto &f : v) { mgic_field_destroy(f); f = nullptr; }
+  }
+};
+
+static int bicgstab(LinOp &L, BiCGWork &W, mgic_field *phi, const mgic_field *rhs, const BiCGParams &P, int *iterations,
+                    int *exitStatus, double *hist, int maxHist) {
+  mgic_op *op = L.op;
+  MGIC_TRY(W.alloc(op));
+  mgic_field *r = W.v[0], *rt = W.v[1], *e = W.v[2], *p = W.v[3], *pt = W.v[4], *st = W.v[5], *t = W.v[6], *v = W.v[7];
+  int nh = 0;
+  auto push = [&](double x) { if (hist && nh < maxHist) hist[nh] = x; nh++; };
+  int recount = 0;
+  MGIC_TRY(mgic_op_residual(op, r, phi, rhs, P.homogeneous));
+  MGIC_TRY(mgic_op_assign(op, rt, r));
+  MGIC_TRY(mgic_op_set_to_zero(op, e));
+  MGIC_TRY(mgic_op_set_to_zero(op, pt));
+  MGIC_TRY(mgic_op_set_to_zero(op, st));
+  int i = 0;
+  double rho[4] = {0, 0, 0, 0}, norm[2];
+  MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+  const double initial_norm = norm[0], initial_rnorm = norm[0];
+  norm[1] = norm[0];
+  double alpha[2] = {0, 0}, beta[2] = {0, 0}, omega[2] = {0, 0};
+  bool init = true;
+  int restarts = 0, status = -1;
+  push(norm[0]);
+  while ((i < P.imax && norm[0] > P.eps * norm[1]) && (norm[1] > 0)) {
+    i++;
+    norm[1] = norm[0]; alpha[1] = alpha[0]; beta[1] = beta[0]; omega[1] = omega[0];
+    rho[3] = rho[2]; rho[2] = rho[1];
+    MGIC_TRY(mgic_op_dot(op, rt, r, &rho[1]));
+    if (rho[1] == 0.0) {  // we are finished, we will not converge anymore
+      MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+      status = 2;
+      if (iterations) *iterations = i;
+      if (exitStatus) *exitStatus = status;
+      return MGIC_OK;
+    }
+    if (init) {
+      MGIC_TRY(mgic_op_assign(op, p, r));
+      init = false;
+    } else {
+      beta[1] = (rho[1] / rho[2]) * (alpha[1] / omega[1]);
+      MGIC_TRY(mgic_op_scale(op, p, beta[1]));
+      MGIC_TRY(mgic_op_incr(op, p, v, -beta[1] * omega[1]));
+      MGIC_TRY(mgic_op_incr(op, p, r, 1.0));
+    }
+    MGIC_TRY(L.preCond(pt, p));
+    MGIC_TRY(mgic_op_apply(op, v, pt, 1));
+    double m;
+    MGIC_TRY(mgic_op_dot(op, rt, v, &m));
+    alpha[0] = rho[1] / m;
+    if (fabs(m) > P.small * fabs(rho[1])) {
+      MGIC_TRY(mgic_op_incr(op, r, v, -alpha[0]));
+      MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+      MGIC_TRY(mgic_op_incr(op, e, pt, alpha[0]));
+    } else {
+      MGIC_TRY(mgic_op_set_to_zero(op, r));
+      norm[0] = 0.0;
+    }
+    if (norm[0] > P.eps * initial_norm && norm[0] > P.reps * initial_rnorm) {
+      MGIC_TRY(L.preCond(st, r));
+      MGIC_TRY(mgic_op_apply(op, t, st, 1));
+      double tr, tt;
+      MGIC_TRY(mgic_op_dot(op, t, r, &tr));
+      MGIC_TRY(mgic_op_dot(op, t, t, &tt));
+      omega[0] = tr / tt;
+      MGIC_TRY(mgic_op_incr(op, e, st, omega[0]));
+      MGIC_TRY(mgic_op_incr(op, r, t, -omega[0]));
+      MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+    }
+    push(norm[0]);
+    if (norm[0] <= P.eps * initial_norm || norm[0] <= P.reps * initial_rnorm) {
+      status = 1;
+      break;
+    }
+    if (omega[0] == 0.0 || norm[0] > (1 - P.hang) * norm[1]) {
+      if (recount == 0) recount = 1;
+      else {
+        recount = 0;
+        MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+        if (restarts == P.numRestarts) {
+          status = 3;
+          if (iterations) *iterations = i;
+          if (exitStatus) *exitStatus = status;
+          return MGIC_OK;
+        }
+        MGIC_TRY(mgic_op_residual(op, r, phi, rhs, P.homogeneous));
+        MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+        rho[1] = 0.0; rho[2] = 0.0; rho[3] = 0.0;
+        alpha[0] = 0; beta[0] = 0; omega[0] = 0;
+        MGIC_TRY(mgic_op_assign(op, rt, r));
+        MGIC_TRY(mgic_op_set_to_zero(op, e));
+        restarts++;
+        init = true;
+      }
+    }
+  }
+  MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+  if (iterations) *iterations = i;
+  if (exitStatus) *exitStatus = status;
+  return MGIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ factory / MG
+struct mgic_mg {
+  mgic_ctx *ctx = nullptr;
+  mgic_params P;
+  int nd = 0;
+  std::vector<mgic_op *> ops;
+  std::vector<mgic_field *> e, r;        // MultiGrid m_correction / m_residual; [0] unused (caller's vectors)
+  std::vector<mgic_field *> aOwn, bOwn;  // CoarseAverage'd coefficients of depth > 0
+  mgic_field *a0 = nullptr, *b0 = nullptr;
+  bool bIsOne = false;
+  int lastBottomIters = 0;
+  BiCGWork bottomWork, outerWork;
+  mgic_field *pc_e = nullptr;  // unused placeholder for future graph capture
+};
+
+static int mg_coarsen_coefs(mgic_mg *mg) {
+  const int type = mg->P.coefficient_average_type >= 0 ? mg->P.coefficient_average_type : MGIC_AVG_ARITHMETIC;  // Factory.cpp:44-46,321
+  if (type != MGIC_AVG_ARITHMETIC && type != MGIC_AVG_HARMONIC) {
+    mgic_set_error("MGNewOp -- bad averagetype");  // Factory.cpp:222-224
+    return MGIC_ERR_ARG;
+  }
+  for (int d = 1; d < mg->nd; d++) {
+    const int coarsening = 1 << d;
+    mgic_op *o = mg->ops[d];
+    // directly from the AMR-level coefficients, not recursively (Factory.cpp:208-220)
+    MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->aOwn[d]->p, mg->a0->p, mg->a0->sy, mg->a0->sz, coarsening, type));
+    if (!mg->bIsOne)
+      MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->bOwn[d]->p, mg->b0->p, mg->b0->sy, mg->b0->sz, coarsening, type));
+    MGIC_TRY(mgic_op_compute_lambda(o));  // :229
+  }
+  MGIC_TRY(mgic_op_compute_lambda(mg->ops[0]));
+  return MGIC_OK;
+}
+
+extern "C" int mgic_mg_create(mgic_ctx *c, const mgic_params *P, mgic_field *a0, mgic_field *b0, mgic_mg **out) {
+  return mgic_mg_create_ex(c, P, a0, b0, 0, out);
+}
+extern "C" int mgic_mg_create_ex(mgic_ctx *c, const mgic_params *P, mgic_field *a0, mgic_field *b0, int flags, mgic_mg **out) {
+  MGIC_REQUIRE(c && P && a0 && out, "NULL argument");
+  MGIC_REQUIRE(P->max_level == 0, "single AMR level only (max_level = 0)");
+  MGIC_REQUIRE(P->max_grid_size >= 1, "max_grid_size must be positive");
+  for (int d = 0; d < 3; d++) MGIC_REQUIRE(P->N[d] % P->max_grid_size == 0, "N must be a multiple of max_grid_size (domainSplit lattice)");
+  MGIC_REQUIRE(a0->nx == P->N[0] && a0->ny == P->N[1] && a0->gnz == P->N[2], "aCoef does not match params.N");
+  mgic_mg *mg = new mgic_mg;
+  mg->ctx = c;
+  mg->P = *P;
+  mg->a0 = a0;
+  mg->b0 = b0;
+  const int s_maxCoarse = 2;  // [Chombo] AMRPoissonOp::s_maxCoarse
+  const double dx0 = P->L / P->N[0];  // PoissonParameters.cpp:82
+  int bclo[3], bchi[3];
+  for (int d = 0; d < 3; d++) {
+    bclo[d] = P->is_periodic ? MGIC_BC_PERIODIC : P->bc_lo[d];
+    bchi[d] = P->is_periodic ? MGIC_BC_PERIODIC : P->bc_hi[d];
+  }
+  // bCoef == 1 everywhere (set_b_coef, SetLevelData.cpp:330-340): b*x == x exactly, and every average of ones
+  // is exactly one, so the b stream can be dropped from all kernels without changing a bit of the result.
+  if (!b0) mg->bIsOne = true;
+  else if (b0->nx != a0->nx || b0->ny != a0->ny || b0->nz != a0->nz) { mgic_set_error("bCoef does not match aCoef"); return MGIC_ERR_ARG; }
+  else {
+    mgic_op probe;
+    probe.ctx = c; probe.n[0] = b0->nx; probe.n[1] = b0->ny; probe.n[2] = b0->gnz; probe.k0 = b0->k0; probe.nzl = b0->nz;
+    MGIC_TRY(mgk::is_constant(c, probe.geom(), b0->p, 1.0, 1));
+    double cnt;
+    MGIC_TRY(fetch_scalars(c, 1, 1, 0, &cnt));
+    mg->bIsOne = (cnt == 0.0) && !(flags & MGIC_MG_KEEP_B);
+  }
+  for (int depth = 0;; depth++) {
+    if (P->preCondSolverDepth >= 0 && depth > P->preCondSolverDepth) break;  // [Chombo] MultiGrid m_maxDepth
+    const int coarsening = 1 << depth;
+    // Factory.cpp:168-172: boxes (the max_grid_size lattice) must be coarsenable by coarsening * s_maxCoarse
+    if (coarsening > 1 && (P->max_grid_size % (coarsening * s_maxCoarse)) != 0) break;
+    int n[3] = {P->N[0] / coarsening, P->N[1] / coarsening, P->N[2] / coarsening};
+    if (a0->k0 % coarsening != 0 || a0->nz % coarsening != 0) {
+      mgic_set_error("z-slab [%d,%d) is not coarsenable by %d: choose slabs that are multiples of max_grid_size", a0->k0,
+                     a0->k0 + a0->nz, coarsening);
+      return MGIC_ERR_ARG;
+    }
+    mgic_op *o = nullptr;
+    MGIC_TRY(mgic_op_create(c, n, a0->k0 / coarsening, a0->nz / coarsening, dx0 * coarsening, P->alpha, P->beta, bclo, bchi,
+                            P->bc_value, &o));
+    o->profTag = (depth == 0);
+    mg->ops.push_back(o);
+    mgic_field *ea = nullptr, *ra = nullptr, *aa = nullptr, *ba = nullptr;
+    if (depth > 0) {
+      MGIC_TRY(mgic_field_create(o, &ea));
+      MGIC_TRY(mgic_field_create(o, &ra));
+      MGIC_TRY(mgic_field_create(o, &aa));
+      if (!mg->bIsOne) MGIC_TRY(mgic_field_create(o, &ba));
+      MGIC_TRY(mgic_op_set_coefs(o, aa, mg->bIsOne ? nullptr : ba, P->alpha, P->beta));
+    } else {
+      MGIC_TRY(mgic_op_set_coefs(o, a0, mg->bIsOne ? nullptr : b0, P->alpha, P->beta));  // :194-197
+    }
+    mg->e.push_back(ea); mg->r.push_back(ra); mg->aOwn.push_back(aa); mg->bOwn.push_back(ba);
+  }
+  mg->nd = (int)mg->ops.size();
+  MGIC_TRY(mg_coarsen_coefs(mg));
+  *out = mg;
+  return MGIC_OK;
+}
+
+extern "C" int mgic_mg_destroy(mgic_mg *mg) {
+  if (!mg) return MGIC_OK;
+  cudaStreamSynchronize(mg->ctx->stream);
+  mg->bottomWork.release();
+  mg->outerWork.release();
+  for (int d = 0; d < mg->nd; d++) {
+    mgic_field_destroy(mg->e[d]); mgic_field_destroy(mg->r[d]);
+    mgic_field_destroy(mg->aOwn[d]); mgic_field_destroy(mg->bOwn[d]);
+    mgic_op_destroy(mg->ops[d]);
+  }
+  delete mg;
+  return MGIC_OK;
+}
+extern "C" int mgic_mg_depths(const mgic_mg *mg) { return mg ? mg->nd : 0; }
+extern "C" int mgic_mg_op(mgic_mg *mg, int depth, mgic_op **op) {
+  MGIC_REQUIRE(mg && op, "NULL argument");
+  *op = (depth >= 0 && depth < mg->nd) ? mg->ops[depth] : nullptr;  // MGnewOp returns NULL past the limit
+  return MGIC_OK;
+}
+extern "C" int mgic_mg_scratch(mgic_mg *mg, int depth, mgic_field **e, mgic_field **r) {
+  MGIC_REQUIRE(mg && depth >= 1 && depth < mg->nd, "depth out of range (scratch exists for depth >= 1)");
+  if (e) *e = mg->e[depth];
+  if (r) *r = mg->r[depth];
+  return MGIC_OK;
+}
+extern "C" int mgic_mg_refresh_coefs(mgic_mg *mg) {
+  MGIC_REQUIRE(mg, "mg is NULL");
+  return mg_coarsen_coefs(mg);
+}
+extern "C" int mgic_mg_set_smoother(mgic_mg *mg, int kind) {
+  MGIC_REQUIRE(mg, "mg is NULL");
+  for (auto *o : mg->ops) MGIC_TRY(mgic_op_set_smoother(o, kind));
+  return MGIC_OK;
+}
+extern "C" int mgic_mg_b_is_one(const mgic_mg *mg) { return mg && mg->bIsOne; }
+
+struct BottomLin : LinOp {
+  int preCond(mgic_field *cor, mgic_field *res) override { return mgic_op_precond(op, cor, res); }
+};
+
+extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field *r, int *iterations) {
+  MGIC_REQUIRE(mg && e && r, "NULL argument");
+  BottomLin L;
+  L.op = mg->ops.back();
+  BiCGParams bp;
+  bp.homogeneous = true;  // [Chombo] MultiGrid::define: m_bottomSolver->define(op, true)
+  int it = 0, st = 0;
+  MGIC_TRY(bicgstab(L, mg->bottomWork, e, r, bp, &it, &st, nullptr, 0));
+  mg->lastBottomIters = it;
+  if (iterations) *iterations = it;
+  return MGIC_OK;
+}
+extern "C" int mgic_mg_last_bottom_iterations(const mgic_mg *mg) { return mg ? mg->lastBottomIters : 0; }
+
+// [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
+static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r) {
+  mgic_op *op = mg->ops[depth];
+  const int S = mg->P.numMGsmooth;
+  if (depth == mg->nd - 1) {
+    const long long cells = (long long)op->n[0] * op->n[1] * op->n[2];
+    if (cells == 1) return mgic_op_relax(op, e, r, 1);
+    MGIC_TRY(mgic_op_relax(op, e, r, S));
+    return mgic_mg_bottom_solve(mg, e, r, nullptr);
+  }
+  MGIC_TRY(mgic_op_relax(op, e, r, S));
+  MGIC_TRY(mgic_op_restrict_residual(op, mg->r[depth + 1], e, r));
+  MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
+  MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1]));
+  MGIC_TRY(mgic_op_prolong_increment(op, e, mg->e[depth + 1]));
+  return mgic_op_relax(op, e, r, S);
+}
+
+extern "C" int mgic_mg_vcycle(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
+  MGIC_REQUIRE(mg && e && r, "NULL argument");
+  REQ_SHAPE(mg->ops[0], e); REQ_SHAPE(mg->ops[0], r);
+  mg->lastBottomIters = 0;
+  return mg_cycle(mg, 0, e, r);
+}
+
+// f1: [Chombo] MultilevelLinearOp::preCond on one AMR level = zero cor, numMGIterations V-cycles
+struct OuterLin : LinOp {
+  mgic_mg *mg;
+  int preCond(mgic_field *cor, mgic_field *res) override {
+    MGIC_TRY(mgic_op_set_to_zero(op, cor));
+    for (int it = 0; it < mg->P.numMGIterations; it++) MGIC_TRY(mg_cycle(mg, 0, cor, res));
+    return MGIC_OK;
+  }
+};
+
+extern "C" int mgic_mg_outer_solve(mgic_mg *mg, mgic_field *dpsi, const mgic_field *rhs, int *iterations, int *exit_status,
+                                   double *norms, int max_norms) {
+  MGIC_REQUIRE(mg && dpsi && rhs, "NULL argument");
+  OuterLin L;
+  L.op = mg->ops[0];
+  L.mg = mg;
+  BiCGParams bp;
+  bp.homogeneous = false;         // Main_PoissonSolver.cpp:172-173
+  bp.normType = 0;                // :176
+  bp.eps = mg->P.tolerance;       // :177
+  bp.imax = mg->P.max_iterations; // :178
+  return bicgstab(L, mg->outerWork, dpsi, rhs, bp, iterations, exit_status, norms, max_norms);
+}
+
+// ------------------------------------------------------------------------------------------------ source terms
+extern "C" int mgic_vars_create(mgic_ctx *c, const mgic_params *P, int k0, int nzl, mgic_vars **out) {
+  MGIC_REQUIRE(c && P && out, "NULL argument");
+  MGIC_REQUIRE(k0 >= 0 && nzl >= 1 && k0 + nzl <= P->N[2], "bad slab");
+  MGIC_CUDA(cudaSetDevice(c->device));
+  mgic_vars *v = new mgic_vars;
+  v->ctx = c; v->P = *P;
+  for (int d = 0; d < 3; d++) v->n[d] = P->N[d];
+  v->k0 = k0; v->nzl = nzl; v->dx = P->L / P->N[0];
+  v->sy = P->N[0] + 2; v->sz = v->sy * (P->N[1] + 2); v->sc = v->sz * (nzl + 2);
+  MGIC_CUDA(cudaMalloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
+  MGIC_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->sc * 8 * sizeof(double), c->stream));
+  *out = v;
+  return MGIC_OK;
+}
+extern "C" int mgic_vars_destroy(mgic_vars *v) {
+  if (!v) return MGIC_OK;
+  cudaFree(v->d);
+  delete v;
+  return MGIC_OK;
+}
+static int vars_copy(const mgic_vars *v, int comp, double *host, int ghost) {
+  MGIC_REQUIRE(v && host && comp >= 0 && comp < 8, "bad argument");
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  const size_t hx = v->n[0] + 2 * ghost, hy = v->n[1] + 2 * ghost;
+  p.srcPtr = make_cudaPitchedPtr(v->d + (size_t)comp * v->sc, (size_t)v->sy * sizeof(double), v->sy, v->n[1] + 2);
+  p.srcPos = make_cudaPos((size_t)(1 - ghost) * sizeof(double), 1 - ghost, 1 - ghost);
+  p.dstPtr = make_cudaPitchedPtr(host, hx * sizeof(double), hx, hy);
+  p.dstPos = make_cudaPos(0, 0, ghost ? 0 : v->k0);
+  p.extent = make_cudaExtent(hx * sizeof(double), hy, v->nzl + 2 * ghost);
+  p.kind = cudaMemcpyDeviceToHost;
+  MGIC_CUDA(cudaMemcpy3DAsync(&p, v->ctx->stream));
+  MGIC_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return MGIC_OK;
+}
+extern "C" int mgic_vars_download(const mgic_vars *v, int comp, double *host) { return vars_copy(v, comp, host, 0); }
+extern "C" int mgic_vars_download_ghosted(const mgic_vars *v, int comp, double *host) { return vars_copy(v, comp, host, 1); }
+
+extern "C" int mgic_set_initial_conditions(mgic_vars *v, mgic_field *dpsi) {
+  MGIC_REQUIRE(v, "vars is NULL");
+  MGIC_TRY(mgk::init_conditions(v));
+  if (dpsi) MGIC_CUDA(cudaMemsetAsync(dpsi->base, 0, dpsi->bytes, v->ctx->stream));  // dpsi = 0 (SetLevelData.cpp:55)
+  return MGIC_OK;
+}
+static bool vars_match(const mgic_vars *v, const mgic_field *f) {
+  return f && f->nx == v->n[0] && f->ny == v->n[1] && f->nz == v->nzl && f->k0 == v->k0;
+}
+extern "C" int mgic_set_a_coef(mgic_vars *v, mgic_field *aCoef, double constant_K) {
+  MGIC_REQUIRE(v && vars_match(v, aCoef), "aCoef does not match multigrid_vars");
+  return mgk::set_rhs_acoef(v, nullptr, aCoef->p, constant_K);
+}
+extern "C" int mgic_set_rhs(mgic_vars *v, mgic_field *rhs, double constant_K) {
+  MGIC_REQUIRE(v && vars_match(v, rhs), "rhs does not match multigrid_vars");
+  return mgk::set_rhs_acoef(v, rhs->p, nullptr, constant_K);
+}
+extern "C" int mgic_set_rhs_and_a_coef(mgic_vars *v, mgic_field *rhs, mgic_field *aCoef, double constant_K) {
+  MGIC_REQUIRE(v && vars_match(v, rhs) && vars_match(v, aCoef), "fields do not match multigrid_vars");
+  return mgk::set_rhs_acoef(v, rhs->p, aCoef->p, constant_K);
+}
+extern "C" int mgic_set_b_coef(mgic_vars *v, mgic_field *bCoef) {
+  MGIC_REQUIRE(v && vars_match(v, bCoef), "bCoef does not match multigrid_vars");
+  Geom g; g.nx = bCoef->nx; g.ny = bCoef->ny; g.nz = bCoef->nz; g.sy = bCoef->sy; g.sz = bCoef->sz; g.k0 = bCoef->k0; g.gnz = bCoef->gnz;
+  return mgk::set_val(v->ctx, g, bCoef->p, 1.0);  // SetLevelData.cpp:338
+}
+
+// set_update_psi0 (SetLevelData.cpp:243-263) + computeNorm(dpsi, p = 2) (Main_PoissonSolver.cpp:208)
+extern "C" int mgic_update_psi0(mgic_vars *v, mgic_op *op0, mgic_field *dpsi, double *dpsi_norm) {
+  MGIC_REQUIRE(v && op0 && dpsi, "NULL argument");
+  REQ_SHAPE(op0, dpsi);
+  MGIC_REQUIRE(vars_match(v, dpsi), "dpsi does not match multigrid_vars");
+  MGIC_TRY(halo(op0, dpsi, 1));  // :249 (the reference exchanges three layers; one is read)
+  MGIC_TRY(mgk::update_psi(v, op0->geom(), op0->bck(true), dpsi->p));
+  if (dpsi_norm) {
+    double s;
+    MGIC_TRY(local_reduce(op0, dpsi, nullptr, 2, &s));
+    const double dV = op0->dx * op0->dx * op0->dx;
+    *dpsi_norm = sqrt(s * dV);  // [Chombo] computeNorm: (sum |x|^2 dx^3)^(1/2)
+  }
+  return MGIC_OK;
+}
+
+// The NL loop of Main_PoissonSolver.cpp:131-216 for one AMR level, device resident.
+extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_norms, int max_out, int *nl_iterations,
+                             double *psi_out) {
+  MGIC_REQUIRE(c && P, "NULL argument");
+  MGIC_REQUIRE(c->nranks == 1, "mgic_nl_solve drives a single GPU; multi-rank callers compose the pieces per rank");
+  mgic_vars *vars = nullptr;
+  mgic_op *lay = nullptr;
+  mgic_field *dpsi = nullptr, *rhs = nullptr, *aC = nullptr, *bC = nullptr;
+  int rc = MGIC_OK, its = 0;
+  int bclo[3], bchi[3];
+  for (int d = 0; d < 3; d++) {
+    bclo[d] = P->is_periodic ? MGIC_BC_PERIODIC : P->bc_lo[d];
+    bchi[d] = P->is_periodic ? MGIC_BC_PERIODIC : P->bc_hi[d];
+  }
+#define NL_TRY(x) do { rc = (x); if (rc != MGIC_OK) goto done; } while (0)
+  NL_TRY(mgic_vars_create(c, P, 0, P->N[2], &vars));
+  NL_TRY(mgic_op_create(c, P->N, 0, P->N[2], P->L / P->N[0], P->alpha, P->beta, bclo, bchi, P->bc_value, &lay));
+  NL_TRY(mgic_field_create(lay, &dpsi));
+  NL_TRY(mgic_field_create(lay, &rhs));
+  NL_TRY(mgic_field_create(lay, &aC));
+  NL_TRY(mgic_field_create(lay, &bC));
+  NL_TRY(mgic_set_initial_conditions(vars, dpsi));                       // Main:93
+  for (int NL_iter = 0; NL_iter < P->max_NL_iterations; NL_iter++) {     // :131
+    NL_TRY(mgic_set_rhs_and_a_coef(vars, rhs, aC, 0.0));                 // :154-160 (non-periodic: constant_K = 0)
+    NL_TRY(mgic_set_b_coef(vars, bC));
+    mgic_mg *mg = nullptr;
+    NL_TRY(mgic_mg_create(c, P, aC, bC, &mg));                           // :163-170 (rebuilt every NL iteration)
+    int it = 0, st = 0;
+    rc = mgic_mg_outer_solve(mg, dpsi, rhs, &it, &st, nullptr, 0);       // :184
+    double nrm = 0.0;
+    if (rc == MGIC_OK) rc = mgic_update_psi0(vars, mg->ops[0], dpsi, &nrm);  // :189-208
+    mgic_mg_destroy(mg);
+    if (rc != MGIC_OK) goto done;
+    if (dpsi_norms && NL_iter < max_out) dpsi_norms[NL_iter] = nrm;
+    its = NL_iter + 1;
+    if (nrm < P->tolerance || nrm > 1e5) break;                          // :212
+  }
+  if (psi_out) NL_TRY(mgic_vars_download(vars, 0, psi_out));
+done:
+#undef NL_TRY
+  if (nl_iterations) *nl_iterations = its;
+  mgic_field_destroy(dpsi); mgic_field_destroy(rhs); mgic_field_destroy(aC); mgic_field_destroy(bC);
+  mgic_op_destroy(lay);
+  mgic_vars_destroy(vars);
+  return rc;
+}

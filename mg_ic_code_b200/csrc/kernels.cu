@@ -1,0 +1,382 @@
+// kernels.cu -- sm_100a CUDA kernels of the multigrid hot path (level-wide, device-resident fields).
+//
+// Every kernel keeps the operation order of the reference's Fortran and the file is
+// compiled with -fmad=false, so results are bit-identical to a non-contracting CPU evaluation.
+//
+// Data layout: one FP64 array per level field, x fastest, no ghost cells in x/y (rows stay 16/32-byte
+// aligned for vector loads), MGIC_GZ ghost planes below and above the rank's z-slab.  Physical boundary
+// ghosts are never stored: the value the reference's ParseBC (Source/SetBCs.cpp:49-131) would have written
+// into the ghost cell, ghost = a*near + b, is recomputed on the fly from the cell's own current value.
+#include <cooperative_groups.h>
+
+#include "mgic_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+// ---- launch bookkeeping ---------------------------------------------------------------------------------
+inline int post_launch(mgic_ctx *c, const char *what) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    mgic_set_error("kernel %s: %s", what, cudaGetErrorString(e));
+    return MGIC_ERR_CUDA;
+  }
+  return MGIC_OK;
+}
+
+// ---- stencil helpers --------------------------------------------------------------------------------------
+// The CHF_DTERM block common to the four operator kernels (VariableCoeffPoissonOperatorF.ChF:111-120,
+// 219-228, 322-330, 415-424): each bracket left to right, brackets added in x, y, z order.
+__device__ __forceinline__ double lap7(double c, double xm, double xp, double ym, double yp, double zm, double zp) {
+  const double t = 2.0 * c;
+  return ((xp + xm) - t) + ((yp + ym) - t) + ((zp + zm) - t);
+}
+
+// Neighbour values of cell (i,j,k) (local indices) with the physical BC folded in.
+struct Nb { double xm, xp, ym, yp, zm, zp; };
+
+__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *__restrict__ p, long long wrapIdx) {
+  // Dirichlet / Neumann: a*c + b  (DiriBC order 1: 2v - near;  NeumBC: near + sign*dx*v  [Chombo BCFunc])
+  return bc.type[f] == MGIC_BC_PERIODIC ? p[wrapIdx] : bc.a[f] * c + bc.b[f];
+}
+
+__device__ __forceinline__ Nb neighbours(const double *__restrict__ p, long long idx, int i, int j, int k, const Geom &g,
+                                         const BCk &bc, double c) {
+  Nb n;
+  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1));
+  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1));
+  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy);
+  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy);
+  // z: ghost planes exist in memory; MGIC_FACE_INTERIOR means they hold the neighbour slab's planes
+  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz);
+  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz);
+  return n;
+}
+
+// ---- GSRB colour pass: GSRBHELMHOLTZVC3D (VariableCoeffPoissonOperatorF.ChF:56-139) ------------------------
+// One thread per cell of the colour: i = 2t + parity so that (i + j + k_global + color) is even (:98-106).
+template <bool HAS_B>
+__global__ void __launch_bounds__(256) k_gsrb_color(Geom g, BCk bc, double *__restrict__ phi, const double *__restrict__ rhs,
+                                                    const double *__restrict__ a, const double *__restrict__ b,
+                                                    const double *__restrict__ lam, double alpha, double beta,
+                                                    double dxinv, int color) {
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.ny) return;
+  const int i = 2 * t + ((j + k + g.k0 + color) & 1);
+  if (i >= g.nx) return;
+  const long long idx = i + j * g.sy + k * g.sz;
+  const double c = phi[idx];
+  const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+  double lof = alpha * a[idx] * c;                       // :107-108
+  double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);  // :111-120
+  l = l * dxinv;                                         // :122  (ldpsi*dxinv)*bCoef
+  if (HAS_B) l = l * b[idx];
+  lof = lof - beta * l;                                  // :124
+  phi[idx] = c - lam[idx] * (lof - rhs[idx]);            // :127-128
+}
+
+// ---- applyOp / residual: VCCOMPUTEOP3D (:181-237), VCCOMPUTERES3D (:283-339) --------------------------------
+// MODE 0: lhs = alpha*a*phi - S*dxinv*beta*b ; MODE 1: lhs = (rhs - alpha*a*phi) + S*dxinv*beta*b
+template <int MODE, bool HAS_B>
+__global__ void __launch_bounds__(256) k_op(Geom g, BCk bc, double *__restrict__ lhs, const double *__restrict__ phi,
+                                            const double *__restrict__ rhs, const double *__restrict__ a,
+                                            const double *__restrict__ b, double alpha, double beta, double dxinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long idx = i + j * g.sy + k * g.sz;
+  const double c = phi[idx];
+  const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+  double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);
+  l = l * dxinv * beta;                                  // :227 / :331  ((ldpsi*dxinv)*beta)*bCoef
+  if (HAS_B) l = l * b[idx];
+  if (MODE == 0) {
+    lhs[idx] = alpha * a[idx] * c - l;                   // :211-212, :229
+  } else {
+    lhs[idx] = (rhs[idx] - alpha * a[idx] * c) + l;      // :314-316, :333
+  }
+}
+
+// ---- restrictResidual: RESTRICTRESVC3D (:379-437) ------------------------------------------------------------
+// One thread per coarse cell; the eight fine contributions are accumulated in the order the Fortran loop
+// nest delivers them to that coarse cell: (0,0,0),(1,0,0),(0,1,0),(1,1,0),(0,0,1),... starting from the
+// zero the caller stored (VariableCoeffPoissonOperator.cpp:177).
+template <bool HAS_B>
+__global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__restrict__ resC, long long csy, long long csz,
+                                                  const double *__restrict__ phi, const double *__restrict__ rhs,
+                                                  const double *__restrict__ a, const double *__restrict__ b, double alpha,
+                                                  double beta, double dxinv) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J = blockIdx.y * blockDim.y + threadIdx.y;
+  const int K = blockIdx.z;
+  if (2 * I >= g.nx || 2 * J >= g.ny) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+      for (int di = 0; di < 2; di++) {
+        const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+        const long long idx = i + j * g.sy + k * g.sz;
+        const double c = phi[idx];
+        const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+        double lof = alpha * a[idx] * c;                       // :411-412
+        double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);
+        l = l * dxinv * beta;                                  // :427
+        if (HAS_B) l = l * b[idx];
+        lof = lof - l;                                         // :429
+        acc = acc + (rhs[idx] - lof) / 8.0;                    // :431-432
+      }
+  resC[I + J * csy + K * csz] = acc;
+}
+
+// ---- prolongIncrement: [Chombo] AMRPoissonOpF.ChF PROLONG, m = 2 ---------------------------------------------
+__global__ void __launch_bounds__(128) k_prolong(Geom g, double *__restrict__ phi, const double *__restrict__ coarse,
+                                                 long long csy, long long csz) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J = blockIdx.y * blockDim.y + threadIdx.y;
+  const int K = blockIdx.z;
+  if (2 * I >= g.nx || 2 * J >= g.ny) return;
+  const double c = coarse[I + J * csy + K * csz];
+#pragma unroll
+  for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++) {
+      double2 *q = reinterpret_cast<double2 *>(phi + 2 * I + (2 * J + dj) * g.sy + (2 * K + dk) * g.sz);
+      double2 v = *q;
+      v.x = v.x + c;
+      v.y = v.y + c;
+      *q = v;
+    }
+}
+
+// ---- lambda: resetLambda (VariableCoeffPoissonOperator.cpp:220-249) ------------------------------------------
+__global__ void k_lambda(long long n, double *__restrict__ lam, const double *__restrict__ a, double alpha, double plus) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    double v = a[q];   // copy   :234
+    v = v * alpha;     // mult   :235
+    v = v + plus;      // plus   :241
+    lam[q] = 1.0 / v;  // invert :244
+  }
+}
+
+// ---- BLAS-1 over the contiguous valid cells of the slab ---------------------------------------------------
+enum { EW_MULT, EW_INCR, EW_AXBY, EW_SCALE, EW_ASSIGN, EW_SETVAL, EW_JACOBI };
+template <int OP>
+__global__ void k_ew(long long n, double *__restrict__ y, const double *__restrict__ x1, const double *__restrict__ x2,
+                     double s1, double s2) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    if (OP == EW_MULT) y[q] = x1[q] * x2[q];
+    else if (OP == EW_INCR) y[q] = y[q] + s1 * x1[q];
+    else if (OP == EW_AXBY) y[q] = s1 * x1[q] + s2 * x2[q];
+    else if (OP == EW_SCALE) y[q] = y[q] * s1;
+    else if (OP == EW_ASSIGN) y[q] = x1[q];
+    else if (OP == EW_SETVAL) y[q] = s1;
+    else if (OP == EW_JACOBI) y[q] = y[q] + s1 * (x2[q] * x1[q]);  // phi += 0.5 * (lambda * resid)  (levelJacobi :375-381)
+  }
+}
+
+// ---- reductions: warp shuffle -> block -> fixed-order final pass by the last block (deterministic) ----------
+// kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y, 4 count(x != s)
+template <int KIND>
+__device__ __forceinline__ double red_elem(double x, double y, double s) {
+  if (KIND == 0 || KIND == 1) return fabs(x);
+  if (KIND == 2) return x * x;
+  if (KIND == 3) return x * y;
+  return (x != s) ? 1.0 : 0.0;
+}
+template <int KIND>
+__device__ __forceinline__ double red_comb(double a, double b) { return KIND == 0 ? fmax(a, b) : a + b; }
+
+template <int KIND>
+__device__ __forceinline__ double block_reduce(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_comb<KIND>(v, __shfl_down_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = red_comb<KIND>(v, __shfl_down_sync(0xffffffffu, v, o));
+  }
+  return v;  // valid in thread 0
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_reduce(long long n, const double *__restrict__ x, const double *__restrict__ y, double s,
+                                                double *__restrict__ part, unsigned int *__restrict__ count,
+                                                double *__restrict__ out) {
+  __shared__ double sh[32];
+  __shared__ bool last;
+  double v = 0.0;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+    v = red_comb<KIND>(v, red_elem<KIND>(x[q], KIND == 3 ? y[q] : 0.0, s));
+  v = block_reduce<KIND>(v, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = v;
+    __threadfence();
+    last = (atomicAdd(count, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double w = 0.0;
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) w = red_comb<KIND>(w, part[q]);
+    __syncthreads();
+    w = block_reduce<KIND>(w, sh);
+    if (threadIdx.x == 0) {
+      *out = w;
+      *count = 0;
+    }
+  }
+}
+
+// ---- coefficient coarsening: [Chombo] CoarseAverage (AverageF.ChF AVERAGE / AVERAGEHARMONIC) -----------------
+// refScale = 1/nRef^3; fine cells summed ii fastest; arithmetic: sum*refScale; harmonic: 1/(sum(1/f)*refScale)
+__global__ void __launch_bounds__(128) k_coarse_average(Geom gc, double *__restrict__ c, const double *__restrict__ f,
+                                                        long long fsy, long long fsz, int nref, int harmonic) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J = blockIdx.y * blockDim.y + threadIdx.y;
+  const int K = blockIdx.z;
+  if (I >= gc.nx || J >= gc.ny) return;
+  const double refScale = 1.0 / (double)(nref * nref * nref);
+  double sum = 0.0;
+  for (int kk = 0; kk < nref; kk++)
+    for (int jj = 0; jj < nref; jj++)
+      for (int ii = 0; ii < nref; ii++) {
+        const double fv = f[(I * nref + ii) + (J * nref + jj) * fsy + (long long)(K * nref + kk) * fsz];
+        sum = sum + (harmonic ? 1.0 / fv : fv);
+      }
+  c[I + J * gc.sy + K * gc.sz] = harmonic ? 1.0 / (sum * refScale) : sum * refScale;
+}
+
+inline dim3 grid3(int nx, int ny, int nz, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
+inline int ew_grid(mgic_ctx *c, long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)c->numSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+// ================================================================================================================
+namespace mgk {
+
+int gsrb_color(mgic_ctx *c, const Geom &g, const BCk &bc, double *phi, const double *rhs, const double *a, const double *b,
+               const double *lam, double alpha, double beta, double dx, int color) {
+  const double dxinv = 1.0 / (dx * dx);  // :89
+  dim3 blk(64, 4, 1);
+  dim3 grd = grid3((g.nx + 1) / 2, g.ny, g.nz, blk);
+  if (b)
+    k_gsrb_color<true><<<grd, blk, 0, c->stream>>>(g, bc, phi, rhs, a, b, lam, alpha, beta, dxinv, color);
+  else
+    k_gsrb_color<false><<<grd, blk, 0, c->stream>>>(g, bc, phi, rhs, a, b, lam, alpha, beta, dxinv, color);
+  return post_launch(c, "gsrb_color");
+}
+
+int apply_op(mgic_ctx *c, const Geom &g, const BCk &bc, double *lhs, const double *phi, const double *a, const double *b,
+             double alpha, double beta, double dx) {
+  const double dxinv = 1.0 / (dx * dx);
+  dim3 blk(64, 4, 1);
+  dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
+  if (b) k_op<0, true><<<grd, blk, 0, c->stream>>>(g, bc, lhs, phi, nullptr, a, b, alpha, beta, dxinv);
+  else k_op<0, false><<<grd, blk, 0, c->stream>>>(g, bc, lhs, phi, nullptr, a, b, alpha, beta, dxinv);
+  return post_launch(c, "apply_op");
+}
+
+int residual(mgic_ctx *c, const Geom &g, const BCk &bc, double *res, const double *phi, const double *rhs, const double *a,
+             const double *b, double alpha, double beta, double dx) {
+  const double dxinv = 1.0 / (dx * dx);
+  dim3 blk(64, 4, 1);
+  dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
+  if (b) k_op<1, true><<<grd, blk, 0, c->stream>>>(g, bc, res, phi, rhs, a, b, alpha, beta, dxinv);
+  else k_op<1, false><<<grd, blk, 0, c->stream>>>(g, bc, res, phi, rhs, a, b, alpha, beta, dxinv);
+  return post_launch(c, "residual");
+}
+
+int restrict_res(mgic_ctx *c, const Geom &g, const BCk &bc, double *resC, long long csy, long long csz, const double *phi,
+                 const double *rhs, const double *a, const double *b, double alpha, double beta, double dx) {
+  const double dxinv = 1.0 / (dx * dx);
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(g.nx / 2, g.ny / 2, g.nz / 2, blk);
+  if (b) k_restrict<true><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
+  else k_restrict<false><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
+  return post_launch(c, "restrict");
+}
+
+int prolong(mgic_ctx *c, const Geom &g, double *phi, const double *coarse, long long csy, long long csz) {
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(g.nx / 2, g.ny / 2, g.nz / 2, blk);
+  k_prolong<<<grd, blk, 0, c->stream>>>(g, phi, coarse, csy, csz);
+  return post_launch(c, "prolong");
+}
+
+static inline long long ncells(const Geom &g) { return (long long)g.nx * g.ny * g.nz; }
+
+int compute_lambda(mgic_ctx *c, const Geom &g, double *lam, const double *a, double alpha, double beta, double dx) {
+  const double plus = 2.0 * 3 * beta / (dx * dx);  // :241
+  const long long n = ncells(g);
+  k_lambda<<<ew_grid(c, n), 256, 0, c->stream>>>(n, lam, a, alpha, plus);
+  return post_launch(c, "lambda");
+}
+
+#define EW_LAUNCH(OP, y, x1, x2, s1, s2)                                              \
+  const long long n = ncells(g);                                                      \
+  k_ew<OP><<<ew_grid(c, n), 256, 0, c->stream>>>(n, y, x1, x2, s1, s2);                \
+  return post_launch(c, #OP)
+
+int mult(mgic_ctx *c, const Geom &g, double *y, const double *x, const double *l) { EW_LAUNCH(EW_MULT, y, x, l, 0.0, 0.0); }
+int incr(mgic_ctx *c, const Geom &g, double *y, const double *x, double s) { EW_LAUNCH(EW_INCR, y, x, nullptr, s, 0.0); }
+int axby(mgic_ctx *c, const Geom &g, double *y, const double *x1, const double *x2, double a, double b) {
+  EW_LAUNCH(EW_AXBY, y, x1, x2, a, b);
+}
+int scale(mgic_ctx *c, const Geom &g, double *y, double s) { EW_LAUNCH(EW_SCALE, y, nullptr, nullptr, s, 0.0); }
+int assign(mgic_ctx *c, const Geom &g, double *y, const double *x) { EW_LAUNCH(EW_ASSIGN, y, x, nullptr, 0.0, 0.0); }
+int set_val(mgic_ctx *c, const Geom &g, double *y, double v) { EW_LAUNCH(EW_SETVAL, y, nullptr, nullptr, v, 0.0); }
+int jacobi_update(mgic_ctx *c, const Geom &g, double *phi, const double *res, const double *lam, double w) {
+  EW_LAUNCH(EW_JACOBI, phi, res, lam, w, 0.0);
+}
+
+int reduce(mgic_ctx *c, const Geom &g, const double *x, const double *y, int kind, int slot) {
+  const long long n = ncells(g);
+  // grid depends only on n -> summation tree (and result bits) are a function of the level size alone
+  long long nb = (n + 256 * 8 - 1) / (256 * 8);
+  if (nb < 1) nb = 1;
+  if (nb > (long long)c->partCap) nb = (long long)c->partCap;
+  const int grd = (int)nb;
+  double *out = c->d_scal + slot;
+  switch (kind) {
+    case 0: k_reduce<0><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
+    case 1: k_reduce<1><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
+    case 2: k_reduce<2><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
+    case 3: k_reduce<3><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
+    default: mgic_set_error("reduce: bad kind %d", kind); return MGIC_ERR_ARG;
+  }
+  return post_launch(c, "reduce");
+}
+
+int is_constant(mgic_ctx *c, const Geom &g, const double *x, double value, int slot) {
+  const long long n = ncells(g);
+  long long nb = (n + 256 * 8 - 1) / (256 * 8);
+  if (nb < 1) nb = 1;
+  if (nb > (long long)c->partCap) nb = (long long)c->partCap;
+  k_reduce<4><<<(int)nb, 256, 0, c->stream>>>(n, x, nullptr, value, c->d_part, c->d_count, c->d_scal + slot);
+  return post_launch(c, "is_constant");
+}
+
+int coarse_average(mgic_ctx *c, const Geom &gc, double *cp, const double *fine, long long fsy, long long fsz, int nref,
+                   int harmonic) {
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(gc.nx, gc.ny, gc.nz, blk);
+  k_coarse_average<<<grd, blk, 0, c->stream>>>(gc, cp, fine, fsy, fsz, nref, harmonic);
+  return post_launch(c, "coarse_average");
+}
+
+}  // namespace mgk

@@ -1,0 +1,161 @@
+// mgic_internal.h -- internal structures shared by the CUDA translation units.
+#ifndef MGIC_INTERNAL_H
+#define MGIC_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "mgic.h"
+
+// ---- error plumbing -------------------------------------------------------
+void mgic_set_error(const char *fmt, ...);
+#define MGIC_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      mgic_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));    \
+      return (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? MGIC_ERR_NO_DEVICE \
+                                                                              : MGIC_ERR_CUDA;  \
+    }                                                                                           \
+  } while (0)
+#define MGIC_TRY(call)          \
+  do {                          \
+    int r__ = (call);           \
+    if (r__ != MGIC_OK) return r__; \
+  } while (0)
+#define MGIC_REQUIRE(cond, msg)                                  \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      mgic_set_error("%s:%d: %s", __FILE__, __LINE__, msg);      \
+      return MGIC_ERR_ARG;                                       \
+    }                                                            \
+  } while (0)
+
+// ---- kernel-side geometry ---------------------------------------------------
+// Face order: 0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi.
+// type: 0 Dirichlet, 1 Neumann, 2 periodic, 3 interior (the neighbour plane is in memory: z-slab halo)
+#define MGIC_FACE_INTERIOR 3
+struct BCk {
+  int type[6];
+  double a[6], b[6];  // ghost = a*centre + b   (Dirichlet: a=-1, b=2v; Neumann: a=+1, b=sign*dx*v)
+};
+
+struct Geom {
+  int nx, ny, nz;     // local valid cells (z: this rank's slab)
+  long long sy, sz;   // strides in doubles (sy = nx, sz = nx*ny)
+  int k0;             // global k of local plane 0 (colouring uses global indices)
+  int gnz;            // global nz
+};
+
+// ---- host-side objects ------------------------------------------------------
+struct mgic_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  long long launches = 0;
+  int rank = 0, nranks = 1;
+  int numSMs = 148;
+  double *d_scal = nullptr;   // device scratch scalars (reduction results)
+  double *h_scal = nullptr;   // pinned host mirror
+  double *d_part = nullptr;   // reduction partials
+  unsigned int *d_count = nullptr;
+  size_t partCap = 0;
+  // halo exchange hook (multi-GPU): set by mgic_comm; null on one GPU
+  int (*halo_exchange)(mgic_ctx *, mgic_field *, int depth_planes) = nullptr;
+  int (*allreduce)(mgic_ctx *, double *hostvals, int n, int op /*0 sum 1 max*/) = nullptr;
+  void *comm = nullptr;
+  // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
+};
+
+// records a CUDA-event pair around the launches issued in its scope when profiling is armed
+struct ProfScope {
+  mgic_ctx *c; bool on; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(mgic_ctx *ctx, bool tagged) : c(ctx), on(ctx->profiling && tagged) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(b, c->stream); c->profEvents.emplace_back(a, b); }
+  }
+};
+
+#define MGIC_GZ 2  // z ghost planes carried by every field (halo depth of one fused red+black sweep)
+
+struct mgic_field {
+  mgic_ctx *ctx = nullptr;
+  int nx = 0, ny = 0, nz = 0, gz = MGIC_GZ;
+  long long sy = 0, sz = 0;
+  double *base = nullptr;  // first ghost plane
+  double *p = nullptr;     // local cell (0,0,0)
+  size_t bytes = 0;
+  int k0 = 0, gnz = 0;
+};
+
+struct mgic_op {
+  mgic_ctx *ctx = nullptr;
+  int n[3] = {0, 0, 0};
+  int k0 = 0, nzl = 0;
+  double dx = 0, alpha = 0, beta = 0;
+  int bc_lo[3] = {0, 0, 0}, bc_hi[3] = {0, 0, 0};
+  double bc_value = 0;
+  mgic_field *a = nullptr, *b = nullptr;  // shared, not owned
+  mgic_field *lambda = nullptr;           // owned
+  mgic_field *scratch = nullptr;          // owned; ping-pong target of the fused sweep
+  bool lambdaDirty = true;
+  bool profTag = true;                    // finest-level operator: its GSRB launches are the profiled kernel
+  int smoother = 1;                       // 0: one launch per colour; 1: fused red+black plane-streaming sweep
+  Geom geom() const {
+    Geom g; g.nx = n[0]; g.ny = n[1]; g.nz = nzl; g.sy = n[0]; g.sz = (long long)n[0] * n[1]; g.k0 = k0; g.gnz = n[2];
+    return g;
+  }
+  BCk bck(bool homogeneous) const;
+};
+
+struct mgic_vars {
+  mgic_ctx *ctx = nullptr;
+  mgic_params P;
+  int n[3]; int k0 = 0, nzl = 0; double dx = 0;
+  int ng = 1;
+  long long sy = 0, sz = 0, sc = 0;  // padded strides
+  double *d = nullptr;               // 8 components, each (nx+2)(ny+2)(nzl+2)
+};
+
+// ---- kernel launchers (kernels.cu) -------------------------------------------
+namespace mgk {
+int gsrb_color(mgic_ctx *, const Geom &, const BCk &, double *phi, const double *rhs, const double *a, const double *b,
+               const double *lam, double alpha, double beta, double dx, int color);
+int apply_op(mgic_ctx *, const Geom &, const BCk &, double *lhs, const double *phi, const double *a, const double *b,
+             double alpha, double beta, double dx);
+int residual(mgic_ctx *, const Geom &, const BCk &, double *res, const double *phi, const double *rhs, const double *a,
+             const double *b, double alpha, double beta, double dx);
+int restrict_res(mgic_ctx *, const Geom &fine, const BCk &, double *resC, long long csy, long long csz, const double *phi,
+                 const double *rhs, const double *a, const double *b, double alpha, double beta, double dx);
+int prolong(mgic_ctx *, const Geom &fine, double *phi, const double *coarse, long long csy, long long csz);
+int compute_lambda(mgic_ctx *, const Geom &, double *lam, const double *a, double alpha, double beta, double dx);
+int mult(mgic_ctx *, const Geom &, double *y, const double *x, const double *l);      // y = x*l
+int incr(mgic_ctx *, const Geom &, double *y, const double *x, double s);             // y = y + s*x
+int axby(mgic_ctx *, const Geom &, double *y, const double *x1, const double *x2, double a, double b);
+int scale(mgic_ctx *, const Geom &, double *y, double s);
+int assign(mgic_ctx *, const Geom &, double *y, const double *x);
+int set_val(mgic_ctx *, const Geom &, double *y, double v);
+int jacobi_update(mgic_ctx *, const Geom &, double *phi, const double *res, const double *lam, double w);
+// reductions: result left in ctx->d_scal[slot]; kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y
+int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot);
+int coarse_average(mgic_ctx *, const Geom &coarse, double *c, const double *fine, long long fsy, long long fsz, int nref,
+                   int harmonic);
+int is_constant(mgic_ctx *, const Geom &, const double *x, double value, int slot);  // d_scal[slot] = #cells != value
+// source terms (padded multigrid_vars arrays)
+int init_conditions(mgic_vars *);
+int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
+int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
+// relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
+int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations);
+// a ghosted FArrayBox staged in HBM (chf_abi.cu)
+struct FabView { double *p; int lo[3]; long long s1, s2, sc; };
+}  // namespace mgk
+
+#endif

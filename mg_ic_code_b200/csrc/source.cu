@@ -1,0 +1,202 @@
+// source.cu -- device evaluation of the problem data that feeds the operator:
+// set_initial_conditions, set_rhs, set_a_coef, set_update_psi0 of Source/SetLevelData.cpp with the two
+// stencil kernels of Source/SetLevelDataF.ChF and the Bowen-York formulas of Source/SetBinaryBH.H fused in.
+//
+// multigrid_vars lives in HBM as 8 components (MultigridUserVariables.hpp:10-23), each padded by ONE ghost
+// layer on every side (the reference allocates three, Main_PoissonSolver.cpp:79, but its stencils read one).
+// Arithmetic keeps the reference's evaluation order; exp() and the psi_0 powers are the only operations
+// that are not bit-reproducible against libm (tested to 1e-13 relative).
+#include "mgic_internal.h"
+
+namespace {
+
+enum { c_psi = 0, c_A11 = 1, c_A12 = 2, c_A13 = 3, c_A22 = 4, c_A23 = 5, c_A33 = 6, c_phi = 7 };
+
+struct SrcP {
+  double G_Newton, phi_amplitude, phi_wavelength;
+  double m1, m2, spin1, spin2, mom1, mom2, off1, off2;
+  double dx, half[3];  // half[d] = (dx * N[d]) / 2
+  int nx, ny, nz, k0;
+  long long sy, sz, sc;
+};
+
+__device__ __forceinline__ double eps3(int a, int b, int c) {
+  // Levi-Civita entries set at Source/SetBinaryBH.H:30-36
+  if ((a == 0 && b == 1 && c == 2) || (a == 1 && b == 2 && c == 0) || (a == 2 && b == 0 && c == 1)) return 1.0;
+  if ((a == 0 && b == 2 && c == 1) || (a == 2 && b == 1 && c == 0) || (a == 1 && b == 0 && c == 2)) return -1.0;
+  return 0.0;
+}
+
+// get_Aij -- Source/SetBinaryBH.H:24-52 (Alcubierre 3.4.22), accumulation order as written there
+__device__ double get_Aij(int i, int j, double r1, double r2, const double *n1, const double *n2, const double *J1,
+                          const double *J2, const double *P1, const double *P2) {
+  double Aij = 1.5 / r1 / r1 * (n1[i] * P1[j] + n1[j] * P1[i]) + 1.5 / r2 / r2 * (n2[i] * P2[j] + n2[j] * P2[i]);
+  const double dij = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    Aij += 1.5 / r1 / r1 * (n1[i] * n1[j] - dij) * P1[k] * n1[k] + 1.5 / r2 / r2 * (n2[i] * n2[j] - dij) * P2[k] * n2[k];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      Aij += -3.0 / r1 / r1 / r1 * (eps3(i, l, k) * n1[j] + eps3(j, l, k) * n1[i]) * n1[l] * J1[k] -
+             3.0 / r2 / r2 / r2 * (eps3(i, l, k) * n2[j] + eps3(j, l, k) * n2[i]) * n2[l] * J2[k];
+    }
+  }
+  return Aij;
+}
+
+// cell centre: Source/SetLevelData.cpp:58-60   loc = (iv + 0.5) * dx - domainLength / 2
+__device__ __forceinline__ void cell_loc(const SrcP &P, int i, int j, int kg, double loc[3]) {
+  const int iv[3] = {i, j, kg};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double l = iv[d] + 0.5 * 1.0;
+    l *= P.dx;
+    l -= P.half[d];
+    loc[d] = l;
+  }
+}
+
+// set_initial_conditions over the ghosted box -- Source/SetLevelData.cpp:32-71, SetBinaryBH.H:54-83, MyPhiFunction.H:11-16
+__global__ void __launch_bounds__(128) k_init(SrcP P, double *__restrict__ mv) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  const int j = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+  const int k = (int)blockIdx.z - 1;
+  if (i > P.nx || j > P.ny) return;
+  const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
+  double loc[3];
+  cell_loc(P, i, j, k + P.k0, loc);
+  mv[q + c_psi * P.sc] = 1.0;
+  const double r2 = loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2];
+  mv[q + c_phi * P.sc] = P.phi_amplitude * exp(-r2 / P.phi_wavelength);
+  double l1[3] = {loc[0] - P.off1, loc[1], loc[2]};
+  double l2[3] = {loc[0] - P.off2, loc[1], loc[2]};
+  const double r1 = sqrt(l1[0] * l1[0] + l1[1] * l1[1] + l1[2] * l1[2]);
+  const double rr2 = sqrt(l2[0] * l2[0] + l2[1] * l2[1] + l2[2] * l2[2]);
+  const double n1[3] = {l1[0] / r1, l1[1] / r1, l1[2] / r1};
+  const double n2[3] = {l2[0] / rr2, l2[1] / rr2, l2[2] / rr2};
+  const double J1[3] = {0.0, 0.0, P.spin1}, J2[3] = {0.0, 0.0, P.spin2};
+  const double P1[3] = {0.0, P.mom1, 0.0}, P2[3] = {0.0, P.mom2, 0.0};
+  mv[q + c_A11 * P.sc] = get_Aij(0, 0, r1, rr2, n1, n2, J1, J2, P1, P2);
+  mv[q + c_A22 * P.sc] = get_Aij(1, 1, r1, rr2, n1, n2, J1, J2, P1, P2);
+  mv[q + c_A33 * P.sc] = get_Aij(2, 2, r1, rr2, n1, n2, J1, J2, P1, P2);
+  mv[q + c_A12 * P.sc] = get_Aij(0, 1, r1, rr2, n1, n2, J1, J2, P1, P2);
+  mv[q + c_A13 * P.sc] = get_Aij(0, 2, r1, rr2, n1, n2, J1, J2, P1, P2);
+  mv[q + c_A23 * P.sc] = get_Aij(1, 2, r1, rr2, n1, n2, J1, J2, P1, P2);
+}
+
+// set_rhs + set_a_coef fused -- Source/SetLevelData.cpp:73-127, 281-325; SetLevelDataF.ChF:15-58, 65-103
+__global__ void __launch_bounds__(128) k_rhs_acoef(SrcP P, const double *__restrict__ mv, double *__restrict__ rhs,
+                                                   double *__restrict__ aC, double constant_K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= P.nx || j >= P.ny) return;
+  const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
+  const long long o = i + (long long)j * P.nx + (long long)k * P.nx * P.ny;
+  const long long st[3] = {1, P.sy, P.sz};
+  const double *psi = mv + c_psi * P.sc, *phi = mv + c_phi * P.sc;
+  // GETRHOGRADPHIF: rho = sum_d 0.5 * (0.5/dx * (phi+ - phi-))^2
+  double rho = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double g = 0.5 / P.dx * (phi[q + st[d]] - phi[q - st[d]]);
+    rho = rho + 0.5 * g * g;
+  }
+  // GETLAPLACIANPSIF: lap = sum_d 1/dx/dx * (psi- - 2 psi + psi+)
+  double lap = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double dd = 1.0 / P.dx / P.dx * (+1.0 * psi[q - st[d]] - 2.0 * psi[q] + 1.0 * psi[q + st[d]]);
+    lap = lap + dd;
+  }
+  double loc[3];
+  cell_loc(P, i, j, k + P.k0, loc);
+  // set_m_value (:266-278): rho_matter = 0
+  const double rho_m = 0.5 * 0.0 * 0.0 + 0.0;
+  const double m = (2.0 / 3.0) * (constant_K * constant_K) - 16.0 * M_PI * P.G_Newton * rho_m;
+  const double a11 = mv[q + c_A11 * P.sc], a22 = mv[q + c_A22 * P.sc], a33 = mv[q + c_A33 * P.sc];
+  const double a12 = mv[q + c_A12 * P.sc], a13 = mv[q + c_A13 * P.sc], a23 = mv[q + c_A23 * P.sc];
+  const double A2 = a11 * a11 + a22 * a22 + a33 * a33 + 2 * (a12 * a12) + 2 * (a13 * a13) + 2 * (a23 * a23);  // :110-116
+  // set_binary_bh_psi (SetBinaryBH.H:85-99)
+  const double x1 = loc[0] - P.off1, x2 = loc[0] - P.off2;
+  const double r1 = sqrt(x1 * x1 + loc[1] * loc[1] + loc[2] * loc[2]);
+  const double r2 = sqrt(x2 * x2 + loc[1] * loc[1] + loc[2] * loc[2]);
+  const double psi_0 = psi[q] + (P.m1 / r1 + P.m2 / r2);  // :118-119
+  const double p2 = psi_0 * psi_0, p4 = p2 * p2, p5 = p4 * psi_0, p7 = p4 * p2 * psi_0, p8 = p4 * p4;
+  if (aC) aC[o] = -0.625 * m * p4 - A2 * (1.0 / p8) + 2.0 * M_PI * P.G_Newton * rho;  // :321-322
+  if (rhs) rhs[o] = 0.125 * m * p5 - 0.125 * A2 * (1.0 / p7) - 2.0 * M_PI * P.G_Newton * rho * psi_0 - lap;  // :121-124
+}
+
+// set_update_psi0 -- Source/SetLevelData.cpp:243-263: psi += dpsi over the GHOSTED box.  dpsi's domain-face
+// ghost is what the solver's last homogeneous BC fill left there: a*near (+0).
+__global__ void __launch_bounds__(128) k_update_psi(SrcP P, Geom g, BCk bc, double *__restrict__ mv,
+                                                    const double *__restrict__ dpsi) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  const int j = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+  const int k = (int)blockIdx.z - 1;
+  if (i > P.nx || j > P.ny) return;
+  const int oi = (i < 0) + (i >= P.nx), oj = (j < 0) + (j >= P.ny), ok = (k < 0) + (k >= P.nz);
+  if (oi + oj + ok > 1) return;  // edges / corners: never read by the 7-point stencils
+  const int ci = min(max(i, 0), P.nx - 1), cj = min(max(j, 0), P.ny - 1), ck = min(max(k, 0), P.nz - 1);
+  const long long cidx = ci + cj * g.sy + ck * g.sz;
+  double v = dpsi[cidx];
+  if (oi + oj + ok == 1) {
+    const int f = oi ? (i < 0 ? 0 : 1) : (oj ? (j < 0 ? 2 : 3) : (k < 0 ? 4 : 5));
+    if (bc.type[f] == MGIC_FACE_INTERIOR) v = dpsi[cidx + (k < 0 ? -g.sz : g.sz)];
+    else if (bc.type[f] == MGIC_BC_PERIODIC) {
+      const long long w = (f == 0) ? (g.nx - 1) : (f == 1) ? -(long long)(g.nx - 1)
+                        : (f == 2) ? (long long)(g.ny - 1) * g.sy : (f == 3) ? -(long long)(g.ny - 1) * g.sy
+                        : (f == 4) ? (long long)(g.nz - 1) * g.sz : -(long long)(g.nz - 1) * g.sz;
+      v = dpsi[cidx + w];
+    } else v = bc.a[f] * v + bc.b[f];
+  }
+  const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
+  mv[q + c_psi * P.sc] += v;
+}
+
+SrcP make_srcp(const mgic_vars *v) {
+  SrcP s;
+  const mgic_params &P = v->P;
+  s.G_Newton = P.G_Newton; s.phi_amplitude = P.phi_amplitude; s.phi_wavelength = P.phi_wavelength;
+  s.m1 = P.bh1_bare_mass; s.m2 = P.bh2_bare_mass; s.spin1 = P.bh1_spin; s.spin2 = P.bh2_spin;
+  s.mom1 = P.bh1_momentum; s.mom2 = P.bh2_momentum; s.off1 = P.bh1_offset; s.off2 = P.bh2_offset;
+  s.dx = v->dx;
+  for (int d = 0; d < 3; d++) s.half[d] = (v->dx * P.N[d]) / 2.0;  // PoissonParameters.cpp:83-85
+  s.nx = v->n[0]; s.ny = v->n[1]; s.nz = v->nzl; s.k0 = v->k0;
+  s.sy = v->sy; s.sz = v->sz; s.sc = v->sc;
+  return s;
+}
+
+int post(mgic_ctx *c, const char *what) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { mgic_set_error("kernel %s: %s", what, cudaGetErrorString(e)); return MGIC_ERR_CUDA; }
+  return MGIC_OK;
+}
+
+}  // namespace
+
+namespace mgk {
+
+int init_conditions(mgic_vars *v) {
+  SrcP s = make_srcp(v);
+  dim3 blk(32, 4, 1), grd((s.nx + 2 + 31) / 32, (s.ny + 2 + 3) / 4, s.nz + 2);
+  k_init<<<grd, blk, 0, v->ctx->stream>>>(s, v->d);
+  return post(v->ctx, "init_conditions");
+}
+
+int set_rhs_acoef(mgic_vars *v, double *rhs, double *acoef, double constant_K) {
+  SrcP s = make_srcp(v);
+  dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
+  k_rhs_acoef<<<grd, blk, 0, v->ctx->stream>>>(s, v->d, rhs, acoef, constant_K);
+  return post(v->ctx, "set_rhs_acoef");
+}
+
+int update_psi(mgic_vars *v, const Geom &g, const BCk &bc, const double *dpsi) {
+  SrcP s = make_srcp(v);
+  dim3 blk(32, 4, 1), grd((s.nx + 2 + 31) / 32, (s.ny + 2 + 3) / 4, s.nz + 2);
+  k_update_psi<<<grd, blk, 0, v->ctx->stream>>>(s, g, bc, v->d, dpsi);
+  return post(v->ctx, "update_psi");
+}
+
+}  // namespace mgk

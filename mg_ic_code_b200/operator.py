@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's operator interface on top of the C ABI.
+
+Names and argument meaning follow Source/VariableCoeffPoissonOperator.H:40-168,
+Source/VariableCoeffPoissonOperatorFactory.H:57-92 and the [Chombo] AMRLevelOp / MultiGrid methods the
+reference inherits.  A LevelField is the device-resident stand-in for LevelData<FArrayBox> (one component);
+its numpy views are global ghost-free arrays indexed [k, j, i].  Errors raise MgicError where the reference
+calls MayDay::Error / MayDay::Abort.  Everything computes on the GPU; nothing here touches the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._capi import MgicError, check, lib
+from .params import make_params
+
+
+class Context:
+    """One GPU (+ stream).  Multi-GPU: one Context per process/rank (see mg_ic_code_b200.comm)."""
+
+    def __init__(self, device=0, rank=0, nranks=1):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.mgic_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.rank, self.nranks = rank, nranks
+        if nranks > 1:
+            check(self.L.mgic_ctx_set_rank(h, rank, nranks))
+
+    def sync(self):
+        check(self.L.mgic_ctx_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self.L.mgic_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def profile(self, enable=True):
+        """arm / disarm CUDA-event timing of the finest-level GSRB launches"""
+        check(self.L.mgic_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        n, ms = C.c_longlong(), C.c_double()
+        check(self.L.mgic_ctx_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    @property
+    def stream(self):
+        return self.L.mgic_ctx_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return self.L.mgic_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.mgic_ctx_destroy(self.h)
+            self.h = None
+
+
+class LevelField:
+    """Device-resident LevelData<FArrayBox> (1 component) on the level of `op`."""
+
+    def __init__(self, op, handle=None, owned=True):
+        self.op, self.L = op, op.L
+        self.owned = owned
+        if handle is None:
+            handle = C.c_void_p()
+            check(self.L.mgic_field_create(op.h, C.byref(handle)))
+        self.h = handle
+
+    @property
+    def shape(self):
+        n = self.op.n
+        return (n[2], n[1], n[0])
+
+    def upload(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        if a.shape != self.shape:
+            raise MgicError(f"array shape {a.shape} != level shape {self.shape}")
+        check(self.L.mgic_field_upload(self.h, a))
+        return self
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros(self.shape, dtype=np.float64)
+        check(self.L.mgic_field_download(self.h, out))
+        return out
+
+    def upload_fab(self, fab, lo, hi, region_lo=None, region_hi=None):
+        i3 = C.c_int * 3
+        rl, rh = (lo if region_lo is None else region_lo), (hi if region_hi is None else region_hi)
+        check(self.L.mgic_field_upload_fab(self.h, np.ascontiguousarray(fab, dtype=np.float64), i3(*lo), i3(*hi), i3(*rl), i3(*rh)))
+
+    def download_fab(self, fab, lo, hi, region_lo=None, region_hi=None):
+        i3 = C.c_int * 3
+        rl, rh = (lo if region_lo is None else region_lo), (hi if region_hi is None else region_hi)
+        check(self.L.mgic_field_download_fab(self.h, fab, i3(*lo), i3(*hi), i3(*rl), i3(*rh)))
+        self.op.ctx.sync()
+
+    def close(self):
+        if self.h and self.owned:
+            self.L.mgic_field_destroy(self.h)
+        self.h = None
+
+
+class VariableCoeffPoissonOperator:
+    """L = alpha*aCoef*I - beta*bCoef*Laplacian on one level (VariableCoeffPoissonOperator.H:25)."""
+
+    def __init__(self, ctx, n, dx, alpha=1.0, beta=-1.0, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), bc_value=0.0, k0=0,
+                 nz_local=None, handle=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.owned = handle is None
+        if handle is None:
+            i3 = C.c_int * 3
+            handle = C.c_void_p()
+            nzl = n[2] - k0 if nz_local is None else nz_local
+            check(self.L.mgic_op_create(ctx.h, i3(*n), k0, nzl, dx, alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value,
+                                        C.byref(handle)))
+        self.h = handle
+        n3 = (C.c_int * 3)()
+        k0_, nzl_, dx_ = C.c_int(), C.c_int(), C.c_double()
+        check(self.L.mgic_op_dims(self.h, n3, C.byref(k0_), C.byref(nzl_), C.byref(dx_)))
+        self.n, self.k0, self.nz_local, self.dx = (n3[0], n3[1], n3[2]), k0_.value, nzl_.value, dx_.value
+
+    # AMRLevelOp::create
+    def create(self):
+        return LevelField(self)
+
+    def setCoefs(self, aCoef, bCoef, alpha, beta):
+        self._a, self._b = aCoef, bCoef
+        check(self.L.mgic_op_set_coefs(self.h, aCoef.h, bCoef.h if bCoef is not None else None, alpha, beta))
+
+    def setAlphaAndBeta(self, alpha, beta):
+        check(self.L.mgic_op_set_alpha_beta(self.h, alpha, beta))
+
+    def resetLambda(self):
+        check(self.L.mgic_op_reset_lambda(self.h))
+
+    def computeLambda(self):
+        check(self.L.mgic_op_compute_lambda(self.h))
+
+    def lambda_field(self):
+        h = C.c_void_p()
+        check(self.L.mgic_op_get_lambda(self.h, C.byref(h)))
+        return LevelField(self, h, owned=False)
+
+    def set_smoother(self, kind):
+        check(self.L.mgic_op_set_smoother(self.h, kind))
+
+    def relax(self, e, residual, iterations):
+        check(self.L.mgic_op_relax(self.h, e.h, residual.h, iterations))
+
+    def levelGSRB(self, e, residual):
+        check(self.L.mgic_op_relax(self.h, e.h, residual.h, 1))
+
+    def gsrb_color(self, e, residual, whichPass):
+        check(self.L.mgic_op_gsrb_color(self.h, e.h, residual.h, whichPass))
+
+    def levelJacobi(self, e, residual):
+        check(self.L.mgic_op_level_jacobi(self.h, e.h, residual.h))
+
+    def residual(self, lhs, phi, rhs, homogeneous=False):
+        check(self.L.mgic_op_residual(self.h, lhs.h, phi.h, rhs.h, int(homogeneous)))
+
+    def applyOp(self, lhs, phi, homogeneous=False):
+        check(self.L.mgic_op_apply(self.h, lhs.h, phi.h, int(homogeneous)))
+
+    def applyOpNoBoundary(self, lhs, phi):
+        check(self.L.mgic_op_apply_no_boundary(self.h, lhs.h, phi.h))
+
+    def restrictResidual(self, resCoarse, phiFine, rhsFine):
+        check(self.L.mgic_op_restrict_residual(self.h, resCoarse.h, phiFine.h, rhsFine.h))
+
+    def prolongIncrement(self, phiThisLevel, correctCoarse):
+        check(self.L.mgic_op_prolong_increment(self.h, phiThisLevel.h, correctCoarse.h))
+
+    def preCond(self, phi, rhs):
+        check(self.L.mgic_op_precond(self.h, phi.h, rhs.h))
+
+    def norm(self, x, ord=0):
+        out = C.c_double()
+        check(self.L.mgic_op_norm(self.h, x.h, ord, C.byref(out)))
+        return out.value
+
+    def dotProduct(self, x, y):
+        out = C.c_double()
+        check(self.L.mgic_op_dot(self.h, x.h, y.h, C.byref(out)))
+        return out.value
+
+    def incr(self, y, x, scale):
+        check(self.L.mgic_op_incr(self.h, y.h, x.h, scale))
+
+    def axby(self, y, x1, x2, a, b):
+        check(self.L.mgic_op_axby(self.h, y.h, x1.h, x2.h, a, b))
+
+    def scale(self, y, s):
+        check(self.L.mgic_op_scale(self.h, y.h, s))
+
+    def assign(self, y, x):
+        check(self.L.mgic_op_assign(self.h, y.h, x.h))
+
+    assignLocal = assign
+
+    def setToZero(self, y):
+        check(self.L.mgic_op_set_to_zero(self.h, y.h))
+
+    def setVal(self, y, v):
+        check(self.L.mgic_op_set_val(self.h, y.h, v))
+
+    def close(self):
+        if self.h and self.owned:
+            self.L.mgic_op_destroy(self.h)
+        self.h = None
+
+
+class VariableCoeffPoissonOperatorFactory:
+    """define() + MGnewOp(depth) until NULL (VariableCoeffPoissonOperatorFactory.cpp:59-106,139-234), i.e. the
+    hierarchy [Chombo] MultiGrid::define builds, plus MultiGrid::oneCycle and the solvers that drive it."""
+
+    def __init__(self, ctx, params, aCoef, bCoef, keep_b=False):
+        self.ctx, self.L = ctx, ctx.L
+        self.params = params if not isinstance(params, dict) else make_params(params)
+        self._a, self._b = aCoef, bCoef
+        h = C.c_void_p()
+        check(self.L.mgic_mg_create_ex(ctx.h, C.byref(self.params), aCoef.h, bCoef.h if bCoef is not None else None,
+                                       1 if keep_b else 0, C.byref(h)))
+        self.h = h
+        self.depths = self.L.mgic_mg_depths(h)
+
+    def MGnewOp(self, depth):
+        h = C.c_void_p()
+        check(self.L.mgic_mg_op(self.h, depth, C.byref(h)))
+        if not h:
+            return None
+        return VariableCoeffPoissonOperator(self.ctx, None, None, handle=h)
+
+    def AMRnewOp(self):
+        return self.MGnewOp(0)
+
+    def scratch(self, depth):
+        e, r = C.c_void_p(), C.c_void_p()
+        check(self.L.mgic_mg_scratch(self.h, depth, C.byref(e), C.byref(r)))
+        op = self.MGnewOp(depth)
+        return LevelField(op, e, owned=False), LevelField(op, r, owned=False)
+
+    def refresh_coefs(self):
+        check(self.L.mgic_mg_refresh_coefs(self.h))
+
+    def set_smoother(self, kind):
+        check(self.L.mgic_mg_set_smoother(self.h, kind))
+
+    @property
+    def b_is_one(self):
+        return bool(self.L.mgic_mg_b_is_one(self.h))
+
+    # [Chombo] MultiGrid::oneCycle(e, r), homogeneous
+    def vcycle(self, e, r):
+        check(self.L.mgic_mg_vcycle(self.h, e.h, r.h))
+
+    def bottom_solve(self, e, r):
+        it = C.c_int()
+        check(self.L.mgic_mg_bottom_solve(self.h, e.h, r.h, C.byref(it)))
+        return it.value
+
+    @property
+    def last_bottom_iterations(self):
+        return self.L.mgic_mg_last_bottom_iterations(self.h)
+
+    # solver.solve(dpsi, rhs): BiCGStab preconditioned by numMGIterations V-cycles (Main_PoissonSolver.cpp:173-184)
+    def solve(self, dpsi, rhs, max_norms=512):
+        it, st = C.c_int(), C.c_int()
+        norms = (C.c_double * max_norms)()
+        check(self.L.mgic_mg_outer_solve(self.h, dpsi.h, rhs.h, C.byref(it), C.byref(st), norms, max_norms))
+        return it.value, st.value, np.array(norms[: min(it.value + 1, max_norms)])
+
+    def close(self):
+        if self.h:
+            self.L.mgic_mg_destroy(self.h)
+            self.h = None
+
+
+class MultigridVars:
+    """multigrid_vars (8 components, MultigridUserVariables.hpp) + the Set* functions of Source/SetLevelData.cpp."""
+
+    NAMES = ("psi", "A11_0", "A12_0", "A13_0", "A22_0", "A23_0", "A33_0", "phi_0")
+
+    def __init__(self, ctx, params, k0=0, nz_local=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.params = params if not isinstance(params, dict) else make_params(params)
+        nzl = self.params.N[2] - k0 if nz_local is None else nz_local
+        h = C.c_void_p()
+        check(self.L.mgic_vars_create(ctx.h, C.byref(self.params), k0, nzl, C.byref(h)))
+        self.h, self.k0, self.nz_local = h, k0, nzl
+
+    def set_initial_conditions(self, dpsi=None):
+        check(self.L.mgic_set_initial_conditions(self.h, dpsi.h if dpsi is not None else None))
+
+    def set_a_coef(self, aCoef, constant_K=0.0):
+        check(self.L.mgic_set_a_coef(self.h, aCoef.h, constant_K))
+
+    def set_b_coef(self, bCoef):
+        check(self.L.mgic_set_b_coef(self.h, bCoef.h))
+
+    def set_rhs(self, rhs, constant_K=0.0):
+        check(self.L.mgic_set_rhs(self.h, rhs.h, constant_K))
+
+    def set_rhs_and_a_coef(self, rhs, aCoef, constant_K=0.0):
+        check(self.L.mgic_set_rhs_and_a_coef(self.h, rhs.h, aCoef.h, constant_K))
+
+    def set_update_psi0(self, op0, dpsi):
+        out = C.c_double()
+        check(self.L.mgic_update_psi0(self.h, op0.h, dpsi.h, C.byref(out)))
+        return out.value
+
+    def download(self, comp, ghosted=False):
+        N = self.params.N
+        if ghosted:
+            out = np.zeros((self.nz_local + 2, N[1] + 2, N[0] + 2))
+            check(self.L.mgic_vars_download_ghosted(self.h, comp, out))
+        else:
+            out = np.zeros((N[2], N[1], N[0]))
+            check(self.L.mgic_vars_download(self.h, comp, out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.mgic_vars_destroy(self.h)
+            self.h = None
+
+
+def level_op_from_params(ctx, params, k0=0, nz_local=None):
+    """The AMR-level operator geometry of params (dx = L/N[0], PoissonParameters.cpp:82) without coefficients."""
+    p = params if not isinstance(params, dict) else make_params(params)
+    per = bool(p.is_periodic)
+    lo = [2] * 3 if per else list(p.bc_lo)
+    hi = [2] * 3 if per else list(p.bc_hi)
+    return VariableCoeffPoissonOperator(ctx, tuple(p.N), p.L / p.N[0], p.alpha, p.beta, lo, hi, p.bc_value, k0, nz_local)
+
+
+def nl_solve(ctx, params, want_psi=True):
+    """The nonlinear loop of Main_PoissonSolver.cpp:131-216 (single level) on the GPU."""
+    p = params if not isinstance(params, dict) else make_params(params)
+    norms = (C.c_double * 64)()
+    its = C.c_int()
+    psi = np.zeros((p.N[2], p.N[1], p.N[0])) if want_psi else None
+    check(ctx.L.mgic_nl_solve(ctx.h, C.byref(p), norms, 64, C.byref(its), psi.ctypes.data if want_psi else None))
+    return np.array(norms[: its.value]), psi

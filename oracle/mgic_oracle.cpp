@@ -1040,6 +1040,11 @@ int orc_define_solver(orc_problem *pb) {
 int orc_mg_depths(const orc_problem *pb) { return (int)pb->ops.size(); }
 
 void orc_level_dims(const orc_problem *pb, int depth, int n[3], double *dx) {
+  if (depth == 0 || pb->ops.empty()) {   // level 0 geometry exists before the solver is defined
+    for (int d = 0; d < 3; d++) n[d] = pb->grids.domain.size(d);
+    *dx = pb->dx0;
+    return;
+  }
   const Op *op = pb->ops[depth];
   for (int d = 0; d < 3; d++) n[d] = op->lay.domain.size(d);
   *dx = op->dx;

@@ -1,0 +1,101 @@
+"""Independent numpy twin of the operator kernels on ONE global array (no boxes), used to pin the boxed C++
+oracle: GSRB / residual / applyOp / restrict are partition invariant (global-index colouring, exchange before
+every colour), so oracle(any box size) must equal this twin bit for bit.  Arrays are indexed [k, j, i].
+
+Follows Source/VariableCoeffPoissonOperatorF.ChF:56-139,181-237,283-339,379-437 and
+Source/SetBCs.cpp:49-131 ([Chombo] DiriBC order 1 / NeumBC).  Test infrastructure only.
+"""
+import numpy as np
+
+
+def ghosted(phi, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), value=0.0, dx=1.0, homogeneous=True):
+    """phi with one ghost layer filled by the physical BC (0 Dirichlet: 2v - near, 1 Neumann: near + side*dx*v)."""
+    v = 0.0 if homogeneous else value
+    g = np.zeros(tuple(s + 2 for s in phi.shape))
+    g[1:-1, 1:-1, 1:-1] = phi
+    for d in range(3):           # d = 0 -> x (last axis)
+        ax = 2 - d
+        lo = [slice(1, -1)] * 3
+        hi = [slice(1, -1)] * 3
+        nlo = [slice(1, -1)] * 3
+        nhi = [slice(1, -1)] * 3
+        lo[ax], nlo[ax] = 0, 1
+        hi[ax], nhi[ax] = -1, -2
+        g[tuple(lo)] = (2 * v - g[tuple(nlo)]) if bc_lo[d] == 0 else (g[tuple(nlo)] + (-1) * dx * v)
+        g[tuple(hi)] = (2 * v - g[tuple(nhi)]) if bc_hi[d] == 0 else (g[tuple(nhi)] + (+1) * dx * v)
+    return g
+
+
+def lap7(g):
+    c = g[1:-1, 1:-1, 1:-1]
+    t = 2.0 * c
+    return (((g[1:-1, 1:-1, 2:] + g[1:-1, 1:-1, :-2]) - t) + ((g[1:-1, 2:, 1:-1] + g[1:-1, :-2, 1:-1]) - t)
+            + ((g[2:, 1:-1, 1:-1] + g[:-2, 1:-1, 1:-1]) - t))
+
+
+def colour_mask(shape, red_black):
+    k, j, i = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), np.arange(shape[2]), indexing="ij")
+    return ((i + j + k + red_black) % 2) == 0
+
+
+def gsrb_colour(phi, rhs, a, b, lam, alpha, beta, dx, red_black, **bc):
+    g = ghosted(phi, dx=dx, homogeneous=True, **bc)
+    dxinv = 1.0 / (dx * dx)
+    lof = alpha * a * phi
+    l = lap7(g)
+    l = l * dxinv * b
+    lof = lof - beta * l
+    new = phi - lam * (lof - rhs)
+    return np.where(colour_mask(phi.shape, red_black), new, phi)
+
+
+def relax(phi, rhs, a, b, lam, alpha, beta, dx, iterations, **bc):
+    for _ in range(iterations):
+        for p in (0, 1):
+            phi = gsrb_colour(phi, rhs, a, b, lam, alpha, beta, dx, p, **bc)
+    return phi
+
+
+def apply_op(phi, a, b, alpha, beta, dx, homogeneous=True, value=0.0, **bc):
+    g = ghosted(phi, dx=dx, homogeneous=homogeneous, value=value, **bc)
+    l = lap7(g) * (1.0 / (dx * dx)) * beta * b
+    return alpha * a * phi - l
+
+
+def residual(phi, rhs, a, b, alpha, beta, dx, homogeneous=True, value=0.0, **bc):
+    g = ghosted(phi, dx=dx, homogeneous=homogeneous, value=value, **bc)
+    l = lap7(g) * (1.0 / (dx * dx)) * beta * b
+    return (rhs - alpha * a * phi) + l
+
+
+def restrict_residual(phi, rhs, a, b, alpha, beta, dx, **bc):
+    g = ghosted(phi, dx=dx, homogeneous=True, **bc)
+    l = lap7(g) * (1.0 / (dx * dx)) * beta * b
+    lof = alpha * a * phi - l
+    q = (rhs - lof) / 8.0
+    out = np.zeros(tuple(s // 2 for s in phi.shape))
+    for dk in (0, 1):
+        for dj in (0, 1):
+            for di in (0, 1):
+                out = out + q[dk::2, dj::2, di::2]
+    return out
+
+
+def prolong_increment(phi, coarse):
+    return phi + np.repeat(np.repeat(np.repeat(coarse, 2, axis=0), 2, axis=1), 2, axis=2)
+
+
+def compute_lambda(a, alpha, beta, dx):
+    return 1.0 / (a * alpha + 2.0 * 3 * beta / (dx * dx))
+
+
+def coarse_average(f, nref, harmonic):
+    nz, ny, nx = (s // nref for s in f.shape)
+    s = np.zeros((nz, ny, nx))
+    for kk in range(nref):
+        for jj in range(nref):
+            for ii in range(nref):
+                fv = f[kk::nref, jj::nref, ii::nref]
+                s = s + (1.0 / fv if harmonic else fv)
+    scale = 1.0 / float(nref ** 3)
+    return 1.0 / (s * scale) if harmonic else s * scale

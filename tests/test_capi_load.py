@@ -1,0 +1,91 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares, and
+refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import mg_ic_code_b200 as m
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("mgic.h", "mgic_chf.h", "mgic_comm.h"):
+        p = os.path.join(ROOT, "include", h)
+        if not os.path.exists(p):
+            continue
+        src = open(p).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = "\n".join(l for l in src.splitlines() if not l.strip().startswith("#"))
+        src = src.replace("\\\n", " ")
+        for mm in re.finditer(r"\b([a-z_0-9]+)\s*\(", src):
+            n = mm.group(1)
+            if n.startswith("mgic_") or n.endswith("3d_") or n in ("getlaplacianpsif_", "getrhogradphif_", "prolong_"):
+                names.add(n)
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    L = m.lib()
+    syms = declared_symbols()
+    assert len(syms) > 60
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_chf_symbol_names_are_fortran_mangled():
+    L = m.lib()
+    for s in ("gsrbhelmholtzvc3d_", "vccomputeop3d_", "vccomputeres3d_", "restrictresvc3d_", "getlaplacianpsif_",
+              "getrhogradphif_", "prolong_"):
+        assert hasattr(L, s)
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(m.MgicError, match="no CPU fallback"):
+        m.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mg_ic_code_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dp, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"import_module\(.oracle", r"libmgic_oracle", r"#include\s+.*oracle"):
+                    assert not re.search(pat, src, flags=re.M), f"{f} reaches into oracle/ ({pat})"
+
+
+def test_params_reader(tmp_path):
+    txt = """# sample in the reference's params.txt format
+alpha = 1.0
+beta  = -1.0
+L = 100.0
+N = 64 32 16
+max_level    = 0
+block_factor = 8
+max_grid_size = 16   # max box size
+numMGsmooth = 2 # smooths
+numMGIterations = 3
+tolerance  = 1.0e-9
+coefficient_average_type = harmonic
+is_periodic = 0
+bc_lo       = 0 1 0
+bc_hi       = 1 0 0
+bc_value = 0.5
+bh1_offset = 12.5
+"""
+    p = tmp_path / "params.txt"
+    p.write_text(txt)
+    P = m.read_params(str(p), overrides=["numMGsmooth=4"])
+    assert list(P.N) == [64, 32, 16] and P.numMGsmooth == 4 and P.numMGIterations == 3
+    assert list(P.bc_lo) == [0, 1, 0] and list(P.bc_hi) == [1, 0, 0] and P.bc_value == 0.5
+    assert P.coefficient_average_type == 1 and P.bh1_offset == 12.5 and P.tolerance == 1e-9
+    p.write_text(txt.replace("harmonic", "geometric"))
+    with pytest.raises(m.MgicError, match="bad coefficient_average_type"):
+        m.read_params(str(p))

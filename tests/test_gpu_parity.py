@@ -1,0 +1,315 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar: every stencil / transfer kernel is BIT-EXACT (same operation order, no FMA contraction on either side);
+reductions (norm / dot) differ only by summation order (rtol 1e-13); whole V-cycles, the outer BiCGStab and the
+NL loop, which contain reductions in their control flow, are held to the north-star tolerance of 1e-10 relative
+in max-norm.  Source terms use exp() and psi powers: 1e-13 relative to the field's max.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import mg_ic_code_b200 as m
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+CASES = {
+    "c16": dict(N=(16, 16, 16), max_grid_size=8, L=40.0),
+    "neumann": dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1), bc_value=0.25,
+                    coefficient_average_type=0),
+    "c64": dict(N=(64, 64, 64), max_grid_size=16),
+    "c8": dict(N=(8, 8, 8), max_grid_size=8, L=10.0),
+}
+
+
+def relerr(x, y):
+    d = np.abs(np.asarray(x) - np.asarray(y)).max()
+    s = np.abs(np.asarray(y)).max()
+    return d / s if s > 0 else d
+
+
+class Pair:
+    """Oracle problem + GPU hierarchy fed with the ORACLE's coefficients, so kernels can be compared bit for bit."""
+
+    def __init__(self, ctx, keep_b=False, smoother=None, **over):
+        self.o = Oracle(**over)
+        self.nd = self.o.setup()
+        self.P = m.make_params(self.o.params)
+        self.lvl = m.level_op_from_params(ctx, self.P)
+        self.a, self.b = self.lvl.create(), self.lvl.create()
+        self.a.upload(self.o.get("A")); self.b.upload(self.o.get("B"))
+        self.f = m.VariableCoeffPoissonOperatorFactory(ctx, self.P, self.a, self.b, keep_b=keep_b)
+        if smoother is not None:
+            self.f.set_smoother(smoother)
+        self.op = self.f.MGnewOp(0)
+        self.e, self.r, self.t = self.op.create(), self.op.create(), self.op.create()
+        n = self.o.params["N"]
+        self.shape = (n[2], n[1], n[0])
+
+    def load(self, e, r):
+        self.o.set("E", e); self.o.set("R", r)
+        self.e.upload(e); self.r.upload(r)
+
+    def rand(self, seed=0):
+        rng = np.random.default_rng(seed)
+        return rng.standard_normal(self.shape), rng.standard_normal(self.shape)
+
+
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8"])
+@pytest.mark.parametrize("keep_b", [False, True])
+def test_kernels_bit_exact(ctx, case, keep_b):
+    p = Pair(ctx, keep_b=keep_b, smoother=0, **CASES[case])
+    assert p.f.depths == p.nd
+    assert p.f.b_is_one == (not keep_b)
+    e, r = p.rand(1)
+    p.load(e, r)
+    # lambda + coarsened coefficients (CoarseAverage harmonic / arithmetic)
+    assert np.array_equal(p.op.lambda_field().download(), p.o.get("LAMBDA"))
+    for d in range(1, p.nd):
+        opd = p.f.MGnewOp(d)
+        assert np.array_equal(opd.lambda_field().download(), p.o.get("LAMBDA", d))
+    assert p.f.MGnewOp(p.nd) is None  # MGnewOp returns NULL past the depth limit
+    # residual (homogeneous and inhomogeneous BC), applyOp
+    for homog in (True, False):
+        p.op.residual(p.t, p.e, p.r, homog)
+        assert np.array_equal(p.t.download(), p.o.residual(0, homog))
+        p.op.applyOp(p.t, p.e, homog)
+        assert np.array_equal(p.t.download(), p.o.apply(0, homog))
+    # one colour at a time, then full sweeps
+    for colour in (0, 1):
+        p.op.gsrb_color(p.e, p.r, colour)
+        p.o.gsrb_color(0, colour)
+        assert np.array_equal(p.e.download(), p.o.get("E"))
+    p.op.relax(p.e, p.r, 3)
+    p.o.relax(0, 3)
+    assert np.array_equal(p.e.download(), p.o.get("E"))
+    # restrictResidual / prolongIncrement
+    if p.nd > 1:
+        ec, rc = p.f.scratch(1)
+        p.op.restrictResidual(rc, p.e, p.r)
+        p.o.restrict(0)
+        assert np.array_equal(rc.download(), p.o.get("R", 1))
+        c = np.random.default_rng(5).standard_normal(rc.shape)
+        ec.upload(c); p.o.set("E", c, 1)
+        p.op.prolongIncrement(p.e, ec)
+        p.o.prolong(0)
+        assert np.array_equal(p.e.download(), p.o.get("E"))
+    # preCond
+    p.op.preCond(p.e, p.r)
+    p.o.precond(0)
+    assert np.array_equal(p.e.download(), p.o.get("E"))
+
+
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8"])
+def test_fused_smoother_bit_exact(ctx, case):
+    p = Pair(ctx, smoother=1, **CASES[case])
+    e, r = p.rand(2)
+    for d in range(p.nd):
+        opd = p.f.MGnewOp(d)
+        ed, rd = (p.e, p.r) if d == 0 else p.f.scratch(d)
+        rng = np.random.default_rng(10 + d)
+        ev, rv = rng.standard_normal(ed.shape), rng.standard_normal(ed.shape)
+        ed.upload(ev); rd.upload(rv)
+        p.o.set("E", ev, d); p.o.set("R", rv, d)
+        for its in (1, 2, 3):
+            opd.relax(ed, rd, its)
+            p.o.relax(d, its)
+            assert np.array_equal(ed.download(), p.o.get("E", d)), (d, its)
+
+
+def test_reductions_and_blas1(ctx):
+    p = Pair(ctx, **CASES["c64"])
+    e, r = p.rand(3)
+    p.load(e, r)
+    for ord_ in (0, 1, 2):
+        assert np.isclose(p.op.norm(p.r, ord_), p.o.norm(0, "R", ord_), rtol=1e-13, atol=0)
+    assert p.op.norm(p.r, 0) == np.abs(r).max()
+    assert np.isclose(p.op.dotProduct(p.e, p.r), p.o.dot(0, "E", "R"), rtol=1e-11, atol=1e-9)
+    # deterministic: same bits on every call
+    assert p.op.dotProduct(p.e, p.r) == p.op.dotProduct(p.e, p.r)
+    p.op.incr(p.e, p.r, -0.37)
+    assert np.array_equal(p.e.download(), e + (-0.37) * r)
+    p.op.scale(p.e, 1.7)
+    assert np.array_equal(p.e.download(), (e + (-0.37) * r) * 1.7)
+    p.op.axby(p.t, p.e, p.r, 0.5, -2.0)
+    assert np.array_equal(p.t.download(), 0.5 * p.e.download() + (-2.0) * r)
+    p.op.assign(p.t, p.r)
+    assert np.array_equal(p.t.download(), r)
+    p.op.setToZero(p.t)
+    assert not p.t.download().any()
+
+
+def test_level_jacobi(ctx):
+    p = Pair(ctx, **CASES["c16"])
+    e, r = p.rand(4)
+    p.load(e, r)
+    p.op.levelJacobi(p.e, p.r)
+    res = p.o.residual(0, True)
+    expect = e + 0.5 * (res * p.o.get("LAMBDA"))
+    assert np.array_equal(p.e.download(), expect)
+
+
+@pytest.mark.parametrize("case,smooth", [("c64", 2), ("c64", 4), ("c16", 2), ("neumann", 3)])
+def test_vcycle_parity(ctx, case, smooth):
+    over = dict(CASES[case], numMGsmooth=smooth)
+    p = Pair(ctx, **over)
+    rhs = p.o.get("RHS")
+    p.o.load_rhs_zero_e()
+    p.r.upload(rhs); p.op.setToZero(p.e)
+    for cyc in range(5):
+        it_o = p.o.vcycle()
+        p.f.vcycle(p.e, p.r)
+        assert p.f.last_bottom_iterations == it_o   # same bottom BiCGStab iteration count
+        eo, eg = p.o.get("E"), p.e.download()
+        assert relerr(eg, eo) < 1e-10, (cyc, relerr(eg, eo))
+        p.op.residual(p.t, p.e, p.r, True)
+        ro = np.abs(p.o.residual(0, True)).max()
+        rg = p.op.norm(p.t, 0)
+        assert abs(rg - ro) <= 1e-10 * max(ro, 1e-300) + 1e-16 * np.abs(rhs).max(), (cyc, rg, ro)
+
+
+@pytest.mark.parametrize("name,cycles,over", [
+    ("solver_32_v22", 5, dict(N=(32, 32, 32), max_grid_size=16, numMGsmooth=2)),
+    ("solver_32_v44_box8", 4, dict(N=(32, 32, 32), max_grid_size=8, numMGsmooth=4)),
+])
+def test_golden_solver_fixtures(ctx, name, cycles, over):
+    """Against the committed fixtures only (no oracle at run time except to fetch coefficients)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    P = m.make_params(dict(m.DEFAULTS, **over))
+    lvl = m.level_op_from_params(ctx, P)
+    vars_ = m.MultigridVars(ctx, P)
+    dpsi, rhs, a, b = lvl.create(), lvl.create(), lvl.create(), lvl.create()
+    vars_.set_initial_conditions(dpsi)
+    vars_.set_rhs_and_a_coef(rhs, a)
+    vars_.set_b_coef(b)
+    f = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b)
+    op = f.MGnewOp(0)
+    e, t = op.create(), op.create()
+    hist = [op.norm(rhs, 0)]
+    for _ in range(cycles):
+        f.vcycle(e, rhs)
+        op.residual(t, e, rhs, True)
+        hist.append(op.norm(t, 0))
+    assert np.allclose(hist, g["vcycle_resnorm"], rtol=1e-8, atol=1e-15 * hist[0])
+    assert relerr(e.download(), g["e_after"]) < 1e-9
+    it, st, norms = f.solve(dpsi, rhs)
+    assert it == int(g["outer_iters"]) and st == int(g["outer_status"])
+    assert relerr(dpsi.download(), g["dpsi"]) < 1e-9
+    nl, psi = m.nl_solve(ctx, P)
+    assert len(nl) == len(g["nl_dpsi_norms"])
+    assert np.allclose(nl[:2], g["nl_dpsi_norms"][:2], rtol=1e-8)
+    assert relerr(psi, g["psi"]) < 1e-10
+
+
+def test_source_terms(ctx):
+    over = CASES["c64"]
+    o = Oracle(**over)
+    o.set_initial_conditions()
+    o.set_coefs_and_rhs()
+    P = m.make_params(o.params)
+    lvl = m.level_op_from_params(ctx, P)
+    v = m.MultigridVars(ctx, P)
+    dpsi, rhs, a, b = lvl.create(), lvl.create(), lvl.create(), lvl.create()
+    v.set_initial_conditions(dpsi)
+    for c in range(8):
+        got, ref = v.download(c), o.get("MGVAR0", comp=c)
+        if c in (0, 1, 2, 3, 4, 5, 6):
+            assert np.array_equal(got, ref), m.MultigridVars.NAMES[c]   # +,-,*,/,sqrt only: bit exact
+        else:
+            assert relerr(got, ref) < 1e-14
+        gh = v.download(c, ghosted=True)
+        assert relerr(gh[1:-1, 1:-1, 1:-1], ref) < 1e-14
+        refg = o.get_ghosted("MGVAR0", 1, comp=c)
+        # face ghosts (edges / corners are never read)
+        assert relerr(gh[0, 1:-1, 1:-1], refg[0, 1:-1, 1:-1]) < 1e-13
+        assert relerr(gh[1:-1, 1:-1, -1], refg[1:-1, 1:-1, -1]) < 1e-13
+    v.set_rhs(rhs); v.set_a_coef(a); v.set_b_coef(b)
+    assert relerr(rhs.download(), o.get("RHS")) < 1e-13
+    assert relerr(a.download(), o.get("A")) < 1e-13
+    assert np.all(b.download() == 1.0)
+    r2, a2 = lvl.create(), lvl.create()
+    v.set_rhs_and_a_coef(r2, a2)
+    assert np.array_equal(r2.download(), rhs.download()) and np.array_equal(a2.download(), a.download())
+
+
+def test_outer_solve_and_update_psi(ctx):
+    over = dict(N=(32, 32, 32), max_grid_size=16, numMGsmooth=4)
+    o = Oracle(**over)
+    o.setup()
+    it_o, st_o, fn_o, norms_o = o.outer_solve()
+    P = m.make_params(o.params)
+    lvl = m.level_op_from_params(ctx, P)
+    a, b, rhs, dpsi = lvl.create(), lvl.create(), lvl.create(), lvl.create()
+    a.upload(o.get("A")); b.upload(o.get("B")); rhs.upload(o.get("RHS"))
+    f = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b)
+    it, st, norms = f.solve(dpsi, rhs)
+    assert (it, st) == (it_o, st_o)
+    assert relerr(dpsi.download(), o.get("DPSI")) < 1e-10
+    assert np.allclose(norms[:2], norms_o[:2], rtol=1e-9)
+    v = m.MultigridVars(ctx, P)
+    v.set_initial_conditions(None)
+    nrm = v.set_update_psi0(f.MGnewOp(0), dpsi)
+    nrm_o = o.update_psi0()
+    assert np.isclose(nrm, nrm_o, rtol=1e-10)
+    psig = v.download(0, ghosted=True)
+    psio = o.get_ghosted("MGVAR0", 1, comp=0)
+    assert relerr(psig[1:-1, 1:-1, 1:-1], psio[1:-1, 1:-1, 1:-1]) < 1e-12
+    for sl in ((0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1)), (slice(1, -1), 0, slice(1, -1)),
+               (slice(1, -1), slice(1, -1), -1)):
+        assert relerr(psig[sl], psio[sl]) < 1e-12
+
+
+def test_nl_solve_parity(ctx):
+    over = dict(N=(32, 32, 32), max_grid_size=16)
+    o = Oracle(**over)
+    o.set_initial_conditions()
+    nl_o = o.nl_solve()
+    nl, psi = m.nl_solve(ctx, m.make_params(o.params))
+    assert len(nl) == len(nl_o)
+    assert np.allclose(nl[:3], nl_o[:3], rtol=1e-7)
+    assert relerr(psi, o.get("MGVAR0", comp=0)) < 1e-10
+
+
+def test_trivial_kat_gpu(ctx):
+    P = m.make_params(dict(m.DEFAULTS, N=(16, 16, 16), max_grid_size=8, bh1_momentum=0.0, bh2_momentum=0.0, bh1_spin=0.0,
+                           bh2_spin=0.0, phi_amplitude=0.0))
+    nl, psi = m.nl_solve(ctx, P)
+    assert len(nl) == 1 and nl[0] == 0.0 and np.all(psi == 1.0)
+
+
+def test_fab_upload_download_roundtrip(ctx):
+    P = m.make_params(dict(m.DEFAULTS, N=(16, 16, 16), max_grid_size=8))
+    lvl = m.level_op_from_params(ctx, P)
+    f = lvl.create()
+    rng = np.random.default_rng(0)
+    full = rng.standard_normal((16, 16, 16))
+    # boxed upload: 8 ghosted FABs (3 ghosts) covering the domain, valid regions only
+    for bk in range(2):
+        for bj in range(2):
+            for bi in range(2):
+                lo = (bi * 8, bj * 8, bk * 8); hi = (lo[0] + 7, lo[1] + 7, lo[2] + 7)
+                glo = tuple(x - 3 for x in lo); ghi = tuple(x + 3 for x in hi)
+                fab = np.full((14, 14, 14), np.nan)
+                fab[3:-3, 3:-3, 3:-3] = full[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+                f.upload_fab(fab, glo, ghi, lo, hi)
+    assert np.array_equal(f.download(), full)
+    fab = np.zeros((14, 14, 14))
+    f.download_fab(fab, (5, 5, 5), (18, 18, 18))
+    assert np.array_equal(fab[:11, :11, :11], full[5:16, 5:16, 5:16]) and not fab[11:].any()
+
+
+def test_errors_mirror_reference(ctx):
+    P = m.make_params(dict(m.DEFAULTS, N=(16, 16, 16), max_grid_size=8))
+    with pytest.raises(m.MgicError, match="bogus bc flag"):
+        m.VariableCoeffPoissonOperator(ctx, (16, 16, 16), 1.0, bc_lo=(0, 5, 0))
+    lvl = m.level_op_from_params(ctx, P)
+    a = lvl.create()
+    P.coefficient_average_type = 7
+    with pytest.raises(m.MgicError, match="bad averagetype"):
+        m.VariableCoeffPoissonOperatorFactory(ctx, P, a, None)
+    other = m.VariableCoeffPoissonOperator(ctx, (8, 8, 8), 1.0)
+    with pytest.raises(m.MgicError, match="does not live on this operator"):
+        lvl.setToZero(other.create())

@@ -1,0 +1,167 @@
+"""CPU tests that pin the ORACLE (the reference ships no tests / golden vectors -- SURVEY.md 4, 8c):
+known-answer tests, the independent numpy twin, decomposition invariance, and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+import np_twin as T
+from oracle import Oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_trivial_kat_rhs_and_acoef_vanish():
+    # no momentum, no spin, no scalar field => Aij = 0, rho_grad = 0, m = 0, lap(psi=1) = 0 => rhs = aCoef = 0
+    o = Oracle(N=(16, 16, 16), max_grid_size=8, bh1_momentum=0.0, bh2_momentum=0.0, bh1_spin=0.0, bh2_spin=0.0,
+               phi_amplitude=0.0)
+    o.setup()
+    assert np.all(o.get("RHS") == 0.0)
+    assert np.all(o.get("A") == 0.0)
+    o.load_rhs_zero_e()
+    o.vcycle()
+    assert np.all(o.get("E") == 0.0)
+
+
+def test_trace_free_kat():
+    o = Oracle(N=(32, 32, 32), max_grid_size=16)
+    o.set_initial_conditions()
+    tr = o.get("MGVAR0", comp=1) + o.get("MGVAR0", comp=4) + o.get("MGVAR0", comp=6)
+    amax = max(np.abs(o.get("MGVAR0", comp=c)).max() for c in (1, 4, 6))
+    assert np.abs(tr).max() < 1e-14 * max(amax, 1.0)
+
+
+def test_survey_anchor_values_64():
+    # SURVEY.md App. D (values of the survey's independent throwaway numpy restatement)
+    o = Oracle(N=(64, 64, 64), numMGsmooth=4)
+    assert o.setup() == 4  # MG levels 64, 32, 16, 8 with 16^3 boxes
+    rhs, a = o.get("RHS"), o.get("A")
+    assert np.isclose(np.abs(rhs).max(), 5.756623e-04, rtol=1e-6)
+    assert np.isclose(a.min(), -3.126775e-03, rtol=1e-6) and np.isclose(a.max(), 2.433068e-04, rtol=1e-6)
+    assert int((a > 0).sum()) == 32
+    o.load_rhs_zero_e()
+    hist = []
+    for _ in range(3):
+        o.vcycle()
+        hist.append(np.abs(o.residual(0, True)).max())
+    assert np.allclose(hist, [3.374e-07, 3.895e-09, 2.676e-11], rtol=2e-3)
+
+
+def test_manufactured_solution_second_order():
+    # dpsi = prod sin(pi x_d / L) vanishes on the Dirichlet boundary; L dpsi = (a + lap) dpsi
+    errs = []
+    for n in (16, 32):
+        o = Oracle(N=(n, n, n), max_grid_size=8, L=1.0)
+        o.setup()
+        dx = 1.0 / n
+        x = (np.arange(n) + 0.5) * dx
+        Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+        u = np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+        a = 0.3 * np.ones_like(u)
+        o.set("A", a)
+        o.set("E", u)
+        lu = o.apply(0, True)
+        exact = (0.3 - 3 * np.pi ** 2) * u
+        errs.append(np.abs(lu - exact).max())
+    assert errs[0] / errs[1] > 3.5  # second order: ratio -> 4
+
+
+@pytest.mark.parametrize("bc", [dict(bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)), dict(bc_lo=(1, 0, 1), bc_hi=(0, 1, 0))])
+def test_decomposition_invariance_and_numpy_twin(bc):
+    n = (32, 16, 24)
+    rng = np.random.default_rng(7)
+    e = rng.standard_normal((n[2], n[1], n[0]))
+    r = rng.standard_normal((n[2], n[1], n[0]))
+    results = []
+    for box in (8, 4):
+        o = Oracle(N=n, max_grid_size=box, L=50.0, bc_value=0.0, coefficient_average_type=0, **bc)
+        o.setup()
+        o.set("E", e); o.set("R", r)
+        a, b, lam, dx = o.get("A"), o.get("B"), o.get("LAMBDA"), o.dims(0)[1]
+        res = o.residual(0, True)
+        app = o.apply(0, True)
+        o.restrict(0)
+        rc = o.get("R", 1)
+        o.relax(0, 2)
+        results.append((res, app, rc, o.get("E")))
+    for x, y in zip(*results):
+        assert np.array_equal(x, y)
+    kw = dict(bc_lo=bc["bc_lo"], bc_hi=bc["bc_hi"])
+    assert np.array_equal(results[0][0], T.residual(e, r, a, b, 1.0, -1.0, dx, **kw))
+    assert np.array_equal(results[0][1], T.apply_op(e, a, b, 1.0, -1.0, dx, **kw))
+    assert np.array_equal(results[0][2], T.restrict_residual(e, r, a, b, 1.0, -1.0, dx, **kw))
+    assert np.array_equal(results[0][3], T.relax(e, r, a, b, lam, 1.0, -1.0, dx, 2, **kw))
+
+
+def test_inhomogeneous_bc_twin():
+    n = (16, 16, 16)
+    rng = np.random.default_rng(3)
+    e = rng.standard_normal((16, 16, 16)); r = rng.standard_normal((16, 16, 16))
+    o = Oracle(N=n, max_grid_size=8, L=20.0, bc_value=0.75, bc_lo=(0, 1, 0), bc_hi=(1, 0, 0))
+    o.setup()
+    o.set("E", e); o.set("R", r)
+    a, b, dx = o.get("A"), o.get("B"), o.dims(0)[1]
+    kw = dict(bc_lo=(0, 1, 0), bc_hi=(1, 0, 0), value=0.75, homogeneous=False)
+    assert np.array_equal(o.residual(0, False), T.residual(e, r, a, b, 1.0, -1.0, dx, **kw))
+    assert np.array_equal(o.apply(0, False), T.apply_op(e, a, b, 1.0, -1.0, dx, **kw))
+
+
+def test_mg_depth_follows_box_size():
+    # Factory.cpp:168-172: depth limit = boxes coarsenable by 2^depth * s_maxCoarse
+    for box, depths in ((8, 3), (16, 4), (32, 5)):
+        o = Oracle(N=(32, 32, 32), max_grid_size=box)
+        assert o.setup() == depths
+    o = Oracle(N=(32, 32, 32), max_grid_size=16, preCondSolverDepth=1)
+    assert o.setup() == 2
+
+
+def test_coarse_average_matches_twin():
+    for typ in (0, 1):
+        o = Oracle(N=(32, 32, 32), max_grid_size=16, coefficient_average_type=typ)
+        nd = o.setup()
+        a = o.get("A")
+        for d in range(1, nd):
+            assert np.array_equal(o.get("A", d), T.coarse_average(a, 2 ** d, typ == 1))
+            assert np.all(o.get("B", d) == 1.0)
+
+
+@pytest.mark.parametrize("name,over", [
+    ("kernels_16_dirichlet", dict(N=(16, 16, 16), max_grid_size=8, L=40.0)),
+    ("kernels_24x16x32_neumann", dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1),
+                                      bc_value=0.25, coefficient_average_type=0)),
+])
+def test_golden_kernels(name, over):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    o = Oracle(**over)
+    assert o.setup() == int(g["depths"])
+    assert np.array_equal(o.get("RHS"), g["rhs"]) and np.array_equal(o.get("A"), g["a"])
+    o.set("E", g["e"]); o.set("R", g["r"])
+    assert np.array_equal(o.residual(0, True), g["residual_h"])
+    assert np.array_equal(o.residual(0, False), g["residual_i"])
+    assert np.array_equal(o.apply(0, True), g["apply_h"])
+    o.restrict(0)
+    assert np.array_equal(o.get("R", 1), g["restrict"])
+    o.relax(0, 4)
+    assert np.array_equal(o.get("E"), g["relax4"])
+
+
+@pytest.mark.parametrize("name,cycles,over", [
+    ("solver_32_v22", 5, dict(N=(32, 32, 32), max_grid_size=16, numMGsmooth=2)),
+    ("solver_32_v44_box8", 4, dict(N=(32, 32, 32), max_grid_size=8, numMGsmooth=4)),
+])
+def test_golden_solver(name, cycles, over):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    o = Oracle(**over)
+    o.setup()
+    o.load_rhs_zero_e()
+    hist = [o.norm(0, "R", 0)]
+    for _ in range(cycles):
+        o.vcycle()
+        hist.append(float(np.abs(o.residual(0, True)).max()))
+    assert np.allclose(hist, g["vcycle_resnorm"], rtol=1e-9, atol=1e-18)
+    o2 = Oracle(**over)
+    o2.set_initial_conditions()
+    nl = o2.nl_solve()
+    assert len(nl) == len(g["nl_dpsi_norms"])
+    assert np.allclose(nl[:2], g["nl_dpsi_norms"][:2], rtol=1e-8)
+    assert nl[-1] < o2.params["tolerance"]
