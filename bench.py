@@ -180,6 +180,10 @@ def run_gpu(args):
     if world > 1:
         from mg_ic_code_b200 import comm
         comm.attach(ctx, dist)
+    if args.fused_cfg is not None:
+        ctx.set_option("fused_cfg", args.fused_cfg)
+    if args.fused_min_cells is not None:
+        ctx.set_option("fused_min_cells", args.fused_min_cells)
 
     n = args.n
     # weak scaling (C5): every GPU owns n^2 x n planes; the global domain grows in z
@@ -317,6 +321,8 @@ def main():
     ap.add_argument("--keep-b", action="store_true", help="stream bCoef even though it is identically 1")
     ap.add_argument("--smoother", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fused-cfg", type=int, default=None, help="tile shape of the fused sweep (tuning)")
+    ap.add_argument("--fused-min-cells", type=int, default=None, help="levels below this use the per-colour kernel (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -86,6 +86,9 @@ int mgic_ctx_set_stream(mgic_ctx *, void *cuda_stream);
 void *mgic_ctx_stream(mgic_ctx *);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long long mgic_ctx_launch_count(mgic_ctx *);
+/* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
+ * per-colour kernel).  Results do not depend on them. */
+int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);
 /* per-launch CUDA-event timing of the dominant kernel (the finest level's GSRB launches): arm with enable = 1,
  * run, then read the number of timed launches and their summed device time (bench.py roofline) */
 int mgic_ctx_profile(mgic_ctx *, int enable);

@@ -92,6 +92,13 @@ extern "C" int mgic_ctx_set_rank(mgic_ctx *c, int rank, int nranks) {
   return MGIC_OK;
 }
 
+extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long value) {
+  MGIC_REQUIRE(c && name, "NULL argument");
+  if (!strcmp(name, "fused_cfg")) c->fusedCfg = (int)value;
+  else if (!strcmp(name, "fused_min_cells")) c->fusedMinCells = value;
+  else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
+  return MGIC_OK;
+}
 extern "C" int mgic_ctx_profile(mgic_ctx *c, int enable) {
   MGIC_REQUIRE(c, "ctx is NULL");
   MGIC_CUDA(cudaStreamSynchronize(c->stream));

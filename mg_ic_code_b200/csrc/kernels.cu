@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "mgic_internal.h"
+#include "mgic_device.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -27,13 +28,6 @@ inline int post_launch(mgic_ctx *c, const char *what) {
 }
 
 // ---- stencil helpers --------------------------------------------------------------------------------------
-// The CHF_DTERM block common to the four operator kernels (VariableCoeffPoissonOperatorF.ChF:111-120,
-// 219-228, 322-330, 415-424): each bracket left to right, brackets added in x, y, z order.
-__device__ __forceinline__ double lap7(double c, double xm, double xp, double ym, double yp, double zm, double zp) {
-  const double t = 2.0 * c;
-  return ((xp + xm) - t) + ((yp + ym) - t) + ((zp + zm) - t);
-}
-
 // Neighbour values of cell (i,j,k) (local indices) with the physical BC folded in.
 struct Nb { double xm, xp, ym, yp, zm, zp; };
 
@@ -71,12 +65,8 @@ __global__ void __launch_bounds__(256) k_gsrb_color(Geom g, BCk bc, double *__re
   const long long idx = i + j * g.sy + k * g.sz;
   const double c = phi[idx];
   const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
-  double lof = alpha * a[idx] * c;                       // :107-108
-  double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);  // :111-120
-  l = l * dxinv;                                         // :122  (ldpsi*dxinv)*bCoef
-  if (HAS_B) l = l * b[idx];
-  lof = lof - beta * l;                                  // :124
-  phi[idx] = c - lam[idx] * (lof - rhs[idx]);            // :127-128
+  phi[idx] = gsrb_point<HAS_B>(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp, a[idx], HAS_B ? b[idx] : 1.0, lam[idx], rhs[idx], alpha, beta,
+                               dxinv);
 }
 
 // ---- applyOp / residual: VCCOMPUTEOP3D (:181-237), VCCOMPUTERES3D (:283-339) --------------------------------

@@ -68,6 +68,9 @@ struct mgic_ctx {
   int (*allreduce)(mgic_ctx *, double *hostvals, int n, int op /*0 sum 1 max*/) = nullptr;
   void *comm = nullptr;
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
+  // tuning knobs (mgic_ctx_set_option)
+  int fusedCfg = 1;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
+  long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
 };

@@ -32,6 +32,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         check(self.L.mgic_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, name, value):
+        check(self.L.mgic_ctx_set_option(self.h, name.encode(), int(value)))
+
     def profile(self, enable=True):
         """arm / disarm CUDA-event timing of the finest-level GSRB launches"""
         check(self.L.mgic_ctx_profile(self.h, int(enable)))

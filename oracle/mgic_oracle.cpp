@@ -829,8 +829,8 @@ static LevelData *fieldOf(orc_problem *pb, int depth, int field) {
   switch (field) {
     case ORC_F_E: return &pb->e[depth];
     case ORC_F_R: return &pb->r[depth];
-    case ORC_F_A: return pb->ops[depth]->aCoef;
-    case ORC_F_B: return pb->ops[depth]->bCoef;
+    case ORC_F_A: return (depth == 0 || pb->ops.empty()) ? &pb->aCoef : pb->ops[depth]->aCoef;
+    case ORC_F_B: return (depth == 0 || pb->ops.empty()) ? &pb->bCoef : pb->ops[depth]->bCoef;
     case ORC_F_LAMBDA: return &pb->ops[depth]->lambda;
     case ORC_F_TMP: return &pb->tmp[depth];
     case ORC_F_DPSI: return &pb->dpsi;
@@ -1095,7 +1095,7 @@ void orc_set_field(orc_problem *pb, int depth, int field, const double *in) {
       for (int j = b.lo[1]; j <= b.hi[1]; j++)
         for (int i = b.lo[0]; i <= b.hi[0]; i++) f(i, j, k, comp) = in[i + nx * (j + ny * (long)k)];
   }
-  if (field == ORC_F_A || field == ORC_F_B) pb->ops[depth]->lambdaNeedsResetting = true;
+  if ((field == ORC_F_A || field == ORC_F_B) && depth < (int)pb->ops.size()) pb->ops[depth]->lambdaNeedsResetting = true;
 }
 
 void orc_op_relax(orc_problem *pb, int d, int iterations) { pb->ops[d]->relax(pb->e[d], pb->r[d], iterations); }

@@ -22,6 +22,7 @@ CASES = {
                     coefficient_average_type=0),
     "c64": dict(N=(64, 64, 64), max_grid_size=16),
     "c8": dict(N=(8, 8, 8), max_grid_size=8, L=10.0),
+    "wide": dict(N=(160, 48, 40), max_grid_size=8, L=100.0),
 }
 
 
@@ -103,21 +104,42 @@ def test_kernels_bit_exact(ctx, case, keep_b):
     assert np.array_equal(p.e.download(), p.o.get("E"))
 
 
-@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8"])
-def test_fused_smoother_bit_exact(ctx, case):
-    p = Pair(ctx, smoother=1, **CASES[case])
-    e, r = p.rand(2)
-    for d in range(p.nd):
-        opd = p.f.MGnewOp(d)
-        ed, rd = (p.e, p.r) if d == 0 else p.f.scratch(d)
-        rng = np.random.default_rng(10 + d)
-        ev, rv = rng.standard_normal(ed.shape), rng.standard_normal(ed.shape)
-        ed.upload(ev); rd.upload(rv)
-        p.o.set("E", ev, d); p.o.set("R", rv, d)
-        for its in (1, 2, 3):
-            opd.relax(ed, rd, its)
-            p.o.relax(d, its)
-            assert np.array_equal(ed.download(), p.o.get("E", d)), (d, its)
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
+def test_fused_smoother_bit_exact(ctx, case, cfg):
+    """fused red+black plane-streaming sweep (TMA-staged halo'd planes) == per-colour oracle sweeps, every tile shape,
+    on every MG depth (tiles larger than the level, ragged tiles, z chunks)."""
+    ctx.set_option("fused_min_cells", 0)
+    ctx.set_option("fused_cfg", cfg)
+    try:
+        p = Pair(ctx, smoother=1, **CASES[case])
+        for d in range(p.nd):
+            opd = p.f.MGnewOp(d)
+            ed, rd = (p.e, p.r) if d == 0 else p.f.scratch(d)
+            rng = np.random.default_rng(10 + d)
+            ev, rv = rng.standard_normal(ed.shape), rng.standard_normal(ed.shape)
+            ed.upload(ev); rd.upload(rv)
+            p.o.set("E", ev, d); p.o.set("R", rv, d)
+            for its in (1, 2, 3):
+                opd.relax(ed, rd, its)
+                p.o.relax(d, its)
+                assert np.array_equal(ed.download(), p.o.get("E", d)), (d, its)
+    finally:
+        ctx.set_option("fused_min_cells", 2097152)
+        ctx.set_option("fused_cfg", 1)
+
+
+def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
+    ctx.set_option("fused_min_cells", 0)
+    try:
+        p = Pair(ctx, keep_b=True, smoother=1, **CASES["neumann"])
+        e, r = p.rand(9)
+        p.load(e, r)
+        p.op.relax(p.e, p.r, 2)
+        p.o.relax(0, 2)
+        assert np.array_equal(p.e.download(), p.o.get("E"))
+    finally:
+        ctx.set_option("fused_min_cells", 2097152)
 
 
 def test_reductions_and_blas1(ctx):
