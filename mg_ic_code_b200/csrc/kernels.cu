@@ -27,28 +27,6 @@ inline int post_launch(mgic_ctx *c, const char *what) {
   return MGIC_OK;
 }
 
-// ---- stencil helpers --------------------------------------------------------------------------------------
-// Neighbour values of cell (i,j,k) (local indices) with the physical BC folded in.
-struct Nb { double xm, xp, ym, yp, zm, zp; };
-
-__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *__restrict__ p, long long wrapIdx) {
-  // Dirichlet / Neumann: a*c + b  (DiriBC order 1: 2v - near;  NeumBC: near + sign*dx*v  [Chombo BCFunc])
-  return bc.type[f] == MGIC_BC_PERIODIC ? p[wrapIdx] : bc.a[f] * c + bc.b[f];
-}
-
-__device__ __forceinline__ Nb neighbours(const double *__restrict__ p, long long idx, int i, int j, int k, const Geom &g,
-                                         const BCk &bc, double c) {
-  Nb n;
-  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1));
-  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1));
-  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy);
-  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy);
-  // z: ghost planes exist in memory; MGIC_FACE_INTERIOR means they hold the neighbour slab's planes
-  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz);
-  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz);
-  return n;
-}
-
 // ---- GSRB colour pass: GSRBHELMHOLTZVC3D (VariableCoeffPoissonOperatorF.ChF:56-139) ------------------------
 // One thread per cell of the colour: i = 2t + parity so that (i + j + k_global + color) is even (:98-106).
 template <bool HAS_B>

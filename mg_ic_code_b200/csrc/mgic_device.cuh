@@ -3,6 +3,8 @@
 #ifndef MGIC_DEVICE_CUH
 #define MGIC_DEVICE_CUH
 
+#include "mgic_internal.h"
+
 // The CHF_DTERM block common to the four operator kernels (VariableCoeffPoissonOperatorF.ChF:111-120,
 // 219-228, 322-330, 415-424): each bracket left to right, brackets added in x, y, z order.
 __device__ __forceinline__ double lap7(double c, double xm, double xp, double ym, double yp, double zm, double zp) {
@@ -21,4 +23,26 @@ __device__ __forceinline__ double gsrb_point(double c, double xm, double xp, dou
   lof = lof - beta * l;                     // :124
   return c - lv * (lof - rv);               // :127-128
 }
+
+// Neighbour values of cell (i,j,k) (local indices) with the physical BC folded in.
+struct Nb { double xm, xp, ym, yp, zm, zp; };
+
+__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *p, long long wrapIdx) {
+  // Dirichlet / Neumann: a*c + b  (DiriBC order 1: 2v - near;  NeumBC: near + sign*dx*v  [Chombo BCFunc])
+  return bc.type[f] == MGIC_BC_PERIODIC ? p[wrapIdx] : bc.a[f] * c + bc.b[f];
+}
+
+__device__ __forceinline__ Nb neighbours(const double *p, long long idx, int i, int j, int k, const Geom &g,
+                                         const BCk &bc, double c) {
+  Nb n;
+  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1));
+  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1));
+  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy);
+  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy);
+  // z: ghost planes exist in memory; MGIC_FACE_INTERIOR means they hold the neighbour slab's planes
+  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz);
+  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz);
+  return n;
+}
+
 #endif

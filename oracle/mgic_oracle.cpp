@@ -1076,9 +1076,11 @@ void orc_get_field_ghosted(orc_problem *pb, int depth, int field, int ng, double
     for (int k = g.lo[2]; k <= g.hi[2]; k++)
       for (int j = g.lo[1]; j <= g.hi[1]; j++)
         for (int i = g.lo[0]; i <= g.hi[0]; i++) {
-          bool inValid = (i >= v.lo[0] && i <= v.hi[0] && j >= v.lo[1] && j <= v.hi[1] && k >= v.lo[2] && k <= v.hi[2]);
-          bool inDom = (i >= dom.lo[0] && i <= dom.hi[0] && j >= dom.lo[1] && j <= dom.hi[1] && k >= dom.lo[2] && k <= dom.hi[2]);
-          if (inValid || !inDom) out[(i + ng) + nx * ((j + ng) + ny * (long)(k + ng))] = f(i, j, k, comp);
+          // a cell outside the domain is reported by the box that owns the nearest domain cell
+          int ci = std::min(std::max(i, dom.lo[0]), dom.hi[0]), cj = std::min(std::max(j, dom.lo[1]), dom.hi[1]),
+              ck = std::min(std::max(k, dom.lo[2]), dom.hi[2]);
+          bool owner = (ci >= v.lo[0] && ci <= v.hi[0] && cj >= v.lo[1] && cj <= v.hi[1] && ck >= v.lo[2] && ck <= v.hi[2]);
+          if (owner) out[(i + ng) + nx * ((j + ng) + ny * (long)(k + ng))] = f(i, j, k, comp);
         }
   }
 }
