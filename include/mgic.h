@@ -87,7 +87,9 @@ void *mgic_ctx_stream(mgic_ctx *);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long long mgic_ctx_launch_count(mgic_ctx *);
 /* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
- * per-colour kernel).  Results do not depend on them. */
+ * per-colour kernel), "bottom_kernel" (1: bottom BiCGStab as one persistent kernel, 0: host driven), "use_graph" (1: V-cycles
+ * replayed as CUDA graphs).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of
+ * the bottom solver's dot products. */
 int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);
 /* per-launch CUDA-event timing of the dominant kernel (the finest level's GSRB launches): arm with enable = 1,
  * run, then read the number of timed launches and their summed device time (bench.py roofline) */
@@ -174,7 +176,7 @@ int mgic_mg_refresh_coefs(mgic_mg *);
 /* [Chombo] MultiGrid::oneCycle (homogeneous) == cycle(0, e, r): relax/restrict/recurse/prolong/relax + bottom solve */
 int mgic_mg_vcycle(mgic_mg *, mgic_field *e, const mgic_field *r);
 int mgic_mg_bottom_solve(mgic_mg *, mgic_field *e, const mgic_field *r, int *iterations);
-int mgic_mg_last_bottom_iterations(const mgic_mg *);
+int mgic_mg_last_bottom_iterations(mgic_mg *);
 /* select the smoother implementation on every depth (see mgic_op_set_smoother) */
 int mgic_mg_set_smoother(mgic_mg *, int kind);
 

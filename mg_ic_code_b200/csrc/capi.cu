@@ -96,6 +96,8 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   MGIC_REQUIRE(c && name, "NULL argument");
   if (!strcmp(name, "fused_cfg")) c->fusedCfg = (int)value;
   else if (!strcmp(name, "fused_min_cells")) c->fusedMinCells = value;
+  else if (!strcmp(name, "bottom_kernel")) c->bottomKernel = (int)value;
+  else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
@@ -601,7 +603,12 @@ struct mgic_mg {
   bool bIsOne = false;
   int lastBottomIters = 0;
   BiCGWork bottomWork, outerWork;
-  mgic_field *pc_e = nullptr;  // unused placeholder for future graph capture
+  int *d_bottomOut = nullptr;   // device {iterations, status} of the last persistent bottom solve
+  bool bottomOnDevice = false;
+  // V-cycle graphs, keyed by the (correction, residual) arrays they were captured for
+  struct VGraph { const void *e, *r; cudaGraphExec_t exec; long long launches; };
+  std::vector<VGraph> graphs;
+  bool graphBroken = false;
 };
 
 static int mg_coarsen_coefs(mgic_mg *mg) {
@@ -695,6 +702,8 @@ extern "C" int mgic_mg_destroy(mgic_mg *mg) {
   cudaStreamSynchronize(mg->ctx->stream);
   mg->bottomWork.release();
   mg->outerWork.release();
+  for (auto &g : mg->graphs) cudaGraphExecDestroy(g.exec);
+  cudaFree(mg->d_bottomOut);
   for (int d = 0; d < mg->nd; d++) {
     mgic_field_destroy(mg->e[d]); mgic_field_destroy(mg->r[d]);
     mgic_field_destroy(mg->aOwn[d]); mgic_field_destroy(mg->bOwn[d]);
@@ -732,17 +741,39 @@ struct BottomLin : LinOp {
 
 extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field *r, int *iterations) {
   MGIC_REQUIRE(mg && e && r, "NULL argument");
+  mgic_op *op = mg->ops.back();
+  REQ_SHAPE(op, e); REQ_SHAPE(op, r);
+  if (mg->ctx->bottomKernel && mg->ctx->nranks == 1) {
+    // one persistent cooperative kernel (bottom.cu); iteration count stays on the device until asked for
+    MGIC_TRY(mg->bottomWork.alloc(op));
+    MGIC_TRY(mgic_op_reset_lambda(op));
+    if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
+    MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
+    mg->bottomOnDevice = true;
+    if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
+    return MGIC_OK;
+  }
   BottomLin L;
-  L.op = mg->ops.back();
+  L.op = op;
   BiCGParams bp;
   bp.homogeneous = true;  // [Chombo] MultiGrid::define: m_bottomSolver->define(op, true)
   int it = 0, st = 0;
   MGIC_TRY(bicgstab(L, mg->bottomWork, e, r, bp, &it, &st, nullptr, 0));
   mg->lastBottomIters = it;
+  mg->bottomOnDevice = false;
   if (iterations) *iterations = it;
   return MGIC_OK;
 }
-extern "C" int mgic_mg_last_bottom_iterations(const mgic_mg *mg) { return mg ? mg->lastBottomIters : 0; }
+extern "C" int mgic_mg_last_bottom_iterations(mgic_mg *mg) {
+  if (!mg) return 0;
+  if (mg->bottomOnDevice && mg->d_bottomOut) {
+    int h[2] = {0, 0};
+    if (cudaStreamSynchronize(mg->ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(h, mg->d_bottomOut, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    mg->lastBottomIters = h[0];
+  }
+  return mg->lastBottomIters;
+}
 
 // [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
 static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r) {
@@ -762,11 +793,70 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r) 
   return mgic_op_relax(op, e, r, S);
 }
 
+// One V-cycle, replayed as a CUDA graph when possible: the cycle is a fixed launch sequence (the bottom solve is a
+// single kernel), so it is captured once per (correction, residual) pair and afterwards costs one graph launch.
+static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
+  mgic_ctx *c = mg->ctx;
+  const bool graphable = c->useGraph && c->bottomKernel && c->nranks == 1 && !c->profiling && !mg->graphBroken;
+  if (!graphable) return mg_cycle(mg, 0, e, r);
+  for (auto &g : mg->graphs)
+    if (g.e == e->p && g.r == r->p) {
+      MGIC_CUDA(cudaGraphLaunch(g.exec, c->stream));
+      c->launches += g.launches;
+      mg->bottomOnDevice = true;
+      return MGIC_OK;
+    }
+  // everything the cycle allocates lazily must exist before capture
+  MGIC_TRY(mg->bottomWork.alloc(mg->ops.back()));
+  if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
+  for (auto *o : mg->ops) {
+    MGIC_TRY(mgic_op_reset_lambda(o));
+    if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
+  }
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  // ping-pong state (fused sweeps swap array pointers inside the field handles) must be the same after the cycle
+  std::vector<std::pair<mgic_field *, double *>> saved;
+  saved.emplace_back(e, e->base);
+  for (int d = 0; d < mg->nd; d++) {
+    if (mg->e[d]) saved.emplace_back(mg->e[d], mg->e[d]->base);
+    saved.emplace_back(mg->ops[d]->scratch, mg->ops[d]->scratch->base);
+  }
+  const long long l0 = c->launches;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  int rc = MGIC_OK;
+  if (ok) {
+    rc = mg_cycle(mg, 0, e, r);
+    ok = (cudaStreamEndCapture(c->stream, &graph) == cudaSuccess) && rc == MGIC_OK && graph;
+  }
+  const long long nl = c->launches - l0;
+  c->launches = l0;
+  for (auto &sv : saved) ok = ok && (sv.first->base == sv.second);
+  if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    // not capturable (e.g. an odd number of fused sweeps on some level): restore the handles, run eagerly from now on
+    cudaGetLastError();
+    for (auto &sv : saved) {
+      sv.first->base = sv.second;
+      sv.first->p = sv.second + (long long)MGIC_GZ * sv.first->sz;
+    }
+    mg->graphBroken = true;
+    return mg_cycle(mg, 0, e, r);
+  }
+  mg->graphs.push_back({e->p, r->p, exec, nl});
+  MGIC_CUDA(cudaGraphLaunch(exec, c->stream));
+  c->launches += nl;
+  mg->bottomOnDevice = true;
+  return MGIC_OK;
+}
+
 extern "C" int mgic_mg_vcycle(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
   MGIC_REQUIRE(mg && e && r, "NULL argument");
   REQ_SHAPE(mg->ops[0], e); REQ_SHAPE(mg->ops[0], r);
   mg->lastBottomIters = 0;
-  return mg_cycle(mg, 0, e, r);
+  return vcycle_run(mg, e, r);
 }
 
 // f1: [Chombo] MultilevelLinearOp::preCond on one AMR level = zero cor, numMGIterations V-cycles
@@ -774,7 +864,7 @@ struct OuterLin : LinOp {
   mgic_mg *mg;
   int preCond(mgic_field *cor, mgic_field *res) override {
     MGIC_TRY(mgic_op_set_to_zero(op, cor));
-    for (int it = 0; it < mg->P.numMGIterations; it++) MGIC_TRY(mg_cycle(mg, 0, cor, res));
+    for (int it = 0; it < mg->P.numMGIterations; it++) MGIC_TRY(vcycle_run(mg, cor, res));
     return MGIC_OK;
   }
 };

@@ -60,34 +60,102 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-enum : unsigned {
-  F_DOM = 1u,      // pair inside the domain
-  F_ROWRED = 2u,   // row inside the red region (tile grown by one) and the domain
-  F_TILE = 4u,     // pair inside the tile (black update + output)
-  F_PFIRST = 8u,   // leftmost pair of the region: only its element 1 is in the red region
-  F_PLAST = 16u,   // rightmost pair: only element 0
-  F_X0 = 32u, F_XN = 64u, F_Y0 = 128u, F_YN = 256u,  // pair touches a physical x / y face
-  F_YODD = 512u
+// Geometry of one CTA: a warp is one row of the halo'd region, a lane is one x-pair (16 bytes), so the colour of
+// a lane's red cell is warp-uniform and compiled in (template parameter E): no per-thread selects.
+//   region  = RW x (TY+4) cells, RW = 64 (32 pairs), staged by TMA           [tile grown by 2]
+//   threads = rows 1 .. TY+2 of the region (TY+2 warps)                       [tile grown by 1 = red region]
+//   tile    = rows 2 .. TY+1, lanes 1 .. 30  => TX = 60 cells x TY rows of output per plane
+constexpr int TX = 60, RW = 64;
+
+template <int TY, int NSLOT, bool HAS_B>
+struct Fused {
+  static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, NT = 32 * NW;
+  static constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double);
+  static constexpr size_t SMEM = (size_t)NSLOT * PLANE_BYTES + 2 * NW * 32 * sizeof(double) + NSLOT * sizeof(uint64_t);
+
+  // per-thread state
+  double2 c0, c1, c2, c3;        // the lane's pair in planes kr-2, kr-1, kr, kr+1 (reds already updated where due)
+  double2 ca, cl, cr, cb;        // coefficient pairs of plane kr (aCoef, lambda, rhs, bCoef)
+  double sa, sl, sr, sb;         // black-cell halves of plane kr-1
+  const double *dense;           // TMA slot of plane kr
+  double *redw;                  // red buffer written this step (plane kr)
+  const double *redr;            // red buffer of plane kr-1
+  int lane, w, s;
+  bool inDom, tile, anyxy, bx0, bxn, by0, byn;
+
+  template <int E>
+  __device__ __forceinline__ void step(const Geom &g, const BCk &bc, double alpha, double beta, double dxinv, int kr, bool doRed,
+                                       bool doBlack, bool zloPhys, bool zhiPhys, double *outp) {
+    constexpr unsigned FULL = 0xffffffffu;
+    if (doRed) {
+      const double c = E ? c2.y : c2.x;
+      // x neighbours: one lives in the pair, the other in the neighbouring lane's pair (old black value)
+      const double xo = E ? __shfl_down_sync(FULL, c2.x, 1) : __shfl_up_sync(FULL, c2.y, 1);
+      double xm = E ? c2.x : xo, xp = E ? xo : c2.y;
+      double ym = dense[s + E - RW], yp = dense[s + E + RW];
+      double zm = E ? c1.y : c1.x, zp = E ? c3.y : c3.x;
+      if (anyxy) {
+        if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
+        if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
+        if (by0) ym = bc.a[2] * c + bc.b[2];
+        if (byn) yp = bc.a[3] * c + bc.b[3];
+      }
+      if (kr == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
+      if (kr == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+      const bool act = inDom && !(E == 0 && lane == 0) && !(E == 1 && lane == 31);
+      double nv = c;
+      if (act)
+        nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, E ? ca.y : ca.x, HAS_B ? (E ? cb.y : cb.x) : 1.0, E ? cl.y : cl.x,
+                               E ? cr.y : cr.x, alpha, beta, dxinv);
+      if (E) c2.y = nv; else c2.x = nv;
+      redw[w * 32 + lane] = nv;
+    }
+    if (doBlack) {
+      const int kb = kr - 1;
+      const double c = E ? c1.y : c1.x;
+      const double xo = E ? __shfl_down_sync(FULL, c1.x, 1) : __shfl_up_sync(FULL, c1.y, 1);  // neighbour pair's new red
+      double xm = E ? c1.x : xo, xp = E ? xo : c1.y;
+      if (tile) {
+        double ym = redr[(w - 1) * 32 + lane], yp = redr[(w + 1) * 32 + lane];
+        double zm = E ? c0.y : c0.x, zp = E ? c2.y : c2.x;
+        if (anyxy) {
+          if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
+          if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
+          if (by0) ym = bc.a[2] * c + bc.b[2];
+          if (byn) yp = bc.a[3] * c + bc.b[3];
+        }
+        if (kb == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
+        if (kb == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+        const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, sa, HAS_B ? sb : 1.0, sl, sr, alpha, beta, dxinv);
+        const double2 o = E ? make_double2(c1.x, nv) : make_double2(nv, c1.y);
+        *reinterpret_cast<double2 *>(outp) = o;
+      }
+    }
+    if (doRed) {  // keep the black-cell halves of plane kr for the next step
+      sa = E ? ca.x : ca.y; sl = E ? cl.x : cl.y; sr = E ? cr.x : cr.y;
+      if (HAS_B) sb = E ? cb.x : cb.y;
+    }
+  }
 };
 
-template <int TX, int TY, int NT, int NSLOT, bool HAS_B>
-__global__ void __launch_bounds__(NT) k_gsrb_fused(const __grid_constant__ CUtensorMap tmap, Geom g, BCk bc,
-                                                   double *__restrict__ out, const double *__restrict__ rhs,
-                                                   const double *__restrict__ a, const double *__restrict__ b,
-                                                   const double *__restrict__ lam, double alpha, double beta, double dxinv,
-                                                   int zchunk, int redLo, int redHi) {
-  constexpr int PR = TX / 2 + 2, RW = 2 * PR, RR = TY + 4, PLANE = RW * RR, NI = PR * RR, CPT = (NI + NT - 1) / NT;
-  constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double);
+template <int TY, int NSLOT, bool HAS_B, int MINB>
+__global__ void __launch_bounds__(32 * (TY + 2), MINB)
+k_gsrb_fused(const __grid_constant__ CUtensorMap tmap, Geom g, BCk bc, double *__restrict__ out, const double *__restrict__ rhs,
+             const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ lam, double alpha, double beta,
+             double dxinv, int zchunk, int redLo, int redHi) {
+  using F = Fused<TY, NSLOT, HAS_B>;
+  constexpr int PLANE = F::PLANE, NW = F::NW;
+  constexpr uint32_t PLANE_BYTES = F::PLANE_BYTES;
   static_assert(PLANE_BYTES % 128 == 0, "TMA destination slots must stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *planes = reinterpret_cast<double *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * PLANE_BYTES);
+  double *redbuf = reinterpret_cast<double *>(smem_raw + (size_t)NSLOT * PLANE_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * PLANE_BYTES + 2 * NW * 32 * sizeof(double));
 
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int zs = blockIdx.z * zchunk, ze = min(zs + zchunk, g.nz);
-  const int pfirst = zs - 2;                    // first plane staged
-  const int plast = ze + 1;                     // last plane staged
+  const int pfirst = zs - 2, plast = ze + 1;  // planes staged
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; s++) mbar_init(&full[s], 1);
@@ -96,145 +164,87 @@ __global__ void __launch_bounds__(NT) k_gsrb_fused(const __grid_constant__ CUten
   __syncthreads();
   if (tid == 0) {
     for (int p = pfirst; p < pfirst + NSLOT && p <= plast; p++) {
-      const int s = p - pfirst;
-      mbar_arrive_expect_tx(&full[s], PLANE_BYTES);
-      tma_load_3d(planes + (size_t)s * PLANE, &tmap, &full[s], x0 - 2, y0 - 2, p + MGIC_GZ);
+      const int sl = p - pfirst;
+      mbar_arrive_expect_tx(&full[sl], PLANE_BYTES);
+      tma_load_3d(planes + (size_t)sl * PLANE, &tmap, &full[sl], x0 - 2, y0 - 2, p + MGIC_GZ);
     }
   }
 
-  // the thread's pair columns (fixed for the whole march)
-  int sidx[CPT];
-  long long gofs[CPT];
-  unsigned flg[CPT];
-#pragma unroll
-  for (int m = 0; m < CPT; m++) {
-    const int q = tid + m * NT;
-    const int rr = q / PR, pp = q - rr * PR;
-    const int x = x0 - 2 + 2 * pp, y = y0 - 2 + rr;
-    unsigned f = 0;
-    if (q < NI && x >= 0 && x + 1 < g.nx && y >= 0 && y < g.ny) {
-      f |= F_DOM;
-      if (rr >= 1 && rr <= RR - 2) f |= F_ROWRED;
-      if (rr >= 2 && rr <= RR - 3 && pp >= 1 && pp <= PR - 2) f |= F_TILE;
-      if (pp == 0) f |= F_PFIRST;
-      if (pp == PR - 1) f |= F_PLAST;
-      if (x == 0) f |= F_X0;
-      if (x == g.nx - 2) f |= F_XN;
-      if (y == 0) f |= F_Y0;
-      if (y == g.ny - 1) f |= F_YN;
-      if (y & 1) f |= F_YODD;
-    }
-    flg[m] = f;
-    sidx[m] = rr * RW + 2 * pp;
-    gofs[m] = x + (long long)y * g.sy;
-  }
-  // black-cell halves of the coefficient pairs of the plane whose red update ran one step earlier
-  double st_a[CPT], st_l[CPT], st_r[CPT], st_b[HAS_B ? CPT : 1];
-
+  F st;
+  st.lane = tid & 31;
+  st.w = tid >> 5;
+  const int rr = st.w + 1;
+  const int x = x0 - 2 + 2 * st.lane, y = y0 - 2 + rr;
+  st.inDom = (x >= 0 && x + 1 < g.nx && y >= 0 && y < g.ny);
+  st.tile = st.inDom && st.w >= 1 && st.w <= TY && st.lane >= 1 && st.lane <= 30;
+  st.bx0 = (x == 0); st.bxn = (x == g.nx - 2); st.by0 = (y == 0); st.byn = (y == g.ny - 1);
+  st.anyxy = st.bx0 || st.bxn || st.by0 || st.byn;
+  st.s = rr * RW + 2 * st.lane;
+  const int yodd = y & 1;
+  const long long gofs = x + (long long)y * g.sy;
   const bool zloPhys = bc.type[4] != MGIC_FACE_INTERIOR, zhiPhys = bc.type[5] != MGIC_FACE_INTERIOR;
+  const double2 zero2 = make_double2(0.0, 0.0);
+  st.c0 = zero2; st.sa = st.sl = st.sr = st.sb = 0.0;
+  st.ca = st.cl = st.cr = st.cb = zero2;
+
+  // prologue: the lane's pairs of planes zs-2 and zs-1; coefficient pairs of the first red plane
+  mbar_wait(&full[0], 0);
+  st.c1 = *reinterpret_cast<const double2 *>(planes + st.s);
+  if (plast >= pfirst + 1) mbar_wait(&full[1 % NSLOT], 0);
+  st.c2 = *reinterpret_cast<const double2 *>(planes + (size_t)(1 % NSLOT) * PLANE + st.s);
+  {
+    const int k = zs - 1;
+    if (st.inDom && k >= redLo && k <= redHi) {
+      const long long gi = gofs + (long long)k * g.sz;
+      st.ca = *reinterpret_cast<const double2 *>(a + gi);
+      st.cl = *reinterpret_cast<const double2 *>(lam + gi);
+      st.cr = *reinterpret_cast<const double2 *>(rhs + gi);
+      if (HAS_B) st.cb = *reinterpret_cast<const double2 *>(b + gi);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && pfirst + NSLOT <= plast) {  // slot of plane zs-2 is free again
+    mbar_arrive_expect_tx(&full[0], PLANE_BYTES);
+    tma_load_3d(planes, &tmap, &full[0], x0 - 2, y0 - 2, pfirst + NSLOT + MGIC_GZ);
+  }
 
   for (int kr = zs - 1; kr <= ze; kr++) {
-    const int kb = kr - 1;
     const bool doRed = (kr >= redLo && kr <= redHi);
-    const bool doBlack = (kb >= zs && kb < ze);
-    // wait for the planes this step reads for the first time
-    if (kr == zs - 1) {
-      for (int p = pfirst; p <= kr; p++) mbar_wait(&full[(p - pfirst) % NSLOT], ((p - pfirst) / NSLOT) & 1);
+    const bool doBlack = (kr - 1 >= zs && kr - 1 < ze);
+    // prefetch the coefficient pairs of plane kr+1 (consumed by the next step's red update)
+    double2 na = zero2, nl = zero2, nr = zero2, nb = zero2;
+    const bool nextRed = (kr + 1 >= redLo && kr + 1 <= redHi && kr + 1 <= ze);
+    if (st.inDom && nextRed) {
+      const long long gi = gofs + (long long)(kr + 1) * g.sz;
+      na = *reinterpret_cast<const double2 *>(a + gi);
+      nl = *reinterpret_cast<const double2 *>(lam + gi);
+      nr = *reinterpret_cast<const double2 *>(rhs + gi);
+      if (HAS_B) nb = *reinterpret_cast<const double2 *>(b + gi);
     }
-    if (kr + 1 <= plast) mbar_wait(&full[(kr + 1 - pfirst) % NSLOT], ((kr + 1 - pfirst) / NSLOT) & 1);
-
-    double *P = planes + (size_t)((kr - pfirst) % NSLOT) * PLANE;                 // plane kr
-    double *Pm = planes + (size_t)((kr - 1 - pfirst + NSLOT) % NSLOT) * PLANE;    // plane kr-1
-    double *Pp = planes + (size_t)((kr + 1 - pfirst) % NSLOT) * PLANE;            // plane kr+1
-    const int par = (kr + g.k0) & 1;
-
-    // ---------------- RED: plane kr, in place in shared memory ------------------------------------------------
-    double nx_a[CPT], nx_l[CPT], nx_r[CPT], nx_b[HAS_B ? CPT : 1];
-    if (doRed) {
-#pragma unroll
-      for (int m = 0; m < CPT; m++) {
-        const unsigned f = flg[m];
-        const int e = (((f & F_YODD) ? 1 : 0) + par) & 1;   // red element of the pair: (x + e + y + k) even, x even
-        const bool act = (f & F_DOM) && (f & F_ROWRED) && !((f & F_PFIRST) && e == 0) && !((f & F_PLAST) && e == 1);
-        if (f & F_DOM) {
-          // coefficient pair of plane kr (kept for the black update of this plane in the next step)
-          const long long gi = gofs[m] + (long long)kr * g.sz;
-          if (act || (f & F_TILE)) {
-            const double2 a2 = *reinterpret_cast<const double2 *>(a + gi);
-            const double2 l2 = *reinterpret_cast<const double2 *>(lam + gi);
-            const double2 r2 = *reinterpret_cast<const double2 *>(rhs + gi);
-            double2 b2 = make_double2(1.0, 1.0);
-            if (HAS_B) b2 = *reinterpret_cast<const double2 *>(b + gi);
-            nx_a[m] = e ? a2.x : a2.y; nx_l[m] = e ? l2.x : l2.y; nx_r[m] = e ? r2.x : r2.y;
-            if (HAS_B) nx_b[m] = e ? b2.x : b2.y;
-            if (act) {
-              const int s = sidx[m];
-              const double2 cp = *reinterpret_cast<const double2 *>(P + s);
-              const double c = e ? cp.y : cp.x;
-              double xm = e ? cp.x : P[s - 1];
-              double xp = e ? P[s + 2] : cp.y;
-              double ym = P[s + e - RW], yp = P[s + e + RW];
-              double zm = Pm[s + e], zp = Pp[s + e];
-              if ((f & F_X0) && e == 0) xm = bc.a[0] * c + bc.b[0];
-              if ((f & F_XN) && e == 1) xp = bc.a[1] * c + bc.b[1];
-              if (f & F_Y0) ym = bc.a[2] * c + bc.b[2];
-              if (f & F_YN) yp = bc.a[3] * c + bc.b[3];
-              if (kr == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-              if (kr == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
-              const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, e ? a2.y : a2.x, e ? b2.y : b2.x, e ? l2.y : l2.x,
-                                                  e ? r2.y : r2.x, alpha, beta, dxinv);
-              P[s + e] = nv;
-            }
-          }
-        }
-      }
+    // the lane's pair of plane kr+1
+    if (kr + 1 <= plast) {
+      const int q = kr + 1 - pfirst;
+      mbar_wait(&full[q % NSLOT], (q / NSLOT) & 1);
+      st.c3 = *reinterpret_cast<const double2 *>(planes + (size_t)(q % NSLOT) * PLANE + st.s);
     }
+    st.dense = planes + (size_t)((kr - pfirst) % NSLOT) * PLANE;
+    st.redw = redbuf + (size_t)(kr & 1) * NW * 32;
+    st.redr = redbuf + (size_t)((kr - 1) & 1) * NW * 32;
+    double *outp = out + gofs + (long long)(kr - 1) * g.sz;
+    const int e = (yodd + kr + g.k0) & 1;  // warp-uniform: element of the pair that is red in plane kr
+    if (e) st.template step<1>(g, bc, alpha, beta, dxinv, kr, doRed, doBlack, zloPhys, zhiPhys, outp);
+    else st.template step<0>(g, bc, alpha, beta, dxinv, kr, doRed, doBlack, zloPhys, zhiPhys, outp);
+    st.c0 = st.c1; st.c1 = st.c2; st.c2 = st.c3;
+    st.ca = na; st.cl = nl; st.cr = nr;
+    if (HAS_B) st.cb = nb;
     __syncthreads();
-    // the slot of plane kr-3 is dead now (its last reader was the black update of plane kr-2 in the previous step)
+    // plane kr's slot is dead (pair copied a step ago, y neighbours read by this step's red update)
     if (tid == 0) {
-      const int pn = kr - 3 + NSLOT;
-      if (kr - 3 >= pfirst && pn <= plast) {
-        const int s = (pn - pfirst) % NSLOT;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&full[s], PLANE_BYTES);
-        tma_load_3d(planes + (size_t)s * PLANE, &tmap, &full[s], x0 - 2, y0 - 2, pn + MGIC_GZ);
-      }
-    }
-    // ---------------- BLACK: plane kb = kr-1, result streamed to phi_out --------------------------------------
-    if (doBlack) {
-      double *Q = Pm;                                                               // plane kb
-      double *Qm = planes + (size_t)((kb - 1 - pfirst + NSLOT) % NSLOT) * PLANE;    // plane kb-1
-      double *Qp = P;                                                               // plane kb+1 = kr
-#pragma unroll
-      for (int m = 0; m < CPT; m++) {
-        const unsigned f = flg[m];
-        if (f & F_TILE) {
-          const int e = (((f & F_YODD) ? 1 : 0) + par) & 1;  // black element of plane kb == red element of plane kr
-          const int s = sidx[m];
-          const double2 cp = *reinterpret_cast<const double2 *>(Q + s);
-          const double c = e ? cp.y : cp.x;
-          double xm = e ? cp.x : Q[s - 1];
-          double xp = e ? Q[s + 2] : cp.y;
-          double ym = Q[s + e - RW], yp = Q[s + e + RW];
-          double zm = Qm[s + e], zp = Qp[s + e];
-          if ((f & F_X0) && e == 0) xm = bc.a[0] * c + bc.b[0];
-          if ((f & F_XN) && e == 1) xp = bc.a[1] * c + bc.b[1];
-          if (f & F_Y0) ym = bc.a[2] * c + bc.b[2];
-          if (f & F_YN) yp = bc.a[3] * c + bc.b[3];
-          if (kb == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-          if (kb == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
-          const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, st_a[m], HAS_B ? st_b[m] : 1.0, st_l[m], st_r[m], alpha,
-                                              beta, dxinv);
-          const double2 o = e ? make_double2(cp.x, nv) : make_double2(nv, cp.y);
-          *reinterpret_cast<double2 *>(out + gofs[m] + (long long)kb * g.sz) = o;
-        }
-      }
-    }
-    if (doRed) {
-#pragma unroll
-      for (int m = 0; m < CPT; m++) {
-        st_a[m] = nx_a[m]; st_l[m] = nx_l[m]; st_r[m] = nx_r[m];
-        if (HAS_B) st_b[m] = nx_b[m];
+      const int pn = kr + NSLOT;
+      if (pn <= plast) {
+        const int sl = (kr - pfirst) % NSLOT;
+        mbar_arrive_expect_tx(&full[sl], PLANE_BYTES);
+        tma_load_3d(planes + (size_t)sl * PLANE, &tmap, &full[sl], x0 - 2, y0 - 2, pn + MGIC_GZ);
       }
     }
   }
@@ -289,32 +299,31 @@ Plan plan_chunks(int tiles, int nz, int resident) {
   return best;
 }
 
-template <int TX, int TY, int NT, int NSLOT, bool HAS_B>
+template <int TY, int NSLOT, bool HAS_B, int MINB>
 int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
-  constexpr int PR = TX / 2 + 2, RW = 2 * PR, RR = TY + 4;
-  constexpr size_t SMEM = (size_t)NSLOT * RW * RR * 8 + NSLOT * 8;
+  using F = Fused<TY, NSLOT, HAS_B>;
   mgic_ctx *c = o->ctx;
-  auto kern = k_gsrb_fused<TX, TY, NT, NSLOT, HAS_B>;
+  auto kern = k_gsrb_fused<TY, NSLOT, HAS_B, MINB>;
   static bool attrSet = false;
   static int resident = 1;
   if (!attrSet) {
-    MGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    MGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM));
     int per = 1;
-    MGIC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NT, SMEM));
+    MGIC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, F::NT, F::SMEM));
     resident = (per < 1 ? 1 : per) * c->numSMs;
     attrSet = true;
   }
   const Geom g = o->geom();
   const BCk bc = o->bck(true);
   CUtensorMap tm;
-  MGIC_TRY(make_tmap(&tm, in - (long long)MGIC_GZ * g.sz, g.nx, g.ny, g.nz + 2 * MGIC_GZ, RW, RR));
+  MGIC_TRY(make_tmap(&tm, in - (long long)MGIC_GZ * g.sz, g.nx, g.ny, g.nz + 2 * MGIC_GZ, RW, F::RR));
   const int tilesX = (g.nx + TX - 1) / TX, tilesY = (g.ny + TY - 1) / TY;
   const Plan pl = plan_chunks(tilesX * tilesY, g.nz, resident);
   const int redLo = (bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
   const int redHi = (bc.type[5] == MGIC_FACE_INTERIOR) ? g.nz : g.nz - 1;
   dim3 grd(tilesX, tilesY, pl.nch);
-  kern<<<grd, NT, SMEM, c->stream>>>(tm, g, bc, outp, r->p, o->a->p, o->b ? o->b->p : nullptr, o->lambda->p, o->alpha, o->beta,
-                                     1.0 / (o->dx * o->dx), pl.zchunk, redLo, redHi);
+  kern<<<grd, F::NT, F::SMEM, c->stream>>>(tm, g, bc, outp, r->p, o->a->p, o->b ? o->b->p : nullptr, o->lambda->p, o->alpha, o->beta,
+                                           1.0 / (o->dx * o->dx), pl.zchunk, redLo, redHi);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { mgic_set_error("kernel gsrb_fused: %s", cudaGetErrorString(e)); return MGIC_ERR_CUDA; }
@@ -323,12 +332,14 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r) 
 
 template <bool HAS_B>
 int launch(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
-  const int cfg = o->ctx->fusedCfg;
-  if (o->n[0] >= 128 && cfg == 0) return launch_cfg<128, 16, 512, 6, HAS_B>(o, in, outp, r);
-  if (o->n[0] >= 64 && cfg == 2) return launch_cfg<64, 32, 512, 6, HAS_B>(o, in, outp, r);
-  if (o->n[0] >= 128 && cfg == 3) return launch_cfg<128, 8, 512, 6, HAS_B>(o, in, outp, r);
-  if (o->n[0] >= 64) return launch_cfg<64, 16, 256, 6, HAS_B>(o, in, outp, r);
-  return launch_cfg<32, 8, 128, 6, HAS_B>(o, in, outp, r);
+  switch (o->ctx->fusedCfg) {
+    case 0: return launch_cfg<8, 4, HAS_B, 2>(o, in, outp, r);
+    case 2: return launch_cfg<24, 4, HAS_B, 1>(o, in, outp, r);
+    case 3: return launch_cfg<16, 6, HAS_B, 1>(o, in, outp, r);
+    case 4: return launch_cfg<8, 6, HAS_B, 2>(o, in, outp, r);
+    case 5: return launch_cfg<12, 4, HAS_B, 2>(o, in, outp, r);
+    default: return launch_cfg<16, 4, HAS_B, 1>(o, in, outp, r);
+  }
 }
 
 }  // namespace

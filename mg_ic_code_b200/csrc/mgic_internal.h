@@ -71,6 +71,8 @@ struct mgic_ctx {
   // tuning knobs (mgic_ctx_set_option)
   int fusedCfg = 1;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
+  int bottomKernel = 1;                   // 1: bottom BiCGStab as one persistent cooperative kernel (bottom.cu); 0: host-driven
+  int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
 };
@@ -155,6 +157,8 @@ int is_constant(mgic_ctx *, const Geom &, const double *x, double value, int slo
 int init_conditions(mgic_vars *);
 int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
+int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
+                    int *d_out);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
 int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations);
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)

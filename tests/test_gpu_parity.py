@@ -104,7 +104,7 @@ def test_kernels_bit_exact(ctx, case, keep_b):
     assert np.array_equal(p.e.download(), p.o.get("E"))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
 def test_fused_smoother_bit_exact(ctx, case, cfg):
     """fused red+black plane-streaming sweep (TMA-staged halo'd planes) == per-colour oracle sweeps, every tile shape,
@@ -140,6 +140,29 @@ def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
         assert np.array_equal(p.e.download(), p.o.get("E"))
     finally:
         ctx.set_option("fused_min_cells", 2097152)
+
+
+def test_graph_and_bottom_kernel_variants_agree(ctx):
+    """CUDA-graph replay == eager launches bit for bit; persistent bottom kernel vs host-driven BiCGStab differ only by
+    the summation order of the bottom solver's dot products."""
+    results = {}
+    for name, opts in (("eager_host", dict(use_graph=0, bottom_kernel=0)), ("eager_dev", dict(use_graph=0, bottom_kernel=1)),
+                       ("graph_dev", dict(use_graph=1, bottom_kernel=1))):
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        try:
+            p = Pair(ctx, **dict(CASES["c64"], numMGsmooth=2))
+            p.r.upload(p.o.get("RHS")); p.op.setToZero(p.e)
+            its = []
+            for _ in range(3):
+                p.f.vcycle(p.e, p.r)
+                its.append(p.f.last_bottom_iterations)
+            results[name] = (p.e.download(), its)
+        finally:
+            ctx.set_option("use_graph", 1); ctx.set_option("bottom_kernel", 1)
+    assert np.array_equal(results["eager_dev"][0], results["graph_dev"][0])
+    assert results["eager_dev"][1] == results["graph_dev"][1] == results["eager_host"][1]
+    assert relerr(results["eager_dev"][0], results["eager_host"][0]) < 1e-11
 
 
 def test_reductions_and_blas1(ctx):
