@@ -123,15 +123,15 @@ extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *t
   return MGIC_OK;
 }
 
-// read back `n` device scalars starting at slot (one sync); multi-rank: combine with op (0 sum, 1 max)
+// read back `n` device scalars starting at slot (one sync); multi-rank: all-reduced on the device first (op 0 sum, 1 max)
 static int fetch_scalars(mgic_ctx *c, int slot, int n, int op, double *out) {
+  if (c->nranks > 1) {
+    MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm_init)");
+    MGIC_TRY(c->allreduce(c, c->d_scal + slot, n, op));
+  }
   MGIC_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->d_scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
   for (int q = 0; q < n; q++) out[q] = c->h_scal[slot + q];
-  if (c->nranks > 1) {
-    MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm)");
-    MGIC_TRY(c->allreduce(c, out, n, op));
-  }
   return MGIC_OK;
 }
 
@@ -182,6 +182,7 @@ extern "C" int mgic_op_create(mgic_ctx *c, const int n[3], int k0, int nz_local,
     if (bc_hi[d] < 0 || bc_hi[d] > 2) { mgic_set_error("bogus bc flag high side %d", bc_hi[d]); return MGIC_ERR_ARG; }   // SetBCs.cpp:123
     MGIC_REQUIRE((bc_lo[d] == MGIC_BC_PERIODIC) == (bc_hi[d] == MGIC_BC_PERIODIC), "periodic must be set on both sides");
   }
+  MGIC_REQUIRE(c->nranks == 1 || bc_lo[2] != MGIC_BC_PERIODIC, "periodic z across ranks is not supported");
   MGIC_CUDA(cudaSetDevice(c->device));
   mgic_op *o = new mgic_op;
   o->ctx = c;
@@ -232,6 +233,11 @@ extern "C" int mgic_op_reset_lambda(mgic_op *o) {
   if (!o->lambda) MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
   if (!o->lambdaDirty) return MGIC_OK;
   MGIC_TRY(mgk::compute_lambda(o->ctx, o->geom(), o->lambda->p, o->a->p, o->alpha, o->beta, o->dx));
+  if (o->ctx->nranks > 1) {  // the fused sweep updates the neighbour's first plane redundantly: it needs its coefficients
+    MGIC_TRY(mgk::mgic_halo(o, o->a, 1));
+    MGIC_TRY(mgk::mgic_halo(o, o->lambda, 1));
+    if (o->b) MGIC_TRY(mgk::mgic_halo(o, o->b, 1));
+  }
   o->lambdaDirty = false;
   return MGIC_OK;
 }
@@ -329,13 +335,14 @@ extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy,
 }
 
 // ------------------------------------------------------------------------------------------------ op methods
-static int halo(mgic_op *o, mgic_field *f, int planes) {
+int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
   if (o->ctx->nranks > 1) {
     MGIC_REQUIRE(o->ctx->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
     return o->ctx->halo_exchange(o->ctx, f, planes);
   }
   return MGIC_OK;
 }
+static int halo(mgic_op *o, mgic_field *f, int planes) { return mgk::mgic_halo(o, f, planes); }
 static inline const double *bptr(const mgic_op *o) { return o->b ? o->b->p : nullptr; }
 
 // one colour pass of levelGSRB (VariableCoeffPoissonOperator.cpp:290-331): exchange, BC (folded in), kernel
@@ -354,7 +361,7 @@ extern "C" int mgic_op_relax(mgic_op *o, mgic_field *e, const mgic_field *r, int
   MGIC_REQUIRE(o && e && r, "NULL argument");
   REQ_SHAPE(o, e); REQ_SHAPE(o, r);
   MGIC_TRY(mgic_op_reset_lambda(o));
-  if (o->smoother == 1 && o->ctx->nranks == 1) return mgk::gsrb_fused(o, e, r, iterations);
+  if (o->smoother == 1 && mgk::gsrb_fused_applicable(o)) return mgk::gsrb_fused(o, e, r, iterations);
   for (int it = 0; it < iterations; it++)
     for (int pass = 0; pass <= 1; pass++) MGIC_TRY(mgic_op_gsrb_color(o, e, r, pass));
   return MGIC_OK;

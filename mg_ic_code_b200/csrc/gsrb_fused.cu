@@ -57,7 +57,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Geometry of one CTA: a warp is one row of the halo'd region, a lane is one x-pair (16 bytes), so the colour of
@@ -337,8 +336,11 @@ int launch(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
     case 2: return launch_cfg<24, 4, HAS_B, 1>(o, in, outp, r);
     case 3: return launch_cfg<16, 6, HAS_B, 1>(o, in, outp, r);
     case 4: return launch_cfg<8, 6, HAS_B, 2>(o, in, outp, r);
-    case 5: return launch_cfg<12, 4, HAS_B, 2>(o, in, outp, r);
-    default: return launch_cfg<16, 4, HAS_B, 1>(o, in, outp, r);
+    case 1: return launch_cfg<16, 4, HAS_B, 1>(o, in, outp, r);
+    case 6: return launch_cfg<12, 6, HAS_B, 2>(o, in, outp, r);
+    case 7: return launch_cfg<10, 4, HAS_B, 2>(o, in, outp, r);
+    case 8: return launch_cfg<6, 4, HAS_B, 3>(o, in, outp, r);
+    default: return launch_cfg<12, 4, HAS_B, 2>(o, in, outp, r);
   }
 }
 
@@ -346,24 +348,24 @@ int launch(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
 
 namespace mgk {
 
-// relax(e, r, iterations) with fused sweeps.  Periodic faces (TMA cannot wrap) and odd nx fall back to the
-// per-colour kernel, which computes the same bits.
+// Periodic faces (TMA cannot wrap), odd nx and small (launch-latency bound) levels use the per-colour kernel, which
+// computes the same bits.
+bool gsrb_fused_applicable(const mgic_op *o) {
+  for (int d = 0; d < 3; d++)
+    if (o->bc_lo[d] == MGIC_BC_PERIODIC) return false;
+  const long long cells = (long long)o->n[0] * o->n[1] * o->nzl;
+  if ((o->n[0] & 1) || o->n[0] < 8 || cells < o->ctx->fusedMinCells) return false;
+  if (o->ctx->nranks > 1 && o->nzl < MGIC_GZ) return false;
+  return true;
+}
+
+// relax(e, r, iterations) with fused sweeps.  Multi-rank: one 2-plane halo exchange of e per sweep (the neighbour's
+// first plane is updated redundantly) instead of the reference's two 1-plane exchanges, plus one of rhs per call.
 int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations) {
-  const Geom g = o->geom();
-  bool periodic = false;
-  for (int d = 0; d < 3; d++) periodic = periodic || o->bc_lo[d] == MGIC_BC_PERIODIC;
-  const long long cells = (long long)g.nx * g.ny * g.nz;
-  if (periodic || (g.nx & 1) || g.nx < 8 || cells < o->ctx->fusedMinCells) {
-    const BCk bc = o->bck(true);
-    for (int it = 0; it < iterations; it++)
-      for (int pass = 0; pass <= 1; pass++) {
-        ProfScope ps(o->ctx, o->profTag);
-        MGIC_TRY(gsrb_color(o->ctx, g, bc, e->p, r->p, o->a->p, o->b ? o->b->p : nullptr, o->lambda->p, o->alpha, o->beta, o->dx, pass));
-      }
-    return MGIC_OK;
-  }
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
+  if (o->ctx->nranks > 1) MGIC_TRY(mgic_halo(o, const_cast<mgic_field *>(r), 1));
   for (int it = 0; it < iterations; it++) {
+    if (o->ctx->nranks > 1) MGIC_TRY(mgic_halo(o, e, 2));
     {
       ProfScope ps(o->ctx, o->profTag);
       if (o->b) MGIC_TRY(launch<true>(o, e->p, o->scratch->p, r));

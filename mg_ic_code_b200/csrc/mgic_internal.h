@@ -65,11 +65,11 @@ struct mgic_ctx {
   size_t partCap = 0;
   // halo exchange hook (multi-GPU): set by mgic_comm; null on one GPU
   int (*halo_exchange)(mgic_ctx *, mgic_field *, int depth_planes) = nullptr;
-  int (*allreduce)(mgic_ctx *, double *hostvals, int n, int op /*0 sum 1 max*/) = nullptr;
+  int (*allreduce)(mgic_ctx *, double *devvals, int n, int op /*0 sum 1 max*/) = nullptr;
   void *comm = nullptr;
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
   // tuning knobs (mgic_ctx_set_option)
-  int fusedCfg = 1;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
+  int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
   int bottomKernel = 1;                   // 1: bottom BiCGStab as one persistent cooperative kernel (bottom.cu); 0: host-driven
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
@@ -159,6 +159,9 @@ int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
 int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                     int *d_out);
+// z-halo exchange of a field on the operator's level (no-op on one rank)
+int mgic_halo(mgic_op *, mgic_field *, int planes);
+bool gsrb_fused_applicable(const mgic_op *);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
 int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations);
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)

@@ -1,5 +1,5 @@
 """Profiling driver: a few finest-level relax() calls (and optionally a V-cycle) at n^3, nothing else.
-   python tools/prof_relax.py [n] [sweeps] [smoother] [fused_cfg] [vcycles]"""
+   python tools/prof_relax.py [n] [sweeps] [smoother] [fused_cfg] [vcycles] [use_graph]"""
 import os
 import sys
 
@@ -11,7 +11,9 @@ sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 smoother = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 vcycles = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+graph = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 ctx = m.Context(0)
+ctx.set_option("use_graph", graph)
 if cfg >= 0:
     ctx.set_option("fused_cfg", cfg)
 P = m.make_params(dict(m.DEFAULTS, N=(n, n, n), max_grid_size=32, numMGsmooth=2))
