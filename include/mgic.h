@@ -87,7 +87,8 @@ void *mgic_ctx_stream(mgic_ctx *);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long long mgic_ctx_launch_count(mgic_ctx *);
 /* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
- * per-colour kernel), "bottom_kernel" (1: bottom BiCGStab as one persistent kernel, 0: host driven), "use_graph" (1: V-cycles
+ * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: one persistent kernel in a thread-block cluster, 3: the same as a
+ * cooperative grid, 0: host-driven launches), "use_graph" (1: V-cycles
  * replayed as CUDA graphs).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of
  * the bottom solver's dot products. */
 int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);

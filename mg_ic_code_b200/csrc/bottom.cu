@@ -1,4 +1,4 @@
-// bottom.cu -- the multigrid bottom solve as ONE persistent cooperative kernel.
+// bottom.cu -- the multigrid bottom solve as ONE persistent kernel (one thread-block cluster, or a cooperative grid).
 //
 // [Chombo 3.2] MultiGrid::cycle ends in m_bottomSolver->solve(e, r): BiCGStabSolver<LevelData<FArrayBox>> with
 // its defaults (imax 80, eps 1e-6, reps 1e-12, hang 1e-8, small 1e-30, 5 restarts, normType 2), preconditioned by
@@ -18,7 +18,14 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int BT = 256;  // threads per block
+constexpr int BT = 256;   // threads per block, cooperative-grid variant
+constexpr int CT = 512;   // threads per block, cluster variant
+constexpr int CSIZE = 8;  // CTAs per cluster (portable maximum): the whole solve runs in ONE cluster
+
+// all CTAs of the cluster: hardware barrier with release / acquire at cluster scope (orders global memory too)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 struct BottomArgs {
   Geom g;
@@ -34,10 +41,14 @@ struct BottomArgs {
   int *out;  // [0] iterations, [1] exit status
 };
 
-template <bool HAS_B>
+template <bool HAS_B, bool CLUSTER>
 struct Bottom {
   const BottomArgs &A;
   cg::grid_group grid;
+  __device__ __forceinline__ void gsync() {
+    if (CLUSTER) cluster_sync_all();
+    else grid.sync();
+  }
   long long n, gtid, gsize;
   int nred;
   double *sh;  // 66 doubles of shared memory
@@ -69,7 +80,7 @@ struct Bottom {
       }
       if (l == 0) { buf[2 * blockIdx.x] = x0; buf[2 * blockIdx.x + 1] = x1; }
     }
-    grid.sync();
+    gsync();
     if (w == 0) {
       double x0 = 0.0, x1 = 0.0;
       for (int q = l; q < (int)gridDim.x; q += 32) {  // fixed order: same bits in every block
@@ -122,7 +133,7 @@ struct Bottom {
   // relax(x, rhs, 2): four colour passes, a grid barrier before each (levelGSRB, VariableCoeffPoissonOperator.cpp:290-331)
   __device__ void relax2(double *x, const double *rhs) {
     for (int pass = 0; pass < 4; pass++) {
-      grid.sync();
+      gsync();
       const int color = pass & 1;
       for (long long q = gtid; q < n; q += gsize) {
         int i, j, k;
@@ -135,7 +146,7 @@ struct Bottom {
         }
       }
     }
-    grid.sync();
+    gsync();
   }
 
   __device__ void solve() {
@@ -230,7 +241,7 @@ struct Bottom {
           recount = 0;
           for (long long q = gtid; q < n; q += gsize) phi[q] = phi[q] + 1.0 * e[q];
           if (restarts == A.numRestarts) { status = 3; finished = true; break; }
-          grid.sync();
+          gsync();
           s0 = 0.0; s1 = 0.0;
           for (long long q = gtid; q < n; q += gsize) {
             const double rv = res_point(phi, rhs, q);
@@ -254,7 +265,16 @@ struct Bottom {
 template <bool HAS_B>
 __global__ void __launch_bounds__(BT) k_bottom_bicgstab(BottomArgs A) {
   __shared__ double sh[66];
-  Bottom<HAS_B> s(A, sh);
+  Bottom<HAS_B, false> s(A, sh);
+  s.solve();
+}
+
+// same solve inside one thread-block cluster: barriers are the cluster's hardware barrier (~0.3 us instead of the
+// ~4 us of a 128-block cooperative grid barrier), which is what bounds this latency-dominated kernel
+template <bool HAS_B>
+__global__ void __cluster_dims__(CSIZE, 1, 1) __launch_bounds__(CT) k_bottom_bicgstab_cluster(BottomArgs A) {
+  __shared__ double sh[66];
+  Bottom<HAS_B, true> s(A, sh);
   s.solve();
 }
 
@@ -277,6 +297,15 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   A.imax = 80; A.eps = 1.0e-6; A.reps = 1.0e-12; A.hang = 1.0e-8; A.small = 1.0e-30; A.numRestarts = 5;
   A.out = d_out;
   const long long n = (long long)A.g.nx * A.g.ny * A.g.nz;
+  if (c->bottomKernel != 3 && n <= (long long)CSIZE * CT * 128) {
+    // one cluster of CSIZE CTAs
+    if (o->b) k_bottom_bicgstab_cluster<true><<<CSIZE, CT, 0, c->stream>>>(A);
+    else k_bottom_bicgstab_cluster<false><<<CSIZE, CT, 0, c->stream>>>(A);
+    c->launches++;
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { mgic_set_error("kernel bottom_bicgstab_cluster: %s", cudaGetErrorString(e2)); return MGIC_ERR_CUDA; }
+    return MGIC_OK;
+  }
   void *kern = o->b ? (void *)k_bottom_bicgstab<true> : (void *)k_bottom_bicgstab<false>;
   static int perSM[2] = {0, 0};
   int &per = perSM[o->b ? 1 : 0];

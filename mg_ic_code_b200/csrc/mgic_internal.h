@@ -71,7 +71,8 @@ struct mgic_ctx {
   // tuning knobs (mgic_ctx_set_option)
   int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
-  int bottomKernel = 1;                   // 1: bottom BiCGStab as one persistent cooperative kernel (bottom.cu); 0: host-driven
+  int bottomKernel = 1;                   // bottom BiCGStab: 1 one persistent kernel in a thread-block cluster, 3 same as a
+                                          // cooperative grid, 0 host-driven launches (bottom.cu)
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;

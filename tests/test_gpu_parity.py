@@ -147,6 +147,7 @@ def test_graph_and_bottom_kernel_variants_agree(ctx):
     the summation order of the bottom solver's dot products."""
     results = {}
     for name, opts in (("eager_host", dict(use_graph=0, bottom_kernel=0)), ("eager_dev", dict(use_graph=0, bottom_kernel=1)),
+                       ("eager_coop", dict(use_graph=0, bottom_kernel=3)),
                        ("graph_dev", dict(use_graph=1, bottom_kernel=1))):
         for k, v in opts.items():
             ctx.set_option(k, v)
@@ -161,7 +162,8 @@ def test_graph_and_bottom_kernel_variants_agree(ctx):
         finally:
             ctx.set_option("use_graph", 1); ctx.set_option("bottom_kernel", 1)
     assert np.array_equal(results["eager_dev"][0], results["graph_dev"][0])
-    assert results["eager_dev"][1] == results["graph_dev"][1] == results["eager_host"][1]
+    assert results["eager_dev"][1] == results["graph_dev"][1] == results["eager_host"][1] == results["eager_coop"][1]
+    assert relerr(results["eager_dev"][0], results["eager_coop"][0]) < 1e-11
     assert relerr(results["eager_dev"][0], results["eager_host"][0]) < 1e-11
 
 
