@@ -205,8 +205,7 @@ def run_gpu(args):
     cells_total = cells_local * world
 
     def step():
-        op.setToZero(e)
-        f.vcycle(e, rhs)
+        f.vcycle_from_zero(e, rhs)   # setToZero(e); MultiGrid::oneCycle(e, rhs)
 
     def barrier():
         ctx.sync()
@@ -262,8 +261,7 @@ def run_gpu(args):
 
     def step_e2e():
         m._capi.check(L.mgic_field_upload_async(r_dev.h, C.c_void_p(h_r.data_ptr() - off)))
-        op.setToZero(e)
-        f.vcycle(e, r_dev)
+        f.vcycle_from_zero(e, r_dev)
         m._capi.check(L.mgic_field_download_async(e.h, C.c_void_p(h_e.data_ptr() - off)))
 
     e2e_steps = max(3, min(args.steps, 10))

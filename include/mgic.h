@@ -89,7 +89,7 @@ long long mgic_ctx_launch_count(mgic_ctx *);
 /* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
  * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: one persistent kernel in a thread-block cluster, 3: the same as a
  * cooperative grid, 0: host-driven launches), "use_graph" (1: V-cycles
- * replayed as CUDA graphs).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of
+ * replayed as CUDA graphs), "fuse_transfers" (1: setToZero / prolongIncrement folded into the following fused sweep).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of
  * the bottom solver's dot products. */
 int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);
 /* per-launch CUDA-event timing of the dominant kernel (the finest level's GSRB launches): arm with enable = 1,
@@ -131,6 +131,8 @@ int mgic_field_upload_fab(mgic_field *, const double *fab, const int fab_lo[3], 
                           const int region_lo[3], const int region_hi[3]);
 int mgic_field_download_fab(const mgic_field *, double *fab, const int fab_lo[3], const int fab_hi[3],
                             const int region_lo[3], const int region_hi[3]);
+/* wait for the asynchronous fab copies issued on the field's context */
+int mgic_field_sync(const mgic_field *);
 /* device pointer of local cell (0,0,0) and strides in doubles (plumbing for torch / tests) */
 int mgic_field_devptr(const mgic_field *, void **ptr, long long *stride_y, long long *stride_z);
 
@@ -176,6 +178,9 @@ int mgic_mg_scratch(mgic_mg *, int depth, mgic_field **e, mgic_field **r);  /* M
 int mgic_mg_refresh_coefs(mgic_mg *);
 /* [Chombo] MultiGrid::oneCycle (homogeneous) == cycle(0, e, r): relax/restrict/recurse/prolong/relax + bottom solve */
 int mgic_mg_vcycle(mgic_mg *, mgic_field *e, const mgic_field *r);
+/* setToZero(e) + oneCycle(e, r) in one call: what [Chombo] MultilevelLinearOp::preCond issues first; the zero fill and the
+ * first read of e are skipped */
+int mgic_mg_vcycle_from_zero(mgic_mg *, mgic_field *e, const mgic_field *r);
 int mgic_mg_bottom_solve(mgic_mg *, mgic_field *e, const mgic_field *r, int *iterations);
 int mgic_mg_last_bottom_iterations(mgic_mg *);
 /* select the smoother implementation on every depth (see mgic_op_set_smoother) */

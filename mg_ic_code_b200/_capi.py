@@ -58,7 +58,7 @@ def lib():
         "mgic_op_set_alpha_beta": [vp, C.c_double, C.c_double], "mgic_op_reset_lambda": [vp],
         "mgic_op_compute_lambda": [vp], "mgic_op_get_lambda": [vp, pvp],
         "mgic_op_dims": [vp, i3, ip, ip, dp],
-        "mgic_field_create": [vp, pvp], "mgic_field_destroy": [vp],
+        "mgic_field_create": [vp, pvp], "mgic_field_destroy": [vp], "mgic_field_sync": [vp],
         "mgic_field_upload": [vp, nd], "mgic_field_download": [vp, nd],
         "mgic_field_upload_async": [vp, vp], "mgic_field_download_async": [vp, vp],
         "mgic_field_upload_fab": [vp, nd, i3, i3, i3, i3], "mgic_field_download_fab": [vp, nd, i3, i3, i3, i3],
@@ -74,7 +74,7 @@ def lib():
         "mgic_mg_create": [vp, C.POINTER(MgicParams), vp, vp, pvp],
         "mgic_mg_create_ex": [vp, C.POINTER(MgicParams), vp, vp, C.c_int, pvp],
         "mgic_mg_destroy": [vp], "mgic_mg_op": [vp, C.c_int, pvp], "mgic_mg_scratch": [vp, C.c_int, pvp, pvp],
-        "mgic_mg_refresh_coefs": [vp], "mgic_mg_vcycle": [vp, vp, vp], "mgic_mg_bottom_solve": [vp, vp, vp, ip],
+        "mgic_mg_refresh_coefs": [vp], "mgic_mg_vcycle": [vp, vp, vp], "mgic_mg_vcycle_from_zero": [vp, vp, vp], "mgic_mg_bottom_solve": [vp, vp, vp, ip],
         "mgic_mg_set_smoother": [vp, C.c_int],
         "mgic_mg_outer_solve": [vp, vp, vp, ip, ip, dp, C.c_int],
         "mgic_vars_create": [vp, C.POINTER(MgicParams), C.c_int, C.c_int, pvp], "mgic_vars_destroy": [vp],

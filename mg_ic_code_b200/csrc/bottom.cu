@@ -20,7 +20,7 @@ namespace {
 
 constexpr int BT = 256;   // threads per block, cooperative-grid variant
 constexpr int CT = 512;   // threads per block, cluster variant
-constexpr int CSIZE = 8;  // CTAs per cluster (portable maximum): the whole solve runs in ONE cluster
+constexpr int CSIZE = 8;  // CTAs per cluster: portable maximum; 16 is used when the device can place it
 
 // all CTAs of the cluster: hardware barrier with release / acquire at cluster scope (orders global memory too)
 __device__ __forceinline__ void cluster_sync_all() {
@@ -130,19 +130,54 @@ struct Bottom {
     return (rhs[q] - A.alpha * A.a[q] * c) + l;
   }
 
-  // relax(x, rhs, 2): four colour passes, a grid barrier before each (levelGSRB, VariableCoeffPoissonOperator.cpp:290-331)
+  // one GSRB point: everything it reads, gathered before anything is written (lets two points overlap their loads)
+  struct Pt { long long q; double c, av, bv, lv, rv; Nb nb; };
+  __device__ __forceinline__ Pt gather(const double *x, const double *rhs, long long h, int color, int hx) const {
+    Pt p;
+    const long long row = h / hx;
+    const int t = (int)(h - row * hx), j = (int)(row % A.g.ny), k = (int)(row / A.g.ny);
+    const int i = 2 * t + ((j + k + A.g.k0 + color) & 1);
+    p.q = i + (long long)j * A.g.sy + (long long)k * A.g.sz;
+    p.c = x[p.q];
+    p.nb = neighbours(x, p.q, i, j, k, A.g, A.bc, p.c);
+    p.av = A.a[p.q]; p.bv = HAS_B ? A.b[p.q] : 1.0; p.lv = A.lam[p.q]; p.rv = rhs[p.q];
+    return p;
+  }
+  __device__ __forceinline__ double point(const Pt &p) const {
+    return gsrb_point<HAS_B>(p.c, p.nb.xm, p.nb.xp, p.nb.ym, p.nb.yp, p.nb.zm, p.nb.zp, p.av, p.bv, p.lv, p.rv, A.alpha, A.beta,
+                             A.dxinv);
+  }
+  // relax(x, rhs, 2): four colour passes, a barrier before each (levelGSRB, VariableCoeffPoissonOperator.cpp:290-331).
+  // Threads enumerate the cells OF THE COLOUR (i = 2t + parity, VariableCoeffPoissonOperatorF.ChF:98-106), two at a time.
   __device__ void relax2(double *x, const double *rhs) {
+    const bool even = (A.g.nx & 1) == 0;
+    const int hx = A.g.nx / 2;
+    const long long nh = (long long)hx * A.g.ny * A.g.nz;
     for (int pass = 0; pass < 4; pass++) {
       gsync();
       const int color = pass & 1;
-      for (long long q = gtid; q < n; q += gsize) {
-        int i, j, k;
-        ijk(q, i, j, k);
-        if (((i + j + k + A.g.k0 + color) & 1) == 0) {
-          const double c = x[q];
-          const Nb nb = neighbours(x, q, i, j, k, A.g, A.bc, c);
-          x[q] = gsrb_point<HAS_B>(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp, A.a[q], HAS_B ? A.b[q] : 1.0, A.lam[q], rhs[q],
-                                   A.alpha, A.beta, A.dxinv);
+      if (even) {
+        for (long long h0 = gtid; h0 < nh; h0 += 2 * gsize) {
+          const long long h1 = h0 + gsize;
+          const Pt p0 = gather(x, rhs, h0, color, hx);
+          if (h1 < nh) {
+            const Pt p1 = gather(x, rhs, h1, color, hx);
+            x[p0.q] = point(p0);
+            x[p1.q] = point(p1);
+          } else {
+            x[p0.q] = point(p0);
+          }
+        }
+      } else {
+        for (long long q = gtid; q < n; q += gsize) {
+          int i, j, k;
+          ijk(q, i, j, k);
+          if (((i + j + k + A.g.k0 + color) & 1) == 0) {
+            const double c = x[q];
+            const Nb nb = neighbours(x, q, i, j, k, A.g, A.bc, c);
+            x[q] = gsrb_point<HAS_B>(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp, A.a[q], HAS_B ? A.b[q] : 1.0, A.lam[q], rhs[q],
+                                     A.alpha, A.beta, A.dxinv);
+          }
         }
       }
     }
@@ -272,7 +307,7 @@ __global__ void __launch_bounds__(BT) k_bottom_bicgstab(BottomArgs A) {
 // same solve inside one thread-block cluster: barriers are the cluster's hardware barrier (~0.3 us instead of the
 // ~4 us of a 128-block cooperative grid barrier), which is what bounds this latency-dominated kernel
 template <bool HAS_B>
-__global__ void __cluster_dims__(CSIZE, 1, 1) __launch_bounds__(CT) k_bottom_bicgstab_cluster(BottomArgs A) {
+__global__ void __launch_bounds__(CT) k_bottom_bicgstab_cluster(BottomArgs A) {
   __shared__ double sh[66];
   Bottom<HAS_B, true> s(A, sh);
   s.solve();
@@ -298,12 +333,30 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   A.out = d_out;
   const long long n = (long long)A.g.nx * A.g.ny * A.g.nz;
   if (c->bottomKernel != 3 && n <= (long long)CSIZE * CT * 128) {
-    // one cluster of CSIZE CTAs
-    if (o->b) k_bottom_bicgstab_cluster<true><<<CSIZE, CT, 0, c->stream>>>(A);
-    else k_bottom_bicgstab_cluster<false><<<CSIZE, CT, 0, c->stream>>>(A);
+    // ONE cluster; 16 CTAs (non-portable size) when the level is big enough to use them and the device can place it
+    void (*ck)(BottomArgs) = o->b ? k_bottom_bicgstab_cluster<true> : k_bottom_bicgstab_cluster<false>;
+    static int maxCluster[2] = {0, 0};
+    int &mc = maxCluster[o->b ? 1 : 0];
+    if (!mc) {
+      mc = CSIZE;
+      if (cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(16); q.blockDim = dim3(CT);
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 16; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        q.attrs = &at; q.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, ck, &q) == cudaSuccess && nc >= 1) mc = 16;
+      }
+      cudaGetLastError();
+    }
+    int cs = (n > (long long)CSIZE * CT * 2) ? mc : CSIZE;
+    if (c->bottomKernel == 2) cs = CSIZE;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(CT); cfg.stream = c->stream;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    MGIC_CUDA(cudaLaunchKernelEx(&cfg, ck, A));
     c->launches++;
-    cudaError_t e2 = cudaGetLastError();
-    if (e2 != cudaSuccess) { mgic_set_error("kernel bottom_bicgstab_cluster: %s", cudaGetErrorString(e2)); return MGIC_ERR_CUDA; }
     return MGIC_OK;
   }
   void *kern = o->b ? (void *)k_bottom_bicgstab<true> : (void *)k_bottom_bicgstab<false>;

@@ -98,6 +98,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "fused_min_cells")) c->fusedMinCells = value;
   else if (!strcmp(name, "bottom_kernel")) c->bottomKernel = (int)value;
   else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
+  else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
@@ -326,6 +327,11 @@ extern "C" int mgic_field_download_fab(const mgic_field *f, double *fab, const i
   MGIC_REQUIRE(f && fab && flo && fhi && rlo && rhi, "NULL argument");
   return fab_copy(f, fab, flo, fhi, rlo, rhi, false);
 }
+extern "C" int mgic_field_sync(const mgic_field *f) {
+  MGIC_REQUIRE(f, "field is NULL");
+  MGIC_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return MGIC_OK;
+}
 extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy, long long *sz) {
   MGIC_REQUIRE(f && ptr, "NULL argument");
   *ptr = f->p;
@@ -339,6 +345,13 @@ int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
   if (o->ctx->nranks > 1) {
     MGIC_REQUIRE(o->ctx->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
     return o->ctx->halo_exchange(o->ctx, f, planes);
+  }
+  return MGIC_OK;
+}
+int mgk::mgic_halo_shape(mgic_ctx *c, mgic_field *f, int planes) {
+  if (c->nranks > 1) {
+    MGIC_REQUIRE(c->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
+    return c->halo_exchange(c, f, planes);
   }
   return MGIC_OK;
 }
@@ -613,7 +626,7 @@ struct mgic_mg {
   int *d_bottomOut = nullptr;   // device {iterations, status} of the last persistent bottom solve
   bool bottomOnDevice = false;
   // V-cycle graphs, keyed by the (correction, residual) arrays they were captured for
-  struct VGraph { const void *e, *r; cudaGraphExec_t exec; long long launches; };
+  struct VGraph { const void *e, *r; bool zero; cudaGraphExec_t exec; long long launches; };
   std::vector<VGraph> graphs;
   bool graphBroken = false;
 };
@@ -783,31 +796,51 @@ extern "C" int mgic_mg_last_bottom_iterations(mgic_mg *mg) {
 }
 
 // [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
-static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r) {
+// relax(e, r, S) where e is known to be zero: the first fused sweep reads nothing for it (and the zero fill is skipped)
+static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int S) {
+  if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op)) {
+    MGIC_TRY(mgic_op_reset_lambda(op));
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_FROM_ZERO, nullptr);
+  }
+  MGIC_TRY(mgic_op_set_to_zero(op, e));
+  return mgic_op_relax(op, e, r, S);
+}
+// prolongIncrement(e, eCoarse) followed by relax(e, r, S): the increment is folded into the first fused sweep
+static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S) {
+  if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op) && op->ctx->fusePR) {
+    MGIC_TRY(mgic_op_reset_lambda(op));
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec);
+  }
+  MGIC_TRY(mgic_op_prolong_increment(op, e, ec));
+  return mgic_op_relax(op, e, r, S);
+}
+
+// [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
+static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, bool eIsZero) {
   mgic_op *op = mg->ops[depth];
   const int S = mg->P.numMGsmooth;
+  const bool z = eIsZero && mg->ctx->fusePR;
   if (depth == mg->nd - 1) {
     const long long cells = (long long)op->n[0] * op->n[1] * op->n[2];
-    if (cells == 1) return mgic_op_relax(op, e, r, 1);
-    MGIC_TRY(mgic_op_relax(op, e, r, S));
+    if (cells == 1) return z ? relax_from_zero(op, e, r, 1) : mgic_op_relax(op, e, r, 1);
+    MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
     return mgic_mg_bottom_solve(mg, e, r, nullptr);
   }
-  MGIC_TRY(mgic_op_relax(op, e, r, S));
+  MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
   MGIC_TRY(mgic_op_restrict_residual(op, mg->r[depth + 1], e, r));
-  MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
-  MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1]));
-  MGIC_TRY(mgic_op_prolong_increment(op, e, mg->e[depth + 1]));
-  return mgic_op_relax(op, e, r, S);
+  if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));   // setToZero(e[depth+1])
+  MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
+  return prolong_relax(op, e, mg->e[depth + 1], r, S);
 }
 
 // One V-cycle, replayed as a CUDA graph when possible: the cycle is a fixed launch sequence (the bottom solve is a
 // single kernel), so it is captured once per (correction, residual) pair and afterwards costs one graph launch.
-static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
+static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZero = false) {
   mgic_ctx *c = mg->ctx;
   const bool graphable = c->useGraph && c->bottomKernel && c->nranks == 1 && !c->profiling && !mg->graphBroken;
-  if (!graphable) return mg_cycle(mg, 0, e, r);
+  if (!graphable) return mg_cycle(mg, 0, e, r, eIsZero);
   for (auto &g : mg->graphs)
-    if (g.e == e->p && g.r == r->p) {
+    if (g.e == e->p && g.r == r->p && g.zero == eIsZero) {
       MGIC_CUDA(cudaGraphLaunch(g.exec, c->stream));
       c->launches += g.launches;
       mg->bottomOnDevice = true;
@@ -834,7 +867,7 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
   bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
   int rc = MGIC_OK;
   if (ok) {
-    rc = mg_cycle(mg, 0, e, r);
+    rc = mg_cycle(mg, 0, e, r, eIsZero);
     ok = (cudaStreamEndCapture(c->stream, &graph) == cudaSuccess) && rc == MGIC_OK && graph;
   }
   const long long nl = c->launches - l0;
@@ -850,9 +883,9 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
       sv.first->p = sv.second + (long long)MGIC_GZ * sv.first->sz;
     }
     mg->graphBroken = true;
-    return mg_cycle(mg, 0, e, r);
+    return mg_cycle(mg, 0, e, r, eIsZero);
   }
-  mg->graphs.push_back({e->p, r->p, exec, nl});
+  mg->graphs.push_back({e->p, r->p, eIsZero, exec, nl});
   MGIC_CUDA(cudaGraphLaunch(exec, c->stream));
   c->launches += nl;
   mg->bottomOnDevice = true;
@@ -865,13 +898,22 @@ extern "C" int mgic_mg_vcycle(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
   mg->lastBottomIters = 0;
   return vcycle_run(mg, e, r);
 }
+// setToZero(e) followed by one V-cycle (what [Chombo] MultilevelLinearOp::preCond does first): knowing that e is zero
+// lets the first sweep skip both the fill and the read of e
+extern "C" int mgic_mg_vcycle_from_zero(mgic_mg *mg, mgic_field *e, const mgic_field *r) {
+  MGIC_REQUIRE(mg && e && r, "NULL argument");
+  REQ_SHAPE(mg->ops[0], e); REQ_SHAPE(mg->ops[0], r);
+  mg->lastBottomIters = 0;
+  if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[0], e));
+  return vcycle_run(mg, e, r, true);
+}
 
 // f1: [Chombo] MultilevelLinearOp::preCond on one AMR level = zero cor, numMGIterations V-cycles
 struct OuterLin : LinOp {
   mgic_mg *mg;
   int preCond(mgic_field *cor, mgic_field *res) override {
-    MGIC_TRY(mgic_op_set_to_zero(op, cor));
-    for (int it = 0; it < mg->P.numMGIterations; it++) MGIC_TRY(vcycle_run(mg, cor, res));
+    if (mg->P.numMGIterations < 1 || !mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(op, cor));
+    for (int it = 0; it < mg->P.numMGIterations; it++) MGIC_TRY(vcycle_run(mg, cor, res, it == 0));
     return MGIC_OK;
   }
 };

@@ -16,7 +16,7 @@
 // re-reads hit L2.  Arithmetic is the shared gsrb_point() => bit-identical to the per-colour kernel.
 #include <cuda.h>
 
-#include <map>
+#include <cstring>
 
 #include "mgic_internal.h"
 #include "mgic_device.cuh"
@@ -64,35 +64,103 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 //   region  = RW x (TY+4) cells, RW = 64 (32 pairs), staged by TMA           [tile grown by 2]
 //   threads = rows 1 .. TY+2 of the region (TY+2 warps)                       [tile grown by 1 = red region]
 //   tile    = rows 2 .. TY+1, lanes 1 .. 30  => TX = 60 cells x TY rows of output per plane
-constexpr int TX = 60, RW = 64;
+// The z march is unrolled by four (= NSLOT): the four register pairs, the two coefficient sets and the TMA slots
+// rotate by renaming, not by moves, and slot indices are compile-time.
+constexpr int TX = 60, RW = 64, NSLOT = 4;
 
-template <int TY, int NSLOT, bool HAS_B>
+static_assert(mgk::FUSED_PLAIN == 0 && mgk::FUSED_FROM_ZERO == 1 && mgk::FUSED_PROLONG == 2, "mode numbering");
+enum { MODE_PLAIN = 0,     // phi_out = sweep(phi_in)
+       MODE_ZERO = 1,      // phi_in is identically zero (the correction of a fresh MG level): nothing is read for it
+       MODE_PROLONG = 2 }; // phi_in + piecewise-constant prolongation of the coarse correction, added on the fly
+                           // ([Chombo] AMRPoissonOp::prolongIncrement fused into the first post-smoothing sweep)
+
+struct FusedArgs {
+  Geom g;
+  BCk bc;
+  double *out;
+  double alpha, beta, dxinv;
+  int zchunk, redLo, redHi;
+  const double *coarse;   // MODE_PROLONG: coarse correction, local cell (0,0,0)
+  long long csy, csz;
+};
+
+// All five input streams arrive by TMA: per z plane one slot = the halo'd phi plane plus the (TY+2)-row planes of
+// aCoef, lambda, rhs (and bCoef), completed through ONE mbarrier.  Threads never form a global load address.
+template <int TY, bool HAS_B, int MODE>
 struct Fused {
-  static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, NT = 32 * NW;
-  static constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double);
-  static constexpr size_t SMEM = (size_t)NSLOT * PLANE_BYTES + 2 * NW * 32 * sizeof(double) + NSLOT * sizeof(uint64_t);
+  static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, CPLANE = RW * NW, NT = 32 * NW, NCOEF = HAS_B ? 4 : 3;
+  static constexpr int SLOT = PLANE + NCOEF * CPLANE;  // doubles
+  static constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double), CPLANE_BYTES = CPLANE * sizeof(double);
+  static constexpr uint32_t TX_BYTES = (MODE == MODE_ZERO ? 0 : PLANE_BYTES) + NCOEF * CPLANE_BYTES;
+  static constexpr size_t SMEM = (size_t)NSLOT * SLOT * sizeof(double) + 2 * NW * 32 * sizeof(double) + NSLOT * sizeof(uint64_t);
 
-  // per-thread state
-  double2 c0, c1, c2, c3;        // the lane's pair in planes kr-2, kr-1, kr, kr+1 (reds already updated where due)
-  double2 ca, cl, cr, cb;        // coefficient pairs of plane kr (aCoef, lambda, rhs, bCoef)
-  double sa, sl, sr, sb;         // black-cell halves of plane kr-1
-  const double *dense;           // TMA slot of plane kr
-  double *redw;                  // red buffer written this step (plane kr)
-  const double *redr;            // red buffer of plane kr-1
-  int lane, w, s;
-  bool inDom, tile, anyxy, bx0, bxn, by0, byn;
+  const FusedArgs &A;
+  const CUtensorMap *tm_phi, *tm_a, *tm_l, *tm_r, *tm_b;
+  double *slots, *redbuf;
+  uint64_t *full;
+  // thread constants
+  int tid, lane, w, s, cidx, x0, y0, zs, ze, pfirst, plast;
+  long long cofs, cofsm, cofsp;
+  double *outp;   // this lane's pair in the output plane being written; advanced by one plane per step
+  bool inDom, tile, anyxy, bx0, bxn, by0, byn, zloPhys, zhiPhys;
+  // black-cell halves of the coefficient pairs of the plane whose red update ran one step earlier
+  double sa, sl, sr, sb;
 
-  template <int E>
-  __device__ __forceinline__ void step(const Geom &g, const BCk &bc, double alpha, double beta, double dxinv, int kr, bool doRed,
-                                       bool doBlack, bool zloPhys, bool zhiPhys, double *outp) {
+  __device__ __forceinline__ Fused(const FusedArgs &a_) : A(a_) {}
+
+  __device__ __forceinline__ void issue(int plane, int slot) {  // thread 0: stage one plane of every stream
+    double *d = slots + (size_t)slot * SLOT;
+    mbar_arrive_expect_tx(&full[slot], TX_BYTES);
+    const int z = plane + MGIC_GZ;
+    if (MODE != MODE_ZERO) tma_load_3d(d, tm_phi, &full[slot], x0 - 2, y0 - 2, z);
+    tma_load_3d(d + PLANE, tm_a, &full[slot], x0 - 2, y0 - 1, z);
+    tma_load_3d(d + PLANE + CPLANE, tm_l, &full[slot], x0 - 2, y0 - 1, z);
+    tma_load_3d(d + PLANE + 2 * CPLANE, tm_r, &full[slot], x0 - 2, y0 - 1, z);
+    if (HAS_B) tma_load_3d(d + PLANE + 3 * CPLANE, tm_b, &full[slot], x0 - 2, y0 - 1, z);
+  }
+
+  __device__ __forceinline__ double2 load_pair(int plane, const double *slot) const {
+    if (MODE == MODE_ZERO) return make_double2(0.0, 0.0);
+    double2 v = *reinterpret_cast<const double2 *>(slot + s);
+    if (MODE == MODE_PROLONG && inDom) {
+      const double cv = A.coarse[cofs + (long long)(plane >> 1) * A.csz];
+      v.x = v.x + cv; v.y = v.y + cv;   // phi(i,j,k) + coarse(i/2, j/2, k/2)
+    }
+    return v;
+  }
+
+  // one plane step: red update of plane kr (pc), black update + output of plane kr-1 (pm1)
+  template <int E, int U>
+  __device__ __forceinline__ void step(int kr, int it, const double2 &pm2, const double2 &pm1, double2 &pc, double2 &pn) {
     constexpr unsigned FULL = 0xffffffffu;
+    const bool doRed = (kr >= A.redLo && kr <= A.redHi);
+    const bool doBlack = (kr - 1 >= zs && kr - 1 < ze);
+    constexpr int SN = (2 + U) & 3, SC = (1 + U) & 3;
+    // the lane's pair of plane kr+1
+    if (kr + 1 <= plast) mbar_wait(&full[SN], (it + ((2 + U) >> 2)) & 1);
+    pn = load_pair(kr + 1, slots + SN * SLOT);
+    const double *dense = slots + SC * SLOT;
+    double *redw = redbuf + (kr & 1) * NW * 32;
+    const double *redr = redbuf + ((kr - 1) & 1) * NW * 32;
+    const BCk &bc = A.bc;
+    double2 ca, cl, cr, cb;
     if (doRed) {
-      const double c = E ? c2.y : c2.x;
+      ca = *reinterpret_cast<const double2 *>(dense + PLANE + cidx);
+      cl = *reinterpret_cast<const double2 *>(dense + PLANE + CPLANE + cidx);
+      cr = *reinterpret_cast<const double2 *>(dense + PLANE + 2 * CPLANE + cidx);
+      if (HAS_B) cb = *reinterpret_cast<const double2 *>(dense + PLANE + 3 * CPLANE + cidx);
+      const double c = E ? pc.y : pc.x;
       // x neighbours: one lives in the pair, the other in the neighbouring lane's pair (old black value)
-      const double xo = E ? __shfl_down_sync(FULL, c2.x, 1) : __shfl_up_sync(FULL, c2.y, 1);
-      double xm = E ? c2.x : xo, xp = E ? xo : c2.y;
-      double ym = dense[s + E - RW], yp = dense[s + E + RW];
-      double zm = E ? c1.y : c1.x, zp = E ? c3.y : c3.x;
+      const double xo = E ? __shfl_down_sync(FULL, pc.x, 1) : __shfl_up_sync(FULL, pc.y, 1);
+      double xm = E ? pc.x : xo, xp = E ? xo : pc.y;
+      double ym = 0.0, yp = 0.0;
+      if (MODE != MODE_ZERO) { ym = dense[s + E - RW]; yp = dense[s + E + RW]; }
+      if (MODE == MODE_PROLONG && inDom) {
+        const long long ck = (long long)(kr >> 1) * A.csz;
+        ym = ym + A.coarse[cofsm + ck];
+        yp = yp + A.coarse[cofsp + ck];
+      }
+      double zm = E ? pm1.y : pm1.x, zp = E ? pn.y : pn.x;
       if (anyxy) {
         if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
         if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
@@ -100,23 +168,21 @@ struct Fused {
         if (byn) yp = bc.a[3] * c + bc.b[3];
       }
       if (kr == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-      if (kr == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
-      const bool act = inDom && !(E == 0 && lane == 0) && !(E == 1 && lane == 31);
-      double nv = c;
-      if (act)
-        nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, E ? ca.y : ca.x, HAS_B ? (E ? cb.y : cb.x) : 1.0, E ? cl.y : cl.x,
-                               E ? cr.y : cr.x, alpha, beta, dxinv);
-      if (E) c2.y = nv; else c2.x = nv;
+      if (kr == A.g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+      // lanes outside the red region / the domain compute a value nobody reads (their coefficients are zero-filled)
+      const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, E ? ca.y : ca.x, HAS_B ? (E ? cb.y : cb.x) : 1.0,
+                                          E ? cl.y : cl.x, E ? cr.y : cr.x, A.alpha, A.beta, A.dxinv);
+      if (E) pc.y = nv; else pc.x = nv;
       redw[w * 32 + lane] = nv;
     }
     if (doBlack) {
       const int kb = kr - 1;
-      const double c = E ? c1.y : c1.x;
-      const double xo = E ? __shfl_down_sync(FULL, c1.x, 1) : __shfl_up_sync(FULL, c1.y, 1);  // neighbour pair's new red
-      double xm = E ? c1.x : xo, xp = E ? xo : c1.y;
+      const double c = E ? pm1.y : pm1.x;
+      const double xo = E ? __shfl_down_sync(FULL, pm1.x, 1) : __shfl_up_sync(FULL, pm1.y, 1);  // neighbour pair's new red
+      double xm = E ? pm1.x : xo, xp = E ? xo : pm1.y;
       if (tile) {
         double ym = redr[(w - 1) * 32 + lane], yp = redr[(w + 1) * 32 + lane];
-        double zm = E ? c0.y : c0.x, zp = E ? c2.y : c2.x;
+        double zm = E ? pm2.y : pm2.x, zp = E ? pc.y : pc.x;
         if (anyxy) {
           if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
           if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
@@ -124,129 +190,94 @@ struct Fused {
           if (byn) yp = bc.a[3] * c + bc.b[3];
         }
         if (kb == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-        if (kb == g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
-        const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, sa, HAS_B ? sb : 1.0, sl, sr, alpha, beta, dxinv);
-        const double2 o = E ? make_double2(c1.x, nv) : make_double2(nv, c1.y);
+        if (kb == A.g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+        const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, sa, HAS_B ? sb : 1.0, sl, sr, A.alpha, A.beta, A.dxinv);
+        const double2 o = E ? make_double2(pm1.x, nv) : make_double2(nv, pm1.y);
         *reinterpret_cast<double2 *>(outp) = o;
       }
     }
+    outp += A.g.sz;
     if (doRed) {  // keep the black-cell halves of plane kr for the next step
       sa = E ? ca.x : ca.y; sl = E ? cl.x : cl.y; sr = E ? cr.x : cr.y;
       if (HAS_B) sb = E ? cb.x : cb.y;
     }
+    __syncthreads();
+    // plane kr's slot is dead: its phi pair was copied a step ago, its y neighbours and coefficients were read above
+    if (tid == 0 && kr + NSLOT <= plast) issue(kr + NSLOT, SC);
+  }
+
+  template <int E0>
+  __device__ __forceinline__ void march(double2 p1, double2 p2) {
+    double2 p0 = make_double2(0.0, 0.0), p3 = p0;
+    for (int it = 0;; it++) {
+      const int kr = zs - 1 + 4 * it;
+      if (kr > ze) break;
+      step<E0, 0>(kr, it, p0, p1, p2, p3);
+      if (kr + 1 > ze) break;
+      step<1 - E0, 1>(kr + 1, it, p1, p2, p3, p0);
+      if (kr + 2 > ze) break;
+      step<E0, 2>(kr + 2, it, p2, p3, p0, p1);
+      if (kr + 3 > ze) break;
+      step<1 - E0, 3>(kr + 3, it, p3, p0, p1, p2);
+    }
+  }
+
+  __device__ __forceinline__ void run(unsigned char *smem_raw) {
+    slots = reinterpret_cast<double *>(smem_raw);
+    redbuf = reinterpret_cast<double *>(smem_raw + (size_t)NSLOT * SLOT * sizeof(double));
+    full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * SLOT * sizeof(double) + 2 * NW * 32 * sizeof(double));
+    tid = threadIdx.x;
+    x0 = blockIdx.x * TX; y0 = blockIdx.y * TY;
+    zs = blockIdx.z * A.zchunk; ze = min(zs + A.zchunk, A.g.nz);
+    pfirst = zs - 2; plast = ze + 1;
+    if (tid == 0) {
+      for (int q = 0; q < NSLOT; q++) mbar_init(&full[q], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int p = pfirst; p < pfirst + NSLOT && p <= plast; p++) issue(p, p - pfirst);
+    lane = tid & 31; w = tid >> 5;
+    const int rr = w + 1;
+    const int x = x0 - 2 + 2 * lane, y = y0 - 2 + rr;
+    inDom = (x >= 0 && x + 1 < A.g.nx && y >= 0 && y < A.g.ny);
+    tile = inDom && w >= 1 && w <= TY && lane >= 1 && lane <= 30;
+    bx0 = (x == 0); bxn = (x == A.g.nx - 2); by0 = (y == 0); byn = (y == A.g.ny - 1);
+    anyxy = bx0 || bxn || by0 || byn;
+    s = rr * RW + 2 * lane;
+    cidx = w * RW + 2 * lane;
+    outp = A.out + (x + (long long)y * A.g.sy + (long long)(zs - 2) * A.g.sz);  // plane kr-1 at the first step (kr = zs-1)
+    cofs = cofsm = cofsp = 0;
+    if (MODE == MODE_PROLONG && inDom) {
+      cofs = (x >> 1) + (long long)(y >> 1) * A.csy;
+      cofsm = (x >> 1) + (long long)(max(y - 1, 0) >> 1) * A.csy;
+      cofsp = (x >> 1) + (long long)(min(y + 1, A.g.ny - 1) >> 1) * A.csy;
+    }
+    zloPhys = A.bc.type[4] != MGIC_FACE_INTERIOR; zhiPhys = A.bc.type[5] != MGIC_FACE_INTERIOR;
+    sa = sl = sr = sb = 0.0;
+    // prologue: the lane's pairs of planes zs-2 and zs-1
+    mbar_wait(&full[0], 0);
+    const double2 p1 = load_pair(zs - 2, slots);
+    mbar_wait(&full[1], 0);
+    const double2 p2 = load_pair(zs - 1, slots + SLOT);
+    __syncthreads();
+    if (tid == 0 && pfirst + NSLOT <= plast) issue(pfirst + NSLOT, 0);  // slot of plane zs-2 is free again
+    const int e0 = ((y & 1) + zs - 1 + A.g.k0) & 1;  // warp-uniform: element of the pair that is red in plane zs-1
+    if (e0) march<1>(p1, p2);
+    else march<0>(p1, p2);
   }
 };
 
-template <int TY, int NSLOT, bool HAS_B, int MINB>
+template <int TY, bool HAS_B, int MODE, int MINB>
 __global__ void __launch_bounds__(32 * (TY + 2), MINB)
-k_gsrb_fused(const __grid_constant__ CUtensorMap tmap, Geom g, BCk bc, double *__restrict__ out, const double *__restrict__ rhs,
-             const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ lam, double alpha, double beta,
-             double dxinv, int zchunk, int redLo, int redHi) {
-  using F = Fused<TY, NSLOT, HAS_B>;
-  constexpr int PLANE = F::PLANE, NW = F::NW;
-  constexpr uint32_t PLANE_BYTES = F::PLANE_BYTES;
-  static_assert(PLANE_BYTES % 128 == 0, "TMA destination slots must stay 128-byte aligned");
+k_gsrb_fused(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_l,
+             const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_b, const FusedArgs A) {
+  using F = Fused<TY, HAS_B, MODE>;
+  static_assert(F::PLANE_BYTES % 128 == 0 && F::CPLANE_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *planes = reinterpret_cast<double *>(smem_raw);
-  double *redbuf = reinterpret_cast<double *>(smem_raw + (size_t)NSLOT * PLANE_BYTES);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * PLANE_BYTES + 2 * NW * 32 * sizeof(double));
-
-  const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int zs = blockIdx.z * zchunk, ze = min(zs + zchunk, g.nz);
-  const int pfirst = zs - 2, plast = ze + 1;  // planes staged
-
-  if (tid == 0) {
-    for (int s = 0; s < NSLOT; s++) mbar_init(&full[s], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int p = pfirst; p < pfirst + NSLOT && p <= plast; p++) {
-      const int sl = p - pfirst;
-      mbar_arrive_expect_tx(&full[sl], PLANE_BYTES);
-      tma_load_3d(planes + (size_t)sl * PLANE, &tmap, &full[sl], x0 - 2, y0 - 2, p + MGIC_GZ);
-    }
-  }
-
-  F st;
-  st.lane = tid & 31;
-  st.w = tid >> 5;
-  const int rr = st.w + 1;
-  const int x = x0 - 2 + 2 * st.lane, y = y0 - 2 + rr;
-  st.inDom = (x >= 0 && x + 1 < g.nx && y >= 0 && y < g.ny);
-  st.tile = st.inDom && st.w >= 1 && st.w <= TY && st.lane >= 1 && st.lane <= 30;
-  st.bx0 = (x == 0); st.bxn = (x == g.nx - 2); st.by0 = (y == 0); st.byn = (y == g.ny - 1);
-  st.anyxy = st.bx0 || st.bxn || st.by0 || st.byn;
-  st.s = rr * RW + 2 * st.lane;
-  const int yodd = y & 1;
-  const long long gofs = x + (long long)y * g.sy;
-  const bool zloPhys = bc.type[4] != MGIC_FACE_INTERIOR, zhiPhys = bc.type[5] != MGIC_FACE_INTERIOR;
-  const double2 zero2 = make_double2(0.0, 0.0);
-  st.c0 = zero2; st.sa = st.sl = st.sr = st.sb = 0.0;
-  st.ca = st.cl = st.cr = st.cb = zero2;
-
-  // prologue: the lane's pairs of planes zs-2 and zs-1; coefficient pairs of the first red plane
-  mbar_wait(&full[0], 0);
-  st.c1 = *reinterpret_cast<const double2 *>(planes + st.s);
-  if (plast >= pfirst + 1) mbar_wait(&full[1 % NSLOT], 0);
-  st.c2 = *reinterpret_cast<const double2 *>(planes + (size_t)(1 % NSLOT) * PLANE + st.s);
-  {
-    const int k = zs - 1;
-    if (st.inDom && k >= redLo && k <= redHi) {
-      const long long gi = gofs + (long long)k * g.sz;
-      st.ca = *reinterpret_cast<const double2 *>(a + gi);
-      st.cl = *reinterpret_cast<const double2 *>(lam + gi);
-      st.cr = *reinterpret_cast<const double2 *>(rhs + gi);
-      if (HAS_B) st.cb = *reinterpret_cast<const double2 *>(b + gi);
-    }
-  }
-  __syncthreads();
-  if (tid == 0 && pfirst + NSLOT <= plast) {  // slot of plane zs-2 is free again
-    mbar_arrive_expect_tx(&full[0], PLANE_BYTES);
-    tma_load_3d(planes, &tmap, &full[0], x0 - 2, y0 - 2, pfirst + NSLOT + MGIC_GZ);
-  }
-
-  for (int kr = zs - 1; kr <= ze; kr++) {
-    const bool doRed = (kr >= redLo && kr <= redHi);
-    const bool doBlack = (kr - 1 >= zs && kr - 1 < ze);
-    // prefetch the coefficient pairs of plane kr+1 (consumed by the next step's red update)
-    double2 na = zero2, nl = zero2, nr = zero2, nb = zero2;
-    const bool nextRed = (kr + 1 >= redLo && kr + 1 <= redHi && kr + 1 <= ze);
-    if (st.inDom && nextRed) {
-      const long long gi = gofs + (long long)(kr + 1) * g.sz;
-      na = *reinterpret_cast<const double2 *>(a + gi);
-      nl = *reinterpret_cast<const double2 *>(lam + gi);
-      nr = *reinterpret_cast<const double2 *>(rhs + gi);
-      if (HAS_B) nb = *reinterpret_cast<const double2 *>(b + gi);
-    }
-    // the lane's pair of plane kr+1
-    if (kr + 1 <= plast) {
-      const int q = kr + 1 - pfirst;
-      mbar_wait(&full[q % NSLOT], (q / NSLOT) & 1);
-      st.c3 = *reinterpret_cast<const double2 *>(planes + (size_t)(q % NSLOT) * PLANE + st.s);
-    }
-    st.dense = planes + (size_t)((kr - pfirst) % NSLOT) * PLANE;
-    st.redw = redbuf + (size_t)(kr & 1) * NW * 32;
-    st.redr = redbuf + (size_t)((kr - 1) & 1) * NW * 32;
-    double *outp = out + gofs + (long long)(kr - 1) * g.sz;
-    const int e = (yodd + kr + g.k0) & 1;  // warp-uniform: element of the pair that is red in plane kr
-    if (e) st.template step<1>(g, bc, alpha, beta, dxinv, kr, doRed, doBlack, zloPhys, zhiPhys, outp);
-    else st.template step<0>(g, bc, alpha, beta, dxinv, kr, doRed, doBlack, zloPhys, zhiPhys, outp);
-    st.c0 = st.c1; st.c1 = st.c2; st.c2 = st.c3;
-    st.ca = na; st.cl = nl; st.cr = nr;
-    if (HAS_B) st.cb = nb;
-    __syncthreads();
-    // plane kr's slot is dead (pair copied a step ago, y neighbours read by this step's red update)
-    if (tid == 0) {
-      const int pn = kr + NSLOT;
-      if (pn <= plast) {
-        const int sl = (kr - pfirst) % NSLOT;
-        mbar_arrive_expect_tx(&full[sl], PLANE_BYTES);
-        tma_load_3d(planes + (size_t)sl * PLANE, &tmap, &full[sl], x0 - 2, y0 - 2, pn + MGIC_GZ);
-      }
-    }
-  }
+  F f(A);
+  f.tm_phi = &tm_phi; f.tm_a = &tm_a; f.tm_l = &tm_l; f.tm_r = &tm_r; f.tm_b = &tm_b;
+  f.run(smem_raw);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -298,11 +329,11 @@ Plan plan_chunks(int tiles, int nz, int resident) {
   return best;
 }
 
-template <int TY, int NSLOT, bool HAS_B, int MINB>
-int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
-  using F = Fused<TY, NSLOT, HAS_B>;
+template <int TY, bool HAS_B, int MODE, int MINB>
+int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
+  using F = Fused<TY, HAS_B, MODE>;
   mgic_ctx *c = o->ctx;
-  auto kern = k_gsrb_fused<TY, NSLOT, HAS_B, MINB>;
+  auto kern = k_gsrb_fused<TY, HAS_B, MODE, MINB>;
   static bool attrSet = false;
   static int resident = 1;
   if (!attrSet) {
@@ -312,36 +343,55 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r) 
     resident = (per < 1 ? 1 : per) * c->numSMs;
     attrSet = true;
   }
-  const Geom g = o->geom();
-  const BCk bc = o->bck(true);
-  CUtensorMap tm;
-  MGIC_TRY(make_tmap(&tm, in - (long long)MGIC_GZ * g.sz, g.nx, g.ny, g.nz + 2 * MGIC_GZ, RW, F::RR));
-  const int tilesX = (g.nx + TX - 1) / TX, tilesY = (g.ny + TY - 1) / TY;
-  const Plan pl = plan_chunks(tilesX * tilesY, g.nz, resident);
-  const int redLo = (bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
-  const int redHi = (bc.type[5] == MGIC_FACE_INTERIOR) ? g.nz : g.nz - 1;
+  FusedArgs A;
+  A.g = o->geom();
+  A.bc = o->bck(true);
+  A.out = outp;
+  A.alpha = o->alpha; A.beta = o->beta; A.dxinv = 1.0 / (o->dx * o->dx);
+  A.coarse = coarse ? coarse->p : nullptr; A.csy = coarse ? coarse->sy : 0; A.csz = coarse ? coarse->sz : 0;
+  const int np = A.g.nz + 2 * MGIC_GZ;
+  const long long goff = (long long)MGIC_GZ * A.g.sz;
+  CUtensorMap tp, ta, tl, tr, tb;
+  MGIC_TRY(make_tmap(&ta, o->a->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
+  MGIC_TRY(make_tmap(&tl, o->lambda->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
+  MGIC_TRY(make_tmap(&tr, r->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
+  if (HAS_B) MGIC_TRY(make_tmap(&tb, o->b->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
+  else tb = ta;
+  if (MODE != MODE_ZERO) MGIC_TRY(make_tmap(&tp, in - goff, A.g.nx, A.g.ny, np, RW, F::RR));
+  else tp = ta;
+  const int tilesX = (A.g.nx + TX - 1) / TX, tilesY = (A.g.ny + TY - 1) / TY;
+  const Plan pl = plan_chunks(tilesX * tilesY, A.g.nz, resident);
+  A.zchunk = pl.zchunk;
+  A.redLo = (A.bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
+  A.redHi = (A.bc.type[5] == MGIC_FACE_INTERIOR) ? A.g.nz : A.g.nz - 1;
   dim3 grd(tilesX, tilesY, pl.nch);
-  kern<<<grd, F::NT, F::SMEM, c->stream>>>(tm, g, bc, outp, r->p, o->a->p, o->b ? o->b->p : nullptr, o->lambda->p, o->alpha, o->beta,
-                                           1.0 / (o->dx * o->dx), pl.zchunk, redLo, redHi);
+  kern<<<grd, F::NT, F::SMEM, c->stream>>>(tp, ta, tl, tr, tb, A);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { mgic_set_error("kernel gsrb_fused: %s", cudaGetErrorString(e)); return MGIC_ERR_CUDA; }
   return MGIC_OK;
 }
 
-template <bool HAS_B>
-int launch(mgic_op *o, const double *in, double *outp, const mgic_field *r) {
+template <bool HAS_B, int MODE>
+int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
   switch (o->ctx->fusedCfg) {
-    case 0: return launch_cfg<8, 4, HAS_B, 2>(o, in, outp, r);
-    case 2: return launch_cfg<24, 4, HAS_B, 1>(o, in, outp, r);
-    case 3: return launch_cfg<16, 6, HAS_B, 1>(o, in, outp, r);
-    case 4: return launch_cfg<8, 6, HAS_B, 2>(o, in, outp, r);
-    case 1: return launch_cfg<16, 4, HAS_B, 1>(o, in, outp, r);
-    case 6: return launch_cfg<12, 6, HAS_B, 2>(o, in, outp, r);
-    case 7: return launch_cfg<10, 4, HAS_B, 2>(o, in, outp, r);
-    case 8: return launch_cfg<6, 4, HAS_B, 3>(o, in, outp, r);
-    default: return launch_cfg<12, 4, HAS_B, 2>(o, in, outp, r);
+    case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse);
+    case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse);
+    case 2: return launch_cfg<12, HAS_B, MODE, 1>(o, in, outp, r, coarse);
+    case 3: return launch_cfg<6, HAS_B, MODE, 3>(o, in, outp, r, coarse);
+    default: return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse);
   }
+}
+
+int launch(mgic_op *o, int mode, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
+  if (o->b) {
+    if (mode == MODE_ZERO) return launch_mode<true, MODE_ZERO>(o, in, outp, r, coarse);
+    if (mode == MODE_PROLONG) return launch_mode<true, MODE_PROLONG>(o, in, outp, r, coarse);
+    return launch_mode<true, MODE_PLAIN>(o, in, outp, r, coarse);
+  }
+  if (mode == MODE_ZERO) return launch_mode<false, MODE_ZERO>(o, in, outp, r, coarse);
+  if (mode == MODE_PROLONG) return launch_mode<false, MODE_PROLONG>(o, in, outp, r, coarse);
+  return launch_mode<false, MODE_PLAIN>(o, in, outp, r, coarse);
 }
 
 }  // namespace
@@ -361,15 +411,19 @@ bool gsrb_fused_applicable(const mgic_op *o) {
 
 // relax(e, r, iterations) with fused sweeps.  Multi-rank: one 2-plane halo exchange of e per sweep (the neighbour's
 // first plane is updated redundantly) instead of the reference's two 1-plane exchanges, plus one of rhs per call.
-int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations) {
+// first = FUSED_FROM_ZERO: e is known to be zero (setToZero + relax of [Chombo] MultiGrid::cycle); first =
+// FUSED_PROLONG: e += prolong(coarse) is applied on the fly by the first sweep (prolongIncrement + relax).
+int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, int first, const mgic_field *coarse) {
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
-  if (o->ctx->nranks > 1) MGIC_TRY(mgic_halo(o, const_cast<mgic_field *>(r), 1));
+  const bool multi = o->ctx->nranks > 1;
+  if (multi) MGIC_TRY(mgic_halo(o, const_cast<mgic_field *>(r), 1));
+  if (multi && first == FUSED_PROLONG) MGIC_TRY(mgic_halo_shape(o->ctx, const_cast<mgic_field *>(coarse), 1));
   for (int it = 0; it < iterations; it++) {
-    if (o->ctx->nranks > 1) MGIC_TRY(mgic_halo(o, e, 2));
+    const int mode = (it == 0) ? first : FUSED_PLAIN;
+    if (multi && mode != FUSED_FROM_ZERO) MGIC_TRY(mgic_halo(o, e, 2));
     {
       ProfScope ps(o->ctx, o->profTag);
-      if (o->b) MGIC_TRY(launch<true>(o, e->p, o->scratch->p, r));
-      else MGIC_TRY(launch<false>(o, e->p, o->scratch->p, r));
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse));
     }
     std::swap(e->base, o->scratch->base);  // ping-pong: the field handle now owns the freshly written array
     std::swap(e->p, o->scratch->p);

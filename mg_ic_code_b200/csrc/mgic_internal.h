@@ -73,6 +73,7 @@ struct mgic_ctx {
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
   int bottomKernel = 1;                   // bottom BiCGStab: 1 one persistent kernel in a thread-block cluster, 3 same as a
                                           // cooperative grid, 0 host-driven launches (bottom.cu)
+  int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
@@ -164,7 +165,10 @@ int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *c
 int mgic_halo(mgic_op *, mgic_field *, int planes);
 bool gsrb_fused_applicable(const mgic_op *);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
-int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations);
+enum { FUSED_PLAIN = 0, FUSED_FROM_ZERO = 1, FUSED_PROLONG = 2 };
+int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations, int first = FUSED_PLAIN,
+               const mgic_field *coarse = nullptr);
+int mgic_halo_shape(mgic_ctx *, mgic_field *, int planes);  // halo exchange of a field of any level
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)
 struct FabView { double *p; int lo[3]; long long s1, s2, sc; };
 }  // namespace mgk

@@ -258,6 +258,10 @@ class VariableCoeffPoissonOperatorFactory:
     def vcycle(self, e, r):
         check(self.L.mgic_mg_vcycle(self.h, e.h, r.h))
 
+    # setToZero(e); oneCycle(e, r) -- the first V-cycle of [Chombo] MultilevelLinearOp::preCond
+    def vcycle_from_zero(self, e, r):
+        check(self.L.mgic_mg_vcycle_from_zero(self.h, e.h, r.h))
+
     def bottom_solve(self, e, r):
         it = C.c_int()
         check(self.L.mgic_mg_bottom_solve(self.h, e.h, r.h, C.byref(it)))

@@ -104,7 +104,7 @@ def test_kernels_bit_exact(ctx, case, keep_b):
     assert np.array_equal(p.e.download(), p.o.get("E"))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
 def test_fused_smoother_bit_exact(ctx, case, cfg):
     """fused red+black plane-streaming sweep (TMA-staged halo'd planes) == per-colour oracle sweeps, every tile shape,
@@ -126,7 +126,7 @@ def test_fused_smoother_bit_exact(ctx, case, cfg):
                 assert np.array_equal(ed.download(), p.o.get("E", d)), (d, its)
     finally:
         ctx.set_option("fused_min_cells", 2097152)
-        ctx.set_option("fused_cfg", 5)
+        ctx.set_option("fused_cfg", 4)
 
 
 def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
@@ -143,28 +143,47 @@ def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
 
 
 def test_graph_and_bottom_kernel_variants_agree(ctx):
-    """CUDA-graph replay == eager launches bit for bit; persistent bottom kernel vs host-driven BiCGStab differ only by
-    the summation order of the bottom solver's dot products."""
+    """CUDA-graph replay == eager launches bit for bit; fused sweeps on every level, with setToZero / prolongIncrement
+    folded into the following sweep or not, == per-colour kernels bit for bit; the bottom-solver variants (persistent
+    cluster kernel, cooperative-grid kernel, host-driven launches) differ only by the summation order of its dot products."""
+    base = dict(use_graph=1, bottom_kernel=1, fuse_transfers=1, fused_min_cells=2097152)
+    variants = {
+        "eager_host": dict(use_graph=0, bottom_kernel=0),
+        "eager_dev": dict(use_graph=0),
+        "eager_coop": dict(use_graph=0, bottom_kernel=3),
+        "graph_dev": dict(),
+        "fused_all": dict(fused_min_cells=0),
+        "fused_all_eager": dict(fused_min_cells=0, use_graph=0),
+        "fused_all_unfolded": dict(fused_min_cells=0, fuse_transfers=0),
+        "colour_only": dict(smoother=0),
+    }
     results = {}
-    for name, opts in (("eager_host", dict(use_graph=0, bottom_kernel=0)), ("eager_dev", dict(use_graph=0, bottom_kernel=1)),
-                       ("eager_coop", dict(use_graph=0, bottom_kernel=3)),
-                       ("graph_dev", dict(use_graph=1, bottom_kernel=1))):
-        for k, v in opts.items():
-            ctx.set_option(k, v)
-        try:
-            p = Pair(ctx, **dict(CASES["c64"], numMGsmooth=2))
-            p.r.upload(p.o.get("RHS")); p.op.setToZero(p.e)
-            its = []
-            for _ in range(3):
-                p.f.vcycle(p.e, p.r)
+    try:
+        for name, opts in variants.items():
+            cfg = dict(base, **{k: v for k, v in opts.items() if k != "smoother"})
+            for k, v in cfg.items():
+                ctx.set_option(k, v)
+            for smooth in (2, 3):   # odd sweep counts exercise the ping-pong parity handling of the graph capture
+                p = Pair(ctx, smoother=opts.get("smoother"), **dict(CASES["c64"], numMGsmooth=smooth))
+                p.r.upload(p.o.get("RHS")); p.op.setToZero(p.e)
+                its = []
+                p.f.vcycle_from_zero(p.e, p.r)
                 its.append(p.f.last_bottom_iterations)
-            results[name] = (p.e.download(), its)
-        finally:
-            ctx.set_option("use_graph", 1); ctx.set_option("bottom_kernel", 1)
-    assert np.array_equal(results["eager_dev"][0], results["graph_dev"][0])
-    assert results["eager_dev"][1] == results["graph_dev"][1] == results["eager_host"][1] == results["eager_coop"][1]
-    assert relerr(results["eager_dev"][0], results["eager_coop"][0]) < 1e-11
-    assert relerr(results["eager_dev"][0], results["eager_host"][0]) < 1e-11
+                for _ in range(2):
+                    p.f.vcycle(p.e, p.r)
+                    its.append(p.f.last_bottom_iterations)
+                results[name, smooth] = (p.e.download(), its)
+    finally:
+        for k, v in base.items():
+            ctx.set_option(k, v)
+    for smooth in (2, 3):
+        ref = results["eager_dev", smooth]
+        for name in ("graph_dev", "fused_all", "fused_all_eager", "fused_all_unfolded", "colour_only"):
+            assert np.array_equal(results[name, smooth][0], ref[0]), (name, smooth)
+            assert results[name, smooth][1] == ref[1]
+        for name in ("eager_host", "eager_coop"):
+            assert results[name, smooth][1] == ref[1]
+            assert relerr(results[name, smooth][0], ref[0]) < 1e-11, (name, smooth)
 
 
 def test_reductions_and_blas1(ctx):
@@ -215,7 +234,8 @@ def test_vcycle_parity(ctx, case, smooth):
         p.op.residual(p.t, p.e, p.r, True)
         ro = np.abs(p.o.residual(0, True)).max()
         rg = p.op.norm(p.t, 0)
-        assert abs(rg - ro) <= 1e-10 * max(ro, 1e-300) + 1e-16 * np.abs(rhs).max(), (cyc, rg, ro)
+        # floor: the residual is a difference of O(|rhs|) terms, so it carries ~1e-13 |rhs| of evaluation round-off
+        assert abs(rg - ro) <= 1e-10 * ro + 1e-13 * np.abs(rhs).max(), (cyc, rg, ro)
 
 
 @pytest.mark.parametrize("name,cycles,over", [
