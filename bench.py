@@ -284,8 +284,14 @@ def run_gpu(args):
         e2e_val = cells_total / (ms_e2e / e2e_steps * 1e-3) / 1e9
         sweep_b, level_b = algorithmic_bytes_per_cell(args.smooth, args.keep_b)
         peak, peak_src = peaks()
-        per_launch_cells = cells_local if args.smoother == 1 else cells_local / 2.0   # one launch = a sweep / a colour pass
-        alg_bytes_launch = sweep_b * per_launch_cells if args.smoother == 1 else sweep_b / 2.0 * cells_local
+        # one launch = a sweep (fused) or a colour pass.  Fused sweeps of one V-cycle on the finest level: the first
+        # pre-smoothing sweep starts from the zero correction (no read of e: -8 B/cell), the first post-smoothing sweep
+        # adds the prolonged coarse correction on the fly (+1 B/cell); average over the 2*S sweeps.
+        if args.smoother == 1:
+            S2 = 2 * args.smooth
+            alg_bytes_launch = ((sweep_b - 8) + (sweep_b + 1) + (S2 - 2) * sweep_b) / S2 * cells_local
+        else:
+            alg_bytes_launch = sweep_b / 2.0 * cells_local
         kdur = k_ms / max(k_launches, 1) * 1e-3
         achieved = alg_bytes_launch / kdur / 1e9 if k_launches else None
         vcycle_bytes = level_b * cells_local * sum(1.0 / 8 ** d for d in range(f.depths))
