@@ -36,6 +36,22 @@ def algorithmic_bytes_per_cell(smooth, keep_b):
     return sweep, level
 
 
+def profiled_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/), valid for the configuration it was taken on (512^3, bCoef dropped, default tile shape)."""
+    p = os.path.join(ROOT, "profiles", "r1_fused_v4_ncu_summary.json")
+    if not (os.path.exists(p) and args.n == 512 and not args.keep_b and args.smoother == 1 and args.fused_cfg in (None, 4)):
+        return None
+    try:
+        m = json.load(open(p))["metrics"]
+        rd = [float(x) for x in m["dram__bytes_read.sum"]["per_launch"]]
+        wr = [float(x) for x in m["dram__bytes_write.sum"]["per_launch"]]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m["dram__bytes_read.sum"]["unit"]]
+        return (sum(rd) / len(rd) + sum(wr) / len(wr)) * scale
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -302,7 +318,8 @@ def run_gpu(args):
                                                 global_cells=cells_total),
             "roofline": {"bound": "hbm", "kernel": "finest-level GSRB " + ("fused red+black sweep" if args.smoother == 1 else "colour pass"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "traffic": profiled_traffic(args),
+                         "traffic_source": "profiles/r1_fused_v4_ncu_summary.json (ncu --set full, plain sweep)", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
                          "launches_timed": k_launches, "avg_launch_ms": kdur * 1e3,
                          "kernel_share_of_step": k_ms / ms_prof,
                          "share_measured_on": "second pass of the same K steps launched eagerly with per-launch CUDA events "

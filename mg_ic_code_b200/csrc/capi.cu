@@ -234,7 +234,7 @@ extern "C" int mgic_op_reset_lambda(mgic_op *o) {
   if (!o->lambda) MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
   if (!o->lambdaDirty) return MGIC_OK;
   MGIC_TRY(mgk::compute_lambda(o->ctx, o->geom(), o->lambda->p, o->a->p, o->alpha, o->beta, o->dx));
-  if (o->ctx->nranks > 1) {  // the fused sweep updates the neighbour's first plane redundantly: it needs its coefficients
+  if (o->ctx->nranks > 1 && !o->isGlobal) {  // the fused sweep updates the neighbour's first plane redundantly: it needs its coefficients
     MGIC_TRY(mgk::mgic_halo(o, o->a, 1));
     MGIC_TRY(mgk::mgic_halo(o, o->lambda, 1));
     if (o->b) MGIC_TRY(mgk::mgic_halo(o, o->b, 1));
@@ -342,7 +342,7 @@ extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy,
 
 // ------------------------------------------------------------------------------------------------ op methods
 int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
-  if (o->ctx->nranks > 1) {
+  if (o->ctx->nranks > 1 && !o->isGlobal) {
     MGIC_REQUIRE(o->ctx->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
     return o->ctx->halo_exchange(o->ctx, f, planes);
   }
@@ -629,6 +629,11 @@ struct mgic_mg {
   struct VGraph { const void *e, *r; bool zero; cudaGraphExec_t exec; long long launches; };
   std::vector<VGraph> graphs;
   bool graphBroken = false;
+  // multi-rank: the bottom level agglomerated on EVERY rank (all-gather, redundant one-kernel solve, keep the own slab)
+  mgic_op *gbOp = nullptr;
+  mgic_field *gbA = nullptr, *gbB = nullptr, *gbE = nullptr, *gbR = nullptr;
+  BiCGWork gbWork;
+  bool warm = false;   // multi-rank: one eager V-cycle has run (NCCL connections exist) before graph capture
 };
 
 static int mg_coarsen_coefs(mgic_mg *mg) {
@@ -647,6 +652,13 @@ static int mg_coarsen_coefs(mgic_mg *mg) {
     MGIC_TRY(mgic_op_compute_lambda(o));  // :229
   }
   MGIC_TRY(mgic_op_compute_lambda(mg->ops[0]));
+  if (mg->gbOp) {  // coefficients of the agglomerated bottom level
+    mgic_op *bo = mg->ops.back();
+    const size_t cnt = (size_t)bo->n[0] * bo->n[1] * bo->nzl;
+    MGIC_TRY(mg->ctx->allgather(mg->ctx, bo->a->p, mg->gbA->p, cnt));
+    if (mg->gbB) MGIC_TRY(mg->ctx->allgather(mg->ctx, bo->b->p, mg->gbB->p, cnt));
+    MGIC_TRY(mgic_op_compute_lambda(mg->gbOp));
+  }
   return MGIC_OK;
 }
 
@@ -712,6 +724,19 @@ extern "C" int mgic_mg_create_ex(mgic_ctx *c, const mgic_params *P, mgic_field *
     mg->e.push_back(ea); mg->r.push_back(ra); mg->aOwn.push_back(aa); mg->bOwn.push_back(ba);
   }
   mg->nd = (int)mg->ops.size();
+  if (c->nranks > 1 && c->bottomKernel && c->allgather) {
+    mgic_op *bo = mg->ops.back();
+    if (bo->nzl * c->nranks == bo->n[2] && bo->k0 == c->rank * bo->nzl) {  // equal slabs in rank order
+      MGIC_TRY(mgic_op_create(c, bo->n, 0, bo->n[2], bo->dx, P->alpha, P->beta, bclo, bchi, P->bc_value, &mg->gbOp));
+      mg->gbOp->isGlobal = true;
+      mg->gbOp->profTag = false;
+      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbA));
+      if (!mg->bIsOne) MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbB));
+      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbE));
+      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbR));
+      MGIC_TRY(mgic_op_set_coefs(mg->gbOp, mg->gbA, mg->gbB, P->alpha, P->beta));
+    }
+  }
   MGIC_TRY(mg_coarsen_coefs(mg));
   *out = mg;
   return MGIC_OK;
@@ -722,6 +747,9 @@ extern "C" int mgic_mg_destroy(mgic_mg *mg) {
   cudaStreamSynchronize(mg->ctx->stream);
   mg->bottomWork.release();
   mg->outerWork.release();
+  mg->gbWork.release();
+  mgic_field_destroy(mg->gbA); mgic_field_destroy(mg->gbB); mgic_field_destroy(mg->gbE); mgic_field_destroy(mg->gbR);
+  mgic_op_destroy(mg->gbOp);
   for (auto &g : mg->graphs) cudaGraphExecDestroy(g.exec);
   cudaFree(mg->d_bottomOut);
   for (int d = 0; d < mg->nd; d++) {
@@ -769,6 +797,21 @@ extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field
     MGIC_TRY(mgic_op_reset_lambda(op));
     if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
     MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
+    mg->bottomOnDevice = true;
+    if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
+    return MGIC_OK;
+  }
+  if (mg->gbOp && mg->ctx->bottomKernel) {
+    // multi-rank: every rank gathers the whole bottom level (a few MB over NVLink), solves it redundantly with the
+    // one-kernel solver -- identical bits on every rank, identical to the single-GPU solve -- and keeps its own slab
+    const size_t cnt = (size_t)op->n[0] * op->n[1] * op->nzl;
+    MGIC_TRY(mg->gbWork.alloc(mg->gbOp));
+    if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
+    MGIC_TRY(mg->ctx->allgather(mg->ctx, e->p, mg->gbE->p, cnt));
+    MGIC_TRY(mg->ctx->allgather(mg->ctx, r->p, mg->gbR->p, cnt));
+    MGIC_TRY(mgk::bottom_bicgstab(mg->gbOp, mg->gbE, mg->gbR, mg->gbWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
+    MGIC_CUDA(cudaMemcpyAsync(e->p, mg->gbE->p + (size_t)op->k0 * op->n[0] * op->n[1], cnt * sizeof(double), cudaMemcpyDeviceToDevice,
+                              mg->ctx->stream));
     mg->bottomOnDevice = true;
     if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
     return MGIC_OK;
@@ -837,8 +880,12 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
 // single kernel), so it is captured once per (correction, residual) pair and afterwards costs one graph launch.
 static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZero = false) {
   mgic_ctx *c = mg->ctx;
-  const bool graphable = c->useGraph && c->bottomKernel && c->nranks == 1 && !c->profiling && !mg->graphBroken;
+  const bool graphable = c->useGraph && c->bottomKernel && (c->nranks == 1 || mg->gbOp) && !c->profiling && !mg->graphBroken;
   if (!graphable) return mg_cycle(mg, 0, e, r, eIsZero);
+  if (c->nranks > 1 && !mg->warm) {  // NCCL sets up its connections on first use: not inside a capture
+    mg->warm = true;
+    return mg_cycle(mg, 0, e, r, eIsZero);
+  }
   for (auto &g : mg->graphs)
     if (g.e == e->p && g.r == r->p && g.zero == eIsZero) {
       MGIC_CUDA(cudaGraphLaunch(g.exec, c->stream));
@@ -848,6 +895,7 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
     }
   // everything the cycle allocates lazily must exist before capture
   MGIC_TRY(mg->bottomWork.alloc(mg->ops.back()));
+  if (mg->gbOp) MGIC_TRY(mg->gbWork.alloc(mg->gbOp));
   if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
   for (auto *o : mg->ops) {
     MGIC_TRY(mgic_op_reset_lambda(o));
@@ -864,7 +912,7 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
   const long long l0 = c->launches;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  bool ok = cudaStreamBeginCapture(c->stream, c->nranks > 1 ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal) == cudaSuccess;
   int rc = MGIC_OK;
   if (ok) {
     rc = mg_cycle(mg, 0, e, r, eIsZero);

@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   const char *(*GetErrorString)(ncclResult_t);
 };
 
@@ -38,7 +39,7 @@ NcclApi *api() {
   if (!a.field) { a.h = nullptr; return nullptr; }
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
   SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-  SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+  SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   return &a;
 }
@@ -68,6 +69,14 @@ int allreduce_hook(mgic_ctx *c, double *dev, int n, int op) {
   return MGIC_OK;
 }
 
+int allgather_hook(mgic_ctx *c, const double *send, double *recv, size_t count) {
+  NcclApi *A = api();
+  Comm *cm = (Comm *)c->comm;
+  if (!A || !cm) { mgic_set_error("NCCL communicator not initialised"); return MGIC_ERR_STATE; }
+  NCCL_TRY(A->AllGather(send, recv, count, ncclDouble, cm->comm, c->stream));
+  return MGIC_OK;
+}
+
 }  // namespace
 
 extern "C" int mgic_comm_unique_id(unsigned char id[MGIC_NCCL_ID_BYTES]) {
@@ -94,6 +103,7 @@ extern "C" int mgic_comm_init(mgic_ctx *c, const unsigned char id[MGIC_NCCL_ID_B
   c->rank = rank; c->nranks = nranks;
   c->halo_exchange = halo_hook;
   c->allreduce = allreduce_hook;
+  c->allgather = allgather_hook;
   return MGIC_OK;
 }
 
@@ -104,7 +114,7 @@ extern "C" int mgic_comm_destroy(mgic_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (A && cm->comm) A->CommDestroy(cm->comm);
   delete cm;
-  c->comm = nullptr; c->halo_exchange = nullptr; c->allreduce = nullptr;
+  c->comm = nullptr; c->halo_exchange = nullptr; c->allreduce = nullptr; c->allgather = nullptr;
   return MGIC_OK;
 }
 

@@ -66,6 +66,7 @@ struct mgic_ctx {
   // halo exchange hook (multi-GPU): set by mgic_comm; null on one GPU
   int (*halo_exchange)(mgic_ctx *, mgic_field *, int depth_planes) = nullptr;
   int (*allreduce)(mgic_ctx *, double *devvals, int n, int op /*0 sum 1 max*/) = nullptr;
+  int (*allgather)(mgic_ctx *, const double *send, double *recv, size_t count) = nullptr;  // equal counts per rank
   void *comm = nullptr;
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
   // tuning knobs (mgic_ctx_set_option)
@@ -113,6 +114,7 @@ struct mgic_op {
   mgic_field *lambda = nullptr;           // owned
   mgic_field *scratch = nullptr;          // owned; ping-pong target of the fused sweep
   bool lambdaDirty = true;
+  bool isGlobal = false;                  // whole-domain operator on a multi-rank context (agglomerated level): no halos
   bool profTag = true;                    // finest-level operator: its GSRB launches are the profiled kernel
   int smoother = 1;                       // 0: one launch per colour; 1: fused red+black plane-streaming sweep
   Geom geom() const {
