@@ -340,6 +340,10 @@ def run_gpu(args):
 
 
 def main():
+    # libraries (NCCL's version banner, torchrun) may write to fd 1: keep the real stdout for the ONE JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=20)

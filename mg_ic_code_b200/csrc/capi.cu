@@ -99,6 +99,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "bottom_kernel")) c->bottomKernel = (int)value;
   else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
   else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
+  else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
@@ -349,7 +350,7 @@ int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
   return MGIC_OK;
 }
 int mgk::mgic_halo_shape(mgic_ctx *c, mgic_field *f, int planes) {
-  if (c->nranks > 1) {
+  if (c->nranks > 1 && !f->noHalo) {
     MGIC_REQUIRE(c->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
     return c->halo_exchange(c, f, planes);
   }
@@ -629,10 +630,13 @@ struct mgic_mg {
   struct VGraph { const void *e, *r; bool zero; cudaGraphExec_t exec; long long launches; };
   std::vector<VGraph> graphs;
   bool graphBroken = false;
-  // multi-rank: the bottom level agglomerated on EVERY rank (all-gather, redundant one-kernel solve, keep the own slab)
-  mgic_op *gbOp = nullptr;
-  mgic_field *gbA = nullptr, *gbB = nullptr, *gbE = nullptr, *gbR = nullptr;
-  BiCGWork gbWork;
+  // multi-rank agglomeration: from depth dA down every rank holds the WHOLE level (all-gather of the restricted
+  // residual, redundant single-GPU cycle incl. the one-kernel bottom solve, own slab of the correction prolonged back):
+  // small levels need no halo traffic and the bottom solve no host round trips.  Results are bit-identical on every
+  // rank and identical to the single-GPU cycle.
+  int dA = 1 << 30;
+  std::vector<mgic_op *> locOps;          // slab geometry of the agglomerated depths (coefficient averaging, views)
+  std::vector<mgic_field *> locA, locB;   // slab-shaped staging of the coarsened coefficients
   bool warm = false;   // multi-rank: one eager V-cycle has run (NCCL connections exist) before graph capture
 };
 
@@ -646,19 +650,24 @@ static int mg_coarsen_coefs(mgic_mg *mg) {
     const int coarsening = 1 << d;
     mgic_op *o = mg->ops[d];
     // directly from the AMR-level coefficients, not recursively (Factory.cpp:208-220)
-    MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->aOwn[d]->p, mg->a0->p, mg->a0->sy, mg->a0->sz, coarsening, type));
-    if (!mg->bIsOne)
-      MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->bOwn[d]->p, mg->b0->p, mg->b0->sy, mg->b0->sz, coarsening, type));
+    if (d >= mg->dA) {
+      // agglomerated depth: average this rank's slab, then all-gather the slabs into the whole-level array
+      mgic_op *lo = mg->locOps[d];
+      const size_t cnt = (size_t)lo->n[0] * lo->n[1] * lo->nzl;
+      MGIC_TRY(mgk::coarse_average(mg->ctx, lo->geom(), mg->locA[d]->p, mg->a0->p, mg->a0->sy, mg->a0->sz, coarsening, type));
+      MGIC_TRY(mg->ctx->allgather(mg->ctx, mg->locA[d]->p, mg->aOwn[d]->p, cnt));
+      if (!mg->bIsOne) {
+        MGIC_TRY(mgk::coarse_average(mg->ctx, lo->geom(), mg->locB[d]->p, mg->b0->p, mg->b0->sy, mg->b0->sz, coarsening, type));
+        MGIC_TRY(mg->ctx->allgather(mg->ctx, mg->locB[d]->p, mg->bOwn[d]->p, cnt));
+      }
+    } else {
+      MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->aOwn[d]->p, mg->a0->p, mg->a0->sy, mg->a0->sz, coarsening, type));
+      if (!mg->bIsOne)
+        MGIC_TRY(mgk::coarse_average(mg->ctx, o->geom(), mg->bOwn[d]->p, mg->b0->p, mg->b0->sy, mg->b0->sz, coarsening, type));
+    }
     MGIC_TRY(mgic_op_compute_lambda(o));  // :229
   }
   MGIC_TRY(mgic_op_compute_lambda(mg->ops[0]));
-  if (mg->gbOp) {  // coefficients of the agglomerated bottom level
-    mgic_op *bo = mg->ops.back();
-    const size_t cnt = (size_t)bo->n[0] * bo->n[1] * bo->nzl;
-    MGIC_TRY(mg->ctx->allgather(mg->ctx, bo->a->p, mg->gbA->p, cnt));
-    if (mg->gbB) MGIC_TRY(mg->ctx->allgather(mg->ctx, bo->b->p, mg->gbB->p, cnt));
-    MGIC_TRY(mgic_op_compute_lambda(mg->gbOp));
-  }
   return MGIC_OK;
 }
 
@@ -706,11 +715,27 @@ extern "C" int mgic_mg_create_ex(mgic_ctx *c, const mgic_params *P, mgic_field *
                      a0->k0 + a0->nz, coarsening);
       return MGIC_ERR_ARG;
     }
+    const int k0d = a0->k0 / coarsening, nzd = a0->nz / coarsening;
+    // agglomerate this depth (and all deeper ones) on every rank once the slab is small: its sweeps are launch /
+    // exchange-latency bound, not bandwidth bound
+    bool agg = mg->dA <= depth;
+    if (!agg && c->nranks > 1 && c->allgather && depth >= 1 && nzd * c->nranks == n[2] && k0d == c->rank * nzd &&
+        (long long)n[0] * n[1] * nzd <= c->aggloCells)
+      agg = true;
+    if (agg && mg->dA > depth) mg->dA = depth;
     mgic_op *o = nullptr;
-    MGIC_TRY(mgic_op_create(c, n, a0->k0 / coarsening, a0->nz / coarsening, dx0 * coarsening, P->alpha, P->beta, bclo, bchi,
-                            P->bc_value, &o));
+    MGIC_TRY(mgic_op_create(c, n, agg ? 0 : k0d, agg ? n[2] : nzd, dx0 * coarsening, P->alpha, P->beta, bclo, bchi, P->bc_value, &o));
+    o->isGlobal = agg;
     o->profTag = (depth == 0);
     mg->ops.push_back(o);
+    mgic_op *lo = nullptr;
+    mgic_field *la = nullptr, *lb = nullptr;
+    if (agg) {
+      MGIC_TRY(mgic_op_create(c, n, k0d, nzd, dx0 * coarsening, P->alpha, P->beta, bclo, bchi, P->bc_value, &lo));
+      MGIC_TRY(mgic_field_create(lo, &la));
+      if (!mg->bIsOne) MGIC_TRY(mgic_field_create(lo, &lb));
+    }
+    mg->locOps.push_back(lo); mg->locA.push_back(la); mg->locB.push_back(lb);
     mgic_field *ea = nullptr, *ra = nullptr, *aa = nullptr, *ba = nullptr;
     if (depth > 0) {
       MGIC_TRY(mgic_field_create(o, &ea));
@@ -724,19 +749,6 @@ extern "C" int mgic_mg_create_ex(mgic_ctx *c, const mgic_params *P, mgic_field *
     mg->e.push_back(ea); mg->r.push_back(ra); mg->aOwn.push_back(aa); mg->bOwn.push_back(ba);
   }
   mg->nd = (int)mg->ops.size();
-  if (c->nranks > 1 && c->bottomKernel && c->allgather) {
-    mgic_op *bo = mg->ops.back();
-    if (bo->nzl * c->nranks == bo->n[2] && bo->k0 == c->rank * bo->nzl) {  // equal slabs in rank order
-      MGIC_TRY(mgic_op_create(c, bo->n, 0, bo->n[2], bo->dx, P->alpha, P->beta, bclo, bchi, P->bc_value, &mg->gbOp));
-      mg->gbOp->isGlobal = true;
-      mg->gbOp->profTag = false;
-      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbA));
-      if (!mg->bIsOne) MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbB));
-      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbE));
-      MGIC_TRY(mgic_field_create(mg->gbOp, &mg->gbR));
-      MGIC_TRY(mgic_op_set_coefs(mg->gbOp, mg->gbA, mg->gbB, P->alpha, P->beta));
-    }
-  }
   MGIC_TRY(mg_coarsen_coefs(mg));
   *out = mg;
   return MGIC_OK;
@@ -747,9 +759,10 @@ extern "C" int mgic_mg_destroy(mgic_mg *mg) {
   cudaStreamSynchronize(mg->ctx->stream);
   mg->bottomWork.release();
   mg->outerWork.release();
-  mg->gbWork.release();
-  mgic_field_destroy(mg->gbA); mgic_field_destroy(mg->gbB); mgic_field_destroy(mg->gbE); mgic_field_destroy(mg->gbR);
-  mgic_op_destroy(mg->gbOp);
+  for (size_t d = 0; d < mg->locOps.size(); d++) {
+    mgic_field_destroy(mg->locA[d]); mgic_field_destroy(mg->locB[d]);
+    mgic_op_destroy(mg->locOps[d]);
+  }
   for (auto &g : mg->graphs) cudaGraphExecDestroy(g.exec);
   cudaFree(mg->d_bottomOut);
   for (int d = 0; d < mg->nd; d++) {
@@ -791,27 +804,12 @@ extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field
   MGIC_REQUIRE(mg && e && r, "NULL argument");
   mgic_op *op = mg->ops.back();
   REQ_SHAPE(op, e); REQ_SHAPE(op, r);
-  if (mg->ctx->bottomKernel && mg->ctx->nranks == 1) {
+  if (mg->ctx->bottomKernel && (mg->ctx->nranks == 1 || op->isGlobal)) {
     // one persistent cooperative kernel (bottom.cu); iteration count stays on the device until asked for
     MGIC_TRY(mg->bottomWork.alloc(op));
     MGIC_TRY(mgic_op_reset_lambda(op));
     if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
     MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
-    mg->bottomOnDevice = true;
-    if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
-    return MGIC_OK;
-  }
-  if (mg->gbOp && mg->ctx->bottomKernel) {
-    // multi-rank: every rank gathers the whole bottom level (a few MB over NVLink), solves it redundantly with the
-    // one-kernel solver -- identical bits on every rank, identical to the single-GPU solve -- and keeps its own slab
-    const size_t cnt = (size_t)op->n[0] * op->n[1] * op->nzl;
-    MGIC_TRY(mg->gbWork.alloc(mg->gbOp));
-    if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
-    MGIC_TRY(mg->ctx->allgather(mg->ctx, e->p, mg->gbE->p, cnt));
-    MGIC_TRY(mg->ctx->allgather(mg->ctx, r->p, mg->gbR->p, cnt));
-    MGIC_TRY(mgk::bottom_bicgstab(mg->gbOp, mg->gbE, mg->gbR, mg->gbWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
-    MGIC_CUDA(cudaMemcpyAsync(e->p, mg->gbE->p + (size_t)op->k0 * op->n[0] * op->n[1], cnt * sizeof(double), cudaMemcpyDeviceToDevice,
-                              mg->ctx->stream));
     mg->bottomOnDevice = true;
     if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
     return MGIC_OK;
@@ -839,6 +837,19 @@ extern "C" int mgic_mg_last_bottom_iterations(mgic_mg *mg) {
 }
 
 // [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
+// non-owning view of this rank's slab inside a whole-level (agglomerated) array
+static mgic_field slab_view(const mgic_field *whole, const mgic_op *slab) {
+  mgic_field v;
+  v.ctx = whole->ctx;
+  v.nx = whole->nx; v.ny = whole->ny; v.nz = slab->nzl;
+  v.sy = whole->sy; v.sz = whole->sz;
+  v.base = nullptr;
+  v.p = whole->p + (long long)slab->k0 * whole->sz;
+  v.bytes = 0; v.k0 = slab->k0; v.gnz = whole->gnz;
+  v.noHalo = true;
+  return v;
+}
+
 // relax(e, r, S) where e is known to be zero: the first fused sweep reads nothing for it (and the zero fill is skipped)
 static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int S) {
   if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op)) {
@@ -870,6 +881,19 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     return mgic_mg_bottom_solve(mg, e, r, nullptr);
   }
   MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
+  if (depth + 1 == mg->dA) {
+    // slab-distributed -> agglomerated: restrict into this rank's slab of the whole-level residual, all-gather in
+    // place, run the rest of the cycle on the whole level, prolong from the slab view of the whole-level correction
+    // (its ghost planes are the neighbouring planes of the same array: no exchange)
+    mgic_op *lo = mg->locOps[depth + 1];
+    mgic_field rv = slab_view(mg->r[depth + 1], lo);
+    MGIC_TRY(mgic_op_restrict_residual(op, &rv, e, r));
+    MGIC_TRY(mg->ctx->allgather(mg->ctx, rv.p, mg->r[depth + 1]->p, (size_t)lo->n[0] * lo->n[1] * lo->nzl));
+    if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
+    MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
+    mgic_field ev = slab_view(mg->e[depth + 1], lo);
+    return prolong_relax(op, e, &ev, r, S);
+  }
   MGIC_TRY(mgic_op_restrict_residual(op, mg->r[depth + 1], e, r));
   if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));   // setToZero(e[depth+1])
   MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
@@ -880,7 +904,7 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
 // single kernel), so it is captured once per (correction, residual) pair and afterwards costs one graph launch.
 static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZero = false) {
   mgic_ctx *c = mg->ctx;
-  const bool graphable = c->useGraph && c->bottomKernel && (c->nranks == 1 || mg->gbOp) && !c->profiling && !mg->graphBroken;
+  const bool graphable = c->useGraph && c->bottomKernel && (c->nranks == 1 || mg->ops.back()->isGlobal) && !c->profiling && !mg->graphBroken;
   if (!graphable) return mg_cycle(mg, 0, e, r, eIsZero);
   if (c->nranks > 1 && !mg->warm) {  // NCCL sets up its connections on first use: not inside a capture
     mg->warm = true;
@@ -895,7 +919,6 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
     }
   // everything the cycle allocates lazily must exist before capture
   MGIC_TRY(mg->bottomWork.alloc(mg->ops.back()));
-  if (mg->gbOp) MGIC_TRY(mg->gbWork.alloc(mg->gbOp));
   if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
   for (auto *o : mg->ops) {
     MGIC_TRY(mgic_op_reset_lambda(o));

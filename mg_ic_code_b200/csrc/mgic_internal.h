@@ -75,6 +75,7 @@ struct mgic_ctx {
   int bottomKernel = 1;                   // bottom BiCGStab: 1 one persistent kernel in a thread-block cluster, 3 same as a
                                           // cooperative grid, 0 host-driven launches (bottom.cu)
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
+  long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
@@ -101,6 +102,7 @@ struct mgic_field {
   double *p = nullptr;     // local cell (0,0,0)
   size_t bytes = 0;
   int k0 = 0, gnz = 0;
+  bool noHalo = false;     // slab view into a whole-level array: its ghost planes are real neighbour planes
 };
 
 struct mgic_op {
