@@ -264,6 +264,7 @@ def run_gpu(args):
     barrier()
     ms_prof = ev0.elapsed_time(ev1)
     k_launches, k_ms = ctx.profile_read()
+    breakdown = {k: {"launches": v[0] // args.steps, "ms_per_step": v[1] / args.steps} for k, v in ctx.profile_breakdown().items()}
     ctx.profile(False)
     # ---- end-to-end through the C ABI with HOST buffers: H2D residual, V-cycle, D2H correction ----------------
     # each rank's pinned buffers hold its own slab; the C ABI addresses global arrays, so pass the slab-shifted base
@@ -330,6 +331,7 @@ def run_gpu(args):
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "what": "pinned-host residual -> HBM, setToZero + V-cycle, correction -> pinned host, through the C ABI"},
             "gpu_launches": launches, "clocks": clocks,
+            "breakdown_rank0": dict(breakdown, note="per V-cycle, eager profiling pass, CUDA events per category on rank 0"),
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)

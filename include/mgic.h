@@ -97,6 +97,8 @@ int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);
  * run, then read the number of timed launches and their summed device time (bench.py roofline) */
 int mgic_ctx_profile(mgic_ctx *, int enable);
 int mgic_ctx_profile_read(mgic_ctx *, long long *launches, double *total_ms);
+/* same per category: 0 finest GSRB, 1 halo exchange, 2 all-gather, 3 bottom solve, 4 restrict, 5 coarser GSRB, 6 prolong */
+int mgic_ctx_profile_read_tag(mgic_ctx *, int tag, long long *launches, double *total_ms);
 /* multi-GPU z-slab decomposition: this context is rank `rank` of `nranks` (one process per GPU);
  * peers are wired with mgic_ctx_set_peer_halo(); see mgic_comm.h */
 int mgic_ctx_set_rank(mgic_ctx *, int rank, int nranks);

@@ -52,7 +52,8 @@ def lib():
         "mgic_ctx_create": [C.c_int, pvp], "mgic_ctx_destroy": [vp], "mgic_ctx_sync": [vp],
         "mgic_ctx_set_stream": [vp, vp], "mgic_ctx_profile": [vp, C.c_int],
         "mgic_ctx_set_option": [vp, C.c_char_p, C.c_longlong],
-        "mgic_ctx_profile_read": [vp, C.POINTER(C.c_longlong), dp], "mgic_ctx_set_rank": [vp, C.c_int, C.c_int],
+        "mgic_ctx_profile_read": [vp, C.POINTER(C.c_longlong), dp],
+        "mgic_ctx_profile_read_tag": [vp, C.c_int, C.POINTER(C.c_longlong), dp], "mgic_ctx_set_rank": [vp, C.c_int, C.c_int],
         "mgic_op_create": [vp, i3, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_destroy": [vp], "mgic_op_set_coefs": [vp, vp, vp, C.c_double, C.c_double],
         "mgic_op_set_alpha_beta": [vp, C.c_double, C.c_double], "mgic_op_reset_lambda": [vp],

@@ -106,23 +106,29 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
 extern "C" int mgic_ctx_profile(mgic_ctx *c, int enable) {
   MGIC_REQUIRE(c, "ctx is NULL");
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
-  for (auto &ev : c->profEvents) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto &ev : c->profEvents) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   c->profEvents.clear();
   c->profiling = enable != 0;
   return MGIC_OK;
 }
-extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *total_ms) {
+extern "C" int mgic_ctx_profile_read_tag(mgic_ctx *c, int tag, long long *launches, double *total_ms) {
   MGIC_REQUIRE(c && launches && total_ms, "NULL argument");
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
   double tot = 0.0;
+  long long n = 0;
   for (auto &ev : c->profEvents) {
+    if (ev.tag != tag) continue;
     float ms = 0.f;
-    MGIC_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    MGIC_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
     tot += ms;
+    n++;
   }
-  *launches = (long long)c->profEvents.size();
+  *launches = n;
   *total_ms = tot;
   return MGIC_OK;
+}
+extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *total_ms) {
+  return mgic_ctx_profile_read_tag(c, PROF_GSRB0, launches, total_ms);
 }
 
 // read back `n` device scalars starting at slot (one sync); multi-rank: all-reduced on the device first (op 0 sum, 1 max)
@@ -345,6 +351,7 @@ extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy,
 int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
   if (o->ctx->nranks > 1 && !o->isGlobal) {
     MGIC_REQUIRE(o->ctx->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
+    ProfScope ps(o->ctx, false, PROF_HALO);
     return o->ctx->halo_exchange(o->ctx, f, planes);
   }
   return MGIC_OK;
@@ -352,6 +359,7 @@ int mgk::mgic_halo(mgic_op *o, mgic_field *f, int planes) {
 int mgk::mgic_halo_shape(mgic_ctx *c, mgic_field *f, int planes) {
   if (c->nranks > 1 && !f->noHalo) {
     MGIC_REQUIRE(c->halo_exchange, "multi-rank context without a halo hook (mgic_comm)");
+    ProfScope ps(c, false, PROF_HALO);
     return c->halo_exchange(c, f, planes);
   }
   return MGIC_OK;
@@ -415,6 +423,7 @@ extern "C" int mgic_op_restrict_residual(mgic_op *o, mgic_field *resC, mgic_fiel
   MGIC_REQUIRE(o->n[0] % 2 == 0 && o->n[1] % 2 == 0 && o->nzl % 2 == 0 && o->k0 % 2 == 0, "level is not coarsenable by 2");
   MGIC_REQUIRE(resC->nx == o->n[0] / 2 && resC->ny == o->n[1] / 2 && resC->nz == o->nzl / 2, "coarse residual has the wrong shape");
   MGIC_TRY(halo(o, phi, 1));  // :163
+  ProfScope ps(o->ctx, false, PROF_RESTRICT);
   return mgk::restrict_res(o->ctx, o->geom(), o->bck(true), resC->p, resC->sy, resC->sz, phi->p, rhs->p, o->a->p, bptr(o),
                            o->alpha, o->beta, o->dx);
 }
@@ -423,6 +432,7 @@ extern "C" int mgic_op_prolong_increment(mgic_op *o, mgic_field *phi, const mgic
   REQ_SHAPE(o, phi);
   MGIC_REQUIRE(coarse->nx == o->n[0] / 2 && coarse->ny == o->n[1] / 2 && coarse->nz == o->nzl / 2 && o->n[0] % 2 == 0,
                "coarse correction has the wrong shape");
+  ProfScope ps(o->ctx, false, PROF_PROLONG);
   return mgk::prolong(o->ctx, o->geom(), phi->p, coarse->p, coarse->sy, coarse->sz);
 }
 // preCond (:72-104): phi = rhs * lambda, then relax(phi, rhs, 2)
@@ -809,7 +819,10 @@ extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field
     MGIC_TRY(mg->bottomWork.alloc(op));
     MGIC_TRY(mgic_op_reset_lambda(op));
     if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
-    MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
+    {
+      ProfScope ps(mg->ctx, false, PROF_BOTTOM);
+      MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
+    }
     mg->bottomOnDevice = true;
     if (iterations) *iterations = mgic_mg_last_bottom_iterations(mg);
     return MGIC_OK;
@@ -888,7 +901,10 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     mgic_op *lo = mg->locOps[depth + 1];
     mgic_field rv = slab_view(mg->r[depth + 1], lo);
     MGIC_TRY(mgic_op_restrict_residual(op, &rv, e, r));
-    MGIC_TRY(mg->ctx->allgather(mg->ctx, rv.p, mg->r[depth + 1]->p, (size_t)lo->n[0] * lo->n[1] * lo->nzl));
+    {
+      ProfScope ps(mg->ctx, false, PROF_GATHER);
+      MGIC_TRY(mg->ctx->allgather(mg->ctx, rv.p, mg->r[depth + 1]->p, (size_t)lo->n[0] * lo->n[1] * lo->nzl));
+    }
     if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
     MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
     mgic_field ev = slab_view(mg->e[depth + 1], lo);

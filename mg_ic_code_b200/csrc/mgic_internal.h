@@ -78,17 +78,21 @@ struct mgic_ctx {
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
   bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
+  struct ProfEv { cudaEvent_t a, b; int tag; };
+  std::vector<ProfEv> profEvents;
 };
 
 // records a CUDA-event pair around the launches issued in its scope when profiling is armed
+// tags: 0 finest-level GSRB (the roofline kernel), 1 halo exchange, 2 all-gather, 3 bottom solve, 4 restrict,
+//       5 coarser-level GSRB, 6 prolong, 7 BLAS-1 / other
+enum { PROF_GSRB0 = 0, PROF_HALO = 1, PROF_GATHER = 2, PROF_BOTTOM = 3, PROF_RESTRICT = 4, PROF_GSRBC = 5, PROF_PROLONG = 6, PROF_OTHER = 7 };
 struct ProfScope {
-  mgic_ctx *c; bool on; cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(mgic_ctx *ctx, bool tagged) : c(ctx), on(ctx->profiling && tagged) {
+  mgic_ctx *c; bool on; int tag; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(mgic_ctx *ctx, bool finest, int tg = -1) : c(ctx), on(ctx->profiling), tag(tg < 0 ? (finest ? PROF_GSRB0 : PROF_GSRBC) : tg) {
     if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
   }
   ~ProfScope() {
-    if (on) { cudaEventRecord(b, c->stream); c->profEvents.emplace_back(a, b); }
+    if (on) { cudaEventRecord(b, c->stream); c->profEvents.push_back({a, b, tag}); }
   }
 };
 

@@ -44,6 +44,18 @@ class Context:
         check(self.L.mgic_ctx_profile_read(self.h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    PROFILE_TAGS = ("gsrb_finest", "halo_exchange", "all_gather", "bottom_solve", "restrict", "gsrb_coarser", "prolong", "other")
+
+    def profile_breakdown(self):
+        """{category: (launches, total ms)} of the armed profiling pass"""
+        out = {}
+        for tag, name in enumerate(self.PROFILE_TAGS):
+            n, ms = C.c_longlong(), C.c_double()
+            check(self.L.mgic_ctx_profile_read_tag(self.h, tag, C.byref(n), C.byref(ms)))
+            if n.value:
+                out[name] = (n.value, ms.value)
+        return out
+
     @property
     def stream(self):
         return self.L.mgic_ctx_stream(self.h)
