@@ -202,10 +202,15 @@ def run_gpu(args):
         ctx.set_option("fused_min_cells", args.fused_min_cells)
 
     n = args.n
-    # weak scaling (C5): every GPU owns n^2 x n planes; the global domain grows in z
-    N = (n, n, n * world)
-    P = m.make_params(dict(m.DEFAULTS, N=N, L=100.0, max_grid_size=args.box, numMGsmooth=args.smooth))
-    k0, nzl = rank * n, n
+    # weak scaling: n^3 cells per GPU; the domain doubles in z, then y, then x:
+    # 512^3 -> 512x512x1024 -> 512x1024x1024 -> 1024^3, dx constant (L is the x-length), z-slabs of nz/world planes
+    mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+    if mult is None:
+        mult = (1, 1, world)
+    N = (n * mult[0], n * mult[1], n * mult[2])
+    P = m.make_params(dict(m.DEFAULTS, N=N, L=100.0 * mult[0], max_grid_size=args.box, numMGsmooth=args.smooth))
+    nzl = N[2] // world
+    k0 = rank * nzl
     lvl = m.level_op_from_params(ctx, P, k0, nzl)
     vars_ = m.MultigridVars(ctx, P, k0, nzl)
     dpsi, rhs, a, b = lvl.create(), lvl.create(), lvl.create(), lvl.create()
@@ -217,7 +222,7 @@ def run_gpu(args):
     f.set_smoother(args.smoother)
     op = f.MGnewOp(0)
     e = op.create()
-    cells_local = n * n * nzl
+    cells_local = N[0] * N[1] * nzl
     cells_total = cells_local * world
 
     def step():
@@ -270,7 +275,7 @@ def run_gpu(args):
     # each rank's pinned buffers hold its own slab; the C ABI addresses global arrays, so pass the slab-shifted base
     h_r = torch.empty(cells_local, dtype=torch.float64).pin_memory()
     h_e = torch.empty(cells_local, dtype=torch.float64).pin_memory()
-    off = k0 * n * n * 8
+    off = k0 * N[0] * N[1] * 8
     L = m.lib()
     m._capi.check(L.mgic_field_download_async(rhs.h, C.c_void_p(h_r.data_ptr() - off)))
     ctx.sync()
@@ -316,7 +321,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload_config(args), mg_depths=f.depths, bottom_bicgstab_iterations=bottom_iters,
-                                                global_cells=cells_total),
+                                                global_cells=cells_total, global_N=list(N), slab_planes_per_gpu=nzl),
             "roofline": {"bound": "hbm", "kernel": "finest-level GSRB " + ("fused red+black sweep" if args.smoother == 1 else "colour pass"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": profiled_traffic(args),

@@ -19,7 +19,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int BT = 256;   // threads per block, cooperative-grid variant
-constexpr int CT = 512;   // threads per block, cluster variant
+constexpr int CT = 1024;  // threads per block, cluster variant (<= 64 registers: latency, not registers, bounds this kernel)
 constexpr int CSIZE = 8;  // CTAs per cluster: portable maximum; 16 is used when the device can place it
 
 // all CTAs of the cluster: hardware barrier with release / acquire at cluster scope (orders global memory too)
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(BT) k_bottom_bicgstab(BottomArgs A) {
 // same solve inside one thread-block cluster: barriers are the cluster's hardware barrier (~0.3 us instead of the
 // ~4 us of a 128-block cooperative grid barrier), which is what bounds this latency-dominated kernel
 template <bool HAS_B>
-__global__ void __launch_bounds__(CT) k_bottom_bicgstab_cluster(BottomArgs A) {
+__global__ void __launch_bounds__(CT, 1) k_bottom_bicgstab_cluster(BottomArgs A) {
   __shared__ double sh[66];
   Bottom<HAS_B, true> s(A, sh);
   s.solve();
@@ -332,7 +332,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   A.imax = 80; A.eps = 1.0e-6; A.reps = 1.0e-12; A.hang = 1.0e-8; A.small = 1.0e-30; A.numRestarts = 5;
   A.out = d_out;
   const long long n = (long long)A.g.nx * A.g.ny * A.g.nz;
-  if (c->bottomKernel != 3 && n <= (long long)CSIZE * CT * 128) {
+  if (c->bottomKernel != 3 && n <= 262144) {
     // ONE cluster; 16 CTAs (non-portable size) when the level is big enough to use them and the device can place it
     void (*ck)(BottomArgs) = o->b ? k_bottom_bicgstab_cluster<true> : k_bottom_bicgstab_cluster<false>;
     static int maxCluster[2] = {0, 0};
@@ -349,7 +349,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
       }
       cudaGetLastError();
     }
-    int cs = (n > (long long)CSIZE * CT * 2) ? mc : CSIZE;
+    int cs = (n > (long long)CSIZE * CT) ? mc : CSIZE;
     if (c->bottomKernel == 2) cs = CSIZE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs); cfg.blockDim = dim3(CT); cfg.stream = c->stream;
@@ -366,7 +366,6 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   long long blocks = (n + BT - 1) / BT;
   // few, fat blocks keep the grid barrier cheap; never more than can be co-resident (cooperative launch)
   long long cap = std::min<long long>((long long)per * c->numSMs, (long long)partCap / 4);
-  cap = std::min<long long>(cap, 128);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   void *args[] = {&A};
