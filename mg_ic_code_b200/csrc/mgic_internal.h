@@ -72,8 +72,9 @@ struct mgic_ctx {
   // tuning knobs (mgic_ctx_set_option)
   int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
-  int bottomKernel = 1;                   // bottom BiCGStab: 1 one persistent kernel in a thread-block cluster, 3 same as a
-                                          // cooperative grid, 0 host-driven launches (bottom.cu)
+  int bottomKernel = 1;                   // bottom BiCGStab: 1 brick kernel, 4 grid barriers / iteration (bottom_brick.cu);
+                                          // 2 one kernel in a thread-block cluster, 3 same as a cooperative grid (bottom.cu);
+                                          // 0 host-driven launches
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
@@ -169,6 +170,8 @@ int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
 int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                     int *d_out);
+int bottom_bicgstab_brick(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
+                          int *d_out, int *used);
 // z-halo exchange of a field on the operator's level (no-op on one rank)
 int mgic_halo(mgic_op *, mgic_field *, int planes);
 bool gsrb_fused_applicable(const mgic_op *);
