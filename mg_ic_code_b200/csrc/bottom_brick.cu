@@ -58,14 +58,20 @@ struct Brick {
     rx = rhi[0] - rlo[0] + 1; ry = rhi[1] - rlo[1] + 1; rz = rhi[2] - rlo[2] + 1;
     bxl = hi[0] - lo[0] + 1; byl = hi[1] - lo[1] + 1; bzl = hi[2] - lo[2] + 1;
     nown = bxl * byl * bzl;
+    gsy = (int)A.g.sy; gsz = (int)A.g.sz;
     S = smem; P = smem + (size_t)rx * ry * rz;
   }
 
-  __device__ __forceinline__ long long gidx(int i, int j, int k) const { return i + (long long)j * A.g.sy + (long long)k * A.g.sz; }
+  // exact a / b for 0 <= a < 2^22, 0 < b: (a + 0.5) / b is at least 0.5/b away from an integer, far more than the error
+  // of the approximate float division (integer division has no hardware instruction; it dominated this kernel)
+  static __device__ __forceinline__ int fdiv(int a, int b) { return __float2int_rz(__fdividef((float)a + 0.5f, (float)b)); }
+  int gsy, gsz;  // the level is tiny: 32-bit global indices
+  __device__ __forceinline__ int gidx(int i, int j, int k) const { return i + j * gsy + k * gsz; }
   __device__ __forceinline__ int sidx(int i, int j, int k) const { return (i - rlo[0]) + rx * ((j - rlo[1]) + ry * (k - rlo[2])); }
   __device__ __forceinline__ void own_cell(int m, int &i, int &j, int &k) const {  // m-th brick cell of this thread
     const int q = threadIdx.x + m * NT;
-    i = lo[0] + q % bxl; j = lo[1] + (q / bxl) % byl; k = lo[2] + q / (bxl * byl);
+    const int row = fdiv(q, bxl), kk = fdiv(row, byl);
+    i = lo[0] + (q - row * bxl); j = lo[1] + (row - kk * byl); k = lo[2] + kk;
   }
   __device__ __forceinline__ int nmine() const { return (nown - (int)threadIdx.x + NT - 1) / NT; }
 #define FOR_OWN(m) _Pragma("unroll") for (int m = 0; m < MAXOWN; m++) if (m < mine)
@@ -94,12 +100,13 @@ struct Brick {
       const int hx = (sxl + 1) / 2, nh = hx * syl * szl;
       __syncthreads();
       for (int h = threadIdx.x; h < nh; h += NT) {
-        const int row = h / hx, t = h - row * hx;
-        const int j = slo[1] + row % syl, k = slo[2] + row / syl;
+        const int row = fdiv(h, hx), t = h - row * hx;
+        const int kk = fdiv(row, syl);
+        const int j = slo[1] + (row - kk * syl), k = slo[2] + kk;
         const int i = slo[0] + 2 * t + ((slo[0] + j + k + A.g.k0 + color) & 1);
         if (i > shi[0]) continue;
         const int s = sidx(i, j, k);
-        const long long q = gidx(i, j, k);
+        const int q = gidx(i, j, k);
         const double c = S[s];
         const Nb nb = nbS(i, j, k, s, c);
         S[s] = gsrb_point<HAS_B>(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp, __ldg(A.a + q), HAS_B ? __ldg(A.b + q) : 1.0,
@@ -111,7 +118,7 @@ struct Brick {
   // VCCOMPUTEOP3D point (VariableCoeffPoissonOperatorF.ChF:209-234) from the shared-memory region
   __device__ __forceinline__ double opS(int i, int j, int k) const {
     const int s = sidx(i, j, k);
-    const long long q = gidx(i, j, k);
+    const int q = gidx(i, j, k);
     const double c = S[s];
     const Nb nb = nbS(i, j, k, s, c);
     double l = lap7(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp);
@@ -121,7 +128,7 @@ struct Brick {
   }
   // VCCOMPUTERES3D point (:312-336) straight from global memory (phi is complete when this runs)
   __device__ __forceinline__ double resG(const double *x, int i, int j, int k) const {
-    const long long q = gidx(i, j, k);
+    const int q = gidx(i, j, k);
     const double c = x[q];
     const Nb nb = neighbours(x, q, i, j, k, A.g, A.bc, c);
     double l = lap7(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp);
@@ -164,8 +171,9 @@ struct Brick {
     const int rn = rx * ry * rz;
     __syncthreads();
     for (int s = threadIdx.x; s < rn; s += NT) {
-      const int i = rlo[0] + s % rx, j = rlo[1] + (s / rx) % ry, k = rlo[2] + s / (rx * ry);
-      const long long q = gidx(i, j, k);
+      const int row = fdiv(s, rx), kk = fdiv(row, ry);
+      const int i = rlo[0] + (s - row * rx), j = rlo[1] + (row - kk * ry), k = rlo[2] + kk;
+      const int q = gidx(i, j, k);
       const bool mine = (i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]);
       const double x = make(q, mine);
       P[s] = x;
@@ -181,7 +189,7 @@ struct Brick {
     // residual(r, phi, rhs, homogeneous); r_tilde = r; e = 0
     FOR_OWN(m) {
       int i, j, k; own_cell(m, i, j, k);
-      const long long q = gidx(i, j, k);
+      const int q = gidx(i, j, k);
       const double rv = resG(phi, i, j, k);
       r[q] = rv; rt[q] = rv; e[q] = 0.0;
       s0 += rv * rv;
@@ -197,18 +205,18 @@ struct Brick {
       norm1 = norm0; alpha1 = alpha0; omega1 = omega0;
       // rho1 = dot(r_tilde, r) was reduced together with the norm of the phase that last changed r
       if (rho1 == 0.0) {
-        FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const long long q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+        FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
         status = 2; finished = true;
         break;
       }
       // ---- phase A: p update, p_tilde = preCond(p), v = L p_tilde, m = dot(r_tilde, v) ------------------------------
       if (init) {
-        load_region([&](long long q, bool own_) { const double pv = r[q]; if (own_) pout[q] = pv; return pv; });
+        load_region([&](int q, bool own_) { const double pv = r[q]; if (own_) pout[q] = pv; return pv; });
         init = false;
       } else {
         beta1 = (rho1 / rho2) * (alpha1 / omega1);
         const double c2 = -beta1 * omega1, b1 = beta1;
-        load_region([&](long long q, bool own_) {
+        load_region([&](int q, bool own_) {
           double pv = pin[q] * b1;      // scale(p, beta)
           pv = pv + c2 * vin[q];        // incr(p, v, -beta*omega)
           pv = pv + 1.0 * r[q];         // incr(p, r, 1)
@@ -220,7 +228,7 @@ struct Brick {
       s0 = 0.0; s1 = 0.0;
       FOR_OWN(m) {
         int i, j, k; own_cell(m, i, j, k);
-        const long long q = gidx(i, j, k);
+        const int q = gidx(i, j, k);
         const double vv = opS(i, j, k);
         own[m] = vv; vout[q] = vv;
         s0 += rt[q] * vv;
@@ -234,7 +242,7 @@ struct Brick {
         const double na = -alpha0;
         FOR_OWN(m) {
           int i, j, k; own_cell(m, i, j, k);
-          const long long q = gidx(i, j, k);
+          const int q = gidx(i, j, k);
           const double rv = r[q] + na * own[m];
           r[q] = rv; s0 += rv * rv; s1 += rt[q] * rv;
           e[q] = e[q] + alpha0 * S[sidx(i, j, k)];
@@ -250,12 +258,12 @@ struct Brick {
       double rhoNext = s1;
       if (norm0 > A.eps * initial_norm && norm0 > A.reps * initial_rnorm) {
         // ---- phase C: s_tilde = preCond(r), t = L s_tilde, dots (t,r), (t,t) ----------------------------------------
-        load_region([&](long long q, bool) { return r[q]; });
+        load_region([&](int q, bool) { return r[q]; });
         sweeps();
         s0 = 0.0; s1 = 0.0;
         FOR_OWN(m) {
           int i, j, k; own_cell(m, i, j, k);
-          const long long q = gidx(i, j, k);
+          const int q = gidx(i, j, k);
           const double tv = opS(i, j, k);
           own[m] = tv;
           s0 += tv * r[q]; s1 += tv * tv;
@@ -267,7 +275,7 @@ struct Brick {
         s0 = 0.0; s1 = 0.0;
         FOR_OWN(m) {
           int i, j, k; own_cell(m, i, j, k);
-          const long long q = gidx(i, j, k);
+          const int q = gidx(i, j, k);
           e[q] = e[q] + omega0 * S[sidx(i, j, k)];
           const double rv = r[q] + no * own[m];
           r[q] = rv; s0 += rv * rv; s1 += rt[q] * rv;
@@ -283,13 +291,13 @@ struct Brick {
         if (recount == 0) recount = 1;
         else {
           recount = 0;
-          FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const long long q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+          FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
           if (restarts == A.numRestarts) { status = 3; finished = true; break; }
           gsync();
           s0 = 0.0; s1 = 0.0;
           FOR_OWN(m) {
             int i, j, k; own_cell(m, i, j, k);
-            const long long q = gidx(i, j, k);
+            const int q = gidx(i, j, k);
             const double rv = resG(phi, i, j, k);
             r[q] = rv; rt[q] = rv; e[q] = 0.0;
             s0 += rv * rv;
@@ -303,7 +311,7 @@ struct Brick {
       }
     }
     if (!finished)
-      FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const long long q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+      FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
     if (blockIdx.x == 0 && threadIdx.x == 0) { A.out[0] = it; A.out[1] = status; }
   }
 };
