@@ -58,6 +58,7 @@ extern "C" int mgic_ctx_destroy(mgic_ctx *c) {
   cudaFreeHost(c->h_scal);
   cudaFree(c->d_part);
   cudaFree(c->d_count);
+  if (c->commStream) { cudaStreamDestroy(c->commStream); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin); }
   if (c->ownStream) cudaStreamDestroy(c->stream);
   delete c;
   return MGIC_OK;
@@ -100,6 +101,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
   else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
   else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
+  else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
@@ -873,10 +875,10 @@ static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int 
   return mgic_op_relax(op, e, r, S);
 }
 // prolongIncrement(e, eCoarse) followed by relax(e, r, S): the increment is folded into the first fused sweep
-static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S) {
+static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S, bool rhsHaloValid) {
   if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op) && op->ctx->fusePR) {
     MGIC_TRY(mgic_op_reset_lambda(op));
-    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec);
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec, rhsHaloValid);
   }
   MGIC_TRY(mgic_op_prolong_increment(op, e, ec));
   return mgic_op_relax(op, e, r, S);
@@ -894,6 +896,8 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     return mgic_mg_bottom_solve(mg, e, r, nullptr);
   }
   MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
+  // the pre-smoothing fused relax exchanged the ghost planes of r; r is not written again on this depth
+  const bool preFused = S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op);
   if (depth + 1 == mg->dA) {
     // slab-distributed -> agglomerated: restrict into this rank's slab of the whole-level residual, all-gather in
     // place, run the rest of the cycle on the whole level, prolong from the slab view of the whole-level correction
@@ -908,12 +912,12 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
     MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
     mgic_field ev = slab_view(mg->e[depth + 1], lo);
-    return prolong_relax(op, e, &ev, r, S);
+    return prolong_relax(op, e, &ev, r, S, preFused);
   }
   MGIC_TRY(mgic_op_restrict_residual(op, mg->r[depth + 1], e, r));
   if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));   // setToZero(e[depth+1])
   MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
-  return prolong_relax(op, e, mg->e[depth + 1], r, S);
+  return prolong_relax(op, e, mg->e[depth + 1], r, S, preFused);
 }
 
 // One V-cycle, replayed as a CUDA graph when possible: the cycle is a fixed launch sequence (the bottom solve is a

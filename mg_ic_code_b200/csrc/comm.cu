@@ -104,6 +104,11 @@ extern "C" int mgic_comm_init(mgic_ctx *c, const unsigned char id[MGIC_NCCL_ID_B
   c->halo_exchange = halo_hook;
   c->allreduce = allreduce_hook;
   c->allgather = allgather_hook;
+  if (!c->commStream) {
+    MGIC_CUDA(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+    MGIC_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    MGIC_CUDA(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+  }
   return MGIC_OK;
 }
 
@@ -129,15 +134,16 @@ extern "C" int mgic_comm_halo_exchange(mgic_ctx *c, mgic_field *f, int planes) {
   if (!A || !cm) { mgic_set_error("NCCL communicator not initialised"); return MGIC_ERR_STATE; }
   const bool hasLo = f->k0 > 0, hasHi = f->k0 + f->nz < f->gnz;
   const size_t cnt = (size_t)planes * f->sz;
+  cudaStream_t st = c->haloStream ? c->haloStream : c->stream;
   NCCL_TRY(A->GroupStart());
   if (hasLo) {
-    NCCL_TRY(A->Send(f->p, cnt, ncclDouble, c->rank - 1, cm->comm, c->stream));
-    NCCL_TRY(A->Recv(f->p - (long long)planes * f->sz, cnt, ncclDouble, c->rank - 1, cm->comm, c->stream));
+    NCCL_TRY(A->Send(f->p, cnt, ncclDouble, c->rank - 1, cm->comm, st));
+    NCCL_TRY(A->Recv(f->p - (long long)planes * f->sz, cnt, ncclDouble, c->rank - 1, cm->comm, st));
     cm->haloBytes += (long long)cnt * 8;
   }
   if (hasHi) {
-    NCCL_TRY(A->Send(f->p + (long long)(f->nz - planes) * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, c->stream));
-    NCCL_TRY(A->Recv(f->p + (long long)f->nz * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, c->stream));
+    NCCL_TRY(A->Send(f->p + (long long)(f->nz - planes) * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, st));
+    NCCL_TRY(A->Recv(f->p + (long long)f->nz * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, st));
     cm->haloBytes += (long long)cnt * 8;
   }
   NCCL_TRY(A->GroupEnd());

@@ -80,6 +80,7 @@ struct FusedArgs {
   double *out;
   double alpha, beta, dxinv;
   int zchunk, redLo, redHi;
+  int zbeg, zend;         // output planes of this launch: [zbeg, zend) (interior / boundary launches of the overlapped sweep)
   const double *coarse;   // MODE_PROLONG: coarse correction, local cell (0,0,0)
   long long csy, csz;
 };
@@ -228,7 +229,7 @@ struct Fused {
     full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * SLOT * sizeof(double) + 2 * NW * 32 * sizeof(double));
     tid = threadIdx.x;
     x0 = blockIdx.x * TX; y0 = blockIdx.y * TY;
-    zs = blockIdx.z * A.zchunk; ze = min(zs + A.zchunk, A.g.nz);
+    zs = A.zbeg + blockIdx.z * A.zchunk; ze = min(zs + A.zchunk, A.zend);
     pfirst = zs - 2; plast = ze + 1;
     if (tid == 0) {
       for (int q = 0; q < NSLOT; q++) mbar_init(&full[q], 1);
@@ -330,7 +331,7 @@ Plan plan_chunks(int tiles, int nz, int resident) {
 }
 
 template <int TY, bool HAS_B, int MODE, int MINB>
-int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
+int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
   using F = Fused<TY, HAS_B, MODE>;
   mgic_ctx *c = o->ctx;
   auto kern = k_gsrb_fused<TY, HAS_B, MODE, MINB>;
@@ -360,8 +361,9 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   if (MODE != MODE_ZERO) MGIC_TRY(make_tmap(&tp, in - goff, A.g.nx, A.g.ny, np, RW, F::RR));
   else tp = ta;
   const int tilesX = (A.g.nx + TX - 1) / TX, tilesY = (A.g.ny + TY - 1) / TY;
-  const Plan pl = plan_chunks(tilesX * tilesY, A.g.nz, resident);
+  const Plan pl = plan_chunks(tilesX * tilesY, zend - zbeg, resident);
   A.zchunk = pl.zchunk;
+  A.zbeg = zbeg; A.zend = zend;
   A.redLo = (A.bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
   A.redHi = (A.bc.type[5] == MGIC_FACE_INTERIOR) ? A.g.nz : A.g.nz - 1;
   dim3 grd(tilesX, tilesY, pl.nch);
@@ -373,25 +375,25 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
 }
 
 template <bool HAS_B, int MODE>
-int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
+int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
   switch (o->ctx->fusedCfg) {
-    case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse);
-    case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse);
-    case 2: return launch_cfg<12, HAS_B, MODE, 1>(o, in, outp, r, coarse);
-    case 3: return launch_cfg<6, HAS_B, MODE, 3>(o, in, outp, r, coarse);
-    default: return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse);
+    case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+    case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
+    case 2: return launch_cfg<12, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
+    case 3: return launch_cfg<6, HAS_B, MODE, 3>(o, in, outp, r, coarse, zbeg, zend);
+    default: return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
   }
 }
 
-int launch(mgic_op *o, int mode, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse) {
+int launch(mgic_op *o, int mode, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
   if (o->b) {
-    if (mode == MODE_ZERO) return launch_mode<true, MODE_ZERO>(o, in, outp, r, coarse);
-    if (mode == MODE_PROLONG) return launch_mode<true, MODE_PROLONG>(o, in, outp, r, coarse);
-    return launch_mode<true, MODE_PLAIN>(o, in, outp, r, coarse);
+    if (mode == MODE_ZERO) return launch_mode<true, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend);
+    if (mode == MODE_PROLONG) return launch_mode<true, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend);
+    return launch_mode<true, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend);
   }
-  if (mode == MODE_ZERO) return launch_mode<false, MODE_ZERO>(o, in, outp, r, coarse);
-  if (mode == MODE_PROLONG) return launch_mode<false, MODE_PROLONG>(o, in, outp, r, coarse);
-  return launch_mode<false, MODE_PLAIN>(o, in, outp, r, coarse);
+  if (mode == MODE_ZERO) return launch_mode<false, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend);
+  if (mode == MODE_PROLONG) return launch_mode<false, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend);
+  return launch_mode<false, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend);
 }
 
 }  // namespace
@@ -411,19 +413,45 @@ bool gsrb_fused_applicable(const mgic_op *o) {
 
 // relax(e, r, iterations) with fused sweeps.  Multi-rank: one 2-plane halo exchange of e per sweep (the neighbour's
 // first plane is updated redundantly) instead of the reference's two 1-plane exchanges, plus one of rhs per call.
+// The exchange runs on the context's communication stream WHILE the interior planes are swept; only the first and last
+// OVL planes of the slab (two small launches) wait for it.
 // first = FUSED_FROM_ZERO: e is known to be zero (setToZero + relax of [Chombo] MultiGrid::cycle); first =
 // FUSED_PROLONG: e += prolong(coarse) is applied on the fly by the first sweep (prolongIncrement + relax).
-int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, int first, const mgic_field *coarse) {
+int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, int first, const mgic_field *coarse,
+               bool rhsHaloValid) {
+  constexpr int OVL = 8;
+  mgic_ctx *c = o->ctx;
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
-  const bool multi = o->ctx->nranks > 1;
-  if (multi) MGIC_TRY(mgic_halo(o, const_cast<mgic_field *>(r), 1));
-  if (multi && first == FUSED_PROLONG) MGIC_TRY(mgic_halo_shape(o->ctx, const_cast<mgic_field *>(coarse), 1));
+  const bool multi = c->nranks > 1 && !o->isGlobal;
+  const Geom g = o->geom();
+  const bool overlap = multi && c->overlapHalo && !c->profiling && c->commStream && g.nz >= 4 * OVL;
   for (int it = 0; it < iterations; it++) {
     const int mode = (it == 0) ? first : FUSED_PLAIN;
-    if (multi && mode != FUSED_FROM_ZERO) MGIC_TRY(mgic_halo(o, e, 2));
-    {
-      ProfScope ps(o->ctx, o->profTag);
-      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse));
+    const bool needE = multi && mode != FUSED_FROM_ZERO;
+    const bool needR = multi && it == 0 && !rhsHaloValid;
+    const bool needC = multi && mode == FUSED_PROLONG;
+    if (overlap && (needE || needR || needC)) {
+      // fork: the exchange depends on everything issued so far (the previous sweep wrote the planes being sent)
+      MGIC_CUDA(cudaEventRecord(c->evFork, c->stream));
+      MGIC_CUDA(cudaStreamWaitEvent(c->commStream, c->evFork, 0));
+      c->haloStream = c->commStream;
+      int rc = MGIC_OK;
+      if (needR) rc = mgic_halo(o, const_cast<mgic_field *>(r), 1);
+      if (rc == MGIC_OK && needC) rc = mgic_halo_shape(c, const_cast<mgic_field *>(coarse), 1);
+      if (rc == MGIC_OK && needE) rc = mgic_halo(o, e, 2);
+      c->haloStream = nullptr;
+      MGIC_TRY(rc);
+      MGIC_CUDA(cudaEventRecord(c->evJoin, c->commStream));
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, OVL, g.nz - OVL));     // interior: no ghost plane is read
+      MGIC_CUDA(cudaStreamWaitEvent(c->stream, c->evJoin, 0));                       // join
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, 0, OVL));
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, g.nz - OVL, g.nz));
+    } else {
+      if (needR) MGIC_TRY(mgic_halo(o, const_cast<mgic_field *>(r), 1));
+      if (needC) MGIC_TRY(mgic_halo_shape(c, const_cast<mgic_field *>(coarse), 1));
+      if (needE) MGIC_TRY(mgic_halo(o, e, 2));
+      ProfScope ps(c, o->profTag);
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, 0, g.nz));
     }
     std::swap(e->base, o->scratch->base);  // ping-pong: the field handle now owns the freshly written array
     std::swap(e->p, o->scratch->p);

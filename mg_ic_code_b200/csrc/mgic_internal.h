@@ -68,6 +68,10 @@ struct mgic_ctx {
   int (*allreduce)(mgic_ctx *, double *devvals, int n, int op /*0 sum 1 max*/) = nullptr;
   int (*allgather)(mgic_ctx *, const double *send, double *recv, size_t count) = nullptr;  // equal counts per rank
   void *comm = nullptr;
+  // halo exchange overlapped with interior work: a second stream + fork/join events (capturable into a CUDA graph)
+  cudaStream_t commStream = nullptr, haloStream = nullptr;  // haloStream != null: the halo hook issues on it
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  int overlapHalo = 1;
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
   // tuning knobs (mgic_ctx_set_option)
   int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
@@ -178,7 +182,7 @@ bool gsrb_fused_applicable(const mgic_op *);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
 enum { FUSED_PLAIN = 0, FUSED_FROM_ZERO = 1, FUSED_PROLONG = 2 };
 int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations, int first = FUSED_PLAIN,
-               const mgic_field *coarse = nullptr);
+               const mgic_field *coarse = nullptr, bool rhsHaloValid = false);
 int mgic_halo_shape(mgic_ctx *, mgic_field *, int planes);  // halo exchange of a field of any level
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)
 struct FabView { double *p; int lo[3]; long long s1, s2, sc; };
