@@ -18,9 +18,9 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int NT = 512;
+constexpr int NT = 1024;
 constexpr int HALO = 5;
-constexpr int MAXOWN = 8;  // brick cells per thread
+constexpr int MAXOWN = 4;  // brick cells per thread
 
 struct BrickArgs {
   Geom g;

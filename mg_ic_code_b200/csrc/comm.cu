@@ -105,7 +105,11 @@ extern "C" int mgic_comm_init(mgic_ctx *c, const unsigned char id[MGIC_NCCL_ID_B
   c->allreduce = allreduce_hook;
   c->allgather = allgather_hook;
   if (!c->commStream) {
-    MGIC_CUDA(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+    // highest priority: the exchange kernels must get an SM slot as soon as one CTA of the concurrently running sweep
+    // retires, instead of queueing behind the rest of its grid
+    int prLo = 0, prHi = 0;
+    MGIC_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+    MGIC_CUDA(cudaStreamCreateWithPriority(&c->commStream, cudaStreamNonBlocking, prHi));
     MGIC_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     MGIC_CUDA(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   }
