@@ -99,18 +99,34 @@ struct Brick {
       const int sxl = shi[0] - slo[0] + 1, syl = shi[1] - slo[1] + 1, szl = shi[2] - slo[2] + 1;
       const int hx = (sxl + 1) / 2, nh = hx * syl * szl;
       __syncthreads();
-      for (int h = threadIdx.x; h < nh; h += NT) {
+      // two cells of the colour per trip, everything they read gathered before either is written: the per-cell chain
+      // (global coefficient loads -> FP64 -> store) is latency bound, so independent cells must overlap
+      struct Cell { int s; double c, av, bv, lv, rv; Nb nb; bool ok; };
+      auto gather = [&](int h) {
+        Cell x;
+        x.ok = false; x.s = 0; x.c = x.av = x.bv = x.lv = x.rv = 0.0; x.nb = Nb();
+        if (h >= nh) return x;
         const int row = fdiv(h, hx), t = h - row * hx;
         const int kk = fdiv(row, syl);
         const int j = slo[1] + (row - kk * syl), k = slo[2] + kk;
         const int i = slo[0] + 2 * t + ((slo[0] + j + k + A.g.k0 + color) & 1);
-        if (i > shi[0]) continue;
-        const int s = sidx(i, j, k);
+        if (i > shi[0]) return x;
+        x.ok = true;
+        x.s = sidx(i, j, k);
         const int q = gidx(i, j, k);
-        const double c = S[s];
-        const Nb nb = nbS(i, j, k, s, c);
-        S[s] = gsrb_point<HAS_B>(c, nb.xm, nb.xp, nb.ym, nb.yp, nb.zm, nb.zp, __ldg(A.a + q), HAS_B ? __ldg(A.b + q) : 1.0,
-                                 __ldg(A.lam + q), P[s], A.alpha, A.beta, A.dxinv);
+        x.av = __ldg(A.a + q); x.lv = __ldg(A.lam + q); x.bv = HAS_B ? __ldg(A.b + q) : 1.0;
+        x.c = S[x.s]; x.rv = P[x.s];
+        x.nb = nbS(i, j, k, x.s, x.c);
+        return x;
+      };
+      for (int h = threadIdx.x; h < nh; h += 2 * NT) {
+        const Cell x0 = gather(h), x1 = gather(h + NT);
+        if (x0.ok)
+          S[x0.s] = gsrb_point<HAS_B>(x0.c, x0.nb.xm, x0.nb.xp, x0.nb.ym, x0.nb.yp, x0.nb.zm, x0.nb.zp, x0.av, x0.bv, x0.lv, x0.rv, A.alpha,
+                                      A.beta, A.dxinv);
+        if (x1.ok)
+          S[x1.s] = gsrb_point<HAS_B>(x1.c, x1.nb.xm, x1.nb.xp, x1.nb.ym, x1.nb.yp, x1.nb.zm, x1.nb.zp, x1.av, x1.bv, x1.lv, x1.rv, A.alpha,
+                                      A.beta, A.dxinv);
       }
     }
     __syncthreads();
@@ -170,14 +186,29 @@ struct Brick {
   template <class F> __device__ void load_region(F make) {
     const int rn = rx * ry * rz;
     __syncthreads();
-    for (int s = threadIdx.x; s < rn; s += NT) {
-      const int row = fdiv(s, rx), kk = fdiv(row, ry);
-      const int i = rlo[0] + (s - row * rx), j = rlo[1] + (row - kk * ry), k = rlo[2] + kk;
-      const int q = gidx(i, j, k);
-      const bool mine = (i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]);
-      const double x = make(q, mine);
-      P[s] = x;
-      S[s] = x * __ldg(A.lam + q);   // preCond: phi = rhs * lambda (VariableCoeffPoissonOperator.cpp:94-101)
+    for (int s0 = threadIdx.x; s0 < rn; s0 += 2 * NT) {
+      double x[2], lm[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int s = s0 + u * NT;
+        x[u] = 0.0; lm[u] = 0.0;
+        if (s < rn) {
+          const int row = fdiv(s, rx), kk = fdiv(row, ry);
+          const int i = rlo[0] + (s - row * rx), j = rlo[1] + (row - kk * ry), k = rlo[2] + kk;
+          const int q = gidx(i, j, k);
+          const bool mine = (i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]);
+          lm[u] = __ldg(A.lam + q);
+          x[u] = make(q, mine);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int s = s0 + u * NT;
+        if (s < rn) {
+          P[s] = x[u];
+          S[s] = x[u] * lm[u];   // preCond: phi = rhs * lambda (VariableCoeffPoissonOperator.cpp:94-101)
+        }
+      }
     }
   }
 
