@@ -207,6 +207,8 @@ def run_gpu(args):
     mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
     if mult is None:
         mult = (1, 1, world)
+    if args.scaling == "strong":   # config C3: the n^3 domain itself is cut into `world` z-slabs
+        mult = (1, 1, 1)
     N = (n * mult[0], n * mult[1], n * mult[2])
     P = m.make_params(dict(m.DEFAULTS, N=N, L=100.0 * mult[0], max_grid_size=args.box, numMGsmooth=args.smooth))
     nzl = N[2] // world
@@ -319,7 +321,7 @@ def run_gpu(args):
         vcycle_bytes = level_b * cells_local * sum(1.0 / 8 ** d for d in range(f.depths))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload_config(args), mg_depths=f.depths, bottom_bicgstab_iterations=bottom_iters,
                                                 global_cells=cells_total, global_N=list(N), slab_planes_per_gpu=nzl),
             "roofline": {"bound": "hbm", "kernel": "finest-level GSRB " + ("fused red+black sweep" if args.smoother == 1 else "colour pass"),
@@ -360,6 +362,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=256, help="side of the CPU sample problem")
     ap.add_argument("--smooth", type=int, default=2, help="numMGsmooth (pre = post = bottom)")
     ap.add_argument("--box", type=int, default=32, help="max_grid_size (sets the MG depth, Factory.cpp:168-172)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, config C5): n^3 cells per GPU; strong (config C3): one n^3 domain over all GPUs")
     ap.add_argument("--keep-b", action="store_true", help="stream bCoef even though it is identically 1")
     ap.add_argument("--smoother", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
