@@ -192,32 +192,23 @@ struct Brick {
   }
   __device__ void gsync() { if (gridDim.x > 1) grid.sync(); else __syncthreads(); }
 
-  // load the region: S = x*lambda, P = x where x is built per cell by `make` (a lambda over the global index)
+  // load the region: S = x*lambda, P = x where x is built per cell by `make` (a lambda over the global index).
+  // Plane-major like the sweeps: a thread keeps one (x, y) position and walks over z.
   template <class F> __device__ void load_region(F make) {
-    const int rn = rx * ry * rz;
+    const int M = rxy, G = max(NT / M, 1);
     __syncthreads();
-    for (int s0 = threadIdx.x; s0 < rn; s0 += 2 * NT) {
-      double x[2], lm[2];
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int s = s0 + u * NT;
-        x[u] = 0.0; lm[u] = 0.0;
-        if (s < rn) {
-          const int row = fdiv(s, rx), kk = fdiv(row, ry);
-          const int i = rlo[0] + (s - row * rx), j = rlo[1] + (row - kk * ry), k = rlo[2] + kk;
-          const int q = gidx(i, j, k);
-          const bool mine = (i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]);
-          lm[u] = __ldg(A.lam + q);
-          x[u] = make(q, mine);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int s = s0 + u * NT;
-        if (s < rn) {
-          P[s] = x[u];
-          S[s] = x[u] * lm[u];   // preCond: phi = rhs * lambda (VariableCoeffPoissonOperator.cpp:94-101)
-        }
+    for (int m0 = 0; m0 < M; m0 += NT) {
+      const int g = fdiv((int)threadIdx.x, M), m = m0 + (int)threadIdx.x - g * M;
+      if (g >= G || m >= M) continue;
+      const int jr = fdiv(m, rx), ir = m - jr * rx;
+      const int i = rlo[0] + ir, j = rlo[1] + jr;
+      const bool mineXY = (i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1]);
+      const int qrow = i + j * gsy;
+      for (int k = rlo[2] + g; k <= rhi[2]; k += G) {
+        const int q = qrow + gsz * k, sx = m + rxy * (k - rlo[2]);
+        const double x = make(q, mineXY && k >= lo[2] && k <= hi[2]);
+        P[sx] = x;
+        S[sx] = x * __ldg(A.lam + q);   // preCond: phi = rhs * lambda (VariableCoeffPoissonOperator.cpp:94-101)
       }
     }
   }
