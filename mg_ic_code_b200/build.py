@@ -30,16 +30,30 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """Compile every translation unit for sm_100a (objects in parallel), link the shared library in-tree."""
     if not force and not stale():
         return SO
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", SO] + sources()
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+        flags.insert(0, "-Xptxas=-v")
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = [nvcc] + flags + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, sources()))
+    subprocess.check_call([nvcc, "-shared", "-o", SO] + objs)
     return SO
 
 

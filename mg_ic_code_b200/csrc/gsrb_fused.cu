@@ -379,8 +379,6 @@ int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r,
   switch (o->ctx->fusedCfg) {
     case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
     case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
-    case 2: return launch_cfg<12, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
-    case 3: return launch_cfg<6, HAS_B, MODE, 3>(o, in, outp, r, coarse, zbeg, zend);
     default: return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
   }
 }

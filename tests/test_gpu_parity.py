@@ -104,7 +104,7 @@ def test_kernels_bit_exact(ctx, case, keep_b):
     assert np.array_equal(p.e.download(), p.o.get("E"))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 4])
 @pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
 def test_fused_smoother_bit_exact(ctx, case, cfg):
     """fused red+black plane-streaming sweep (TMA-staged halo'd planes) == per-colour oracle sweeps, every tile shape,
