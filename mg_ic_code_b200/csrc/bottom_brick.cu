@@ -20,7 +20,7 @@ namespace {
 
 constexpr int NT = 1024;
 constexpr int HALO = 5;
-constexpr int MAXOWN = 4;  // brick cells per thread
+constexpr int MAXOWN = 2;  // brick cells per thread
 
 struct BrickArgs {
   Geom g;
@@ -47,6 +47,7 @@ struct Brick {
   int lo[3], hi[3], rlo[3], rhi[3], rx, ry, rz, rxy, bxl, byl, bzl, nown;
   bool touches;  // the brick grown by four cells reaches a physical face
   double own[MAXOWN];  // v / t of the thread's brick cells, kept across a barrier
+  int ownq[MAXOWN], owns[MAXOWN], ownijk[MAXOWN];  // their global index, region index and packed (i,j,k): decoded once
 
   __device__ Brick(const BrickArgs &a_, double *smem, double *sh_) : A(a_), grid(cg::this_grid()), sh(sh_) {
     const int b = blockIdx.x;
@@ -78,6 +79,14 @@ struct Brick {
     i = lo[0] + (q - row * bxl); j = lo[1] + (row - kk * byl); k = lo[2] + kk;
   }
   __device__ __forceinline__ int nmine() const { return (nown - (int)threadIdx.x + NT - 1) / NT; }
+  __device__ void decode_own() {
+#pragma unroll
+    for (int m = 0; m < MAXOWN; m++) {
+      int i = lo[0], j = lo[1], k = lo[2];
+      if (m < nmine()) own_cell(m, i, j, k);
+      ownq[m] = gidx(i, j, k); owns[m] = sidx(i, j, k); ownijk[m] = i | (j << 10) | (k << 20);
+    }
+  }
 #define FOR_OWN(m) _Pragma("unroll") for (int m = 0; m < MAXOWN; m++) if (m < mine)
 
   // neighbours of (i,j,k) from the shared-memory region, physical BC folded in (same rule as mgic_device.cuh)
@@ -217,11 +226,11 @@ struct Brick {
     double *phi = A.phi, *r = A.r, *rt = A.rt, *e = A.e;
     double *pin = A.p0, *pout = A.p1, *vin = A.v0, *vout = A.v1;
     const int mine = nmine();
+    decode_own();
     double s0 = 0.0, s1 = 0.0;
     // residual(r, phi, rhs, homogeneous); r_tilde = r; e = 0
     FOR_OWN(m) {
-      int i, j, k; own_cell(m, i, j, k);
-      const int q = gidx(i, j, k);
+      const int q = ownq[m], i = ownijk[m] & 1023, j = (ownijk[m] >> 10) & 1023, k = ownijk[m] >> 20;
       const double rv = resG(phi, i, j, k);
       r[q] = rv; rt[q] = rv; e[q] = 0.0;
       s0 += rv * rv;
@@ -237,7 +246,7 @@ struct Brick {
       norm1 = norm0; alpha1 = alpha0; omega1 = omega0;
       // rho1 = dot(r_tilde, r) was reduced together with the norm of the phase that last changed r
       if (rho1 == 0.0) {
-        FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+        FOR_OWN(m) { const int q = ownq[m]; phi[q] = phi[q] + 1.0 * e[q]; }
         status = 2; finished = true;
         break;
       }
@@ -259,9 +268,8 @@ struct Brick {
       sweeps();
       s0 = 0.0; s1 = 0.0;
       FOR_OWN(m) {
-        int i, j, k; own_cell(m, i, j, k);
-        const int q = gidx(i, j, k);
-        const double vv = opS(i, j, k);
+        const int q = ownq[m];
+        const double vv = opS(ownijk[m] & 1023, (ownijk[m] >> 10) & 1023, ownijk[m] >> 20);
         own[m] = vv; vout[q] = vv;
         s0 += rt[q] * vv;
       }
@@ -273,16 +281,15 @@ struct Brick {
       if (fabs(mm) > A.small * fabs(rho1)) {
         const double na = -alpha0;
         FOR_OWN(m) {
-          int i, j, k; own_cell(m, i, j, k);
-          const int q = gidx(i, j, k);
+          const int q = ownq[m];
           const double rv = r[q] + na * own[m];
           r[q] = rv; s0 += rv * rv; s1 += rt[q] * rv;
-          e[q] = e[q] + alpha0 * S[sidx(i, j, k)];
+          e[q] = e[q] + alpha0 * S[owns[m]];
         }
         reduce2(s0, s1);
         norm0 = sqrt(s0);
       } else {
-        FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); r[gidx(i, j, k)] = 0.0; }
+        FOR_OWN(m) { r[ownq[m]] = 0.0; }
         reduce2(s0, s1);
         norm0 = 0.0;
       }
@@ -294,9 +301,8 @@ struct Brick {
         sweeps();
         s0 = 0.0; s1 = 0.0;
         FOR_OWN(m) {
-          int i, j, k; own_cell(m, i, j, k);
-          const int q = gidx(i, j, k);
-          const double tv = opS(i, j, k);
+          const int q = ownq[m];
+          const double tv = opS(ownijk[m] & 1023, (ownijk[m] >> 10) & 1023, ownijk[m] >> 20);
           own[m] = tv;
           s0 += tv * r[q]; s1 += tv * tv;
         }
@@ -306,9 +312,8 @@ struct Brick {
         const double no = -omega0;
         s0 = 0.0; s1 = 0.0;
         FOR_OWN(m) {
-          int i, j, k; own_cell(m, i, j, k);
-          const int q = gidx(i, j, k);
-          e[q] = e[q] + omega0 * S[sidx(i, j, k)];
+          const int q = ownq[m];
+          e[q] = e[q] + omega0 * S[owns[m]];
           const double rv = r[q] + no * own[m];
           r[q] = rv; s0 += rv * rv; s1 += rt[q] * rv;
         }
@@ -323,13 +328,12 @@ struct Brick {
         if (recount == 0) recount = 1;
         else {
           recount = 0;
-          FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+          FOR_OWN(m) { const int q = ownq[m]; phi[q] = phi[q] + 1.0 * e[q]; }
           if (restarts == A.numRestarts) { status = 3; finished = true; break; }
           gsync();
           s0 = 0.0; s1 = 0.0;
           FOR_OWN(m) {
-            int i, j, k; own_cell(m, i, j, k);
-            const int q = gidx(i, j, k);
+            const int q = ownq[m], i = ownijk[m] & 1023, j = (ownijk[m] >> 10) & 1023, k = ownijk[m] >> 20;
             const double rv = resG(phi, i, j, k);
             r[q] = rv; rt[q] = rv; e[q] = 0.0;
             s0 += rv * rv;
@@ -343,7 +347,7 @@ struct Brick {
       }
     }
     if (!finished)
-      FOR_OWN(m) { int i, j, k; own_cell(m, i, j, k); const int q = gidx(i, j, k); phi[q] = phi[q] + 1.0 * e[q]; }
+      FOR_OWN(m) { const int q = ownq[m]; phi[q] = phi[q] + 1.0 * e[q]; }
     if (blockIdx.x == 0 && threadIdx.x == 0) { A.out[0] = it; A.out[1] = status; }
   }
 };
