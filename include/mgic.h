@@ -87,7 +87,8 @@ void *mgic_ctx_stream(mgic_ctx *);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long long mgic_ctx_launch_count(mgic_ctx *);
 /* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
- * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: brick kernel with four grid barriers per iteration, 2: one kernel in a
+ * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: all vectors in the distributed shared memory of one cluster when the level fits,
+ * else 4; 4: brick kernel with four grid barriers per iteration, 2: one kernel in a
  * thread-block cluster, 3: the same as a cooperative grid, 0: host-driven launches), "use_graph" (1: V-cycles
  * replayed as CUDA graphs), "fuse_transfers" (1: setToZero / prolongIncrement folded into the following fused sweep),
  * "agglo_cells" (multi-rank: MG depths whose slab has at most this many cells are gathered onto every rank).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of

@@ -332,7 +332,12 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   A.imax = 80; A.eps = 1.0e-6; A.reps = 1.0e-12; A.hang = 1.0e-8; A.small = 1.0e-30; A.numRestarts = 5;
   A.out = d_out;
   const long long n = (long long)A.g.nx * A.g.ny * A.g.nz;
-  if (c->bottomKernel == 1) {  // brick kernel: four grid barriers per iteration (bottom_brick.cu)
+  if (c->bottomKernel == 1) {  // whole level in one cluster's shared memory (bottom_dsmem.cu), if it fits
+    int used = 0;
+    MGIC_TRY(bottom_bicgstab_dsmem(o, e, r, d_out, &used));
+    if (used) return MGIC_OK;
+  }
+  if (c->bottomKernel == 1 || c->bottomKernel == 4) {  // brick kernel: four grid barriers per iteration (bottom_brick.cu)
     int used = 0;
     MGIC_TRY(bottom_bicgstab_brick(o, e, r, work, part, partCap, d_out, &used));
     if (used) return MGIC_OK;

@@ -71,12 +71,13 @@ struct mgic_ctx {
   // halo exchange overlapped with interior work: a second stream + fork/join events (capturable into a CUDA graph)
   cudaStream_t commStream = nullptr, haloStream = nullptr;  // haloStream != null: the halo hook issues on it
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  int overlapHalo = 1;
+  int overlapHalo = 0;   // measured on 2 and 8 GPUs: the exchange is too cheap next to a sweep for the split launches to pay
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
   // tuning knobs (mgic_ctx_set_option)
   int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
-  int bottomKernel = 1;                   // bottom BiCGStab: 1 brick kernel, 4 grid barriers / iteration (bottom_brick.cu);
+  int bottomKernel = 1;                   // bottom BiCGStab: 1 all vectors in one cluster's shared memory if the level fits
+                                          // (bottom_dsmem.cu), else as 4; 4 brick kernel, 4 grid barriers / iteration (bottom_brick.cu);
                                           // 2 one kernel in a thread-block cluster, 3 same as a cooperative grid (bottom.cu);
                                           // 0 host-driven launches
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
@@ -174,6 +175,7 @@ int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
 int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                     int *d_out);
+int bottom_bicgstab_dsmem(mgic_op *, mgic_field *e, const mgic_field *r, int *d_out, int *used);
 int bottom_bicgstab_brick(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                           int *d_out, int *used);
 // z-halo exchange of a field on the operator's level (no-op on one rank)

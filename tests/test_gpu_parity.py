@@ -152,6 +152,7 @@ def test_graph_and_bottom_kernel_variants_agree(ctx):
         "eager_dev": dict(use_graph=0),
         "eager_coop": dict(use_graph=0, bottom_kernel=3),
         "eager_cluster": dict(use_graph=0, bottom_kernel=2),
+        "eager_brick": dict(use_graph=0, bottom_kernel=4),
         "graph_dev": dict(),
         "fused_all": dict(fused_min_cells=0),
         "fused_all_eager": dict(fused_min_cells=0, use_graph=0),
@@ -182,7 +183,7 @@ def test_graph_and_bottom_kernel_variants_agree(ctx):
         for name in ("graph_dev", "fused_all", "fused_all_eager", "fused_all_unfolded", "colour_only"):
             assert np.array_equal(results[name, smooth][0], ref[0]), (name, smooth)
             assert results[name, smooth][1] == ref[1]
-        for name in ("eager_host", "eager_coop", "eager_cluster"):
+        for name in ("eager_host", "eager_coop", "eager_cluster", "eager_brick"):
             assert results[name, smooth][1] == ref[1]
             assert relerr(results[name, smooth][0], ref[0]) < 1e-11, (name, smooth)
 
