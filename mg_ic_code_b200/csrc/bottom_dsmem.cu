@@ -220,7 +220,7 @@ struct Ds {
         norm0 = 0.0;
       }
       if (norm0 > A.eps * initial_norm && norm0 > A.reps * initial_rnorm) {
-        cl.sync();                                             // every CTA is done reading x as p_tilde
+        // (remote reads of x as p_tilde ended before the barrier inside the reduction of m)
         FOR_CELLS(m) { const int l = li[m]; x[l] = r[l] * lam[l]; }
         relax2(x, r);                                          // s_tilde = preCond(r)
         s0 = 0.0; s1 = 0.0;
@@ -260,7 +260,7 @@ struct Ds {
           init = true;
         }
       }
-      cl.sync();  // x is rewritten at the top of the next iteration: everyone must be done reading it across CTAs
+      // (x is rewritten only after the next iteration's rho reduction, which contains a cluster barrier)
     }
     if (!finished) FOR_CELLS(m) { const int l = li[m]; phi[l] = phi[l] + 1.0 * e[l]; }
     FOR_CELLS(m) { A.phi[g0 + li[m]] = phi[li[m]]; }
