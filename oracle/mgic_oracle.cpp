@@ -94,7 +94,8 @@ struct FAB {
   void setVal(Real v) { std::fill(d.begin(), d.end(), v); }
 };
 
-struct CopyItem { int from, to; Box region; };
+// region is in the DESTINATION's index space; the source cell is region - shift (shift != 0: periodic image)
+struct CopyItem { int from, to; Box region; int shift[3]; };
 
 struct Layout {
   std::vector<Box> boxes;
@@ -140,7 +141,26 @@ struct Layout {
         for (int from : cand) {
           if (from == to) continue;
           Box r = g & boxes[from];
-          if (!r.empty()) out.push_back({from, to, r});
+          if (!r.empty()) out.push_back({from, to, r, {0, 0, 0}});
+        }
+        if (periodic) {
+          // [Chombo] Copier::exchangeDefine on a periodic ProblemDomain: ghost cells outside the domain are filled from
+          // the periodic image of the valid cells (every non-zero shift by whole domain lengths)
+          for (int s2 = -1; s2 <= 1; s2++)
+            for (int s1 = -1; s1 <= 1; s1++)
+              for (int s0 = -1; s0 <= 1; s0++) {
+                if (!s0 && !s1 && !s2) continue;
+                const int sh[3] = {s0 * domain.size(0), s1 * domain.size(1), s2 * domain.size(2)};
+                Box gs = g;  // the ghost region seen in the source's index space
+                for (int d = 0; d < 3; d++) { gs.lo[d] -= sh[d]; gs.hi[d] -= sh[d]; }
+                if ((gs & domain).empty()) continue;
+                for (int from = 0; from < (int)boxes.size(); from++) {
+                  Box r = gs & boxes[from];
+                  if (r.empty()) continue;
+                  for (int d = 0; d < 3; d++) { r.lo[d] += sh[d]; r.hi[d] += sh[d]; }
+                  out.push_back({from, to, r, {sh[0], sh[1], sh[2]}});
+                }
+              }
         }
       }
     }
@@ -167,7 +187,8 @@ static void exchange(LevelData &ld, const std::vector<CopyItem> &items) {
     for (int c = 0; c < ld.nc; c++)
       for (int k = it.region.lo[2]; k <= it.region.hi[2]; k++)
         for (int j = it.region.lo[1]; j <= it.region.hi[1]; j++)
-          for (int i = it.region.lo[0]; i <= it.region.hi[0]; i++) dst(i, j, k, c) = src(i, j, k, c);
+          for (int i = it.region.lo[0]; i <= it.region.hi[0]; i++)
+            dst(i, j, k, c) = src(i - it.shift[0], j - it.shift[1], k - it.shift[2], c);
   }
 }
 

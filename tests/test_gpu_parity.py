@@ -23,6 +23,7 @@ CASES = {
     "c64": dict(N=(64, 64, 64), max_grid_size=16),
     "c8": dict(N=(8, 8, 8), max_grid_size=8, L=10.0),
     "wide": dict(N=(160, 48, 40), max_grid_size=8, L=100.0),
+    "periodic": dict(N=(16, 16, 32), max_grid_size=8, L=20.0, is_periodic=1),
 }
 
 
@@ -59,7 +60,7 @@ class Pair:
         return rng.standard_normal(self.shape), rng.standard_normal(self.shape)
 
 
-@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8"])
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "periodic"])
 @pytest.mark.parametrize("keep_b", [False, True])
 def test_kernels_bit_exact(ctx, case, keep_b):
     p = Pair(ctx, keep_b=keep_b, smoother=0, **CASES[case])
@@ -105,7 +106,7 @@ def test_kernels_bit_exact(ctx, case, keep_b):
 
 
 @pytest.mark.parametrize("cfg", [0, 1, 4])
-@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide", "periodic"])
 def test_fused_smoother_bit_exact(ctx, case, cfg):
     """fused red+black plane-streaming sweep (TMA-staged halo'd planes) == per-colour oracle sweeps, every tile shape,
     on every MG depth (tiles larger than the level, ragged tiles, z chunks)."""
@@ -220,7 +221,7 @@ def test_level_jacobi(ctx):
     assert np.array_equal(p.e.download(), expect)
 
 
-@pytest.mark.parametrize("case,smooth", [("c64", 2), ("c64", 4), ("c16", 2), ("neumann", 3)])
+@pytest.mark.parametrize("case,smooth", [("c64", 2), ("c64", 4), ("c16", 2), ("neumann", 3), ("periodic", 2)])
 def test_vcycle_parity(ctx, case, smooth):
     over = dict(CASES[case], numMGsmooth=smooth)
     p = Pair(ctx, **over)

@@ -106,6 +106,22 @@ def test_inhomogeneous_bc_twin():
     assert np.array_equal(o.apply(0, False), T.apply_op(e, a, b, 1.0, -1.0, dx, **kw))
 
 
+def test_periodic_exchange_matches_numpy_roll():
+    # is_periodic = 1: ParseBC does nothing (Source/SetBCs.cpp:63) and the exchange copier wraps around the domain
+    n = (16, 8, 24)
+    o = Oracle(N=n, max_grid_size=8, L=20.0, is_periodic=1)
+    o.setup()
+    rng = np.random.default_rng(2)
+    e = rng.standard_normal((n[2], n[1], n[0])); r = rng.standard_normal(e.shape)
+    o.set("E", e); o.set("R", r)
+    a, dx = o.get("A"), o.dims(0)[1]
+    t = 2 * e
+    lap = ((np.roll(e, -1, 2) + np.roll(e, 1, 2)) - t) + ((np.roll(e, -1, 1) + np.roll(e, 1, 1)) - t) + \
+          ((np.roll(e, -1, 0) + np.roll(e, 1, 0)) - t)
+    assert np.array_equal(o.residual(0, True), (r - 1.0 * a * e) + lap * (1.0 / (dx * dx)) * (-1.0) * 1.0)
+    assert np.array_equal(o.apply(0, True), 1.0 * a * e - lap * (1.0 / (dx * dx)) * (-1.0) * 1.0)
+
+
 def test_mg_depth_follows_box_size():
     # Factory.cpp:168-172: depth limit = boxes coarsenable by 2^depth * s_maxCoarse
     for box, depths in ((8, 3), (16, 4), (32, 5)):
