@@ -379,7 +379,10 @@ int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r,
   switch (o->ctx->fusedCfg) {
     case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
     case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
-    default: return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+    default:
+      // two CTAs per SM need a slot ring of <= ~110 KB: 10 rows with three coefficient streams, 8 rows with four
+      if (HAS_B) return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+      return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
   }
 }
 
