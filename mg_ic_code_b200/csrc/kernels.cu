@@ -7,12 +7,8 @@
 // aligned for vector loads), MGIC_GZ ghost planes below and above the rank's z-slab.  Physical boundary
 // ghosts are never stored: the value the reference's ParseBC (Source/SetBCs.cpp:49-131) would have written
 // into the ghost cell, ghost = a*near + b, is recomputed on the fly from the cell's own current value.
-#include <cooperative_groups.h>
-
 #include "mgic_internal.h"
 #include "mgic_device.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
