@@ -196,6 +196,10 @@ def run_gpu(args):
     if world > 1:
         from mg_ic_code_b200 import comm
         comm.attach(ctx, dist)
+    if args.halo == "nccl":
+        ctx.set_option("p2p_halo", 0)
+    if args.overlap_halo:
+        ctx.set_option("overlap_halo", 1)
     if args.fused_cfg is not None:
         ctx.set_option("fused_cfg", args.fused_cfg)
     if args.fused_min_cells is not None:
@@ -302,6 +306,13 @@ def run_gpu(args):
         t = torch.tensor([ms, ms_e2e, k_ms, ms_prof], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, k_ms, ms_prof = t.tolist()
+    halo_info = None
+    if world > 1:
+        from mg_ic_code_b200 import comm
+        hs = comm.halo_stats(ctx)
+        halo_info = {"transport": "NVLink peer stores (CUDA IPC, k_halo_push)" if hs[0] > 0 and hs[1] == 0 else
+                     ("ncclSend/ncclRecv" if hs[0] == 0 else "mixed"), "peer_store_exchanges": hs[0], "nccl_exchanges": hs[1],
+                     "bytes_sent_rank0": comm.halo_bytes(ctx), "overlap_with_interior": bool(args.overlap_halo)}
     if rank == 0:
         ms_step = ms / args.steps
         value = cells_total / (ms_step * 1e-3) / 1e9
@@ -340,6 +351,8 @@ def run_gpu(args):
             "gpu_launches": launches, "clocks": clocks,
             "breakdown_rank0": dict(breakdown, note="per V-cycle, eager profiling pass, CUDA events per category on rank 0"),
         }
+        if halo_info:
+            line["config"]["halo"] = halo_info
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -368,6 +381,8 @@ def main():
     ap.add_argument("--smoother", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fused-cfg", type=int, default=None, help="tile shape of the fused sweep (tuning)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="halo planes by NVLink peer stores or ncclSend/ncclRecv")
+    ap.add_argument("--overlap-halo", action="store_true", help="exchange on a second stream while the interior planes are swept")
     ap.add_argument("--fused-min-cells", type=int, default=None, help="levels below this use the per-colour kernel (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":

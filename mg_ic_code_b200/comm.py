@@ -1,7 +1,8 @@
 """Multi-GPU plumbing (one process per GPU): slab partition + NCCL communicator bootstrap over torch.distributed.
 
-torch.distributed is used only to broadcast the 128-byte NCCL unique id; halo planes and scalar reductions then go
-through the library's own ncclSend / ncclRecv / ncclAllReduce calls on the context stream (include/mgic_comm.h)."""
+torch.distributed is used only to broadcast the 128-byte NCCL unique id; halo planes then go through the library's own
+peer-store kernel over CUDA-IPC mappings (or ncclSend / ncclRecv) and scalars through ncclAllReduce, all on the context
+stream (include/mgic_comm.h)."""
 import ctypes as C
 
 from ._capi import MgicError, check, lib
@@ -49,6 +50,15 @@ def attach(ctx, dist):
 
 def halo_bytes(ctx):
     return lib().mgic_comm_halo_bytes(ctx.h)
+
+
+def halo_stats(ctx):
+    """(exchanges by NVLink peer stores, exchanges by ncclSend/ncclRecv, peer mapping available) since attach()"""
+    L = lib()
+    a, b, ok = C.c_longlong(0), C.c_longlong(0), C.c_int(0)
+    L.mgic_comm_halo_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    check(L.mgic_comm_halo_stats(ctx.h, C.byref(a), C.byref(b), C.byref(ok)))
+    return a.value, b.value, bool(ok.value)
 
 
 def detach(ctx):

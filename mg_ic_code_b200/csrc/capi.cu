@@ -3,6 +3,7 @@
 // bottom BiCGStab, the outer BiCGStab (f1) and the nonlinear loop of Main_PoissonSolver.cpp.
 //
 // Host code here only sequences kernel launches; all field data stays in HBM.  There is no CPU compute path.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -102,6 +103,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
   else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
   else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
+  else if (!strcmp(name, "p2p_halo")) c->p2pHalo = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
@@ -170,7 +172,11 @@ static int field_alloc(mgic_ctx *c, int nx, int ny, int nz, int k0, int gnz, mgi
   f->sy = nx; f->sz = (long long)nx * ny;
   f->k0 = k0; f->gnz = gnz;
   f->bytes = (size_t)f->sz * (nz + 2 * MGIC_GZ) * sizeof(double);
-  cudaError_t e = cudaMalloc(&f->base, f->bytes);
+  size_t alloc = f->bytes;
+  // multi-rank: arrays are exported to the z-neighbours by CUDA IPC, which names whole cudaMalloc blocks; allocations
+  // of at least 2 MiB get a block of their own
+  if (c->nranks > 1) alloc = (std::max(alloc, (size_t)1) + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+  cudaError_t e = cudaMalloc(&f->base, alloc);
   if (e != cudaSuccess) {
     mgic_set_error("cudaMalloc(%zu bytes) failed: %s", f->bytes, cudaGetErrorString(e));
     delete f;
@@ -271,7 +277,8 @@ extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
 }
 extern "C" int mgic_field_destroy(mgic_field *f) {
   if (!f) return MGIC_OK;
-  cudaFree(f->base);
+  mgic_ctx *c = f->ctx;
+  if (!(c && c->array_release && c->array_release(c, f->base))) cudaFree(f->base);
   delete f;
   return MGIC_OK;
 }
@@ -943,6 +950,16 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
   for (auto *o : mg->ops) {
     MGIC_TRY(mgic_op_reset_lambda(o));
     if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
+  }
+  if (c->array_prepare) {  // arrays whose halo planes travel inside the graph: map them into the neighbours now (collective)
+    MGIC_TRY(c->array_prepare(c, e));
+    MGIC_TRY(c->array_prepare(c, const_cast<mgic_field *>(r)));
+    for (int d = 0; d < mg->nd; d++) {
+      if (mg->ops[d]->isGlobal) continue;
+      if (mg->e[d]) MGIC_TRY(c->array_prepare(c, mg->e[d]));
+      if (mg->r[d]) MGIC_TRY(c->array_prepare(c, mg->r[d]));
+      MGIC_TRY(c->array_prepare(c, mg->ops[d]->scratch));
+    }
   }
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
   // ping-pong state (fused sweeps swap array pointers inside the field handles) must be the same after the cycle

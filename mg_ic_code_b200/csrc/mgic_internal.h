@@ -67,7 +67,10 @@ struct mgic_ctx {
   int (*halo_exchange)(mgic_ctx *, mgic_field *, int depth_planes) = nullptr;
   int (*allreduce)(mgic_ctx *, double *devvals, int n, int op /*0 sum 1 max*/) = nullptr;
   int (*allgather)(mgic_ctx *, const double *send, double *recv, size_t count) = nullptr;  // equal counts per rank
+  int (*array_prepare)(mgic_ctx *, mgic_field *) = nullptr;  // collective: make the field's array exchangeable by peer stores (never inside a capture)
+  int (*array_release)(mgic_ctx *, void *base) = nullptr;  // field array about to be freed; 1 = the hook frees it later
   void *comm = nullptr;
+  int p2pHalo = 1;       // halo planes by NVLink peer stores (comm.cu k_halo_push) when the ranks could map each other
   // halo exchange overlapped with interior work: a second stream + fork/join events (capturable into a CUDA graph)
   cudaStream_t commStream = nullptr, haloStream = nullptr;  // haloStream != null: the halo hook issues on it
   cudaEvent_t evFork = nullptr, evJoin = nullptr;

@@ -47,18 +47,24 @@ def timeit(fn, reps=10):
 
 
 res = {}
-for ov in (0, 1):
-    ctx.set_option("overlap_halo", ov)
-    res[f"relax4_overlap{ov}"] = timeit(lambda: op.relax(e, rhs, 4))
-    for g in (0, 1):
-        ctx.set_option("use_graph", g)
-        f2 = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b)   # fresh graph cache
-        o2 = f2.MGnewOp(0)
-        e2 = o2.create()
-        res[f"vcycle_overlap{ov}_graph{g}"] = timeit(lambda: f2.vcycle_from_zero(e2, rhs))
-        f2.close()
+for p2p in (1, 0):
+    ctx.set_option("p2p_halo", p2p)
+    tr = "p2p" if p2p else "nccl"
+    for ov in (0, 1):
+        ctx.set_option("overlap_halo", ov)
+        res[f"{tr}_relax4_overlap{ov}"] = timeit(lambda: op.relax(e, rhs, 4))
+        for g in ((1,) if ov else (0, 1)):
+            ctx.set_option("use_graph", g)
+            f2 = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b)   # fresh graph cache
+            o2 = f2.MGnewOp(0)
+            e2 = o2.create()
+            res[f"{tr}_vcycle_overlap{ov}_graph{g}"] = timeit(lambda: f2.vcycle_from_zero(e2, rhs))
+            f2.close()
 ctx.set_option("use_graph", 1)
+ctx.set_option("overlap_halo", 0)
+ctx.set_option("p2p_halo", 1)
 if rank == 0:
-    print("HALO BENCH", world, "ranks", N, {k: round(x, 3) for k, x in res.items()}, "halo bytes rank0", comm.halo_bytes(ctx))
+    print("HALO BENCH", world, "ranks", N, {k: round(x, 3) for k, x in res.items()}, "halo bytes rank0", comm.halo_bytes(ctx),
+          "exchanges (p2p, nccl, p2p available)", comm.halo_stats(ctx))
 dist.barrier()
 dist.destroy_process_group()

@@ -76,6 +76,16 @@ for _ in range(3):
     D2["f"].vcycle(D2["e"], D2["rhs"])
 results["vcycle_e_overlap"] = gather(D2["e"])
 ctx.set_option("overlap_halo", 0)
+# and with the halo planes sent by ncclSend/ncclRecv instead of peer stores
+stats_p2p = comm.halo_stats(ctx)
+ctx.set_option("p2p_halo", 0)
+D3 = build(ctx, k0, nzl)
+D3["op"].setToZero(D3["e"])
+for _ in range(3):
+    D3["f"].vcycle(D3["e"], D3["rhs"])
+results["vcycle_e_nccl"] = gather(D3["e"])
+ctx.set_option("p2p_halo", 1)
+stats_all = comm.halo_stats(ctx)
 ok = True
 if rank == 0:
     c1 = m.Context(local)
@@ -111,6 +121,11 @@ if rank == 0:
     same = np.array_equal(results["vcycle_e_overlap"], results["vcycle_e"])
     print("vcycle with overlapped halo exchange: bitwise", "OK" if same else "MISMATCH")
     ok &= same
+    same = np.array_equal(results["vcycle_e_nccl"], results["vcycle_e"])
+    print("vcycle with ncclSend/ncclRecv halos: bitwise", "OK" if same else "MISMATCH")
+    ok &= same
+    print("halo exchanges (peer stores, nccl, peer mapping available): before the nccl pass", stats_p2p, "after", stats_all)
+    ok &= stats_all[1] > 0 and (not stats_all[2] or (stats_p2p[0] > 0 and stats_p2p[1] == 0))
     print("MULTIGPU CHECK", "PASSED" if ok else "FAILED", f"({world} ranks, {n}^3, halo bytes sent by rank 0: {comm.halo_bytes(ctx)})")
 flag = torch.tensor([int(ok)], device="cuda")
 dist.broadcast(flag, 0)
