@@ -87,13 +87,19 @@ void *mgic_ctx_stream(mgic_ctx *);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 long long mgic_ctx_launch_count(mgic_ctx *);
 /* tuning knobs: "fused_cfg" (tile shape of the fused GSRB sweep), "fused_min_cells" (smaller levels use the
- * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: all vectors in the distributed shared memory of one cluster when the level fits,
- * else 4; 4: brick kernel with four grid barriers per iteration, 2: one kernel in a
- * thread-block cluster, 3: the same as a cooperative grid, 0: host-driven launches), "use_graph" (1: V-cycles
- * replayed as CUDA graphs), "fuse_transfers" (1: setToZero / prolongIncrement folded into the following fused sweep),
- * "agglo_cells" (multi-rank: MG depths whose slab has at most this many cells are gathered onto every rank).  Fields do not depend on fused_* / use_graph; bottom_kernel changes only the summation order of
- * the bottom solver's dot products. */
+ * per-colour kernel), "bottom_kernel" (bottom BiCGStab as 1: all vectors in the distributed shared memory of one
+ * cluster when the level fits, else bricks held by 16-CTA clusters, else 4; 5: cluster-held bricks first; 4: per-CTA
+ * bricks with four grid barriers per iteration; 2: one kernel in a thread-block cluster; 3: the same as a cooperative
+ * grid; 0: host-driven launches), "use_graph" (1: V-cycles replayed as CUDA graphs), "fuse_transfers" (1: setToZero /
+ * prolongIncrement folded into the following fused sweep), "agglo_cells" (multi-rank: MG depths whose slab has at most
+ * this many cells are gathered onto every rank), "overlap_halo" (multi-rank: exchange on a second stream while the
+ * interior planes are swept), "p2p_halo" (multi-rank: 1 halo planes by NVLink peer stores, 0 ncclSend/ncclRecv; same
+ * value on every rank).  Fields do not depend on fused_* / use_graph / *_halo; bottom_kernel changes only the
+ * summation order of the bottom solver's dot products. */
 int mgic_ctx_set_option(mgic_ctx *, const char *name, long long value);
+/* reads an option back; also "last_bottom_kernel": which bottom solver ran last (0 host-driven, 1 one cluster's shared
+ * memory, 2 cluster kernel, 3 cooperative grid, 4 brick kernel, 5 cluster-sized bricks); -1 = unknown name */
+long long mgic_ctx_get_option(mgic_ctx *, const char *name);
 /* per-launch CUDA-event timing of the dominant kernel (the finest level's GSRB launches): arm with enable = 1,
  * run, then read the number of timed launches and their summed device time (bench.py roofline) */
 int mgic_ctx_profile(mgic_ctx *, int enable);

@@ -332,15 +332,25 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   A.imax = 80; A.eps = 1.0e-6; A.reps = 1.0e-12; A.hang = 1.0e-8; A.small = 1.0e-30; A.numRestarts = 5;
   A.out = d_out;
   const long long n = (long long)A.g.nx * A.g.ny * A.g.nz;
-  if (c->bottomKernel == 1) {  // whole level in one cluster's shared memory (bottom_dsmem.cu), if it fits
+  if (c->bottomKernel == 5) {  // cluster-sized bricks even where the level would fit one cluster (tuning)
+    int used = 0;
+    MGIC_TRY(bottom_bicgstab_cbrick(o, e, r, work, part, partCap, d_out, &used));
+    if (used) { c->lastBottomKernel = 5; return MGIC_OK; }
+  }
+  if (c->bottomKernel == 1 || c->bottomKernel == 5) {  // whole level in one cluster's shared memory (bottom_dsmem.cu), if it fits
     int used = 0;
     MGIC_TRY(bottom_bicgstab_dsmem(o, e, r, d_out, &used));
-    if (used) return MGIC_OK;
+    if (used) { c->lastBottomKernel = 1; return MGIC_OK; }
   }
-  if (c->bottomKernel == 1 || c->bottomKernel == 4) {  // brick kernel: four grid barriers per iteration (bottom_brick.cu)
+  if (c->bottomKernel == 1) {  // bricks held by 16-CTA clusters, four grid barriers per iteration (bottom_cbrick.cu)
+    int used = 0;
+    MGIC_TRY(bottom_bicgstab_cbrick(o, e, r, work, part, partCap, d_out, &used));
+    if (used) { c->lastBottomKernel = 5; return MGIC_OK; }
+  }
+  if (c->bottomKernel == 1 || c->bottomKernel == 4 || c->bottomKernel == 5) {  // brick kernel: four grid barriers per iteration (bottom_brick.cu)
     int used = 0;
     MGIC_TRY(bottom_bicgstab_brick(o, e, r, work, part, partCap, d_out, &used));
-    if (used) return MGIC_OK;
+    if (used) { c->lastBottomKernel = 4; return MGIC_OK; }
   }
   if (c->bottomKernel != 3 && n <= 262144) {
     // ONE cluster; 16 CTAs (non-portable size) when the level is big enough to use them and the device can place it
@@ -367,6 +377,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
     cfg.attrs = &at; cfg.numAttrs = 1;
     MGIC_CUDA(cudaLaunchKernelEx(&cfg, ck, A));
     c->launches++;
+    c->lastBottomKernel = 2;
     return MGIC_OK;
   }
   void *kern = o->b ? (void *)k_bottom_bicgstab<true> : (void *)k_bottom_bicgstab<false>;
@@ -381,6 +392,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   void *args[] = {&A};
   MGIC_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(BT), args, 0, c->stream));
   c->launches++;
+  c->lastBottomKernel = 3;
   return MGIC_OK;
 }
 

@@ -107,6 +107,19 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   return MGIC_OK;
 }
+extern "C" long long mgic_ctx_get_option(mgic_ctx *c, const char *name) {
+  if (!c || !name) return -1;
+  if (!strcmp(name, "fused_cfg")) return c->fusedCfg;
+  if (!strcmp(name, "fused_min_cells")) return c->fusedMinCells;
+  if (!strcmp(name, "bottom_kernel")) return c->bottomKernel;
+  if (!strcmp(name, "use_graph")) return c->useGraph;
+  if (!strcmp(name, "fuse_transfers")) return c->fusePR;
+  if (!strcmp(name, "agglo_cells")) return c->aggloCells;
+  if (!strcmp(name, "overlap_halo")) return c->overlapHalo;
+  if (!strcmp(name, "p2p_halo")) return c->p2pHalo;
+  if (!strcmp(name, "last_bottom_kernel")) return c->lastBottomKernel;
+  return -1;
+}
 extern "C" int mgic_ctx_profile(mgic_ctx *c, int enable) {
   MGIC_REQUIRE(c, "ctx is NULL");
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
@@ -838,6 +851,7 @@ extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field
   }
   BottomLin L;
   L.op = op;
+  mg->ctx->lastBottomKernel = 0;
   BiCGParams bp;
   bp.homogeneous = true;  // [Chombo] MultiGrid::define: m_bottomSolver->define(op, true)
   int it = 0, st = 0;

@@ -80,9 +80,11 @@ struct mgic_ctx {
   int fusedCfg = 5;                       // tile configuration of the fused GSRB sweep (gsrb_fused.cu)
   long long fusedMinCells = 2097152;      // levels smaller than this use the per-colour kernel (launch-latency bound)
   int bottomKernel = 1;                   // bottom BiCGStab: 1 all vectors in one cluster's shared memory if the level fits
-                                          // (bottom_dsmem.cu), else as 4; 4 brick kernel, 4 grid barriers / iteration (bottom_brick.cu);
+                                          // (bottom_dsmem.cu), else cluster-sized bricks (bottom_cbrick.cu), else as 4;
+                                          // 5 cluster-sized bricks first; 4 brick kernel, 4 grid barriers / iteration (bottom_brick.cu);
                                           // 2 one kernel in a thread-block cluster, 3 same as a cooperative grid (bottom.cu);
                                           // 0 host-driven launches
+  int lastBottomKernel = -1;               // which bottom solver ran last: 0 host, 1 dsmem, 2 cluster, 3 coop, 4 brick, 5 cluster bricks
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
@@ -181,6 +183,8 @@ int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *c
 int bottom_bicgstab_dsmem(mgic_op *, mgic_field *e, const mgic_field *r, int *d_out, int *used);
 int bottom_bicgstab_brick(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                           int *d_out, int *used);
+int bottom_bicgstab_cbrick(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
+                           int *d_out, int *used);
 // z-halo exchange of a field on the operator's level (no-op on one rank)
 int mgic_halo(mgic_op *, mgic_field *, int planes);
 bool gsrb_fused_applicable(const mgic_op *);

@@ -35,6 +35,11 @@ class Context:
     def set_option(self, name, value):
         check(self.L.mgic_ctx_set_option(self.h, name.encode(), int(value)))
 
+    def get_option(self, name):
+        self.L.mgic_ctx_get_option.restype = C.c_longlong
+        self.L.mgic_ctx_get_option.argtypes = [C.c_void_p, C.c_char_p]
+        return self.L.mgic_ctx_get_option(self.h, name.encode())
+
     def profile(self, enable=True):
         """arm / disarm CUDA-event timing of the finest-level GSRB launches"""
         check(self.L.mgic_ctx_profile(self.h, int(enable)))

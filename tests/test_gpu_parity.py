@@ -398,3 +398,48 @@ def test_errors_mirror_reference(ctx):
     other = m.VariableCoeffPoissonOperator(ctx, (8, 8, 8), 1.0)
     with pytest.raises(m.MgicError, match="does not live on this operator"):
         lvl.setToZero(other.create())
+
+
+@pytest.mark.parametrize("shape,bc", [((64, 64, 64), None), ((32, 64, 64), None), ((32, 32, 64), None),
+                                      ((64, 64, 64), dict(bc_lo=(1, 0, 1), bc_hi=(0, 1, 0), bc_value=0.0))])
+@pytest.mark.parametrize("keep_b", [False, True])
+def test_bottom_solver_on_agglomerated_size_levels(ctx, shape, bc, keep_b):
+    """Bottom levels of the multi-GPU runs (32x32x64 ... 64^3, too big for one cluster's shared memory): the kernel with
+    cluster-held bricks (bottom_cbrick.cu) against the per-CTA brick kernel and the host-driven BiCGStab -- same
+    iteration count, corrections equal up to the summation order of the dot products.  max_grid_size 2 makes the level
+    its own bottom level (Factory.cpp:168-172)."""
+    P = m.make_params(dict(m.DEFAULTS, N=shape, L=100.0 * shape[0] / 64, max_grid_size=2, **(bc or {})))
+    lvl = m.level_op_from_params(ctx, P)
+    v = m.MultigridVars(ctx, P)
+    dpsi, rhs, a, b = lvl.create(), lvl.create(), lvl.create(), lvl.create()
+    v.set_initial_conditions(dpsi); v.set_rhs_and_a_coef(rhs, a); v.set_b_coef(b)
+    f = m.VariableCoeffPoissonOperatorFactory(ctx, P, a, b, keep_b=keep_b)
+    assert f.depths == 1
+    op = f.MGnewOp(0)
+    r = np.random.default_rng(5).standard_normal((shape[2], shape[1], shape[0]))
+    res, e = op.create(), op.create()
+    res.upload(r)
+    out = {}
+    try:
+        for name, kern in (("host", 0), ("brick", 4), ("default", 1), ("cbrick", 5)):
+            ctx.set_option("bottom_kernel", kern)
+            op.setToZero(e)
+            its = f.bottom_solve(e, res)
+            out[name] = (its, e.download(), ctx.get_option("last_bottom_kernel"))
+    finally:
+        ctx.set_option("bottom_kernel", 1)
+    assert out["host"][2] == 0 and out["brick"][2] == 4
+    assert out["default"][2] == 5 and out["cbrick"][2] == 5, "the cluster-brick kernel did not run"
+    assert 1 < out["host"][0] <= 80
+    rn = np.sqrt((r * r).sum())
+    for name in ("host", "brick", "default", "cbrick"):
+        its, x, _ = out[name]
+        # each variant meets BiCGStab's own stopping test (|res|_2 <= 1e-6 |res_0|_2, res_0 = rhs since e starts at 0) ...
+        e.upload(x)
+        op.residual(dpsi, e, res, True)
+        assert op.norm(dpsi, 2) <= 1.01e-6 * rn, name
+        # ... after (nearly) the same number of iterations: the dot products are summed in a different order per variant,
+        # which on a random right-hand side can move the crossing of the threshold by an iteration or two
+        assert abs(its - out["host"][0]) <= 3, (name, its, out["host"][0])
+        assert relerr(x, out["host"][1]) < (1e-9 if its == out["host"][0] else 2e-4), name  # stopped one step apart: 1e-6 residuals
+    assert np.array_equal(out["default"][1], out["cbrick"][1])
