@@ -136,6 +136,14 @@ int mgic_field_download(const mgic_field *, double *host);
 /* same, ordered on the context stream without a host sync (pinned host memory; pair with mgic_ctx_sync) */
 int mgic_field_upload_async(mgic_field *, const double *host);
 int mgic_field_download_async(const mgic_field *, double *host);
+/* the same copies on the context's transfer streams (one per PCIe direction) instead of the compute stream, so that
+ * the upload of the next right-hand side, a V-cycle and the download of the previous correction overlap: each copy is
+ * ordered after everything issued on the compute stream before the call; mgic_field_wait() makes the compute stream
+ * wait for the field's last prefetch / writeback (call it before the field is used or overwritten by a kernel);
+ * mgic_ctx_sync() / mgic_field_sync() also drain the transfer streams.  Pinned host memory. */
+int mgic_field_prefetch(mgic_field *, const double *host);
+int mgic_field_writeback(mgic_field *, double *host);
+int mgic_field_wait(mgic_field *);
 /* one FArrayBox (host, inclusive bounds incl. ghosts, Fortran order): copies fab ∩ region ∩ (this rank's slab) */
 int mgic_field_upload_fab(mgic_field *, const double *fab, const int fab_lo[3], const int fab_hi[3],
                           const int region_lo[3], const int region_hi[3]);

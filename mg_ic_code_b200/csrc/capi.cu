@@ -60,6 +60,7 @@ extern "C" int mgic_ctx_destroy(mgic_ctx *c) {
   cudaFree(c->d_part);
   cudaFree(c->d_count);
   if (c->commStream) { cudaStreamDestroy(c->commStream); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin); }
+  if (c->h2dStream) { cudaStreamSynchronize(c->h2dStream); cudaStreamSynchronize(c->d2hStream); cudaStreamDestroy(c->h2dStream); cudaStreamDestroy(c->d2hStream); cudaEventDestroy(c->evXfer); }
   if (c->ownStream) cudaStreamDestroy(c->stream);
   delete c;
   return MGIC_OK;
@@ -68,6 +69,7 @@ extern "C" int mgic_ctx_destroy(mgic_ctx *c) {
 extern "C" int mgic_ctx_sync(mgic_ctx *c) {
   MGIC_REQUIRE(c, "ctx is NULL");
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->h2dStream) { MGIC_CUDA(cudaStreamSynchronize(c->h2dStream)); MGIC_CUDA(cudaStreamSynchronize(c->d2hStream)); }
   return MGIC_OK;
 }
 
@@ -291,6 +293,7 @@ extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
 extern "C" int mgic_field_destroy(mgic_field *f) {
   if (!f) return MGIC_OK;
   mgic_ctx *c = f->ctx;
+  if (f->evPending) { cudaEventSynchronize(f->evPending); cudaEventDestroy(f->evPending); }
   if (!(c && c->array_release && c->array_release(c, f->base))) cudaFree(f->base);
   delete f;
   return MGIC_OK;
@@ -320,6 +323,38 @@ extern "C" int mgic_field_download_async(const mgic_field *f, double *host) {
   MGIC_REQUIRE(f && host, "NULL argument");
   const size_t n = (size_t)f->sz * f->nz;
   MGIC_CUDA(cudaMemcpyAsync(host + (size_t)f->k0 * f->sz, f->p, n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+  return MGIC_OK;
+}
+// transfers on their own streams (one per PCIe direction), ordered after everything issued so far on the compute stream
+static int xfer_streams(mgic_ctx *c) {
+  if (c->h2dStream) return MGIC_OK;
+  MGIC_CUDA(cudaStreamCreateWithFlags(&c->h2dStream, cudaStreamNonBlocking));
+  MGIC_CUDA(cudaStreamCreateWithFlags(&c->d2hStream, cudaStreamNonBlocking));
+  MGIC_CUDA(cudaEventCreateWithFlags(&c->evXfer, cudaEventDisableTiming));
+  return MGIC_OK;
+}
+static int xfer(mgic_field *f, cudaStream_t st, void *dst, const void *src, cudaMemcpyKind kind) {
+  mgic_ctx *c = f->ctx;
+  if (!f->evPending) MGIC_CUDA(cudaEventCreateWithFlags(&f->evPending, cudaEventDisableTiming));
+  MGIC_CUDA(cudaEventRecord(c->evXfer, c->stream));
+  MGIC_CUDA(cudaStreamWaitEvent(st, c->evXfer, 0));
+  MGIC_CUDA(cudaMemcpyAsync(dst, src, (size_t)f->sz * f->nz * sizeof(double), kind, st));
+  MGIC_CUDA(cudaEventRecord(f->evPending, st));
+  return MGIC_OK;
+}
+extern "C" int mgic_field_prefetch(mgic_field *f, const double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  MGIC_TRY(xfer_streams(f->ctx));
+  return xfer(f, f->ctx->h2dStream, f->p, host + (size_t)f->k0 * f->sz, cudaMemcpyHostToDevice);
+}
+extern "C" int mgic_field_writeback(mgic_field *f, double *host) {
+  MGIC_REQUIRE(f && host, "NULL argument");
+  MGIC_TRY(xfer_streams(f->ctx));
+  return xfer(f, f->ctx->d2hStream, host + (size_t)f->k0 * f->sz, f->p, cudaMemcpyDeviceToHost);
+}
+extern "C" int mgic_field_wait(mgic_field *f) {
+  MGIC_REQUIRE(f, "field is NULL");
+  if (f->evPending) MGIC_CUDA(cudaStreamWaitEvent(f->ctx->stream, f->evPending, 0));
   return MGIC_OK;
 }
 
@@ -359,6 +394,7 @@ extern "C" int mgic_field_download_fab(const mgic_field *f, double *fab, const i
 extern "C" int mgic_field_sync(const mgic_field *f) {
   MGIC_REQUIRE(f, "field is NULL");
   MGIC_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  if (f->evPending) MGIC_CUDA(cudaEventSynchronize(f->evPending));
   return MGIC_OK;
 }
 extern "C" int mgic_field_devptr(const mgic_field *f, void **ptr, long long *sy, long long *sz) {
@@ -439,15 +475,20 @@ extern "C" int mgic_op_level_jacobi(mgic_op *o, mgic_field *e, const mgic_field 
   return halo(o, e, 1);                                                    // :384
 }
 
-extern "C" int mgic_op_restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, const mgic_field *rhs) {
+// haloPlanes = 2: the caller will sweep phi next without changing it (the fused prolong + relax of the V-cycle), so the
+// exchange the sweep would need is done here and the one-plane exchange of the restriction is saved
+static int restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, const mgic_field *rhs, int haloPlanes) {
   MGIC_REQUIRE(o && resC && phi && rhs && o->a, "NULL argument");
   REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
   MGIC_REQUIRE(o->n[0] % 2 == 0 && o->n[1] % 2 == 0 && o->nzl % 2 == 0 && o->k0 % 2 == 0, "level is not coarsenable by 2");
   MGIC_REQUIRE(resC->nx == o->n[0] / 2 && resC->ny == o->n[1] / 2 && resC->nz == o->nzl / 2, "coarse residual has the wrong shape");
-  MGIC_TRY(halo(o, phi, 1));  // :163
+  MGIC_TRY(halo(o, phi, haloPlanes));  // :163
   ProfScope ps(o->ctx, false, PROF_RESTRICT);
   return mgk::restrict_res(o->ctx, o->geom(), o->bck(true), resC->p, resC->sy, resC->sz, phi->p, rhs->p, o->a->p, bptr(o),
                            o->alpha, o->beta, o->dx);
+}
+extern "C" int mgic_op_restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, const mgic_field *rhs) {
+  return restrict_residual(o, resC, phi, rhs, 1);
 }
 extern "C" int mgic_op_prolong_increment(mgic_op *o, mgic_field *phi, const mgic_field *coarse) {
   MGIC_REQUIRE(o && phi && coarse, "NULL argument");
@@ -896,10 +937,14 @@ static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int 
   return mgic_op_relax(op, e, r, S);
 }
 // prolongIncrement(e, eCoarse) followed by relax(e, r, S): the increment is folded into the first fused sweep
-static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S, bool rhsHaloValid) {
-  if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op) && op->ctx->fusePR) {
+static bool prolong_relax_is_fused(const mgic_op *op, int S) {
+  return S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op) && op->ctx->fusePR;
+}
+static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S, bool rhsHaloValid,
+                         bool eHaloValid) {
+  if (prolong_relax_is_fused(op, S)) {
     MGIC_TRY(mgic_op_reset_lambda(op));
-    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec, rhsHaloValid);
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec, rhsHaloValid, eHaloValid);
   }
   MGIC_TRY(mgic_op_prolong_increment(op, e, ec));
   return mgic_op_relax(op, e, r, S);
@@ -919,13 +964,16 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
   MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
   // the pre-smoothing fused relax exchanged the ghost planes of r; r is not written again on this depth
   const bool preFused = S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op);
+  // e is not touched between the restriction and the fused prolong + relax: one two-plane exchange serves both
+  const bool eOnce = prolong_relax_is_fused(op, S) && MGIC_GZ >= 2 && op->nzl >= 2;
+  const int rp = eOnce ? 2 : 1;
   if (depth + 1 == mg->dA) {
     // slab-distributed -> agglomerated: restrict into this rank's slab of the whole-level residual, all-gather in
     // place, run the rest of the cycle on the whole level, prolong from the slab view of the whole-level correction
     // (its ghost planes are the neighbouring planes of the same array: no exchange)
     mgic_op *lo = mg->locOps[depth + 1];
     mgic_field rv = slab_view(mg->r[depth + 1], lo);
-    MGIC_TRY(mgic_op_restrict_residual(op, &rv, e, r));
+    MGIC_TRY(restrict_residual(op, &rv, e, r, rp));
     {
       ProfScope ps(mg->ctx, false, PROF_GATHER);
       MGIC_TRY(mg->ctx->allgather(mg->ctx, rv.p, mg->r[depth + 1]->p, (size_t)lo->n[0] * lo->n[1] * lo->nzl));
@@ -933,12 +981,12 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
     MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
     mgic_field ev = slab_view(mg->e[depth + 1], lo);
-    return prolong_relax(op, e, &ev, r, S, preFused);
+    return prolong_relax(op, e, &ev, r, S, preFused, eOnce);
   }
-  MGIC_TRY(mgic_op_restrict_residual(op, mg->r[depth + 1], e, r));
+  MGIC_TRY(restrict_residual(op, mg->r[depth + 1], e, r, rp));
   if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));   // setToZero(e[depth+1])
   MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
-  return prolong_relax(op, e, mg->e[depth + 1], r, S, preFused);
+  return prolong_relax(op, e, mg->e[depth + 1], r, S, preFused, eOnce);
 }
 
 // One V-cycle, replayed as a CUDA graph when possible: the cycle is a fixed launch sequence (the bottom solve is a

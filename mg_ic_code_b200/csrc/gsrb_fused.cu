@@ -419,7 +419,7 @@ bool gsrb_fused_applicable(const mgic_op *o) {
 // first = FUSED_FROM_ZERO: e is known to be zero (setToZero + relax of [Chombo] MultiGrid::cycle); first =
 // FUSED_PROLONG: e += prolong(coarse) is applied on the fly by the first sweep (prolongIncrement + relax).
 int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, int first, const mgic_field *coarse,
-               bool rhsHaloValid) {
+               bool rhsHaloValid, bool eHaloValid) {
   constexpr int OVL = 8;
   mgic_ctx *c = o->ctx;
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
@@ -428,7 +428,7 @@ int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, i
   const bool overlap = multi && c->overlapHalo && !c->profiling && c->commStream && g.nz >= 4 * OVL;
   for (int it = 0; it < iterations; it++) {
     const int mode = (it == 0) ? first : FUSED_PLAIN;
-    const bool needE = multi && mode != FUSED_FROM_ZERO;
+    const bool needE = multi && mode != FUSED_FROM_ZERO && !(it == 0 && eHaloValid);  // eHaloValid: two ghost planes of e are current
     const bool needR = multi && it == 0 && !rhsHaloValid;
     const bool needC = multi && mode == FUSED_PROLONG;
     if (overlap && (needE || needR || needC)) {

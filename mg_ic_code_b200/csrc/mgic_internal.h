@@ -74,6 +74,10 @@ struct mgic_ctx {
   // halo exchange overlapped with interior work: a second stream + fork/join events (capturable into a CUDA graph)
   cudaStream_t commStream = nullptr, haloStream = nullptr;  // haloStream != null: the halo hook issues on it
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  // host <-> HBM transfers overlapped with compute (mgic_field_prefetch / mgic_field_writeback): one stream per PCIe
+  // direction, so that an upload, a V-cycle and a download can be in flight together
+  cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+  cudaEvent_t evXfer = nullptr;
   int overlapHalo = 0;   // measured on 2 and 8 GPUs: the exchange is too cheap next to a sweep for the split launches to pay
   // optional per-launch CUDA-event timing of the dominant kernel (finest-level GSRB), see mgic_ctx_profile
   // tuning knobs (mgic_ctx_set_option)
@@ -118,6 +122,7 @@ struct mgic_field {
   size_t bytes = 0;
   int k0 = 0, gnz = 0;
   bool noHalo = false;     // slab view into a whole-level array: its ghost planes are real neighbour planes
+  cudaEvent_t evPending = nullptr;  // completion of the field's last prefetch / writeback (mgic_field_wait)
 };
 
 struct mgic_op {
@@ -191,7 +196,7 @@ bool gsrb_fused_applicable(const mgic_op *);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
 enum { FUSED_PLAIN = 0, FUSED_FROM_ZERO = 1, FUSED_PROLONG = 2 };
 int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations, int first = FUSED_PLAIN,
-               const mgic_field *coarse = nullptr, bool rhsHaloValid = false);
+               const mgic_field *coarse = nullptr, bool rhsHaloValid = false, bool eHaloValid = false);
 int mgic_halo_shape(mgic_ctx *, mgic_field *, int planes);  // halo exchange of a field of any level
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)
 struct FabView { double *p; int lo[3]; long long s1, s2, sc; };
