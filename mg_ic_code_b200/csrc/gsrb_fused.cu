@@ -81,27 +81,32 @@ struct FusedArgs {
   double alpha, beta, dxinv;
   int zchunk, redLo, redHi;
   int zbeg, zend;         // output planes of this launch: [zbeg, zend) (interior / boundary launches of the overlapped sweep)
-  const double *coarse;   // MODE_PROLONG: coarse correction, local cell (0,0,0)
-  long long csy, csz;
 };
 
-// All five input streams arrive by TMA: per z plane one slot = the halo'd phi plane plus the (TY+2)-row planes of
-// aCoef, lambda, rhs (and bCoef), completed through ONE mbarrier.  Threads never form a global load address.
+// All input streams arrive by TMA: per z plane one slot = the halo'd phi plane plus the (TY+2)-row planes of aCoef,
+// lambda, rhs (and bCoef) -- and, in MODE_PROLONG, the 34 x (TY+4)/2 tile of the coarse correction under the region --
+// completed through ONE mbarrier.  Threads never form a global load address.  (The coarse values used to be plain
+// global loads: three dependent-latency loads per lane and plane made that sweep 36 % slower than the plain one,
+// 1138 vs 835 us on 512^3, profiles/r1b_launches_bench_512.csv.)
 template <int TY, bool HAS_B, int MODE>
 struct Fused {
   static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, CPLANE = RW * NW, NT = 32 * NW, NCOEF = HAS_B ? 4 : 3;
-  static constexpr int SLOT = PLANE + NCOEF * CPLANE;  // doubles
-  static constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double), CPLANE_BYTES = CPLANE * sizeof(double);
-  static constexpr uint32_t TX_BYTES = (MODE == MODE_ZERO ? 0 : PLANE_BYTES) + NCOEF * CPLANE_BYTES;
+  // coarse tile: TMA wants the innermost start coordinate on a 16-byte boundary, i.e. an even coarse x; (x0-2)/2 is odd, so
+  // the tile starts one coarse cell further left and is RW/2 + 2 wide (the lane's coarse cell is column lane + 1)
+  static constexpr int CROWS = RR / 2, CW = RW / 2 + 2, CBOX = (MODE == MODE_PROLONG) ? CW * CROWS : 0, CTILE = (CBOX + 15) / 16 * 16;
+  static constexpr int COFF = PLANE + NCOEF * CPLANE;
+  static constexpr int SLOT = PLANE + NCOEF * CPLANE + CTILE;  // doubles
+  static constexpr uint32_t PLANE_BYTES = PLANE * sizeof(double), CPLANE_BYTES = CPLANE * sizeof(double), CTILE_BYTES = CTILE * sizeof(double);
+  static constexpr uint32_t TX_BYTES = (MODE == MODE_ZERO ? 0 : PLANE_BYTES) + NCOEF * CPLANE_BYTES + CBOX * sizeof(double);
   static constexpr size_t SMEM = (size_t)NSLOT * SLOT * sizeof(double) + 2 * NW * 32 * sizeof(double) + NSLOT * sizeof(uint64_t);
 
   const FusedArgs &A;
-  const CUtensorMap *tm_phi, *tm_a, *tm_l, *tm_r, *tm_b;
+  const CUtensorMap *tm_phi, *tm_a, *tm_l, *tm_r, *tm_b, *tm_c;
   double *slots, *redbuf;
   uint64_t *full;
   // thread constants
   int tid, lane, w, s, cidx, x0, y0, zs, ze, pfirst, plast;
-  long long cofs, cofsm, cofsp;
+  int ci, cim, cip;   // MODE_PROLONG: the lane's coarse cell in the slot's coarse tile, and those of the rows y-1 / y+1
   double *outp;   // this lane's pair in the output plane being written; advanced by one plane per step
   bool inDom, tile, anyxy, bx0, bxn, by0, byn, zloPhys, zhiPhys;
   // black-cell halves of the coefficient pairs of the plane whose red update ran one step earlier
@@ -118,13 +123,15 @@ struct Fused {
     tma_load_3d(d + PLANE + CPLANE, tm_l, &full[slot], x0 - 2, y0 - 1, z);
     tma_load_3d(d + PLANE + 2 * CPLANE, tm_r, &full[slot], x0 - 2, y0 - 1, z);
     if (HAS_B) tma_load_3d(d + PLANE + 3 * CPLANE, tm_b, &full[slot], x0 - 2, y0 - 1, z);
+    // coarse plane under fine plane `plane` (x0 - 2 and y0 - 2 are even; >> floors the ghost planes -2, -1 to -1)
+    if (MODE == MODE_PROLONG) tma_load_3d(d + COFF, tm_c, &full[slot], ((x0 - 2) >> 1) - 1, (y0 - 2) >> 1, (plane >> 1) + MGIC_GZ);
   }
 
   __device__ __forceinline__ double2 load_pair(int plane, const double *slot) const {
     if (MODE == MODE_ZERO) return make_double2(0.0, 0.0);
     double2 v = *reinterpret_cast<const double2 *>(slot + s);
     if (MODE == MODE_PROLONG && inDom) {
-      const double cv = A.coarse[cofs + (long long)(plane >> 1) * A.csz];
+      const double cv = slot[COFF + ci];
       v.x = v.x + cv; v.y = v.y + cv;   // phi(i,j,k) + coarse(i/2, j/2, k/2)
     }
     return v;
@@ -156,10 +163,9 @@ struct Fused {
       double xm = E ? pc.x : xo, xp = E ? xo : pc.y;
       double ym = 0.0, yp = 0.0;
       if (MODE != MODE_ZERO) { ym = dense[s + E - RW]; yp = dense[s + E + RW]; }
-      if (MODE == MODE_PROLONG && inDom) {
-        const long long ck = (long long)(kr >> 1) * A.csz;
-        ym = ym + A.coarse[cofsm + ck];
-        yp = yp + A.coarse[cofsp + ck];
+      if (MODE == MODE_PROLONG && inDom) {  // (rows outside the domain read the tile's zero fill; the BC below replaces them)
+        ym = ym + dense[COFF + cim];
+        yp = yp + dense[COFF + cip];
       }
       double zm = E ? pm1.y : pm1.x, zp = E ? pn.y : pn.x;
       if (anyxy) {
@@ -248,12 +254,7 @@ struct Fused {
     s = rr * RW + 2 * lane;
     cidx = w * RW + 2 * lane;
     outp = A.out + (x + (long long)y * A.g.sy + (long long)(zs - 2) * A.g.sz);  // plane kr-1 at the first step (kr = zs-1)
-    cofs = cofsm = cofsp = 0;
-    if (MODE == MODE_PROLONG && inDom) {
-      cofs = (x >> 1) + (long long)(y >> 1) * A.csy;
-      cofsm = (x >> 1) + (long long)(max(y - 1, 0) >> 1) * A.csy;
-      cofsp = (x >> 1) + (long long)(min(y + 1, A.g.ny - 1) >> 1) * A.csy;
-    }
+    ci = (rr >> 1) * CW + lane + 1; cim = ((rr - 1) >> 1) * CW + lane + 1; cip = ((rr + 1) >> 1) * CW + lane + 1;
     zloPhys = A.bc.type[4] != MGIC_FACE_INTERIOR; zhiPhys = A.bc.type[5] != MGIC_FACE_INTERIOR;
     sa = sl = sr = sb = 0.0;
     // prologue: the lane's pairs of planes zs-2 and zs-1
@@ -272,12 +273,14 @@ struct Fused {
 template <int TY, bool HAS_B, int MODE, int MINB>
 __global__ void __launch_bounds__(32 * (TY + 2), MINB)
 k_gsrb_fused(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_l,
-             const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_b, const FusedArgs A) {
+             const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
+             const FusedArgs A) {
   using F = Fused<TY, HAS_B, MODE>;
-  static_assert(F::PLANE_BYTES % 128 == 0 && F::CPLANE_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+  static_assert(F::PLANE_BYTES % 128 == 0 && F::CPLANE_BYTES % 128 == 0 && F::CTILE_BYTES % 128 == 0,
+                "TMA destinations must stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   F f(A);
-  f.tm_phi = &tm_phi; f.tm_a = &tm_a; f.tm_l = &tm_l; f.tm_r = &tm_r; f.tm_b = &tm_b;
+  f.tm_phi = &tm_phi; f.tm_a = &tm_a; f.tm_l = &tm_l; f.tm_r = &tm_r; f.tm_b = &tm_b; f.tm_c = &tm_c;
   f.run(smem_raw);
 }
 
@@ -349,10 +352,9 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   A.bc = o->bck(true);
   A.out = outp;
   A.alpha = o->alpha; A.beta = o->beta; A.dxinv = 1.0 / (o->dx * o->dx);
-  A.coarse = coarse ? coarse->p : nullptr; A.csy = coarse ? coarse->sy : 0; A.csz = coarse ? coarse->sz : 0;
   const int np = A.g.nz + 2 * MGIC_GZ;
   const long long goff = (long long)MGIC_GZ * A.g.sz;
-  CUtensorMap tp, ta, tl, tr, tb;
+  CUtensorMap tp, ta, tl, tr, tb, tc;
   MGIC_TRY(make_tmap(&ta, o->a->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
   MGIC_TRY(make_tmap(&tl, o->lambda->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
   MGIC_TRY(make_tmap(&tr, r->p - goff, A.g.nx, A.g.ny, np, RW, F::NW));
@@ -360,6 +362,9 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   else tb = ta;
   if (MODE != MODE_ZERO) MGIC_TRY(make_tmap(&tp, in - goff, A.g.nx, A.g.ny, np, RW, F::RR));
   else tp = ta;
+  if (MODE == MODE_PROLONG)
+    MGIC_TRY(make_tmap(&tc, coarse->p - (long long)MGIC_GZ * coarse->sz, coarse->nx, coarse->ny, coarse->nz + 2 * MGIC_GZ, F::CW, F::CROWS));
+  else tc = ta;
   const int tilesX = (A.g.nx + TX - 1) / TX, tilesY = (A.g.ny + TY - 1) / TY;
   const Plan pl = plan_chunks(tilesX * tilesY, zend - zbeg, resident);
   A.zchunk = pl.zchunk;
@@ -367,7 +372,7 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   A.redLo = (A.bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
   A.redHi = (A.bc.type[5] == MGIC_FACE_INTERIOR) ? A.g.nz : A.g.nz - 1;
   dim3 grd(tilesX, tilesY, pl.nch);
-  kern<<<grd, F::NT, F::SMEM, c->stream>>>(tp, ta, tl, tr, tb, A);
+  kern<<<grd, F::NT, F::SMEM, c->stream>>>(tp, ta, tl, tr, tb, tc, A);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { mgic_set_error("kernel gsrb_fused: %s", cudaGetErrorString(e)); return MGIC_ERR_CUDA; }
@@ -380,8 +385,11 @@ int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r,
     case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
     case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
     default:
-      // two CTAs per SM need a slot ring of <= ~110 KB: 10 rows with three coefficient streams, 8 rows with four
-      if (HAS_B) return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+      // two CTAs per SM need a slot ring of <= ~110 KB: 10 rows with three coefficient streams, 8 rows with four or with
+      // the coarse tile of the prolonging sweep
+      // (6 rows when both apply)
+      if (HAS_B && MODE == MODE_PROLONG) return launch_cfg<6, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+      if (HAS_B || MODE == MODE_PROLONG) return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
       return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
   }
 }
@@ -425,6 +433,11 @@ int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, i
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
   const bool multi = c->nranks > 1 && !o->isGlobal;
   const Geom g = o->geom();
+  if (first == FUSED_PROLONG && (coarse->nx & 1)) {
+    // the coarse rows are not 16-byte multiples: no tensor map; prolong with the separate kernel, then plain sweeps
+    MGIC_TRY(prolong(c, g, e->p, coarse->p, coarse->sy, coarse->sz));
+    first = FUSED_PLAIN; coarse = nullptr; eHaloValid = false;
+  }
   const bool overlap = multi && c->overlapHalo && !c->profiling && c->commStream && g.nz >= 4 * OVL;
   for (int it = 0; it < iterations; it++) {
     const int mode = (it == 0) ? first : FUSED_PLAIN;
