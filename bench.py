@@ -37,19 +37,20 @@ def algorithmic_bytes_per_cell(smooth, keep_b):
 
 
 def profiled_traffic(args):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/), valid for the configuration it was taken on (512^3, bCoef dropped, default tile shape)."""
-    p = os.path.join(ROOT, "profiles", "r1_fused_v4_ncu_summary.json")
-    if not (os.path.exists(p) and args.n == 512 and not args.keep_b and args.smoother == 1 and args.fused_cfg in (None, 4)):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel -- the average over the four
+    finest-level sweeps of one V-cycle (zero-start, plain, prolonging, plain), like `achieved` -- from the committed
+    `ncu --set full` capture of this command (profiles/), valid for the configuration it was taken on (512^3, bCoef
+    dropped, default tile shapes)."""
+    p = os.path.join(ROOT, "profiles", TRAFFIC_SOURCE)
+    if not (os.path.exists(p) and args.n == 512 and not args.keep_b and args.smoother == 1 and args.smooth == 2 and args.fused_cfg in (None, 4, 5)):
         return None
     try:
-        m = json.load(open(p))["metrics"]
-        rd = [float(x) for x in m["dram__bytes_read.sum"]["per_launch"]]
-        wr = [float(x) for x in m["dram__bytes_write.sum"]["per_launch"]]
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m["dram__bytes_read.sum"]["unit"]]
-        return (sum(rd) / len(rd) + sum(wr) / len(wr)) * scale
+        return float(json.load(open(p))["finest_level_avg_dram_gbyte_per_launch"]["total"]) * 1e9
     except Exception:
         return None
+
+
+TRAFFIC_SOURCE = "r1c_fused_vcycle_ncu_summary.json"
 
 
 def peaks():
@@ -354,7 +355,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "finest-level GSRB " + ("fused red+black sweep" if args.smoother == 1 else "colour pass"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": profiled_traffic(args),
-                         "traffic_source": "profiles/r1_fused_v4_ncu_summary.json (ncu --set full, plain sweep)", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "traffic_source": "profiles/" + TRAFFIC_SOURCE + " (ncu --set full of this command: the four finest-level sweeps of one V-cycle)", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
                          "launches_timed": k_launches, "avg_launch_ms": kdur * 1e3,
                          "kernel_share_of_step": k_ms / ms_prof,
                          "share_measured_on": "second pass of the same K steps launched eagerly with per-launch CUDA events "
