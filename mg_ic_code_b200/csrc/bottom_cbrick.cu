@@ -13,7 +13,9 @@
 // those of bottom.cu / the oracle (gsrb_point, lap7, the [Chombo] BiCGStabSolver restatement).
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "mgic_internal.h"
 #include "mgic_device.cuh"
@@ -35,7 +37,7 @@ struct CbArgs {
   double *part;      // 2 buffers x 2 values x gridDim partials
   unsigned *bar;     // barrier of the clusters: [0] arrivals, [BAR_GEN] generation
   int nclusters;
-  int bx, by, bz, nbx, nby;
+  int nbx, nby, nbz; // bricks per direction; brick q of n cells spans [q*n/nb, (q+1)*n/nb)
   int cs, maxp;      // cluster size; most region planes a CTA holds
   unsigned stride;   // doubles per shared-memory vector
   int imax;
@@ -78,9 +80,9 @@ struct Cb {
     rank = (int)cl.block_rank();
     const int b = blockIdx.x / A.cs;
     const int ib = b % A.nbx, jb = (b / A.nbx) % A.nby, kb = b / (A.nbx * A.nby);
-    const int n[3] = {A.g.nx, A.g.ny, A.g.nz}, bs[3] = {A.bx, A.by, A.bz}, q[3] = {ib, jb, kb};
+    const int n[3] = {A.g.nx, A.g.ny, A.g.nz}, nb[3] = {A.nbx, A.nby, A.nbz}, q[3] = {ib, jb, kb};
     for (int d = 0; d < 3; d++) {
-      lo[d] = q[d] * bs[d]; hi[d] = min(lo[d] + bs[d], n[d]) - 1;
+      lo[d] = (q[d] * n[d]) / nb[d]; hi[d] = ((q[d] + 1) * n[d]) / nb[d] - 1;
       rlo[d] = max(lo[d] - HALO, 0); rhi[d] = min(hi[d] + HALO, n[d] - 1);
     }
     rx = rhi[0] - rlo[0] + 1; ry = rhi[1] - rlo[1] + 1; rz = rhi[2] - rlo[2] + 1;
@@ -439,27 +441,59 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
     npok = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : 0;
     cudaGetLastError();
   }
-  // largest region edge of a brick of edge b in a level of edge nn (the halo is clipped at the domain faces)
-  auto ext = [](int b, int nn) { const int nb = nn / b; return nb == 1 ? nn : (nb == 2 ? b + HALO : b + 2 * HALO); };
-  for (int cs = npok ? 16 : 8; cs >= 8; cs >>= 1) {
-    for (int target = (cs == 16 ? 8 : 16); target >= 1; target >>= 1) {
-      // bricks: halve the longest edge (x before y before z on ties) until `target` bricks exist
-      int b[3] = {g.nx, g.ny, g.nz}, count = 1;
-      while (count < target) {
-        int d = 0;
-        if (b[1] > b[d]) d = 1;
-        if (b[2] > b[d]) d = 2;
-        if (b[d] % 2 || b[d] / 2 < 8) break;
-        b[d] /= 2; count *= 2;
-      }
-      if (count != target) continue;
-      if (b[2] < cs) continue;  // every CTA of a cluster needs at least one plane
-      const int rzmax = ext(b[2], g.nz), maxp = (rzmax + cs - 1) / cs;
-      const size_t stride = (size_t)maxp * ext(b[0], g.nx) * ext(b[1], g.ny);
-      const size_t smem = nvec * stride * sizeof(double);
-      if (smem > 200 * 1024) continue;
+  // Brick decomposition: any (nbx, nby, nbz) whose clusters are all co-resident (B200 places 7 clusters of 16 CTAs or 15
+  // of 8), bricks of at least 8 cells per edge, every CTA of a cluster at least one plane.  A pass is bound by the cell
+  // visits of one CTA, so the candidates are tried in the order of the per-CTA shared-memory vector length.
+  struct Cand { int cs, nb[3], maxp, count; size_t stride; };
+  std::vector<Cand> cands;
+  // clusters the device can hold at once, per cluster size (1024-thread CTAs: one per SM whatever the shared memory)
+  static int maxAct[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
+  int *ma = maxAct[(o->b ? 1 : 0) + (NT == 512 ? 0 : 2)];
+  for (int ci = 0; ci < 2; ci++) {
+    if (ma[ci] >= 0) continue;
+    const int cs = ci ? 8 : 16;
+    ma[ci] = 0;
+    if (cs == 16 && !npok) continue;
+    const size_t smem = 160 * 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16 * cs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) ma[ci] = n;
+    cudaGetLastError();
+  }
+  const int nn[3] = {g.nx, g.ny, g.nz};
+  // largest / smallest region edge over the bricks of one direction (the halo is clipped at the domain faces)
+  auto rmax = [&](int d, int nb) { const int bmax = (nn[d] + nb - 1) / nb; return std::min(nn[d], bmax + (nb == 1 ? 0 : nb == 2 ? HALO : 2 * HALO)); };
+  auto rmin = [&](int d, int nb) { const int bmin = nn[d] / nb; return std::min(nn[d], bmin + (nb == 1 ? 0 : HALO)); };
+  for (int cs = npok ? 16 : 8; cs >= 8; cs >>= 1)
+    for (int nbz = 1; nbz <= 8; nbz++)
+      for (int nby = 1; nby <= 8; nby++)
+        for (int nbx = 1; nbx <= 8; nbx++) {
+          const int count = nbx * nby * nbz;
+          if (count > ma[cs == 16 ? 0 : 1] || nn[0] / nbx < 8 || nn[1] / nby < 8 || nn[2] / nbz < 8) continue;
+          if (rmin(2, nbz) < cs) continue;
+          Cand q;
+          q.cs = cs; q.nb[0] = nbx; q.nb[1] = nby; q.nb[2] = nbz; q.count = count;
+          q.maxp = (rmax(2, nbz) + cs - 1) / cs;
+          q.stride = (size_t)q.maxp * rmax(0, nbx) * rmax(1, nby);
+          if (nvec * q.stride * sizeof(double) > 200 * 1024 || 4 * count * cs > partCap) continue;
+          cands.push_back(q);
+        }
+  std::stable_sort(cands.begin(), cands.end(), [](const Cand &x, const Cand &y) {
+    return x.stride != y.stride ? x.stride < y.stride : x.count < y.count;
+  });
+  static const bool debug = getenv("MGIC_DEBUG") != nullptr;
+  int tried = 0;
+  for (const Cand &q : cands) {
+    if (++tried > 12) break;  // each rejected candidate costs an occupancy query per launch
+    {
+      const int cs = q.cs, count = q.count, maxp = q.maxp;
+      const size_t stride = q.stride, smem = nvec * stride * sizeof(double);
       const int blocks = count * cs;
-      if (4 * blocks > partCap) continue;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
@@ -467,9 +501,8 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
-      static const bool debug = getenv("MGIC_DEBUG") != nullptr;
       const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-      if (debug) fprintf(stderr, "mgic cbrick: cs %d bricks %d (%d,%d,%d) smem %zu -> max active clusters %d (%s)\n", cs, count, b[0], b[1], b[2], smem, nclusters, cudaGetErrorString(oe));
+      if (debug) fprintf(stderr, "mgic cbrick: cs %d bricks %dx%dx%d smem %zu -> max active clusters %d (%s)\n", cs, q.nb[0], q.nb[1], q.nb[2], smem, nclusters, cudaGetErrorString(oe));
       if (oe != cudaSuccess || nclusters < count) { cudaGetLastError(); continue; }
       if (!g_bar[c->device]) {
         MGIC_CUDA(cudaMalloc(&g_bar[c->device], 2 * BAR_GEN * sizeof(unsigned)));
@@ -481,8 +514,7 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
       A.phi = e->p; A.rhs = r->p; A.a = o->a->p; A.b = o->b ? o->b->p : nullptr; A.lam = o->lambda->p;
       A.r = work[0]->p; A.rt = work[1]->p; A.e = work[2]->p; A.p0 = work[3]->p; A.p1 = work[4]->p; A.v0 = work[5]->p; A.v1 = work[6]->p;
       A.part = part; A.bar = g_bar[c->device]; A.nclusters = count;
-      A.bx = b[0]; A.by = b[1]; A.bz = b[2];
-      A.nbx = g.nx / b[0]; A.nby = g.ny / b[1];
+      A.nbx = q.nb[0]; A.nby = q.nb[1]; A.nbz = q.nb[2];
       A.cs = cs; A.maxp = maxp; A.stride = (unsigned)stride;
       A.imax = 80; A.eps = 1.0e-6; A.reps = 1.0e-12; A.hang = 1.0e-8; A.small = 1.0e-30; A.numRestarts = 5;
       A.out = d_out;

@@ -432,9 +432,7 @@ def test_bottom_solver_on_agglomerated_size_levels(ctx, shape, bc, keep_b):
     finally:
         ctx.set_option("bottom_kernel", 1)
     assert out["host"][2] == 0 and out["brick"][2] == 4
-    # (with bCoef streamed, the five shared-memory vectors of a 32x32x64 brick exceed an SM: 64^3 falls back to bricks per CTA)
-    want = 4 if (keep_b and shape == (64, 64, 64)) else 5
-    assert out["default"][2] == want and out["cbrick"][2] == want, "the cluster-brick kernel did not run"
+    assert out["default"][2] == 5 and out["cbrick"][2] == 5, "the cluster-brick kernel did not run"
     assert 1 < out["host"][0] < 70
     rn = np.sqrt((r * r).sum())
     for name in ("host", "brick", "default", "cbrick"):
