@@ -100,13 +100,13 @@ __device__ __forceinline__ u64 now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// spin until *p >= v; a neighbour that died must not leave this GPU spinning forever: trap after 20 s
+// spin until *p >= v; a neighbour that died must not leave this GPU spinning forever: trap after 60 s
 __device__ __forceinline__ void wait_ge(const u64 *p, u64 v) {
   if (ld_acquire_sys(p) >= v) return;
   const u64 t0 = now_ns();
   while (ld_acquire_sys(p) < v) {
     __nanosleep(100);
-    if (now_ns() - t0 > 20000000000ull) { printf("mgic: halo exchange timed out waiting for a neighbour rank\n"); __trap(); }
+    if (now_ns() - t0 > 60000000000ull) { printf("mgic: halo exchange timed out waiting for a neighbour rank\n"); __trap(); }
   }
 }
 
