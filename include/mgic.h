@@ -117,6 +117,17 @@ int mgic_ctx_set_rank(mgic_ctx *, int rank, int nranks);
  * [k0, k0+nz_local).  Single GPU: k0 = 0, nz_local = n[2]. */
 int mgic_op_create(mgic_ctx *, const int n[3], int k0, int nz_local, double dx, double alpha, double beta,
                    const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
+/* One AMR level > 0 (first half): the operator on a box [lo, hi] (inclusive, level index space,
+ * coarsenable by 2) of the refined domain n_domain.  Faces of the box that are not domain faces are coarse-fine
+ * interfaces; there the operator does what the reference's class does itself on such a level --
+ * [Chombo] AMRPoissonOp::homogeneousCFInterp before each colour pass of levelGSRB
+ * (Source/VariableCoeffPoissonOperator.cpp:296) and before restrictResidual (:156): the ghost value is the parabola
+ * through the two interior cells and a ZERO coarse value.  mgic_op_relax / _level_gsrb / _precond /
+ * _restrict_residual and the vector operations work on it; mgic_op_residual / _apply need QuadCFInterp's coarse-fine
+ * ghost values (inherited AMRPoissonOp::AMRResidual* / AMROperator*), which are not built: they fail with MGIC_ERR_ARG.
+ * Fields of the operator are patch-shaped. */
+int mgic_op_create_patch(mgic_ctx *, const int n_domain[3], const int lo[3], const int hi[3], double dx, double dx_coarse,
+                         double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
 int mgic_op_destroy(mgic_op *);
 /* setCoefs (VariableCoeffPoissonOperator.cpp:208-218): coefficients are SHARED (caller keeps them alive);
  * bCoef may be NULL == the constant 1 (set_b_coef, Source/SetLevelData.cpp:330-340) */

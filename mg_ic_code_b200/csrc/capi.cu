@@ -177,6 +177,25 @@ BCk mgic_op::bck(bool homogeneous) const {
   if (k0 > 0) k.type[4] = MGIC_FACE_INTERIOR;
   if (k0 + nzl < n[2]) k.type[5] = MGIC_FACE_INTERIOR;
   if (ctx->nranks > 1 && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
+  for (int q = 0; q < 7; q++) k.cf[q] = 0.0;
+  if (isPatch) {
+    // INTERPHOMO's constants, computed in its order ([Chombo] AMRPoissonOpF.ChF; oracle: Op::homogeneousCFInterp)
+    const double x1 = dx;
+    const double x2 = 0.5 * (3. * x1 + dxCrse);
+    const double denom = 1.0 - ((x1 + x2) / x1);
+    const double x = 2. * x1;
+    k.cf[0] = 1 / (x1 * x1);          // m1
+    k.cf[1] = 1 / (x1 * (x1 - x2));   // m2
+    k.cf[2] = 1 / (denom);            // idenom
+    k.cf[3] = 1 / (x1 - x2);          // q1
+    k.cf[4] = x1 + x2;                // q2
+    k.cf[5] = x;
+    k.cf[6] = x * x;                  // xsquared
+    for (int d = 0; d < 3; d++) {
+      if (cfLo[d]) k.type[2 * d] = MGIC_FACE_CF;
+      if (cfHi[d]) k.type[2 * d + 1] = MGIC_FACE_CF;
+    }
+  }
   return k;
 }
 
@@ -220,6 +239,32 @@ extern "C" int mgic_op_create(mgic_ctx *c, const int n[3], int k0, int nz_local,
   for (int d = 0; d < 3; d++) { o->n[d] = n[d]; o->bc_lo[d] = bc_lo[d]; o->bc_hi[d] = bc_hi[d]; }
   o->k0 = k0; o->nzl = nz_local; o->dx = dx; o->alpha = alpha; o->beta = beta; o->bc_value = bc_value;
   *out = o;
+  return MGIC_OK;
+}
+
+// One AMR level > 0: a box [lo, hi] of the refined domain (VariableCoeffPoissonOperator.cpp:156,296: the operator's own
+// coarse-fine code is homogeneousCFInterp before levelGSRB's colour passes and before restrictResidual)
+extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const int lo[3], const int hi[3], double dx, double dx_coarse,
+                                    double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out) {
+  MGIC_REQUIRE(c && n_domain && lo && hi && out && bc_lo && bc_hi, "NULL argument");
+  MGIC_REQUIRE(c->nranks == 1, "AMR patches on a multi-rank context are not supported");
+  int n[3];
+  for (int d = 0; d < 3; d++) {
+    MGIC_REQUIRE(lo[d] >= 0 && hi[d] < n_domain[d] && hi[d] - lo[d] + 1 >= 2, "patch box outside the domain or thinner than two cells");
+    MGIC_REQUIRE(lo[d] % 2 == 0 && hi[d] % 2 == 1, "patch box must be coarsenable by 2");
+    n[d] = hi[d] - lo[d] + 1;
+  }
+  MGIC_REQUIRE(dx_coarse > dx && dx > 0, "the coarser level's spacing must exceed the patch's");
+  MGIC_TRY(mgic_op_create(c, n, 0, n[2], dx, alpha, beta, bc_lo, bc_hi, bc_value, out));
+  mgic_op *o = *out;
+  o->isPatch = true;
+  o->dxCrse = dx_coarse;
+  o->cshift = (lo[0] + lo[1] + lo[2]) & 1;
+  o->smoother = 0;  // the fused sweep stages planes by TMA and has no coarse-fine ghost variant: per-colour kernel
+  for (int d = 0; d < 3; d++) {
+    o->cfLo[d] = lo[d] > 0;
+    o->cfHi[d] = hi[d] < n_domain[d] - 1;
+  }
   return MGIC_OK;
 }
 
@@ -449,6 +494,7 @@ extern "C" int mgic_op_relax(mgic_op *o, mgic_field *e, const mgic_field *r, int
 
 extern "C" int mgic_op_residual(mgic_op *o, mgic_field *lhs, mgic_field *phi, const mgic_field *rhs, int homogeneous) {
   MGIC_REQUIRE(o && lhs && phi && rhs && o->a, "NULL argument");
+  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp, which is not built; relax, restrictResidual and preCond use homogeneousCFInterp");
   REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
   MGIC_TRY(halo(o, phi, 1));  // :48
   return mgk::residual(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, rhs->p, o->a->p, bptr(o), o->alpha, o->beta,
@@ -456,6 +502,7 @@ extern "C" int mgic_op_residual(mgic_op *o, mgic_field *lhs, mgic_field *phi, co
 }
 extern "C" int mgic_op_apply(mgic_op *o, mgic_field *lhs, mgic_field *phi, int homogeneous) {
   MGIC_REQUIRE(o && lhs && phi && o->a, "NULL argument");
+  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp, which is not built; relax, restrictResidual and preCond use homogeneousCFInterp");
   REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi);
   MGIC_TRY(halo(o, phi, 1));  // :131
   return mgk::apply_op(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, o->a->p, bptr(o), o->alpha, o->beta, o->dx);

@@ -412,6 +412,7 @@ namespace mgk {
 // Periodic faces (TMA cannot wrap), odd nx and small (launch-latency bound) levels use the per-colour kernel, which
 // computes the same bits.
 bool gsrb_fused_applicable(const mgic_op *o) {
+  if (o->isPatch) return false;  // coarse-fine ghosts need the second interior cell: per-colour kernel
   for (int d = 0; d < 3; d++)
     if (o->bc_lo[d] == MGIC_BC_PERIODIC) return false;
   const long long cells = (long long)o->n[0] * o->n[1] * o->nzl;

@@ -27,21 +27,31 @@ __device__ __forceinline__ double gsrb_point(double c, double xm, double xp, dou
 // Neighbour values of cell (i,j,k) (local indices) with the physical BC folded in.
 struct Nb { double xm, xp, ym, yp, zm, zp; };
 
-__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *p, long long wrapIdx) {
+// [Chombo] AMRPoissonOpF.ChF INTERPHOMO: the parabola through pa (second interior cell), pb (first interior cell) and a
+// zero coarse value, at the ghost cell; operation order of the Fortran (constants precomputed on the host the same way)
+__device__ __forceinline__ double cf_homog(const double *cf, double pa, double pb) {
+  const double a = ((pb - pa) * cf[0] - (pb)*cf[1]) * cf[2];
+  const double b = (pb)*cf[3] - a * cf[4];
+  return a * cf[6] + b * cf[5] + pa;
+}
+
+__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *p, long long wrapIdx, long long farIdx) {
   // Dirichlet / Neumann: a*c + b  (DiriBC order 1: 2v - near;  NeumBC: near + sign*dx*v  [Chombo BCFunc])
-  return bc.type[f] == MGIC_BC_PERIODIC ? p[wrapIdx] : bc.a[f] * c + bc.b[f];
+  if (bc.type[f] == MGIC_BC_PERIODIC) return p[wrapIdx];
+  if (bc.type[f] == MGIC_FACE_CF) return cf_homog(bc.cf, p[farIdx], c);
+  return bc.a[f] * c + bc.b[f];
 }
 
 __device__ __forceinline__ Nb neighbours(const double *p, long long idx, int i, int j, int k, const Geom &g,
                                          const BCk &bc, double c) {
   Nb n;
-  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1));
-  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1));
-  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy);
-  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy);
+  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1), idx + 1);
+  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1), idx - 1);
+  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy, idx + g.sy);
+  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy, idx - g.sy);
   // z: ghost planes exist in memory; MGIC_FACE_INTERIOR means they hold the neighbour slab's planes
-  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz);
-  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz);
+  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz, idx + g.sz);
+  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz, idx - g.sz);
   return n;
 }
 

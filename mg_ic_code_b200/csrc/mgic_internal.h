@@ -38,9 +38,14 @@ void mgic_set_error(const char *fmt, ...);
 // Face order: 0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi.
 // type: 0 Dirichlet, 1 Neumann, 2 periodic, 3 interior (the neighbour plane is in memory: z-slab halo)
 #define MGIC_FACE_INTERIOR 3
+// 4 coarse-fine interface of an AMR patch, homogeneous form ([Chombo] homogeneousCFInterp): the ghost value is the
+// parabola through the two interior cells and a zero coarse value -- a function of the current field like the physical
+// ghosts, so it is evaluated in the stencil too (cf[] = m1, m2, idenom, q1, q2, x, x*x of INTERPHOMO)
+#define MGIC_FACE_CF 4
 struct BCk {
   int type[6];
   double a[6], b[6];  // ghost = a*centre + b   (Dirichlet: a=-1, b=2v; Neumann: a=+1, b=sign*dx*v)
+  double cf[7];
 };
 
 struct Geom {
@@ -136,11 +141,16 @@ struct mgic_op {
   mgic_field *lambda = nullptr;           // owned
   mgic_field *scratch = nullptr;          // owned; ping-pong target of the fused sweep
   bool lambdaDirty = true;
+  // AMR patch (mgic_op_create_patch): n[] is the patch, cfLo/cfHi mark its coarse-fine faces, cshift keeps the GLOBAL-index
+  // colouring ((lo0+lo1+lo2) & 1), dxCrse is the coarser level's spacing
+  bool isPatch = false, cfLo[3] = {false, false, false}, cfHi[3] = {false, false, false};
+  int cshift = 0;
+  double dxCrse = 0;
   bool isGlobal = false;                  // whole-domain operator on a multi-rank context (agglomerated level): no halos
   bool profTag = true;                    // finest-level operator: its GSRB launches are the profiled kernel
   int smoother = 1;                       // 0: one launch per colour; 1: fused red+black plane-streaming sweep
   Geom geom() const {
-    Geom g; g.nx = n[0]; g.ny = n[1]; g.nz = nzl; g.sy = n[0]; g.sz = (long long)n[0] * n[1]; g.k0 = k0; g.gnz = n[2];
+    Geom g; g.nx = n[0]; g.ny = n[1]; g.nz = nzl; g.sy = n[0]; g.sz = (long long)n[0] * n[1]; g.k0 = k0 + cshift; g.gnz = n[2];
     return g;
   }
   BCk bck(bool homogeneous) const;

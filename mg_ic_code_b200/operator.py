@@ -140,6 +140,18 @@ class VariableCoeffPoissonOperator:
         check(self.L.mgic_op_dims(self.h, n3, C.byref(k0_), C.byref(nzl_), C.byref(dx_)))
         self.n, self.k0, self.nz_local, self.dx = (n3[0], n3[1], n3[2]), k0_.value, nzl_.value, dx_.value
 
+    @classmethod
+    def patch(cls, ctx, n_domain, lo, hi, dx, dx_coarse=None, alpha=1.0, beta=-1.0, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), bc_value=0.0):
+        """The operator on one box [lo, hi] of an AMR level > 0: coarse-fine faces get [Chombo] homogeneousCFInterp in
+        relax / restrictResidual / preCond (VariableCoeffPoissonOperator.cpp:156,296)."""
+        i3 = C.c_int * 3
+        h = C.c_void_p()
+        check(ctx.L.mgic_op_create_patch(ctx.h, i3(*n_domain), i3(*lo), i3(*hi), dx, 2 * dx if dx_coarse is None else dx_coarse,
+                                         alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value, C.byref(h)))
+        op = cls(ctx, None, None, handle=h)
+        op.owned = True
+        return op
+
     # AMRLevelOp::create
     def create(self):
         return LevelField(self)

@@ -383,6 +383,47 @@ struct Op {
   LevelData *aCoef = nullptr, *bCoef = nullptr;   // shared at depth 0 (Factory.cpp:194-197)
   LevelData aOwn, bOwn, lambda;
   bool lambdaNeedsResetting = true;
+  // an AMR level > 0 (a union of boxes that does not cover the domain): the coarser level's spacing
+  bool hasCoarser = false; Real dxCrse = 0;
+
+  // [Chombo] AMRPoissonOp::homogeneousCFInterp -> AMRPoissonOpF.ChF INTERPHOMO (restated from the published
+  // algorithm; Chombo is not vendored): every face ghost cell on a coarse-fine interface gets the value at x = 2*dx of
+  // the parabola through the second interior cell (at 0), the first interior cell (at dx) and a ZERO coarse value at
+  // x2 = (3*dx + dxCrse)/2.  All face ghost cells inside the domain are filled; the exchange that follows at every call
+  // site (VariableCoeffPoissonOperator.cpp:163,301) overwrites the ones a neighbouring box of the level covers.
+  void homogeneousCFInterp(LevelData &phi) {
+    if (!hasCoarser) return;
+    const Real x1 = dx;
+    const Real x2 = 0.5 * (3. * x1 + dxCrse);
+    const Real denom = 1.0 - ((x1 + x2) / x1);
+    const Real idenom = 1 / (denom);
+    const Real x = 2. * x1;
+    const Real xsquared = x * x;
+    const Real m1 = 1 / (x1 * x1);
+    const Real m2 = 1 / (x1 * (x1 - x2));
+    const Real q1 = 1 / (x1 - x2);
+    const Real q2 = x1 + x2;
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < phi.size(); n++) {
+      FAB &f = phi.fab[n];
+      for (int dir = 0; dir < 3; dir++)
+        for (int side = -1; side <= 1; side += 2) {
+          const Box region = adjCellBox(lay.boxes[n], dir, side, 1) & lay.domain & f.b;
+          if (region.empty()) continue;
+          int ii[3] = {0, 0, 0}; ii[dir] = side;
+          for (int c = 0; c < phi.nc; c++)
+            for (int k = region.lo[2]; k <= region.hi[2]; k++)
+              for (int j = region.lo[1]; j <= region.hi[1]; j++)
+                for (int i = region.lo[0]; i <= region.hi[0]; i++) {
+                  const Real pa = f(i - 2 * ii[0], j - 2 * ii[1], k - 2 * ii[2], c);
+                  const Real pb = f(i - ii[0], j - ii[1], k - ii[2], c);
+                  const Real a = ((pb - pa) * m1 - (pb)*m2) * idenom;
+                  const Real b = (pb)*q1 - a * q2;
+                  f(i, j, k, c) = a * xsquared + b * x + pa;
+                }
+        }
+    }
+  }
 
   // resetLambda -- VariableCoeffPoissonOperator.cpp:220-249
   void resetLambda() {
@@ -409,7 +450,7 @@ struct Op {
 
   // levelGSRB -- VariableCoeffPoissonOperator.cpp:273-332
   void gsrbColor(LevelData &dpsi, const LevelData &rhs, int whichPass) {
-    // homogeneousCFInterp: no-op without a coarser AMR level            :296
+    homogeneousCFInterp(dpsi);                                         // :296 (no-op without a coarser AMR level)
     exchange(dpsi, lay.exFace1);                                       // :301
     applyBC(dpsi, true);                                               // :307-310
 #pragma omp parallel for schedule(static)
@@ -445,6 +486,7 @@ struct Op {
   }
   // restrictResidual -- VariableCoeffPoissonOperator.cpp:151-194
   void restrictResidual(LevelData &resCoarse, LevelData &dpsiFine, const LevelData &rhsFine) {
+    homogeneousCFInterp(dpsiFine);                                     // :156
     applyBC(dpsiFine, true);                                           // :158-161
     exchange(dpsiFine, lay.exFace1);                                   // :163
 #pragma omp parallel for schedule(static)
@@ -1132,6 +1174,95 @@ void orc_op_prolong(orc_problem *pb, int d) { pb->ops[d]->prolongIncrement(pb->e
 void orc_op_precond(orc_problem *pb, int d) { pb->ops[d]->preCond(pb->e[d], pb->r[d]); }
 double orc_op_norm(orc_problem *pb, int d, int field, int ord) { return pb->ops[d]->norm(*fieldOf(pb, d, field), ord); }
 double orc_op_dot(orc_problem *pb, int d, int f1, int f2) { return pb->ops[d]->dot(*fieldOf(pb, d, f1), *fieldOf(pb, d, f2)); }
+
+// ---- one AMR level > 0: a box of the refined domain (split into max_grid_size boxes) with its coarser level's spacing.
+// What the reference's operator class itself does on such a level: levelGSRB and restrictResidual with
+// homogeneousCFInterp (VariableCoeffPoissonOperator.cpp:156,296).  Fields are patch-shaped arrays, x fastest.
+struct orc_patch {
+  Op op;
+  LevelData e, r, a, b, rc;   // correction (1 ghost), residual, coefficients, MG-coarsened residual
+  Layout clay;
+  Box box;
+};
+
+orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi[3], int max_grid_size, double dx, double dx_crse,
+                            double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value) {
+  const Box pbox(lo, hi);
+  const Box dom(0, 0, 0, n_domain[0] - 1, n_domain[1] - 1, n_domain[2] - 1);
+  // (AMR boxes are aligned to block_factor; restrictResidual needs every box coarsenable by 2)
+  if (pbox.empty() || !dom.contains(pbox) || !pbox.coarsenable(2) || max_grid_size % 2) return nullptr;
+  orc_patch *pp = new orc_patch;
+  pp->box = pbox;
+  Op &op = pp->op;
+  op.lay.domain = Box(0, 0, 0, n_domain[0] - 1, n_domain[1] - 1, n_domain[2] - 1);
+  domainSplit(pp->box, max_grid_size, op.lay.boxes);
+  op.lay.buildCopier(op.lay.exFace1, 1, true);
+  op.dx = dx; op.alpha = alpha; op.beta = beta;
+  op.hasCoarser = true; op.dxCrse = dx_crse;
+  for (int d = 0; d < 3; d++) { op.bc.lo[d] = bc_lo[d]; op.bc.hi[d] = bc_hi[d]; }
+  op.bc.value = bc_value;
+  pp->e.define(&op.lay, 1, 1); pp->r.define(&op.lay, 1, 0); pp->a.define(&op.lay, 1, 0); pp->b.define(&op.lay, 1, 0);
+  op.aCoef = &pp->a; op.bCoef = &pp->b;
+  op.lambda.define(&op.lay, 1, 0);
+  pp->clay.domain = op.lay.domain.coarsened(2);
+  for (auto &bx : op.lay.boxes) pp->clay.boxes.push_back(bx.coarsened(2));
+  pp->rc.define(&pp->clay, 1, 0);
+  return pp;
+}
+void orc_patch_destroy(orc_patch *pp) { delete pp; }
+
+static LevelData *patchField(orc_patch *pp, int field) {
+  switch (field) {
+    case ORC_F_E: return &pp->e;
+    case ORC_F_R: return &pp->r;
+    case ORC_F_A: return &pp->a;
+    case ORC_F_B: return &pp->b;
+    case ORC_F_TMP: return &pp->rc;
+    case ORC_F_LAMBDA: return &pp->op.lambda;
+  }
+  fprintf(stderr, "orc_patch: bad field %d\n", field); abort();
+}
+// patch-shaped array (coarsened patch for ORC_F_TMP = the restricted residual)
+void orc_patch_set(orc_patch *pp, int field, const double *in) {
+  LevelData *ld = patchField(pp, field);
+  const Box pb = (field == ORC_F_TMP) ? pp->box.coarsened(2) : pp->box;
+  const long nx = pb.size(0), ny = pb.size(1);
+  for (int n = 0; n < ld->size(); n++) {
+    const Box &b = ld->lay->boxes[n]; FAB &f = ld->fab[n];
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++) f(i, j, k) = in[(i - pb.lo[0]) + nx * ((j - pb.lo[1]) + ny * (long)(k - pb.lo[2]))];
+  }
+  if (field == ORC_F_A || field == ORC_F_B) pp->op.lambdaNeedsResetting = true;
+}
+void orc_patch_get(orc_patch *pp, int field, double *out) {
+  if (field == ORC_F_LAMBDA) pp->op.resetLambda();
+  const LevelData *ld = patchField(pp, field);
+  const Box pb = (field == ORC_F_TMP) ? pp->box.coarsened(2) : pp->box;
+  const long nx = pb.size(0), ny = pb.size(1);
+  for (int n = 0; n < ld->size(); n++) {
+    const Box &b = ld->lay->boxes[n]; const FAB &f = ld->fab[n];
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++) out[(i - pb.lo[0]) + nx * ((j - pb.lo[1]) + ny * (long)(k - pb.lo[2]))] = f(i, j, k);
+  }
+}
+int orc_patch_num_boxes(const orc_patch *pp) { return (int)pp->op.lay.boxes.size(); }
+void orc_patch_relax(orc_patch *pp, int iterations) { pp->op.relax(pp->e, pp->r, iterations); }
+void orc_patch_gsrb_color(orc_patch *pp, int whichPass) { pp->op.resetLambda(); pp->op.gsrbColor(pp->e, pp->r, whichPass); }
+void orc_patch_restrict(orc_patch *pp) { pp->op.restrictResidual(pp->rc, pp->e, pp->r); }
+void orc_patch_precond(orc_patch *pp) { pp->op.preCond(pp->e, pp->r); }
+// the ghost value homogeneousCFInterp produces from the two interior cells (far, near) -- the coefficients' pin
+double orc_interp_homo(double dx, double dx_crse, double far_value, double near_value) {
+  Op op; op.dx = dx; op.dxCrse = dx_crse; op.hasCoarser = true;
+  op.lay.domain = Box(0, 0, 0, 7, 0, 0);
+  op.lay.boxes.push_back(Box(0, 0, 0, 3, 0, 0));
+  LevelData x; x.define(&op.lay, 1, 1);
+  x.fab[0].setVal(0.0);
+  x.fab[0](2, 0, 0) = far_value; x.fab[0](3, 0, 0) = near_value;
+  op.homogeneousCFInterp(x);
+  return x.fab[0](4, 0, 0);
+}
 
 int orc_vcycle(orc_problem *pb) {
   pb->lastBottomIters = 0;

@@ -137,6 +137,23 @@ double orc_update_psi0(orc_problem *);
 /* full NL loop (Main_PoissonSolver.cpp:131-216); dpsi_norms[NL_iter]; returns #NL iterations */
 int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
 
+/* ---- one AMR level > 0 (a box of the refined domain, split into max_grid_size boxes): what the reference's operator
+ * class does there itself -- levelGSRB and restrictResidual with [Chombo] homogeneousCFInterp
+ * (VariableCoeffPoissonOperator.cpp:156,296).  Fields: ORC_F_E, ORC_F_R, ORC_F_A, ORC_F_B, ORC_F_LAMBDA as patch-shaped
+ * arrays (x fastest); ORC_F_TMP = the restricted residual on the patch coarsened by 2. */
+typedef struct orc_patch orc_patch;
+orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi[3], int max_grid_size, double dx, double dx_crse,
+                            double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value);
+void orc_patch_destroy(orc_patch *);
+void orc_patch_set(orc_patch *, int field, const double *in);
+void orc_patch_get(orc_patch *, int field, double *out);
+int orc_patch_num_boxes(const orc_patch *);
+void orc_patch_relax(orc_patch *, int iterations);
+void orc_patch_gsrb_color(orc_patch *, int whichPass);
+void orc_patch_restrict(orc_patch *);
+void orc_patch_precond(orc_patch *);
+double orc_interp_homo(double dx, double dx_crse, double far_value, double near_value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,19 @@ def lib():
         L.orc_update_psi0.restype = C.c_double
         L.orc_nl_solve.argtypes = [C.c_void_p, dp, C.c_int]
         L.orc_nl_solve.restype = C.c_int
+        i3 = C.c_int * 3
+        L.orc_patch_create.restype = C.c_void_p
+        L.orc_patch_create.argtypes = [i3, i3, i3, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double]
+        L.orc_patch_destroy.argtypes = [C.c_void_p]
+        L.orc_patch_set.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_patch_get.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_patch_num_boxes.argtypes = [C.c_void_p]
+        L.orc_patch_relax.argtypes = [C.c_void_p, C.c_int]
+        L.orc_patch_gsrb_color.argtypes = [C.c_void_p, C.c_int]
+        L.orc_patch_restrict.argtypes = [C.c_void_p]
+        L.orc_patch_precond.argtypes = [C.c_void_p]
+        L.orc_interp_homo.argtypes = [C.c_double] * 4
+        L.orc_interp_homo.restype = C.c_double
         _lib = L
     return _lib
 
@@ -229,3 +242,61 @@ class Oracle:
     @property
     def num_threads(self):
         return self.L.orc_num_threads()
+
+
+class OraclePatch:
+    """One AMR level > 0 on the CPU oracle: a box [lo, hi] of the refined domain, split into max_grid_size boxes, with
+    [Chombo] homogeneousCFInterp at its coarse-fine faces (VariableCoeffPoissonOperator.cpp:156,296)."""
+
+    def __init__(self, n_domain, lo, hi, dx, dx_crse=None, max_grid_size=8, alpha=1.0, beta=-1.0, bc_lo=(0, 0, 0),
+                 bc_hi=(0, 0, 0), bc_value=0.0):
+        self.L = lib()
+        i3 = C.c_int * 3
+        self.lo, self.hi = tuple(lo), tuple(hi)
+        self.shape = tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
+        self.cshape = tuple(s // 2 for s in self.shape)
+        self.h = self.L.orc_patch_create(i3(*n_domain), i3(*lo), i3(*hi), max_grid_size, dx, 2 * dx if dx_crse is None else dx_crse,
+                                         alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value)
+        if not self.h:
+            raise ValueError("patch box must lie in the domain and be coarsenable by 2 (even lo, odd hi), max_grid_size even")
+
+    def close(self):
+        if self.h:
+            self.L.orc_patch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_boxes(self):
+        return self.L.orc_patch_num_boxes(self.h)
+
+    def set(self, field, arr):
+        self.L.orc_patch_set(self.h, FIELD[field], np.ascontiguousarray(arr, dtype=np.float64))
+
+    def get(self, field):
+        out = np.empty(self.cshape if field == "TMP" else self.shape, dtype=np.float64)
+        self.L.orc_patch_get(self.h, FIELD[field], out)
+        return out
+
+    def relax(self, iterations):
+        self.L.orc_patch_relax(self.h, iterations)
+
+    def gsrb_color(self, which):
+        self.L.orc_patch_gsrb_color(self.h, which)
+
+    def restrict(self):
+        """restrictResidual(e, r) -> the residual on the patch coarsened by 2"""
+        self.L.orc_patch_restrict(self.h)
+        return self.get("TMP")
+
+    def precond(self):
+        self.L.orc_patch_precond(self.h)
+
+
+def interp_homo(dx, dx_crse, far, near):
+    return lib().orc_interp_homo(dx, dx_crse, far, near)

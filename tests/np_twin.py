@@ -8,8 +8,28 @@ Source/SetBCs.cpp:49-131 ([Chombo] DiriBC order 1 / NeumBC).  Test infrastructur
 import numpy as np
 
 
-def ghosted(phi, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), value=0.0, dx=1.0, homogeneous=True):
-    """phi with one ghost layer filled by the physical BC (0 Dirichlet: 2v - near, 1 Neumann: near + side*dx*v)."""
+def interp_homo(pa, pb, dx, dx_crse):
+    """[Chombo] INTERPHOMO: value at 2*dx of the parabola through pa (second interior cell, at 0), pb (first interior
+    cell, at dx) and zero at (3*dx + dx_crse)/2 -- same operation order as the oracle."""
+    x1 = dx
+    x2 = 0.5 * (3. * x1 + dx_crse)
+    denom = 1.0 - ((x1 + x2) / x1)
+    idenom = 1 / (denom)
+    x = 2. * x1
+    xsquared = x * x
+    m1 = 1 / (x1 * x1)
+    m2 = 1 / (x1 * (x1 - x2))
+    q1 = 1 / (x1 - x2)
+    q2 = x1 + x2
+    a = ((pb - pa) * m1 - (pb) * m2) * idenom
+    b = (pb) * q1 - a * q2
+    return a * xsquared + b * x + pa
+
+
+def ghosted(phi, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), value=0.0, dx=1.0, homogeneous=True, cf_lo=(False,) * 3,
+            cf_hi=(False,) * 3, dx_crse=None, origin=(0, 0, 0)):
+    """phi with one ghost layer filled by the physical BC (0 Dirichlet: 2v - near, 1 Neumann: near + side*dx*v) or, on
+    the coarse-fine faces of an AMR patch (cf_lo / cf_hi), by homogeneousCFInterp from the two interior cells."""
     v = 0.0 if homogeneous else value
     g = np.zeros(tuple(s + 2 for s in phi.shape))
     g[1:-1, 1:-1, 1:-1] = phi
@@ -21,8 +41,17 @@ def ghosted(phi, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), value=0.0, dx=1.0, homogeneou
         nhi = [slice(1, -1)] * 3
         lo[ax], nlo[ax] = 0, 1
         hi[ax], nhi[ax] = -1, -2
-        g[tuple(lo)] = (2 * v - g[tuple(nlo)]) if bc_lo[d] == 0 else (g[tuple(nlo)] + (-1) * dx * v)
-        g[tuple(hi)] = (2 * v - g[tuple(nhi)]) if bc_hi[d] == 0 else (g[tuple(nhi)] + (+1) * dx * v)
+        flo = [slice(1, -1)] * 3
+        fhi = [slice(1, -1)] * 3
+        flo[ax], fhi[ax] = 2, -3
+        if cf_lo[d]:
+            g[tuple(lo)] = interp_homo(g[tuple(flo)], g[tuple(nlo)], dx, dx_crse)
+        else:
+            g[tuple(lo)] = (2 * v - g[tuple(nlo)]) if bc_lo[d] == 0 else (g[tuple(nlo)] + (-1) * dx * v)
+        if cf_hi[d]:
+            g[tuple(hi)] = interp_homo(g[tuple(fhi)], g[tuple(nhi)], dx, dx_crse)
+        else:
+            g[tuple(hi)] = (2 * v - g[tuple(nhi)]) if bc_hi[d] == 0 else (g[tuple(nhi)] + (+1) * dx * v)
     return g
 
 
@@ -39,6 +68,7 @@ def colour_mask(shape, red_black):
 
 
 def gsrb_colour(phi, rhs, a, b, lam, alpha, beta, dx, red_black, **bc):
+    red_black = red_black + sum(bc.get("origin", (0, 0, 0)))   # colouring by GLOBAL index
     g = ghosted(phi, dx=dx, homogeneous=True, **bc)
     dxinv = 1.0 / (dx * dx)
     lof = alpha * a * phi

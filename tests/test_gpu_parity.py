@@ -478,3 +478,54 @@ def test_prefetch_writeback_overlap_streams(ctx):
     ctx.sync()   # drains the transfer streams too
     for i in range(steps):
         assert np.array_equal(out_host[i].numpy(), want[i]), i
+
+
+PATCHES = {
+    "interior": dict(n=(32, 32, 32), lo=(8, 8, 8), hi=(23, 23, 23), bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+    "on_faces": dict(n=(32, 32, 48), lo=(0, 8, 16), hi=(15, 31, 47), bc_lo=(1, 0, 0), bc_hi=(0, 1, 0)),
+    "slab": dict(n=(40, 24, 24), lo=(10, 0, 4), hi=(25, 7, 19), bc_lo=(0, 1, 0), bc_hi=(0, 0, 0)),
+    "c4_level2": dict(n=(128, 128, 128), lo=(32, 48, 48), hi=(95, 79, 79), bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PATCHES))
+@pytest.mark.parametrize("with_b", [False, True])
+def test_amr_patch_level_homogeneous_cf(ctx, name, with_b):
+    """One box of an AMR level > 0 (first half): levelGSRB colour passes, relax, preCond and
+    restrictResidual with [Chombo] homogeneousCFInterp at the coarse-fine faces (VariableCoeffPoissonOperator.cpp:156,296)
+    -- bit-exact against the boxed oracle, whose explicit ghost fill + exchange + BC per pass the kernels fold into the
+    stencil.  residual / applyOp need QuadCFInterp (not built) and say so."""
+    from oracle import OraclePatch
+    c = PATCHES[name]
+    dx = 0.25
+    P = OraclePatch(c["n"], c["lo"], c["hi"], dx, max_grid_size=8, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"])
+    rng = np.random.default_rng(6)
+    e0, r = rng.standard_normal(P.shape), rng.standard_normal(P.shape)
+    a = 0.1 * rng.standard_normal(P.shape) - 0.5
+    b = 1 + 0.1 * rng.standard_normal(P.shape) if with_b else np.ones(P.shape)
+    for f, x in (("E", e0), ("R", r), ("A", a), ("B", b)):
+        P.set(f, x)
+    op = m.VariableCoeffPoissonOperator.patch(ctx, c["n"], c["lo"], c["hi"], dx, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"])
+    cop = m.VariableCoeffPoissonOperator(ctx, tuple(s // 2 for s in P.shape[::-1]), 2 * dx)   # holds the coarsened-patch field
+    A, B, E, R, RC = op.create(), op.create(), op.create(), op.create(), cop.create()
+    A.upload(a); B.upload(b); R.upload(r); E.upload(e0)
+    op.setCoefs(A, B if with_b else None, 1.0, -1.0)
+    assert np.array_equal(op.lambda_field().download(), P.get("LAMBDA"))
+    for _ in range(2):
+        for colour in (0, 1):
+            P.gsrb_color(colour)
+            op.gsrb_color(E, R, colour)
+            assert np.array_equal(E.download(), P.get("E")), colour
+    P.relax(3); op.relax(E, R, 3)
+    assert np.array_equal(E.download(), P.get("E"))
+    op.restrictResidual(RC, E, R)
+    assert np.array_equal(RC.download(), P.restrict())
+    P.precond(); op.preCond(E, R)
+    assert np.array_equal(E.download(), P.get("E"))
+    with pytest.raises(m.MgicError, match="QuadCFInterp"):
+        op.residual(A, E, R, True)
+    with pytest.raises(m.MgicError, match="QuadCFInterp"):
+        op.applyOp(A, E, True)
+    for x in (A, B, E, R, RC):
+        x.close()
+    op.close(); cop.close()

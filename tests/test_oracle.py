@@ -181,3 +181,54 @@ def test_golden_solver(name, cycles, over):
     assert len(nl) == len(g["nl_dpsi_norms"])
     assert np.allclose(nl[:2], g["nl_dpsi_norms"][:2], rtol=1e-8)
     assert nl[-1] < o2.params["tolerance"]
+
+
+# ---- AMR level > 0: the operator's own coarse-fine code (homogeneousCFInterp, Operator.cpp:156,296) ----------------------
+PATCHES = {
+    "interior": dict(n=(32, 32, 32), lo=(8, 8, 8), hi=(23, 23, 23), bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+    "on_faces": dict(n=(32, 32, 48), lo=(0, 8, 16), hi=(15, 31, 47), bc_lo=(1, 0, 0), bc_hi=(0, 1, 0)),
+    "slab": dict(n=(40, 24, 24), lo=(10, 0, 4), hi=(25, 7, 19), bc_lo=(0, 1, 0), bc_hi=(0, 0, 0)),
+}
+
+
+def test_homogeneous_cf_interp_is_the_parabola_with_a_zero_coarse_value():
+    """ghost = 2/3 near - 1/5 far at refinement ratio 2 ([Chombo] INTERPHOMO restated); exact for any parabola that
+    vanishes at the coarse cell centre."""
+    from oracle import interp_homo
+    for dx in (0.1, 0.390625, 1.0):
+        assert abs(interp_homo(dx, 2 * dx, 0.0, 1.0) - 2.0 / 3.0) < 4e-15
+        assert abs(interp_homo(dx, 2 * dx, 1.0, 0.0) + 1.0 / 5.0) < 4e-15
+        # far cell at 0, near at dx, ghost at 2dx, coarse centre at 2.5dx
+        q = lambda t: (t - 2.5 * dx) * (0.3 * t + 1.7)
+        assert abs(interp_homo(dx, 2 * dx, q(0.0), q(dx)) - q(2 * dx)) < 1e-13 * (1 + abs(q(2 * dx)))
+
+
+@pytest.mark.parametrize("name", sorted(PATCHES))
+@pytest.mark.parametrize("mgs", [8, 16])
+def test_patch_level_matches_numpy_twin(name, mgs):
+    """One AMR patch: the boxed oracle (explicit homogeneousCFInterp ghost fill, then exchange, then BC, per colour pass)
+    equals the single-array twin that evaluates the same ghost values on the fly -- bit for bit, for any box size,
+    with physical and coarse-fine faces mixed."""
+    from oracle import OraclePatch
+    c = PATCHES[name]
+    dx = 0.5
+    P = OraclePatch(c["n"], c["lo"], c["hi"], dx, max_grid_size=mgs, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"])
+    rng = np.random.default_rng(4)
+    e, r = rng.standard_normal(P.shape), rng.standard_normal(P.shape)
+    a, b = 0.1 * rng.standard_normal(P.shape) - 0.5, 1 + 0.1 * rng.standard_normal(P.shape)
+    for f, x in (("E", e), ("R", r), ("A", a), ("B", b)):
+        P.set(f, x)
+    kw = dict(bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], cf_lo=tuple(c["lo"][d] > 0 for d in range(3)),
+              cf_hi=tuple(c["hi"][d] < c["n"][d] - 1 for d in range(3)), dx_crse=2 * dx)
+    lam = T.compute_lambda(a, 1.0, -1.0, dx)
+    assert np.array_equal(lam, P.get("LAMBDA"))
+    t = e.copy()
+    for _ in range(2):
+        for colour in (0, 1):
+            P.gsrb_color(colour)
+            t = T.gsrb_colour(t, r, a, b, lam, 1.0, -1.0, dx, colour, origin=c["lo"], **kw)
+            assert np.array_equal(t, P.get("E"))
+    assert np.array_equal(P.restrict(), T.restrict_residual(t, r, a, b, 1.0, -1.0, dx, **kw))
+    P.set("E", e)
+    P.precond()
+    assert np.array_equal(P.get("E"), T.relax(r * lam, r, a, b, lam, 1.0, -1.0, dx, 2, origin=c["lo"], **kw))
