@@ -123,11 +123,23 @@ int mgic_op_create(mgic_ctx *, const int n[3], int k0, int nz_local, double dx, 
  * [Chombo] AMRPoissonOp::homogeneousCFInterp before each colour pass of levelGSRB
  * (Source/VariableCoeffPoissonOperator.cpp:296) and before restrictResidual (:156): the ghost value is the parabola
  * through the two interior cells and a ZERO coarse value.  mgic_op_relax / _level_gsrb / _precond /
- * _restrict_residual and the vector operations work on it; mgic_op_residual / _apply need QuadCFInterp's coarse-fine
- * ghost values (inherited AMRPoissonOp::AMRResidual* / AMROperator*), which are not built: they fail with MGIC_ERR_ARG.
- * Fields of the operator are patch-shaped. */
+ * _restrict_residual and the vector operations work on it; mgic_op_residual / _apply fail with MGIC_ERR_ARG: on a
+ * patch the coarse-fine ghost values come from the coarser level (next two functions).  Fields are patch-shaped. */
 int mgic_op_create_patch(mgic_ctx *, const int n_domain[3], const int lo[3], const int hi[3], double dx, double dx_coarse,
                          double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
+/* [Chombo] AMRPoissonOp::AMROperatorNF / AMRResidualNF (inherited by the reference's operator, VariableCoeffPoissonOperator.H:25)
+ * on a patch that has a coarser but no finer level: QuadCFInterp::coarseFineInterp(phi, phi_coarse) -- per fine ghost cell
+ * a second-order tangential Taylor interpolation of the coarse field, then the parabola through it and the two interior
+ * fine cells -- followed by applyOpI / residualI.  phi_coarse is a field of the coarser level;
+ * coarse_lo = the index, in that level's index space, of its cell (0,0,0): {0,0,0} for a level that covers the domain,
+ * the coarser patch's lo otherwise.  It must cover the coarsened patch grown by two cells (proper nesting). */
+int mgic_op_amr_operator_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
+                            int homogeneous);
+int mgic_op_amr_residual_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
+                            const mgic_field *rhs, int homogeneous);
+/* the coarse-fine ghost values of one face (0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi) left by the last of the two
+ * calls above: x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j] */
+int mgic_op_cf_ghosts(mgic_op *patch, int face, double *host);
 int mgic_op_destroy(mgic_op *);
 /* setCoefs (VariableCoeffPoissonOperator.cpp:208-218): coefficients are SHARED (caller keeps them alive);
  * bCoef may be NULL == the constant 1 (set_b_coef, Source/SetLevelData.cpp:330-340) */

@@ -56,6 +56,8 @@ def lib():
         "mgic_ctx_profile_read_tag": [vp, C.c_int, C.POINTER(C.c_longlong), dp], "mgic_ctx_set_rank": [vp, C.c_int, C.c_int],
         "mgic_op_create": [vp, i3, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_create_patch": [vp, i3, i3, i3, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
+        "mgic_op_cf_ghosts": [vp, C.c_int, nd],
+        "mgic_op_amr_operator_nf": [vp, vp, vp, vp, i3, C.c_int], "mgic_op_amr_residual_nf": [vp, vp, vp, vp, i3, vp, C.c_int],
         "mgic_op_destroy": [vp], "mgic_op_set_coefs": [vp, vp, vp, C.c_double, C.c_double],
         "mgic_op_set_alpha_beta": [vp, C.c_double, C.c_double], "mgic_op_reset_lambda": [vp],
         "mgic_op_compute_lambda": [vp], "mgic_op_get_lambda": [vp, pvp],

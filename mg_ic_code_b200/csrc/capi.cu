@@ -178,6 +178,7 @@ BCk mgic_op::bck(bool homogeneous) const {
   if (k0 + nzl < n[2]) k.type[5] = MGIC_FACE_INTERIOR;
   if (ctx->nranks > 1 && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
   for (int q = 0; q < 7; q++) k.cf[q] = 0.0;
+  for (int f = 0; f < 6; f++) k.face[f] = nullptr;
   if (isPatch) {
     // INTERPHOMO's constants, computed in its order ([Chombo] AMRPoissonOpF.ChF; oracle: Op::homogeneousCFInterp)
     const double x1 = dx;
@@ -264,6 +265,7 @@ extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const in
   for (int d = 0; d < 3; d++) {
     o->cfLo[d] = lo[d] > 0;
     o->cfHi[d] = hi[d] < n_domain[d] - 1;
+    o->plo[d] = lo[d]; o->ndom[d] = n_domain[d];
   }
   return MGIC_OK;
 }
@@ -272,6 +274,7 @@ extern "C" int mgic_op_destroy(mgic_op *o) {
   if (!o) return MGIC_OK;
   mgic_field_destroy(o->lambda);
   mgic_field_destroy(o->scratch);
+  for (int f = 0; f < 6; f++) cudaFree(o->cfFace[f]);
   delete o;
   return MGIC_OK;
 }
@@ -494,7 +497,7 @@ extern "C" int mgic_op_relax(mgic_op *o, mgic_field *e, const mgic_field *r, int
 
 extern "C" int mgic_op_residual(mgic_op *o, mgic_field *lhs, mgic_field *phi, const mgic_field *rhs, int homogeneous) {
   MGIC_REQUIRE(o && lhs && phi && rhs && o->a, "NULL argument");
-  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp, which is not built; relax, restrictResidual and preCond use homogeneousCFInterp");
+  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp: use mgic_op_amr_residual_nf / mgic_op_amr_operator_nf with the coarser level's field");
   REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
   MGIC_TRY(halo(o, phi, 1));  // :48
   return mgk::residual(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, rhs->p, o->a->p, bptr(o), o->alpha, o->beta,
@@ -502,11 +505,67 @@ extern "C" int mgic_op_residual(mgic_op *o, mgic_field *lhs, mgic_field *phi, co
 }
 extern "C" int mgic_op_apply(mgic_op *o, mgic_field *lhs, mgic_field *phi, int homogeneous) {
   MGIC_REQUIRE(o && lhs && phi && o->a, "NULL argument");
-  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp, which is not built; relax, restrictResidual and preCond use homogeneousCFInterp");
+  MGIC_REQUIRE(!o->isPatch, "residual / applyOp on an AMR patch need the coarse-fine ghost values of QuadCFInterp: use mgic_op_amr_residual_nf / mgic_op_amr_operator_nf with the coarser level's field");
   REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi);
   MGIC_TRY(halo(o, phi, 1));  // :131
   return mgk::apply_op(o->ctx, o->geom(), o->bck(homogeneous != 0), lhs->p, phi->p, o->a->p, bptr(o), o->alpha, o->beta, o->dx);
 }
+// [Chombo] QuadCFInterp::coarseFineInterp(phi, phiCoarse) on an AMR patch: the ghost values of every coarse-fine face go
+// into the operator's face arrays (the fields carry no x/y ghost cells); returns the kernel-side BC table that reads them
+static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *pc, const int clo[3], bool homogeneous, BCk *out) {
+  MGIC_REQUIRE(o->isPatch, "coarse-fine interpolation needs an AMR patch operator (mgic_op_create_patch)");
+  MGIC_REQUIRE(pc && clo, "NULL argument");
+  const int n[3] = {o->n[0], o->n[1], o->n[2]};
+  const int cn[3] = {pc->nx, pc->ny, pc->nz};
+  for (int d = 0; d < 3; d++) {
+    // coarse cells the stencils can touch: the coarsened patch grown by two, inside the coarse domain
+    const int need_lo = std::max(0, (o->plo[d] >> 1) - 2), need_hi = std::min(o->ndom[d] / 2 - 1, ((o->plo[d] + n[d] - 1) >> 1) + 2);
+    MGIC_REQUIRE(clo[d] <= need_lo && clo[d] + cn[d] - 1 >= need_hi,
+                 "the coarse field does not cover the coarsened patch grown by two cells (proper nesting)");
+  }
+  BCk k = o->bck(homogeneous);
+  for (int f = 0; f < 6; f++) {
+    k.face[f] = nullptr;
+    const int dir = f / 2, side = (f % 2) ? +1 : -1;
+    if (!(side < 0 ? o->cfLo[dir] : o->cfHi[dir])) continue;
+    const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+    if (!o->cfFace[f]) MGIC_CUDA(cudaMalloc(&o->cfFace[f], (size_t)n[ta] * n[tb] * sizeof(double)));
+    MGIC_TRY(mgk::quad_cf_face(o->ctx, o->geom(), o->plo, o->ndom, o->dx, dir, side, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfFace[f]));
+    k.type[f] = MGIC_FACE_GHOST;
+    k.face[f] = o->cfFace[f];
+  }
+  *out = k;
+  return MGIC_OK;
+}
+// the ghost values QuadCFInterp left on one coarse-fine face (0 x-lo ... 5 z-hi) at the last AMROperatorNF / AMRResidualNF:
+// x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j]
+extern "C" int mgic_op_cf_ghosts(mgic_op *o, int face, double *host) {
+  MGIC_REQUIRE(o && host && face >= 0 && face < 6, "bad argument");
+  MGIC_REQUIRE(o->isPatch && o->cfFace[face], "no coarse-fine ghost values on this face yet");
+  const int dir = face / 2, ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+  MGIC_CUDA(cudaStreamSynchronize(o->ctx->stream));
+  MGIC_CUDA(cudaMemcpy(host, o->cfFace[face], (size_t)o->n[ta] * o->n[tb] * sizeof(double), cudaMemcpyDeviceToHost));
+  return MGIC_OK;
+}
+// [Chombo] AMRPoissonOp::AMROperatorNF (the level has a coarser but no finer level): coarseFineInterp, then applyOpI
+extern "C" int mgic_op_amr_operator_nf(mgic_op *o, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
+                                       int homogeneous) {
+  MGIC_REQUIRE(o && lhs && phi && o->a, "NULL argument");
+  REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi);
+  BCk k;
+  MGIC_TRY(quad_cf_interp(o, phi, phi_coarse, coarse_lo, homogeneous != 0, &k));
+  return mgk::apply_op(o->ctx, o->geom(), k, lhs->p, phi->p, o->a->p, bptr(o), o->alpha, o->beta, o->dx);
+}
+// [Chombo] AMRPoissonOp::AMRResidualNF: rhs - AMROperatorNF(phi)
+extern "C" int mgic_op_amr_residual_nf(mgic_op *o, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
+                                       const mgic_field *rhs, int homogeneous) {
+  MGIC_REQUIRE(o && lhs && phi && rhs && o->a, "NULL argument");
+  REQ_SHAPE(o, lhs); REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
+  BCk k;
+  MGIC_TRY(quad_cf_interp(o, phi, phi_coarse, coarse_lo, homogeneous != 0, &k));
+  return mgk::residual(o->ctx, o->geom(), k, lhs->p, phi->p, rhs->p, o->a->p, bptr(o), o->alpha, o->beta, o->dx);
+}
+
 // applyOpNoBoundary (:123-149): the stencil on whatever the ghost cells hold.  With ghosts folded into the
 // kernels the only ghost state a caller can have produced through this API is the last BC fill, which for
 // every call site in the reference's solver stack is the homogeneous one.

@@ -122,6 +122,92 @@ __global__ void __launch_bounds__(128) k_prolong(Geom g, double *__restrict__ ph
     }
 }
 
+// ---- [Chombo] QuadCFInterp::coarseFineInterp on one coarse-fine face of an AMR patch, ratio 2 -------------------------
+// One thread per ghost cell of the face.  phiStar = the coarse field taken to the ghost cell's tangential position by a
+// second-order Taylor expansion (centred differences, one-sided next to a domain face, mixed term dropped where a
+// diagonal coarse cell is outside the domain), then QuadCFInterpF.ChF QUADINTERP: the parabola through the two interior
+// fine cells and phiStar.  Operation order of the oracle (Op::quadCFInterp).
+struct QcfArgs {
+  Geom g;                 // the patch
+  int plo[3], cdom[3];    // patch lower corner (fine level index space), coarse domain size
+  int clo[3];             // coarse-level index of coarse[0]
+  long long csy, csz;
+  int dir, side, ta, tb;  // tangential directions ta < tb
+  double h;
+};
+__global__ void __launch_bounds__(256) k_quad_cf_face(QcfArgs A, const double *__restrict__ phi, const double *__restrict__ coarse,
+                                                      double *__restrict__ face) {
+  const int qa = blockIdx.x * blockDim.x + threadIdx.x, qb = blockIdx.y * blockDim.y + threadIdx.y;   // local tangential indices
+  // geometry per direction without dynamically indexed local arrays: (value for x, y, z) selected by compile-time-simple tests
+  const int dir = A.dir, ta = A.ta, tb = A.tb;
+  const int nA = ta == 0 ? A.g.nx : A.g.ny;                  // ta is 0 or 1
+  const int nB = tb == 1 ? A.g.ny : A.g.nz;                  // tb is 1 or 2
+  const int nD = dir == 0 ? A.g.nx : (dir == 1 ? A.g.ny : A.g.nz);
+  if (qa >= nA || qb >= nB) return;
+  const long long fsA = ta == 0 ? 1 : A.g.sy, fsB = tb == 1 ? A.g.sy : A.g.sz, fsD = dir == 0 ? 1 : (dir == 1 ? A.g.sy : A.g.sz);
+  const long long csA = ta == 0 ? 1 : A.csy, csB = tb == 1 ? A.csy : A.csz, csD = dir == 0 ? 1 : (dir == 1 ? A.csy : A.csz);
+  const int ploA = ta == 0 ? A.plo[0] : A.plo[1], ploB = tb == 1 ? A.plo[1] : A.plo[2];
+  const int ploD = dir == 0 ? A.plo[0] : (dir == 1 ? A.plo[1] : A.plo[2]);
+  const int cloA = ta == 0 ? A.clo[0] : A.clo[1], cloB = tb == 1 ? A.clo[1] : A.clo[2];
+  const int cloD = dir == 0 ? A.clo[0] : (dir == 1 ? A.clo[1] : A.clo[2]);
+  const int cdA = ta == 0 ? A.cdom[0] : A.cdom[1], cdB = tb == 1 ? A.cdom[1] : A.cdom[2];
+  const double h = A.h, H = 2.0 * A.h;
+  // the ghost cell in the level's index space and the coarse cell that contains it
+  const int fA = ploA + qa, fB = ploB + qb, fD = ploD + (A.side < 0 ? -1 : nD);
+  const int cA = fA >> 1, cB = fB >> 1, cD = fD >> 1;
+  const double *cc = coarse + ((cA - cloA) * csA + (cB - cloB) * csB + (cD - cloD) * csD);   // C(oa, ob) = cc[oa*csA + ob*csB]
+  const double c0 = cc[0];
+  double phistar = c0;
+  // tangential direction ta
+  const double xa = (fA + 0.5) * h - (cA + 0.5) * H;
+  {
+    const bool hasLo = cA - 1 >= 0, hasHi = cA + 1 <= cdA - 1;
+    double d1, d2;
+    if (hasLo && hasHi) {
+      d1 = (cc[csA] - cc[-csA]) / (2.0 * H);
+      d2 = ((cc[csA] - 2.0 * c0) + cc[-csA]) / (H * H);
+    } else if (hasHi) {
+      d1 = ((4.0 * cc[csA] - 3.0 * c0) - cc[2 * csA]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[csA]) + cc[2 * csA]) / (H * H);
+    } else {
+      d1 = ((3.0 * c0 - 4.0 * cc[-csA]) + cc[-2 * csA]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[-csA]) + cc[-2 * csA]) / (H * H);
+    }
+    phistar = phistar + (d1 * xa + 0.5 * d2 * xa * xa);
+  }
+  // tangential direction tb
+  const double xb = (fB + 0.5) * h - (cB + 0.5) * H;
+  {
+    const bool hasLo = cB - 1 >= 0, hasHi = cB + 1 <= cdB - 1;
+    double d1, d2;
+    if (hasLo && hasHi) {
+      d1 = (cc[csB] - cc[-csB]) / (2.0 * H);
+      d2 = ((cc[csB] - 2.0 * c0) + cc[-csB]) / (H * H);
+    } else if (hasHi) {
+      d1 = ((4.0 * cc[csB] - 3.0 * c0) - cc[2 * csB]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[csB]) + cc[2 * csB]) / (H * H);
+    } else {
+      d1 = ((3.0 * c0 - 4.0 * cc[-csB]) + cc[-2 * csB]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[-csB]) + cc[-2 * csB]) / (H * H);
+    }
+    phistar = phistar + (d1 * xb + 0.5 * d2 * xb * xb);
+  }
+  const bool corners = cA - 1 >= 0 && cA + 1 <= cdA - 1 && cB - 1 >= 0 && cB + 1 <= cdB - 1;
+  if (corners) {
+    const double mixed = (((cc[csA + csB] - cc[csA - csB]) - cc[-csA + csB]) + cc[-csA - csB]) / (4.0 * H * H);
+    phistar = phistar + mixed * xa * xb;
+  }
+  // QUADINTERP along the normal: pb = first interior cell, pa = second
+  const long long nearIdx = qa * fsA + qb * fsB + (A.side < 0 ? 0 : (long long)(nD - 1) * fsD);
+  const long long inward = A.side < 0 ? fsD : -fsD;
+  const double pb = phi[nearIdx], pa = phi[nearIdx + inward];
+  const double x = 2.0 * h;
+  const double nref = 2.0;
+  const double a = (2.0 / h / h) * ((2.0 * phistar + pa * (nref + 1.0)) - pb * (nref + 3.0)) / (nref * nref + 4.0 * nref + 3.0);
+  const double b = (pb - pa) / h - a * h;
+  face[qa + (long long)nA * qb] = (pa + b * x) + a * x * x;
+}
+
 // ---- lambda: resetLambda (VariableCoeffPoissonOperator.cpp:220-249) ------------------------------------------
 __global__ void k_lambda(long long n, double *__restrict__ lam, const double *__restrict__ a, double alpha, double plus) {
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
@@ -275,6 +361,22 @@ int restrict_res(mgic_ctx *c, const Geom &g, const BCk &bc, double *resC, long l
   if (b) k_restrict<true><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
   else k_restrict<false><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
   return post_launch(c, "restrict");
+}
+
+int quad_cf_face(mgic_ctx *c, const Geom &g, const int plo[3], const int ndom[3], double h, int dir, int side, const double *phi,
+                 const double *coarse, long long csy, long long csz, const int clo[3], double *face) {
+  QcfArgs A;
+  A.g = g;
+  for (int d = 0; d < 3; d++) { A.plo[d] = plo[d]; A.cdom[d] = ndom[d] / 2; A.clo[d] = clo[d]; }
+  A.csy = csy; A.csz = csz;
+  A.dir = dir; A.side = side;
+  A.ta = dir == 0 ? 1 : 0; A.tb = dir == 2 ? 1 : 2;
+  A.h = h;
+  const int n[3] = {g.nx, g.ny, g.nz};
+  dim3 blk(32, 8, 1);
+  dim3 grd((n[A.ta] + blk.x - 1) / blk.x, (n[A.tb] + blk.y - 1) / blk.y, 1);
+  k_quad_cf_face<<<grd, blk, 0, c->stream>>>(A, phi, coarse, face);
+  return post_launch(c, "quad_cf_face");
 }
 
 int prolong(mgic_ctx *c, const Geom &g, double *phi, const double *coarse, long long csy, long long csz) {

@@ -35,23 +35,27 @@ __device__ __forceinline__ double cf_homog(const double *cf, double pa, double p
   return a * cf[6] + b * cf[5] + pa;
 }
 
-__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *p, long long wrapIdx, long long farIdx) {
+__device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const double *p, long long wrapIdx, long long farIdx,
+                                        int faceIdx) {
   // Dirichlet / Neumann: a*c + b  (DiriBC order 1: 2v - near;  NeumBC: near + sign*dx*v  [Chombo BCFunc])
   if (bc.type[f] == MGIC_BC_PERIODIC) return p[wrapIdx];
   if (bc.type[f] == MGIC_FACE_CF) return cf_homog(bc.cf, p[farIdx], c);
+  if (bc.type[f] == MGIC_FACE_GHOST) return bc.face[f][faceIdx];
   return bc.a[f] * c + bc.b[f];
 }
 
 __device__ __forceinline__ Nb neighbours(const double *p, long long idx, int i, int j, int k, const Geom &g,
                                          const BCk &bc, double c) {
   Nb n;
-  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1), idx + 1);
-  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1), idx - 1);
-  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy, idx + g.sy);
-  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy, idx - g.sy);
+  n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1), idx + 1, j + g.ny * k);
+  n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1), idx - 1, j + g.ny * k);
+  n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy, idx + g.sy, i + g.nx * k);
+  n.yp = (j < g.ny - 1) ? p[idx + g.sy] : ghost(bc, 3, c, p, idx - (long long)(g.ny - 1) * g.sy, idx - g.sy, i + g.nx * k);
   // z: ghost planes exist in memory; MGIC_FACE_INTERIOR means they hold the neighbour slab's planes
-  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz] : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz, idx + g.sz);
-  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz] : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz, idx - g.sz);
+  n.zm = (k > 0 || bc.type[4] == MGIC_FACE_INTERIOR) ? p[idx - g.sz]
+                                                    : ghost(bc, 4, c, p, idx + (long long)(g.nz - 1) * g.sz, idx + g.sz, i + g.nx * j);
+  n.zp = (k < g.nz - 1 || bc.type[5] == MGIC_FACE_INTERIOR) ? p[idx + g.sz]
+                                                           : ghost(bc, 5, c, p, idx - (long long)(g.nz - 1) * g.sz, idx - g.sz, i + g.nx * j);
   return n;
 }
 

@@ -42,10 +42,14 @@ void mgic_set_error(const char *fmt, ...);
 // parabola through the two interior cells and a zero coarse value -- a function of the current field like the physical
 // ghosts, so it is evaluated in the stencil too (cf[] = m1, m2, idenom, q1, q2, x, x*x of INTERPHOMO)
 #define MGIC_FACE_CF 4
+// 5 coarse-fine interface with STORED ghost values ([Chombo] QuadCFInterp::coarseFineInterp: they depend on the coarser
+// level's field): face[f] is a 2-D array over the face, x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j]
+#define MGIC_FACE_GHOST 5
 struct BCk {
   int type[6];
   double a[6], b[6];  // ghost = a*centre + b   (Dirichlet: a=-1, b=2v; Neumann: a=+1, b=sign*dx*v)
   double cf[7];
+  const double *face[6];
 };
 
 struct Geom {
@@ -146,6 +150,8 @@ struct mgic_op {
   bool isPatch = false, cfLo[3] = {false, false, false}, cfHi[3] = {false, false, false};
   int cshift = 0;
   double dxCrse = 0;
+  int plo[3] = {0, 0, 0}, ndom[3] = {0, 0, 0};   // the patch's lower corner and the level's domain size
+  double *cfFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // QuadCFInterp ghost values per coarse-fine face
   bool isGlobal = false;                  // whole-domain operator on a multi-rank context (agglomerated level): no halos
   bool profTag = true;                    // finest-level operator: its GSRB launches are the profiled kernel
   int smoother = 1;                       // 0: one launch per colour; 1: fused red+black plane-streaming sweep
@@ -186,6 +192,9 @@ int set_val(mgic_ctx *, const Geom &, double *y, double v);
 int jacobi_update(mgic_ctx *, const Geom &, double *phi, const double *res, const double *lam, double w);
 // reductions: result left in ctx->d_scal[slot]; kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y
 int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot);
+// QuadCFInterp on one coarse-fine face (dir, side) of a patch: ghost values into `face`
+int quad_cf_face(mgic_ctx *, const Geom &g, const int plo[3], const int ndom[3], double h, int dir, int side, const double *phi,
+                 const double *coarse, long long csy, long long csz, const int clo[3], double *face);
 int coarse_average(mgic_ctx *, const Geom &coarse, double *c, const double *fine, long long fsy, long long fsz, int nref,
                    int harmonic);
 int is_constant(mgic_ctx *, const Geom &, const double *x, double value, int slot);  // d_scal[slot] = #cells != value

@@ -198,6 +198,21 @@ class VariableCoeffPoissonOperator:
     def applyOpNoBoundary(self, lhs, phi):
         check(self.L.mgic_op_apply_no_boundary(self.h, lhs.h, phi.h))
 
+    # [Chombo] AMRPoissonOp::AMROperatorNF / AMRResidualNF on a patch (QuadCFInterp from the coarser level's field)
+    def AMROperatorNF(self, lhs, phi, phiCoarse, coarse_lo=(0, 0, 0), homogeneous=False):
+        check(self.L.mgic_op_amr_operator_nf(self.h, lhs.h, phi.h, phiCoarse.h, (C.c_int * 3)(*coarse_lo), int(homogeneous)))
+
+    def AMRResidualNF(self, lhs, phi, phiCoarse, rhs, coarse_lo=(0, 0, 0), homogeneous=False):
+        check(self.L.mgic_op_amr_residual_nf(self.h, lhs.h, phi.h, phiCoarse.h, (C.c_int * 3)(*coarse_lo), rhs.h, int(homogeneous)))
+
+    def cf_ghosts(self, face):
+        """QuadCFInterp's ghost values on one coarse-fine face (2-D array, slow axis first) after AMROperatorNF / AMRResidualNF"""
+        d = face // 2
+        ta, tb = (1, 2) if d == 0 else ((0, 2) if d == 1 else (0, 1))
+        out = np.empty((self.n[tb], self.n[ta]))
+        check(self.L.mgic_op_cf_ghosts(self.h, face, out))
+        return out
+
     def restrictResidual(self, resCoarse, phiFine, rhsFine):
         check(self.L.mgic_op_restrict_residual(self.h, resCoarse.h, phiFine.h, rhsFine.h))
 

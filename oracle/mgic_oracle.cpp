@@ -448,6 +448,87 @@ struct Op {
     for (int n = 0; n < x.size(); n++) ParseBC(x.fab[n], lay.boxes[n], lay.domain, lay.periodic, bc, dx, homog);
   }
 
+  // [Chombo] QuadCFInterp::coarseFineInterp(phiFine, phiCoarse), ratio 2 (restated from the published algorithm, SURVEY
+  // App. B.10; Chombo is not vendored): every face ghost cell on a coarse-fine interface gets the value at x = 2h of the
+  // parabola through the second interior cell (0), the first interior cell (h) and phiStar at the coarse cell centre
+  // h(nref+3)/2 (QuadCFInterpF.ChF QUADINTERP).  phiStar = the coarse field taken to the ghost cell's tangential position
+  // by a second-order Taylor expansion: centred first and second differences (one-sided second-order ones next to a
+  // domain face) in each tangential direction, plus the mixed term from the four diagonal coarse cells (dropped where one
+  // of them is outside the domain).  `crse` holds the coarse level on `cdom` (its valid cells; copyTo of Chombo).
+  // As with homogeneousCFInterp every face ghost cell inside the domain is filled; the exchange of the caller
+  // (applyOpI / residualI :131 / :48) overwrites those that a neighbouring box covers.
+  void quadCFInterp(LevelData &phi, const FAB &crse, const Box &cdom) {
+    const int nref = 2;
+    const Real h = dx, H = dxCrse;
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < phi.size(); n++) {
+      FAB &f = phi.fab[n];
+      for (int dir = 0; dir < 3; dir++)
+        for (int side = -1; side <= 1; side += 2) {
+          const Box region = adjCellBox(lay.boxes[n], dir, side, 1) & lay.domain & f.b;
+          if (region.empty()) continue;
+          int ii[3] = {0, 0, 0}; ii[dir] = side;
+          const int t1 = (dir + 1) % 3, t2 = (dir + 2) % 3;
+          const int ta = std::min(t1, t2), tb = std::max(t1, t2);   // tangential directions in ascending order
+          for (int k = region.lo[2]; k <= region.hi[2]; k++)
+            for (int j = region.lo[1]; j <= region.hi[1]; j++)
+              for (int i = region.lo[0]; i <= region.hi[0]; i++) {
+                const int ivf[3] = {i, j, k};
+                int ivc[3]; for (int d = 0; d < 3; d++) ivc[d] = coarsen1(ivf[d], nref);
+                auto C = [&](int o_a, int o_b) -> Real {
+                  int q[3] = {ivc[0], ivc[1], ivc[2]}; q[ta] += o_a; q[tb] += o_b;
+                  return crse(q[0], q[1], q[2]);
+                };
+                const Real c0 = C(0, 0);
+                Real phistar = c0;
+                Real xt[2];
+                for (int w = 0; w < 2; w++) {
+                  const int t = w ? tb : ta;
+                  const Real x = (ivf[t] + 0.5) * h - (ivc[t] + 0.5) * H;
+                  xt[w] = x;
+                  const bool hasLo = ivc[t] - 1 >= cdom.lo[t], hasHi = ivc[t] + 1 <= cdom.hi[t];
+                  auto Ct = [&](int o) { return w ? C(0, o) : C(o, 0); };
+                  Real d1, d2;
+                  if (hasLo && hasHi) {
+                    d1 = (Ct(1) - Ct(-1)) / (2.0 * H);
+                    d2 = ((Ct(1) - 2.0 * c0) + Ct(-1)) / (H * H);
+                  } else if (hasHi) {
+                    d1 = ((4.0 * Ct(1) - 3.0 * c0) - Ct(2)) / (2.0 * H);
+                    d2 = ((c0 - 2.0 * Ct(1)) + Ct(2)) / (H * H);
+                  } else {
+                    d1 = ((3.0 * c0 - 4.0 * Ct(-1)) + Ct(-2)) / (2.0 * H);
+                    d2 = ((c0 - 2.0 * Ct(-1)) + Ct(-2)) / (H * H);
+                  }
+                  phistar = phistar + (d1 * x + 0.5 * d2 * x * x);
+                }
+                const bool corners = ivc[ta] - 1 >= cdom.lo[ta] && ivc[ta] + 1 <= cdom.hi[ta] && ivc[tb] - 1 >= cdom.lo[tb] &&
+                                     ivc[tb] + 1 <= cdom.hi[tb];
+                if (corners) {
+                  const Real mixed = (((C(1, 1) - C(1, -1)) - C(-1, 1)) + C(-1, -1)) / (4.0 * H * H);
+                  phistar = phistar + mixed * xt[0] * xt[1];
+                }
+                // QUADINTERP
+                const Real x = 2.0 * h;
+                const Real pa = f(i - 2 * ii[0], j - 2 * ii[1], k - 2 * ii[2]);
+                const Real pb = f(i - ii[0], j - ii[1], k - ii[2]);
+                const Real a = (2.0 / h / h) * ((2.0 * phistar + pa * (nref + 1.0)) - pb * (nref + 3.0)) / (nref * nref + 4.0 * nref + 3.0);
+                const Real b = (pb - pa) / h - a * h;
+                f(i, j, k) = (pa + b * x) + a * x * x;
+              }
+        }
+    }
+  }
+  // [Chombo] AMRPoissonOp::AMROperatorNF / AMRResidualNF on the finest level: coarse-fine interpolation from the coarser
+  // level's field, then the level operator (applyOpI / residualI of the reference)
+  void amrOperatorNF(LevelData &lhs, LevelData &phi, const FAB &crse, const Box &cdom, bool homogPhysBC) {
+    quadCFInterp(phi, crse, cdom);
+    applyOp(lhs, phi, homogPhysBC);
+  }
+  void amrResidualNF(LevelData &lhs, LevelData &phi, const FAB &crse, const Box &cdom, const LevelData &rhs, bool homogPhysBC) {
+    quadCFInterp(phi, crse, cdom);
+    residual(lhs, phi, rhs, homogPhysBC);
+  }
+
   // levelGSRB -- VariableCoeffPoissonOperator.cpp:273-332
   void gsrbColor(LevelData &dpsi, const LevelData &rhs, int whichPass) {
     homogeneousCFInterp(dpsi);                                         // :296 (no-op without a coarser AMR level)
@@ -1180,9 +1261,10 @@ double orc_op_dot(orc_problem *pb, int d, int f1, int f2) { return pb->ops[d]->d
 // homogeneousCFInterp (VariableCoeffPoissonOperator.cpp:156,296).  Fields are patch-shaped arrays, x fastest.
 struct orc_patch {
   Op op;
-  LevelData e, r, a, b, rc;   // correction (1 ghost), residual, coefficients, MG-coarsened residual
+  LevelData e, r, a, b, rc, lof;   // correction (1 ghost), residual, coefficients, MG-coarsened residual, operator output
   Layout clay;
   Box box;
+  FAB crse; Box cdom;              // the coarser AMR level's field on its whole domain (QuadCFInterp input)
 };
 
 orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi[3], int max_grid_size, double dx, double dx_crse,
@@ -1207,6 +1289,9 @@ orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi
   pp->clay.domain = op.lay.domain.coarsened(2);
   for (auto &bx : op.lay.boxes) pp->clay.boxes.push_back(bx.coarsened(2));
   pp->rc.define(&pp->clay, 1, 0);
+  pp->lof.define(&op.lay, 1, 0);
+  pp->cdom = op.lay.domain.coarsened(2);
+  pp->crse.define(pp->cdom, 1);
   return pp;
 }
 void orc_patch_destroy(orc_patch *pp) { delete pp; }
@@ -1219,6 +1304,7 @@ static LevelData *patchField(orc_patch *pp, int field) {
     case ORC_F_B: return &pp->b;
     case ORC_F_TMP: return &pp->rc;
     case ORC_F_LAMBDA: return &pp->op.lambda;
+    case ORC_F_RHS: return &pp->lof;
   }
   fprintf(stderr, "orc_patch: bad field %d\n", field); abort();
 }
@@ -1252,6 +1338,11 @@ void orc_patch_relax(orc_patch *pp, int iterations) { pp->op.relax(pp->e, pp->r,
 void orc_patch_gsrb_color(orc_patch *pp, int whichPass) { pp->op.resetLambda(); pp->op.gsrbColor(pp->e, pp->r, whichPass); }
 void orc_patch_restrict(orc_patch *pp) { pp->op.restrictResidual(pp->rc, pp->e, pp->r); }
 void orc_patch_precond(orc_patch *pp) { pp->op.preCond(pp->e, pp->r); }
+// the coarser AMR level's field: an array over its whole domain (n_domain / 2), x fastest
+void orc_patch_set_coarse(orc_patch *pp, const double *in) { std::copy(in, in + pp->crse.d.size(), pp->crse.d.begin()); }
+// AMROperatorNF / AMRResidualNF: lof (read back as ORC_F_RHS) = L(e) resp. r - L(e), coarse-fine ghosts by QuadCFInterp
+void orc_patch_amr_operator_nf(orc_patch *pp, int homog) { pp->op.amrOperatorNF(pp->lof, pp->e, pp->crse, pp->cdom, homog != 0); }
+void orc_patch_amr_residual_nf(orc_patch *pp, int homog) { pp->op.amrResidualNF(pp->lof, pp->e, pp->crse, pp->cdom, pp->r, homog != 0); }
 // the ghost value homogeneousCFInterp produces from the two interior cells (far, near) -- the coefficients' pin
 double orc_interp_homo(double dx, double dx_crse, double far_value, double near_value) {
   Op op; op.dx = dx; op.dxCrse = dx_crse; op.hasCoarser = true;

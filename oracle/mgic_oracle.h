@@ -152,6 +152,11 @@ void orc_patch_relax(orc_patch *, int iterations);
 void orc_patch_gsrb_color(orc_patch *, int whichPass);
 void orc_patch_restrict(orc_patch *);
 void orc_patch_precond(orc_patch *);
+/* [Chombo] QuadCFInterp + AMRPoissonOp::AMROperatorNF / AMRResidualNF: the coarser level's field over its whole domain
+ * (n_domain / 2); the result is read back as field ORC_F_RHS */
+void orc_patch_set_coarse(orc_patch *, const double *in);
+void orc_patch_amr_operator_nf(orc_patch *, int homogeneous_phys_bc);
+void orc_patch_amr_residual_nf(orc_patch *, int homogeneous_phys_bc);
 double orc_interp_homo(double dx, double dx_crse, double far_value, double near_value);
 
 #ifdef __cplusplus

@@ -118,6 +118,9 @@ def lib():
         L.orc_patch_gsrb_color.argtypes = [C.c_void_p, C.c_int]
         L.orc_patch_restrict.argtypes = [C.c_void_p]
         L.orc_patch_precond.argtypes = [C.c_void_p]
+        L.orc_patch_set_coarse.argtypes = [C.c_void_p, dp]
+        L.orc_patch_amr_operator_nf.argtypes = [C.c_void_p, C.c_int]
+        L.orc_patch_amr_residual_nf.argtypes = [C.c_void_p, C.c_int]
         L.orc_interp_homo.argtypes = [C.c_double] * 4
         L.orc_interp_homo.restype = C.c_double
         _lib = L
@@ -296,6 +299,19 @@ class OraclePatch:
 
     def precond(self):
         self.L.orc_patch_precond(self.h)
+
+    def set_coarse(self, arr):
+        """the coarser AMR level's field over its whole domain, [k, j, i], shape n_domain / 2"""
+        self.L.orc_patch_set_coarse(self.h, np.ascontiguousarray(arr, dtype=np.float64))
+
+    def amr_operator_nf(self, homogeneous=True):
+        """[Chombo] AMROperatorNF: QuadCFInterp from the coarse field, then applyOp"""
+        self.L.orc_patch_amr_operator_nf(self.h, int(homogeneous))
+        return self.get("RHS")
+
+    def amr_residual_nf(self, homogeneous=True):
+        self.L.orc_patch_amr_residual_nf(self.h, int(homogeneous))
+        return self.get("RHS")
 
 
 def interp_homo(dx, dx_crse, far, near):

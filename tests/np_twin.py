@@ -129,3 +129,83 @@ def coarse_average(f, nref, harmonic):
                 s = s + (1.0 / fv if harmonic else fv)
     scale = 1.0 / float(nref ** 3)
     return 1.0 / (s * scale) if harmonic else s * scale
+
+
+def quad_cf_face(phi, coarse, lo, hi, n_domain, dx, d, side):
+    """[Chombo] QuadCFInterp on one coarse-fine face (direction d, side -1/+1) of the patch [lo, hi]: the ghost values as a
+    2-D array indexed [tb, ta] (tangential directions ta < tb).  Same operation order as the oracle's Op::quadCFInterp."""
+    nref = 2
+    h, H = dx, 2.0 * dx
+    ta, tb = sorted(t for t in range(3) if t != d)
+    gi = lo[d] - 1 if side < 0 else hi[d] + 1
+    fa = np.arange(lo[ta], hi[ta] + 1)[None, :]
+    fb = np.arange(lo[tb], hi[tb] + 1)[:, None]
+    ca, cb, cn = fa // nref, fb // nref, gi // nref
+    cdom = [n // nref for n in n_domain]
+
+    def C(oa, ob):
+        idx = [None, None, None]
+        idx[d] = np.full(np.broadcast(ca, cb).shape, cn)
+        idx[ta] = np.broadcast_to(np.clip(ca + oa, 0, cdom[ta] - 1), idx[d].shape)
+        idx[tb] = np.broadcast_to(np.clip(cb + ob, 0, cdom[tb] - 1), idx[d].shape)
+        return coarse[idx[2], idx[1], idx[0]]
+
+    c0 = C(0, 0)
+    phistar = c0
+    xs = []
+    for w, (t, ft, ct) in enumerate(((ta, fa, ca), (tb, fb, cb))):
+        x = (ft + 0.5) * h - (ct + 0.5) * H
+        x = np.broadcast_to(x, c0.shape)
+        xs.append(x)
+        Ct = (lambda o: C(0, o)) if w else (lambda o: C(o, 0))
+        has_lo = np.broadcast_to(ct - 1 >= 0, c0.shape)
+        has_hi = np.broadcast_to(ct + 1 <= cdom[t] - 1, c0.shape)
+        d1c = (Ct(1) - Ct(-1)) / (2.0 * H)
+        d2c = ((Ct(1) - 2.0 * c0) + Ct(-1)) / (H * H)
+        d1f = ((4.0 * Ct(1) - 3.0 * c0) - Ct(2)) / (2.0 * H)
+        d2f = ((c0 - 2.0 * Ct(1)) + Ct(2)) / (H * H)
+        d1b = ((3.0 * c0 - 4.0 * Ct(-1)) + Ct(-2)) / (2.0 * H)
+        d2b = ((c0 - 2.0 * Ct(-1)) + Ct(-2)) / (H * H)
+        d1 = np.where(has_lo & has_hi, d1c, np.where(has_hi, d1f, d1b))
+        d2 = np.where(has_lo & has_hi, d2c, np.where(has_hi, d2f, d2b))
+        phistar = phistar + (d1 * x + 0.5 * d2 * x * x)
+    corners = np.broadcast_to((ca - 1 >= 0) & (ca + 1 <= cdom[ta] - 1) & (cb - 1 >= 0) & (cb + 1 <= cdom[tb] - 1), c0.shape)
+    mixed = (((C(1, 1) - C(1, -1)) - C(-1, 1)) + C(-1, -1)) / (4.0 * H * H)
+    phistar = np.where(corners, phistar + mixed * xs[0] * xs[1], phistar)
+    # the two interior cells along the normal
+    sl_near, sl_far = [slice(None)] * 3, [slice(None)] * 3
+    ax = 2 - d
+    sl_near[ax] = 0 if side < 0 else -1
+    sl_far[ax] = 1 if side < 0 else -2
+    pb, pa = phi[tuple(sl_near)], phi[tuple(sl_far)]    # 2-D, indexed by the remaining axes in [k, j, i] order = [tb, ta]
+    x = 2.0 * h
+    a = (2.0 / h / h) * ((2.0 * phistar + pa * (nref + 1.0)) - pb * (nref + 3.0)) / (nref * nref + 4.0 * nref + 3.0)
+    b = (pb - pa) / h - a * h
+    return (pa + b * x) + a * x * x
+
+
+def ghosted_amr(phi, coarse, lo, hi, n_domain, dx, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), value=0.0, homogeneous=True):
+    """phi of the patch [lo, hi] with one ghost layer: QuadCFInterp from `coarse` on the coarse-fine faces, the physical
+    BC on domain faces (what AMROperatorNF hands to applyOpI)."""
+    g = ghosted(phi, bc_lo=bc_lo, bc_hi=bc_hi, value=value, dx=dx, homogeneous=homogeneous)
+    for d in range(3):
+        ax = 2 - d
+        for side, is_cf in ((-1, lo[d] > 0), (+1, hi[d] < n_domain[d] - 1)):
+            if not is_cf:
+                continue
+            sl = [slice(1, -1)] * 3
+            sl[ax] = 0 if side < 0 else -1
+            g[tuple(sl)] = quad_cf_face(phi, coarse, lo, hi, n_domain, dx, d, side)
+    return g
+
+
+def amr_operator_nf(phi, coarse, a, b, alpha, beta, dx, lo, hi, n_domain, homogeneous=True, value=0.0, **bc):
+    g = ghosted_amr(phi, coarse, lo, hi, n_domain, dx, homogeneous=homogeneous, value=value, **bc)
+    l = lap7(g) * (1.0 / (dx * dx)) * beta * b
+    return alpha * a * phi - l
+
+
+def amr_residual_nf(phi, coarse, rhs, a, b, alpha, beta, dx, lo, hi, n_domain, homogeneous=True, value=0.0, **bc):
+    g = ghosted_amr(phi, coarse, lo, hi, n_domain, dx, homogeneous=homogeneous, value=value, **bc)
+    l = lap7(g) * (1.0 / (dx * dx)) * beta * b
+    return (rhs - alpha * a * phi) + l

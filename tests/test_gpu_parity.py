@@ -529,3 +529,50 @@ def test_amr_patch_level_homogeneous_cf(ctx, name, with_b):
     for x in (A, B, E, R, RC):
         x.close()
     op.close(); cop.close()
+
+
+@pytest.mark.parametrize("name", sorted(PATCHES))
+def test_amr_patch_operator_with_quad_cf_interp(ctx, name):
+    """[Chombo] AMROperatorNF / AMRResidualNF on a patch (second half): QuadCFInterp from the coarser
+    level's field + applyOpI / residualI, bit-exact against the boxed oracle; the coarse field given as the whole coarse
+    level and as a coarser patch (offset origin); a coarse field that does not cover the stencils is refused."""
+    from oracle import OraclePatch
+    c = PATCHES[name]
+    dx, val = 0.25, 0.3
+    P = OraclePatch(c["n"], c["lo"], c["hi"], dx, max_grid_size=8, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], bc_value=val)
+    rng = np.random.default_rng(9)
+    e, r = rng.standard_normal(P.shape), rng.standard_normal(P.shape)
+    a, b = 0.1 * rng.standard_normal(P.shape) - 0.5, 1 + 0.1 * rng.standard_normal(P.shape)
+    cn = tuple(x // 2 for x in c["n"])
+    crse = rng.standard_normal(cn[::-1])
+    for f, x in (("E", e), ("R", r), ("A", a), ("B", b)):
+        P.set(f, x)
+    P.set_coarse(crse)
+    op = m.VariableCoeffPoissonOperator.patch(ctx, c["n"], c["lo"], c["hi"], dx, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], bc_value=val)
+    cop = m.VariableCoeffPoissonOperator(ctx, cn, 2 * dx)
+    A, B, E, R, LHS, CR = op.create(), op.create(), op.create(), op.create(), op.create(), cop.create()
+    A.upload(a); B.upload(b); R.upload(r); E.upload(e); CR.upload(crse)
+    op.setCoefs(A, B, 1.0, -1.0)
+    for homog in (True, False):
+        op.AMROperatorNF(LHS, E, CR, homogeneous=homog)
+        assert np.array_equal(LHS.download(), P.amr_operator_nf(homog)), homog
+        op.AMRResidualNF(LHS, E, CR, R, homogeneous=homog)
+        assert np.array_equal(LHS.download(), P.amr_residual_nf(homog)), homog
+    # the same from a coarser PATCH: the coarsened box grown by two cells, clipped to the coarse domain
+    clo = tuple(max(0, c["lo"][d] // 2 - 2) for d in range(3))
+    chi = tuple(min(cn[d] - 1, c["hi"][d] // 2 + 2) for d in range(3))
+    sub = np.ascontiguousarray(crse[clo[2]:chi[2] + 1, clo[1]:chi[1] + 1, clo[0]:chi[0] + 1])
+    pop = m.VariableCoeffPoissonOperator(ctx, sub.shape[::-1], 2 * dx)
+    CP = pop.create()
+    CP.upload(sub)
+    op.AMRResidualNF(LHS, E, CP, R, coarse_lo=clo, homogeneous=True)
+    assert np.array_equal(LHS.download(), P.amr_residual_nf(True))
+    if all(chi[d] - clo[d] + 1 > 4 for d in range(3)):
+        small = m.VariableCoeffPoissonOperator(ctx, tuple(chi[d] - clo[d] - 1 for d in range(3)), 2 * dx)
+        CS = small.create()
+        with pytest.raises(m.MgicError, match="proper nesting"):
+            op.AMRResidualNF(LHS, E, CS, R, coarse_lo=tuple(x + 1 for x in clo), homogeneous=True)
+        CS.close(); small.close()
+    for x in (A, B, E, R, LHS, CR, CP):
+        x.close()
+    op.close(); cop.close(); pop.close()

@@ -232,3 +232,48 @@ def test_patch_level_matches_numpy_twin(name, mgs):
     P.set("E", e)
     P.precond()
     assert np.array_equal(P.get("E"), T.relax(r * lam, r, a, b, lam, 1.0, -1.0, dx, 2, origin=c["lo"], **kw))
+
+
+def _quadratic(x, y, z):
+    return 0.3 + 0.7 * x - 0.2 * y + 0.5 * z + 0.11 * x * x - 0.23 * y * y + 0.05 * z * z + 0.4 * x * y - 0.31 * y * z + 0.17 * x * z
+
+
+@pytest.mark.parametrize("lo,hi", [((8, 8, 8), (23, 23, 23)), ((2, 2, 2), (29, 29, 29))])
+def test_quad_cf_interp_is_exact_for_quadratics(lo, hi):
+    """[Chombo] QuadCFInterp restated (tangential second-order Taylor expansion of the coarse field incl. the mixed term,
+    one-sided next to domain faces, then the normal parabola): with ghost values from it the 7-point operator of ANY
+    quadratic polynomial is exact in every cell of the patch, also next to the coarse-fine faces, edges and corners."""
+    from oracle import OraclePatch
+    n, dx = (32, 32, 32), 0.25
+    P = OraclePatch(n, lo, hi, dx, max_grid_size=8)
+    k, j, i = np.meshgrid(*(np.arange(lo[d], hi[d] + 1) for d in (2, 1, 0)), indexing="ij")
+    K, J, I = np.meshgrid(*(np.arange(n[d] // 2) for d in (2, 1, 0)), indexing="ij")
+    P.set("E", _quadratic((i + .5) * dx, (j + .5) * dx, (k + .5) * dx))
+    P.set_coarse(_quadratic((I + .5) * 2 * dx, (J + .5) * 2 * dx, (K + .5) * 2 * dx))
+    P.set("A", np.zeros(P.shape)); P.set("B", np.ones(P.shape)); P.set("R", np.zeros(P.shape))
+    lap = 2 * (0.11 - 0.23 + 0.05)
+    assert np.abs(P.amr_operator_nf(True) - lap).max() < 1e-11      # alpha*a = 0, beta = -1: L(phi) = laplacian
+    assert np.abs(P.amr_residual_nf(True) + lap).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", sorted(PATCHES))
+def test_patch_amr_operator_matches_numpy_twin(name):
+    """AMROperatorNF / AMRResidualNF (QuadCFInterp from the coarser level, then applyOpI / residualI): boxed oracle ==
+    single-array twin, bit for bit, homogeneous and inhomogeneous physical BC."""
+    from oracle import OraclePatch
+    c = PATCHES[name]
+    dx, val = 0.25, 0.3
+    P = OraclePatch(c["n"], c["lo"], c["hi"], dx, max_grid_size=8, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], bc_value=val)
+    rng = np.random.default_rng(8)
+    e, r = rng.standard_normal(P.shape), rng.standard_normal(P.shape)
+    a, b = 0.1 * rng.standard_normal(P.shape) - 0.5, 1 + 0.1 * rng.standard_normal(P.shape)
+    crse = rng.standard_normal(tuple(x // 2 for x in c["n"][::-1]))
+    for f, x in (("E", e), ("R", r), ("A", a), ("B", b)):
+        P.set(f, x)
+    P.set_coarse(crse)
+    kw = dict(bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], value=val)
+    for homog in (True, False):
+        assert np.array_equal(P.amr_operator_nf(homog),
+                              T.amr_operator_nf(e, crse, a, b, 1.0, -1.0, dx, c["lo"], c["hi"], c["n"], homogeneous=homog, **kw))
+        assert np.array_equal(P.amr_residual_nf(homog),
+                              T.amr_residual_nf(e, crse, r, a, b, 1.0, -1.0, dx, c["lo"], c["hi"], c["n"], homogeneous=homog, **kw))
