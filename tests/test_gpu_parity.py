@@ -576,3 +576,76 @@ def test_amr_patch_operator_with_quad_cf_interp(ctx, name):
     for x in (A, B, E, R, LHS, CR, CP):
         x.close()
     op.close(); cop.close(); pop.close()
+
+
+def test_two_level_amr_vcycle_on_the_c_abi(ctx):
+    """The two-level AMR V-cycle of tests/test_oracle.py (structure of [Chombo] AMRVCycle) with every numerical step on the
+    GPU through the C ABI -- patch relax (homogeneousCFInterp), AMRResidualNF (QuadCFInterp), the base level's
+    MultiGrid::oneCycle (CUDA graph), level-0 residual; only the 8-cell averaging and the piecewise-constant prolongation
+    between the two arrays are done by the test on the host.  Same convergence and the same fields as the oracle."""
+    from oracle import OraclePatch
+    from test_oracle import two_level_amr_vcycles
+    N, L = 32, 100.0
+    over = dict(N=(N, N, N), max_grid_size=16, numMGsmooth=2, L=L)
+    p = Pair(ctx, keep_b=True, smoother=1, **over)
+    o = p.o
+    a0, b0, rhs0 = o.get("A"), o.get("B"), o.get("RHS")
+    clo, chi = (8, 8, 8), (23, 23, 23)
+    lo, hi = tuple(2 * x for x in clo), tuple(2 * x + 1 for x in chi)
+    dx1 = L / N / 2
+    sl = tuple(slice(clo[d], chi[d] + 1) for d in (2, 1, 0))
+    rep = lambda x: np.repeat(np.repeat(np.repeat(x[sl], 2, 0), 2, 1), 2, 2)
+    # ---- oracle side
+    P = OraclePatch((2 * N,) * 3, lo, hi, dx1, max_grid_size=16)
+    P.set("A", rep(a0)); P.set("B", rep(b0))
+
+    def o_res_nf(phi, coarse, rhs, homog):
+        P.set("E", phi); P.set("R", rhs); P.set_coarse(coarse)
+        return P.amr_residual_nf(homog)
+
+    def o_relax(e, r):
+        P.set("E", e); P.set("R", r); P.relax(2)
+        return P.get("E")
+
+    def o_res0(phi, rhs):
+        o.set("E", phi); o.set("R", rhs)
+        return o.residual(0, False)
+
+    def o_vc(r):
+        o.set("R", r); o.set("E", np.zeros_like(r)); o.vcycle()
+        return o.get("E")
+
+    h_o, phi0_o, phi1_o = two_level_amr_vcycles(o_res0, o_vc, o_relax, o_res_nf, a0.shape, P.shape, sl, rhs0, rep(rhs0), 5)
+    # ---- GPU side
+    op1 = m.VariableCoeffPoissonOperator.patch(ctx, (2 * N,) * 3, lo, hi, dx1)
+    A1, B1, E1, R1, T1 = (op1.create() for _ in range(5))
+    A1.upload(rep(a0)); B1.upload(rep(b0))
+    op1.setCoefs(A1, B1, 1.0, -1.0)
+    C0 = p.op.create()
+
+    def g_res_nf(phi, coarse, rhs, homog):
+        E1.upload(phi); R1.upload(rhs); C0.upload(coarse)
+        op1.AMRResidualNF(T1, E1, C0, R1, homogeneous=homog)
+        return T1.download()
+
+    def g_relax(e, r):
+        E1.upload(e); R1.upload(r)
+        op1.relax(E1, R1, 2)
+        return E1.download()
+
+    def g_res0(phi, rhs):
+        p.e.upload(phi); p.r.upload(rhs)
+        p.op.residual(p.t, p.e, p.r, False)
+        return p.t.download()
+
+    def g_vc(r):
+        p.r.upload(r)
+        p.f.vcycle_from_zero(p.e, p.r)
+        return p.e.download()
+
+    h_g, phi0_g, phi1_g = two_level_amr_vcycles(g_res0, g_vc, g_relax, g_res_nf, a0.shape, P.shape, sl, rhs0, rep(rhs0), 5)
+    tot = [max(h) for h in h_g]
+    assert all(tot[i + 1] < 0.1 * tot[i] for i in range(len(tot) - 1)), tot
+    assert relerr(phi0_g, phi0_o) < 1e-10 and relerr(phi1_g, phi1_o) < 1e-10
+    for (a, b), (c, d) in zip(h_g[:3], h_o[:3]):      # residual histories while they are far above the rounding floor
+        assert abs(a - c) <= 1e-8 * c and abs(b - d) <= 1e-8 * d

@@ -277,3 +277,65 @@ def test_patch_amr_operator_matches_numpy_twin(name):
                               T.amr_operator_nf(e, crse, a, b, 1.0, -1.0, dx, c["lo"], c["hi"], c["n"], homogeneous=homog, **kw))
         assert np.array_equal(P.amr_residual_nf(homog),
                               T.amr_residual_nf(e, crse, r, a, b, 1.0, -1.0, dx, c["lo"], c["hi"], c["n"], homogeneous=homog, **kw))
+
+
+def two_level_amr_vcycles(level0_residual, level0_vcycle, patch_relax, patch_residual_nf, a0_shape, shape, sl, rhs0, rhs1, cycles):
+    """A two-level AMR V-cycle iteration in the structure of [Chombo] AMRMultiGrid::AMRVCycle (SURVEY App. B.9), written
+    over the operator-level primitives only: relax on the patch (homogeneousCFInterp), AMRResidualNF (QuadCFInterp),
+    averaging to the covered coarse cells, MultiGrid::oneCycle on the base level, piecewise-constant prolongation,
+    AMRUpdateResidual, post-relaxation.  Returns the history of (max|r_fine|, max|r_coarse|) and the two fields."""
+    rep = lambda x: np.repeat(np.repeat(np.repeat(x[sl], 2, 0), 2, 1), 2, 2)
+    phi0, phi1 = np.zeros(a0_shape), np.zeros(shape)
+    z0, z1 = np.zeros(a0_shape), np.zeros(shape)
+    hist = []
+    for _ in range(cycles):
+        r1 = patch_residual_nf(phi1, phi0, rhs1, False)
+        r0 = level0_residual(phi0, rhs0)
+        r0[sl] = T.coarse_average(r1, 2, False)          # covered cells: the averaged fine residual
+        hist.append((np.abs(r1).max(), np.abs(r0).max()))
+        e1 = patch_relax(z1, r1)                         # down: pre-relaxation of a zero correction
+        rc = r0.copy()
+        rc[sl] = T.coarse_average(patch_residual_nf(e1, z0, r1, True), 2, False)   # AMRRestrictS
+        e0 = level0_vcycle(rc)                           # base level: MultiGrid::oneCycle
+        e1 = e1 + rep(e0)                                # up: AMRProlongS
+        e1 = e1 + patch_relax(z1, patch_residual_nf(e1, e0, r1, True))   # AMRUpdateResidual + post-relaxation
+        phi1, phi0 = phi1 + e1, phi0 + e0
+    return hist, phi0, phi1
+
+
+def test_two_level_amr_vcycle_converges():
+    """The operator-level AMR pieces work together the way AMRVCycle uses them: on a Bowen-York base
+    level with one refined box the composite residual falls by more than an order of magnitude per V(2,2) cycle."""
+    from oracle import OraclePatch
+    N, L = 32, 100.0
+    o = Oracle(N=(N, N, N), max_grid_size=16, numMGsmooth=2, L=L)
+    o.setup()
+    a0, b0, rhs0 = o.get("A"), o.get("B"), o.get("RHS")
+    clo, chi = (8, 8, 8), (23, 23, 23)
+    lo, hi = tuple(2 * x for x in clo), tuple(2 * x + 1 for x in chi)
+    P = OraclePatch((2 * N,) * 3, lo, hi, L / N / 2, max_grid_size=16)
+    sl = tuple(slice(clo[d], chi[d] + 1) for d in (2, 1, 0))
+    rep = lambda x: np.repeat(np.repeat(np.repeat(x[sl], 2, 0), 2, 1), 2, 2)
+    P.set("A", rep(a0)); P.set("B", rep(b0))
+
+    def patch_residual_nf(phi, coarse, rhs, homog):
+        P.set("E", phi); P.set("R", rhs); P.set_coarse(coarse)
+        return P.amr_residual_nf(homog)
+
+    def patch_relax(e, r):
+        P.set("E", e); P.set("R", r); P.relax(2)
+        return P.get("E")
+
+    def level0_residual(phi, rhs):
+        o.set("E", phi); o.set("R", rhs)
+        return o.residual(0, False)
+
+    def level0_vcycle(r):
+        o.set("R", r); o.set("E", np.zeros_like(r)); o.vcycle()
+        return o.get("E")
+
+    hist, _, _ = two_level_amr_vcycles(level0_residual, level0_vcycle, patch_relax, patch_residual_nf, a0.shape, P.shape, sl,
+                                       rhs0, rep(rhs0), 6)
+    tot = [max(h) for h in hist]
+    assert all(tot[i + 1] < 0.1 * tot[i] for i in range(len(tot) - 1)), tot
+    assert tot[-1] < 1e-6 * tot[0]
