@@ -137,6 +137,17 @@ int mgic_op_amr_operator_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, co
                             int homogeneous);
 int mgic_op_amr_residual_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
                             const mgic_field *rhs, int homogeneous);
+/* ----------------------------------------------------------------- AMR V-cycle
+ * replaces: [Chombo] AMRMultiGrid::AMRVCycle as MultilevelLinearOp::preCond drives it (Main_PoissonSolver.cpp:103-117;
+ * SURVEY App. B.9) over a chain of levels: level 0 = the MG hierarchy `base`, finer level l = patches[l-1], a patch
+ * operator nested with refinement ratio 2 in the level below (one box per level in this version).  reflux is the
+ * reference's no-op.  mgic_amr_vcycle: corr[l] (out) = the correction of one cycle for the residuals res[l];
+ * pre = post = numMGsmooth. */
+typedef struct mgic_amr mgic_amr;
+int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patches, mgic_amr **out);
+int mgic_amr_destroy(mgic_amr *);
+int mgic_amr_levels(const mgic_amr *);
+int mgic_amr_vcycle(mgic_amr *, mgic_field *const *corr, mgic_field *const *res);
 /* the coarse-fine ghost values of one face (0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi) left by the last of the two
  * calls above: x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j] */
 int mgic_op_cf_ghosts(mgic_op *patch, int face, double *host);

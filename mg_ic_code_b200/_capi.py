@@ -57,6 +57,7 @@ def lib():
         "mgic_op_create": [vp, i3, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_create_patch": [vp, i3, i3, i3, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_cf_ghosts": [vp, C.c_int, nd],
+        "mgic_amr_create": [vp, C.c_int, pvp, pvp], "mgic_amr_destroy": [vp], "mgic_amr_vcycle": [vp, pvp, pvp],
         "mgic_op_amr_operator_nf": [vp, vp, vp, vp, i3, C.c_int], "mgic_op_amr_residual_nf": [vp, vp, vp, vp, i3, vp, C.c_int],
         "mgic_op_destroy": [vp], "mgic_op_set_coefs": [vp, vp, vp, C.c_double, C.c_double],
         "mgic_op_set_alpha_beta": [vp, C.c_double, C.c_double], "mgic_op_reset_lambda": [vp],

@@ -1184,6 +1184,119 @@ extern "C" int mgic_mg_vcycle_from_zero(mgic_mg *mg, mgic_field *e, const mgic_f
   return vcycle_run(mg, e, r, true);
 }
 
+// ------------------------------------------------------------------------------------------------ AMR V-cycle
+// [Chombo] AMRMultiGrid::AMRVCycle over a chain of levels (restated from the published algorithm): level 0
+// is the MG hierarchy, every finer level one patch operator nested in the level below.  reflux is the reference's no-op
+// (VariableCoeffPoissonOperator.cpp:264-271), so the coarser residual outside the patch is the caller's and only the
+// cells under the patch are overwritten by the averaged fine residual.  Host orchestration over the operator methods:
+//   down:  corr_l = 0; relax(corr_l, res_l, pre)                       (homogeneousCFInterp)
+//          corr_{l-1} = 0; res_{l-1}[under the patch] = average(res_l - L(corr_l))      (AMRRestrictS; QuadCFInterp from 0)
+//   base:  corr_0 = MultiGrid::oneCycle(res_0) from zero               (the V-cycle graph)
+//   up:    corr_l += prolong(corr_{l-1})                               (AMRProlongS, piecewise constant)
+//          res_l -= L(corr_l), coarse-fine ghosts from corr_{l-1}       (AMRUpdateResidual)
+//          d = 0; relax(d, res_l, post); corr_l += d
+struct mgic_amr {
+  mgic_ctx *ctx = nullptr;
+  mgic_mg *base = nullptr;
+  std::vector<mgic_op *> ops;                   // [0] = base level operator; finer: patch operators (not owned)
+  std::vector<mgic_field *> corr, res, tmp;     // owned, one per level
+  std::vector<int> off;                         // 3 per level: coarsened patch origin inside the level below's array
+};
+
+extern "C" int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patches, mgic_amr **out) {
+  MGIC_REQUIRE(base && out && nfiner >= 0 && (nfiner == 0 || patches), "bad argument");
+  MGIC_REQUIRE(base->ctx->nranks == 1, "AMR levels on a multi-rank context are not supported");
+  mgic_amr *A = new mgic_amr;
+  A->ctx = base->ctx; A->base = base;
+  A->ops.push_back(base->ops[0]);
+  A->off.assign(3, 0);
+  for (int l = 1; l <= nfiner; l++) {
+    mgic_op *o = patches[l - 1];
+    const mgic_op *below = A->ops[l - 1];
+    if (!o || !o->isPatch || !o->a) { mgic_set_error("finer level %d is not a patch operator with coefficients", l); delete A; return MGIC_ERR_ARG; }
+    for (int d = 0; d < 3; d++) {
+      const int belowLo = below->isPatch ? below->plo[d] : 0;
+      const int oc = (o->plo[d] >> 1) - belowLo;
+      const bool ratioOk = o->ndom[d] == 2 * (below->isPatch ? below->ndom[d] : below->n[d]);
+      if (!ratioOk || oc < 0 || oc + o->n[d] / 2 > below->n[d]) {
+        mgic_set_error("level %d is not nested in level %d with refinement ratio 2", l, l - 1);
+        delete A;
+        return MGIC_ERR_ARG;
+      }
+      A->off.push_back(oc);
+    }
+    A->ops.push_back(o);
+  }
+  for (mgic_op *o : A->ops) {
+    mgic_field *c = nullptr, *r = nullptr, *t = nullptr;
+    MGIC_TRY(mgic_field_create(o, &c)); MGIC_TRY(mgic_field_create(o, &r)); MGIC_TRY(mgic_field_create(o, &t));
+    A->corr.push_back(c); A->res.push_back(r); A->tmp.push_back(t);
+  }
+  *out = A;
+  return MGIC_OK;
+}
+extern "C" int mgic_amr_destroy(mgic_amr *A) {
+  if (!A) return MGIC_OK;
+  for (auto *f : A->corr) mgic_field_destroy(f);
+  for (auto *f : A->res) mgic_field_destroy(f);
+  for (auto *f : A->tmp) mgic_field_destroy(f);
+  delete A;
+  return MGIC_OK;
+}
+extern "C" int mgic_amr_levels(const mgic_amr *A) { return A ? (int)A->ops.size() : 0; }
+
+// the cells of level l-1's array `below` that lie under level l's patch
+static double *under_patch(const mgic_amr *A, int l, mgic_field *below) {
+  return below->p + A->off[3 * l] + (long long)A->off[3 * l + 1] * below->sy + (long long)A->off[3 * l + 2] * below->sz;
+}
+static void coarse_lo_of(const mgic_amr *A, int l, int lo[3]) {  // origin of level l's array in its level's index space
+  const mgic_op *o = A->ops[l];
+  for (int d = 0; d < 3; d++) lo[d] = o->isPatch ? o->plo[d] : 0;
+}
+
+static int amr_cycle(mgic_amr *A, int l) {
+  mgic_op *o = A->ops[l];
+  const int S = A->base->P.numMGsmooth;
+  if (l == 0) return vcycle_run(A->base, A->corr[0], A->res[0], true);   // corr_0 = oneCycle(res_0) from zero
+  mgic_op *ob = A->ops[l - 1];
+  int clo[3];
+  coarse_lo_of(A, l - 1, clo);
+  // ---- down
+  MGIC_TRY(mgic_op_set_to_zero(o, A->corr[l]));
+  MGIC_TRY(mgic_op_relax(o, A->corr[l], A->res[l], S));
+  MGIC_TRY(mgic_op_set_to_zero(ob, A->corr[l - 1]));
+  MGIC_TRY(mgic_op_amr_residual_nf(o, A->tmp[l], A->corr[l], A->corr[l - 1], clo, A->res[l], 1));
+  {
+    Geom gc = o->geom();
+    gc.nx /= 2; gc.ny /= 2; gc.nz /= 2; gc.sy = A->res[l - 1]->sy; gc.sz = A->res[l - 1]->sz;
+    MGIC_TRY(mgk::coarse_average(A->ctx, gc, under_patch(A, l, A->res[l - 1]), A->tmp[l]->p, A->tmp[l]->sy, A->tmp[l]->sz, 2, 0));
+  }
+  MGIC_TRY(amr_cycle(A, l - 1));
+  // ---- up
+  MGIC_TRY(mgk::prolong(A->ctx, o->geom(), A->corr[l]->p, under_patch(A, l, A->corr[l - 1]), A->corr[l - 1]->sy, A->corr[l - 1]->sz));
+  MGIC_TRY(mgic_op_amr_residual_nf(o, A->tmp[l], A->corr[l], A->corr[l - 1], clo, A->res[l], 1));
+  MGIC_TRY(mgic_op_assign(o, A->res[l], A->tmp[l]));
+  MGIC_TRY(mgic_op_set_to_zero(o, A->tmp[l]));
+  MGIC_TRY(mgic_op_relax(o, A->tmp[l], A->res[l], S));
+  MGIC_TRY(mgic_op_incr(o, A->corr[l], A->tmp[l], 1.0));
+  return MGIC_OK;
+}
+
+// corr[l] (out) = the correction of one AMR V-cycle for the residuals res[l] (in), l = 0 .. levels-1.  res[l-1] under a
+// finer patch is ignored (replaced by the averaged fine residual), as in AMRVCycle.
+extern "C" int mgic_amr_vcycle(mgic_amr *A, mgic_field *const *corr, mgic_field *const *res) {
+  MGIC_REQUIRE(A && corr && res, "NULL argument");
+  const int nl = (int)A->ops.size();
+  for (int l = 0; l < nl; l++) {
+    MGIC_REQUIRE(corr[l] && res[l], "NULL level field");
+    REQ_SHAPE(A->ops[l], corr[l]); REQ_SHAPE(A->ops[l], res[l]);
+    MGIC_TRY(mgic_op_assign(A->ops[l], A->res[l], res[l]));
+  }
+  MGIC_TRY(amr_cycle(A, nl - 1));
+  for (int l = 0; l < nl; l++) MGIC_TRY(mgic_op_assign(A->ops[l], corr[l], A->corr[l]));
+  return MGIC_OK;
+}
+
 // f1: [Chombo] MultilevelLinearOp::preCond on one AMR level = zero cor, numMGIterations V-cycles
 struct OuterLin : LinOp {
   mgic_mg *mg;

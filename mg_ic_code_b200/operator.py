@@ -328,6 +328,30 @@ class VariableCoeffPoissonOperatorFactory:
             self.h = None
 
 
+class AMRHierarchy:
+    """[Chombo] AMRMultiGrid::AMRVCycle over a chain of levels: level 0 = the factory's MG hierarchy, finer levels = patch
+    operators (VariableCoeffPoissonOperator.patch), each nested with ratio 2 in the level below."""
+
+    def __init__(self, factory, patches):
+        self.L, self.factory, self.patches = factory.L, factory, list(patches)
+        arr = (C.c_void_p * max(len(self.patches), 1))(*[p.h.value for p in self.patches])
+        h = C.c_void_p()
+        check(self.L.mgic_amr_create(factory.h, len(self.patches), arr, C.byref(h)))
+        self.h = h
+
+    def vcycle(self, corr, res):
+        """corr[l] (out) = one AMR V-cycle's correction for the residuals res[l], l = 0 .. levels-1"""
+        n = len(self.patches) + 1
+        ca = (C.c_void_p * n)(*[f.h.value for f in corr])
+        ra = (C.c_void_p * n)(*[f.h.value for f in res])
+        check(self.L.mgic_amr_vcycle(self.h, ca, ra))
+
+    def close(self):
+        if self.h:
+            self.L.mgic_amr_destroy(self.h)
+            self.h = None
+
+
 class MultigridVars:
     """multigrid_vars (8 components, MultigridUserVariables.hpp) + the Set* functions of Source/SetLevelData.cpp."""
 

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import mg_ic_code_b200 as m
+import np_twin
 from oracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -649,3 +650,66 @@ def test_two_level_amr_vcycle_on_the_c_abi(ctx):
     assert relerr(phi0_g, phi0_o) < 1e-10 and relerr(phi1_g, phi1_o) < 1e-10
     for (a, b), (c, d) in zip(h_g[:3], h_o[:3]):      # residual histories while they are far above the rounding floor
         assert abs(a - c) <= 1e-8 * c and abs(b - d) <= 1e-8 * d
+
+
+def test_amr_vcycle_library_entry_three_levels(ctx):
+    """mgic_amr_vcycle ([Chombo] AMRMultiGrid::AMRVCycle as a C-ABI entry point) on three levels -- a Bowen-York 32^3 base
+    level, a refined box in it and a refined box in that -- against the same cycle orchestrated here call by call over
+    the operator-level primitives (which the two tests above pin to the oracle): identical bits on every level, and
+    repeated cycles on the composite residual converge."""
+    N, L = 32, 100.0
+    p = Pair(ctx, keep_b=True, smoother=1, N=(N, N, N), max_grid_size=16, numMGsmooth=2, L=L)
+    a0, b0, rhs0 = p.o.get("A"), p.o.get("B"), p.o.get("RHS")
+    rep = lambda x: np.repeat(np.repeat(np.repeat(x, 2, 0), 2, 1), 2, 2)
+    # level l >= 1: box [lo, hi] of the 2^l-times refined domain; sl[l] = the cells of level l-1's ARRAY under it
+    boxes = {1: ((16, 16, 16), (47, 47, 47)), 2: ((48, 48, 48), (79, 79, 79))}
+    origin = {0: (0, 0, 0), 1: boxes[1][0], 2: boxes[2][0]}
+    ops, sl, coef = {0: p.op}, {}, {0: (a0, b0)}
+    for l in (1, 2):
+        lo, hi = boxes[l]
+        ops[l] = m.VariableCoeffPoissonOperator.patch(ctx, (N << l,) * 3, lo, hi, L / N / (1 << l))
+        sl[l] = tuple(slice(lo[d] // 2 - origin[l - 1][d], hi[d] // 2 - origin[l - 1][d] + 1) for d in (2, 1, 0))
+        coef[l] = tuple(rep(c[sl[l]]) for c in coef[l - 1])
+    F = {l: dict(E=ops[l].create(), R=ops[l].create(), T=ops[l].create(), A=ops[l].create(), B=ops[l].create()) for l in (1, 2)}
+    for l in (1, 2):
+        F[l]["A"].upload(coef[l][0]); F[l]["B"].upload(coef[l][1])
+        ops[l].setCoefs(F[l]["A"], F[l]["B"], 1.0, -1.0)
+    C = {0: p.op.create(), 1: ops[1].create()}     # holders for the coarser level's field in AMRResidualNF
+    shape = {0: a0.shape, 1: coef[1][0].shape, 2: coef[2][0].shape}
+
+    def res_nf(l, phi, coarse, rhs):
+        F[l]["E"].upload(phi); F[l]["R"].upload(rhs); C[l - 1].upload(coarse)
+        ops[l].AMRResidualNF(F[l]["T"], F[l]["E"], C[l - 1], F[l]["R"], coarse_lo=origin[l - 1], homogeneous=True)
+        return F[l]["T"].download()
+
+    def relax0(l, r):
+        F[l]["E"].upload(np.zeros(shape[l])); F[l]["R"].upload(r)
+        ops[l].relax(F[l]["E"], F[l]["R"], 2)
+        return F[l]["E"].download()
+
+    def ref_cycle(l, res, corr):
+        if l == 0:
+            p.r.upload(res[0]); p.f.vcycle_from_zero(p.e, p.r)
+            corr[0] = p.e.download()
+            return
+        corr[l] = relax0(l, res[l])
+        corr[l - 1] = np.zeros(shape[l - 1])
+        res[l - 1][sl[l]] = np_twin.coarse_average(res_nf(l, corr[l], corr[l - 1], res[l]), 2, False)
+        ref_cycle(l - 1, res, corr)
+        corr[l] = corr[l] + rep(corr[l - 1][sl[l]])
+        res[l] = res_nf(l, corr[l], corr[l - 1], res[l])
+        corr[l] = corr[l] + relax0(l, res[l])
+
+    amr = m.AMRHierarchy(p.f, [ops[1], ops[2]])
+    rng = np.random.default_rng(12)
+    res_in = {0: rhs0.copy(), 1: rep(rhs0[sl[1]]) + 1e-6 * rng.standard_normal(shape[1]), 2: 1e-5 * rng.standard_normal(shape[2])}
+    want_res, want = {l: res_in[l].copy() for l in res_in}, {}
+    ref_cycle(2, want_res, want)
+    Rin = [p.op.create(), ops[1].create(), ops[2].create()]
+    Cout = [p.op.create(), ops[1].create(), ops[2].create()]
+    for l in range(3):
+        Rin[l].upload(res_in[l])
+    amr.vcycle(Cout, Rin)
+    for l in range(3):
+        assert np.array_equal(Cout[l].download(), want[l]), l
+    amr.close()
