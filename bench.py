@@ -64,49 +64,94 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / clock-event (throttle) reasons sampled DURING the timed region: an NVML thread (10 ms period; the
+    timed region is ~100 ms) with the recipe's `nvidia-smi --query-gpu ... -lms` process beside it as the fallback.
+    start() returns only once a first sample exists, so a slow nvidia-smi / NVML start-up cannot leave the window empty."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc = index, [], None          # nvidia-smi: (time, csv line)
+        self.nv, self.nv_rows, self.nv_max, self.nv_stop = None, [], None, threading.Event()   # NVML: (time, MHz, mask)
 
-    def start(self):
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()]
+        if ids and self.index < len(ids) and ids[self.index].strip().isdigit():
+            return int(ids[self.index])
+        return self.index
+
+    def start(self, wait_s=8.0):
+        dev = self._nvml_index()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv_bits = (pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                            pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap)
+
+            def loop():
+                while not self.nv_stop.is_set():
+                    try:
+                        self.nv_rows.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons(h))))
+                    except Exception:
+                        pass
+                    self.nv_stop.wait(0.01)
+            self.nv = threading.Thread(target=loop, daemon=True)
+            self.nv.start()
+        except Exception:
+            self.nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        deadline = time.time() + wait_s
+        while time.time() < deadline and (self.nv or self.proc):
+            if (self.nv is None or self.nv_rows) and (self.proc is None or self.rows):
+                break
+            if self.proc is not None and self.proc.poll() is not None and not self.rows:
+                self.proc = None        # nvidia-smi exited without a row
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for t, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            inside = t0 - 0.05 <= t <= t1 + 0.15
-            try:
+        if not self.proc and not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"], "samples": 0}
+        time.sleep(0.12)
+        self.nv_stop.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons, source = [], self.nv_max, set(), "nvml"
+        for t, mhz, mask in self.nv_rows:
+            if t0 <= t <= t1:
+                sm.append(mhz)
+                reasons.update(n for n, b in zip(self.NAMES, self.nv_bits) if mask & b)
+        if not sm:                       # no NVML: the nvidia-smi rows (its timestamps lag the sample by up to one period)
+            source = "nvidia-smi"
+            for t, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                inside = t0 - 0.05 <= t <= t1 + 0.1
+                try:
+                    if inside:
+                        sm.append(float(f[1]))
+                    smax = float(f[2])
+                except ValueError:
+                    continue
                 if inside:
-                    sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            if inside:
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                    reasons.update(n for n, val in zip(self.NAMES, f[4:8]) if val.lower().startswith("active"))
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": source}
 
 
 def run_reference(args):
