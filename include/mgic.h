@@ -137,17 +137,44 @@ int mgic_op_amr_operator_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, co
                             int homogeneous);
 int mgic_op_amr_residual_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, const mgic_field *phi_coarse, const int coarse_lo[3],
                             const mgic_field *rhs, int homogeneous);
-/* ----------------------------------------------------------------- AMR V-cycle
- * replaces: [Chombo] AMRMultiGrid::AMRVCycle as MultilevelLinearOp::preCond drives it (Main_PoissonSolver.cpp:103-117;
- * SURVEY App. B.9) over a chain of levels: level 0 = the MG hierarchy `base`, finer level l = patches[l-1], a patch
- * operator nested with refinement ratio 2 in the level below (one box per level in this version).  reflux is the
- * reference's no-op.  mgic_amr_vcycle: corr[l] (out) = the correction of one cycle for the residuals res[l];
- * pre = post = numMGsmooth. */
+/* ----------------------------------------------------------------- AMR hierarchy
+ * replaces: [Chombo] AMRMultiGrid::AMRVCycle as MultilevelLinearOp::preCond drives it, MultilevelLinearOp itself and the
+ * outer BiCGStabSolver<Vector<LevelData<FArrayBox>*>> (Main_PoissonSolver.cpp:103-117,169-184) on a
+ * hierarchy of levels: level 0 = the MG hierarchy `base` (one array), finer level l = a list of patch operators
+ * (mgic_op_create_patch, coefficients set), each nested with refinement ratio 2 in ONE array of the level below
+ * (proper nesting: two coarse cells inside it, except at domain faces) and separated from its siblings by at least one
+ * coarse cell -- config C4's shape (one box on level 1, two disjoint boxes on level 2); touching boxes are rejected.
+ * reflux is the reference's no-op (VariableCoeffPoissonOperator.cpp:264-271).
+ * A LEVEL VECTOR is an array of mgic_amr_nodes() fields: [0] on the base level, then one per patch in creation order
+ * (level 1's patches first).  npatches[l-1] = number of patches of level l; `patches` is the flattened list.
+ * mgic_amr_create = a chain, one patch per level. */
 typedef struct mgic_amr mgic_amr;
 int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patches, mgic_amr **out);
+int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npatches, mgic_op *const *patches, mgic_amr **out);
 int mgic_amr_destroy(mgic_amr *);
 int mgic_amr_levels(const mgic_amr *);
+int mgic_amr_nodes(const mgic_amr *);
+int mgic_amr_node_info(const mgic_amr *, int node, int *level, int *parent_node);
+/* AMRVCycle: corr (out) = the correction of one cycle for the residuals res, pre = post = numMGsmooth, MultiGrid::oneCycle
+ * on the base level; res of a coarser array under a finer patch is replaced by the averaged fine residual */
 int mgic_amr_vcycle(mgic_amr *, mgic_field *const *corr, mgic_field *const *res);
+/* MultilevelLinearOp::applyOp / residual: per level applyOpI / residualI with the coarse-fine ghost cells interpolated
+ * from the level below (AMROperatorNF / AMRResidualNF) */
+int mgic_amr_apply(mgic_amr *, mgic_field *const *lhs, mgic_field *const *phi, int homogeneous);
+int mgic_amr_residual(mgic_amr *, mgic_field *const *res, mgic_field *const *phi, mgic_field *const *rhs, int homogeneous);
+/* AMRPoissonOp::zeroCovered level by level; CoarseAverage::averageToCoarse from the finest level down */
+int mgic_amr_zero_covered(mgic_amr *, mgic_field *const *x);
+int mgic_amr_average_down(mgic_amr *, mgic_field *const *x);
+/* over the valid cells NOT covered by a finer level: ord 0 max |x| (the outer solver's norm, Main_PoissonSolver.cpp:176);
+ * ord 1, 2 computeNorm's (sum |x|^p dx_l^3)^(1/p) (:208); dot = sum x*y*dx_l^3 (MultilevelLinearOp::dotProduct) */
+int mgic_amr_norm(mgic_amr *, mgic_field *const *x, int ord, double *out);
+int mgic_amr_dot(mgic_amr *, mgic_field *const *x, mgic_field *const *y, double *out);
+/* MultilevelLinearOp::preCond: cor = 0, then numMGIterations AMR V-cycles, each on the residual of the correction so far */
+int mgic_amr_precond(mgic_amr *, mgic_field *const *cor, mgic_field *const *res);
+/* solver.solve(dpsi, rhs) (Main_PoissonSolver.cpp:184) on the hierarchy: BiCGStab over the level vectors, AMR V-cycle
+ * preconditioner, max-norm, eps = tolerance, imax = max_iterations; exit_status / norms as mgic_mg_outer_solve */
+int mgic_amr_outer_solve(mgic_amr *, mgic_field *const *dpsi, mgic_field *const *rhs, int *iterations, int *exit_status,
+                         double *norms, int max_norms);
 /* the coarse-fine ghost values of one face (0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi) left by the last of the two
  * calls above: x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j] */
 int mgic_op_cf_ghosts(mgic_op *patch, int face, double *host);

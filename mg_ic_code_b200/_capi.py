@@ -57,7 +57,12 @@ def lib():
         "mgic_op_create": [vp, i3, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_create_patch": [vp, i3, i3, i3, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_cf_ghosts": [vp, C.c_int, nd],
-        "mgic_amr_create": [vp, C.c_int, pvp, pvp], "mgic_amr_destroy": [vp], "mgic_amr_vcycle": [vp, pvp, pvp],
+        "mgic_amr_create": [vp, C.c_int, pvp, pvp], "mgic_amr_create_levels": [vp, C.c_int, ip, pvp, pvp],
+        "mgic_amr_destroy": [vp], "mgic_amr_vcycle": [vp, pvp, pvp], "mgic_amr_node_info": [vp, C.c_int, ip, ip],
+        "mgic_amr_apply": [vp, pvp, pvp, C.c_int], "mgic_amr_residual": [vp, pvp, pvp, pvp, C.c_int],
+        "mgic_amr_zero_covered": [vp, pvp], "mgic_amr_average_down": [vp, pvp],
+        "mgic_amr_norm": [vp, pvp, C.c_int, dp], "mgic_amr_dot": [vp, pvp, pvp, dp], "mgic_amr_precond": [vp, pvp, pvp],
+        "mgic_amr_outer_solve": [vp, pvp, pvp, ip, ip, dp, C.c_int],
         "mgic_op_amr_operator_nf": [vp, vp, vp, vp, i3, C.c_int], "mgic_op_amr_residual_nf": [vp, vp, vp, vp, i3, vp, C.c_int],
         "mgic_op_destroy": [vp], "mgic_op_set_coefs": [vp, vp, vp, C.c_double, C.c_double],
         "mgic_op_set_alpha_beta": [vp, C.c_double, C.c_double], "mgic_op_reset_lambda": [vp],
@@ -97,7 +102,7 @@ def lib():
     L.mgic_ctx_stream.restype = vp
     L.mgic_ctx_launch_count.argtypes = [vp]
     L.mgic_ctx_launch_count.restype = C.c_longlong
-    for name in ("mgic_mg_depths", "mgic_mg_last_bottom_iterations", "mgic_mg_b_is_one"):
+    for name in ("mgic_mg_depths", "mgic_mg_last_bottom_iterations", "mgic_mg_b_is_one", "mgic_amr_levels", "mgic_amr_nodes"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = C.c_int
     _lib = L

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(one, sources()))
-    subprocess.check_call([nvcc, "-shared", "-o", SO] + objs)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs)
     return SO
 
 

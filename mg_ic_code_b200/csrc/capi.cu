@@ -691,22 +691,40 @@ struct BiCGWork {
   }
 };
 
-static int bicgstab(LinOp &L, BiCGWork &W, mgic_field *phi, const mgic_field *rhs, const BiCGParams &P, int *iterations,
-                    int *exitStatus, double *hist, int maxHist) {
-  mgic_op *op = L.op;
-  MGIC_TRY(W.alloc(op));
-  mgic_field *r = W.v[0], *rt = W.v[1], *e = W.v[2], *p = W.v[3], *pt = W.v[4], *st = W.v[5], *t = W.v[6], *v = W.v[7];
+// The solver is written over a vector space S: one level (LevelSpace: the mgic_op_* vector operations) or the composite
+// level vector of an AMR hierarchy (AmrSpace below: [Chombo] MultilevelLinearOp).
+struct LevelSpace {
+  typedef mgic_field *Vec;
+  typedef const mgic_field *CVec;
+  LinOp &L;
+  mgic_op *op;
+  explicit LevelSpace(LinOp &l) : L(l), op(l.op) {}
+  int residual(Vec r, Vec phi, CVec rhs, bool homogeneous) { return mgic_op_residual(op, r, phi, rhs, homogeneous); }
+  int apply(Vec lhs, Vec phi, int homogeneous) { return mgic_op_apply(op, lhs, phi, homogeneous); }
+  int preCond(Vec cor, Vec res) { return L.preCond(cor, res); }
+  int assign(Vec y, CVec x) { return mgic_op_assign(op, y, x); }
+  int set_to_zero(Vec y) { return mgic_op_set_to_zero(op, y); }
+  int norm(CVec x, int ord, double *out) { return mgic_op_norm(op, x, ord, out); }
+  int dot(CVec x, CVec y, double *out) { return mgic_op_dot(op, x, y, out); }
+  int scale(Vec y, double s) { return mgic_op_scale(op, y, s); }
+  int incr(Vec y, CVec x, double s) { return mgic_op_incr(op, y, x, s); }
+};
+
+template <class S>
+static int bicgstab_t(S &sp, typename S::Vec phi, typename S::CVec rhs, typename S::Vec const w[8], const BiCGParams &P,
+                      int *iterations, int *exitStatus, double *hist, int maxHist) {
+  typename S::Vec r = w[0], rt = w[1], e = w[2], p = w[3], pt = w[4], st = w[5], t = w[6], v = w[7];
   int nh = 0;
   auto push = [&](double x) { if (hist && nh < maxHist) hist[nh] = x; nh++; };
   int recount = 0;
-  MGIC_TRY(mgic_op_residual(op, r, phi, rhs, P.homogeneous));
-  MGIC_TRY(mgic_op_assign(op, rt, r));
-  MGIC_TRY(mgic_op_set_to_zero(op, e));
-  MGIC_TRY(mgic_op_set_to_zero(op, pt));
-  MGIC_TRY(mgic_op_set_to_zero(op, st));
+  MGIC_TRY(sp.residual(r, phi, rhs, P.homogeneous));
+  MGIC_TRY(sp.assign(rt, r));
+  MGIC_TRY(sp.set_to_zero(e));
+  MGIC_TRY(sp.set_to_zero(pt));
+  MGIC_TRY(sp.set_to_zero(st));
   int i = 0;
   double rho[4] = {0, 0, 0, 0}, norm[2];
-  MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+  MGIC_TRY(sp.norm(r, P.normType, &norm[0]));
   const double initial_norm = norm[0], initial_rnorm = norm[0];
   norm[1] = norm[0];
   double alpha[2] = {0, 0}, beta[2] = {0, 0}, omega[2] = {0, 0};
@@ -717,46 +735,46 @@ static int bicgstab(LinOp &L, BiCGWork &W, mgic_field *phi, const mgic_field *rh
     i++;
     norm[1] = norm[0]; alpha[1] = alpha[0]; beta[1] = beta[0]; omega[1] = omega[0];
     rho[3] = rho[2]; rho[2] = rho[1];
-    MGIC_TRY(mgic_op_dot(op, rt, r, &rho[1]));
+    MGIC_TRY(sp.dot(rt, r, &rho[1]));
     if (rho[1] == 0.0) {  // we are finished, we will not converge anymore
-      MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+      MGIC_TRY(sp.incr(phi, e, 1.0));
       status = 2;
       if (iterations) *iterations = i;
       if (exitStatus) *exitStatus = status;
       return MGIC_OK;
     }
     if (init) {
-      MGIC_TRY(mgic_op_assign(op, p, r));
+      MGIC_TRY(sp.assign(p, r));
       init = false;
     } else {
       beta[1] = (rho[1] / rho[2]) * (alpha[1] / omega[1]);
-      MGIC_TRY(mgic_op_scale(op, p, beta[1]));
-      MGIC_TRY(mgic_op_incr(op, p, v, -beta[1] * omega[1]));
-      MGIC_TRY(mgic_op_incr(op, p, r, 1.0));
+      MGIC_TRY(sp.scale(p, beta[1]));
+      MGIC_TRY(sp.incr(p, v, -beta[1] * omega[1]));
+      MGIC_TRY(sp.incr(p, r, 1.0));
     }
-    MGIC_TRY(L.preCond(pt, p));
-    MGIC_TRY(mgic_op_apply(op, v, pt, 1));
+    MGIC_TRY(sp.preCond(pt, p));
+    MGIC_TRY(sp.apply(v, pt, 1));
     double m;
-    MGIC_TRY(mgic_op_dot(op, rt, v, &m));
+    MGIC_TRY(sp.dot(rt, v, &m));
     alpha[0] = rho[1] / m;
     if (fabs(m) > P.small * fabs(rho[1])) {
-      MGIC_TRY(mgic_op_incr(op, r, v, -alpha[0]));
-      MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
-      MGIC_TRY(mgic_op_incr(op, e, pt, alpha[0]));
+      MGIC_TRY(sp.incr(r, v, -alpha[0]));
+      MGIC_TRY(sp.norm(r, P.normType, &norm[0]));
+      MGIC_TRY(sp.incr(e, pt, alpha[0]));
     } else {
-      MGIC_TRY(mgic_op_set_to_zero(op, r));
+      MGIC_TRY(sp.set_to_zero(r));
       norm[0] = 0.0;
     }
     if (norm[0] > P.eps * initial_norm && norm[0] > P.reps * initial_rnorm) {
-      MGIC_TRY(L.preCond(st, r));
-      MGIC_TRY(mgic_op_apply(op, t, st, 1));
+      MGIC_TRY(sp.preCond(st, r));
+      MGIC_TRY(sp.apply(t, st, 1));
       double tr, tt;
-      MGIC_TRY(mgic_op_dot(op, t, r, &tr));
-      MGIC_TRY(mgic_op_dot(op, t, t, &tt));
+      MGIC_TRY(sp.dot(t, r, &tr));
+      MGIC_TRY(sp.dot(t, t, &tt));
       omega[0] = tr / tt;
-      MGIC_TRY(mgic_op_incr(op, e, st, omega[0]));
-      MGIC_TRY(mgic_op_incr(op, r, t, -omega[0]));
-      MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+      MGIC_TRY(sp.incr(e, st, omega[0]));
+      MGIC_TRY(sp.incr(r, t, -omega[0]));
+      MGIC_TRY(sp.norm(r, P.normType, &norm[0]));
     }
     push(norm[0]);
     if (norm[0] <= P.eps * initial_norm || norm[0] <= P.reps * initial_rnorm) {
@@ -767,28 +785,35 @@ static int bicgstab(LinOp &L, BiCGWork &W, mgic_field *phi, const mgic_field *rh
       if (recount == 0) recount = 1;
       else {
         recount = 0;
-        MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+        MGIC_TRY(sp.incr(phi, e, 1.0));
         if (restarts == P.numRestarts) {
           status = 3;
           if (iterations) *iterations = i;
           if (exitStatus) *exitStatus = status;
           return MGIC_OK;
         }
-        MGIC_TRY(mgic_op_residual(op, r, phi, rhs, P.homogeneous));
-        MGIC_TRY(mgic_op_norm(op, r, P.normType, &norm[0]));
+        MGIC_TRY(sp.residual(r, phi, rhs, P.homogeneous));
+        MGIC_TRY(sp.norm(r, P.normType, &norm[0]));
         rho[1] = 0.0; rho[2] = 0.0; rho[3] = 0.0;
         alpha[0] = 0; beta[0] = 0; omega[0] = 0;
-        MGIC_TRY(mgic_op_assign(op, rt, r));
-        MGIC_TRY(mgic_op_set_to_zero(op, e));
+        MGIC_TRY(sp.assign(rt, r));
+        MGIC_TRY(sp.set_to_zero(e));
         restarts++;
         init = true;
       }
     }
   }
-  MGIC_TRY(mgic_op_incr(op, phi, e, 1.0));
+  MGIC_TRY(sp.incr(phi, e, 1.0));
   if (iterations) *iterations = i;
   if (exitStatus) *exitStatus = status;
   return MGIC_OK;
+}
+
+static int bicgstab(LinOp &L, BiCGWork &W, mgic_field *phi, const mgic_field *rhs, const BiCGParams &P, int *iterations,
+                    int *exitStatus, double *hist, int maxHist) {
+  MGIC_TRY(W.alloc(L.op));
+  LevelSpace sp(L);
+  return bicgstab_t(sp, phi, rhs, W.v, P, iterations, exitStatus, hist, maxHist);
 }
 
 // ------------------------------------------------------------------------------------------------ factory / MG
@@ -1184,117 +1209,336 @@ extern "C" int mgic_mg_vcycle_from_zero(mgic_mg *mg, mgic_field *e, const mgic_f
   return vcycle_run(mg, e, r, true);
 }
 
-// ------------------------------------------------------------------------------------------------ AMR V-cycle
-// [Chombo] AMRMultiGrid::AMRVCycle over a chain of levels (restated from the published algorithm): level 0
-// is the MG hierarchy, every finer level one patch operator nested in the level below.  reflux is the reference's no-op
-// (VariableCoeffPoissonOperator.cpp:264-271), so the coarser residual outside the patch is the caller's and only the
-// cells under the patch are overwritten by the averaged fine residual.  Host orchestration over the operator methods:
-//   down:  corr_l = 0; relax(corr_l, res_l, pre)                       (homogeneousCFInterp)
-//          corr_{l-1} = 0; res_{l-1}[under the patch] = average(res_l - L(corr_l))      (AMRRestrictS; QuadCFInterp from 0)
+// ------------------------------------------------------------------------------------------------ AMR hierarchy
+// [Chombo] AMRMultiGrid::AMRVCycle and MultilevelLinearOp over a hierarchy of levels (restated from
+// the published algorithm): level 0 is the MG hierarchy (one array), every finer level a list of patch operators, each
+// nested with refinement ratio 2 in ONE array of the level below and not touching its siblings (no fine-fine exchange).
+// A "level vector" is an array of fields in node order: [0] the base level, then the patches in creation order.
+// reflux is the reference's no-op (VariableCoeffPoissonOperator.cpp:264-271), so AMROperator == AMROperatorNF and the
+// coarser residual outside the patches is the caller's; only cells under a patch are overwritten by the averaged fine
+// residual.  Host orchestration over the operator methods:
+//   down:  corr_q = 0; relax(corr_q, res_q, pre)                       (homogeneousCFInterp)          for every patch q of level l
+//          corr_P = 0 on level l-1; res_P[under q] = average(res_q - L(corr_q))      (AMRRestrictS; QuadCFInterp from 0)
 //   base:  corr_0 = MultiGrid::oneCycle(res_0) from zero               (the V-cycle graph)
-//   up:    corr_l += prolong(corr_{l-1})                               (AMRProlongS, piecewise constant)
-//          res_l -= L(corr_l), coarse-fine ghosts from corr_{l-1}       (AMRUpdateResidual)
-//          d = 0; relax(d, res_l, post); corr_l += d
+//   up:    corr_q += prolong(corr_P)                                   (AMRProlongS, piecewise constant)
+//          res_q -= L(corr_q), coarse-fine ghosts from corr_P           (AMRUpdateResidual)
+//          d = 0; relax(d, res_q, post); corr_q += d
+struct AmrNode {
+  mgic_op *op = nullptr;           // base level operator / patch operator (not owned)
+  int level = 0, parent = -1;      // parent: node of the level below whose array contains the coarsened patch
+  int lo[3] = {0, 0, 0};           // origin of the node's array in its level's index space
+  int off[3] = {0, 0, 0};          // coarsened patch origin inside the parent's array
+  mgic_field *corr = nullptr, *res = nullptr, *tmp = nullptr;   // owned
+};
 struct mgic_amr {
   mgic_ctx *ctx = nullptr;
   mgic_mg *base = nullptr;
-  std::vector<mgic_op *> ops;                   // [0] = base level operator; finer: patch operators (not owned)
-  std::vector<mgic_field *> corr, res, tmp;     // owned, one per level
-  std::vector<int> off;                         // 3 per level: coarsened patch origin inside the level below's array
+  std::vector<AmrNode> nodes;
+  std::vector<int> levelStart;     // nodes of level l: [levelStart[l], levelStart[l+1])
+  std::vector<mgic_field *> work;  // 8 level vectors of the outer BiCGStab + 2 for composite residual / correction, lazily
+  int nlevels() const { return (int)levelStart.size() - 1; }
 };
 
-extern "C" int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patches, mgic_amr **out) {
-  MGIC_REQUIRE(base && out && nfiner >= 0 && (nfiner == 0 || patches), "bad argument");
+static int amr_fail(mgic_amr *A, const char *fmt, int a, int b) {
+  mgic_set_error(fmt, a, b);
+  delete A;
+  return MGIC_ERR_ARG;
+}
+
+extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npatches, mgic_op *const *patches, mgic_amr **out) {
+  MGIC_REQUIRE(base && out && nfiner >= 0 && (nfiner == 0 || (patches && npatches)), "bad argument");
   MGIC_REQUIRE(base->ctx->nranks == 1, "AMR levels on a multi-rank context are not supported");
   mgic_amr *A = new mgic_amr;
   A->ctx = base->ctx; A->base = base;
-  A->ops.push_back(base->ops[0]);
-  A->off.assign(3, 0);
+  AmrNode root;
+  root.op = base->ops[0];
+  A->nodes.push_back(root);
+  A->levelStart.push_back(0);
+  A->levelStart.push_back(1);
+  int next = 0;
   for (int l = 1; l <= nfiner; l++) {
-    mgic_op *o = patches[l - 1];
-    const mgic_op *below = A->ops[l - 1];
-    if (!o || !o->isPatch || !o->a) { mgic_set_error("finer level %d is not a patch operator with coefficients", l); delete A; return MGIC_ERR_ARG; }
-    for (int d = 0; d < 3; d++) {
-      const int belowLo = below->isPatch ? below->plo[d] : 0;
-      const int oc = (o->plo[d] >> 1) - belowLo;
-      const bool ratioOk = o->ndom[d] == 2 * (below->isPatch ? below->ndom[d] : below->n[d]);
-      if (!ratioOk || oc < 0 || oc + o->n[d] / 2 > below->n[d]) {
-        mgic_set_error("level %d is not nested in level %d with refinement ratio 2", l, l - 1);
-        delete A;
-        return MGIC_ERR_ARG;
+    if (npatches[l - 1] < 1) return amr_fail(A, "level %d has %d patches", l, npatches[l - 1]);
+    for (int q = 0; q < npatches[l - 1]; q++, next++) {
+      mgic_op *o = patches[next];
+      if (!o || !o->isPatch || !o->a) return amr_fail(A, "patch %d of level %d is not a patch operator with coefficients", q, l);
+      AmrNode nd;
+      nd.op = o; nd.level = l;
+      for (int d = 0; d < 3; d++) nd.lo[d] = o->plo[d];
+      // the parent: the one array of the level below that contains the coarsened patch
+      for (int P = A->levelStart[l - 1]; P < A->levelStart[l] && nd.parent < 0; P++) {
+        const AmrNode &pn = A->nodes[P];
+        bool in = true;
+        for (int d = 0; d < 3; d++) {
+          const int pdom = pn.op->isPatch ? pn.op->ndom[d] : pn.op->n[d];
+          const int oc = (o->plo[d] >> 1) - pn.lo[d];
+          in = in && o->ndom[d] == 2 * pdom && oc >= 0 && oc + o->n[d] / 2 <= pn.op->n[d];
+        }
+        if (in) nd.parent = P;
       }
-      A->off.push_back(oc);
+      if (nd.parent < 0) return amr_fail(A, "patch %d of level %d is not nested in one box of the level below with refinement ratio 2", q, l);
+      for (int d = 0; d < 3; d++) nd.off[d] = (o->plo[d] >> 1) - A->nodes[nd.parent].lo[d];
+      // siblings must not touch (their ghost cells would be each other's cells: a fine-fine exchange this version lacks)
+      for (int s2 = A->levelStart[l]; s2 < (int)A->nodes.size(); s2++) {
+        const mgic_op *b = A->nodes[s2].op;
+        bool apart = false;
+        for (int d = 0; d < 3; d++) apart = apart || o->plo[d] > b->plo[d] + b->n[d] || b->plo[d] > o->plo[d] + o->n[d];
+        if (!apart) return amr_fail(A, "patches %d and %d of one level touch or overlap (merge them into one box)", s2 - A->levelStart[l], q);
+      }
+      A->nodes.push_back(nd);
     }
-    A->ops.push_back(o);
+    A->levelStart.push_back((int)A->nodes.size());
   }
-  for (mgic_op *o : A->ops) {
-    mgic_field *c = nullptr, *r = nullptr, *t = nullptr;
-    MGIC_TRY(mgic_field_create(o, &c)); MGIC_TRY(mgic_field_create(o, &r)); MGIC_TRY(mgic_field_create(o, &t));
-    A->corr.push_back(c); A->res.push_back(r); A->tmp.push_back(t);
+  for (AmrNode &nd : A->nodes) {
+    if (mgic_field_create(nd.op, &nd.corr) != MGIC_OK || mgic_field_create(nd.op, &nd.res) != MGIC_OK ||
+        mgic_field_create(nd.op, &nd.tmp) != MGIC_OK) {
+      mgic_amr_destroy(A);
+      return MGIC_ERR_CUDA;
+    }
   }
   *out = A;
   return MGIC_OK;
 }
+// a chain: one patch per finer level
+extern "C" int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patches, mgic_amr **out) {
+  MGIC_REQUIRE(nfiner >= 0, "bad argument");
+  std::vector<int> ones((size_t)std::max(nfiner, 1), 1);
+  return mgic_amr_create_levels(base, nfiner, ones.data(), patches, out);
+}
 extern "C" int mgic_amr_destroy(mgic_amr *A) {
   if (!A) return MGIC_OK;
-  for (auto *f : A->corr) mgic_field_destroy(f);
-  for (auto *f : A->res) mgic_field_destroy(f);
-  for (auto *f : A->tmp) mgic_field_destroy(f);
+  for (AmrNode &nd : A->nodes) { mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); }
+  for (auto *f : A->work) mgic_field_destroy(f);
   delete A;
   return MGIC_OK;
 }
-extern "C" int mgic_amr_levels(const mgic_amr *A) { return A ? (int)A->ops.size() : 0; }
-
-// the cells of level l-1's array `below` that lie under level l's patch
-static double *under_patch(const mgic_amr *A, int l, mgic_field *below) {
-  return below->p + A->off[3 * l] + (long long)A->off[3 * l + 1] * below->sy + (long long)A->off[3 * l + 2] * below->sz;
+extern "C" int mgic_amr_levels(const mgic_amr *A) { return A ? A->nlevels() : 0; }
+extern "C" int mgic_amr_nodes(const mgic_amr *A) { return A ? (int)A->nodes.size() : 0; }
+extern "C" int mgic_amr_node_info(const mgic_amr *A, int node, int *level, int *parent) {
+  MGIC_REQUIRE(A && node >= 0 && node < (int)A->nodes.size(), "bad argument");
+  if (level) *level = A->nodes[node].level;
+  if (parent) *parent = A->nodes[node].parent;
+  return MGIC_OK;
 }
-static void coarse_lo_of(const mgic_amr *A, int l, int lo[3]) {  // origin of level l's array in its level's index space
-  const mgic_op *o = A->ops[l];
-  for (int d = 0; d < 3; d++) lo[d] = o->isPatch ? o->plo[d] : 0;
+
+// the cells of the parent's array `below` that lie under node q's patch, and that sub-box as a geometry
+static double *under_patch(const AmrNode &q, mgic_field *below) {
+  return below->p + q.off[0] + (long long)q.off[1] * below->sy + (long long)q.off[2] * below->sz;
+}
+static Geom under_geom(const AmrNode &q, const mgic_field *below) {
+  Geom gc = q.op->geom();
+  gc.nx /= 2; gc.ny /= 2; gc.nz /= 2; gc.sy = below->sy; gc.sz = below->sz;
+  return gc;
 }
 
 static int amr_cycle(mgic_amr *A, int l) {
-  mgic_op *o = A->ops[l];
   const int S = A->base->P.numMGsmooth;
-  if (l == 0) return vcycle_run(A->base, A->corr[0], A->res[0], true);   // corr_0 = oneCycle(res_0) from zero
-  mgic_op *ob = A->ops[l - 1];
-  int clo[3];
-  coarse_lo_of(A, l - 1, clo);
+  if (l == 0) return vcycle_run(A->base, A->nodes[0].corr, A->nodes[0].res, true);   // corr_0 = oneCycle(res_0) from zero
+  const int q0 = A->levelStart[l], q1 = A->levelStart[l + 1];
   // ---- down
-  MGIC_TRY(mgic_op_set_to_zero(o, A->corr[l]));
-  MGIC_TRY(mgic_op_relax(o, A->corr[l], A->res[l], S));
-  MGIC_TRY(mgic_op_set_to_zero(ob, A->corr[l - 1]));
-  MGIC_TRY(mgic_op_amr_residual_nf(o, A->tmp[l], A->corr[l], A->corr[l - 1], clo, A->res[l], 1));
-  {
-    Geom gc = o->geom();
-    gc.nx /= 2; gc.ny /= 2; gc.nz /= 2; gc.sy = A->res[l - 1]->sy; gc.sz = A->res[l - 1]->sz;
-    MGIC_TRY(mgk::coarse_average(A->ctx, gc, under_patch(A, l, A->res[l - 1]), A->tmp[l]->p, A->tmp[l]->sy, A->tmp[l]->sz, 2, 0));
+  for (int q = q0; q < q1; q++) {
+    AmrNode &n = A->nodes[q];
+    MGIC_TRY(mgic_op_set_to_zero(n.op, n.corr));
+    MGIC_TRY(mgic_op_relax(n.op, n.corr, n.res, S));
+  }
+  for (int P = A->levelStart[l - 1]; P < A->levelStart[l]; P++) MGIC_TRY(mgic_op_set_to_zero(A->nodes[P].op, A->nodes[P].corr));
+  for (int q = q0; q < q1; q++) {
+    AmrNode &n = A->nodes[q];
+    AmrNode &pn = A->nodes[n.parent];
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
+    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, pn.res), under_patch(n, pn.res), n.tmp->p, n.tmp->sy, n.tmp->sz, 2, 0));
   }
   MGIC_TRY(amr_cycle(A, l - 1));
   // ---- up
-  MGIC_TRY(mgk::prolong(A->ctx, o->geom(), A->corr[l]->p, under_patch(A, l, A->corr[l - 1]), A->corr[l - 1]->sy, A->corr[l - 1]->sz));
-  MGIC_TRY(mgic_op_amr_residual_nf(o, A->tmp[l], A->corr[l], A->corr[l - 1], clo, A->res[l], 1));
-  MGIC_TRY(mgic_op_assign(o, A->res[l], A->tmp[l]));
-  MGIC_TRY(mgic_op_set_to_zero(o, A->tmp[l]));
-  MGIC_TRY(mgic_op_relax(o, A->tmp[l], A->res[l], S));
-  MGIC_TRY(mgic_op_incr(o, A->corr[l], A->tmp[l], 1.0));
+  for (int q = q0; q < q1; q++) {
+    AmrNode &n = A->nodes[q];
+    AmrNode &pn = A->nodes[n.parent];
+    MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_patch(n, pn.corr), pn.corr->sy, pn.corr->sz));
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
+    MGIC_TRY(mgic_op_assign(n.op, n.res, n.tmp));
+    MGIC_TRY(mgic_op_set_to_zero(n.op, n.tmp));
+    MGIC_TRY(mgic_op_relax(n.op, n.tmp, n.res, S));
+    MGIC_TRY(mgic_op_incr(n.op, n.corr, n.tmp, 1.0));
+  }
   return MGIC_OK;
 }
 
-// corr[l] (out) = the correction of one AMR V-cycle for the residuals res[l] (in), l = 0 .. levels-1.  res[l-1] under a
-// finer patch is ignored (replaced by the averaged fine residual), as in AMRVCycle.
-extern "C" int mgic_amr_vcycle(mgic_amr *A, mgic_field *const *corr, mgic_field *const *res) {
-  MGIC_REQUIRE(A && corr && res, "NULL argument");
-  const int nl = (int)A->ops.size();
-  for (int l = 0; l < nl; l++) {
-    MGIC_REQUIRE(corr[l] && res[l], "NULL level field");
-    REQ_SHAPE(A->ops[l], corr[l]); REQ_SHAPE(A->ops[l], res[l]);
-    MGIC_TRY(mgic_op_assign(A->ops[l], A->res[l], res[l]));
+static int amr_check_vec(const mgic_amr *A, mgic_field *const *x) {
+  MGIC_REQUIRE(A && x, "NULL argument");
+  for (size_t q = 0; q < A->nodes.size(); q++) {
+    MGIC_REQUIRE(x[q], "NULL field in a level vector");
+    REQ_SHAPE(A->nodes[q].op, x[q]);
   }
-  MGIC_TRY(amr_cycle(A, nl - 1));
-  for (int l = 0; l < nl; l++) MGIC_TRY(mgic_op_assign(A->ops[l], corr[l], A->corr[l]));
   return MGIC_OK;
+}
+
+// corr (out) = the correction of one AMR V-cycle for the residuals res (in), both level vectors.  res of a coarser node
+// under a finer patch is ignored (replaced by the averaged fine residual), as in AMRVCycle.
+extern "C" int mgic_amr_vcycle(mgic_amr *A, mgic_field *const *corr, mgic_field *const *res) {
+  MGIC_TRY(amr_check_vec(A, corr)); MGIC_TRY(amr_check_vec(A, res));
+  for (AmrNode &n : A->nodes) MGIC_TRY(mgic_op_assign(n.op, n.res, res[&n - A->nodes.data()]));
+  MGIC_TRY(amr_cycle(A, A->nlevels() - 1));
+  for (AmrNode &n : A->nodes) MGIC_TRY(mgic_op_assign(n.op, corr[&n - A->nodes.data()], n.corr));
+  return MGIC_OK;
+}
+
+// ---- [Chombo] MultilevelLinearOp over the hierarchy: applyOp / residual per level with the coarse-fine ghosts from the
+// level below (AMROperatorNF; AMROperator's reflux is the reference's no-op), norms and dot products over the valid cells
+// NOT covered by a finer level (zeroCovered on a temporary, as MultilevelLinearOp::dotProduct / norm do).
+extern "C" int mgic_amr_apply(mgic_amr *A, mgic_field *const *lhs, mgic_field *const *phi, int homogeneous) {
+  MGIC_TRY(amr_check_vec(A, lhs)); MGIC_TRY(amr_check_vec(A, phi));
+  MGIC_TRY(mgic_op_apply(A->nodes[0].op, lhs[0], phi[0], homogeneous));
+  for (size_t q = 1; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    MGIC_TRY(mgic_op_amr_operator_nf(n.op, lhs[q], phi[q], phi[n.parent], A->nodes[n.parent].lo, homogeneous));
+  }
+  return MGIC_OK;
+}
+extern "C" int mgic_amr_residual(mgic_amr *A, mgic_field *const *res, mgic_field *const *phi, mgic_field *const *rhs, int homogeneous) {
+  MGIC_TRY(amr_check_vec(A, res)); MGIC_TRY(amr_check_vec(A, phi)); MGIC_TRY(amr_check_vec(A, rhs));
+  MGIC_TRY(mgic_op_residual(A->nodes[0].op, res[0], phi[0], rhs[0], homogeneous));
+  for (size_t q = 1; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, res[q], phi[q], phi[n.parent], A->nodes[n.parent].lo, rhs[q], homogeneous));
+  }
+  return MGIC_OK;
+}
+// x = 0 on every cell that a finer patch covers ([Chombo] AMRPoissonOp::zeroCovered, level by level)
+extern "C" int mgic_amr_zero_covered(mgic_amr *A, mgic_field *const *x) {
+  MGIC_TRY(amr_check_vec(A, x));
+  for (size_t q = 1; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), 0.0));
+  }
+  return MGIC_OK;
+}
+// the covered cells of every coarser array = the 8-cell average of the finer patch, finest level first
+// ([Chombo] CoarseAverage::averageToCoarse, what Main_PoissonSolver.cpp's output path and AMRMultiGrid do after a solve)
+extern "C" int mgic_amr_average_down(mgic_amr *A, mgic_field *const *x) {
+  MGIC_TRY(amr_check_vec(A, x));
+  for (size_t q = A->nodes.size() - 1; q >= 1; q--) {
+    const AmrNode &n = A->nodes[q];
+    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), x[q]->p, x[q]->sy, x[q]->sz, 2, 0));
+  }
+  return MGIC_OK;
+}
+// copy of x with the covered cells zeroed, in the nodes' tmp fields
+static int amr_masked_copy(mgic_amr *A, mgic_field *const *x) {
+  for (size_t q = 0; q < A->nodes.size(); q++) MGIC_TRY(mgic_op_assign(A->nodes[q].op, A->nodes[q].tmp, x[q]));
+  for (size_t q = 1; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    mgic_field *pt = A->nodes[n.parent].tmp;
+    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, pt), under_patch(n, pt), 0.0));
+  }
+  return MGIC_OK;
+}
+// ord 0: max |x| over the valid, uncovered cells (the outer solver's m_normType = 0, Main_PoissonSolver.cpp:176);
+// ord 1, 2: [Chombo] computeNorm -- (sum |x|^p dx_l^3)^(1/p) over the same cells (Main_PoissonSolver.cpp:208)
+extern "C" int mgic_amr_norm(mgic_amr *A, mgic_field *const *x, int ord, double *out) {
+  MGIC_TRY(amr_check_vec(A, x));
+  MGIC_REQUIRE(out && ord >= 0 && ord <= 2, "norm order must be 0, 1 or 2");
+  MGIC_TRY(amr_masked_copy(A, x));
+  double acc = 0.0;
+  for (AmrNode &n : A->nodes) {
+    double v;
+    MGIC_TRY(local_reduce(n.op, n.tmp, nullptr, ord, &v));
+    if (ord == 0) acc = std::max(acc, v);
+    else acc += v * (n.op->dx * n.op->dx * n.op->dx);
+  }
+  *out = ord == 2 ? sqrt(acc) : acc;
+  return MGIC_OK;
+}
+// sum over the valid, uncovered cells of x*y*dx_l^3 ([Chombo] MultilevelLinearOp::dotProduct: covered cells zeroed on
+// temporaries, level products scaled by the cell volume)
+extern "C" int mgic_amr_dot(mgic_amr *A, mgic_field *const *x, mgic_field *const *y, double *out) {
+  MGIC_TRY(amr_check_vec(A, x)); MGIC_TRY(amr_check_vec(A, y));
+  MGIC_REQUIRE(out, "NULL argument");
+  MGIC_TRY(amr_masked_copy(A, x));
+  double acc = 0.0;
+  for (size_t q = 0; q < A->nodes.size(); q++) {
+    AmrNode &n = A->nodes[q];
+    double v;
+    MGIC_TRY(local_reduce(n.op, n.tmp, y[q], 3, &v));
+    acc += v * (n.op->dx * n.op->dx * n.op->dx);
+  }
+  *out = acc;
+  return MGIC_OK;
+}
+
+// level vector k (0..9) of the hierarchy's work space; all ten are allocated at the first call, so the pointers stay valid
+#define MGIC_AMR_WORK 10
+static int amr_work(mgic_amr *A, int k, mgic_field ***vec) {
+  const size_t nn = A->nodes.size();
+  if (A->work.size() < MGIC_AMR_WORK * nn) {
+    A->work.reserve(MGIC_AMR_WORK * nn);
+    while (A->work.size() < MGIC_AMR_WORK * nn) {
+      mgic_field *f = nullptr;
+      MGIC_TRY(mgic_field_create(A->nodes[A->work.size() % nn].op, &f));
+      A->work.push_back(f);
+    }
+  }
+  *vec = A->work.data() + (size_t)k * nn;
+  return MGIC_OK;
+}
+
+// [Chombo] MultilevelLinearOp::preCond: cor = 0, then numMGIterations AMR V-cycles.  AMRVCycle works on the residual it is
+// given, so from the second cycle on it is given the residual of the correction so far (res - L cor) and its result is
+// added -- on one level this is MultiGrid::oneCycle repeated on the same (e, r) pair, which mgic_mg_outer_solve does.
+extern "C" int mgic_amr_precond(mgic_amr *A, mgic_field *const *cor, mgic_field *const *res) {
+  MGIC_TRY(amr_check_vec(A, cor)); MGIC_TRY(amr_check_vec(A, res));
+  const int nIt = A->base->P.numMGIterations;
+  if (nIt < 1) {
+    for (size_t q = 0; q < A->nodes.size(); q++) MGIC_TRY(mgic_op_set_to_zero(A->nodes[q].op, cor[q]));
+    return MGIC_OK;
+  }
+  MGIC_TRY(mgic_amr_vcycle(A, cor, res));
+  mgic_field **r2 = nullptr, **c2 = nullptr;
+  for (int it = 1; it < nIt; it++) {
+    MGIC_TRY(amr_work(A, 8, &r2));
+    MGIC_TRY(amr_work(A, 9, &c2));
+    MGIC_TRY(mgic_amr_residual(A, r2, cor, res, 1));
+    MGIC_TRY(mgic_amr_vcycle(A, c2, r2));
+    for (size_t q = 0; q < A->nodes.size(); q++) MGIC_TRY(mgic_op_incr(A->nodes[q].op, cor[q], c2[q], 1.0));
+  }
+  return MGIC_OK;
+}
+
+struct AmrSpace {
+  typedef mgic_field *const *Vec;
+  typedef mgic_field *const *CVec;
+  mgic_amr *A;
+  int residual(Vec r, Vec phi, CVec rhs, bool homogeneous) { return mgic_amr_residual(A, r, phi, rhs, homogeneous); }
+  int apply(Vec lhs, Vec phi, int homogeneous) { return mgic_amr_apply(A, lhs, phi, homogeneous); }
+  int preCond(Vec cor, Vec res) { return mgic_amr_precond(A, cor, res); }
+  int norm(CVec x, int ord, double *out) { return mgic_amr_norm(A, x, ord, out); }
+  int dot(CVec x, CVec y, double *out) { return mgic_amr_dot(A, x, y, out); }
+#define AMR_EACH(call) \
+  for (size_t q = 0; q < A->nodes.size(); q++) MGIC_TRY(call); \
+  return MGIC_OK
+  int assign(Vec y, CVec x) { AMR_EACH(mgic_op_assign(A->nodes[q].op, y[q], x[q])); }
+  int set_to_zero(Vec y) { AMR_EACH(mgic_op_set_to_zero(A->nodes[q].op, y[q])); }
+  int scale(Vec y, double s) { AMR_EACH(mgic_op_scale(A->nodes[q].op, y[q], s)); }
+  int incr(Vec y, CVec x, double s) { AMR_EACH(mgic_op_incr(A->nodes[q].op, y[q], x[q], s)); }
+#undef AMR_EACH
+};
+
+// The reference's linear solve on a hierarchy (Main_PoissonSolver.cpp:169-184): BiCGStabSolver<Vector<LevelData*>> over
+// MultilevelLinearOp, preconditioned by numMGIterations AMR V-cycles; max-norm, eps = tolerance, imax = max_iterations.
+extern "C" int mgic_amr_outer_solve(mgic_amr *A, mgic_field *const *dpsi, mgic_field *const *rhs, int *iterations, int *exit_status,
+                                    double *norms, int max_norms) {
+  MGIC_TRY(amr_check_vec(A, dpsi)); MGIC_TRY(amr_check_vec(A, rhs));
+  mgic_field *const *w[8];
+  for (int k = 0; k < 8; k++) {
+    mgic_field **v = nullptr;
+    MGIC_TRY(amr_work(A, k, &v));
+    w[k] = v;
+  }
+  AmrSpace sp{A};
+  BiCGParams bp;
+  bp.homogeneous = false;               // Main_PoissonSolver.cpp:172-173
+  bp.normType = 0;                      // :176
+  bp.eps = A->base->P.tolerance;        // :177
+  bp.imax = A->base->P.max_iterations;  // :178
+  return bicgstab_t(sp, dpsi, rhs, w, bp, iterations, exit_status, norms, max_norms);
 }
 
 // f1: [Chombo] MultilevelLinearOp::preCond on one AMR level = zero cor, numMGIterations V-cycles

@@ -309,6 +309,16 @@ __global__ void __launch_bounds__(128) k_coarse_average(Geom gc, double *__restr
   c[I + J * gc.sy + K * gc.sz] = harmonic ? 1.0 / (sum * refScale) : sum * refScale;
 }
 
+// y = v on a sub-box (g.nx x g.ny x g.nz cells, strides g.sy / g.sz of the array that contains it): [Chombo]
+// AMRPoissonOp::zeroCovered -- the cells of a level that a finer level covers -- for the composite norms and dot products
+__global__ void __launch_bounds__(128) k_box_set(Geom g, double *__restrict__ y, double v) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J = blockIdx.y * blockDim.y + threadIdx.y;
+  const int K = blockIdx.z;
+  if (I >= g.nx || J >= g.ny) return;
+  y[I + J * g.sy + K * g.sz] = v;
+}
+
 inline dim3 grid3(int nx, int ny, int nz, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
 inline int ew_grid(mgic_ctx *c, long long n) {
   long long b = (n + 255) / 256;
@@ -437,6 +447,13 @@ int is_constant(mgic_ctx *c, const Geom &g, const double *x, double value, int s
   if (nb > (long long)c->partCap) nb = (long long)c->partCap;
   k_reduce<4><<<(int)nb, 256, 0, c->stream>>>(n, x, nullptr, value, c->d_part, c->d_count, c->d_scal + slot);
   return post_launch(c, "is_constant");
+}
+
+int box_set_val(mgic_ctx *c, const Geom &g, double *y, double v) {
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
+  k_box_set<<<grd, blk, 0, c->stream>>>(g, y, v);
+  return post_launch(c, "box_set_val");
 }
 
 int coarse_average(mgic_ctx *c, const Geom &gc, double *cp, const double *fine, long long fsy, long long fsz, int nref,

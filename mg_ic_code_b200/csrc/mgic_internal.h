@@ -189,6 +189,7 @@ int axby(mgic_ctx *, const Geom &, double *y, const double *x1, const double *x2
 int scale(mgic_ctx *, const Geom &, double *y, double s);
 int assign(mgic_ctx *, const Geom &, double *y, const double *x);
 int set_val(mgic_ctx *, const Geom &, double *y, double v);
+int box_set_val(mgic_ctx *, const Geom &box, double *y, double v);   // sub-box of a larger array (strides box.sy / box.sz)
 int jacobi_update(mgic_ctx *, const Geom &, double *phi, const double *res, const double *lam, double w);
 // reductions: result left in ctx->d_scal[slot]; kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y
 int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot);

@@ -329,22 +329,74 @@ class VariableCoeffPoissonOperatorFactory:
 
 
 class AMRHierarchy:
-    """[Chombo] AMRMultiGrid::AMRVCycle over a chain of levels: level 0 = the factory's MG hierarchy, finer levels = patch
-    operators (VariableCoeffPoissonOperator.patch), each nested with ratio 2 in the level below."""
+    """[Chombo] AMRMultiGrid::AMRVCycle, MultilevelLinearOp and the outer BiCGStab over a hierarchy of levels: level 0 = the
+    factory's MG hierarchy, finer levels = lists of patch operators (VariableCoeffPoissonOperator.patch), each nested with
+    ratio 2 in one array of the level below and not touching its siblings.  `patches`: a flat list (a chain, one patch per
+    level) or a list of lists (level 1's patches, level 2's patches, ...).  A level vector is a list of fields: the base
+    level's, then one per patch in that order."""
 
     def __init__(self, factory, patches):
-        self.L, self.factory, self.patches = factory.L, factory, list(patches)
+        self.L, self.factory = factory.L, factory
+        levels = [list(p) if isinstance(p, (list, tuple)) else [p] for p in patches]
+        self.patches = [q for lv in levels for q in lv]
         arr = (C.c_void_p * max(len(self.patches), 1))(*[p.h.value for p in self.patches])
+        counts = (C.c_int * max(len(levels), 1))(*[len(lv) for lv in levels])
         h = C.c_void_p()
-        check(self.L.mgic_amr_create(factory.h, len(self.patches), arr, C.byref(h)))
+        check(self.L.mgic_amr_create_levels(factory.h, len(levels), counts, arr, C.byref(h)))
         self.h = h
+        self.nodes = self.L.mgic_amr_nodes(h)
+        self.levels = self.L.mgic_amr_levels(h)
+
+    def _vec(self, fields):
+        if len(fields) != self.nodes:
+            raise MgicError(f"a level vector of this hierarchy has {self.nodes} fields, got {len(fields)}")
+        return (C.c_void_p * self.nodes)(*[f.h.value for f in fields])
+
+    def node_info(self, node):
+        lv, par = C.c_int(), C.c_int()
+        check(self.L.mgic_amr_node_info(self.h, node, C.byref(lv), C.byref(par)))
+        return lv.value, par.value
+
+    def create(self):
+        """a new level vector"""
+        return [self.factory.MGnewOp(0).create()] + [p.create() for p in self.patches]
 
     def vcycle(self, corr, res):
-        """corr[l] (out) = one AMR V-cycle's correction for the residuals res[l], l = 0 .. levels-1"""
-        n = len(self.patches) + 1
-        ca = (C.c_void_p * n)(*[f.h.value for f in corr])
-        ra = (C.c_void_p * n)(*[f.h.value for f in res])
-        check(self.L.mgic_amr_vcycle(self.h, ca, ra))
+        """corr (out) = one AMR V-cycle's correction for the residuals res"""
+        check(self.L.mgic_amr_vcycle(self.h, self._vec(corr), self._vec(res)))
+
+    def applyOp(self, lhs, phi, homogeneous=False):
+        check(self.L.mgic_amr_apply(self.h, self._vec(lhs), self._vec(phi), int(homogeneous)))
+
+    def residual(self, res, phi, rhs, homogeneous=False):
+        check(self.L.mgic_amr_residual(self.h, self._vec(res), self._vec(phi), self._vec(rhs), int(homogeneous)))
+
+    def zeroCovered(self, x):
+        check(self.L.mgic_amr_zero_covered(self.h, self._vec(x)))
+
+    def averageDown(self, x):
+        check(self.L.mgic_amr_average_down(self.h, self._vec(x)))
+
+    def norm(self, x, ord=0):
+        out = C.c_double()
+        check(self.L.mgic_amr_norm(self.h, self._vec(x), ord, C.byref(out)))
+        return out.value
+
+    def dotProduct(self, x, y):
+        out = C.c_double()
+        check(self.L.mgic_amr_dot(self.h, self._vec(x), self._vec(y), C.byref(out)))
+        return out.value
+
+    def preCond(self, cor, res):
+        check(self.L.mgic_amr_precond(self.h, self._vec(cor), self._vec(res)))
+
+    def solve(self, dpsi, rhs, max_norms=256):
+        """solver.solve(dpsi, rhs) on the hierarchy: (iterations, exit status, residual max-norm history)"""
+        it, st = C.c_int(), C.c_int()
+        norms = np.zeros(max_norms)
+        check(self.L.mgic_amr_outer_solve(self.h, self._vec(dpsi), self._vec(rhs), C.byref(it), C.byref(st),
+                                          norms.ctypes.data_as(C.POINTER(C.c_double)), max_norms))
+        return it.value, st.value, norms[:min(it.value + 1, max_norms)].copy()
 
     def close(self):
         if self.h:
