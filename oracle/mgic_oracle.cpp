@@ -8,9 +8,11 @@
  * "reference CPU path" (OpenMP over boxes == the reference's one-MPI-rank-per
  * -core box parallelism, jobscript.pbs:3,13).
  *
- * PARITY UNPINNED (see mgic_oracle.h): no golden vectors exist upstream.
- * Everything tagged [Chombo] restates Chombo 3.2 (GNUmakefile:12), which is not
- * under /root/reference.
+ * PARITY (see mgic_oracle.h): the source-term functions are pinned bit for bit
+ * to the reference's own code (oracle/_ref); the operator path is UNPINNED -- no
+ * golden vectors exist upstream and it cannot be built here.  Everything tagged
+ * [Chombo] restates Chombo 3.2 (GNUmakefile:12), which is not under
+ * /root/reference.
  *
  * Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp (see Makefile).
  * -ffp-contract=off keeps the source evaluation order (no FMA contraction) so

@@ -6,15 +6,23 @@
  * reference legs may load this library, and only as the checker / the timed
  * CPU arm.  The product (mg_ic_code_b200/) never links, imports or executes it.
  *
- * PARITY UNPINNED: the reference (eugenealim/MG_IC_code) ships no tests, no
- * golden vectors and cannot be built here (needs Chombo 3.2 + Fortran + MPI +
- * HDF5, none present).  This oracle is a line-faithful restatement of the
+ * PARITY: PINNED TO THE REFERENCE'S OWN CODE for the source terms (SURVEY rows
+ * a18 / a19: set_initial_conditions, set_rhs, set_a_coef, set_b_coef,
+ * set_update_psi0, get_Aij, set_binary_bh_psi, my_phi_function) -- the
+ * reference's Source/SetLevelData.cpp + SetBinaryBH.H + MyPhiFunction.H compile
+ * unmodified against a stand-in for the Chombo containers (oracle/_ref, Makefile
+ * target `ref`) and this oracle reproduces them bit for bit
+ * (tests/test_reference_pins.py, tests/golden/reference_sources_16.npz).
+ * PARITY UNPINNED for the operator path: the reference ships no tests and no
+ * golden vectors, and VariableCoeffPoissonOperator cannot be built here (needs
+ * Chombo 3.2's AMRPoissonOp + a Fortran compiler for the .ChF kernels + MPI,
+ * none present).  There this oracle is a line-faithful restatement of the
  * reference sources cited at each function, plus a restatement of the
  * Chombo 3.2 control flow the path leans on (MultiGrid::cycle,
  * BiCGStabSolver::solve, DiriBC/NeumBC, CoarseAverage, FORT_PROLONG), which is
  * NOT vendored under /root/reference and is restated from its published
- * algorithm.  Its own pins are the known-answer tests in tests/ (trivial KAT,
- * trace-free KAT, manufactured solution, decomposition invariance) and an
+ * algorithm.  Its own pins there are the known-answer tests in tests/ (trivial
+ * KAT, trace-free KAT, manufactured solution, decomposition invariance) and an
  * independent numpy twin (tests/np_twin.py).
  */
 #ifndef MGIC_ORACLE_H

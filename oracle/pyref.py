@@ -1,0 +1,96 @@
+"""ctypes loader for oracle/_ref/libmgic_ref.so (TEST INFRASTRUCTURE): the reference's own Source/SetLevelData.cpp,
+Source/SetBinaryBH.H and MyPhiFunction.H compiled unmodified against a stand-in for the Chombo containers
+(oracle/ref_shim/chombo_standin.H; recipe: `make -C oracle ref`).  Used by tests/test_reference_pins.py and
+tests/golden/make_reference_golden.py to pin the oracle's source-term restatement to the reference's arithmetic."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libmgic_ref.so")
+REFERENCE = os.environ.get("MGIC_REFERENCE", "/root/reference")
+
+
+class RefParams(C.Structure):
+    _fields_ = [("G_Newton", C.c_double), ("phi_amplitude", C.c_double), ("phi_wavelength", C.c_double),
+                ("bh1_bare_mass", C.c_double), ("bh1_spin", C.c_double), ("bh1_momentum", C.c_double), ("bh1_offset", C.c_double),
+                ("bh2_bare_mass", C.c_double), ("bh2_spin", C.c_double), ("bh2_momentum", C.c_double), ("bh2_offset", C.c_double),
+                ("L", C.c_double * 3)]
+
+
+def available():
+    return os.path.exists(SO) or os.path.isdir(os.path.join(REFERENCE, "Source"))
+
+
+def build():
+    """compile the reference's files where they lie (only possible where /root/reference exists); returns the .so or None"""
+    if os.path.isdir(os.path.join(REFERENCE, "Source")):
+        from . import pyoracle
+        pyoracle.build()
+        subprocess.check_call(["make", "-C", _HERE, "ref", f"REF={REFERENCE}"], stdout=subprocess.DEVNULL)
+    return SO if os.path.exists(SO) else None
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if build() is None:
+            raise RuntimeError("oracle/_ref/libmgic_ref.so is not built and /root/reference is absent")
+        L = C.CDLL(SO)
+        nd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.ref_set_level_data.argtypes = [C.POINTER(RefParams), C.c_int * 3, C.c_double, C.c_double, C.c_void_p, nd, nd, nd, nd]
+        L.ref_set_level_data.restype = C.c_int
+        L.ref_point_values.argtypes = [C.POINTER(RefParams), C.c_double * 3, C.c_double * 6, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_point_values.restype = None
+        L.ref_m_value.argtypes = [C.POINTER(RefParams), C.c_double, C.c_double]
+        L.ref_m_value.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def to_struct(params):
+    """params: the oracle's parameter dict (oracle.pyoracle.default_params)"""
+    p = RefParams()
+    for k, _ in RefParams._fields_:
+        if k != "L":
+            setattr(p, k, params[k])
+    N, L = params["N"], params["L"]
+    # PoissonParameters.cpp:70-85: cubic cells, dx = L / N[0], domainLength[d] = N[d] * dx
+    p.L = (C.c_double * 3)(*[L * N[d] / N[0] for d in range(3)])
+    return p
+
+
+def set_level_data(params, constant_K=0.0, dpsi_ghosted=None):
+    """The reference's set_initial_conditions [+ set_update_psi0(dpsi)] + set_a_coef + set_b_coef + set_rhs on one box:
+    (multigrid_vars [8, nz+6, ny+6, nx+6], rhs, aCoef, bCoef [nz, ny, nx])"""
+    N = tuple(params["N"])
+    dx = params["L"] / N[0]
+    g = (N[2] + 6, N[1] + 6, N[0] + 6)
+    mg = np.zeros((8,) + g)
+    rhs, a, b = (np.zeros((N[2], N[1], N[0])) for _ in range(3))
+    d = None
+    if dpsi_ghosted is not None:
+        d = np.ascontiguousarray(dpsi_ghosted, dtype=np.float64)
+        assert d.shape == g
+    p = to_struct(params)
+    lib().ref_set_level_data(C.byref(p), (C.c_int * 3)(*N), dx, constant_K, None if d is None else d.ctypes.data, mg, rhs, a, b)
+    return mg, rhs, a, b
+
+
+def point_values(params, loc):
+    """(Aij[6] in the order A11 A12 A13 A22 A23 A33, psi_bh, phi) from get_Aij / set_binary_bh_psi / my_phi_function"""
+    p = to_struct(params)
+    A = (C.c_double * 6)()
+    psi, phi = C.c_double(), C.c_double()
+    lib().ref_point_values(C.byref(p), (C.c_double * 3)(*loc), A, C.byref(psi), C.byref(phi))
+    return np.array(A[:]), psi.value, phi.value
+
+
+def m_value(params, phi_here, constant_K):
+    p = to_struct(params)
+    return lib().ref_m_value(C.byref(p), phi_here, constant_K)

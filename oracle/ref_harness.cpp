@@ -1,0 +1,110 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own source-term code: this file is
+// linked with /root/reference/Source/SetLevelData.cpp (which includes Source/SetBinaryBH.H and MyPhiFunction.H), compiled
+// unmodified where it lies, against oracle/ref_shim/chombo_standin.H.  It pins the oracle's restatement of SURVEY rows
+// a18 / a19 (set_initial_conditions, set_rhs, set_a_coef, set_b_coef, set_update_psi0, get_Aij, set_binary_bh_psi,
+// my_phi_function) to the reference's arithmetic.  Not pinned by it: the two Fortran stencils (forwarded below to the C
+// restatement -- there is no Fortran compiler) and everything on the operator path (needs Chombo's AMRPoissonOp).
+#include "SetLevelData.H"   // the reference's prototypes (Source/SetLevelData.H:27-71)
+
+#include "mgic_oracle.h"
+
+const IntVect IntVect::Unit(1, 1, 1), IntVect::Zero(0, 0, 0);
+const RealVect RealVect::Unit(1.0, 1.0, 1.0), RealVect::Zero(0.0, 0.0, 0.0);
+
+// defined in Source/SetBinaryBH.H / MyPhiFunction.H (non-inline, compiled in SetLevelData.cpp's translation unit)
+Real get_bh_radius(RealVect &loc_bh, const Real bh_x_offset);
+Real get_Aij(const int i, const int j, const Real &rbh1, const Real &rbh2, const RealVect &n1, const RealVect &n2,
+             const RealVect &J1, const RealVect &J2, const RealVect &P1, const RealVect &P2, const PoissonParameters &a_params);
+Real set_binary_bh_psi(const RealVect &loc, const PoissonParameters &a_params);
+Real my_phi_function(RealVect loc, Real amplitude, Real wavelength, RealVect L);
+
+// SetLevelDataF.ChF cannot be compiled here: the symbols SetLevelDataF_F.H declares come from the C restatement
+extern "C" void getlaplacianpsif_(CHFp_FRA1(l_of_psi), CHFp_CONST_FRA1(psi), CHFp_CONST_REAL(dx), CHFp_BOX(box)) {
+  orc_getlaplacianpsif(CHFt_FRA1(l_of_psi), CHFt_CONST_FRA1(psi), dx, CHFt_BOX(box));
+}
+extern "C" void getrhogradphif_(CHFp_FRA1(rho_grad_phi), CHFp_CONST_FRA1(phi), CHFp_CONST_REAL(dx), CHFp_BOX(box)) {
+  orc_getrhogradphif(CHFt_FRA1(rho_grad_phi), CHFt_CONST_FRA1(phi), dx, CHFt_BOX(box));
+}
+
+extern "C" {
+
+typedef struct {
+  double G_Newton, phi_amplitude, phi_wavelength;
+  double bh1_bare_mass, bh1_spin, bh1_momentum, bh1_offset;
+  double bh2_bare_mass, bh2_spin, bh2_momentum, bh2_offset;
+  double L[3];
+} ref_params;
+
+static PoissonParameters to_params(const ref_params *p) {
+  PoissonParameters q;
+  q.G_Newton = p->G_Newton; q.phi_amplitude = p->phi_amplitude; q.phi_wavelength = p->phi_wavelength;
+  q.bh1_bare_mass = p->bh1_bare_mass; q.bh1_spin = p->bh1_spin; q.bh1_momentum = p->bh1_momentum; q.bh1_offset = p->bh1_offset;
+  q.bh2_bare_mass = p->bh2_bare_mass; q.bh2_spin = p->bh2_spin; q.bh2_momentum = p->bh2_momentum; q.bh2_offset = p->bh2_offset;
+  q.domainLength = RealVect(p->L[0], p->L[1], p->L[2]);
+  q.alpha = 1.0; q.beta = -1.0;
+  return q;
+}
+
+static void copy_out(const FArrayBox &f, int comp, double *out) {
+  if (!out) return;
+  const Real *s = f.dataPtr(comp);
+  for (long q = 0; q < f.box().numPts(); q++) out[q] = s[q];
+}
+
+// One level, one box of N cells, the reference's ghost widths (Main_PoissonSolver.cpp:79-88: multigrid_vars and dpsi 3
+// ghosts, rhs / aCoef / bCoef none).  set_initial_conditions; then, if dpsi_ghosted is given ((N+6)^3, first index
+// fastest), set_update_psi0 with it; then set_a_coef, set_b_coef, set_rhs (the order of Main_PoissonSolver.cpp:154-160).
+// Outputs (any may be NULL): mgvars 8 x (N+6)^3, rhs / acoef / bcoef N^3.
+int ref_set_level_data(const ref_params *p, const int N[3], double dx, double constant_K, const double *dpsi_ghosted,
+                       double *mgvars, double *rhs, double *acoef, double *bcoef) {
+  PoissonParameters params = to_params(p);
+  Box dom(IntVect(0, 0, 0), IntVect(N[0] - 1, N[1] - 1, N[2] - 1));
+  const IntVect g3(3, 3, 3);
+  LevelData<FArrayBox> vars(dom, NUM_MULTIGRID_VARS, g3), dpsi(dom, 1, g3);
+  LevelData<FArrayBox> r(dom, 1, IntVect::Zero), a(dom, 1, IntVect::Zero), b(dom, 1, IntVect::Zero);
+  RealVect vdx(dx, dx, dx);
+  set_initial_conditions(vars, dpsi, vdx, params);
+  DataIterator dit = vars.dataIterator();
+  dit.begin();
+  if (dpsi_ghosted) {
+    FArrayBox &d = dpsi[dit()];
+    Real *dst = d.dataPtr(0);
+    for (long q = 0; q < d.box().numPts(); q++) dst[q] = dpsi_ghosted[q];
+    Copier none;
+    set_update_psi0(vars, dpsi, none);
+  }
+  set_a_coef(a, vars, params, vdx, constant_K);
+  set_b_coef(b, params, vdx);
+  set_rhs(r, vars, vdx, params, constant_K);
+  if (mgvars)
+    for (int c = 0; c < NUM_MULTIGRID_VARS; c++) copy_out(vars[dit()], c, mgvars + (size_t)c * vars[dit()].box().numPts());
+  copy_out(r[dit()], 0, rhs);
+  copy_out(a[dit()], 0, acoef);
+  copy_out(b[dit()], 0, bcoef);
+  return 0;
+}
+
+// the point functions of Source/SetBinaryBH.H and MyPhiFunction.H at one location (relative to the domain centre)
+void ref_point_values(const ref_params *p, const double loc[3], double Aij[6], double *psi_bh, double *phi) {
+  PoissonParameters params = to_params(p);
+  RealVect x(loc[0], loc[1], loc[2]);
+  RealVect l1 = x, l2 = x;
+  Real r1 = get_bh_radius(l1, params.bh1_offset), r2 = get_bh_radius(l2, params.bh2_offset);
+  RealVect n1(l1[0] / r1, l1[1] / r1, l1[2] / r1), n2(l2[0] / r2, l2[1] / r2, l2[2] / r2);
+  RealVect J1(0.0, 0.0, params.bh1_spin), J2(0.0, 0.0, params.bh2_spin);
+  RealVect P1(0.0, params.bh1_momentum, 0.0), P2(0.0, params.bh2_momentum, 0.0);
+  const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};   // c_A11_0 .. c_A33_0 (MultigridUserVariables.hpp)
+  for (int q = 0; q < 6; q++) Aij[q] = get_Aij(ij[q][0], ij[q][1], r1, r2, n1, n2, J1, J2, P1, P2, params);
+  *psi_bh = set_binary_bh_psi(x, params);
+  *phi = my_phi_function(x, params.phi_amplitude, params.phi_wavelength, params.domainLength);
+}
+
+// set_m_value (Source/SetLevelData.cpp:266-279)
+double ref_m_value(const ref_params *p, double phi_here, double constant_K) {
+  PoissonParameters params = to_params(p);
+  Real m = 0;
+  set_m_value(m, phi_here, params, constant_K);
+  return m;
+}
+
+}  // extern "C"
