@@ -20,6 +20,18 @@ class RefParams(C.Structure):
                 ("L", C.c_double * 3)]
 
 
+class RefPoissonParameters(C.Structure):
+    _fields_ = [("nCells", C.c_int * 3), ("maxGridSize", C.c_int), ("blockFactor", C.c_int), ("bufferSize", C.c_int),
+                ("coefficient_average_type", C.c_int), ("verbosity", C.c_int), ("periodic", C.c_int * 3), ("maxLevel", C.c_int),
+                ("numLevels", C.c_int), ("refRatio0", C.c_int), ("refRatioLast", C.c_int), ("domainLo", C.c_int * 3),
+                ("domainHi", C.c_int * 3), ("domainPeriodic", C.c_int * 3),
+                ("fillRatio", C.c_double), ("refineThresh", C.c_double), ("coarsestDx", C.c_double), ("domainLength", C.c_double * 3),
+                ("probLo", C.c_double * 3), ("probHi", C.c_double * 3), ("alpha", C.c_double), ("beta", C.c_double),
+                ("G_Newton", C.c_double), ("phi_amplitude", C.c_double), ("phi_wavelength", C.c_double),
+                ("bh1_bare_mass", C.c_double), ("bh2_bare_mass", C.c_double), ("bh1_spin", C.c_double), ("bh2_spin", C.c_double),
+                ("bh1_momentum", C.c_double), ("bh2_momentum", C.c_double), ("bh1_offset", C.c_double), ("bh2_offset", C.c_double)]
+
+
 def available():
     return os.path.exists(SO) or os.path.isdir(os.path.join(REFERENCE, "Source"))
 
@@ -49,6 +61,9 @@ def lib():
         L.ref_point_values.restype = None
         L.ref_m_value.argtypes = [C.POINTER(RefParams), C.c_double, C.c_double]
         L.ref_m_value.restype = C.c_double
+        L.ref_get_poisson_parameters.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(RefPoissonParameters),
+                                                 C.c_char_p, C.c_int]
+        L.ref_get_poisson_parameters.restype = C.c_int
         _lib = L
     return _lib
 
@@ -94,3 +109,18 @@ def point_values(params, loc):
 def m_value(params, phi_here, constant_K):
     p = to_struct(params)
     return lib().ref_m_value(C.byref(p), phi_here, constant_K)
+
+
+def get_poisson_parameters(path, overrides=()):
+    """The reference's getPoissonParameters (Source/PoissonParameters.cpp:26-131) on an input file + 'key = value' overrides:
+    dict of the PoissonParameters members; raises RuntimeError with the MayDay / ParmParse message."""
+    out = RefPoissonParameters()
+    err = C.create_string_buffer(512)
+    ov = (C.c_char_p * max(len(overrides), 1))(*[o.encode() for o in overrides])
+    if lib().ref_get_poisson_parameters(str(path).encode(), len(overrides), ov, C.byref(out), err, 512):
+        raise RuntimeError(err.value.decode())
+    d = {}
+    for k, t in RefPoissonParameters._fields_:
+        v = getattr(out, k)
+        d[k] = list(v) if hasattr(v, "__len__") else v
+    return d

@@ -1,12 +1,14 @@
-// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own source-term code: this file is
-// linked with /root/reference/Source/SetLevelData.cpp (which includes Source/SetBinaryBH.H and MyPhiFunction.H), compiled
-// unmodified where it lies, against oracle/ref_shim/chombo_standin.H.  It pins the oracle's restatement of SURVEY rows
+// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own source-term and parameter code: this
+// file is linked with /root/reference/Source/SetLevelData.cpp (which includes Source/SetBinaryBH.H and MyPhiFunction.H) and
+// /root/reference/Source/PoissonParameters.cpp, compiled unmodified where they lie, against oracle/ref_shim/chombo_standin.H.  It pins the oracle's restatement of SURVEY rows
 // a18 / a19 (set_initial_conditions, set_rhs, set_a_coef, set_b_coef, set_update_psi0, get_Aij, set_binary_bh_psi,
 // my_phi_function) to the reference's arithmetic.  Not pinned by it: the two Fortran stencils (forwarded below to the C
 // restatement -- there is no Fortran compiler) and everything on the operator path (needs Chombo's AMRPoissonOp).
 #include "SetLevelData.H"   // the reference's prototypes (Source/SetLevelData.H:27-71)
 
 #include "mgic_oracle.h"
+
+#include <cstdio>
 
 const IntVect IntVect::Unit(1, 1, 1), IntVect::Zero(0, 0, 0);
 const RealVect RealVect::Unit(1.0, 1.0, 1.0), RealVect::Zero(0.0, 0.0, 0.0);
@@ -105,6 +107,46 @@ double ref_m_value(const ref_params *p, double phi_here, double constant_K) {
   Real m = 0;
   set_m_value(m, phi_here, params, constant_K);
   return m;
+}
+
+// getPoissonParameters (Source/PoissonParameters.cpp:26-131, compiled unmodified) on an input file in params.txt's format
+// plus `key = value` override lines (the command line of Main_PoissonSolver.cpp:272).  Returns 0, or 1 with the
+// MayDay::Error / ParmParse message in err.
+typedef struct {
+  int nCells[3], maxGridSize, blockFactor, bufferSize, coefficient_average_type, verbosity, periodic[3], maxLevel, numLevels;
+  int refRatio0, refRatioLast, domainLo[3], domainHi[3], domainPeriodic[3];
+  double fillRatio, refineThresh, coarsestDx, domainLength[3], probLo[3], probHi[3], alpha, beta, G_Newton;
+  double phi_amplitude, phi_wavelength, bh1_bare_mass, bh2_bare_mass, bh1_spin, bh2_spin, bh1_momentum, bh2_momentum;
+  double bh1_offset, bh2_offset;
+} ref_poisson_parameters;
+
+int ref_get_poisson_parameters(const char *file, int noverrides, const char *const *overrides, ref_poisson_parameters *o,
+                               char *err, int errlen) {
+  try {
+    if (!ParmParse::standin_load(file)) throw std::runtime_error(std::string("cannot open ") + file);
+    for (int q = 0; q < noverrides; q++) ParmParse::standin_add_line(overrides[q]);
+    PoissonParameters p;
+    getPoissonParameters(p);
+    for (int d = 0; d < 3; d++) {
+      o->nCells[d] = p.nCells[d]; o->periodic[d] = p.periodic[d];
+      o->domainLo[d] = p.coarsestDomain.domainBox().lo[d]; o->domainHi[d] = p.coarsestDomain.domainBox().hi[d];
+      o->domainPeriodic[d] = p.coarsestDomain.isPeriodic(d);
+      o->domainLength[d] = p.domainLength[d]; o->probLo[d] = p.probLo[d]; o->probHi[d] = p.probHi[d];
+    }
+    o->maxGridSize = p.maxGridSize; o->blockFactor = p.blockFactor; o->bufferSize = p.bufferSize;
+    o->coefficient_average_type = p.coefficient_average_type; o->verbosity = p.verbosity;
+    o->maxLevel = p.maxLevel; o->numLevels = p.numLevels;
+    o->refRatio0 = p.refRatio.empty() ? -1 : p.refRatio.front(); o->refRatioLast = p.refRatio.empty() ? -1 : p.refRatio.back();
+    o->fillRatio = p.fillRatio; o->refineThresh = p.refineThresh; o->coarsestDx = p.coarsestDx;
+    o->alpha = p.alpha; o->beta = p.beta; o->G_Newton = p.G_Newton;
+    o->phi_amplitude = p.phi_amplitude; o->phi_wavelength = p.phi_wavelength;
+    o->bh1_bare_mass = p.bh1_bare_mass; o->bh2_bare_mass = p.bh2_bare_mass; o->bh1_spin = p.bh1_spin; o->bh2_spin = p.bh2_spin;
+    o->bh1_momentum = p.bh1_momentum; o->bh2_momentum = p.bh2_momentum; o->bh1_offset = p.bh1_offset; o->bh2_offset = p.bh2_offset;
+    return 0;
+  } catch (const std::exception &e) {
+    if (err && errlen > 0) { std::snprintf(err, errlen, "%s", e.what()); }
+    return 1;
+  }
 }
 
 }  // extern "C"

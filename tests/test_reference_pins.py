@@ -106,3 +106,90 @@ def test_oracle_source_terms_equal_the_reference(over):
     mg2, rhs2, a2, _ = pyref.set_level_data(o.params, dpsi_ghosted=d)
     assert np.array_equal(o.get_ghosted("MGVAR0", 3, comp=0), mg2[0])
     assert np.array_equal(o.get("RHS"), rhs2) and np.array_equal(o.get("A"), a2)
+
+
+# ---- getPoissonParameters (Source/PoissonParameters.cpp:26-131, compiled unmodified) against the two readers of this repo
+REF_PARAMS = os.path.join(pyref.REFERENCE, "params.txt")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+PARAM_CASES = {
+    "params.txt": (),
+    "single_level_512": ("max_level = 0", "N = 512 512 512", "max_grid_size = 32"),
+    "noncubic": ("N = 32 48 64", "L = 50.0", "max_level = 2", "coefficient_average_type = arithmetic"),
+    "periodic": ("is_periodic = 1", "verbosity = 5"),
+}
+
+
+def host_mirror_params(path, overrides, tmp_path_factory):
+    """the C++ host mirror's getPoissonParameters (host/PoissonParameters.H) through a small probe program"""
+    import subprocess
+    exe = str(tmp_path_factory.getbasetemp() / "params_probe")
+    if not os.path.exists(exe):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                               "-I" + os.path.join(ROOT, "mg_ic_code_b200", "host"), os.path.join(HERE, "data", "params_probe.cpp"),
+                               "-L" + os.path.join(ROOT, "mg_ic_code_b200", "lib"), "-lmgic_b200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "mg_ic_code_b200", "lib"), "-o", exe])
+    r = subprocess.run([exe, path] + [o.replace(" = ", "=", 1) for o in overrides], capture_output=True, text=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+@live
+@pytest.mark.skipif(not os.path.exists(REF_PARAMS), reason="needs the reference's params.txt")
+@pytest.mark.parametrize("case", list(PARAM_CASES))
+def test_parameter_readers_agree_with_the_reference(case, tmp_path_factory):
+    import mg_ic_code_b200 as m
+    over = PARAM_CASES[case]
+    ref = pyref.get_poisson_parameters(REF_PARAMS, over)
+    # what the reference derives (PoissonParameters.cpp:64-85,110-128)
+    assert ref["numLevels"] == ref["maxLevel"] + 1 and ref["refRatio0"] == ref["refRatioLast"] == 2
+    assert ref["domainLo"] == [0, 0, 0] and ref["domainHi"] == [n - 1 for n in ref["nCells"]]
+    assert ref["domainLength"] == [ref["coarsestDx"] * n for n in ref["nCells"]] and ref["probHi"] == ref["domainLength"]
+    # the C++ host mirror (what the driver poisson_solver_b200 runs)
+    rc, out, err = host_mirror_params(REF_PARAMS, over, tmp_path_factory)
+    assert rc == 0, err
+    host = json.loads(out.strip().splitlines()[-1])
+    for k, v in host.items():
+        if k == "nRefRatio":
+            assert v == ref["numLevels"]
+        elif k == "periodic":
+            assert [v] * 3 == ref["periodic"] == ref["domainPeriodic"]
+        else:
+            assert v == ref[k], k
+    # the Python reader used by the tests and bench.py
+    P = m.read_params(REF_PARAMS, [o.replace(" = ", "=", 1) for o in over])
+    assert list(P.N) == ref["nCells"] and P.L / P.N[0] == ref["coarsestDx"]
+    assert (P.max_level, P.block_factor, P.max_grid_size, P.is_periodic) == (ref["maxLevel"], ref["blockFactor"], ref["maxGridSize"],
+                                                                             ref["periodic"][0])
+    assert P.coefficient_average_type == ref["coefficient_average_type"] and P.verbosity == ref["verbosity"]
+    for k in ("alpha", "beta", "G_Newton", "phi_amplitude", "phi_wavelength", "bh1_bare_mass", "bh2_bare_mass", "bh1_spin",
+              "bh2_spin", "bh1_momentum", "bh2_momentum", "bh1_offset", "bh2_offset"):
+        assert getattr(P, k) == ref[k], k
+
+
+@live
+@pytest.mark.skipif(not os.path.exists(REF_PARAMS), reason="needs the reference's params.txt")
+def test_parameter_errors_are_the_references(tmp_path, tmp_path_factory):
+    """a missing required key and a bad coefficient_average_type stop the reference (MayDay::Error / ParmParse) and the
+    host mirror alike; an absent coefficient_average_type is the reference's "bogus default" -1"""
+    import mg_ic_code_b200 as m
+    with pytest.raises(RuntimeError, match="bad coefficient_average_type in input"):
+        pyref.get_poisson_parameters(REF_PARAMS, ("coefficient_average_type = geometric",))
+    rc, _, err = host_mirror_params(REF_PARAMS, ("coefficient_average_type = geometric",), tmp_path_factory)
+    assert rc != 0 and "bad coefficient_average_type in input" in err
+    with pytest.raises(m.MgicError, match="bad coefficient_average_type in input"):
+        m.read_params(REF_PARAMS, ["coefficient_average_type=geometric"])
+    text = open(REF_PARAMS).read()
+    for key in ("alpha", "bh2_offset", "max_level", "L", "fill_ratio", "buffer_size", "refine_threshold", "is_periodic"):
+        cut = tmp_path / f"no_{key}.txt"
+        cut.write_text("\n".join(l for l in text.splitlines() if not l.split("=")[0].strip() == key))
+        with pytest.raises(RuntimeError, match=key):
+            pyref.get_poisson_parameters(cut)
+        rc, _, err = host_mirror_params(str(cut), (), tmp_path_factory)
+        assert rc != 0 and key in err, key
+    none = tmp_path / "no_avg.txt"
+    none.write_text("\n".join(l for l in text.splitlines() if not l.startswith("coefficient_average_type")))
+    assert pyref.get_poisson_parameters(none)["coefficient_average_type"] == -1
+    rc, out, _ = host_mirror_params(str(none), (), tmp_path_factory)
+    assert rc == 0 and json.loads(out.strip().splitlines()[-1])["coefficient_average_type"] == -1
+    assert m.read_params(str(none)).coefficient_average_type == -1
