@@ -64,6 +64,21 @@ def lib():
         L.ref_get_poisson_parameters.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(RefPoissonParameters),
                                                  C.c_char_p, C.c_int]
         L.ref_get_poisson_parameters.restype = C.c_int
+        i3 = C.c_int * 3
+        L.ref_op_create.argtypes = [i3, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double]
+        L.ref_op_create.restype = C.c_void_p
+        L.ref_op_destroy.argtypes = [C.c_void_p]
+        L.ref_op_num_boxes.argtypes = [C.c_void_p]
+        L.ref_op_set.argtypes = [C.c_void_p, C.c_int, nd]
+        L.ref_op_get.argtypes = [C.c_void_p, C.c_int, nd]
+        L.ref_op_get_coarse_residual.argtypes = [C.c_void_p, nd]
+        L.ref_op_relax.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_op_relax_status.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_op_relax_status_msg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        for name in ("ref_op_residual", "ref_op_apply"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+        for name in ("ref_op_restrict", "ref_op_precond"):
+            getattr(L, name).argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -124,3 +139,64 @@ def get_poisson_parameters(path, overrides=()):
         v = getattr(out, k)
         d[k] = list(v) if hasattr(v, "__len__") else v
     return d
+
+
+class ReferenceOperator:
+    """The reference's VariableCoeffPoissonOperator (Source/VariableCoeffPoissonOperator.cpp, compiled unmodified) on one level
+    that covers its domain, in boxes of max_grid_size, with the reference's ParseBC (Source/SetBCs.cpp) as boundary
+    function.  Inner loops: the C restatement of the .ChF kernels (no Fortran compiler); base class and containers:
+    oracle/ref_shim/chombo_standin.H.  Fields E (dpsi, one ghost layer), R (rhs), A, B as arrays [k, j, i]."""
+    FIELD = dict(E=0, R=1, A=2, B=3, LAMBDA=4, TMP=5)
+
+    def __init__(self, params):
+        """params: the oracle's parameter dict"""
+        self.L = lib()
+        N = tuple(params["N"])
+        i3 = C.c_int * 3
+        self.shape = (N[2], N[1], N[0])
+        self.h = self.L.ref_op_create(i3(*N), params["max_grid_size"], params["L"] / N[0], params["alpha"], params["beta"],
+                                      i3(*params["bc_lo"]), i3(*params["bc_hi"]), params["bc_value"])
+
+    def close(self):
+        if self.h:
+            self.L.ref_op_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_boxes(self):
+        return self.L.ref_op_num_boxes(self.h)
+
+    def set(self, field, arr):
+        assert self.L.ref_op_set(self.h, self.FIELD[field], np.ascontiguousarray(arr, dtype=np.float64)) == 0
+
+    def get(self, field):
+        out = np.empty(self.shape)
+        assert self.L.ref_op_get(self.h, self.FIELD[field], out) == 0
+        return out
+
+    def relax(self, iterations, mode=1):
+        """AMRPoissonOp::relax: mode 1 levelGSRB (Chombo's default), 4 levelJacobi"""
+        self.L.ref_op_relax(self.h, iterations, mode)
+
+    def residual(self, homogeneous):
+        self.L.ref_op_residual(self.h, int(homogeneous))
+        return self.get("TMP")
+
+    def apply(self, homogeneous):
+        self.L.ref_op_apply(self.h, int(homogeneous))
+        return self.get("TMP")
+
+    def restrict(self):
+        self.L.ref_op_restrict(self.h)
+        out = np.empty(tuple(s // 2 for s in self.shape))
+        self.L.ref_op_get_coarse_residual(self.h, out)
+        return out
+
+    def precond(self):
+        self.L.ref_op_precond(self.h)

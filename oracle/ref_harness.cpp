@@ -5,11 +5,13 @@
 // my_phi_function) to the reference's arithmetic.  Not pinned by it: the two Fortran stencils (forwarded below to the C
 // restatement -- there is no Fortran compiler) and everything on the operator path (needs Chombo's AMRPoissonOp).
 #include "SetLevelData.H"   // the reference's prototypes (Source/SetLevelData.H:27-71)
+#include "SetBCs.H"         // ParseBC, GlobalBCRS (Source/SetBCs.H)
 
 #include "mgic_oracle.h"
 
 #include <cstdio>
 
+int AMRPoissonOp::s_relaxMode = 1;
 const IntVect IntVect::Unit(1, 1, 1), IntVect::Zero(0, 0, 0);
 const RealVect RealVect::Unit(1.0, 1.0, 1.0), RealVect::Zero(0.0, 0.0, 0.0);
 
@@ -28,7 +30,145 @@ extern "C" void getrhogradphif_(CHFp_FRA1(rho_grad_phi), CHFp_CONST_FRA1(phi), C
   orc_getrhogradphif(CHFt_FRA1(rho_grad_phi), CHFt_CONST_FRA1(phi), dx, CHFt_BOX(box));
 }
 
+// VariableCoeffPoissonOperatorF.ChF likewise: the symbols VariableCoeffPoissonOperatorF_F.H declares, from the C restatement
+extern "C" void gsrbhelmholtzvc3d_(CHFp_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_BOX(region), CHFp_CONST_REAL(dx), CHFp_CONST_REAL(alpha),
+                                   CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_CONST_FRA(lambda),
+                                   CHFp_CONST_INT(redBlack)) {
+  orc_gsrbhelmholtzvc3d(CHFt_FRA(dpsi), CHFt_CONST_FRA(rhs), CHFt_BOX(region), dx, alpha, CHFt_CONST_FRA(aCoef), beta,
+                        CHFt_CONST_FRA(bCoef), CHFt_CONST_FRA(lambda), redBlack);
+}
+extern "C" void vccomputeop3d_(CHFp_FRA(lofdpsi), CHFp_CONST_FRA(dpsi), CHFp_CONST_REAL(alpha), CHFp_CONST_FRA(aCoef),
+                               CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region), CHFp_CONST_REAL(dx)) {
+  orc_vccomputeop3d(CHFt_FRA(lofdpsi), CHFt_CONST_FRA(dpsi), alpha, CHFt_CONST_FRA(aCoef), beta, CHFt_CONST_FRA(bCoef),
+                    CHFt_BOX(region), dx);
+}
+extern "C" void vccomputeres3d_(CHFp_FRA(res), CHFp_CONST_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_CONST_REAL(alpha),
+                                CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region),
+                                CHFp_CONST_REAL(dx)) {
+  orc_vccomputeres3d(CHFt_FRA(res), CHFt_CONST_FRA(dpsi), CHFt_CONST_FRA(rhs), alpha, CHFt_CONST_FRA(aCoef), beta,
+                     CHFt_CONST_FRA(bCoef), CHFt_BOX(region), dx);
+}
+extern "C" void restrictresvc3d_(CHFp_FRA(res), CHFp_CONST_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_CONST_REAL(alpha),
+                                 CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region),
+                                 CHFp_CONST_REAL(dx)) {
+  orc_restrictresvc3d(CHFt_FRA(res), CHFt_CONST_FRA(dpsi), CHFt_CONST_FRA(rhs), alpha, CHFt_CONST_FRA(aCoef), beta,
+                      CHFt_CONST_FRA(bCoef), CHFt_BOX(region), dx);
+}
+
+// ---- the reference's operator class (Source/VariableCoeffPoissonOperator.{H,cpp}, compiled unmodified) on one level that
+// covers its domain, split into boxes of max_grid_size; physical BCs by the reference's ParseBC (Source/SetBCs.cpp, compiled
+// unmodified) reading bc_lo / bc_hi / bc_value from the ParmParse table.  AMRPoissonOp::define is Chombo's, so the harness
+// sets the members define would set.
+class RefOp : public VariableCoeffPoissonOperator {
+public:
+  DisjointBoxLayout grids, coarseGrids;
+  LevelData<FArrayBox> e, r, tmp, resCoarse;
+  IntVect n;
+  RefOp(const int N[3], int maxGrid, Real dx, Real alpha, Real beta) : n(N[0], N[1], N[2]) {
+    std::vector<Box> boxes, cboxes;
+    for (int k = 0; k < N[2]; k += maxGrid)
+      for (int j = 0; j < N[1]; j += maxGrid)
+        for (int i = 0; i < N[0]; i += maxGrid) {
+          Box b(IntVect(i, j, k), IntVect(std::min(i + maxGrid, N[0]) - 1, std::min(j + maxGrid, N[1]) - 1, std::min(k + maxGrid, N[2]) - 1));
+          boxes.push_back(b);
+          cboxes.push_back(coarsen(b, 2));
+        }
+    grids = DisjointBoxLayout(boxes);
+    coarseGrids = DisjointBoxLayout(cboxes);
+    m_dx = dx; m_dxCrse = 2 * dx;
+    m_domain = ProblemDomain(Box(IntVect::Zero, IntVect(N[0] - 1, N[1] - 1, N[2] - 1)));
+    m_bc = BCHolder(ParseBC);
+    RefCountedPtr<LevelData<FArrayBox>> a(new LevelData<FArrayBox>(grids, 1, IntVect::Zero));
+    RefCountedPtr<LevelData<FArrayBox>> b(new LevelData<FArrayBox>(grids, 1, IntVect::Zero));
+    setCoefs(a, b, alpha, beta);
+    e.define(grids, 1, IntVect::Unit);
+    r.define(grids, 1, IntVect::Zero);
+    tmp.define(grids, 1, IntVect::Zero);
+    resCoarse.define(coarseGrids, 1, IntVect::Zero);
+    computeLambda();
+  }
+  LevelData<FArrayBox> *field(int which) {
+    switch (which) {
+      case ORC_F_E: return &e;
+      case ORC_F_R: return &r;
+      case ORC_F_A: return &*m_aCoef;
+      case ORC_F_B: return &*m_bCoef;
+      case ORC_F_LAMBDA: return &m_lambda;
+      case ORC_F_TMP: return &tmp;
+      default: return nullptr;
+    }
+  }
+};
+
+static void level_copy(LevelData<FArrayBox> &ld, double *out, const double *in, const IntVect &n) {
+  for (DataIterator dit = ld.dataIterator(); dit.ok(); ++dit) {
+    const Box &b = ld.disjointBoxLayout()[dit()];
+    for (BoxIterator bit(b); bit.ok(); ++bit) {
+      const IntVect &iv = bit();
+      const size_t q = iv[0] + (size_t)n[0] * (iv[1] + (size_t)n[1] * iv[2]);
+      if (in) ld[dit](iv, 0) = in[q];
+      else out[q] = ld[dit](iv, 0);
+    }
+  }
+}
+
 extern "C" {
+
+// bcs: bc_lo[3], bc_hi[3] (0 Dirichlet, 1 Neumann), bc_value -- handed to ParseBC / ParseValue through the ParmParse table
+void *ref_op_create(const int N[3], int max_grid_size, double dx, double alpha, double beta, const int bc_lo[3], const int bc_hi[3],
+                    double bc_value) {
+  char line[128];
+  std::snprintf(line, sizeof line, "bc_lo = %d %d %d", bc_lo[0], bc_lo[1], bc_lo[2]); ParmParse::standin_add_line(line);
+  std::snprintf(line, sizeof line, "bc_hi = %d %d %d", bc_hi[0], bc_hi[1], bc_hi[2]); ParmParse::standin_add_line(line);
+  std::snprintf(line, sizeof line, "bc_value = %.17g", bc_value); ParmParse::standin_add_line(line);
+  GlobalBCRS::s_areBCsParsed = false;      // ParseBC caches bc_lo / bc_hi in statics (SetBCs.cpp:53-58)
+  return new RefOp(N, max_grid_size, dx, alpha, beta);
+}
+void ref_op_destroy(void *h) { delete (RefOp *)h; }
+int ref_op_num_boxes(void *h) { return ((RefOp *)h)->grids.size(); }
+// fields as global ghost-free arrays (first index fastest); ids as in mgic_oracle.h (ORC_F_E, _R, _A, _B, _LAMBDA, _TMP)
+int ref_op_set(void *h, int field, const double *in) {
+  RefOp *o = (RefOp *)h;
+  LevelData<FArrayBox> *ld = o->field(field);
+  if (!ld || field == ORC_F_LAMBDA) return 1;
+  level_copy(*ld, nullptr, in, o->n);
+  if (field == ORC_F_A || field == ORC_F_B) o->setCoefs(o->m_aCoef, o->m_bCoef, o->m_alpha, o->m_beta);   // "if you change this call resetLambda()"
+  return 0;
+}
+int ref_op_get(void *h, int field, double *out) {
+  RefOp *o = (RefOp *)h;
+  LevelData<FArrayBox> *ld = o->field(field);
+  if (!ld) return 1;
+  if (field == ORC_F_LAMBDA) o->resetLambda();
+  level_copy(*ld, out, nullptr, o->n);
+  return 0;
+}
+void ref_op_get_coarse_residual(void *h, double *out) {
+  RefOp *o = (RefOp *)h;
+  level_copy(o->resCoarse, out, nullptr, IntVect(o->n[0] / 2, o->n[1] / 2, o->n[2] / 2));
+}
+void ref_op_relax(void *h, int iterations, int relax_mode) {       // AMRPoissonOp::relax -> levelGSRB (1) / levelJacobi (4)
+  RefOp *o = (RefOp *)h;
+  AMRPoissonOp::s_relaxMode = relax_mode;
+  o->relax(o->e, o->r, iterations);
+  AMRPoissonOp::s_relaxMode = 1;
+}
+// same, reporting a MayDay::Abort / Error instead of unwinding through C: 0 ok, 1 aborted (message in msg)
+int ref_op_relax_status_msg(void *h, int iterations, int relax_mode, char *msg, int msglen) {
+  try {
+    ref_op_relax(h, iterations, relax_mode);
+    return 0;
+  } catch (const std::exception &e) {
+    AMRPoissonOp::s_relaxMode = 1;
+    if (msg && msglen > 0) std::snprintf(msg, msglen, "%s", e.what());
+    return 1;
+  }
+}
+int ref_op_relax_status(void *h, int iterations, int relax_mode) { return ref_op_relax_status_msg(h, iterations, relax_mode, nullptr, 0); }
+void ref_op_residual(void *h, int homogeneous) { RefOp *o = (RefOp *)h; o->residualI(o->tmp, o->e, o->r, homogeneous != 0); }
+void ref_op_apply(void *h, int homogeneous) { RefOp *o = (RefOp *)h; o->applyOpI(o->tmp, o->e, homogeneous != 0); }
+void ref_op_restrict(void *h) { RefOp *o = (RefOp *)h; o->restrictResidual(o->resCoarse, o->e, o->r); }
+void ref_op_precond(void *h) { RefOp *o = (RefOp *)h; o->preCond(o->e, o->r); }
 
 typedef struct {
   double G_Newton, phi_amplitude, phi_wavelength;

@@ -193,3 +193,65 @@ def test_parameter_errors_are_the_references(tmp_path, tmp_path_factory):
     rc, out, _ = host_mirror_params(str(none), (), tmp_path_factory)
     assert rc == 0 and json.loads(out.strip().splitlines()[-1])["coefficient_average_type"] == -1
     assert m.read_params(str(none)).coefficient_average_type == -1
+
+
+# ---- the operator class: Source/VariableCoeffPoissonOperator.cpp + Source/SetBCs.cpp, compiled unmodified (rows a6 - a12, a14).
+# Pinned: the reference's own orchestration -- which ghost cells ParseBC fills with what, the exchange, the per-colour
+# sequence of levelGSRB, residualI / applyOpI / restrictResidual (shifted bounds, zeroed coarse residual) / preCond /
+# levelJacobi, the lambda formula.  NOT pinned by this: the .ChF kernels (the C restatement is linked in their place) and
+# Chombo's DiriBC / NeumBC / exchange (restated in the stand-in).
+OP_CASES = {
+    "c16": dict(N=(16, 16, 16), max_grid_size=8, L=40.0),
+    "one_box": dict(N=(8, 8, 8), max_grid_size=8, L=10.0),
+    "neumann_inhomogeneous": dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1), bc_value=0.25),
+    "all_neumann": dict(N=(16, 16, 16), max_grid_size=4, L=40.0, bc_lo=(1, 1, 1), bc_hi=(1, 1, 1), bc_value=-0.5),
+    "wide_boxes16": dict(N=(48, 16, 32), max_grid_size=16, L=100.0, alpha=0.7, beta=-1.3),
+}
+
+
+@live
+@pytest.mark.parametrize("case", list(OP_CASES))
+def test_oracle_operator_equals_the_reference_class(case):
+    o = Oracle(**OP_CASES[case])
+    o.setup()
+    R = pyref.ReferenceOperator(o.params)
+    n = o.params["N"]
+    assert R.num_boxes == int(np.prod([-(-n[d] // o.params["max_grid_size"]) for d in range(3)]))
+    rng = np.random.default_rng(7)
+    e, r = rng.standard_normal(R.shape), rng.standard_normal(R.shape)
+    b = 1.0 + 0.3 * rng.random(R.shape)                 # a genuinely variable bCoef (the reference's is 1)
+    for bcoef in (o.get("B"), b):
+        R.set("A", o.get("A")); R.set("B", bcoef)
+        o.set("B", bcoef)
+        assert np.array_equal(R.get("LAMBDA"), o.get("LAMBDA"))          # resetLambda (:220-249): bCoef does not enter
+        for homog in (True, False):
+            o.set("E", e); o.set("R", r); R.set("E", e); R.set("R", r)
+            assert np.array_equal(R.residual(homog), o.residual(0, homog)), ("residualI", homog)
+            assert np.array_equal(R.apply(homog), o.apply(0, homog)), ("applyOpI", homog)
+        o.relax(0, 1); R.relax(1)
+        assert np.array_equal(R.get("E"), o.get("E")), "levelGSRB"
+        o.relax(0, 3); R.relax(3)
+        assert np.array_equal(R.get("E"), o.get("E")), "relax(3)"
+        o.restrict(0)
+        assert np.array_equal(R.restrict(), o.get("R", 1)), "restrictResidual"
+        o.precond(0); R.precond()
+        assert np.array_equal(R.get("E"), o.get("E")), "preCond"
+        # levelJacobi (:360-385), reached through AMRPoissonOp::relax with s_relaxMode = 4: the expression the GPU test of
+        # mgic_op_level_jacobi checks against (test_gpu_parity.py::test_level_jacobi)
+        o.set("E", e); o.set("R", r); R.set("E", e); R.set("R", r)
+        R.relax(1, mode=4)
+        assert np.array_equal(R.get("E"), e + 0.5 * (o.residual(0, True) * o.get("LAMBDA"))), "levelJacobi"
+
+
+@live
+def test_reference_operator_aborts_like_the_reference():
+    """the relaxation modes the reference does not implement stop with MayDay::Abort (VariableCoeffPoissonOperator.cpp:334-358)"""
+    import ctypes as C
+    o = Oracle(**OP_CASES["one_box"])
+    o.setup()
+    R = pyref.ReferenceOperator(o.params)
+    assert R.L.ref_op_relax_status(R.h, 1, 1) == 0
+    for mode in (0, 2, 3, 5):
+        msg = C.create_string_buffer(256)
+        assert R.L.ref_op_relax_status_msg(R.h, 1, mode, msg, 256) == 1
+        assert b"Not implemented" in msg.value
