@@ -8,11 +8,11 @@
  * "reference CPU path" (OpenMP over boxes == the reference's one-MPI-rank-per
  * -core box parallelism, jobscript.pbs:3,13).
  *
- * PARITY (see mgic_oracle.h): the source-term functions are pinned bit for bit
- * to the reference's own code (oracle/_ref); the operator path is UNPINNED -- no
- * golden vectors exist upstream and it cannot be built here.  Everything tagged
- * [Chombo] restates Chombo 3.2 (GNUmakefile:12), which is not under
- * /root/reference.
+ * PARITY (see mgic_oracle.h): source terms, parameters, ParseBC, the operator
+ * class's orchestration and the factory are pinned bit for bit to the reference's
+ * own C++ (oracle/_ref); UNPINNED are the .ChF kernels' arithmetic (no Fortran
+ * compiler) and everything tagged [Chombo], which restates Chombo 3.2
+ * (GNUmakefile:12) -- not under /root/reference -- from its published algorithm.
  *
  * Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp (see Makefile).
  * -ffp-contract=off keeps the source evaluation order (no FMA contraction) so

@@ -6,24 +6,27 @@
  * reference legs may load this library, and only as the checker / the timed
  * CPU arm.  The product (mg_ic_code_b200/) never links, imports or executes it.
  *
- * PARITY: PINNED TO THE REFERENCE'S OWN CODE for the source terms (SURVEY rows
- * a18 / a19: set_initial_conditions, set_rhs, set_a_coef, set_b_coef,
- * set_update_psi0, get_Aij, set_binary_bh_psi, my_phi_function) -- the
- * reference's Source/SetLevelData.cpp + SetBinaryBH.H + MyPhiFunction.H compile
- * unmodified against a stand-in for the Chombo containers (oracle/_ref, Makefile
- * target `ref`) and this oracle reproduces them bit for bit
- * (tests/test_reference_pins.py, tests/golden/reference_sources_16.npz).
- * PARITY UNPINNED for the operator path: the reference ships no tests and no
- * golden vectors, and VariableCoeffPoissonOperator cannot be built here (needs
- * Chombo 3.2's AMRPoissonOp + a Fortran compiler for the .ChF kernels + MPI,
- * none present).  There this oracle is a line-faithful restatement of the
- * reference sources cited at each function, plus a restatement of the
- * Chombo 3.2 control flow the path leans on (MultiGrid::cycle,
- * BiCGStabSolver::solve, DiriBC/NeumBC, CoarseAverage, FORT_PROLONG), which is
- * NOT vendored under /root/reference and is restated from its published
- * algorithm.  Its own pins there are the known-answer tests in tests/ (trivial
- * KAT, trace-free KAT, manufactured solution, decomposition invariance) and an
- * independent numpy twin (tests/np_twin.py).
+ * PARITY.  The reference's own C++ compiles unmodified against a stand-in for
+ * the Chombo API it touches (oracle/_ref, Makefile target `ref`:
+ * SetLevelData.cpp + SetBinaryBH.H + MyPhiFunction.H, PoissonParameters.cpp,
+ * SetBCs.cpp, VariableCoeffPoissonOperator.cpp,
+ * VariableCoeffPoissonOperatorFactory.cpp), and this oracle reproduces it BIT FOR
+ * BIT (tests/test_reference_pins.py, tests/golden/reference_sources_16.npz):
+ *   PINNED to the reference's code: the source terms, the
+ *   parameter block, ParseBC's dispatch (a14), the operator class's orchestration
+ *   -- levelGSRB, residualI, applyOpI, restrictResidual, preCond, levelJacobi,
+ *   lambda (a6 - a12) -- and the factory's MG depth limit and coefficient
+ *   coarsening (a17).
+ *   UNPINNED: the arithmetic of the six .ChF kernels (no Fortran compiler: the
+ *   reference's operator is linked against THIS file's restatement of them, which
+ *   follows the .ChF line by line) and everything that is Chombo 3.2's, which is
+ *   not vendored under /root/reference and is restated from its published
+ *   algorithm: DiriBC/NeumBC, exchange, CoarseAverage, FORT_PROLONG,
+ *   MultiGrid::cycle, BiCGStabSolver::solve, AMRMultiGrid, MultilevelLinearOp,
+ *   QuadCFInterp.  The reference ships no tests and no golden vectors.  Pins
+ *   there: the known-answer tests in tests/ (trivial KAT, trace-free KAT,
+ *   manufactured solution, decomposition invariance) and an independent numpy
+ *   twin (tests/np_twin.py).
  */
 #ifndef MGIC_ORACLE_H
 #define MGIC_ORACLE_H

@@ -79,6 +79,14 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         for name in ("ref_op_restrict", "ref_op_precond"):
             getattr(L, name).argtypes = [C.c_void_p]
+        L.ref_factory_create.argtypes = [i3, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, nd, nd]
+        L.ref_factory_create.restype = C.c_void_p
+        L.ref_factory_destroy.argtypes = [C.c_void_p]
+        L.ref_factory_depths.argtypes = [C.c_void_p]
+        L.ref_factory_average_type.argtypes = [C.c_void_p]
+        L.ref_factory_level.argtypes = [C.c_void_p, C.c_int, i3, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_factory_level.restype = None
+        L.ref_factory_get.argtypes = [C.c_void_p, C.c_int, C.c_int, nd]
         _lib = L
     return _lib
 
@@ -200,3 +208,42 @@ class ReferenceOperator:
 
     def precond(self):
         self.L.ref_op_precond(self.h)
+
+
+class ReferenceFactory:
+    """The reference's VariableCoeffPoissonOperatorFactory (Source/VariableCoeffPoissonOperatorFactory.cpp, compiled
+    unmodified), built by defineOperatorFactory (what Main_PoissonSolver.cpp:163-166 calls) on one AMR level, and asked for
+    MGnewOp(depth) until it returns NULL (what MultiGrid::define does).  [Chombo] CoarseAverage / coarsenable / s_maxCoarse
+    are the stand-in's restatements."""
+
+    def __init__(self, params, aCoef, bCoef, coefficient_average_type=None):
+        self.L = lib()
+        N = tuple(params["N"])
+        t = params["coefficient_average_type"] if coefficient_average_type is None else coefficient_average_type
+        self.h = self.L.ref_factory_create((C.c_int * 3)(*N), params["max_grid_size"], params["L"] / N[0], params["alpha"], params["beta"],
+                                           t, np.ascontiguousarray(aCoef, dtype=np.float64), np.ascontiguousarray(bCoef, dtype=np.float64))
+        self.depths = self.L.ref_factory_depths(self.h)
+        self.average_type = self.L.ref_factory_average_type(self.h)
+
+    def level(self, depth):
+        """((nx, ny, nz), dx, number of boxes) of MGnewOp(depth)"""
+        n, dx, nb = (C.c_int * 3)(), C.c_double(), C.c_int()
+        self.L.ref_factory_level(self.h, depth, n, C.byref(dx), C.byref(nb))
+        return tuple(n), dx.value, nb.value
+
+    def get(self, field, depth):
+        (nx, ny, nz), _, _ = self.level(depth)
+        out = np.empty((nz, ny, nx))
+        assert self.L.ref_factory_get(self.h, depth, ReferenceOperator.FIELD[field], out) == 0
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.ref_factory_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -6,12 +6,14 @@
 // restatement -- there is no Fortran compiler) and everything on the operator path (needs Chombo's AMRPoissonOp).
 #include "SetLevelData.H"   // the reference's prototypes (Source/SetLevelData.H:27-71)
 #include "SetBCs.H"         // ParseBC, GlobalBCRS (Source/SetBCs.H)
+#include "VariableCoeffPoissonOperatorFactory.H"
 
 #include "mgic_oracle.h"
 
 #include <cstdio>
 
 int AMRPoissonOp::s_relaxMode = 1;
+int AMRPoissonOp::s_maxCoarse = 2;
 const IntVect IntVect::Unit(1, 1, 1), IntVect::Zero(0, 0, 0);
 const RealVect RealVect::Unit(1.0, 1.0, 1.0), RealVect::Zero(0.0, 0.0, 0.0);
 
@@ -169,6 +171,67 @@ void ref_op_residual(void *h, int homogeneous) { RefOp *o = (RefOp *)h; o->resid
 void ref_op_apply(void *h, int homogeneous) { RefOp *o = (RefOp *)h; o->applyOpI(o->tmp, o->e, homogeneous != 0); }
 void ref_op_restrict(void *h) { RefOp *o = (RefOp *)h; o->restrictResidual(o->resCoarse, o->e, o->r); }
 void ref_op_precond(void *h) { RefOp *o = (RefOp *)h; o->preCond(o->e, o->r); }
+
+// ---- the reference's factory (Source/VariableCoeffPoissonOperatorFactory.cpp, compiled unmodified) through the function
+// Main_PoissonSolver.cpp calls, defineOperatorFactory (:163-166), on one AMR level: how deep MGnewOp goes, and the
+// coefficients / lambda / dx of every depth.  coefficient_average_type as PoissonParameters holds it (-1: not in the input).
+struct RefFactory {
+  AMRLevelOpFactory<LevelData<FArrayBox>> *f = nullptr;
+  ProblemDomain domain;
+  Vector<RefCountedPtr<LevelData<FArrayBox>>> a, b;
+  std::vector<VariableCoeffPoissonOperator *> ops;     // depth 0, 1, ... until MGnewOp returned NULL
+  IntVect n;
+  ~RefFactory() { for (auto *o : ops) delete o; delete f; }
+};
+void *ref_factory_create(const int N[3], int max_grid_size, double dx, double alpha, double beta, int coefficient_average_type,
+                         const double *aCoef, const double *bCoef) {
+  RefFactory *F = new RefFactory;
+  F->n = IntVect(N[0], N[1], N[2]);
+  std::vector<Box> boxes;
+  for (int k = 0; k < N[2]; k += max_grid_size)
+    for (int j = 0; j < N[1]; j += max_grid_size)
+      for (int i = 0; i < N[0]; i += max_grid_size)
+        boxes.push_back(Box(IntVect(i, j, k), IntVect(std::min(i + max_grid_size, N[0]) - 1, std::min(j + max_grid_size, N[1]) - 1,
+                                                     std::min(k + max_grid_size, N[2]) - 1)));
+  Vector<DisjointBoxLayout> grids(1, DisjointBoxLayout(boxes));
+  F->domain = ProblemDomain(Box(IntVect::Zero, IntVect(N[0] - 1, N[1] - 1, N[2] - 1)));
+  Vector<ProblemDomain> domains(1, F->domain);
+  F->a.push_back(RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(grids[0], 1, IntVect::Zero)));
+  F->b.push_back(RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(grids[0], 1, IntVect::Zero)));
+  level_copy(*F->a[0], nullptr, aCoef, F->n);
+  level_copy(*F->b[0], nullptr, bCoef, F->n);
+  PoissonParameters p;
+  p.coarsestDomain = F->domain; p.coarsestDx = dx; p.alpha = alpha; p.beta = beta;
+  p.refRatio.resize(1); p.refRatio.assign(2);
+  p.coefficient_average_type = coefficient_average_type;
+  F->f = defineOperatorFactory(grids, domains, F->a, F->b, p);
+  for (int depth = 0;; depth++) {                         // what MultiGrid::define does
+    MGLevelOp<LevelData<FArrayBox>> *op = F->f->MGnewOp(F->domain, depth, true);
+    if (!op) break;
+    F->ops.push_back(dynamic_cast<VariableCoeffPoissonOperator *>(op));
+  }
+  return F;
+}
+void ref_factory_destroy(void *h) { delete (RefFactory *)h; }
+int ref_factory_depths(void *h) { return (int)((RefFactory *)h)->ops.size(); }
+int ref_factory_average_type(void *h) { return dynamic_cast<VariableCoeffPoissonOperatorFactory *>(((RefFactory *)h)->f)->m_coefficient_average_type; }
+// depth's cells per direction, dx, number of boxes
+void ref_factory_level(void *h, int depth, int n[3], double *dx, int *boxes) {
+  VariableCoeffPoissonOperator *o = ((RefFactory *)h)->ops[depth];
+  const Box &d = o->standin_domain().domainBox();
+  for (int q = 0; q < 3; q++) n[q] = d.hi[q] - d.lo[q] + 1;
+  *dx = o->standin_dx();
+  *boxes = o->standin_grids().size();
+}
+// field: ORC_F_A, ORC_F_B, ORC_F_LAMBDA of a depth, as a global array
+int ref_factory_get(void *h, int depth, int field, double *out) {
+  VariableCoeffPoissonOperator *o = ((RefFactory *)h)->ops[depth];
+  LevelData<FArrayBox> *ld = field == ORC_F_A ? &*o->m_aCoef : field == ORC_F_B ? &*o->m_bCoef : field == ORC_F_LAMBDA ? &o->m_lambda : nullptr;
+  if (!ld) return 1;
+  const Box &d = o->standin_domain().domainBox();
+  level_copy(*ld, out, nullptr, IntVect(d.hi[0] + 1, d.hi[1] + 1, d.hi[2] + 1));
+  return 0;
+}
 
 typedef struct {
   double G_Newton, phi_amplitude, phi_wavelength;

@@ -255,3 +255,44 @@ def test_reference_operator_aborts_like_the_reference():
         msg = C.create_string_buffer(256)
         assert R.L.ref_op_relax_status_msg(R.h, 1, mode, msg, 256) == 1
         assert b"Not implemented" in msg.value
+
+
+# ---- the factory: Source/VariableCoeffPoissonOperatorFactory.cpp, compiled unmodified, through defineOperatorFactory (row a17)
+FACTORY_CASES = {
+    "params.txt_64_box16": dict(N=(64, 64, 64), max_grid_size=16),
+    "arithmetic": dict(N=(32, 32, 32), max_grid_size=8, coefficient_average_type=0),
+    "noncubic": dict(N=(24, 16, 32), max_grid_size=8, L=60.0),
+    "ragged_48_box16": dict(N=(48, 48, 48), max_grid_size=16, L=30.0),
+    "one_box_8": dict(N=(8, 8, 8), max_grid_size=8, L=10.0),
+    "box32": dict(N=(64, 64, 64), max_grid_size=32),
+}
+
+
+@live
+@pytest.mark.parametrize("case", list(FACTORY_CASES))
+def test_oracle_mg_hierarchy_equals_the_reference_factory(case):
+    """how deep MGnewOp goes before it returns NULL (coarsenable(2^depth * s_maxCoarse), Factory.cpp:168-172), and dx, the
+    coefficients (CoarseAverage straight from the AMR level's, arithmetic / harmonic) and lambda of every depth"""
+    o = Oracle(**FACTORY_CASES[case])
+    nd = o.setup()
+    F = pyref.ReferenceFactory(o.params, o.get("A"), o.get("B"))
+    assert F.depths == nd and F.average_type == o.params["coefficient_average_type"]
+    for d in range(nd):
+        n, dx, _ = F.level(d)
+        assert (n, dx) == o.dims(d)
+        for f in ("A", "B", "LAMBDA"):
+            assert np.array_equal(F.get(f, d), o.get(f, d)), (f, d)
+
+
+@live
+def test_absent_average_type_means_arithmetic():
+    """coefficient_average_type absent from the input = -1 in PoissonParameters (PoissonParameters.cpp:98): defineOperatorFactory
+    then leaves the factory's default, arithmetic (Factory.cpp:43-45,321)"""
+    o = Oracle(N=(32, 32, 32), max_grid_size=8, coefficient_average_type=0)
+    o.setup()
+    F = pyref.ReferenceFactory(o.params, o.get("A"), o.get("B"), coefficient_average_type=-1)
+    assert F.average_type == 0
+    assert np.array_equal(F.get("A", 2), o.get("A", 2))
+    h = Oracle(N=(32, 32, 32), max_grid_size=8, coefficient_average_type=1)
+    h.setup()
+    assert not np.array_equal(h.get("A", 2), o.get("A", 2))
