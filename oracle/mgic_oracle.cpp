@@ -10,8 +10,8 @@
  *
  * PARITY (see mgic_oracle.h): source terms, parameters, ParseBC, the operator
  * class's orchestration and the factory are pinned bit for bit to the reference's
- * own C++ (oracle/_ref); UNPINNED are the .ChF kernels' arithmetic (no Fortran
- * compiler) and everything tagged [Chombo], which restates Chombo 3.2
+ * own C++ and to a mechanical translation of its .ChF kernels (oracle/_ref);
+ * UNPINNED is everything tagged [Chombo], which restates Chombo 3.2
  * (GNUmakefile:12) -- not under /root/reference -- from its published algorithm.
  *
  * Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp (see Makefile).

@@ -17,16 +17,18 @@
  *   -- levelGSRB, residualI, applyOpI, restrictResidual, preCond, levelJacobi,
  *   lambda (a6 - a12) -- and the factory's MG depth limit and coefficient
  *   coarsening (a17).
- *   UNPINNED: the arithmetic of the six .ChF kernels (no Fortran compiler: the
- *   reference's operator is linked against THIS file's restatement of them, which
- *   follows the .ChF line by line) and everything that is Chombo 3.2's, which is
- *   not vendored under /root/reference and is restated from its published
- *   algorithm: DiriBC/NeumBC, exchange, CoarseAverage, FORT_PROLONG,
- *   MultiGrid::cycle, BiCGStabSolver::solve, AMRMultiGrid, MultilevelLinearOp,
- *   QuadCFInterp.  The reference ships no tests and no golden vectors.  Pins
- *   there: the known-answer tests in tests/ (trivial KAT, trace-free KAT,
- *   manufactured solution, decomposition invariance) and an independent numpy
- *   twin (tests/np_twin.py).
+ *   PINNED through a mechanical translation: the six .ChF kernels.  There is no
+ *   Fortran compiler, so oracle/chf2c.py translates the reference's .ChF files to
+ *   C++ at build time (syntax only, every expression copied through); the
+ *   reference's classes run on that translation, and this file's restatement of
+ *   the kernels is bit-identical to it.
+ *   UNPINNED: everything that is Chombo 3.2's, which is not vendored under
+ *   /root/reference and is restated from its published algorithm: DiriBC/NeumBC,
+ *   exchange, CoarseAverage, FORT_PROLONG, MultiGrid::cycle,
+ *   BiCGStabSolver::solve, AMRMultiGrid, MultilevelLinearOp, QuadCFInterp.  The
+ *   reference ships no tests and no golden vectors.  Pins there: the known-answer
+ *   tests in tests/ (trivial KAT, trace-free KAT, manufactured solution,
+ *   decomposition invariance) and an independent numpy twin (tests/np_twin.py).
  */
 #ifndef MGIC_ORACLE_H
 #define MGIC_ORACLE_H

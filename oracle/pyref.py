@@ -1,7 +1,9 @@
-"""ctypes loader for oracle/_ref/libmgic_ref.so (TEST INFRASTRUCTURE): the reference's own Source/SetLevelData.cpp,
-Source/SetBinaryBH.H and MyPhiFunction.H compiled unmodified against a stand-in for the Chombo containers
-(oracle/ref_shim/chombo_standin.H; recipe: `make -C oracle ref`).  Used by tests/test_reference_pins.py and
-tests/golden/make_reference_golden.py to pin the oracle's source-term restatement to the reference's arithmetic."""
+"""ctypes loader for oracle/_ref/libmgic_ref.so (TEST INFRASTRUCTURE): the reference's own C++ (SetLevelData.cpp with
+SetBinaryBH.H and MyPhiFunction.H, PoissonParameters.cpp, SetBCs.cpp, VariableCoeffPoissonOperator.cpp,
+VariableCoeffPoissonOperatorFactory.cpp) compiled unmodified against a stand-in for the Chombo API it touches
+(oracle/ref_shim/chombo_standin.H), plus its two .ChF kernel files translated mechanically to C++ (oracle/chf2c.py);
+recipe: `make -C oracle ref`.  The library contains nothing of the oracle.  Used by tests/test_reference_pins.py and
+tests/golden/make_reference_golden.py to pin the oracle's restatement to the reference."""
 import ctypes as C
 import os
 import subprocess
@@ -39,8 +41,6 @@ def available():
 def build():
     """compile the reference's files where they lie (only possible where /root/reference exists); returns the .so or None"""
     if os.path.isdir(os.path.join(REFERENCE, "Source")):
-        from . import pyoracle
-        pyoracle.build()
         subprocess.check_call(["make", "-C", _HERE, "ref", f"REF={REFERENCE}"], stdout=subprocess.DEVNULL)
     return SO if os.path.exists(SO) else None
 

@@ -1,9 +1,11 @@
-// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own source-term and parameter code: this
-// file is linked with /root/reference/Source/SetLevelData.cpp (which includes Source/SetBinaryBH.H and MyPhiFunction.H) and
-// /root/reference/Source/PoissonParameters.cpp, compiled unmodified where they lie, against oracle/ref_shim/chombo_standin.H.  It pins the oracle's restatement of SURVEY rows
-// a18 / a19 (set_initial_conditions, set_rhs, set_a_coef, set_b_coef, set_update_psi0, get_Aij, set_binary_bh_psi,
-// my_phi_function) to the reference's arithmetic.  Not pinned by it: the two Fortran stencils (forwarded below to the C
-// restatement -- there is no Fortran compiler) and everything on the operator path (needs Chombo's AMRPoissonOp).
+// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own code: this file is linked with the
+// reference's Source/SetLevelData.cpp (which includes SetBinaryBH.H and MyPhiFunction.H), PoissonParameters.cpp, SetBCs.cpp,
+// VariableCoeffPoissonOperator.cpp and VariableCoeffPoissonOperatorFactory.cpp, compiled unmodified where they lie against
+// oracle/ref_shim/chombo_standin.H, and with the mechanical C++ translation of its two .ChF kernel files (oracle/chf2c.py).
+// Nothing in the resulting library comes from the oracle (mgic_oracle.h is included for its field ids only), so
+// tests/test_reference_pins.py compares two independent things: the reference's own code and the oracle's restatement.
+// Not the reference's: Chombo (stand-in, restated from the published algorithms) and Fortran's place in the tool chain
+// (translated, not compiled).
 #include "SetLevelData.H"   // the reference's prototypes (Source/SetLevelData.H:27-71)
 #include "SetBCs.H"         // ParseBC, GlobalBCRS (Source/SetBCs.H)
 #include "VariableCoeffPoissonOperatorFactory.H"
@@ -24,38 +26,9 @@ Real get_Aij(const int i, const int j, const Real &rbh1, const Real &rbh2, const
 Real set_binary_bh_psi(const RealVect &loc, const PoissonParameters &a_params);
 Real my_phi_function(RealVect loc, Real amplitude, Real wavelength, RealVect L);
 
-// SetLevelDataF.ChF cannot be compiled here: the symbols SetLevelDataF_F.H declares come from the C restatement
-extern "C" void getlaplacianpsif_(CHFp_FRA1(l_of_psi), CHFp_CONST_FRA1(psi), CHFp_CONST_REAL(dx), CHFp_BOX(box)) {
-  orc_getlaplacianpsif(CHFt_FRA1(l_of_psi), CHFt_CONST_FRA1(psi), dx, CHFt_BOX(box));
-}
-extern "C" void getrhogradphif_(CHFp_FRA1(rho_grad_phi), CHFp_CONST_FRA1(phi), CHFp_CONST_REAL(dx), CHFp_BOX(box)) {
-  orc_getrhogradphif(CHFt_FRA1(rho_grad_phi), CHFt_CONST_FRA1(phi), dx, CHFt_BOX(box));
-}
-
-// VariableCoeffPoissonOperatorF.ChF likewise: the symbols VariableCoeffPoissonOperatorF_F.H declares, from the C restatement
-extern "C" void gsrbhelmholtzvc3d_(CHFp_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_BOX(region), CHFp_CONST_REAL(dx), CHFp_CONST_REAL(alpha),
-                                   CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_CONST_FRA(lambda),
-                                   CHFp_CONST_INT(redBlack)) {
-  orc_gsrbhelmholtzvc3d(CHFt_FRA(dpsi), CHFt_CONST_FRA(rhs), CHFt_BOX(region), dx, alpha, CHFt_CONST_FRA(aCoef), beta,
-                        CHFt_CONST_FRA(bCoef), CHFt_CONST_FRA(lambda), redBlack);
-}
-extern "C" void vccomputeop3d_(CHFp_FRA(lofdpsi), CHFp_CONST_FRA(dpsi), CHFp_CONST_REAL(alpha), CHFp_CONST_FRA(aCoef),
-                               CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region), CHFp_CONST_REAL(dx)) {
-  orc_vccomputeop3d(CHFt_FRA(lofdpsi), CHFt_CONST_FRA(dpsi), alpha, CHFt_CONST_FRA(aCoef), beta, CHFt_CONST_FRA(bCoef),
-                    CHFt_BOX(region), dx);
-}
-extern "C" void vccomputeres3d_(CHFp_FRA(res), CHFp_CONST_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_CONST_REAL(alpha),
-                                CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region),
-                                CHFp_CONST_REAL(dx)) {
-  orc_vccomputeres3d(CHFt_FRA(res), CHFt_CONST_FRA(dpsi), CHFt_CONST_FRA(rhs), alpha, CHFt_CONST_FRA(aCoef), beta,
-                     CHFt_CONST_FRA(bCoef), CHFt_BOX(region), dx);
-}
-extern "C" void restrictresvc3d_(CHFp_FRA(res), CHFp_CONST_FRA(dpsi), CHFp_CONST_FRA(rhs), CHFp_CONST_REAL(alpha),
-                                 CHFp_CONST_FRA(aCoef), CHFp_CONST_REAL(beta), CHFp_CONST_FRA(bCoef), CHFp_BOX(region),
-                                 CHFp_CONST_REAL(dx)) {
-  orc_restrictresvc3d(CHFt_FRA(res), CHFt_CONST_FRA(dpsi), CHFt_CONST_FRA(rhs), alpha, CHFt_CONST_FRA(aCoef), beta,
-                      CHFt_CONST_FRA(bCoef), CHFt_BOX(region), dx);
-}
+// The Fortran symbols the reference's generated prototypes declare (SetLevelDataF_F.H, VariableCoeffPoissonOperatorF_F.H) --
+// getlaplacianpsif_, getrhogradphif_, gsrbhelmholtzvc3d_, vccomputeop3d_, vccomputeres3d_, restrictresvc3d_ -- are defined
+// in oracle/_ref/gen/*.cpp, which chf2c.py generates from the reference's .ChF files at build time.
 
 // ---- the reference's operator class (Source/VariableCoeffPoissonOperator.{H,cpp}, compiled unmodified) on one level that
 // covers its domain, split into boxes of max_grid_size; physical BCs by the reference's ParseBC (Source/SetBCs.cpp, compiled

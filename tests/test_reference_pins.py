@@ -296,3 +296,103 @@ def test_absent_average_type_means_arithmetic():
     h = Oracle(N=(32, 32, 32), max_grid_size=8, coefficient_average_type=1)
     h.setup()
     assert not np.array_equal(h.get("A", 2), o.get("A", 2))
+
+
+# ---- the six .ChF kernels themselves: oracle/chf2c.py's mechanical translation of the reference's Fortran (built into
+# oracle/_ref under the Fortran symbol names) against the oracle's hand restatement, called with the same Fortran-style
+# argument lists on random FABs whose boxes do not start at 0, with ghost cells, both colours, shifted bounds.
+import ctypes as C  # noqa: E402
+
+
+class Fab:
+    """a Fortran-ordered array over [lo, hi] with ncomp components + its argument list (ptr, lo0..2, hi0..2[, ncomp])"""
+
+    def __init__(self, lo, hi, ncomp=1, rng=None, positive=False):
+        self.lo, self.hi, self.nc = lo, hi, ncomp
+        shape = (ncomp,) + tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
+        self.a = rng.standard_normal(shape) if rng is not None else np.zeros(shape)
+        if positive:
+            self.a = 0.5 + np.abs(self.a)
+        self.ints = [C.c_int(v) for v in tuple(lo) + tuple(hi)] + [C.c_int(ncomp)]
+
+    def args(self, comp=True):
+        return [self.a.ctypes.data_as(C.c_void_p)] + [C.byref(i) for i in (self.ints if comp else self.ints[:6])]
+
+    def copy(self):
+        f = Fab(self.lo, self.hi, self.nc)
+        f.a = self.a.copy()
+        return f
+
+
+def box_args(lo, hi, keep):
+    ints = [C.c_int(v) for v in tuple(lo) + tuple(hi)]
+    keep.append(ints)
+    return [C.byref(i) for i in ints]
+
+
+@live
+@pytest.mark.parametrize("lo,n", [((0, 0, 0), (8, 8, 8)), ((4, -6, 10), (9, 6, 7)), ((-8, -8, -8), (5, 4, 3))])
+def test_translated_chf_kernels_equal_the_oracle_kernels(lo, n):
+    from oracle import lib as oracle_lib
+    O, R = oracle_lib(), pyref.lib()
+    rng = np.random.default_rng(abs(hash((lo, n))) % 2 ** 32)
+    hi = tuple(lo[d] + n[d] - 1 for d in range(3))
+    glo, ghi = tuple(x - 1 for x in lo), tuple(x + 1 for x in hi)
+    keep = []
+    dx, alpha, beta = C.c_double(0.37), C.c_double(1.1), C.c_double(-0.9)
+    phi = Fab(glo, ghi, rng=rng)
+    rhs, a, b = Fab(lo, hi, rng=rng), Fab(lo, hi, rng=rng), Fab(lo, hi, rng=rng, positive=True)
+    lam = Fab(lo, hi, rng=rng)
+    region = box_args(lo, hi, keep)
+    # GSRBHELMHOLTZVC3D, red then black
+    p1, p2 = phi.copy(), phi.copy()
+    for colour in (0, 1, 1, 0):
+        c = C.c_int(colour)
+        for L, f, p in ((O, "orc_gsrbhelmholtzvc3d", p1), (R, "gsrbhelmholtzvc3d_", p2)):
+            getattr(L, f).restype = None
+            getattr(L, f)(*p.args(), *rhs.args(), *region, C.byref(dx), C.byref(alpha), *a.args(), C.byref(beta), *b.args(), *lam.args(),
+                          C.byref(c))
+        assert np.array_equal(p1.a, p2.a) and not np.array_equal(p1.a, phi.a)
+    # VCCOMPUTEOP3D / VCCOMPUTERES3D
+    o1, o2 = Fab(lo, hi), Fab(lo, hi)
+    for L, f, out in ((O, "orc_vccomputeop3d", o1), (R, "vccomputeop3d_", o2)):
+        getattr(L, f).restype = None
+        getattr(L, f)(*out.args(), *phi.args(), C.byref(alpha), *a.args(), C.byref(beta), *b.args(), *region, C.byref(dx))
+    assert np.array_equal(o1.a, o2.a) and np.abs(o1.a).max() > 0
+    for L, f, out in ((O, "orc_vccomputeres3d", o1), (R, "vccomputeres3d_", o2)):
+        getattr(L, f).restype = None
+        getattr(L, f)(*out.args(), *phi.args(), *rhs.args(), C.byref(alpha), *a.args(), C.byref(beta), *b.args(), *region, C.byref(dx))
+    assert np.array_equal(o1.a, o2.a)
+    # RESTRICTRESVC3D: bounds shifted so that the region starts at 0 (CHF_*_SHIFT, VariableCoeffPoissonOperator.cpp:173-192)
+    if all(x % 2 == 0 for x in n):
+        sh = lambda f: Fab(tuple(f.lo[d] - lo[d] for d in range(3)), tuple(f.hi[d] - lo[d] for d in range(3)))
+        sphi, srhs, sa, sb = sh(phi), sh(rhs), sh(a), sh(b)
+        sphi.a, srhs.a, sa.a, sb.a = phi.a, rhs.a, a.a, b.a
+        chi = tuple(n[d] // 2 - 1 for d in range(3))
+        c1, c2 = Fab((0, 0, 0), chi), Fab((0, 0, 0), chi)
+        sregion = box_args((0, 0, 0), tuple(x - 1 for x in n), keep)
+        for L, f, out in ((O, "orc_restrictresvc3d", c1), (R, "restrictresvc3d_", c2)):
+            getattr(L, f).restype = None
+            getattr(L, f)(*out.args(), *sphi.args(), *srhs.args(), C.byref(alpha), *sa.args(), C.byref(beta), *sb.args(), *sregion, C.byref(dx))
+        assert np.array_equal(c1.a, c2.a) and np.abs(c1.a).max() > 0
+    # GETLAPLACIANPSIF / GETRHOGRADPHIF (single-component arrays: no ncomp argument)
+    for fo, fr in (("orc_getlaplacianpsif", "getlaplacianpsif_"), ("orc_getrhogradphif", "getrhogradphif_")):
+        for L, f, out in ((O, fo, o1), (R, fr, o2)):
+            getattr(L, f).restype = None
+            getattr(L, f)(*out.args(False), *phi.args(False), C.byref(dx), *region)
+        assert np.array_equal(o1.a, o2.a) and np.abs(o1.a).max() > 0
+
+
+def test_chf_translator_refuses_what_it_does_not_know():
+    """chf2c.py rewrites syntax only and must stop on anything outside the dialect of the reference's two files"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chf2c
+    ok = chf2c.translate("      subroutine F(CHF_FRA1[a], CHF_BOX[b])\n      integer CHF_AUTODECL[i]\n      CHF_AUTOMULTIDO[b;i]\n"
+                         "        a(CHF_AUTOIX[i]) = 1.0/3.0 *\n     &     2.0\n      CHF_ENDDO\n      return\n      end\n")
+    assert "a(i0,i1,i2) = 1.0/3.0 * 2.0;" in ok and 'extern "C" void f_(' in ok
+    for bad in ("      subroutine F(CHF_FRA1[a])\n      a(1,1,1) = 2.0**3\n      end\n",
+                "      subroutine F(CHF_FRA1[a])\n      goto 10\n      end\n",
+                "      subroutine F(CHF_VR[a])\n      end\n",
+                "      subroutine F(CHF_FRA1[a])\n      do i = 10, 1, -1\n      enddo\n      end\n"):
+        with pytest.raises(chf2c.ChfError):
+            chf2c.translate(bad)
