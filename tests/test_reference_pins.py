@@ -396,3 +396,37 @@ def test_chf_translator_refuses_what_it_does_not_know():
                 "      subroutine F(CHF_FRA1[a])\n      do i = 10, 1, -1\n      enddo\n      end\n"):
         with pytest.raises(chf2c.ChfError):
             chf2c.translate(bad)
+
+
+@live
+@pytest.mark.parametrize("name,over", [
+    ("kernels_16_dirichlet", dict(N=(16, 16, 16), max_grid_size=8, L=40.0)),
+    ("kernels_24x16x32_neumann", dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1),
+                                      bc_value=0.25, coefficient_average_type=0)),
+])
+def test_kernel_goldens_are_what_the_reference_computes(name, over):
+    """tests/golden/kernels_*.npz were frozen from the oracle (make_golden.py); the reference's own source terms, operator
+    class, factory and (translated) kernels reproduce every array in them that they can compute, bit for bit -- so the GPU
+    tests that use these fixtures compare against the reference's numbers"""
+    from oracle.pyoracle import default_params
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    params = default_params(**over)
+    mg, rhs, a, b = pyref.set_level_data(params)
+    for c in range(8):
+        assert np.array_equal(mg[c][3:-3, 3:-3, 3:-3], g[f"mgvar{c}"]), c
+    assert np.array_equal(rhs, g["rhs"]) and np.array_equal(a, g["a"]) and np.array_equal(b, g["b"])
+    F = pyref.ReferenceFactory(params, a, b)
+    assert F.depths == int(g["depths"]) and np.array_equal(F.get("LAMBDA", 0), g["lam"])
+    for d in range(1, F.depths):
+        assert np.array_equal(F.get("A", d), g[f"a{d}"]) and np.array_equal(F.get("LAMBDA", d), g[f"lam{d}"])
+    R = pyref.ReferenceOperator(params)
+    R.set("A", a); R.set("B", b); R.set("E", g["e"]); R.set("R", g["r"])
+    assert np.array_equal(R.residual(True), g["residual_h"]) and np.array_equal(R.residual(False), g["residual_i"])
+    assert np.array_equal(R.apply(True), g["apply_h"])
+    assert np.array_equal(R.restrict(), g["restrict"])
+    R.set("E", g["e"])
+    R.relax(4)
+    assert np.array_equal(R.get("E"), g["relax4"])
+    R.set("E", g["e"])
+    R.precond()
+    assert np.array_equal(R.get("E"), g["precond"])
