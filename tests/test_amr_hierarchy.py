@@ -124,3 +124,45 @@ def test_refinement_improves_the_solution_near_the_punctures():
     err_amr = np.abs(phi[1] - u1).max()
     err_coarse = np.abs(rep2(c0[tw.under[1]]) - u1).max()
     assert err_amr < 0.5 * err_coarse, (err_amr, err_coarse)
+
+
+def test_c4_boxes_of_the_timing_tool_make_a_converging_hierarchy():
+    """tools/bench_amr.py's config-C4 geometry (merged level-1 box around both punctures, two disjoint level-2
+    cubes, snapped to block_factor 8, nested by two coarse cells) at half size (128^3 base): a valid hierarchy on which the
+    AMR V(2,2) iteration converges -- with the tool's own piecewise-constant injection of coefficients and right-hand sides"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "bench_amr", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bench_amr.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    with pytest.raises(ValueError):
+        tool.c4_boxes(64)
+    l1, l2 = tool.c4_boxes(256)
+    assert [l1[1][d] - l1[0][d] + 1 for d in range(3)] == [224, 128, 128]           # one box of 112 x 64 x 64 coarse cells
+    assert all([hi[d] - lo[d] + 1 for d in range(3)] == [64, 64, 64] for lo, hi in l2)
+    N, L = 128, 100.0
+    l1, l2 = tool.c4_boxes(N)
+    o = Oracle(N=(N, N, N), max_grid_size=32, numMGsmooth=2, L=L)
+    o.setup()
+    host = {0: dict(a=o.get("A"), b=o.get("B"), r=o.get("RHS"))}
+    origin = {0: (0, 0, 0)}
+    patches, rhs = [[], []], [host[0]["r"]]
+    for level, boxes, parent in ((1, [l1], 0), (2, l2, 1)):
+        for lo, hi in boxes:
+            P = OraclePatch((N << level,) * 3, lo, hi, L / N / (1 << level), max_grid_size=32)
+            sl = tuple(slice(lo[d] // 2 - origin[parent][d], hi[d] // 2 - origin[parent][d] + 1) for d in (2, 1, 0))
+            arr = {k: rep2(x[sl]) for k, x in host[parent].items()}
+            P.set("A", arr["a"]); P.set("B", arr["b"])
+            rhs.append(arr["r"])
+            patches[level - 1].append(P)
+            if level == 1:
+                host[1], origin[1] = arr, lo
+    tw = AmrTwin(OracleBackend(o, patches))
+    assert tw.b.parent == [-1, 0, 1, 1]
+    phi, hist = tw.zeros(), []
+    for _ in range(4):
+        r = tw.residual(phi, rhs, False)
+        hist.append(tw.norm(r, 0))
+        phi = [a + c for a, c in zip(phi, tw.vcycle(r))]
+    assert all(hist[i + 1] < 0.25 * hist[i] for i in range(3)), hist

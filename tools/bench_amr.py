@@ -15,10 +15,8 @@ import os
 import sys
 
 import numpy as np
-import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import mg_ic_code_b200 as m
 
 
 def c4_boxes(n, L=100.0, offset=10.0, block=8):
@@ -57,6 +55,8 @@ def main():
     ap.add_argument("--smooth", type=int, default=2)
     ap.add_argument("--box", type=int, default=32)
     args = ap.parse_args()
+    import torch
+    import mg_ic_code_b200 as m
     n, L = args.n, 100.0
     ctx = m.Context(0)
     P = m.make_params(dict(m.DEFAULTS, N=(n, n, n), L=L, max_grid_size=args.box, numMGsmooth=args.smooth))
