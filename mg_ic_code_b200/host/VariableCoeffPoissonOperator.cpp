@@ -43,7 +43,7 @@ void AMRPoissonOp::createCoarser(LevelData<FArrayBox> &a_coarse, const LevelData
   CH_assert(m_coarserOp);
   DisjointBoxLayout dbl;
   coarsen(dbl, a_fine.disjointBoxLayout(), 2);  // multigrid, so coarsen by 2
-  a_coarse.define(dbl, a_fine.nComp(), a_ghosted ? a_fine.ghostVect() : IntVect::Zero());
+  a_coarse.define(dbl, a_fine.nComp(), a_ghosted ? a_fine.ghostVect() : IntVect::Zero);
   twinOn(a_coarse, m_coarserOp);
   a_coarse.twin()->fresh = DeviceTwin::DEVICE;
 }

@@ -35,7 +35,7 @@ void VariableCoeffPoissonOperatorFactory::define(const ProblemDomain &a_coarseDo
 
 std::shared_ptr<DeviceHierarchy> VariableCoeffPoissonOperatorFactory::hierarchy() {
   if (m_hier) return m_hier;
-  if (!m_dev) m_dev = std::make_shared<DeviceContext>(0);
+  if (!m_dev) m_dev = defaultDevice();
   auto h = std::make_shared<DeviceHierarchy>();
   h->dev = m_dev;
   h->aCoef = m_aCoef[0]; h->bCoef = m_bCoef[0];

@@ -29,15 +29,15 @@ static int poissonSolve(const Vector<DisjointBoxLayout> &a_grids, const PoissonP
   auto dev = std::make_shared<DeviceContext>(0);
   const BCHolder bc = BCHolder::fromParmParse();
   MultigridVarsDevice multigrid_vars(dev, a_params, bc);
-  const IntVect ghosts = IntVect::Unit() * 3;
+  const IntVect ghosts = IntVect::Unit * 3;
   Vector<LevelData<FArrayBox> *> dpsi(nlevels, NULL), rhs(nlevels, NULL);
   Vector<RefCountedPtr<LevelData<FArrayBox>>> aCoef(nlevels), bCoef(nlevels);
   Vector<ProblemDomain> vectDomains(nlevels, a_params.coarsestDomain);
   Vector<RealVect> vectDx(nlevels, RealVect(a_params.coarsestDx, a_params.coarsestDx, a_params.coarsestDx));
   dpsi[0] = new LevelData<FArrayBox>(a_grids[0], 1, ghosts);
-  rhs[0] = new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero());
-  aCoef[0] = RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero()));
-  bCoef[0] = RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero()));
+  rhs[0] = new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero);
+  aCoef[0] = RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero));
+  bCoef[0] = RefCountedPtr<LevelData<FArrayBox>>(new LevelData<FArrayBox>(a_grids[0], 1, IntVect::Zero));
   set_initial_conditions(multigrid_vars, *dpsi[0], vectDx[0], a_params);
 
   const int lBase = 0;

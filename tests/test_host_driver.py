@@ -39,6 +39,53 @@ def test_driver_rejects_bad_input(tmp_path):
     assert r.returncode != 0 and "cannot open" in r.stderr
 
 
+REFERENCE_MAIN = os.path.join(os.environ.get("MGIC_REFERENCE", "/root/reference"), "Main_PoissonSolver.cpp")
+REFMAIN_EXE = os.path.join(ROOT, "mg_ic_code_b200", "lib", "Main_PoissonSolver_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_MAIN), reason="needs the reference's Main_PoissonSolver.cpp")
+def test_reference_main_compiles_unmodified_against_the_host_layer(tmp_path):
+    """The drop-in claim at its strongest: the reference's own Main_PoissonSolver.cpp -- main(), parameter handling, the
+    nonlinear loop -- compiles UNMODIFIED, where it lies, against mg_ic_code_b200/host (+ host/dropin: headers with Chombo's and
+    the reference's names) and links against the C ABI library.  Without a GPU it behaves like the reference up to the first
+    device call and then stops loudly."""
+    import torch
+    exe()
+    assert os.path.exists(REFMAIN_EXE)
+    r = subprocess.run([REFMAIN_EXE], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage" in r.stderr and "<input_file_name>" in r.stderr        # Main_PoissonSolver.cpp:266-269
+    ref_params = os.path.join(os.path.dirname(REFERENCE_MAIN), "params.txt")                     # max_level = 6: needs set_grids' AMR part
+    r = subprocess.run([REFMAIN_EXE, ref_params], capture_output=True, text=True)
+    assert r.returncode != 0 and "max_level must be 0" in r.stderr
+    bad = tmp_path / "bad.txt"
+    bad.write_text(open(PARAMS).read().replace("harmonic", "geometric"))
+    r = subprocess.run([REFMAIN_EXE, str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "bad coefficient_average_type in input" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([REFMAIN_EXE, PARAMS], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr and "MayDay::Error" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a GPU is the driver's")
+def test_reference_main_drives_the_b200_path(tmp_path):
+    """the reference's unmodified main() and nonlinear loop on the B200 path: same NL history and psi as the oracle"""
+    from oracle import Oracle
+    if not os.path.exists(REFMAIN_EXE):
+        pytest.skip("Main_PoissonSolver_b200 was not built (the reference's Main_PoissonSolver.cpp is absent)")
+    o = Oracle(N=(32, 32, 32), max_grid_size=16, numMGsmooth=4, numMGIterations=2)
+    o.set_initial_conditions()
+    nl = o.nl_solve()
+    psi_o = o.get("MGVAR0", comp=0)
+    dump = tmp_path / "psi.bin"
+    r = subprocess.run([REFMAIN_EXE, PARAMS], capture_output=True, text=True, timeout=120, env=dict(os.environ, MGIC_DUMP_PSI=str(dump)))
+    assert r.returncode == 0, r.stderr[-2000:]
+    norms = [float(l.split(" is ")[1]) for l in r.stdout.splitlines() if l.startswith("The norm of dpsi after step")]
+    assert len(norms) == len(nl) and np.allclose(norms[:3], nl[:3], rtol=1e-5)      # pout() prints 6 significant digits
+    psi = np.fromfile(dump).reshape(32, 32, 32)
+    assert np.abs(psi - psi_o).max() / np.abs(psi_o).max() < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("route", ["device", "host"])
 def test_driver_matches_oracle_nl_loop(tmp_path, route):
