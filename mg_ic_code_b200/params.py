@@ -60,14 +60,31 @@ def make_params(d=None, **over):
     return p
 
 
-def read_params(path, overrides=()):
+# keys the reference reads with ParmParse::get / getarr, i.e. whose absence stops it (Source/PoissonParameters.cpp:30-126,
+# Source/SetBCs.cpp:45,55-56) ...
+REQUIRED = ("alpha", "beta", "G_Newton", "phi_amplitude", "phi_wavelength", "bh1_bare_mass", "bh2_bare_mass", "bh1_spin", "bh2_spin",
+            "bh1_offset", "bh2_offset", "bh1_momentum", "bh2_momentum", "max_level", "N", "L", "refine_threshold", "block_factor",
+            "max_grid_size", "fill_ratio", "buffer_size", "is_periodic", "bc_lo", "bc_hi", "bc_value")
+# ... and the in-code defaults of the keys it reads with query (PoissonParameters.cpp:59-60, Main_PoissonSolver.cpp:106-126)
+QUERY_DEFAULTS = dict(verbosity=3, numMGIterations=1, numMGsmooth=4, preCondSolverDepth=-1, tolerance=1.0e-7, max_iterations=10,
+                      max_NL_iterations=4)
+
+
+def read_params(path, overrides=(), strict=False):
     """Read a reference-format params.txt; `overrides` are 'key=value' strings (ParmParse CLI overrides,
-    Main_PoissonSolver.cpp:272)."""
+    Main_PoissonSolver.cpp:272).  strict=True is the reference's behaviour: a missing required key is an error and the
+    optional solver keys take the reference's in-code defaults; otherwise missing keys take params.txt's values (DEFAULTS)."""
     with open(path) as f:
         raw = parse_params_text(f.read())
     for o in overrides:
         k, v = o.split("=", 1)
         raw[k.strip()] = v.split()
+    if strict:
+        for k in REQUIRED:
+            if k not in raw or not raw[k]:
+                raise MgicError(f"ParmParse::get: {k} not found")   # MayDay::Error in the reference
+        for k, v in QUERY_DEFAULTS.items():
+            raw.setdefault(k, [str(v)])
     d = {}
     for k, v in raw.items():
         if k in _INT3:

@@ -187,6 +187,15 @@ def test_parameter_errors_are_the_references(tmp_path, tmp_path_factory):
             pyref.get_poisson_parameters(cut)
         rc, _, err = host_mirror_params(str(cut), (), tmp_path_factory)
         assert rc != 0 and key in err, key
+        with pytest.raises(m.MgicError, match=key):
+            m.read_params(str(cut), strict=True)
+    assert m.read_params(REF_PARAMS, strict=True).numMGsmooth == 4 and m.read_params(REF_PARAMS, strict=True).verbosity == 2
+    bare = tmp_path / "no_solver_keys.txt"
+    solver_keys = ("numMGsmooth", "numMGIterations", "max_iterations", "max_NL_iterations", "tolerance", "verbosity")
+    bare.write_text("\n".join(l for l in text.splitlines() if l.split("=")[0].strip() not in solver_keys))
+    P = m.read_params(str(bare), strict=True)       # the in-code defaults of Main_PoissonSolver.cpp:106-126 / PoissonParameters.cpp:59
+    assert (P.numMGIterations, P.numMGsmooth, P.preCondSolverDepth, P.max_iterations, P.max_NL_iterations, P.verbosity) == (1, 4, -1, 10, 4, 3)
+    assert P.tolerance == 1.0e-7 and pyref.get_poisson_parameters(bare)["verbosity"] == 3
     none = tmp_path / "no_avg.txt"
     none.write_text("\n".join(l for l in text.splitlines() if not l.startswith("coefficient_average_type")))
     assert pyref.get_poisson_parameters(none)["coefficient_average_type"] == -1
