@@ -13,6 +13,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libmgic_ref.so")
+# the same reference C++ with its .ChF symbols resolved by the product's Fortran-ABI drop-ins in libmgic_b200.so
+# (include/mgic_chf.h): needs a GPU to run
+SO_CUDA = os.path.join(_HERE, "_ref", "libmgic_ref_cuda.so")
+B200_SO = os.path.join(os.path.dirname(_HERE), "mg_ic_code_b200", "lib", "libmgic_b200.so")
 REFERENCE = os.environ.get("MGIC_REFERENCE", "/root/reference")
 
 
@@ -42,23 +46,27 @@ def available():
 def build():
     """compile the reference's files where they lie (only possible where /root/reference exists); returns the .so or None"""
     if os.path.isdir(os.path.join(REFERENCE, "Source")):
+        targets = ["ref"] + (["ref_cuda"] if os.path.exists(B200_SO) else [])
         try:
-            subprocess.check_call(["make", "-C", _HERE, "ref", f"REF={REFERENCE}", f"PYTHON={sys.executable}"], stdout=subprocess.DEVNULL)
+            subprocess.check_call(["make", "-C", _HERE] + targets + [f"REF={REFERENCE}", f"PYTHON={sys.executable}"],
+                                  stdout=subprocess.DEVNULL)
         except (subprocess.CalledProcessError, OSError):
             if not os.path.exists(SO):      # a prebuilt library (e.g. on a read-only tree) is still usable
                 raise
     return SO if os.path.exists(SO) else None
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(cuda=False):
+    """cuda=True: the variant whose kernels are the product's CUDA drop-ins behind the Fortran ABI (compute calls need a GPU)"""
+    if cuda not in _libs:
         if build() is None:
             raise RuntimeError("oracle/_ref/libmgic_ref.so is not built and /root/reference is absent")
-        L = C.CDLL(SO)
+        if cuda and not os.path.exists(SO_CUDA):
+            raise RuntimeError("oracle/_ref/libmgic_ref_cuda.so is not built (needs mg_ic_code_b200/lib/libmgic_b200.so and /root/reference)")
+        L = C.CDLL(SO_CUDA if cuda else SO)
         nd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
         L.ref_set_level_data.argtypes = [C.POINTER(RefParams), C.c_int * 3, C.c_double, C.c_double, C.c_void_p, nd, nd, nd, nd]
         L.ref_set_level_data.restype = C.c_int
@@ -92,8 +100,8 @@ def lib():
         L.ref_factory_level.argtypes = [C.c_void_p, C.c_int, i3, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ref_factory_level.restype = None
         L.ref_factory_get.argtypes = [C.c_void_p, C.c_int, C.c_int, nd]
-        _lib = L
-    return _lib
+        _libs[cuda] = L
+    return _libs[cuda]
 
 
 def to_struct(params):
@@ -108,7 +116,7 @@ def to_struct(params):
     return p
 
 
-def set_level_data(params, constant_K=0.0, dpsi_ghosted=None):
+def set_level_data(params, constant_K=0.0, dpsi_ghosted=None, cuda=False):
     """The reference's set_initial_conditions [+ set_update_psi0(dpsi)] + set_a_coef + set_b_coef + set_rhs on one box:
     (multigrid_vars [8, nz+6, ny+6, nx+6], rhs, aCoef, bCoef [nz, ny, nx])"""
     N = tuple(params["N"])
@@ -121,7 +129,7 @@ def set_level_data(params, constant_K=0.0, dpsi_ghosted=None):
         d = np.ascontiguousarray(dpsi_ghosted, dtype=np.float64)
         assert d.shape == g
     p = to_struct(params)
-    lib().ref_set_level_data(C.byref(p), (C.c_int * 3)(*N), dx, constant_K, None if d is None else d.ctypes.data, mg, rhs, a, b)
+    lib(cuda).ref_set_level_data(C.byref(p), (C.c_int * 3)(*N), dx, constant_K, None if d is None else d.ctypes.data, mg, rhs, a, b)
     return mg, rhs, a, b
 
 
@@ -161,9 +169,9 @@ class ReferenceOperator:
     oracle/ref_shim/chombo_standin.H.  Fields E (dpsi, one ghost layer), R (rhs), A, B as arrays [k, j, i]."""
     FIELD = dict(E=0, R=1, A=2, B=3, LAMBDA=4, TMP=5)
 
-    def __init__(self, params):
-        """params: the oracle's parameter dict"""
-        self.L = lib()
+    def __init__(self, params, cuda=False):
+        """params: the oracle's parameter dict; cuda=True: the .ChF symbols are libmgic_b200.so's CUDA drop-ins"""
+        self.L = lib(cuda)
         N = tuple(params["N"])
         i3 = C.c_int * 3
         self.shape = (N[2], N[1], N[0])

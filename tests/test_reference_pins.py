@@ -439,3 +439,23 @@ def test_kernel_goldens_are_what_the_reference_computes(name, over):
     R.set("E", g["e"])
     R.precond()
     assert np.array_equal(R.get("E"), g["precond"])
+
+
+# ---- INTEGRATION.md section A for real: the reference's own operator class and source-term code with their .ChF symbols
+# resolved by the PRODUCT's link-time drop-ins (include/mgic_chf.h; CUDA kernels behind the Fortran ABI) -- oracle/Makefile
+# target ref_cuda links them with --no-undefined.
+@live
+def test_reference_classes_link_against_the_products_fortran_symbols():
+    import subprocess
+    if not os.path.exists(pyref.B200_SO):
+        pytest.skip("libmgic_b200.so is not built")
+    pyref.build()
+    assert os.path.exists(pyref.SO_CUDA)
+    nm = subprocess.run(["nm", "-D", pyref.SO_CUDA], capture_output=True, text=True).stdout
+    undefined = {l.split()[-1] for l in nm.splitlines() if " U " in l}
+    chf = {"gsrbhelmholtzvc3d_", "vccomputeop3d_", "vccomputeres3d_", "restrictresvc3d_", "getlaplacianpsif_", "getrhogradphif_"}
+    assert chf <= undefined                                   # not defined inside: they come from the product library
+    exported = subprocess.run(["nm", "-D", "--defined-only", pyref.B200_SO], capture_output=True, text=True).stdout
+    assert all(f" T {s}" in exported for s in chf)
+    assert "libmgic_b200.so" in subprocess.run(["ldd", pyref.SO_CUDA], capture_output=True, text=True).stdout
+    pyref.lib(cuda=True)                                      # loads (no compute call: those need a GPU and abort() without one)
