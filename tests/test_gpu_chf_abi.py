@@ -94,33 +94,47 @@ def test_source_kernels(ctx):
         assert np.array_equal(o1, o2) and o1.any()
 
 
+REFERENCE_ON_CUDA = r"""
+import sys
+import numpy as np
+from oracle import Oracle, pyref
+over = {"c16": dict(N=(16, 16, 16), max_grid_size=8, L=40.0),
+        "neumann_inhomogeneous": dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1), bc_value=0.25)}[sys.argv[1]]
+o = Oracle(**over)
+o.setup()
+mg, rhs, a, b = pyref.set_level_data(o.params, cuda=True)              # set_rhs / set_a_coef through the CUDA stencils
+assert np.array_equal(rhs, o.get("RHS")) and np.array_equal(a, o.get("A")), "source terms"
+R = pyref.ReferenceOperator(o.params, cuda=True)
+rng = np.random.default_rng(3)
+e, r = rng.standard_normal(R.shape), rng.standard_normal(R.shape)
+R.set("A", o.get("A")); R.set("B", o.get("B"))
+for homog in (True, False):
+    o.set("E", e); o.set("R", r); R.set("E", e); R.set("R", r)
+    assert np.array_equal(R.residual(homog), o.residual(0, homog)), "residualI"
+    assert np.array_equal(R.apply(homog), o.apply(0, homog)), "applyOpI"
+o.relax(0, 2); R.relax(2)
+assert np.array_equal(R.get("E"), o.get("E")), "levelGSRB"
+o.restrict(0)
+assert np.array_equal(R.restrict(), o.get("R", 1)), "restrictResidual"
+o.precond(0); R.precond()
+assert np.array_equal(R.get("E"), o.get("E")), "preCond"
+print("reference classes on the CUDA drop-ins: identical to the oracle")
+"""
+
+
 @pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a GPU is the driver's")
 @pytest.mark.parametrize("case", ["c16", "neumann_inhomogeneous"])
 def test_reference_operator_class_on_the_cuda_drop_ins(case):
     """INTEGRATION.md section A end to end: the reference's own VariableCoeffPoissonOperator.cpp / SetBCs.cpp / SetLevelData.cpp
     (compiled unmodified into oracle/_ref/libmgic_ref_cuda.so, built where /root/reference exists and shipped with the
     snapshot) call gsrbhelmholtzvc3d_ ... getrhogradphif_ per box -- and those symbols are libmgic_b200.so's CUDA kernels
-    behind the Fortran ABI.  Results: the oracle's, bit for bit."""
-    from oracle import Oracle, pyref
+    behind the Fortran ABI.  Results: the oracle's, bit for bit.  Runs in a child process: the Fortran ABI has no error
+    return, it abort()s like MAYDAYERROR."""
+    import subprocess
+    import sys
+    from oracle import pyref
     if not os.path.exists(pyref.SO_CUDA):
         pytest.skip("oracle/_ref/libmgic_ref_cuda.so was not built (needs /root/reference at build time)")
-    over = {"c16": dict(N=(16, 16, 16), max_grid_size=8, L=40.0),
-            "neumann_inhomogeneous": dict(N=(24, 16, 32), max_grid_size=8, L=60.0, bc_lo=(1, 0, 1), bc_hi=(0, 1, 1), bc_value=0.25)}[case]
-    o = Oracle(**over)
-    o.setup()
-    mg, rhs, a, b = pyref.set_level_data(o.params, cuda=True)              # set_rhs / set_a_coef through the CUDA stencils
-    assert np.array_equal(rhs, o.get("RHS")) and np.array_equal(a, o.get("A"))
-    R = pyref.ReferenceOperator(o.params, cuda=True)
-    rng = np.random.default_rng(3)
-    e, r = rng.standard_normal(R.shape), rng.standard_normal(R.shape)
-    R.set("A", o.get("A")); R.set("B", o.get("B"))
-    for homog in (True, False):
-        o.set("E", e); o.set("R", r); R.set("E", e); R.set("R", r)
-        assert np.array_equal(R.residual(homog), o.residual(0, homog))
-        assert np.array_equal(R.apply(homog), o.apply(0, homog))
-    o.relax(0, 2); R.relax(2)
-    assert np.array_equal(R.get("E"), o.get("E"))
-    o.restrict(0)
-    assert np.array_equal(R.restrict(), o.get("R", 1))
-    o.precond(0); R.precond()
-    assert np.array_equal(R.get("E"), o.get("E"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", REFERENCE_ON_CUDA, case], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
