@@ -1,9 +1,14 @@
-"""Generates tests/golden/*.npz from the CPU oracle (python tests/golden/make_golden.py).
+"""Generates tests/golden/kernels_*.npz and solver_*.npz from the CPU oracle (python tests/golden/make_golden.py).
 
-The reference ships NO golden vectors and cannot be built here (needs Chombo 3.2 + Fortran + MPI), so these
-fixtures are the repo's own pins ("parity unpinned" upstream): they freeze the oracle's output so
-that (a) an accidental change of the oracle is caught on CPU and (b) the CUDA path is checked against the same
-numbers on the GPU box, where /root/reference does not exist.
+The reference ships NO golden vectors and cannot be built as a whole here (needs Chombo 3.2 + Fortran + MPI), so these
+fixtures freeze the oracle's output so that (a) an accidental change of the oracle is caught on CPU and (b) the CUDA
+path is checked against the same numbers on the GPU box, where /root/reference does not exist.  Provenance: every array
+of the kernels_*.npz files that the reference's own code can compute -- source terms, lambda and coefficients of every
+MG depth, residual, applyOp, restricted residual, relaxed and preconditioned fields -- is reproduced bit for bit by the
+reference's C++ compiled unmodified plus its translated .ChF kernels (oracle/_ref;
+tests/test_reference_pins.py::test_kernel_goldens_are_what_the_reference_computes).  The solver_*.npz files (V-cycles,
+BiCGStab, nonlinear loop) rest on the oracle's restatement of Chombo's algorithms and have no upstream pin.
+See make_reference_golden.py for the fixture written by the reference's code itself.
 """
 import os
 import sys
