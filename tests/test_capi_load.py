@@ -51,11 +51,35 @@ def test_no_device_fails_loudly():
         m.Context(0)
 
 
+def test_bad_arguments_are_refused_before_any_device_work():
+    """every entry point checks its arguments first: NULL handles come back as MGIC_ERR_ARG with a message, with or without a GPU"""
+    L = m.lib()
+    vp = C.c_void_p
+    out = vp()
+    d = C.c_double()
+    calls = [
+        lambda: L.mgic_amr_create_levels(None, 0, None, None, C.byref(out)),
+        lambda: L.mgic_amr_create(None, 0, None, C.byref(out)),
+        lambda: L.mgic_amr_vcycle(None, None, None),
+        lambda: L.mgic_amr_norm(None, None, 0, C.byref(d)),
+        lambda: L.mgic_amr_outer_solve(None, None, None, None, None, None, 0),
+        lambda: L.mgic_op_norm(None, None, 0, C.byref(d)),
+        lambda: L.mgic_op_relax(None, None, None, 1),
+        lambda: L.mgic_mg_vcycle(None, None, None),
+    ]
+    for call in calls:
+        rc = call()
+        assert rc != 0 and L.mgic_last_error()
+        with pytest.raises(m.MgicError):
+            m._capi.check(rc)
+    assert L.mgic_amr_levels(None) == 0 and L.mgic_amr_nodes(None) == 0 and L.mgic_amr_destroy(None) == 0
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "mg_ic_code_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".H", ".cpp", ".hpp")):
                 src = open(os.path.join(dp, f)).read()
                 for pat in (r"^\s*(from|import)\s+oracle", r"import_module\(.oracle", r"libmgic_oracle", r"#include\s+.*oracle"):
                     assert not re.search(pat, src, flags=re.M), f"{f} reaches into oracle/ ({pat})"
