@@ -355,8 +355,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
   if (c->bottomKernel != 3 && n <= 262144) {
     // ONE cluster; 16 CTAs (non-portable size) when the level is big enough to use them and the device can place it
     void (*ck)(BottomArgs) = o->b ? k_bottom_bicgstab_cluster<true> : k_bottom_bicgstab_cluster<false>;
-    static int maxCluster[2] = {0, 0};
-    int &mc = maxCluster[o->b ? 1 : 0];
+    int &mc = *mgic_dev_cache(c->device, (const void *)ck, 0, 0);
     if (!mc) {
       mc = CSIZE;
       if (cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
@@ -381,8 +380,7 @@ int bottom_bicgstab(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_field *
     return MGIC_OK;
   }
   void *kern = o->b ? (void *)k_bottom_bicgstab<true> : (void *)k_bottom_bicgstab<false>;
-  static int perSM[2] = {0, 0};
-  int &per = perSM[o->b ? 1 : 0];
+  int &per = *mgic_dev_cache(c->device, kern, 0, 0);
   if (!per) MGIC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, BT, 0));
   long long blocks = (n + BT - 1) / BT;
   // few, fat blocks keep the grid barrier cheap; never more than can be co-resident (cooperative launch)

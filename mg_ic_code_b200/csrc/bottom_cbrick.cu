@@ -435,8 +435,7 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
   void (*kern)(CbArgs) = NT == 512 ? (o->b ? k_bottom_cbrick<true, 512> : k_bottom_cbrick<false, 512>)
                                    : (o->b ? k_bottom_cbrick<true, 1024> : k_bottom_cbrick<false, 1024>);
   const int nvec = o->b ? 5 : 4;
-  static int nonPortable[4] = {-1, -1, -1, -1};
-  int &npok = nonPortable[(o->b ? 1 : 0) + (NT == 512 ? 0 : 2)];
+  int &npok = *mgic_dev_cache(c->device, (const void *)kern, 0, -1);
   if (npok < 0) {
     npok = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : 0;
     cudaGetLastError();
@@ -447,12 +446,11 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
   struct Cand { int cs, nb[3], maxp, count; size_t stride; };
   std::vector<Cand> cands;
   // clusters the device can hold at once, per cluster size (1024-thread CTAs: one per SM whatever the shared memory)
-  static int maxAct[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
-  int *ma = maxAct[(o->b ? 1 : 0) + (NT == 512 ? 0 : 2)];
+  int *ma[2] = {mgic_dev_cache(c->device, (const void *)kern, 1, -1), mgic_dev_cache(c->device, (const void *)kern, 2, -1)};
   for (int ci = 0; ci < 2; ci++) {
-    if (ma[ci] >= 0) continue;
+    if (*ma[ci] >= 0) continue;
     const int cs = ci ? 8 : 16;
-    ma[ci] = 0;
+    *ma[ci] = 0;
     if (cs == 16 && !npok) continue;
     const size_t smem = 160 * 1024;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -462,7 +460,7 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) ma[ci] = n;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) *ma[ci] = n;
     cudaGetLastError();
   }
   const int nn[3] = {g.nx, g.ny, g.nz};
@@ -474,7 +472,7 @@ int bottom_bicgstab_cbrick(mgic_op *o, mgic_field *e, const mgic_field *r, mgic_
       for (int nby = 1; nby <= 8; nby++)
         for (int nbx = 1; nbx <= 8; nbx++) {
           const int count = nbx * nby * nbz;
-          if (count > ma[cs == 16 ? 0 : 1] || nn[0] / nbx < 8 || nn[1] / nby < 8 || nn[2] / nbz < 8) continue;
+          if (count > *ma[cs == 16 ? 0 : 1] || nn[0] / nbx < 8 || nn[1] / nby < 8 || nn[2] / nbz < 8) continue;
           if (rmin(2, nbz) < cs) continue;
           Cand q;
           q.cs = cs; q.nb[0] = nbx; q.nb[1] = nby; q.nb[2] = nbz; q.count = count;

@@ -291,8 +291,7 @@ int bottom_bicgstab_dsmem(mgic_op *o, mgic_field *e, const mgic_field *r, int *d
   if (g.nx > 1023 || g.ny > 1023 || g.nz > 2047) return MGIC_OK;
   const int nvec = o->b ? 12 : 11;
   void (*kern)(DsArgs) = o->b ? k_bottom_dsmem<true> : k_bottom_dsmem<false>;
-  static int maxCluster[2] = {-1, -1};
-  int &mc = maxCluster[o->b ? 1 : 0];
+  int &mc = *mgic_dev_cache(c->device, (const void *)kern, 0, -1);
   // largest cluster (<= 16, dividing nz) whose per-CTA slab fits shared memory and the per-thread cell budget
   for (int cs = 16; cs >= 1; cs >>= 1) {
     if (g.nz % cs) continue;

@@ -7,6 +7,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "mgic_internal.h"
 
@@ -19,6 +22,15 @@ void mgic_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 extern "C" const char *mgic_last_error(void) { return g_err; }
+
+int *mgic_dev_cache(int device, const void *key, int sub, int init) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, const void *, int>, int> slots;   // node-based: the returned pointers stay valid
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = slots.find(std::make_tuple(device, key, sub));
+  if (it == slots.end()) it = slots.emplace(std::make_tuple(device, key, sub), init).first;
+  return &it->second;
+}
 extern "C" const char *mgic_version(void) { return "mgic_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -107,6 +119,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
   else if (!strcmp(name, "p2p_halo")) c->p2pHalo = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
+  c->cfgEpoch++;   // captured V-cycle graphs bake the options in: they are re-captured after any change
   return MGIC_OK;
 }
 extern "C" long long mgic_ctx_get_option(mgic_ctx *c, const char *name) {
@@ -661,6 +674,7 @@ extern "C" int mgic_op_set_val(mgic_op *o, mgic_field *y, double v) {
 extern "C" int mgic_op_set_smoother(mgic_op *o, int kind) {
   MGIC_REQUIRE(o && (kind == 0 || kind == 1), "smoother kind must be 0 or 1");
   o->smoother = kind;
+  o->ctx->cfgEpoch++;
   return MGIC_OK;
 }
 
@@ -831,7 +845,10 @@ struct mgic_mg {
   int *d_bottomOut = nullptr;   // device {iterations, status} of the last persistent bottom solve
   bool bottomOnDevice = false;
   // V-cycle graphs, keyed by the (correction, residual) arrays they were captured for
-  struct VGraph { const void *e, *r; bool zero; cudaGraphExec_t exec; long long launches; };
+  // ... and by everything else a capture bakes in: the option epoch of the context and the ping-pong partner of the
+  // finest level (fused sweeps swap the field's array with op->scratch, so after an odd number of caller-driven sweeps
+  // the same field pointer pairs with a different scratch array)
+  struct VGraph { const void *e, *r; bool zero; cudaGraphExec_t exec; long long launches; long long epoch; const void *scratch0; };
   std::vector<VGraph> graphs;
   bool graphBroken = false;
   // multi-rank agglomeration: from depth dA down every rank holds the WHOLE level (all-gather of the restricted
@@ -909,7 +926,9 @@ extern "C" int mgic_mg_create_ex(mgic_ctx *c, const mgic_params *P, mgic_field *
     mg->bIsOne = (cnt == 0.0) && !(flags & MGIC_MG_KEEP_B);
   }
   for (int depth = 0;; depth++) {
-    if (P->preCondSolverDepth >= 0 && depth > P->preCondSolverDepth) break;  // [Chombo] MultiGrid m_maxDepth
+    // [Chombo 3.2] MultiGrid::define: an operator is pushed, m_depth++, and the next one is asked for only while
+    // (m_depth < a_maxDepth || a_maxDepth < 0): maxDepth = D >= 1 gives D operators, D = 0 gives the one it always has
+    if (P->preCondSolverDepth >= 0 && depth >= (P->preCondSolverDepth > 1 ? P->preCondSolverDepth : 1)) break;
     const int coarsening = 1 << depth;
     // Factory.cpp:168-172: boxes (the max_grid_size lattice) must be coarsenable by coarsening * s_maxCoarse
     if (coarsening > 1 && (P->max_grid_size % (coarsening * s_maxCoarse)) != 0) break;
@@ -995,6 +1014,7 @@ extern "C" int mgic_mg_refresh_coefs(mgic_mg *mg) {
 }
 extern "C" int mgic_mg_set_smoother(mgic_mg *mg, int kind) {
   MGIC_REQUIRE(mg, "mg is NULL");
+  mg->ctx->cfgEpoch++;
   for (auto *o : mg->ops) MGIC_TRY(mgic_op_set_smoother(o, kind));
   return MGIC_OK;
 }
@@ -1130,8 +1150,13 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
     mg->warm = true;
     return mg_cycle(mg, 0, e, r, eIsZero);
   }
+  for (size_t gi = 0; gi < mg->graphs.size();) {   // stale captures (options / smoother changed since): drop them
+    if (mg->graphs[gi].epoch != c->cfgEpoch) { cudaGraphExecDestroy(mg->graphs[gi].exec); mg->graphs.erase(mg->graphs.begin() + gi); }
+    else gi++;
+  }
+  const void *scr0 = mg->ops[0]->scratch ? (const void *)mg->ops[0]->scratch->base : nullptr;
   for (auto &g : mg->graphs)
-    if (g.e == e->p && g.r == r->p && g.zero == eIsZero) {
+    if (g.e == e->p && g.r == r->p && g.zero == eIsZero && g.scratch0 == scr0) {
       MGIC_CUDA(cudaGraphLaunch(g.exec, c->stream));
       c->launches += g.launches;
       mg->bottomOnDevice = true;
@@ -1186,7 +1211,7 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
     mg->graphBroken = true;
     return mg_cycle(mg, 0, e, r, eIsZero);
   }
-  mg->graphs.push_back({e->p, r->p, eIsZero, exec, nl});
+  mg->graphs.push_back({e->p, r->p, eIsZero, exec, nl, c->cfgEpoch, (const void *)mg->ops[0]->scratch->base});
   MGIC_CUDA(cudaGraphLaunch(exec, c->stream));
   c->launches += nl;
   mg->bottomOnDevice = true;
@@ -1637,7 +1662,11 @@ extern "C" int mgic_update_psi0(mgic_vars *v, mgic_op *op0, mgic_field *dpsi, do
   REQ_SHAPE(op0, dpsi);
   MGIC_REQUIRE(vars_match(v, dpsi), "dpsi does not match multigrid_vars");
   MGIC_TRY(halo(op0, dpsi, 1));  // :249 (the reference exchanges three layers; one is read)
-  MGIC_TRY(mgk::update_psi(v, op0->geom(), op0->bck(true), dpsi->p));
+  // dpsi's domain-face ghost as [Chombo] BiCGStabSolver leaves it: residual(r, phi, rhs, homogeneous = false) filled it with
+  // the INHOMOGENEOUS value from phi's near cell, then phi += e over the ghosted FABs with e's ghost = a*e_near (every
+  // vector accumulated into e went through applyOp's homogeneous fill): a*near + b with b = 2*bc_value (Dirichlet) /
+  // +-dx*bc_value (Neumann).  Identical to the homogeneous form for params.txt's bc_value = 0.
+  MGIC_TRY(mgk::update_psi(v, op0->geom(), op0->bck(false), dpsi->p));
   if (dpsi_norm) {
     double s;
     MGIC_TRY(local_reduce(op0, dpsi, nullptr, 2, &s));
@@ -1652,6 +1681,7 @@ extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_nor
                              double *psi_out) {
   MGIC_REQUIRE(c && P, "NULL argument");
   MGIC_REQUIRE(c->nranks == 1, "mgic_nl_solve drives a single GPU; multi-rank callers compose the pieces per rank");
+  MGIC_REQUIRE(P->max_level == 0, "mgic_nl_solve: single AMR level (max_level = 0); hierarchies go through mgic_amr_nl_solve");
   mgic_vars *vars = nullptr;
   mgic_op *lay = nullptr;
   mgic_field *dpsi = nullptr, *rhs = nullptr, *aC = nullptr, *bC = nullptr;

@@ -338,14 +338,12 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   using F = Fused<TY, HAS_B, MODE>;
   mgic_ctx *c = o->ctx;
   auto kern = k_gsrb_fused<TY, HAS_B, MODE, MINB>;
-  static bool attrSet = false;
-  static int resident = 1;
-  if (!attrSet) {
+  int &resident = *mgic_dev_cache(c->device, (const void *)kern, 0, 0);   // per device: the opt-in and the occupancy
+  if (!resident) {
     MGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM));
     int per = 1;
     MGIC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, F::NT, F::SMEM));
     resident = (per < 1 ? 1 : per) * c->numSMs;
-    attrSet = true;
   }
   FusedArgs A;
   A.g = o->geom();

@@ -34,6 +34,11 @@ void mgic_set_error(const char *fmt, ...);
     }                                                            \
   } while (0)
 
+// One-time kernel setup (cudaFuncSetAttribute opt-ins, occupancy queries) is PER DEVICE: a process may hold contexts on
+// several devices.  mgic_dev_cache returns a stable int slot for (device, key), created with `init` on first use
+// (mutex-protected map in capi.cu); callers fill it once per device.
+int *mgic_dev_cache(int device, const void *key, int sub, int init);
+
 // ---- kernel-side geometry ---------------------------------------------------
 // Face order: 0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi, 4 z-lo, 5 z-hi.
 // type: 0 Dirichlet, 1 Neumann, 2 periodic, 3 interior (the neighbour plane is in memory: z-slab halo)
@@ -101,6 +106,7 @@ struct mgic_ctx {
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
+  long long cfgEpoch = 0;                 // bumped by every option / smoother change: captured graphs of older epochs are dropped
   bool profiling = false;
   struct ProfEv { cudaEvent_t a, b; int tag; };
   std::vector<ProfEv> profEvents;

@@ -1042,6 +1042,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+// bench.py's reference arm: use n host threads whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 orc_problem *orc_create(const orc_params *p) {
   orc_problem *pb = new orc_problem;
   pb->P = *p;
@@ -1144,7 +1153,9 @@ int orc_define_solver(orc_problem *pb) {
   pb->ops.clear(); pb->e.clear(); pb->r.clear(); pb->tmp.clear();
   const int s_maxCoarse = 2;   // [Chombo] AMRPoissonOp::s_maxCoarse
   for (int depth = 0;; depth++) {
-    if (P.preCondSolverDepth >= 0 && depth > P.preCondSolverDepth) break;   // MultiGrid m_maxDepth [Chombo]
+    // [Chombo 3.2] MultiGrid::define: push an operator, m_depth++, ask for the next one only while
+    // (m_depth < a_maxDepth || a_maxDepth < 0)  =>  maxDepth D >= 1 gives D operators, D = 0 gives one
+    if (P.preCondSolverDepth >= 0 && depth >= (P.preCondSolverDepth > 1 ? P.preCondSolverDepth : 1)) break;
     int coarsening = 1;
     Box domain = pb->grids.domain;
     for (int i = 0; i < depth; i++) { coarsening *= 2; domain = domain.coarsened(2); }   // :161-166

@@ -108,6 +108,7 @@ typedef struct orc_problem orc_problem;
 orc_problem *orc_create(const orc_params *p);
 void orc_destroy(orc_problem *);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* overrides OMP_NUM_THREADS (bench.py reference arm under torchrun) */
 
 /* Main_PoissonSolver.cpp:79-95 */
 void orc_set_initial_conditions(orc_problem *);

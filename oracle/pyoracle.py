@@ -73,6 +73,7 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(OrcParams)]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         for name in ("orc_set_initial_conditions",):
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_set_coefs_and_rhs.argtypes = [C.c_void_p, C.c_double]
@@ -245,6 +246,14 @@ class Oracle:
     @property
     def num_threads(self):
         return self.L.orc_num_threads()
+
+
+def use_all_host_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return lib().orc_num_threads()
 
 
 class OraclePatch:

@@ -122,7 +122,6 @@ print("reference classes on the CUDA drop-ins: identical to the oracle")
 """
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a GPU is the driver's")
 @pytest.mark.parametrize("case", ["c16", "neumann_inhomogeneous"])
 def test_reference_operator_class_on_the_cuda_drop_ins(case):
     """INTEGRATION.md section A end to end: the reference's own VariableCoeffPoissonOperator.cpp / SetBCs.cpp / SetLevelData.cpp

@@ -242,6 +242,47 @@ def test_vcycle_parity(ctx, case, smooth):
         assert abs(rg - ro) <= 1e-10 * ro + 1e-13 * np.abs(rhs).max(), (cyc, rg, ro)
 
 
+def test_baseline_size_256_fused_sweep_and_vcycle(ctx):
+    """Config C2 (BASELINE.json configs[1]): single-level 256^3 Bowen-York binary, max_grid_size 32 -- the launch shapes
+    of the bench (multi-wave grids, z chunking of plan_chunks, the 10-row TMA tiles, zero-start and prolong-fused sweeps,
+    the one-cluster DSMEM bottom solver, CUDA-graph replay) against the oracle: fused sweeps BIT-EXACT on the finest
+    level, V(2,2) cycles to 1e-10 with the same bottom BiCGStab iteration count (GSRBHELMHOLTZVC3D,
+    VariableCoeffPoissonOperatorF.ChF:56-139, driven as MultiGrid::cycle)."""
+    p = Pair(ctx, **dict(N=(256, 256, 256), max_grid_size=32, numMGsmooth=2))
+    assert p.f.depths == p.nd == 5
+    e, r = p.rand(21)
+    p.load(e, r)
+    p.op.relax(p.e, p.r, 1)                     # one plain fused sweep on random data
+    p.o.relax(0, 1)
+    assert np.array_equal(p.e.download(), p.o.get("E"))
+    p.op.relax(p.e, p.r, 2)
+    p.o.relax(0, 2)
+    assert np.array_equal(p.e.download(), p.o.get("E"))
+    rhs = p.o.get("RHS")
+    p.o.load_rhs_zero_e()
+    p.r.upload(rhs); p.op.setToZero(p.e)
+    for cyc in range(3):
+        it_o = p.o.vcycle()
+        if cyc == 0:
+            p.f.vcycle_from_zero(p.e, p.r)      # zero-start first sweep
+        else:
+            p.f.vcycle(p.e, p.r)
+        assert p.f.last_bottom_iterations == it_o
+        eo, eg = p.o.get("E"), p.e.download()
+        assert relerr(eg, eo) < 1e-10, (cyc, relerr(eg, eo))
+        p.op.residual(p.t, p.e, p.r, True)
+        ro = np.abs(p.o.residual(0, True)).max()
+        rg = p.op.norm(p.t, 0)
+        assert abs(rg - ro) <= 1e-10 * ro + 1e-13 * np.abs(rhs).max(), (cyc, rg, ro)
+
+
+def test_mg_depth_limit_follows_chombo_maxdepth(ctx):
+    """preCondSolverDepth = D >= 1 builds D operators, D = 0 one ([Chombo 3.2] MultiGrid::define); same as the oracle"""
+    for D in (0, 1, 2, 3, 9):
+        p = Pair(ctx, **dict(CASES["c64"], preCondSolverDepth=D))
+        assert p.f.depths == p.nd == min(max(D, 1), 4)
+
+
 def test_vcycle_periodic(ctx):
     """is_periodic = 1.  With K = 0 the periodic constraint is not solvable (the reference then fixes K from the
     integrability condition, out of scope here) and V-cycles stagnate, so only ONE cycle is compared and the bottom solver
@@ -321,8 +362,12 @@ def test_source_terms(ctx):
     assert np.array_equal(r2.download(), rhs.download()) and np.array_equal(a2.download(), a.download())
 
 
-def test_outer_solve_and_update_psi(ctx):
-    over = dict(N=(32, 32, 32), max_grid_size=16, numMGsmooth=4)
+@pytest.mark.parametrize("bc", [dict(), dict(bc_value=0.03), dict(bc_lo=(1, 0, 1), bc_hi=(0, 1, 0), bc_value=-0.02)])
+def test_outer_solve_and_update_psi(ctx, bc):
+    """solver.solve + set_update_psi0 (SetLevelData.cpp:243-263): psi += dpsi over the ghosted box.  With bc_value != 0 the
+    ghost layer of dpsi is what [Chombo] BiCGStab leaves there: the INHOMOGENEOUS fill of the initial residual plus the
+    homogeneous ghosts of the accumulated correction = a*near + b."""
+    over = dict(N=(32, 32, 32), max_grid_size=16, numMGsmooth=4, **bc)
     o = Oracle(**over)
     o.setup()
     it_o, st_o, fn_o, norms_o = o.outer_solve()
@@ -344,8 +389,8 @@ def test_outer_solve_and_update_psi(ctx):
     psio = o.get_ghosted("MGVAR0", 1, comp=0)
     assert relerr(psig[1:-1, 1:-1, 1:-1], psio[1:-1, 1:-1, 1:-1]) < 1e-12
     for sl in ((0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1)), (slice(1, -1), 0, slice(1, -1)),
-               (slice(1, -1), slice(1, -1), -1)):
-        assert relerr(psig[sl], psio[sl]) < 1e-12
+               (slice(1, -1), -1, slice(1, -1)), (slice(1, -1), slice(1, -1), 0), (slice(1, -1), slice(1, -1), -1)):
+        assert relerr(psig[sl], psio[sl]) < 1e-12, sl
 
 
 def test_nl_solve_parity(ctx):

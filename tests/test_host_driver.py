@@ -67,7 +67,6 @@ def test_reference_main_compiles_unmodified_against_the_host_layer(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a GPU is the driver's")
 def test_reference_main_drives_the_b200_path(tmp_path):
     """the reference's unmodified main() and nonlinear loop on the B200 path: same NL history and psi as the oracle"""
     from oracle import Oracle

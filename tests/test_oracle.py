@@ -127,8 +127,10 @@ def test_mg_depth_follows_box_size():
     for box, depths in ((8, 3), (16, 4), (32, 5)):
         o = Oracle(N=(32, 32, 32), max_grid_size=box)
         assert o.setup() == depths
-    o = Oracle(N=(32, 32, 32), max_grid_size=16, preCondSolverDepth=1)
-    assert o.setup() == 2
+    # [Chombo 3.2] MultiGrid::define: maxDepth = D >= 1 builds D operators, D = 0 the finest one alone
+    for D, depths in ((0, 1), (1, 1), (2, 2), (3, 3), (9, 4)):
+        o = Oracle(N=(32, 32, 32), max_grid_size=16, preCondSolverDepth=D)
+        assert o.setup() == depths
 
 
 def test_coarse_average_matches_twin():
