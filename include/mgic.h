@@ -127,6 +127,18 @@ int mgic_op_create(mgic_ctx *, const int n[3], int k0, int nz_local, double dx, 
  * patch the coarse-fine ghost values come from the coarser level (next two functions).  Fields are patch-shaped. */
 int mgic_op_create_patch(mgic_ctx *, const int n_domain[3], const int lo[3], const int hi[3], double dx, double dx_coarse,
                          double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
+/* The same for an AMR level (or one connected part of it) made of SEVERAL boxes -- what BRMeshRefine hands to
+ * VariableCoeffPoissonOperatorFactory::define (Source/SetGrids.cpp:113-114, ...Factory.cpp:59-106): boxes of at most
+ * max_grid_size cells that touch and whose union need not be a rectangle.  boxes = nboxes x {lo0,lo1,lo2,hi0,hi1,hi2}
+ * (inclusive, the level's index space, disjoint, coarsenable by 2).  The level lives in ONE array over the union's
+ * bounding box with a cell mask: [Chombo] LevelData::exchange between the level's boxes (VariableCoeffPoissonOperator.cpp:
+ * 48,131,163,301) is a neighbour read, coarse-fine ghosts (homogeneousCFInterp / QuadCFInterp) are evaluated per cell.
+ * Fields have the bounding box's shape; cells outside the boxes are kept at zero.  Results are independent of how the
+ * union is cut into boxes.  A union that fills its bounding box is the rectangular patch above. */
+int mgic_op_create_patch_boxes(mgic_ctx *, const int n_domain[3], int nboxes, const int *boxes, double dx, double dx_coarse,
+                               double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out);
+long long mgic_op_valid_cells(const mgic_op *);            /* cells of the level's boxes (the bounding box for a rectangle) */
+int mgic_op_get_mask(const mgic_op *, unsigned char *host);  /* 1 = cell of the level, over the bounding box, x fastest */
 /* [Chombo] AMRPoissonOp::AMROperatorNF / AMRResidualNF (inherited by the reference's operator, VariableCoeffPoissonOperator.H:25)
  * on a patch that has a coarser but no finer level: QuadCFInterp::coarseFineInterp(phi, phi_coarse) -- per fine ghost cell
  * a second-order tangential Taylor interpolation of the coarse field, then the parabola through it and the two interior
@@ -142,8 +154,9 @@ int mgic_op_amr_residual_nf(mgic_op *patch, mgic_field *lhs, mgic_field *phi, co
  * outer BiCGStabSolver<Vector<LevelData<FArrayBox>*>> (Main_PoissonSolver.cpp:103-117,169-184) on a
  * hierarchy of levels: level 0 = the MG hierarchy `base` (one array), finer level l = a list of patch operators
  * (mgic_op_create_patch, coefficients set), each nested with refinement ratio 2 in ONE array of the level below
- * (proper nesting: two coarse cells inside it, except at domain faces) and separated from its siblings by at least one
- * coarse cell -- config C4's shape (one box on level 1, two disjoint boxes on level 2); touching boxes are rejected.
+ * (proper nesting: its coarse cells and their face neighbours are cells of that array, except at domain faces) and not
+ * touching its siblings -- boxes that touch form ONE node (mgic_op_create_patch_boxes), so a level is given as its
+ * connected components (config C4: one box on level 1, two disjoint boxes on level 2).
  * reflux is the reference's no-op (VariableCoeffPoissonOperator.cpp:264-271).
  * A LEVEL VECTOR is an array of mgic_amr_nodes() fields: [0] on the base level, then one per patch in creation order
  * (level 1's patches first).  npatches[l-1] = number of patches of level l; `patches` is the flattened list.
@@ -285,6 +298,32 @@ int mgic_set_rhs(mgic_vars *, mgic_field *rhs, double constant_K);
 int mgic_set_rhs_and_a_coef(mgic_vars *, mgic_field *rhs, mgic_field *aCoef, double constant_K);  /* both in one pass */
 /* set_update_psi0 (Source/SetLevelData.cpp:243-263) + computeNorm (Main_PoissonSolver.cpp:208) */
 int mgic_update_psi0(mgic_vars *, mgic_op *op0, mgic_field *dpsi, double *dpsi_norm);
+/* ----------------------------------------------------------------- the problem on an AMR hierarchy (max_level > 0)
+ * replaces: poissonSolve, Main_PoissonSolver.cpp:45-256, for a hierarchy: per level multigrid_vars / dpsi / rhs / aCoef /
+ * bCoef (:79-88), set_initial_conditions (:93, Source/SetLevelData.cpp:32-71 with the LEVEL's dx) and per nonlinear
+ * iteration (:131-216): set_rhs / set_a_coef / set_b_coef on every level (Source/SetLevelData.cpp:73-127,281-340),
+ * defineOperatorFactory + MultilevelLinearOp + BiCGStabSolver rebuilt (:163-178), solver.solve (:184), then per level
+ * QuadCFInterp::coarseFineInterp(dpsi, dpsi_coarser) + exchange + set_update_psi0 (:189-205, Source/SetLevelData.cpp:243-263)
+ * and computeNorm(dpsi, p = 2) over the cells no finer level covers (:208).
+ * A level > 0 is given as its connected components ("nodes"); a node is a list of boxes that may touch, held in ONE
+ * masked array (mgic_op_create_patch_boxes).  nnodes[l-1] = nodes of level l, nboxes[q] = boxes of finer node q (levels
+ * flattened, level 1 first), boxes = 6 ints each {lo0,lo1,lo2,hi0,hi1,hi2} in the level's index space (refinement ratio 2
+ * on every level, Source/PoissonParameters.cpp:75-79).  Node 0 is the base level (P->N).  One GPU. */
+typedef struct mgic_hier mgic_hier;
+int mgic_hier_create(mgic_ctx *, const mgic_params *P, int nfiner, const int *nnodes, const int *nboxes, const int *boxes, mgic_hier **out);
+int mgic_hier_destroy(mgic_hier *);
+int mgic_hier_nodes(const mgic_hier *);
+int mgic_hier_node_info(const mgic_hier *, int node, int *level, int lo[3], int n[3], long long *valid_cells);
+int mgic_hier_get_mask(const mgic_hier *, int node, unsigned char *host);            /* 1 = cell of the level, bounding-box shaped */
+int mgic_hier_set_initial_conditions(mgic_hier *);                                    /* Main_PoissonSolver.cpp:90-96 */
+int mgic_hier_nl_iteration(mgic_hier *, double *dpsi_norm, int *solver_iterations, int *solver_status);   /* :131-212 body */
+int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_iterations);                 /* :93 + the loop */
+/* what: 0..7 multigrid_vars component (0 = psi, MultigridUserVariables.hpp), 8 dpsi, 9 rhs, 10 aCoef; bounding-box shaped */
+int mgic_hier_download(const mgic_hier *, int node, int what, double *host);
+/* multigrid_vars of one AMR level > 0 and its psi update (the pieces mgic_hier composes) */
+int mgic_vars_create_patch(mgic_ctx *, const mgic_params *P, const mgic_op *patch, mgic_vars **out);
+int mgic_update_psi0_patch(mgic_vars *, mgic_op *patch, mgic_field *dpsi, const mgic_field *dpsi_coarse, const int coarse_lo[3]);
+
 /* the NL loop of Main_PoissonSolver.cpp:131-216 for a single level, fully device resident */
 int mgic_nl_solve(mgic_ctx *, const mgic_params *, double *dpsi_norms, int max_out, int *nl_iterations,
                   double *psi_out /* optional ghost-free host array */);

@@ -57,6 +57,8 @@ def lib():
         "mgic_op_create": [vp, i3, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_create_patch": [vp, i3, i3, i3, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
         "mgic_op_cf_ghosts": [vp, C.c_int, nd],
+        "mgic_op_create_patch_boxes": [vp, i3, C.c_int, ip, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double, pvp],
+        "mgic_op_get_mask": [vp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")],
         "mgic_amr_create": [vp, C.c_int, pvp, pvp], "mgic_amr_create_levels": [vp, C.c_int, ip, pvp, pvp],
         "mgic_amr_destroy": [vp], "mgic_amr_vcycle": [vp, pvp, pvp], "mgic_amr_node_info": [vp, C.c_int, ip, ip],
         "mgic_amr_apply": [vp, pvp, pvp, C.c_int], "mgic_amr_residual": [vp, pvp, pvp, pvp, C.c_int],
@@ -93,6 +95,13 @@ def lib():
         "mgic_set_rhs": [vp, vp, C.c_double], "mgic_set_rhs_and_a_coef": [vp, vp, vp, C.c_double],
         "mgic_update_psi0": [vp, vp, vp, dp],
         "mgic_nl_solve": [vp, C.POINTER(MgicParams), dp, C.c_int, ip, C.c_void_p],
+        "mgic_hier_create": [vp, C.POINTER(MgicParams), C.c_int, ip, ip, ip, pvp], "mgic_hier_destroy": [vp],
+        "mgic_hier_node_info": [vp, C.c_int, ip, i3, i3, C.POINTER(C.c_longlong)],
+        "mgic_hier_get_mask": [vp, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")],
+        "mgic_hier_set_initial_conditions": [vp], "mgic_hier_nl_iteration": [vp, dp, ip, ip],
+        "mgic_hier_nl_solve": [vp, dp, C.c_int, ip], "mgic_hier_download": [vp, C.c_int, C.c_int, nd],
+        "mgic_vars_create_patch": [vp, C.POINTER(MgicParams), vp, pvp],
+        "mgic_update_psi0_patch": [vp, vp, vp, vp, i3],
     }
     for name, argtypes in sig.items():
         f = getattr(L, name)
@@ -100,9 +109,11 @@ def lib():
         f.restype = C.c_int
     L.mgic_ctx_stream.argtypes = [vp]
     L.mgic_ctx_stream.restype = vp
+    L.mgic_op_valid_cells.argtypes = [vp]
+    L.mgic_op_valid_cells.restype = C.c_longlong
     L.mgic_ctx_launch_count.argtypes = [vp]
     L.mgic_ctx_launch_count.restype = C.c_longlong
-    for name in ("mgic_mg_depths", "mgic_mg_last_bottom_iterations", "mgic_mg_b_is_one", "mgic_amr_levels", "mgic_amr_nodes"):
+    for name in ("mgic_mg_depths", "mgic_mg_last_bottom_iterations", "mgic_mg_b_is_one", "mgic_amr_levels", "mgic_amr_nodes", "mgic_hier_nodes"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = C.c_int
     _lib = L

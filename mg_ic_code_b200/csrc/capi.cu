@@ -192,6 +192,8 @@ BCk mgic_op::bck(bool homogeneous) const {
   if (ctx->nranks > 1 && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
   for (int q = 0; q < 7; q++) k.cf[q] = 0.0;
   for (int f = 0; f < 6; f++) k.face[f] = nullptr;
+  k.mask = mask;
+  for (int d = 0; d < 3; d++) { k.plo[d] = plo[d]; k.ndom[d] = isPatch ? ndom[d] : n[d]; }
   if (isPatch) {
     // INTERPHOMO's constants, computed in its order ([Chombo] AMRPoissonOpF.ChF; oracle: Op::homogeneousCFInterp)
     const double x1 = dx;
@@ -283,11 +285,68 @@ extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const in
   return MGIC_OK;
 }
 
+// One AMR level > 0 (or one connected part of it) made of SEVERAL boxes of the refined domain -- BRMeshRefine's output:
+// boxes of at most max_grid_size cells that touch and whose union is no rectangle.  B200 layout: ONE array over the
+// union's bounding box plus a cell mask, instead of one FAB per box: the fine-fine ghost exchange between the level's
+// boxes ([Chombo] LevelData::exchange, VariableCoeffPoissonOperator.cpp:301) becomes a plain neighbour read, coarse-fine
+// ghosts are evaluated per cell (BCk::mask), and every kernel runs once per level instead of once per box.  Results do
+// not depend on how the union is cut into boxes (global-index colouring, exchange before each colour pass).
+// boxes = nboxes x {lo0, lo1, lo2, hi0, hi1, hi2}, inclusive, in the level's index space.
+extern "C" int mgic_op_create_patch_boxes(mgic_ctx *c, const int n_domain[3], int nboxes, const int *boxes, double dx, double dx_coarse,
+                                          double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out) {
+  MGIC_REQUIRE(c && n_domain && boxes && nboxes >= 1 && out && bc_lo && bc_hi, "bad argument");
+  int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+  for (int q = 0; q < nboxes; q++)
+    for (int d = 0; d < 3; d++) {
+      const int l = boxes[6 * q + d], h = boxes[6 * q + 3 + d];
+      MGIC_REQUIRE(l >= 0 && h < n_domain[d] && h - l + 1 >= 2, "box outside the domain or thinner than two cells");
+      MGIC_REQUIRE(l % 2 == 0 && h % 2 == 1, "boxes must be coarsenable by 2");
+      lo[d] = std::min(lo[d], l); hi[d] = std::max(hi[d], h);
+    }
+  MGIC_TRY(mgic_op_create_patch(c, n_domain, lo, hi, dx, dx_coarse, alpha, beta, bc_lo, bc_hi, bc_value, out));
+  mgic_op *o = *out;
+  const size_t nx = o->n[0], ny = o->n[1], nz = o->n[2];
+  o->hmask.assign(nx * ny * nz, 0);
+  for (int q = 0; q < nboxes; q++) {
+    const int *b = boxes + 6 * q;
+    for (int k = b[2]; k <= b[5]; k++)
+      for (int j = b[1]; j <= b[4]; j++) {
+        unsigned char *row = o->hmask.data() + (size_t)(b[0] - lo[0]) + nx * ((size_t)(j - lo[1]) + ny * (size_t)(k - lo[2]));
+        for (int i = b[0]; i <= b[3]; i++) {
+          if (row[i - b[0]]) { mgic_set_error("boxes %d overlaps an earlier box of the level (a DisjointBoxLayout is disjoint)", q); mgic_op_destroy(o); *out = nullptr; return MGIC_ERR_ARG; }
+          row[i - b[0]] = 1;
+        }
+      }
+  }
+  o->validCells = 0;
+  for (unsigned char m : o->hmask) o->validCells += m;
+  if ((size_t)o->validCells == nx * ny * nz) { o->hmask.clear(); return MGIC_OK; }   // the union IS the bounding box: the rectangular patch
+  // every masked-in cell must have a second masked-in cell inwards of each coarse-fine face (homogeneousCFInterp / QUADINTERP
+  // read two interior cells): guaranteed by boxes >= 2 cells thick, checked here for unions
+  MGIC_CUDA(cudaMalloc(&o->mask, o->hmask.size()));
+  MGIC_CUDA(cudaMemcpyAsync(o->mask, o->hmask.data(), o->hmask.size(), cudaMemcpyHostToDevice, c->stream));
+  MGIC_CUDA(cudaStreamSynchronize(c->stream));
+  return MGIC_OK;
+}
+extern "C" long long mgic_op_valid_cells(const mgic_op *o) {
+  if (!o) return 0;
+  return o->mask ? o->validCells : (long long)o->n[0] * o->n[1] * o->nzl;
+}
+// the level's cell mask over the bounding box (1 = a cell of the level's boxes), x fastest; all ones for a rectangular level
+extern "C" int mgic_op_get_mask(const mgic_op *o, unsigned char *host) {
+  MGIC_REQUIRE(o && host, "NULL argument");
+  const size_t n = (size_t)o->n[0] * o->n[1] * o->nzl;
+  if (o->mask) memcpy(host, o->hmask.data(), n);
+  else memset(host, 1, n);
+  return MGIC_OK;
+}
+
 extern "C" int mgic_op_destroy(mgic_op *o) {
   if (!o) return MGIC_OK;
   mgic_field_destroy(o->lambda);
   mgic_field_destroy(o->scratch);
-  for (int f = 0; f < 6; f++) cudaFree(o->cfFace[f]);
+  for (int f = 0; f < 6; f++) { cudaFree(o->cfFace[f]); cudaFree(o->cfCell[f]); }
+  cudaFree(o->mask);
   delete o;
   return MGIC_OK;
 }
@@ -349,7 +408,9 @@ extern "C" int mgic_op_get_lambda(mgic_op *o, mgic_field **l) {
 extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
   MGIC_REQUIRE(like && out, "NULL argument");
   MGIC_CUDA(cudaSetDevice(like->ctx->device));
-  return field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out);
+  MGIC_TRY(field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out));
+  (*out)->mask = like->mask;
+  return MGIC_OK;
 }
 extern "C" int mgic_field_destroy(mgic_field *f) {
   if (!f) return MGIC_OK;
@@ -363,6 +424,10 @@ extern "C" int mgic_field_upload(mgic_field *f, const double *host) {
   MGIC_REQUIRE(f && host, "NULL argument");
   const size_t n = (size_t)f->sz * f->nz;
   MGIC_CUDA(cudaMemcpyAsync(f->p, host + (size_t)f->k0 * f->sz, n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+  if (f->mask) {   // masked AMR level: whatever the caller holds outside the level's boxes is not data
+    Geom g; g.nx = f->nx; g.ny = f->ny; g.nz = f->nz; g.sy = f->sy; g.sz = f->sz; g.k0 = 0; g.gnz = f->nz;
+    MGIC_TRY(mgk::apply_mask(f->ctx, g, f->p, f->mask));
+  }
   MGIC_CUDA(cudaStreamSynchronize(f->ctx->stream));
   return MGIC_OK;
 }
@@ -537,6 +602,16 @@ static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *p
                  "the coarse field does not cover the coarsened patch grown by two cells (proper nesting)");
   }
   BCk k = o->bck(homogeneous);
+  if (o->mask) {
+    const size_t cells = (size_t)n[0] * n[1] * n[2];
+    for (int f = 0; f < 6; f++) {
+      if (!o->cfFace[f]) MGIC_CUDA(cudaMalloc(&o->cfFace[f], cells * sizeof(double)));
+      k.face[f] = o->cfFace[f];
+    }
+    MGIC_TRY(mgk::quad_cf_masked(o->ctx, o->geom(), o->mask, o->plo, o->ndom, o->dx, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfFace));
+    *out = k;
+    return MGIC_OK;
+  }
   for (int f = 0; f < 6; f++) {
     k.face[f] = nullptr;
     const int dir = f / 2, side = (f % 2) ? +1 : -1;
@@ -550,11 +625,26 @@ static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *p
   *out = k;
   return MGIC_OK;
 }
+// the same interpolation with CELL-indexed ghost arrays whatever the level's shape (face[f][cell] = the ghost beyond face f of
+// `cell`): what set_update_psi0 on an AMR level needs to carry psi's coarse-fine ghosts along (source.cu)
+static int quad_cf_cells(mgic_op *o, const mgic_field *phi, const mgic_field *pc, const int clo[3], bool homogeneous, BCk *out) {
+  MGIC_REQUIRE(o->isPatch && pc && clo, "coarse-fine interpolation needs an AMR patch operator and the coarser field");
+  const size_t cells = (size_t)o->n[0] * o->n[1] * o->n[2];
+  BCk k = o->bck(homogeneous);
+  for (int f = 0; f < 6; f++) {
+    if (!o->cfCell[f]) MGIC_CUDA(cudaMalloc(&o->cfCell[f], cells * sizeof(double)));
+    k.face[f] = o->cfCell[f];
+  }
+  MGIC_TRY(mgk::quad_cf_masked(o->ctx, o->geom(), o->mask, o->plo, o->ndom, o->dx, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfCell));
+  *out = k;
+  return MGIC_OK;
+}
 // the ghost values QuadCFInterp left on one coarse-fine face (0 x-lo ... 5 z-hi) at the last AMROperatorNF / AMRResidualNF:
 // x faces [j + ny*k], y faces [i + nx*k], z faces [i + nx*j]
 extern "C" int mgic_op_cf_ghosts(mgic_op *o, int face, double *host) {
   MGIC_REQUIRE(o && host && face >= 0 && face < 6, "bad argument");
   MGIC_REQUIRE(o->isPatch && o->cfFace[face], "no coarse-fine ghost values on this face yet");
+  MGIC_REQUIRE(!o->mask, "masked level: the ghost values are cell-indexed (not exposed)");
   const int dir = face / 2, ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
   MGIC_CUDA(cudaStreamSynchronize(o->ctx->stream));
   MGIC_CUDA(cudaMemcpy(host, o->cfFace[face], (size_t)o->n[ta] * o->n[tb] * sizeof(double), cudaMemcpyDeviceToHost));
@@ -669,7 +759,9 @@ extern "C" int mgic_op_set_to_zero(mgic_op *o, mgic_field *y) { return mgic_op_s
 extern "C" int mgic_op_set_val(mgic_op *o, mgic_field *y, double v) {
   MGIC_REQUIRE(o && y, "NULL argument");
   REQ_SHAPE(o, y);
-  return mgk::set_val(o->ctx, o->geom(), y->p, v);
+  MGIC_TRY(mgk::set_val(o->ctx, o->geom(), y->p, v));
+  if (o->mask && v != 0.0) MGIC_TRY(mgk::apply_mask(o->ctx, o->geom(), y->p, o->mask));
+  return MGIC_OK;
 }
 extern "C" int mgic_op_set_smoother(mgic_op *o, int kind) {
   MGIC_REQUIRE(o && (kind == 0 || kind == 1), "smoother kind must be 0 or 1");
@@ -1302,12 +1394,57 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
       }
       if (nd.parent < 0) return amr_fail(A, "patch %d of level %d is not nested in one box of the level below with refinement ratio 2", q, l);
       for (int d = 0; d < 3; d++) nd.off[d] = (o->plo[d] >> 1) - A->nodes[nd.parent].lo[d];
-      // siblings must not touch (their ghost cells would be each other's cells: a fine-fine exchange this version lacks)
+      // proper nesting against the parent's cells: every coarse cell under the patch and its six neighbours (inside the
+      // domain) must be cells of the parent level (QuadCFInterp reads them)
+      {
+        const AmrNode &pn = A->nodes[nd.parent];
+        const mgic_op *po = pn.op;
+        auto pvalid = [&](int ci, int cj, int ck) {   // coarse-level index -> is a cell of the parent node
+          const int li = ci - pn.lo[0], lj = cj - pn.lo[1], lk = ck - pn.lo[2];
+          if (li < 0 || lj < 0 || lk < 0 || li >= po->n[0] || lj >= po->n[1] || lk >= po->n[2]) return false;
+          return po->hmask.empty() || po->hmask[(size_t)li + (size_t)po->n[0] * ((size_t)lj + (size_t)po->n[1] * lk)] != 0;
+        };
+        bool nested = true;
+        for (int k = 0; k < o->n[2] && nested; k += 2)
+          for (int j = 0; j < o->n[1] && nested; j += 2)
+            for (int i = 0; i < o->n[0] && nested; i += 2) {
+              if (!o->hmask.empty() && !o->hmask[(size_t)i + (size_t)o->n[0] * ((size_t)j + (size_t)o->n[1] * k)]) continue;
+              const int c[3] = {(o->plo[0] + i) >> 1, (o->plo[1] + j) >> 1, (o->plo[2] + k) >> 1};
+              nested = pvalid(c[0], c[1], c[2]);
+              for (int f = 0; f < 6 && nested; f++) {
+                int q[3] = {c[0], c[1], c[2]};
+                q[f >> 1] += (f & 1) ? 1 : -1;
+                if (q[f >> 1] < 0 || q[f >> 1] >= o->ndom[f >> 1] / 2) continue;   // outside the domain: physical boundary
+                nested = pvalid(q[0], q[1], q[2]);
+              }
+            }
+        if (!nested) return amr_fail(A, "patch %d of level %d is not properly nested in the cells of the level below (one coarse cell all around)", q, l);
+      }
+      // the nodes of one level must not touch: touching boxes belong into ONE node (mgic_op_create_patch_boxes: a union of
+      // boxes in one masked array, where the fine-fine exchange is a neighbour read)
       for (int s2 = A->levelStart[l]; s2 < (int)A->nodes.size(); s2++) {
         const mgic_op *b = A->nodes[s2].op;
         bool apart = false;
         for (int d = 0; d < 3; d++) apart = apart || o->plo[d] > b->plo[d] + b->n[d] || b->plo[d] > o->plo[d] + o->n[d];
-        if (!apart) return amr_fail(A, "patches %d and %d of one level touch or overlap (merge them into one box)", s2 - A->levelStart[l], q);
+        if (apart) continue;
+        bool touch = o->hmask.empty() && b->hmask.empty();
+        if (!touch) {   // bounding boxes touch or overlap: decide on the cells (face, edge or corner contact all count)
+          auto valid = [](const mgic_op *w, int gi, int gj, int gk) {
+            const int li = gi - w->plo[0], lj = gj - w->plo[1], lk = gk - w->plo[2];
+            if (li < 0 || lj < 0 || lk < 0 || li >= w->n[0] || lj >= w->n[1] || lk >= w->n[2]) return false;
+            return w->hmask.empty() || w->hmask[(size_t)li + (size_t)w->n[0] * ((size_t)lj + (size_t)w->n[1] * lk)] != 0;
+          };
+          for (int k = 0; k < o->n[2] && !touch; k++)
+            for (int j = 0; j < o->n[1] && !touch; j++)
+              for (int i = 0; i < o->n[0] && !touch; i++) {
+                if (!valid(o, o->plo[0] + i, o->plo[1] + j, o->plo[2] + k)) continue;
+                for (int dk = -1; dk <= 1 && !touch; dk++)
+                  for (int dj = -1; dj <= 1 && !touch; dj++)
+                    for (int di = -1; di <= 1 && !touch; di++)
+                      touch = valid(b, o->plo[0] + i + di, o->plo[1] + j + dj, o->plo[2] + k + dk);
+              }
+        }
+        if (touch) return amr_fail(A, "patches %d and %d of one level touch or overlap (give them as ONE node: mgic_op_create_patch_boxes)", s2 - A->levelStart[l], q);
       }
       A->nodes.push_back(nd);
     }
@@ -1370,14 +1507,14 @@ static int amr_cycle(mgic_amr *A, int l) {
     AmrNode &n = A->nodes[q];
     AmrNode &pn = A->nodes[n.parent];
     MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
-    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, pn.res), under_patch(n, pn.res), n.tmp->p, n.tmp->sy, n.tmp->sz, 2, 0));
+    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, pn.res), under_patch(n, pn.res), n.tmp->p, n.tmp->sy, n.tmp->sz, 2, 0, n.op->mask));
   }
   MGIC_TRY(amr_cycle(A, l - 1));
   // ---- up
   for (int q = q0; q < q1; q++) {
     AmrNode &n = A->nodes[q];
     AmrNode &pn = A->nodes[n.parent];
-    MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_patch(n, pn.corr), pn.corr->sy, pn.corr->sz));
+    MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_patch(n, pn.corr), pn.corr->sy, pn.corr->sz, n.op->mask));
     MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
     MGIC_TRY(mgic_op_assign(n.op, n.res, n.tmp));
     MGIC_TRY(mgic_op_set_to_zero(n.op, n.tmp));
@@ -1432,7 +1569,8 @@ extern "C" int mgic_amr_zero_covered(mgic_amr *A, mgic_field *const *x) {
   MGIC_TRY(amr_check_vec(A, x));
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), 0.0));
+    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), 0.0, n.op->mask, n.op->n[0],
+                              (long long)n.op->n[0] * n.op->n[1]));
   }
   return MGIC_OK;
 }
@@ -1442,7 +1580,7 @@ extern "C" int mgic_amr_average_down(mgic_amr *A, mgic_field *const *x) {
   MGIC_TRY(amr_check_vec(A, x));
   for (size_t q = A->nodes.size() - 1; q >= 1; q--) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), x[q]->p, x[q]->sy, x[q]->sz, 2, 0));
+    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), x[q]->p, x[q]->sy, x[q]->sz, 2, 0, n.op->mask));
   }
   return MGIC_OK;
 }
@@ -1452,7 +1590,7 @@ static int amr_masked_copy(mgic_amr *A, mgic_field *const *x) {
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
     mgic_field *pt = A->nodes[n.parent].tmp;
-    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, pt), under_patch(n, pt), 0.0));
+    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, pt), under_patch(n, pt), 0.0, n.op->mask, n.op->n[0], (long long)n.op->n[0] * n.op->n[1]));
   }
   return MGIC_OK;
 }
@@ -1605,8 +1743,31 @@ extern "C" int mgic_vars_create(mgic_ctx *c, const mgic_params *P, int k0, int n
   *out = v;
   return MGIC_OK;
 }
+// multigrid_vars of an AMR level > 0 (Main_PoissonSolver.cpp:79-88 for ilev > 0): over the bounding box of the patch
+// operator's level, padded by one ghost layer; psi's coarse-fine ghost values live in six cell-indexed arrays (initial
+// value 1 like every psi ghost, SetLevelData.cpp:42-54)
+extern "C" int mgic_vars_create_patch(mgic_ctx *c, const mgic_params *P, const mgic_op *patch, mgic_vars **out) {
+  MGIC_REQUIRE(c && P && patch && out && patch->isPatch, "bad argument (needs a patch operator)");
+  MGIC_CUDA(cudaSetDevice(c->device));
+  mgic_vars *v = new mgic_vars;
+  v->ctx = c; v->P = *P;
+  for (int d = 0; d < 3; d++) { v->n[d] = patch->n[d]; v->lo[d] = patch->plo[d]; v->ndom[d] = patch->ndom[d]; }
+  v->isPatch = true; v->mask = patch->mask;
+  v->k0 = patch->plo[2]; v->nzl = patch->n[2]; v->dx = patch->dx;
+  v->sy = v->n[0] + 2; v->sz = v->sy * (v->n[1] + 2); v->sc = v->sz * (v->nzl + 2);
+  MGIC_CUDA(cudaMalloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
+  MGIC_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->sc * 8 * sizeof(double), c->stream));
+  const long long cells = (long long)v->n[0] * v->n[1] * v->nzl;
+  for (int f = 0; f < 6; f++) {
+    MGIC_CUDA(cudaMalloc(&v->psiG[f], (size_t)cells * sizeof(double)));
+    MGIC_TRY(mgk::fill(c, v->psiG[f], cells, 1.0));
+  }
+  *out = v;
+  return MGIC_OK;
+}
 extern "C" int mgic_vars_destroy(mgic_vars *v) {
   if (!v) return MGIC_OK;
+  for (int f = 0; f < 6; f++) cudaFree(v->psiG[f]);
   cudaFree(v->d);
   delete v;
   return MGIC_OK;
@@ -1619,7 +1780,7 @@ static int vars_copy(const mgic_vars *v, int comp, double *host, int ghost) {
   p.srcPtr = make_cudaPitchedPtr(v->d + (size_t)comp * v->sc, (size_t)v->sy * sizeof(double), v->sy, v->n[1] + 2);
   p.srcPos = make_cudaPos((size_t)(1 - ghost) * sizeof(double), 1 - ghost, 1 - ghost);
   p.dstPtr = make_cudaPitchedPtr(host, hx * sizeof(double), hx, hy);
-  p.dstPos = make_cudaPos(0, 0, ghost ? 0 : v->k0);
+  p.dstPos = make_cudaPos(0, 0, (ghost || v->isPatch) ? 0 : v->k0);   // patches: a bounding-box-shaped host array
   p.extent = make_cudaExtent(hx * sizeof(double), hy, v->nzl + 2 * ghost);
   p.kind = cudaMemcpyDeviceToHost;
   MGIC_CUDA(cudaMemcpy3DAsync(&p, v->ctx->stream));
@@ -1632,11 +1793,13 @@ extern "C" int mgic_vars_download_ghosted(const mgic_vars *v, int comp, double *
 extern "C" int mgic_set_initial_conditions(mgic_vars *v, mgic_field *dpsi) {
   MGIC_REQUIRE(v, "vars is NULL");
   MGIC_TRY(mgk::init_conditions(v));
+  if (v->isPatch)
+    for (int f = 0; f < 6; f++) MGIC_TRY(mgk::fill(v->ctx, v->psiG[f], (long long)v->n[0] * v->n[1] * v->nzl, 1.0));
   if (dpsi) MGIC_CUDA(cudaMemsetAsync(dpsi->base, 0, dpsi->bytes, v->ctx->stream));  // dpsi = 0 (SetLevelData.cpp:55)
   return MGIC_OK;
 }
 static bool vars_match(const mgic_vars *v, const mgic_field *f) {
-  return f && f->nx == v->n[0] && f->ny == v->n[1] && f->nz == v->nzl && f->k0 == v->k0;
+  return f && f->nx == v->n[0] && f->ny == v->n[1] && f->nz == v->nzl && f->k0 == (v->isPatch ? 0 : v->k0);
 }
 extern "C" int mgic_set_a_coef(mgic_vars *v, mgic_field *aCoef, double constant_K) {
   MGIC_REQUIRE(v && vars_match(v, aCoef), "aCoef does not match multigrid_vars");
@@ -1653,7 +1816,9 @@ extern "C" int mgic_set_rhs_and_a_coef(mgic_vars *v, mgic_field *rhs, mgic_field
 extern "C" int mgic_set_b_coef(mgic_vars *v, mgic_field *bCoef) {
   MGIC_REQUIRE(v && vars_match(v, bCoef), "bCoef does not match multigrid_vars");
   Geom g; g.nx = bCoef->nx; g.ny = bCoef->ny; g.nz = bCoef->nz; g.sy = bCoef->sy; g.sz = bCoef->sz; g.k0 = bCoef->k0; g.gnz = bCoef->gnz;
-  return mgk::set_val(v->ctx, g, bCoef->p, 1.0);  // SetLevelData.cpp:338
+  MGIC_TRY(mgk::set_val(v->ctx, g, bCoef->p, 1.0));  // SetLevelData.cpp:338
+  if (bCoef->mask) MGIC_TRY(mgk::apply_mask(v->ctx, g, bCoef->p, bCoef->mask));
+  return MGIC_OK;
 }
 
 // set_update_psi0 (SetLevelData.cpp:243-263) + computeNorm(dpsi, p = 2) (Main_PoissonSolver.cpp:208)
@@ -1673,6 +1838,187 @@ extern "C" int mgic_update_psi0(mgic_vars *v, mgic_op *op0, mgic_field *dpsi, do
     const double dV = op0->dx * op0->dx * op0->dx;
     *dpsi_norm = sqrt(s * dV);  // [Chombo] computeNorm: (sum |x|^2 dx^3)^(1/2)
   }
+  return MGIC_OK;
+}
+
+// set_update_psi0 on an AMR level > 0 (Main_PoissonSolver.cpp:189-205): QuadCFInterp::coarseFineInterp(dpsi, dpsi_coarse),
+// the exchange between the level's boxes (a neighbour read here), psi += dpsi over the ghosted boxes -- psi's coarse-fine
+// ghosts are carried in the vars' cell-indexed ghost arrays, the physical ghosts in the padded array.
+extern "C" int mgic_update_psi0_patch(mgic_vars *v, mgic_op *patch, mgic_field *dpsi, const mgic_field *dpsi_coarse, const int coarse_lo[3]) {
+  MGIC_REQUIRE(v && patch && dpsi && dpsi_coarse && coarse_lo && v->isPatch && patch->isPatch, "bad argument");
+  REQ_SHAPE(patch, dpsi);
+  MGIC_REQUIRE(vars_match(v, dpsi), "dpsi does not match multigrid_vars");
+  BCk k;
+  MGIC_TRY(quad_cf_cells(patch, dpsi, dpsi_coarse, coarse_lo, false, &k));
+  return mgk::update_psi_patch(v, k, dpsi->p);
+}
+
+// ------------------------------------------------------------------------------------------------ the whole problem on a hierarchy
+// poissonSolve (Main_PoissonSolver.cpp:45-256) for max_level > 0: per level multigrid_vars / dpsi / rhs / aCoef / bCoef
+// (:79-88), set_initial_conditions (:93), and per nonlinear iteration (:131-216) the source terms of every level, the
+// operator factory + MultilevelLinearOp + BiCGStab rebuilt (:163-178), solver.solve (:184), the psi update with interlevel
+// and intralevel ghosts (:189-205) and the composite norm of dpsi (:208).  A level is given as its connected components
+// ("nodes"), each a list of boxes in ONE masked array (mgic_op_create_patch_boxes); node 0 is the base level.
+struct HierNode {
+  int level = 0;
+  mgic_op *op = nullptr;          // patch operator (owned); null for the base level (the MG hierarchy's, rebuilt per iteration)
+  mgic_vars *vars = nullptr;
+  mgic_field *dpsi = nullptr, *rhs = nullptr, *a = nullptr, *b = nullptr;
+};
+struct mgic_hier {
+  mgic_ctx *ctx = nullptr;
+  mgic_params P;            // max_level = number of finer levels
+  mgic_op *lay0 = nullptr;  // base-level geometry (field factory)
+  std::vector<HierNode> nodes;
+  std::vector<int> perLevel;   // nodes per finer level
+  int lastIterations = 0, lastStatus = 0;
+};
+extern "C" int mgic_hier_destroy(mgic_hier *H) {
+  if (!H) return MGIC_OK;
+  for (HierNode &n : H->nodes) {
+    mgic_field_destroy(n.dpsi); mgic_field_destroy(n.rhs); mgic_field_destroy(n.a); mgic_field_destroy(n.b);
+    mgic_vars_destroy(n.vars);
+    mgic_op_destroy(n.op);
+  }
+  mgic_op_destroy(H->lay0);
+  delete H;
+  return MGIC_OK;
+}
+// nfiner finer levels; nnodes[l-1] nodes on level l; nboxes[q] boxes in finer node q (flattened over levels);
+// boxes = all boxes, 6 ints each {lo0,lo1,lo2,hi0,hi1,hi2} in their level's index space
+extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, const int *nnodes, const int *nboxes, const int *boxes,
+                                mgic_hier **out) {
+  MGIC_REQUIRE(c && P && out && nfiner >= 0 && (nfiner == 0 || (nnodes && nboxes && boxes)), "bad argument");
+  MGIC_REQUIRE(c->nranks == 1, "mgic_hier drives one GPU");
+  MGIC_REQUIRE(!P->is_periodic, "the periodic constant-K branch (Main_PoissonSolver.cpp:137-150) is not implemented on hierarchies");
+  mgic_hier *H = new mgic_hier;
+  H->ctx = c; H->P = *P; H->P.max_level = nfiner;
+  int rc = MGIC_OK;
+  int bclo[3], bchi[3];
+  for (int d = 0; d < 3; d++) { bclo[d] = P->bc_lo[d]; bchi[d] = P->bc_hi[d]; }
+  const double dx0 = P->L / P->N[0];
+#define H_TRY(x) do { rc = (x); if (rc != MGIC_OK) { mgic_hier_destroy(H); return rc; } } while (0)
+  H_TRY(mgic_op_create(c, P->N, 0, P->N[2], dx0, P->alpha, P->beta, bclo, bchi, P->bc_value, &H->lay0));
+  {
+    HierNode n0;
+    H->nodes.push_back(n0);
+    HierNode &n = H->nodes.back();
+    H_TRY(mgic_vars_create(c, P, 0, P->N[2], &n.vars));
+    H_TRY(mgic_field_create(H->lay0, &n.dpsi)); H_TRY(mgic_field_create(H->lay0, &n.rhs));
+    H_TRY(mgic_field_create(H->lay0, &n.a)); H_TRY(mgic_field_create(H->lay0, &n.b));
+  }
+  int qn = 0, qb = 0;
+  for (int l = 1; l <= nfiner; l++) {
+    H->perLevel.push_back(nnodes[l - 1]);
+    int ndom[3];
+    for (int d = 0; d < 3; d++) ndom[d] = P->N[d] << l;                       // refRatio == 2 on every level (PoissonParameters.cpp:75-79)
+    const double dxl = dx0 / (double)(1 << l);
+    for (int q = 0; q < nnodes[l - 1]; q++, qn++) {
+      HierNode nd;
+      nd.level = l;
+      H->nodes.push_back(nd);
+      HierNode &n = H->nodes.back();
+      H_TRY(mgic_op_create_patch_boxes(c, ndom, nboxes[qn], boxes + 6 * (size_t)qb, dxl, 2.0 * dxl, P->alpha, P->beta, bclo, bchi,
+                                       P->bc_value, &n.op));
+      qb += nboxes[qn];
+      H_TRY(mgic_vars_create_patch(c, P, n.op, &n.vars));
+      H_TRY(mgic_field_create(n.op, &n.dpsi)); H_TRY(mgic_field_create(n.op, &n.rhs));
+      H_TRY(mgic_field_create(n.op, &n.a)); H_TRY(mgic_field_create(n.op, &n.b));
+    }
+  }
+#undef H_TRY
+  *out = H;
+  return MGIC_OK;
+}
+extern "C" int mgic_hier_nodes(const mgic_hier *H) { return H ? (int)H->nodes.size() : 0; }
+extern "C" int mgic_hier_node_info(const mgic_hier *H, int q, int *level, int lo[3], int n[3], long long *valid_cells) {
+  MGIC_REQUIRE(H && q >= 0 && q < (int)H->nodes.size(), "bad argument");
+  const HierNode &nd = H->nodes[q];
+  if (level) *level = nd.level;
+  for (int d = 0; d < 3; d++) {
+    if (lo) lo[d] = nd.op ? nd.op->plo[d] : 0;
+    if (n) n[d] = nd.op ? nd.op->n[d] : H->P.N[d];
+  }
+  if (valid_cells) *valid_cells = nd.op ? mgic_op_valid_cells(nd.op) : (long long)H->P.N[0] * H->P.N[1] * H->P.N[2];
+  return MGIC_OK;
+}
+// what: 0..7 multigrid_vars component (0 = psi), 8 dpsi, 9 rhs, 10 aCoef; host array has the node's (bounding box) shape
+extern "C" int mgic_hier_download(const mgic_hier *H, int q, int what, double *host) {
+  MGIC_REQUIRE(H && host && q >= 0 && q < (int)H->nodes.size() && what >= 0 && what <= 10, "bad argument");
+  const HierNode &nd = H->nodes[q];
+  if (what < 8) return mgic_vars_download(nd.vars, what, host);
+  return mgic_field_download(what == 8 ? nd.dpsi : what == 9 ? nd.rhs : nd.a, host);
+}
+extern "C" int mgic_hier_get_mask(const mgic_hier *H, int q, unsigned char *host) {
+  MGIC_REQUIRE(H && host && q >= 0 && q < (int)H->nodes.size(), "bad argument");
+  if (q == 0) { memset(host, 1, (size_t)H->P.N[0] * H->P.N[1] * H->P.N[2]); return MGIC_OK; }
+  return mgic_op_get_mask(H->nodes[q].op, host);
+}
+extern "C" int mgic_hier_set_initial_conditions(mgic_hier *H) {   // Main_PoissonSolver.cpp:90-96
+  MGIC_REQUIRE(H, "NULL argument");
+  for (HierNode &n : H->nodes) MGIC_TRY(mgic_set_initial_conditions(n.vars, n.dpsi));
+  return MGIC_OK;
+}
+// one pass of the nonlinear loop's body (Main_PoissonSolver.cpp:131-212, non-periodic: constant_K = 0)
+extern "C" int mgic_hier_nl_iteration(mgic_hier *H, double *dpsi_norm, int *solver_iterations, int *solver_status) {
+  MGIC_REQUIRE(H, "NULL argument");
+  mgic_ctx *c = H->ctx;
+  const size_t nn = H->nodes.size();
+  for (HierNode &n : H->nodes) {                                            // :154-160
+    MGIC_TRY(mgic_set_rhs_and_a_coef(n.vars, n.rhs, n.a, 0.0));
+    MGIC_TRY(mgic_set_b_coef(n.vars, n.b));
+  }
+  mgic_params P0 = H->P;
+  P0.max_level = 0;                                                         // the base level's MG hierarchy
+  mgic_mg *mg = nullptr;
+  mgic_amr *A = nullptr;
+  int rc = mgic_mg_create(c, &P0, H->nodes[0].a, H->nodes[0].b, &mg);      // :163-170 (rebuilt every NL iteration)
+  std::vector<mgic_op *> patches;
+  std::vector<mgic_field *> dpsi(nn), rhs(nn);
+  for (size_t q = 0; q < nn && rc == MGIC_OK; q++) {
+    HierNode &n = H->nodes[q];
+    dpsi[q] = n.dpsi; rhs[q] = n.rhs;
+    if (q == 0) continue;
+    // bCoef == 1 (set_b_coef, SetLevelData.cpp:330-340): b*x == x exactly, so the patch operators drop the stream like the
+    // base level does (mgic_mg_create detects it there)
+    rc = mgic_op_set_coefs(n.op, n.a, nullptr, H->P.alpha, H->P.beta);
+    patches.push_back(n.op);
+  }
+  if (rc == MGIC_OK) rc = mgic_amr_create_levels(mg, (int)H->perLevel.size(), H->perLevel.data(), patches.data(), &A);
+  int it = 0, st = 0;
+  if (rc == MGIC_OK) rc = mgic_amr_outer_solve(A, dpsi.data(), rhs.data(), &it, &st, nullptr, 0);   // :184
+  H->lastIterations = it; H->lastStatus = st;
+  // :189-205, coarsest level first (the finer level's coarse-fine ghosts come from the coarser level's dpsi)
+  if (rc == MGIC_OK) rc = mgic_update_psi0(H->nodes[0].vars, mg->ops[0], H->nodes[0].dpsi, nullptr);
+  for (size_t q = 1; q < nn && rc == MGIC_OK; q++) {
+    int level = 0, parent = -1;
+    rc = mgic_amr_node_info(A, (int)q, &level, &parent);
+    if (rc != MGIC_OK) break;
+    const HierNode &pn = H->nodes[parent];
+    const int zero[3] = {0, 0, 0};
+    rc = mgic_update_psi0_patch(H->nodes[q].vars, H->nodes[q].op, H->nodes[q].dpsi, pn.dpsi, pn.op ? pn.op->plo : zero);
+  }
+  double nrm = 0.0;
+  if (rc == MGIC_OK) rc = mgic_amr_norm(A, dpsi.data(), 2, &nrm);            // :208 computeNorm(dpsi, ..., p = 2)
+  mgic_amr_destroy(A);
+  mgic_mg_destroy(mg);
+  if (dpsi_norm) *dpsi_norm = nrm;
+  if (solver_iterations) *solver_iterations = it;
+  if (solver_status) *solver_status = st;
+  return rc;
+}
+extern "C" int mgic_hier_nl_solve(mgic_hier *H, double *dpsi_norms, int max_out, int *nl_iterations) {
+  MGIC_REQUIRE(H, "NULL argument");
+  MGIC_TRY(mgic_hier_set_initial_conditions(H));                            // :93
+  int its = 0;
+  for (int NL_iter = 0; NL_iter < H->P.max_NL_iterations; NL_iter++) {      // :131
+    double nrm = 0.0;
+    MGIC_TRY(mgic_hier_nl_iteration(H, &nrm, nullptr, nullptr));
+    if (dpsi_norms && NL_iter < max_out) dpsi_norms[NL_iter] = nrm;
+    its = NL_iter + 1;
+    if (nrm < H->P.tolerance || nrm > 1e5) break;                           // :212
+  }
+  if (nl_iterations) *nl_iterations = its;
   return MGIC_OK;
 }
 

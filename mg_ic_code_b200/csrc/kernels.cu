@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) k_gsrb_color(Geom g, BCk bc, double *__re
   const int i = 2 * t + ((j + k + g.k0 + color) & 1);
   if (i >= g.nx) return;
   const long long idx = i + j * g.sy + k * g.sz;
+  if (bc.mask && !bc.mask[idx]) return;   // masked AMR level: not a cell of the level's boxes
   const double c = phi[idx];
   const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
   phi[idx] = gsrb_point<HAS_B>(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp, a[idx], HAS_B ? b[idx] : 1.0, lam[idx], rhs[idx], alpha, beta,
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) k_op(Geom g, BCk bc, double *__restrict__
   const int k = blockIdx.z;
   if (i >= g.nx || j >= g.ny) return;
   const long long idx = i + j * g.sy + k * g.sz;
+  if (bc.mask && !bc.mask[idx]) return;
   const double c = phi[idx];
   const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
   double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__rest
   const int J = blockIdx.y * blockDim.y + threadIdx.y;
   const int K = blockIdx.z;
   if (2 * I >= g.nx || 2 * J >= g.ny) return;
+  if (bc.mask && !bc.mask[2 * I + 2 * J * g.sy + 2 * K * g.sz]) return;   // boxes are coarsenable: all eight cells or none
   double acc = 0.0;
 #pragma unroll
   for (int dk = 0; dk < 2; dk++)
@@ -104,11 +107,12 @@ __global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__rest
 
 // ---- prolongIncrement: [Chombo] AMRPoissonOpF.ChF PROLONG, m = 2 ---------------------------------------------
 __global__ void __launch_bounds__(128) k_prolong(Geom g, double *__restrict__ phi, const double *__restrict__ coarse,
-                                                 long long csy, long long csz) {
+                                                 long long csy, long long csz, const unsigned char *__restrict__ fineMask) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x;
   const int J = blockIdx.y * blockDim.y + threadIdx.y;
   const int K = blockIdx.z;
   if (2 * I >= g.nx || 2 * J >= g.ny) return;
+  if (fineMask && !fineMask[2 * I + 2 * J * g.sy + 2 * K * g.sz]) return;
   const double c = coarse[I + J * csy + K * csz];
 #pragma unroll
   for (int dk = 0; dk < 2; dk++)
@@ -208,6 +212,93 @@ __global__ void __launch_bounds__(256) k_quad_cf_face(QcfArgs A, const double *_
   face[qa + (long long)nA * qb] = (pa + b * x) + a * x * x;
 }
 
+// ---- the same interpolation for a masked AMR level (a union of boxes in one bounding-box array): one thread per cell of
+// the level, one value per face whose neighbour is a coarse-fine ghost (neither a cell of the level nor outside the
+// domain), stored cell-indexed: face[f][idx].  Arithmetic and its order are k_quad_cf_face's (the oracle's Op::quadCFInterp).
+struct QcfmArgs {
+  Geom g;
+  int plo[3], ndom[3], clo[3];
+  long long csy, csz;
+  double h;
+  double *face[6];
+};
+__device__ double quad_cf_eval(const QcfmArgs &A, int dir, int side, const int iv[3], long long idx, const double *__restrict__ phi,
+                               const double *__restrict__ coarse) {
+  const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+  const long long fs[3] = {1, A.g.sy, A.g.sz}, cs[3] = {1, A.csy, A.csz};
+  const double h = A.h, H = 2.0 * A.h;
+  int fg[3] = {A.plo[0] + iv[0], A.plo[1] + iv[1], A.plo[2] + iv[2]};   // the ghost cell in the level's index space
+  fg[dir] += side;
+  const int cA = fg[ta] >> 1, cB = fg[tb] >> 1, cD = fg[dir] >> 1;
+  const int cdA = A.ndom[ta] / 2, cdB = A.ndom[tb] / 2;
+  const long long csA = cs[ta], csB = cs[tb];
+  const double *cc = coarse + ((cA - A.clo[ta]) * csA + (cB - A.clo[tb]) * csB + (cD - A.clo[dir]) * cs[dir]);
+  const double c0 = cc[0];
+  double phistar = c0;
+  const double xa = (fg[ta] + 0.5) * h - (cA + 0.5) * H;
+  {
+    const bool hasLo = cA - 1 >= 0, hasHi = cA + 1 <= cdA - 1;
+    double d1, d2;
+    if (hasLo && hasHi) {
+      d1 = (cc[csA] - cc[-csA]) / (2.0 * H);
+      d2 = ((cc[csA] - 2.0 * c0) + cc[-csA]) / (H * H);
+    } else if (hasHi) {
+      d1 = ((4.0 * cc[csA] - 3.0 * c0) - cc[2 * csA]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[csA]) + cc[2 * csA]) / (H * H);
+    } else {
+      d1 = ((3.0 * c0 - 4.0 * cc[-csA]) + cc[-2 * csA]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[-csA]) + cc[-2 * csA]) / (H * H);
+    }
+    phistar = phistar + (d1 * xa + 0.5 * d2 * xa * xa);
+  }
+  const double xb = (fg[tb] + 0.5) * h - (cB + 0.5) * H;
+  {
+    const bool hasLo = cB - 1 >= 0, hasHi = cB + 1 <= cdB - 1;
+    double d1, d2;
+    if (hasLo && hasHi) {
+      d1 = (cc[csB] - cc[-csB]) / (2.0 * H);
+      d2 = ((cc[csB] - 2.0 * c0) + cc[-csB]) / (H * H);
+    } else if (hasHi) {
+      d1 = ((4.0 * cc[csB] - 3.0 * c0) - cc[2 * csB]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[csB]) + cc[2 * csB]) / (H * H);
+    } else {
+      d1 = ((3.0 * c0 - 4.0 * cc[-csB]) + cc[-2 * csB]) / (2.0 * H);
+      d2 = ((c0 - 2.0 * cc[-csB]) + cc[-2 * csB]) / (H * H);
+    }
+    phistar = phistar + (d1 * xb + 0.5 * d2 * xb * xb);
+  }
+  const bool corners = cA - 1 >= 0 && cA + 1 <= cdA - 1 && cB - 1 >= 0 && cB + 1 <= cdB - 1;
+  if (corners) {
+    const double mixed = (((cc[csA + csB] - cc[csA - csB]) - cc[-csA + csB]) + cc[-csA - csB]) / (4.0 * H * H);
+    phistar = phistar + mixed * xa * xb;
+  }
+  const double pb = phi[idx], pa = phi[idx - side * fs[dir]];   // first / second interior cell along the normal
+  const double x = 2.0 * h;
+  const double nref = 2.0;
+  const double a = (2.0 / h / h) * ((2.0 * phistar + pa * (nref + 1.0)) - pb * (nref + 3.0)) / (nref * nref + 4.0 * nref + 3.0);
+  const double b = (pb - pa) / h - a * h;
+  return (pa + b * x) + a * x * x;
+}
+__global__ void __launch_bounds__(256) k_quad_cf_masked(QcfmArgs A, const unsigned char *__restrict__ mask, const double *__restrict__ phi,
+                                                        const double *__restrict__ coarse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= A.g.nx || j >= A.g.ny) return;
+  const long long idx = i + j * A.g.sy + k * A.g.sz;
+  if (mask && !mask[idx]) return;   // mask == null: a rectangular level, every cell of the array
+  const int iv[3] = {i, j, k}, n[3] = {A.g.nx, A.g.ny, A.g.nz};
+  const long long fs[3] = {1, A.g.sy, A.g.sz};
+  for (int f = 0; f < 6; f++) {
+    const int dir = f >> 1, side = (f & 1) ? 1 : -1;
+    const int q = iv[dir] + side;
+    if (q >= 0 && q < n[dir] && (!mask || mask[idx + side * fs[dir]])) continue;      // a cell of the level
+    const int gq = A.plo[dir] + q;
+    if (gq < 0 || gq >= A.ndom[dir]) continue;                             // physical boundary
+    A.face[f][idx] = quad_cf_eval(A, dir, side, iv, idx, phi, coarse);
+  }
+}
+
 // ---- lambda: resetLambda (VariableCoeffPoissonOperator.cpp:220-249) ------------------------------------------
 __global__ void k_lambda(long long n, double *__restrict__ lam, const double *__restrict__ a, double alpha, double plus) {
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
@@ -293,11 +384,13 @@ __global__ void __launch_bounds__(256) k_reduce(long long n, const double *__res
 // ---- coefficient coarsening: [Chombo] CoarseAverage (AverageF.ChF AVERAGE / AVERAGEHARMONIC) -----------------
 // refScale = 1/nRef^3; fine cells summed ii fastest; arithmetic: sum*refScale; harmonic: 1/(sum(1/f)*refScale)
 __global__ void __launch_bounds__(128) k_coarse_average(Geom gc, double *__restrict__ c, const double *__restrict__ f,
-                                                        long long fsy, long long fsz, int nref, int harmonic) {
+                                                        long long fsy, long long fsz, int nref, int harmonic,
+                                                        const unsigned char *__restrict__ fineMask) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x;
   const int J = blockIdx.y * blockDim.y + threadIdx.y;
   const int K = blockIdx.z;
   if (I >= gc.nx || J >= gc.ny) return;
+  if (fineMask && !fineMask[I * nref + (J * nref) * fsy + (long long)(K * nref) * fsz]) return;   // not under the fine level
   const double refScale = 1.0 / (double)(nref * nref * nref);
   double sum = 0.0;
   for (int kk = 0; kk < nref; kk++)
@@ -311,12 +404,20 @@ __global__ void __launch_bounds__(128) k_coarse_average(Geom gc, double *__restr
 
 // y = v on a sub-box (g.nx x g.ny x g.nz cells, strides g.sy / g.sz of the array that contains it): [Chombo]
 // AMRPoissonOp::zeroCovered -- the cells of a level that a finer level covers -- for the composite norms and dot products
-__global__ void __launch_bounds__(128) k_box_set(Geom g, double *__restrict__ y, double v) {
+__global__ void __launch_bounds__(128) k_box_set(Geom g, double *__restrict__ y, double v, const unsigned char *__restrict__ fineMask,
+                                                 long long msy, long long msz) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x;
   const int J = blockIdx.y * blockDim.y + threadIdx.y;
   const int K = blockIdx.z;
   if (I >= g.nx || J >= g.ny) return;
+  if (fineMask && !fineMask[2 * I + 2 * J * msy + 2 * K * msz]) return;   // ratio 2: the coarse cell is not under the fine level
   y[I + J * g.sy + K * g.sz] = v;
+}
+
+// y = 0 outside the mask (uploads and constant fills of a masked AMR level: cells outside its boxes stay zero)
+__global__ void __launch_bounds__(256) k_apply_mask(long long n, double *__restrict__ y, const unsigned char *__restrict__ mask) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+    if (!mask[q]) y[q] = 0.0;
 }
 
 inline dim3 grid3(int nx, int ny, int nz, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
@@ -389,10 +490,23 @@ int quad_cf_face(mgic_ctx *c, const Geom &g, const int plo[3], const int ndom[3]
   return post_launch(c, "quad_cf_face");
 }
 
-int prolong(mgic_ctx *c, const Geom &g, double *phi, const double *coarse, long long csy, long long csz) {
+int quad_cf_masked(mgic_ctx *c, const Geom &g, const unsigned char *mask, const int plo[3], const int ndom[3], double h, const double *phi,
+                   const double *coarse, long long csy, long long csz, const int clo[3], double *const face[6]) {
+  QcfmArgs A;
+  A.g = g;
+  for (int d = 0; d < 3; d++) { A.plo[d] = plo[d]; A.ndom[d] = ndom[d]; A.clo[d] = clo[d]; }
+  A.csy = csy; A.csz = csz; A.h = h;
+  for (int f = 0; f < 6; f++) A.face[f] = face[f];
+  dim3 blk(64, 4, 1);
+  dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
+  k_quad_cf_masked<<<grd, blk, 0, c->stream>>>(A, mask, phi, coarse);
+  return post_launch(c, "quad_cf_masked");
+}
+
+int prolong(mgic_ctx *c, const Geom &g, double *phi, const double *coarse, long long csy, long long csz, const unsigned char *fineMask) {
   dim3 blk(32, 4, 1);
   dim3 grd = grid3(g.nx / 2, g.ny / 2, g.nz / 2, blk);
-  k_prolong<<<grd, blk, 0, c->stream>>>(g, phi, coarse, csy, csz);
+  k_prolong<<<grd, blk, 0, c->stream>>>(g, phi, coarse, csy, csz, fineMask);
   return post_launch(c, "prolong");
 }
 
@@ -449,18 +563,24 @@ int is_constant(mgic_ctx *c, const Geom &g, const double *x, double value, int s
   return post_launch(c, "is_constant");
 }
 
-int box_set_val(mgic_ctx *c, const Geom &g, double *y, double v) {
+int box_set_val(mgic_ctx *c, const Geom &g, double *y, double v, const unsigned char *fineMask, long long msy, long long msz) {
   dim3 blk(32, 4, 1);
   dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
-  k_box_set<<<grd, blk, 0, c->stream>>>(g, y, v);
+  k_box_set<<<grd, blk, 0, c->stream>>>(g, y, v, fineMask, msy, msz);
   return post_launch(c, "box_set_val");
 }
 
+int apply_mask(mgic_ctx *c, const Geom &g, double *y, const unsigned char *mask) {
+  const long long n = ncells(g);
+  k_apply_mask<<<ew_grid(c, n), 256, 0, c->stream>>>(n, y, mask);
+  return post_launch(c, "apply_mask");
+}
+
 int coarse_average(mgic_ctx *c, const Geom &gc, double *cp, const double *fine, long long fsy, long long fsz, int nref,
-                   int harmonic) {
+                   int harmonic, const unsigned char *fineMask) {
   dim3 blk(32, 4, 1);
   dim3 grd = grid3(gc.nx, gc.ny, gc.nz, blk);
-  k_coarse_average<<<grd, blk, 0, c->stream>>>(gc, cp, fine, fsy, fsz, nref, harmonic);
+  k_coarse_average<<<grd, blk, 0, c->stream>>>(gc, cp, fine, fsy, fsz, nref, harmonic, fineMask);
   return post_launch(c, "coarse_average");
 }
 

@@ -44,9 +44,27 @@ __device__ __forceinline__ double ghost(const BCk &bc, int f, double c, const do
   return bc.a[f] * c + bc.b[f];
 }
 
+// masked AMR level: neighbour beyond face f of cell idx (see BCk::mask)
+__device__ __forceinline__ double nb_masked(const BCk &bc, int f, bool inside, long long nidx, bool domainFace, double c, const double *p,
+                                            long long farIdx, long long idx) {
+  if (inside && bc.mask[nidx]) return p[nidx];               // a cell of the level: the fine-fine exchange
+  if (domainFace) return bc.a[f] * c + bc.b[f];              // ParseBC
+  if (bc.face[f]) return bc.face[f][idx];                    // QuadCFInterp's stored ghost
+  return cf_homog(bc.cf, p[farIdx], c);                      // homogeneousCFInterp
+}
+
 __device__ __forceinline__ Nb neighbours(const double *p, long long idx, int i, int j, int k, const Geom &g,
                                          const BCk &bc, double c) {
   Nb n;
+  if (bc.mask) {
+    n.xm = nb_masked(bc, 0, i > 0, idx - 1, bc.plo[0] + i == 0, c, p, idx + 1, idx);
+    n.xp = nb_masked(bc, 1, i < g.nx - 1, idx + 1, bc.plo[0] + i == bc.ndom[0] - 1, c, p, idx - 1, idx);
+    n.ym = nb_masked(bc, 2, j > 0, idx - g.sy, bc.plo[1] + j == 0, c, p, idx + g.sy, idx);
+    n.yp = nb_masked(bc, 3, j < g.ny - 1, idx + g.sy, bc.plo[1] + j == bc.ndom[1] - 1, c, p, idx - g.sy, idx);
+    n.zm = nb_masked(bc, 4, k > 0, idx - g.sz, bc.plo[2] + k == 0, c, p, idx + g.sz, idx);
+    n.zp = nb_masked(bc, 5, k < g.nz - 1, idx + g.sz, bc.plo[2] + k == bc.ndom[2] - 1, c, p, idx - g.sz, idx);
+    return n;
+  }
   n.xm = (i > 0) ? p[idx - 1] : ghost(bc, 0, c, p, idx + (g.nx - 1), idx + 1, j + g.ny * k);
   n.xp = (i < g.nx - 1) ? p[idx + 1] : ghost(bc, 1, c, p, idx - (g.nx - 1), idx - 1, j + g.ny * k);
   n.ym = (j > 0) ? p[idx - g.sy] : ghost(bc, 2, c, p, idx + (long long)(g.ny - 1) * g.sy, idx + g.sy, i + g.nx * k);

@@ -55,6 +55,14 @@ struct BCk {
   double a[6], b[6];  // ghost = a*centre + b   (Dirichlet: a=-1, b=2v; Neumann: a=+1, b=sign*dx*v)
   double cf[7];
   const double *face[6];
+  // AMR level made of SEVERAL boxes (a union that is not a rectangle: touching boxes, L shapes, ...): the level lives in
+  // ONE array over the union's bounding box and mask[cell] = 1 marks the cells of the level's boxes.  A neighbour that is
+  // a masked-in cell is read from the array (what [Chombo] LevelData::exchange would have copied into the ghost cell); one
+  // outside the domain gets the physical BC; any other is a coarse-fine ghost: homogeneousCFInterp on the fly, or -- when
+  // face[f] is set -- QuadCFInterp's stored value, face[f] being a cell-indexed array (the ghost of cell idx beyond its
+  // face f).  plo = the bounding box's lower corner and ndom the level's domain size, both in the level's index space.
+  const unsigned char *mask;
+  int plo[3], ndom[3];
 };
 
 struct Geom {
@@ -137,6 +145,7 @@ struct mgic_field {
   size_t bytes = 0;
   int k0 = 0, gnz = 0;
   bool noHalo = false;     // slab view into a whole-level array: its ghost planes are real neighbour planes
+  const unsigned char *mask = nullptr;  // masked AMR level (see BCk): cells outside the level's boxes are kept at zero
   cudaEvent_t evPending = nullptr;  // completion of the field's last prefetch / writeback (mgic_field_wait)
 };
 
@@ -158,6 +167,11 @@ struct mgic_op {
   double dxCrse = 0;
   int plo[3] = {0, 0, 0}, ndom[3] = {0, 0, 0};   // the patch's lower corner and the level's domain size
   double *cfFace[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // QuadCFInterp ghost values per coarse-fine face
+  double *cfCell[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // the same, cell-indexed (quad_cf_cells: psi update)
+  // level = union of boxes inside the bounding box n[] (mgic_op_create_patch_boxes): device mask, host copy, valid cells
+  unsigned char *mask = nullptr;
+  std::vector<unsigned char> hmask;
+  long long validCells = 0;
   bool isGlobal = false;                  // whole-domain operator on a multi-rank context (agglomerated level): no halos
   bool profTag = true;                    // finest-level operator: its GSRB launches are the profiled kernel
   int smoother = 1;                       // 0: one launch per colour; 1: fused red+black plane-streaming sweep
@@ -175,6 +189,12 @@ struct mgic_vars {
   int ng = 1;
   long long sy = 0, sz = 0, sc = 0;  // padded strides
   double *d = nullptr;               // 8 components, each (nx+2)(ny+2)(nzl+2)
+  // AMR level > 0 (mgic_vars_create_patch): bounding box lower corner in the level's index space (k0 = lo[2]), the level's
+  // domain, the cell mask of a union of boxes (shared with the operator), psi's coarse-fine ghost values per face and cell
+  bool isPatch = false;
+  int lo[3] = {0, 0, 0}, ndom[3] = {0, 0, 0};
+  const unsigned char *mask = nullptr;
+  double *psiG[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // ---- kernel launchers (kernels.cu) -------------------------------------------
@@ -187,7 +207,12 @@ int residual(mgic_ctx *, const Geom &, const BCk &, double *res, const double *p
              const double *b, double alpha, double beta, double dx);
 int restrict_res(mgic_ctx *, const Geom &fine, const BCk &, double *resC, long long csy, long long csz, const double *phi,
                  const double *rhs, const double *a, const double *b, double alpha, double beta, double dx);
-int prolong(mgic_ctx *, const Geom &fine, double *phi, const double *coarse, long long csy, long long csz);
+int prolong(mgic_ctx *, const Geom &fine, double *phi, const double *coarse, long long csy, long long csz,
+            const unsigned char *fineMask = nullptr);
+int apply_mask(mgic_ctx *, const Geom &, double *y, const unsigned char *mask);   // y = 0 outside the mask
+// QuadCFInterp for every coarse-fine ghost of a masked level: face[f][cell] for the cells whose neighbour beyond face f is one
+int quad_cf_masked(mgic_ctx *, const Geom &g, const unsigned char *mask, const int plo[3], const int ndom[3], double h, const double *phi,
+                   const double *coarse, long long csy, long long csz, const int clo[3], double *const face[6]);
 int compute_lambda(mgic_ctx *, const Geom &, double *lam, const double *a, double alpha, double beta, double dx);
 int mult(mgic_ctx *, const Geom &, double *y, const double *x, const double *l);      // y = x*l
 int incr(mgic_ctx *, const Geom &, double *y, const double *x, double s);             // y = y + s*x
@@ -195,7 +220,8 @@ int axby(mgic_ctx *, const Geom &, double *y, const double *x1, const double *x2
 int scale(mgic_ctx *, const Geom &, double *y, double s);
 int assign(mgic_ctx *, const Geom &, double *y, const double *x);
 int set_val(mgic_ctx *, const Geom &, double *y, double v);
-int box_set_val(mgic_ctx *, const Geom &box, double *y, double v);   // sub-box of a larger array (strides box.sy / box.sz)
+int box_set_val(mgic_ctx *, const Geom &box, double *y, double v, const unsigned char *fineMask = nullptr, long long msy = 0,
+                long long msz = 0);   // sub-box of a larger array (strides box.sy / box.sz); fineMask: only under masked-in fine cells
 int jacobi_update(mgic_ctx *, const Geom &, double *phi, const double *res, const double *lam, double w);
 // reductions: result left in ctx->d_scal[slot]; kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y
 int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot);
@@ -203,12 +229,14 @@ int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind,
 int quad_cf_face(mgic_ctx *, const Geom &g, const int plo[3], const int ndom[3], double h, int dir, int side, const double *phi,
                  const double *coarse, long long csy, long long csz, const int clo[3], double *face);
 int coarse_average(mgic_ctx *, const Geom &coarse, double *c, const double *fine, long long fsy, long long fsz, int nref,
-                   int harmonic);
+                   int harmonic, const unsigned char *fineMask = nullptr);
 int is_constant(mgic_ctx *, const Geom &, const double *x, double value, int slot);  // d_scal[slot] = #cells != value
 // source terms (padded multigrid_vars arrays)
 int init_conditions(mgic_vars *);
 int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
+int update_psi_patch(mgic_vars *, const BCk &withCfFaces, const double *dpsi);
+int fill(mgic_ctx *, double *y, long long n, double value);
 int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                     int *d_out);
 int bottom_bicgstab_dsmem(mgic_op *, mgic_field *e, const mgic_field *r, int *d_out, int *used);

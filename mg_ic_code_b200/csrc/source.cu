@@ -15,9 +15,16 @@ enum { c_psi = 0, c_A11 = 1, c_A12 = 2, c_A13 = 3, c_A22 = 4, c_A23 = 5, c_A33 =
 struct SrcP {
   double G_Newton, phi_amplitude, phi_wavelength;
   double m1, m2, spin1, spin2, mom1, mom2, off1, off2;
-  double dx, half[3];  // half[d] = (dx * N[d]) / 2
+  double dx, half[3];  // dx = this level's spacing; half[d] = (coarsest dx * N[d]) / 2 = domainLength / 2
   int nx, ny, nz, k0;
   long long sy, sz, sc;
+  // AMR level > 0 (mgic_vars_create_patch): the array covers the level's bounding box whose lower corner is (i0, j0, k0) in
+  // the level's index space; mask = the cells of the level's boxes (null: all); psiG[f][cell] = psi in the coarse-fine
+  // ghost cell beyond face f of `cell` (the fields carry no room for it: one ghost position can belong to two faces)
+  int i0, j0, patch;
+  int ndom[3];
+  const unsigned char *mask;
+  double *psiG[6];
 };
 
 __device__ __forceinline__ double eps3(int a, int b, int c) {
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(128) k_init(SrcP P, double *__restrict__ mv) {
   if (i > P.nx || j > P.ny) return;
   const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
   double loc[3];
-  cell_loc(P, i, j, k + P.k0, loc);
+  cell_loc(P, i + P.i0, j + P.j0, k + P.k0, loc);
   mv[q + c_psi * P.sc] = 1.0;
   const double r2 = loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2];
   mv[q + c_phi * P.sc] = P.phi_amplitude * exp(-r2 / P.phi_wavelength);
@@ -93,6 +100,7 @@ __global__ void __launch_bounds__(128) k_rhs_acoef(SrcP P, const double *__restr
   if (i >= P.nx || j >= P.ny) return;
   const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
   const long long o = i + (long long)j * P.nx + (long long)k * P.nx * P.ny;
+  if (P.mask && !P.mask[o]) return;   // not a cell of the level's boxes
   const long long st[3] = {1, P.sy, P.sz};
   const double *psi = mv + c_psi * P.sc, *phi = mv + c_phi * P.sc;
   // GETRHOGRADPHIF: rho = sum_d 0.5 * (0.5/dx * (phi+ - phi-))^2
@@ -104,13 +112,36 @@ __global__ void __launch_bounds__(128) k_rhs_acoef(SrcP P, const double *__restr
   }
   // GETLAPLACIANPSIF: lap = sum_d 1/dx/dx * (psi- - 2 psi + psi+)
   double lap = 0.0;
+  if (!P.patch) {
 #pragma unroll
-  for (int d = 0; d < 3; d++) {
-    const double dd = 1.0 / P.dx / P.dx * (+1.0 * psi[q - st[d]] - 2.0 * psi[q] + 1.0 * psi[q + st[d]]);
-    lap = lap + dd;
+    for (int d = 0; d < 3; d++) {
+      const double dd = 1.0 / P.dx / P.dx * (+1.0 * psi[q - st[d]] - 2.0 * psi[q] + 1.0 * psi[q + st[d]]);
+      lap = lap + dd;
+    }
+  } else {
+    // psi's neighbour: a cell of the level or a physical ghost -> the padded array (what exchange / the solver left there);
+    // a coarse-fine ghost -> psiG (QuadCFInterp'd dpsi accumulated onto the initial 1, Main_PoissonSolver.cpp:193-205)
+    const int iv[3] = {i, j, k}, n[3] = {P.nx, P.ny, P.nz}, lo[3] = {P.i0, P.j0, P.k0};
+    const long long so[3] = {1, (long long)P.nx, (long long)P.nx * P.ny};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double pm, pp;
+      {
+        const int w = iv[d] - 1;
+        const bool cell = w >= 0 && (!P.mask || P.mask[o - so[d]]);
+        pm = (cell || lo[d] + w < 0) ? psi[q - st[d]] : P.psiG[2 * d][o];
+      }
+      {
+        const int w = iv[d] + 1;
+        const bool cell = w < n[d] && (!P.mask || P.mask[o + so[d]]);
+        pp = (cell || lo[d] + w >= P.ndom[d]) ? psi[q + st[d]] : P.psiG[2 * d + 1][o];
+      }
+      const double dd = 1.0 / P.dx / P.dx * (+1.0 * pm - 2.0 * psi[q] + 1.0 * pp);
+      lap = lap + dd;
+    }
   }
   double loc[3];
-  cell_loc(P, i, j, k + P.k0, loc);
+  cell_loc(P, i + P.i0, j + P.j0, k + P.k0, loc);
   // set_m_value (:266-278): rho_matter = 0
   const double rho_m = 0.5 * 0.0 * 0.0 + 0.0;
   const double m = (2.0 / 3.0) * (constant_K * constant_K) - 16.0 * M_PI * P.G_Newton * rho_m;
@@ -154,6 +185,35 @@ __global__ void __launch_bounds__(128) k_update_psi(SrcP P, Geom g, BCk bc, doub
   mv[q + c_psi * P.sc] += v;
 }
 
+// set_update_psi0 on an AMR level > 0: psi += dpsi on the level's cells; beyond each face of a cell either nothing (the
+// neighbour is a cell of the level: the exchange's copy), the physical ghost of the padded array (a*near + b), or the
+// coarse-fine ghost psiG += QuadCFInterp(dpsi) (cf[f][cell], filled just before by the operator).
+__global__ void __launch_bounds__(128) k_update_psi_patch(SrcP P, BCk bc, double *__restrict__ mv, const double *__restrict__ dpsi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= P.nx || j >= P.ny) return;
+  const long long o = i + (long long)j * P.nx + (long long)k * P.nx * P.ny;
+  if (P.mask && !P.mask[o]) return;
+  const long long q = (i + 1) + (j + 1) * P.sy + (k + 1) * P.sz;
+  const long long st[3] = {1, P.sy, P.sz}, so[3] = {1, (long long)P.nx, (long long)P.nx * P.ny};
+  const int iv[3] = {i, j, k}, n[3] = {P.nx, P.ny, P.nz}, lo[3] = {P.i0, P.j0, P.k0};
+  const double v = dpsi[o];
+  double *psi = mv + c_psi * P.sc;
+  psi[q] += v;
+  for (int f = 0; f < 6; f++) {
+    const int d = f >> 1, side = (f & 1) ? 1 : -1;
+    const int w = iv[d] + side;
+    if (w >= 0 && w < n[d] && (!P.mask || P.mask[o + side * so[d]])) continue;
+    if (lo[d] + w < 0 || lo[d] + w >= P.ndom[d]) psi[q + side * st[d]] += bc.a[f] * v + bc.b[f];
+    else P.psiG[f][o] += bc.face[f][o];
+  }
+}
+
+__global__ void k_fill(long long n, double *__restrict__ y, double v) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) y[q] = v;
+}
+
 SrcP make_srcp(const mgic_vars *v) {
   SrcP s;
   const mgic_params &P = v->P;
@@ -161,9 +221,13 @@ SrcP make_srcp(const mgic_vars *v) {
   s.m1 = P.bh1_bare_mass; s.m2 = P.bh2_bare_mass; s.spin1 = P.bh1_spin; s.spin2 = P.bh2_spin;
   s.mom1 = P.bh1_momentum; s.mom2 = P.bh2_momentum; s.off1 = P.bh1_offset; s.off2 = P.bh2_offset;
   s.dx = v->dx;
-  for (int d = 0; d < 3; d++) s.half[d] = (v->dx * P.N[d]) / 2.0;  // PoissonParameters.cpp:83-85
+  for (int d = 0; d < 3; d++) s.half[d] = ((P.L / P.N[0]) * P.N[d]) / 2.0;  // PoissonParameters.cpp:82-85 (the coarsest level's dx)
   s.nx = v->n[0]; s.ny = v->n[1]; s.nz = v->nzl; s.k0 = v->k0;
   s.sy = v->sy; s.sz = v->sz; s.sc = v->sc;
+  s.i0 = v->lo[0]; s.j0 = v->lo[1]; s.patch = v->isPatch ? 1 : 0;
+  for (int d = 0; d < 3; d++) s.ndom[d] = v->ndom[d];
+  s.mask = v->mask;
+  for (int f = 0; f < 6; f++) s.psiG[f] = v->psiG[f];
   return s;
 }
 
@@ -190,6 +254,20 @@ int set_rhs_acoef(mgic_vars *v, double *rhs, double *acoef, double constant_K) {
   dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
   k_rhs_acoef<<<grd, blk, 0, v->ctx->stream>>>(s, v->d, rhs, acoef, constant_K);
   return post(v->ctx, "set_rhs_acoef");
+}
+
+int update_psi_patch(mgic_vars *v, const BCk &bc, const double *dpsi) {
+  SrcP s = make_srcp(v);
+  dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
+  k_update_psi_patch<<<grd, blk, 0, v->ctx->stream>>>(s, bc, v->d, dpsi);
+  return post(v->ctx, "update_psi_patch");
+}
+
+int fill(mgic_ctx *c, double *y, long long n, double value) {
+  long long b = (n + 255) / 256;
+  if (b > 4096) b = 4096;
+  k_fill<<<(int)(b < 1 ? 1 : b), 256, 0, c->stream>>>(n, y, value);
+  return post(c, "fill");
 }
 
 int update_psi(mgic_vars *v, const Geom &g, const BCk &bc, const double *dpsi) {

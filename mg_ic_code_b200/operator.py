@@ -152,6 +152,32 @@ class VariableCoeffPoissonOperator:
         op.owned = True
         return op
 
+    @classmethod
+    def patch_boxes(cls, ctx, n_domain, boxes, dx, dx_coarse=None, alpha=1.0, beta=-1.0, bc_lo=(0, 0, 0), bc_hi=(0, 0, 0), bc_value=0.0):
+        """The operator on an AMR level (or one connected part of it) made of several boxes [(lo, hi), ...] that may touch
+        and whose union need not be a rectangle: one array over the bounding box plus a cell mask."""
+        i3 = C.c_int * 3
+        flat = []
+        for lo, hi in boxes:
+            flat += list(lo) + list(hi)
+        arr = (C.c_int * len(flat))(*flat)
+        h = C.c_void_p()
+        check(ctx.L.mgic_op_create_patch_boxes(ctx.h, i3(*n_domain), len(boxes), arr, dx, 2 * dx if dx_coarse is None else dx_coarse,
+                                               alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value, C.byref(h)))
+        op = cls(ctx, None, None, handle=h)
+        op.owned = True
+        return op
+
+    @property
+    def valid_cells(self):
+        return self.L.mgic_op_valid_cells(self.h)
+
+    def mask(self):
+        """1 = cell of the level's boxes, over the bounding box, [k, j, i]"""
+        out = np.zeros((self.n[2], self.n[1], self.n[0]), dtype=np.uint8)
+        check(self.L.mgic_op_get_mask(self.h, out))
+        return out
+
     # AMRLevelOp::create
     def create(self):
         return LevelField(self)
@@ -450,6 +476,69 @@ class MultigridVars:
     def close(self):
         if self.h:
             self.L.mgic_vars_destroy(self.h)
+            self.h = None
+
+
+class Hierarchy:
+    """poissonSolve (Main_PoissonSolver.cpp:45-256) on an AMR hierarchy: levels = [[node, ...], ...] for levels 1, 2, ...;
+    a node is a list of boxes (lo, hi) -- one connected component of its level, boxes may touch -- or a single (lo, hi)."""
+
+    WHAT = dict(psi=0, A11=1, A12=2, A13=3, A22=4, A23=5, A33=6, phi=7, dpsi=8, rhs=9, aCoef=10)
+
+    def __init__(self, ctx, params, levels):
+        self.ctx, self.L = ctx, ctx.L
+        self.params = params if not isinstance(params, dict) else make_params(params)
+        nnodes, nboxes, flat = [], [], []
+        for lv in levels:
+            nnodes.append(len(lv))
+            for node in lv:
+                boxes = node if isinstance(node, list) else [node]
+                nboxes.append(len(boxes))
+                for lo, hi in boxes:
+                    flat += list(lo) + list(hi)
+        mk = lambda v: (C.c_int * max(len(v), 1))(*v)
+        h = C.c_void_p()
+        check(self.L.mgic_hier_create(ctx.h, C.byref(self.params), len(levels), mk(nnodes), mk(nboxes), mk(flat), C.byref(h)))
+        self.h = h
+        self.nodes = self.L.mgic_hier_nodes(h)
+
+    def node_info(self, q):
+        """(level, lo (i, j, k), n (nx, ny, nz), valid cells)"""
+        lvl, cells = C.c_int(), C.c_longlong()
+        lo, n = (C.c_int * 3)(), (C.c_int * 3)()
+        check(self.L.mgic_hier_node_info(self.h, q, C.byref(lvl), lo, n, C.byref(cells)))
+        return lvl.value, tuple(lo), tuple(n), cells.value
+
+    def mask(self, q):
+        _, _, n, _ = self.node_info(q)
+        out = np.zeros((n[2], n[1], n[0]), dtype=np.uint8)
+        check(self.L.mgic_hier_get_mask(self.h, q, out))
+        return out
+
+    def set_initial_conditions(self):
+        check(self.L.mgic_hier_set_initial_conditions(self.h))
+
+    def nl_iteration(self):
+        """one pass of Main_PoissonSolver.cpp:131-212: (norm of dpsi, BiCGStab iterations, exit status)"""
+        nrm, it, st = C.c_double(), C.c_int(), C.c_int()
+        check(self.L.mgic_hier_nl_iteration(self.h, C.byref(nrm), C.byref(it), C.byref(st)))
+        return nrm.value, it.value, st.value
+
+    def nl_solve(self):
+        norms = (C.c_double * 64)()
+        its = C.c_int()
+        check(self.L.mgic_hier_nl_solve(self.h, norms, 64, C.byref(its)))
+        return np.array(norms[: its.value])
+
+    def download(self, q, what="psi"):
+        _, _, n, _ = self.node_info(q)
+        out = np.zeros((n[2], n[1], n[0]))
+        check(self.L.mgic_hier_download(self.h, q, self.WHAT[what], out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.mgic_hier_destroy(self.h)
             self.h = None
 
 

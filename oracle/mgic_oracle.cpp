@@ -56,6 +56,7 @@ struct Box {
     for (int d = 0; d < 3; d++) if (o.lo[d] < lo[d] || o.hi[d] > hi[d]) return false;
     return true;
   }
+  bool contains(int i, int j, int k) const { return i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]; }
   Box operator&(const Box &o) const {
     Box r;
     for (int d = 0; d < 3; d++) { r.lo[d] = std::max(lo[d], o.lo[d]); r.hi[d] = std::min(hi[d], o.hi[d]); }
@@ -862,7 +863,7 @@ static inline void cellLoc(const orc_params &P, Real dx, int i, int j, int k, Re
   for (int d = 0; d < 3; d++) {
     Real l = iv[d] + 0.5 * 1.0;
     l *= dx;
-    l -= (dx * P.N[d]) / 2.0;   // domainLength[d] = coarsestDx * nCells[d]  (PoissonParameters.cpp:83-85)
+    l -= ((P.L / P.N[0]) * P.N[d]) / 2.0;   // domainLength[d] = coarsestDx * nCells[d]  (PoissonParameters.cpp:82-85); dx = the level's
     loc[d] = l;
   }
 }
@@ -1076,17 +1077,17 @@ void orc_destroy(orc_problem *pb) {
 }
 
 // set_initial_conditions -- Source/SetLevelData.cpp:32-71 (+ set_binary_bh_Aij SetBinaryBH.H:54-83)
-void orc_set_initial_conditions(orc_problem *pb) {
-  const orc_params &P = pb->P; Real dx = pb->dx0;
+// (one AMR level: dx is the LEVEL's spacing, P.L / P.N the coarsest level's -- Main_PoissonSolver.cpp:93 calls it per level)
+static void init_conditions_level(const orc_params &P, Real dx, LevelData &mgvars, LevelData &dpsi) {
 #pragma omp parallel for schedule(static)
-  for (int n = 0; n < pb->mgvars.size(); n++) {
-    FAB &mv = pb->mgvars.fab[n]; FAB &dp = pb->dpsi.fab[n];
+  for (int n = 0; n < mgvars.size(); n++) {
+    FAB &mv = mgvars.fab[n]; FAB &dp = dpsi.fab[n];
     const Box &b = mv.b;                                                  // ghosted box :42
     for (int k = b.lo[2]; k <= b.hi[2]; k++)
       for (int j = b.lo[1]; j <= b.hi[1]; j++)
         for (int i = b.lo[0]; i <= b.hi[0]; i++) {
           mv(i, j, k, 0) = 1.0;                                           // :54
-          dp(i, j, k, 0) = 0.0;                                           // :55
+          if (dp.b.contains(i, j, k)) dp(i, j, k, 0) = 0.0;               // :55
           Real loc[3]; cellLoc(P, dx, i, j, k, loc);                      // :58-60
           mv(i, j, k, 7) = my_phi_function(loc, P.phi_amplitude, P.phi_wavelength);  // :63-65
           // set_binary_bh_Aij
@@ -1106,13 +1107,14 @@ void orc_set_initial_conditions(orc_problem *pb) {
   }
 }
 
-// set_a_coef (SetLevelData.cpp:281-325), set_b_coef (:330-340), set_rhs (:73-127)
-void orc_set_coefs_and_rhs(orc_problem *pb, double constant_K) {
-  const orc_params &P = pb->P; Real dx = pb->dx0;
-  pb->constant_K = constant_K;
+void orc_set_initial_conditions(orc_problem *pb) { init_conditions_level(pb->P, pb->dx0, pb->mgvars, pb->dpsi); }
+
+// set_a_coef (SetLevelData.cpp:281-325), set_b_coef (:330-340), set_rhs (:73-127) on one AMR level
+static void coefs_and_rhs_level(const orc_params &P, Real dx, double constant_K, LevelData &mgvars, LevelData &rhsLD, LevelData &aLD,
+                                LevelData &bLD) {
 #pragma omp parallel for schedule(static)
-  for (int n = 0; n < pb->rhs.size(); n++) {
-    FAB &mv = pb->mgvars.fab[n]; FAB &rhs = pb->rhs.fab[n]; FAB &aC = pb->aCoef.fab[n]; FAB &bC = pb->bCoef.fab[n];
+  for (int n = 0; n < rhsLD.size(); n++) {
+    FAB &mv = mgvars.fab[n]; FAB &rhs = rhsLD.fab[n]; FAB &aC = aLD.fab[n]; FAB &bC = bLD.fab[n];
     const Box &tb = rhs.b;  // no ghost cells
     FAB lap, rho; lap.define(tb, 1); rho.define(tb, 1);
     View psiV = fabview(mv); View phiV = fabview(mv); phiV.p += mv.sc * 7;   // CHF_CONST_FRA1(mv, c_psi / c_phi_0)
@@ -1145,6 +1147,11 @@ void orc_set_coefs_and_rhs(orc_problem *pb, double constant_K) {
         }
   }
 }
+void orc_set_coefs_and_rhs(orc_problem *pb, double constant_K) {
+  pb->constant_K = constant_K;
+  coefs_and_rhs_level(pb->P, pb->dx0, constant_K, pb->mgvars, pb->rhs, pb->aCoef, pb->bCoef);
+}
+
 
 // defineOperatorFactory + MultiGrid::define: MGnewOp(domain, depth) until NULL (Factory.cpp:139-234)
 int orc_define_solver(orc_problem *pb) {
@@ -1278,6 +1285,9 @@ struct orc_patch {
   Layout clay;
   Box box;
   FAB crse; Box cdom;              // the coarser AMR level's field on its whole domain (QuadCFInterp input)
+  // the level's problem data (Main_PoissonSolver.cpp:79-88 on level ilev > 0): multigrid_vars, dpsi, rhs
+  orc_params P; bool hasP = false;
+  LevelData mgvars, dpsi, rhs;
 };
 
 orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi[3], int max_grid_size, double dx, double dx_crse,
@@ -1291,6 +1301,41 @@ orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi
   Op &op = pp->op;
   op.lay.domain = Box(0, 0, 0, n_domain[0] - 1, n_domain[1] - 1, n_domain[2] - 1);
   domainSplit(pp->box, max_grid_size, op.lay.boxes);
+  op.lay.buildCopier(op.lay.exFace1, 1, true);
+  op.dx = dx; op.alpha = alpha; op.beta = beta;
+  op.hasCoarser = true; op.dxCrse = dx_crse;
+  for (int d = 0; d < 3; d++) { op.bc.lo[d] = bc_lo[d]; op.bc.hi[d] = bc_hi[d]; }
+  op.bc.value = bc_value;
+  pp->e.define(&op.lay, 1, 1); pp->r.define(&op.lay, 1, 0); pp->a.define(&op.lay, 1, 0); pp->b.define(&op.lay, 1, 0);
+  op.aCoef = &pp->a; op.bCoef = &pp->b;
+  op.lambda.define(&op.lay, 1, 0);
+  pp->clay.domain = op.lay.domain.coarsened(2);
+  for (auto &bx : op.lay.boxes) pp->clay.boxes.push_back(bx.coarsened(2));
+  pp->rc.define(&pp->clay, 1, 0);
+  pp->lof.define(&op.lay, 1, 0);
+  pp->cdom = op.lay.domain.coarsened(2);
+  pp->crse.define(pp->cdom, 1);
+  return pp;
+}
+// The same level given as a LIST of boxes (BRMeshRefine's output: boxes that touch, union not a rectangle), cut further
+// into max_grid_size boxes.  Fields are exchanged with the caller as arrays over the union's bounding box.
+orc_patch *orc_patch_create_boxes(const int n_domain[3], int nboxes, const int *boxes, int max_grid_size, double dx, double dx_crse,
+                                  double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value) {
+  const Box dom(0, 0, 0, n_domain[0] - 1, n_domain[1] - 1, n_domain[2] - 1);
+  if (nboxes < 1 || max_grid_size % 2) return nullptr;
+  orc_patch *pp = new orc_patch;
+  Op &op = pp->op;
+  op.lay.domain = dom;
+  int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+  for (int q = 0; q < nboxes; q++) {
+    const Box b(boxes + 6 * q, boxes + 6 * q + 3);
+    if (b.empty() || !dom.contains(b) || !b.coarsenable(2)) { delete pp; return nullptr; }
+    for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], b.lo[d]); hi[d] = std::max(hi[d], b.hi[d]); }
+    std::vector<Box> cut;
+    domainSplit(b, max_grid_size, cut);
+    for (auto &c : cut) op.lay.boxes.push_back(c);
+  }
+  pp->box = Box(lo, hi);
   op.lay.buildCopier(op.lay.exFace1, 1, true);
   op.dx = dx; op.alpha = alpha; op.beta = beta;
   op.hasCoarser = true; op.dxCrse = dx_crse;
@@ -1347,6 +1392,59 @@ void orc_patch_get(orc_patch *pp, int field, double *out) {
   }
 }
 int orc_patch_num_boxes(const orc_patch *pp) { return (int)pp->op.lay.boxes.size(); }
+
+// ---- the nonlinear loop's per-level steps on an AMR level > 0 (Main_PoissonSolver.cpp:93, 154-160, 189-205) ----
+// set_initial_conditions on the level's ghosted boxes (psi = 1, dpsi = 0, phi and A_ij analytic, ghost cells included)
+void orc_patch_set_initial_conditions(orc_patch *pp, const orc_params *P) {
+  pp->P = *P; pp->hasP = true;
+  pp->mgvars.define(&pp->op.lay, 8, 1);    // the reference allocates three ghost layers; its stencils read one
+  pp->dpsi.define(&pp->op.lay, 1, 1);
+  pp->rhs.define(&pp->op.lay, 1, 0);
+  init_conditions_level(pp->P, pp->op.dx, pp->mgvars, pp->dpsi);
+}
+// set_a_coef / set_b_coef / set_rhs: into the patch's coefficient fields (ORC_F_A, ORC_F_B) and its rhs (ORC_F_DPSI + 1 = ORC_F_RHS slot below)
+void orc_patch_set_coefs_and_rhs(orc_patch *pp, double constant_K) {
+  coefs_and_rhs_level(pp->P, pp->op.dx, constant_K, pp->mgvars, pp->rhs, pp->a, pp->b);
+  pp->op.lambdaNeedsResetting = true;
+}
+// Main_PoissonSolver.cpp:189-205: QuadCFInterp of dpsi from the coarser level's dpsi, exchange, psi += dpsi over the GHOSTED
+// boxes.  dpsi arrives as a bounding-box array (valid cells); its physical-boundary ghost is what [Chombo] BiCGStab leaves
+// there, a*near + b (inhomogeneous ParseBC fill, see orc_update_psi0's single-level analysis); coarse = the coarser level's
+// dpsi on its whole domain (orc_patch_set_coarse).
+void orc_patch_update_psi(orc_patch *pp, const double *dpsi_in) {
+  const Box pb = pp->box;
+  const long nx = pb.size(0), ny = pb.size(1);
+  for (int n = 0; n < pp->dpsi.size(); n++) {
+    const Box &b = pp->op.lay.boxes[n]; FAB &f = pp->dpsi.fab[n];
+    f.setVal(0.0);
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++) f(i, j, k) = dpsi_in[(i - pb.lo[0]) + nx * ((j - pb.lo[1]) + ny * (long)(k - pb.lo[2]))];
+  }
+  pp->op.quadCFInterp(pp->dpsi, pp->crse, pp->cdom);    // :193-195
+  pp->op.applyBC(pp->dpsi, false);
+  exchange(pp->dpsi, pp->op.lay.exFace1);               // :200-201 + SetLevelData.cpp:249 (face ghosts are the ones read)
+  for (int n = 0; n < pp->mgvars.size(); n++) {
+    FAB &mv = pp->mgvars.fab[n]; const FAB &dp = pp->dpsi.fab[n];
+    const Box &b = mv.b;                                // ghosted :256
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++) mv(i, j, k, 0) += dp(i, j, k, 0);   // :260
+  }
+}
+// component `comp` of multigrid_vars (comp 0..7) or the rhs (comp 8) over the bounding box (valid cells)
+void orc_patch_get_var(orc_patch *pp, int comp, double *out) {
+  const Box pb = pp->box;
+  const long nx = pb.size(0), ny = pb.size(1);
+  const LevelData &ld = comp == 8 ? pp->rhs : pp->mgvars;
+  for (int n = 0; n < ld.size(); n++) {
+    const Box &b = pp->op.lay.boxes[n]; const FAB &f = ld.fab[n];
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++)
+          out[(i - pb.lo[0]) + nx * ((j - pb.lo[1]) + ny * (long)(k - pb.lo[2]))] = f(i, j, k, comp == 8 ? 0 : comp);
+  }
+}
 void orc_patch_relax(orc_patch *pp, int iterations) { pp->op.relax(pp->e, pp->r, iterations); }
 void orc_patch_gsrb_color(orc_patch *pp, int whichPass) { pp->op.resetLambda(); pp->op.gsrbColor(pp->e, pp->r, whichPass); }
 void orc_patch_restrict(orc_patch *pp) { pp->op.restrictResidual(pp->rc, pp->e, pp->r); }
@@ -1422,6 +1520,22 @@ double orc_update_psi0(orc_problem *pb) {
   Real sum = 0.0; for (Real s : part) sum += s;
   Real dV = pb->dx0 * pb->dx0 * pb->dx0;
   return std::sqrt(sum * dV);
+}
+
+// dpsi := the given valid cells, ghost layer 1 = the inhomogeneous ParseBC fill (what [Chombo] BiCGStab leaves there: the
+// initial residual's inhomogeneous fill + the homogeneous ghosts of the accumulated correction).  For callers whose solver
+// ran outside this library (the hierarchy twin of tests/amr_twin.py) before orc_update_psi0.
+void orc_set_dpsi_with_bc(orc_problem *pb, const double *in) {
+  const Box &dom = pb->grids.domain;
+  const long nx = dom.size(0), ny = dom.size(1);
+  for (int n = 0; n < pb->dpsi.size(); n++) {
+    const Box &b = pb->grids.boxes[n]; FAB &f = pb->dpsi.fab[n];
+    f.setVal(0.0);
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+        for (int i = b.lo[0]; i <= b.hi[0]; i++) f(i, j, k) = in[i + nx * (j + ny * (long)k)];
+  }
+  pb->ops[0]->applyBC(pb->dpsi, false);
 }
 
 // NL loop -- Main_PoissonSolver.cpp:131-216 (non-periodic: constant_K = 0)

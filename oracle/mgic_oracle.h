@@ -149,6 +149,7 @@ int orc_outer_solve(orc_problem *, int *exit_status, double *final_norm, double 
 /* Main_PoissonSolver.cpp:189-205 + computeNorm :208 ; returns dpsi_norm */
 double orc_update_psi0(orc_problem *);
 /* full NL loop (Main_PoissonSolver.cpp:131-216); dpsi_norms[NL_iter]; returns #NL iterations */
+void orc_set_dpsi_with_bc(orc_problem *, const double *valid_cells);   /* then orc_update_psi0 */
 int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
 
 /* ---- one AMR level > 0 (a box of the refined domain, split into max_grid_size boxes): what the reference's operator
@@ -158,9 +159,17 @@ int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
 typedef struct orc_patch orc_patch;
 orc_patch *orc_patch_create(const int n_domain[3], const int lo[3], const int hi[3], int max_grid_size, double dx, double dx_crse,
                             double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value);
+/* the level as a list of boxes (nboxes x {lo0,lo1,lo2,hi0,hi1,hi2}) that may touch; fields travel as arrays over the bounding box */
+orc_patch *orc_patch_create_boxes(const int n_domain[3], int nboxes, const int *boxes, int max_grid_size, double dx, double dx_crse,
+                                  double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value);
 void orc_patch_destroy(orc_patch *);
 void orc_patch_set(orc_patch *, int field, const double *in);
 void orc_patch_get(orc_patch *, int field, double *out);
+/* the nonlinear loop's per-level steps on an AMR level > 0 (Main_PoissonSolver.cpp:93,154-160,189-205) */
+void orc_patch_set_initial_conditions(orc_patch *, const orc_params *);
+void orc_patch_set_coefs_and_rhs(orc_patch *, double constant_K);
+void orc_patch_update_psi(orc_patch *, const double *dpsi_bounding_box);
+void orc_patch_get_var(orc_patch *, int comp /* 0..7 multigrid_vars, 8 rhs */, double *out);
 int orc_patch_num_boxes(const orc_patch *);
 void orc_patch_relax(orc_patch *, int iterations);
 void orc_patch_gsrb_color(orc_patch *, int whichPass);

@@ -105,16 +105,23 @@ def lib():
         L.orc_outer_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), dp, C.c_int]
         L.orc_outer_solve.restype = C.c_int
         L.orc_update_psi0.argtypes = [C.c_void_p]
+        L.orc_set_dpsi_with_bc.argtypes = [C.c_void_p, dp]
         L.orc_update_psi0.restype = C.c_double
         L.orc_nl_solve.argtypes = [C.c_void_p, dp, C.c_int]
         L.orc_nl_solve.restype = C.c_int
         i3 = C.c_int * 3
         L.orc_patch_create.restype = C.c_void_p
         L.orc_patch_create.argtypes = [i3, i3, i3, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double]
+        L.orc_patch_create_boxes.restype = C.c_void_p
+        L.orc_patch_create_boxes.argtypes = [i3, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, i3, i3, C.c_double]
         L.orc_patch_destroy.argtypes = [C.c_void_p]
         L.orc_patch_set.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_patch_get.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_patch_num_boxes.argtypes = [C.c_void_p]
+        L.orc_patch_set_initial_conditions.argtypes = [C.c_void_p, C.POINTER(OrcParams)]
+        L.orc_patch_set_coefs_and_rhs.argtypes = [C.c_void_p, C.c_double]
+        L.orc_patch_update_psi.argtypes = [C.c_void_p, dp]
+        L.orc_patch_get_var.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_patch_relax.argtypes = [C.c_void_p, C.c_int]
         L.orc_patch_gsrb_color.argtypes = [C.c_void_p, C.c_int]
         L.orc_patch_restrict.argtypes = [C.c_void_p]
@@ -235,7 +242,11 @@ class Oracle:
         it = self.L.orc_outer_solve(self.h, C.byref(st), C.byref(fn), norms, max_norms)
         return it, st.value, fn.value, norms[: it + 1].copy()
 
-    def update_psi0(self):
+    def update_psi0(self, dpsi=None):
+        """psi += dpsi over the ghosted boxes; dpsi = the solver's own (None) or given valid cells whose physical ghosts get
+        the inhomogeneous BC fill"""
+        if dpsi is not None:
+            self.L.orc_set_dpsi_with_bc(self.h, np.ascontiguousarray(dpsi, dtype=np.float64))
         return self.L.orc_update_psi0(self.h)
 
     def nl_solve(self):
@@ -261,14 +272,25 @@ class OraclePatch:
     [Chombo] homogeneousCFInterp at its coarse-fine faces (VariableCoeffPoissonOperator.cpp:156,296)."""
 
     def __init__(self, n_domain, lo, hi, dx, dx_crse=None, max_grid_size=8, alpha=1.0, beta=-1.0, bc_lo=(0, 0, 0),
-                 bc_hi=(0, 0, 0), bc_value=0.0):
+                 bc_hi=(0, 0, 0), bc_value=0.0, boxes=None):
+        """boxes = [(lo, hi), ...]: the level as a list of boxes that may touch (lo / hi are then ignored and become the
+        bounding box; arrays are bounding-box shaped, cells outside the boxes are not touched)."""
         self.L = lib()
         i3 = C.c_int * 3
+        self.boxes = None if boxes is None else [(tuple(a), tuple(b)) for a, b in boxes]
+        if boxes is not None:
+            lo = [min(b[0][d] for b in self.boxes) for d in range(3)]
+            hi = [max(b[1][d] for b in self.boxes) for d in range(3)]
         self.lo, self.hi = tuple(lo), tuple(hi)
         self.shape = tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
         self.cshape = tuple(s // 2 for s in self.shape)
-        self.h = self.L.orc_patch_create(i3(*n_domain), i3(*lo), i3(*hi), max_grid_size, dx, 2 * dx if dx_crse is None else dx_crse,
-                                         alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value)
+        if boxes is not None:
+            flat = [v for b in self.boxes for v in (list(b[0]) + list(b[1]))]
+            self.h = self.L.orc_patch_create_boxes(i3(*n_domain), len(self.boxes), (C.c_int * len(flat))(*flat), max_grid_size, dx,
+                                                   2 * dx if dx_crse is None else dx_crse, alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value)
+        else:
+            self.h = self.L.orc_patch_create(i3(*n_domain), i3(*lo), i3(*hi), max_grid_size, dx, 2 * dx if dx_crse is None else dx_crse,
+                                             alpha, beta, i3(*bc_lo), i3(*bc_hi), bc_value)
         if not self.h:
             raise ValueError("patch box must lie in the domain and be coarsenable by 2 (even lo, odd hi), max_grid_size even")
 
@@ -290,13 +312,39 @@ class OraclePatch:
     def set(self, field, arr):
         self.L.orc_patch_set(self.h, FIELD[field], np.ascontiguousarray(arr, dtype=np.float64))
 
+    def mask(self):
+        """1 = cell of the level's boxes, over the bounding box, [k, j, i]"""
+        m = np.zeros(self.shape, dtype=np.uint8)
+        for a, b in (self.boxes or [(self.lo, self.hi)]):
+            m[a[2] - self.lo[2]:b[2] - self.lo[2] + 1, a[1] - self.lo[1]:b[1] - self.lo[1] + 1, a[0] - self.lo[0]:b[0] - self.lo[0] + 1] = 1
+        return m
+
     def get(self, field):
-        out = np.empty(self.cshape if field == "TMP" else self.shape, dtype=np.float64)
+        out = np.zeros(self.cshape if field == "TMP" else self.shape, dtype=np.float64)
         self.L.orc_patch_get(self.h, FIELD[field], out)
         return out
 
     def relax(self, iterations):
         self.L.orc_patch_relax(self.h, iterations)
+
+    # -- the nonlinear loop's per-level steps (Main_PoissonSolver.cpp:93, 154-160, 189-205)
+    def set_initial_conditions(self, params):
+        self._params = to_struct(params)
+        self.L.orc_patch_set_initial_conditions(self.h, C.byref(self._params))
+
+    def set_coefs_and_rhs(self, constant_K=0.0):
+        self.L.orc_patch_set_coefs_and_rhs(self.h, constant_K)
+
+    def update_psi(self, dpsi, coarse_dpsi):
+        """psi += dpsi over the ghosted boxes; coarse-fine ghosts of dpsi by QuadCFInterp from the coarser level's dpsi"""
+        self.set_coarse(coarse_dpsi)
+        self.L.orc_patch_update_psi(self.h, np.ascontiguousarray(dpsi, dtype=np.float64))
+
+    def var(self, comp):
+        """multigrid_vars component 0..7 (0 = psi), or 8 = rhs, over the bounding box"""
+        out = np.zeros(self.shape, dtype=np.float64)
+        self.L.orc_patch_get_var(self.h, comp, out)
+        return out
 
     def gsrb_color(self, which):
         self.L.orc_patch_gsrb_color(self.h, which)

@@ -27,6 +27,10 @@ class AmrTwin:
         self.levels = max(backend.level) + 1
         # the cells of the parent's array under node q
         self.under = [None] * self.n
+        # nodes that are unions of boxes in a bounding-box array: fmask[q] = 1 on the node's cells, cmask[q] = the same
+        # coarsened by 2 (boxes are coarsenable: all eight cells or none); None for rectangular nodes
+        self.fmask = list(getattr(backend, "fmask", [None] * self.n))
+        self.cmask = [None if f is None else f[::2, ::2, ::2].astype(bool) for f in self.fmask]
         for q in range(1, self.n):
             p = backend.parent[q]
             off = [backend.lo[q][d] // 2 - backend.lo[p][d] for d in range(3)]
@@ -55,13 +59,24 @@ class AmrTwin:
     def zero_covered(self, x):
         y = [a.copy() for a in x]
         for q in range(1, self.n):
-            y[self.b.parent[q]][self.under[q]] = 0.0
+            self._put_under(y, q, 0.0)
         return y
+
+    def _put_under(self, y, q, values):
+        """the parent's cells under node q := values (only under the node's own cells when it is a masked union)"""
+        sub = y[self.b.parent[q]][self.under[q]]          # a view
+        if self.cmask[q] is None:
+            sub[...] = values
+        else:
+            sub[self.cmask[q]] = values[self.cmask[q]] if isinstance(values, np.ndarray) else values
+
+    def _masked(self, q, x):
+        return x if self.fmask[q] is None else x * self.fmask[q]
 
     def average_down(self, x):
         y = [a.copy() for a in x]
         for q in range(self.n - 1, 0, -1):
-            y[self.b.parent[q]][self.under[q]] = T.coarse_average(y[q], 2, False)
+            self._put_under(y, q, T.coarse_average(y[q], 2, False))
         return y
 
     def norm(self, x, ord=0):
@@ -94,11 +109,11 @@ class AmrTwin:
             corr[p] = np.zeros(b.shape[p])
         for q in mine:
             p = b.parent[q]
-            res[p][self.under[q]] = T.coarse_average(b.residual_nf(q, corr[q], corr[p], res[q], True), 2, False)
+            self._put_under(res, q, T.coarse_average(b.residual_nf(q, corr[q], corr[p], res[q], True), 2, False))
         self._cycle(l - 1, res, corr)
         for q in mine:
             p = b.parent[q]
-            corr[q] = corr[q] + rep2(corr[p][self.under[q]])
+            corr[q] = corr[q] + self._masked(q, rep2(corr[p][self.under[q]]))
             res[q] = b.residual_nf(q, corr[q], corr[p], res[q], True)
             corr[q] = corr[q] + b.relax0(q, res[q], S)
 
@@ -201,6 +216,7 @@ class OracleBackend:
         nz, ny, nx = oracle.get("A").shape
         self.shape = [(nz, ny, nx)] + [p.shape for p in self.P[1:]]
         self.lo = [(0, 0, 0)] + [p.lo for p in self.P[1:]]
+        self.fmask = [None] + [(p.mask().astype(np.float64) if getattr(p, "boxes", None) else None) for p in self.P[1:]]
         self.dx = [oracle.params["L"] / oracle.params["N"][0]]
         self.parent = [-1]
         for q in range(1, self.n_nodes):
@@ -249,3 +265,37 @@ class OracleBackend:
         P = self.P[q]
         P.set("E", np.zeros(self.shape[q])); P.set("R", res); P.relax(n)
         return P.get("E")
+
+
+def hierarchy_nl_solve(oracle, patches, max_nl=None, log=None):
+    """poissonSolve's nonlinear loop (Main_PoissonSolver.cpp:93, 131-216) on a hierarchy over the oracle: `oracle` = the base
+    level (an Oracle, not yet set up), patches = [[OraclePatch, ...] for level 1, ...].  Returns (dpsi norms per NL iteration,
+    psi per node).  dpsi carries over between iterations as the initial guess (:93 is its only zeroing)."""
+    P = oracle.params
+    oracle.set_initial_conditions()
+    flat = [q for lv in patches for q in lv]
+    for q in flat:
+        q.set_initial_conditions(P)
+    dpsi, norms, tw = None, [], None
+    for nl in range(max_nl if max_nl is not None else P["max_NL_iterations"]):
+        oracle.set_coefs_and_rhs()
+        oracle.define_solver()
+        for q in flat:
+            q.set_coefs_and_rhs()
+        tw = AmrTwin(OracleBackend(oracle, patches))
+        rhs = [oracle.get("RHS")] + [q.var(8) for q in flat]
+        if dpsi is None:
+            dpsi = tw.zeros()
+        its, status, hist = tw.bicgstab(dpsi, rhs, eps=P["tolerance"], imax=P["max_iterations"], homog=False)
+        oracle.update_psi0(dpsi[0])
+        for n, q in enumerate(flat, start=1):
+            p = tw.b.parent[n]
+            q.update_psi(dpsi[n], tw.b._coarse_domain(n, dpsi[p]))
+        nrm = tw.norm(dpsi, 2)
+        norms.append(nrm)
+        if log is not None:
+            log.append((its, status, hist[-1]))
+        if nrm < P["tolerance"] or nrm > 1e5:
+            break
+    psi = [oracle.get("MGVAR0", comp=0)] + [q.var(0) for q in flat]
+    return np.array(norms), psi

@@ -4,7 +4,7 @@ seconds.  The GPU tests (test_gpu_amr.py) check the library's mgic_amr_* entry p
 import numpy as np
 import pytest
 
-from amr_twin import AmrTwin, OracleBackend, rep2
+from amr_twin import AmrTwin, OracleBackend, hierarchy_nl_solve, rep2
 from oracle import Oracle, OraclePatch
 
 # boxes [lo, hi] in their level's index space for a base level of N^3 cells, N = 32 (scaled with N // 32)
@@ -12,11 +12,18 @@ C4_BOXES = {1: [((16, 24, 24), (47, 39, 39))],
             2: [((44, 56, 56), (59, 71, 71)), ((68, 56, 56), (83, 71, 71))]}
 
 
-def c4_hierarchy(N=32, L=100.0, smooth=2, mg_iterations=2, box=16):
+# the same three levels with levels made of TOUCHING boxes whose union is no rectangle (what BRMeshRefine produces): a node is
+# a list of boxes = one connected component of its level, held by the library in one masked array
+MASKED_BOXES = {1: [[((16, 24, 24), (31, 39, 39)), ((32, 24, 24), (47, 31, 39))]],
+                2: [[((36, 52, 52), (51, 67, 67)), ((52, 52, 52), (59, 59, 67))], ((68, 50, 52), (83, 59, 67))]}
+
+
+def c4_hierarchy(N=32, L=100.0, smooth=2, mg_iterations=2, box=16, boxes=None):
     """(base Oracle, patches [[level 1], [level 2]], rhs level vector): coefficients and right-hand sides of every level
     are the Bowen-York source terms evaluated AT THAT LEVEL'S resolution (a whole-domain Oracle of the refined grid, cut
-    to the box)."""
+    to the box).  boxes: {level: [node, ...]}, node = (lo, hi) or a list of (lo, hi) that touch."""
     s = N // 32
+    C4_BOXES = boxes if boxes is not None else globals()["C4_BOXES"]
     o = Oracle(N=(N, N, N), max_grid_size=box, numMGsmooth=smooth, numMGIterations=mg_iterations, L=L)
     o.setup()
     rhs, patches = [o.get("RHS")], []
@@ -27,12 +34,16 @@ def c4_hierarchy(N=32, L=100.0, smooth=2, mg_iterations=2, box=16):
         a, b, r = fine.get("A"), fine.get("B"), fine.get("RHS")
         fine.close()
         lv = []
-        for lo, hi in C4_BOXES[l]:
-            lo, hi = tuple(x * s for x in lo), tuple((x + 1) * s - 1 for x in hi)
-            P = OraclePatch((N << l,) * 3, lo, hi, L / N / (1 << l), max_grid_size=box)
+        for node in C4_BOXES[l]:
+            scale = lambda lo, hi: (tuple(x * s for x in lo), tuple((x + 1) * s - 1 for x in hi))
+            if isinstance(node, list):
+                P = OraclePatch((N << l,) * 3, None, None, L / N / (1 << l), max_grid_size=box, boxes=[scale(*b) for b in node])
+            else:
+                P = OraclePatch((N << l,) * 3, *scale(*node), L / N / (1 << l), max_grid_size=box)
+            lo, hi = P.lo, P.hi
             sl = tuple(slice(lo[d], hi[d] + 1) for d in (2, 1, 0))
             P.set("A", a[sl]); P.set("B", b[sl])
-            rhs.append(r[sl].copy())
+            rhs.append(r[sl] * P.mask())
             lv.append(P)
         patches.append(lv)
     return o, patches, rhs
@@ -166,3 +177,69 @@ def test_c4_boxes_of_the_timing_tool_make_a_converging_hierarchy():
         hist.append(tw.norm(r, 0))
         phi = [a + c for a, c in zip(phi, tw.vcycle(r))]
     assert all(hist[i + 1] < 0.25 * hist[i] for i in range(3)), hist
+
+
+def test_touching_boxes_hierarchy_converges():
+    """the same three levels with nodes that are unions of touching boxes (L shapes): AMR V-cycles still contract the
+    composite residual, and the uncovered cells tile the domain exactly once"""
+    o, patches, rhs = c4_hierarchy(boxes=MASKED_BOXES)
+    tw = AmrTwin(OracleBackend(o, patches))
+    assert tw.n == 4 and tw.fmask[1] is not None and tw.fmask[2] is not None and tw.fmask[3] is None
+    assert patches[0][0].num_boxes == 2 and tw.b.shape[1] == (16, 16, 32)
+    ones = [np.ones(s) if tw.fmask[q] is None else tw.fmask[q].copy() for q, s in enumerate(tw.b.shape)]
+    vol = sum(np.count_nonzero(a) * tw.b.dx[q] ** 3 for q, a in enumerate(tw.zero_covered(ones)))
+    assert abs(vol - 100.0 ** 3) < 1e-6
+    phi = tw.zeros()
+    r0 = tw.norm(tw.residual(phi, rhs, True), 0)
+    hist = [r0]
+    for _ in range(5):
+        res = tw.residual(phi, rhs, True)
+        cor = tw.vcycle(res)
+        phi = [a + c for a, c in zip(phi, cor)]
+        hist.append(tw.norm(tw.residual(phi, rhs, True), 0))
+    assert hist[-1] < 1e-4 * hist[0] and all(b < 0.5 * a for a, b in zip(hist, hist[1:])), hist
+    # nothing ever lands outside the level's boxes
+    for q in (1, 2):
+        assert np.all(phi[q][tw.fmask[q] == 0] == 0)
+
+
+def bare_hierarchy(boxes, N=32, L=100.0, smooth=2, mg_iterations=2, box=16, **over):
+    """base Oracle (not set up) + OraclePatch objects without coefficients, for the nonlinear loop"""
+    o = Oracle(N=(N, N, N), max_grid_size=box, numMGsmooth=smooth, numMGIterations=mg_iterations, L=L, **over)
+    patches = []
+    for l in sorted(boxes):
+        lv = []
+        for node in boxes[l]:
+            if isinstance(node, list):
+                lv.append(OraclePatch((N << l,) * 3, None, None, L / N / (1 << l), max_grid_size=box, boxes=node))
+            else:
+                lv.append(OraclePatch((N << l,) * 3, node[0], node[1], L / N / (1 << l), max_grid_size=box))
+        patches.append(lv)
+    return o, patches
+
+
+@pytest.mark.parametrize("boxes", [C4_BOXES, MASKED_BOXES], ids=["c4", "touching_boxes"])
+def test_nonlinear_loop_on_a_hierarchy(boxes):
+    """Main_PoissonSolver.cpp:131-216 with max_level = 2: sources on every level, multilevel BiCGStab, psi update with
+    QuadCFInterp'd ghosts -- the Newton-like iteration converges like the single-level one (5e-2, 2e-5, 1e-8)
+    and the first iteration's sources are the level-resolution Bowen-York terms c4_hierarchy evaluates independently."""
+    o, patches = bare_hierarchy(boxes)
+    log = []
+    norms, psi = hierarchy_nl_solve(o, patches, max_nl=3, log=log)
+    assert len(norms) == 3 and norms[0] > 1e-2 and norms[1] < 1e-3 * norms[0] and norms[2] < 1e-2 * norms[1], norms
+    assert all(st == 1 for _, st, _ in log)
+    # psi stays 1 + O(1e-3) and is smooth across levels: the fine solution averaged down is the coarse one to discretisation error
+    tw = AmrTwin(OracleBackend(o, patches))
+    assert all(np.abs(p[p != 0] - 1).max() < 0.05 for p in psi)
+    down = tw.average_down(psi)
+    assert np.abs(down[0] - psi[0]).max() < 2e-3
+    # iteration 1's rhs on the patches == the independently evaluated level-resolution sources
+    o2, patches2 = bare_hierarchy(boxes)
+    _, _, rhs2 = c4_hierarchy(boxes=boxes)
+    o2.set_initial_conditions()
+    for lv in patches2:
+        for q in lv:
+            q.set_initial_conditions(o2.params); q.set_coefs_and_rhs()
+    flat = [q for lv in patches2 for q in lv]
+    for n, q in enumerate(flat, start=1):
+        assert np.array_equal(q.var(8), rhs2[n])

@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 import mg_ic_code_b200 as m
-from amr_twin import AmrTwin, OracleBackend
-from test_amr_hierarchy import c4_hierarchy
+from amr_twin import AmrTwin, OracleBackend, hierarchy_nl_solve
+from test_amr_hierarchy import C4_BOXES, MASKED_BOXES, bare_hierarchy, c4_hierarchy
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +25,7 @@ class GpuPrimBackend:
 
     def __init__(self, h, ob):
         self.h = h
-        for k in ("n_nodes", "level", "parent", "lo", "shape", "dx", "smooth", "mg_iterations"):
+        for k in ("n_nodes", "level", "parent", "lo", "shape", "dx", "smooth", "mg_iterations", "fmask"):
             setattr(self, k, getattr(ob, k))
         self.F = [dict(E=op.create(), R=op.create(), T=op.create(), C=op.create()) for op in h.ops]
 
@@ -73,8 +73,8 @@ class GpuPrimBackend:
 class C4:
     """the oracle's C4-shaped hierarchy and the same hierarchy on the GPU, fed with the oracle's coefficients"""
 
-    def __init__(self, ctx, mg_iterations=2):
-        self.o, self.patches, self.rhs = c4_hierarchy(mg_iterations=mg_iterations)
+    def __init__(self, ctx, mg_iterations=2, boxes=None):
+        self.o, self.patches, self.rhs = c4_hierarchy(mg_iterations=mg_iterations, boxes=boxes)
         self.ob = OracleBackend(self.o, self.patches)
         self.P = m.make_params(self.o.params)
         lvl = m.level_op_from_params(ctx, self.P)
@@ -88,7 +88,11 @@ class C4:
         for l, lv in enumerate(self.patches, start=1):
             cur = []
             for Pq in lv:
-                op = m.VariableCoeffPoissonOperator.patch(ctx, (N << l,) * 3, Pq.lo, Pq.hi, L / N / (1 << l))
+                if Pq.boxes:      # a union of touching boxes: one masked array
+                    op = m.VariableCoeffPoissonOperator.patch_boxes(ctx, (N << l,) * 3, Pq.boxes, L / N / (1 << l))
+                    assert np.array_equal(op.mask(), Pq.mask()) and op.valid_cells == int(Pq.mask().sum())
+                else:
+                    op = m.VariableCoeffPoissonOperator.patch(ctx, (N << l,) * 3, Pq.lo, Pq.hi, L / N / (1 << l))
                 a, b = op.create(), op.create()
                 a.upload(Pq.get("A")); b.upload(Pq.get("B"))
                 op.setCoefs(a, b, 1.0, -1.0)
@@ -110,9 +114,10 @@ class C4:
         return [scale * rng.standard_normal(s) for s in self.ob.shape]
 
 
-@pytest.fixture(scope="module")
-def c4(ctx):
-    return C4(ctx)
+@pytest.fixture(scope="module", params=["c4", "touching_boxes"])
+def c4(ctx, request):
+    """config C4's shape with rectangular nodes, and the same three levels with nodes that are unions of touching boxes"""
+    return C4(ctx, boxes=MASKED_BOXES if request.param == "touching_boxes" else None)
 
 
 def test_hierarchy_layout_and_rejections(ctx, c4):
@@ -133,6 +138,15 @@ def test_hierarchy_layout_and_rejections(ctx, c4):
         halves.append((op, a))
     with pytest.raises(m.MgicError):
         m.AMRHierarchy(c4.f, [[halves[0][0], halves[1][0]]])
+    # ... as ONE node (a union of boxes) they are a level
+    both = m.VariableCoeffPoissonOperator.patch_boxes(ctx, (2 * N,) * 3, [((16, 24, 24), (31, 39, 39)), ((32, 24, 24), (47, 39, 39))], L / N / 2)
+    assert both.valid_cells == 32 * 16 * 16 and both.n == (32, 16, 16)       # the union fills its bounding box: a rectangular patch
+    a2 = both.create()
+    a2.upload(np.ones(a2.shape))
+    both.setCoefs(a2, a2, 1.0, -1.0)
+    h2 = m.AMRHierarchy(c4.f, [[both]])
+    assert h2.nodes == 2
+    h2.close()
 
 
 def test_c4_vcycle_is_the_orchestrated_cycle_bit_for_bit(c4):
@@ -161,8 +175,8 @@ def test_c4_composite_operators_against_the_oracle(c4):
             assert np.array_equal(out[q].download(), w), ("applyOp", homog, q)
     # reductions over the uncovered cells
     big = [a.copy() for a in phi]
-    big[0][tw.under[1]] = 1e9
-    big[1][tw.under[3]] = -1e9
+    tw._put_under(big, 1, 1e9)
+    tw._put_under(big, 3, -1e9)
     gbig = c4.vec(big)
     assert c4.amr.norm(gbig, 0) == tw.norm(phi, 0)
     for ord_ in (1, 2):
@@ -200,3 +214,44 @@ def test_c4_preconditioner_and_outer_solve_against_the_oracle(c4):
     r = c4.vec()
     c4.amr.residual(r, dpsi, res, False)
     assert c4.amr.norm(r, 0) <= 1e-9 * hist[0]
+
+
+@pytest.mark.parametrize("boxes", [C4_BOXES, MASKED_BOXES], ids=["c4", "touching_boxes"])
+def test_nonlinear_solve_on_a_hierarchy(ctx, boxes):
+    """poissonSolve with max_level = 2 (Main_PoissonSolver.cpp:45-216) through mgic_hier_*: sources on every level with the
+    level's dx, multilevel BiCGStab preconditioned by AMR V-cycles, QuadCFInterp + psi update with carried coarse-fine ghosts,
+    composite norm -- against the oracle-backed twin: same BiCGStab iteration counts, dpsi norms to 1e-7, psi on every
+    node to 1e-10 relative in max-norm (north-star tolerance), iteration 1's sources to 1e-13."""
+    o, patches = bare_hierarchy(boxes)
+    log = []
+    norms_o, psi_o = hierarchy_nl_solve(o, patches, max_nl=3, log=log)
+    levels = [[(q.boxes if q.boxes else (q.lo, q.hi)) for q in lv] for lv in patches]
+    P = m.make_params(dict(o.params, max_NL_iterations=3))
+    H = m.Hierarchy(ctx, P, levels)
+    assert H.nodes == 1 + sum(len(lv) for lv in patches)
+    flat = [q for lv in patches for q in lv]
+    for n, q in enumerate(flat, start=1):
+        lvl, lo, nn, cells = H.node_info(n)
+        assert lo == tuple(q.lo) and nn == q.shape[::-1] and cells == int(q.mask().sum())
+        assert np.array_equal(H.mask(n), q.mask())
+    H.set_initial_conditions()
+    got = []
+    for it in range(3):
+        nrm, its, st = H.nl_iteration()
+        got.append(nrm)
+        assert (its, st) == (log[it][0], log[it][1]), (it, its, st, log[it])
+        if it == 0:   # sources of the first iteration: level-resolution Bowen-York terms
+            o2, p2 = bare_hierarchy(boxes)
+            o2.set_initial_conditions(); o2.set_coefs_and_rhs()
+            assert relerr(H.download(0, "rhs"), o2.get("RHS")) < 1e-13
+            for n, q in enumerate([q for lv in p2 for q in lv], start=1):
+                q.set_initial_conditions(o2.params); q.set_coefs_and_rhs()
+                assert relerr(H.download(n, "rhs"), q.var(8)) < 1e-13, n
+                assert relerr(H.download(n, "aCoef"), q.get("A")) < 1e-13, n
+    assert np.allclose(got, norms_o, rtol=1e-7), (got, norms_o)
+    for n in range(H.nodes):
+        assert relerr(H.download(n, "psi"), psi_o[n]) < 1e-10, n
+    # the one-call form gives the same history
+    H2 = m.Hierarchy(ctx, P, levels)
+    assert np.allclose(H2.nl_solve(), got, rtol=1e-12)
+    H.close(); H2.close()

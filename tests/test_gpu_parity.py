@@ -624,6 +624,78 @@ def test_amr_patch_operator_with_quad_cf_interp(ctx, name):
     op.close(); cop.close(); pop.close()
 
 
+UNIONS = {
+    # two boxes touching on a face, union L-shaped
+    "L": dict(n=(32, 32, 32), boxes=[((8, 8, 8), (23, 15, 23)), ((8, 16, 8), (15, 23, 23))], bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+    # touching the x-lo / y-hi / z-hi domain faces, Neumann and Dirichlet mixed
+    "on_faces": dict(n=(32, 32, 48), boxes=[((0, 8, 16), (15, 15, 47)), ((8, 16, 32), (23, 31, 47))], bc_lo=(1, 0, 0), bc_hi=(0, 1, 1)),
+    # three boxes in a staircase (re-entrant corners: one ghost position, different values per direction)
+    "staircase": dict(n=(40, 40, 40), boxes=[((8, 8, 8), (15, 15, 15)), ((16, 8, 8), (23, 23, 15)), ((16, 16, 16), (31, 31, 31))],
+                      bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+    # BRMeshRefine-like: 8^3 .. 16^3 boxes around a blob
+    "blob": dict(n=(64, 64, 64), boxes=[((16, 16, 16), (31, 31, 31)), ((32, 16, 16), (47, 31, 31)), ((16, 32, 16), (31, 47, 31)),
+                                        ((32, 32, 24), (39, 39, 31)), ((24, 24, 32), (39, 39, 39)), ((24, 24, 8), (31, 31, 15))],
+                 bc_lo=(0, 0, 0), bc_hi=(0, 0, 0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(UNIONS))
+@pytest.mark.parametrize("with_b", [False, True])
+def test_amr_level_of_touching_boxes(ctx, name, with_b):
+    """An AMR level made of several boxes that touch (BRMeshRefine's output; SURVEY row a16, a15's fine-fine exchange on
+    AMR levels): the library holds the union in ONE masked array; the oracle holds one ghosted FAB per max_grid_size box
+    and runs the reference's sequence per pass -- homogeneousCFInterp / QuadCFInterp on every face ghost, exchange between
+    the boxes, BC, kernel (VariableCoeffPoissonOperator.cpp:296-329, :44-66).  Colour passes, relax, preCond,
+    restrictResidual, AMROperatorNF and AMRResidualNF: BIT-EXACT; cells outside the boxes stay zero."""
+    from oracle import OraclePatch
+    c = UNIONS[name]
+    dx, val = 0.25, 0.2
+    P = OraclePatch(c["n"], None, None, dx, max_grid_size=8, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], bc_value=val, boxes=c["boxes"])
+    mask = P.mask()
+    assert P.num_boxes >= len(c["boxes"]) and mask.sum() < mask.size
+    rng = np.random.default_rng(16)
+    e0, r = rng.standard_normal(P.shape), rng.standard_normal(P.shape)
+    a = 0.1 * rng.standard_normal(P.shape) - 0.5
+    b = 1 + 0.1 * rng.standard_normal(P.shape) if with_b else np.ones(P.shape)
+    cn = tuple(x // 2 for x in c["n"])
+    crse = rng.standard_normal(cn[::-1])
+    for f, x in (("E", e0), ("R", r), ("A", a), ("B", b)):
+        P.set(f, x)
+    P.set_coarse(crse)
+    op = m.VariableCoeffPoissonOperator.patch_boxes(ctx, c["n"], c["boxes"], dx, bc_lo=c["bc_lo"], bc_hi=c["bc_hi"], bc_value=val)
+    assert np.array_equal(op.mask(), mask) and op.valid_cells == int(mask.sum())
+    cop = m.VariableCoeffPoissonOperator(ctx, tuple(s // 2 for s in P.shape[::-1]), 2 * dx)   # the coarsened bounding box
+    full = m.VariableCoeffPoissonOperator(ctx, cn, 2 * dx)                                    # the coarser level
+    A, B, E, R, LHS, RC, CR = op.create(), op.create(), op.create(), op.create(), op.create(), cop.create(), full.create()
+    A.upload(a); B.upload(b); R.upload(r); E.upload(e0); CR.upload(crse)     # uploads drop what lies outside the boxes
+    assert np.array_equal(E.download(), e0 * mask)
+    op.setCoefs(A, B if with_b else None, 1.0, -1.0)
+    assert np.array_equal(op.lambda_field().download() * mask, P.get("LAMBDA"))
+    for _ in range(2):
+        for colour in (0, 1):
+            P.gsrb_color(colour)
+            op.gsrb_color(E, R, colour)
+            assert np.array_equal(E.download(), P.get("E")), colour
+    P.relax(3); op.relax(E, R, 3)
+    assert np.array_equal(E.download(), P.get("E"))
+    op.restrictResidual(RC, E, R)
+    assert np.array_equal(RC.download(), P.restrict())
+    for homog in (True, False):
+        op.AMROperatorNF(LHS, E, CR, homogeneous=homog)
+        assert np.array_equal(LHS.download(), P.amr_operator_nf(homog)), ("AMROperatorNF", homog)
+        op.AMRResidualNF(LHS, E, CR, R, homogeneous=homog)
+        assert np.array_equal(LHS.download(), P.amr_residual_nf(homog)), ("AMRResidualNF", homog)
+    P.precond(); op.preCond(E, R)
+    assert np.array_equal(E.download(), P.get("E"))
+    assert np.all(E.download()[mask == 0] == 0)
+    # max-norm / dot products see the level's cells only
+    op.setVal(LHS, 3.0)
+    assert op.norm(LHS, 1) == 3.0 * mask.sum()
+    for x in (A, B, E, R, LHS, RC, CR):
+        x.close()
+    op.close(); cop.close(); full.close()
+
+
 def test_two_level_amr_vcycle_on_the_c_abi(ctx):
     """The two-level AMR V-cycle of tests/test_oracle.py (structure of [Chombo] AMRVCycle) with every numerical step on the
     GPU through the C ABI -- patch relax (homogeneousCFInterp), AMRResidualNF (QuadCFInterp), the base level's
