@@ -320,6 +320,27 @@ int mgic_hier_nl_iteration(mgic_hier *, double *dpsi_norm, int *solver_iteration
 int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_iterations);                 /* :93 + the loop */
 /* what: 0..7 multigrid_vars component (0 = psi, MultigridUserVariables.hpp), 8 dpsi, 9 rhs, 10 aCoef; bounding-box shaped */
 int mgic_hier_download(const mgic_hier *, int node, int what, double *host);
+/* ----------------------------------------------------------------- grid generation
+ * replaces: set_grids, set_tag_cells (Source/SetGrids.cpp:31-148,172-207) with set_regrid_condition
+ * (Source/SetLevelData.cpp:188-240) and [Chombo] BRMeshRefine::regrid (nesting radius 2, :64-68,113-114): base level =
+ * domainSplit lattice of max_grid_size boxes; while a new level appears, on every level tag the cells whose |regrid
+ * condition| >= refine_threshold * max over the level, grow the tags by two cells, and re-cluster (Berger-Rigoutsos
+ * signatures, fill_ratio, boxes multiples of block_factor and at most max_grid_size, proper nesting).  P->max_level is the
+ * deepest level allowed; refine_threshold / fill_ratio are params.txt's keys of that name (buffer_size is read by the
+ * reference but never used: Source/PoissonParameters.cpp:55).  BRMeshRefine is Chombo's (not vendored): restated, see
+ * csrc/grids.cu.  mgic_grids_regrid = the clustering alone on caller-supplied tags (host only, no device needed). */
+typedef struct mgic_grids mgic_grids;
+int mgic_grids_generate(mgic_ctx *, const mgic_params *P, double refine_threshold, double fill_ratio, mgic_grids **out);
+int mgic_grids_regrid(const mgic_params *P, double fill_ratio, int top_level, const int *nboxes, const int *boxes, const int *ntags,
+                      const int *tags, mgic_grids **out);
+int mgic_grids_destroy(mgic_grids *);
+int mgic_grids_levels(const mgic_grids *);
+int mgic_grids_num_boxes(const mgic_grids *, int level);
+/* boxes: 6 ints each {lo0,lo1,lo2,hi0,hi1,hi2}; part_of_box: the connected part (0 .. *nparts-1) each box belongs to */
+int mgic_grids_get_boxes(const mgic_grids *, int level, int *boxes, int *part_of_box, int *nparts);
+int mgic_grids_level_stats(const mgic_grids *, int level, double *max_condition, long long *tagged_cells, long long *cells);
+/* the problem object on these grids: every level > 0 as its connected parts, each in one masked array */
+int mgic_hier_create_from_grids(mgic_ctx *, const mgic_params *P, const mgic_grids *, mgic_hier **out);
 /* multigrid_vars of one AMR level > 0 and its psi update (the pieces mgic_hier composes) */
 int mgic_vars_create_patch(mgic_ctx *, const mgic_params *P, const mgic_op *patch, mgic_vars **out);
 int mgic_update_psi0_patch(mgic_vars *, mgic_op *patch, mgic_field *dpsi, const mgic_field *dpsi_coarse, const int coarse_lo[3]);

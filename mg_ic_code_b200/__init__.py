@@ -5,5 +5,5 @@ reference's operator / factory interface), params.py (params.txt reader).  See D
 """
 from ._capi import MgicError, MgicParams, lib, library_path  # noqa: F401
 from .params import DEFAULTS, make_params, read_params  # noqa: F401
-from .operator import (AMRHierarchy, Context, Hierarchy, LevelField, MultigridVars, VariableCoeffPoissonOperator,  # noqa: F401
+from .operator import (AMRHierarchy, Context, Grids, Hierarchy, LevelField, MultigridVars, VariableCoeffPoissonOperator,  # noqa: F401
                        VariableCoeffPoissonOperatorFactory, level_op_from_params, nl_solve)

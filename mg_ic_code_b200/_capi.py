@@ -101,6 +101,11 @@ def lib():
         "mgic_hier_set_initial_conditions": [vp], "mgic_hier_nl_iteration": [vp, dp, ip, ip],
         "mgic_hier_nl_solve": [vp, dp, C.c_int, ip], "mgic_hier_download": [vp, C.c_int, C.c_int, nd],
         "mgic_vars_create_patch": [vp, C.POINTER(MgicParams), vp, pvp],
+        "mgic_grids_generate": [vp, C.POINTER(MgicParams), C.c_double, C.c_double, pvp],
+        "mgic_grids_regrid": [C.POINTER(MgicParams), C.c_double, C.c_int, ip, ip, ip, ip, pvp],
+        "mgic_grids_destroy": [vp], "mgic_grids_get_boxes": [vp, C.c_int, ip, ip, ip],
+        "mgic_grids_level_stats": [vp, C.c_int, dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
+        "mgic_hier_create_from_grids": [vp, C.POINTER(MgicParams), vp, pvp],
         "mgic_update_psi0_patch": [vp, vp, vp, vp, i3],
     }
     for name, argtypes in sig.items():
@@ -109,6 +114,10 @@ def lib():
         f.restype = C.c_int
     L.mgic_ctx_stream.argtypes = [vp]
     L.mgic_ctx_stream.restype = vp
+    L.mgic_grids_levels.argtypes = [vp]
+    L.mgic_grids_levels.restype = C.c_int
+    L.mgic_grids_num_boxes.argtypes = [vp, C.c_int]
+    L.mgic_grids_num_boxes.restype = C.c_int
     L.mgic_op_valid_cells.argtypes = [vp]
     L.mgic_op_valid_cells.restype = C.c_longlong
     L.mgic_ctx_launch_count.argtypes = [vp]

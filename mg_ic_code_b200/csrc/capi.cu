@@ -1410,15 +1410,18 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
             for (int i = 0; i < o->n[0] && nested; i += 2) {
               if (!o->hmask.empty() && !o->hmask[(size_t)i + (size_t)o->n[0] * ((size_t)j + (size_t)o->n[1] * k)]) continue;
               const int c[3] = {(o->plo[0] + i) >> 1, (o->plo[1] + j) >> 1, (o->plo[2] + k) >> 1};
-              nested = pvalid(c[0], c[1], c[2]);
-              for (int f = 0; f < 6 && nested; f++) {
-                int q[3] = {c[0], c[1], c[2]};
-                q[f >> 1] += (f & 1) ? 1 : -1;
-                if (q[f >> 1] < 0 || q[f >> 1] >= o->ndom[f >> 1] / 2) continue;   // outside the domain: physical boundary
-                nested = pvalid(q[0], q[1], q[2]);
-              }
+              // QuadCFInterp reads, around every coarse cell next to the patch, its tangential and diagonal neighbours: the
+              // whole 3 x 3 x 3 neighbourhood of the cells under the patch must be cells of the parent level (or outside the domain)
+              for (int dk = -1; dk <= 1 && nested; dk++)
+                for (int dj = -1; dj <= 1 && nested; dj++)
+                  for (int di = -1; di <= 1 && nested; di++) {
+                    const int q3[3] = {c[0] + di, c[1] + dj, c[2] + dk};
+                    bool outside = false;
+                    for (int d = 0; d < 3; d++) outside = outside || q3[d] < 0 || q3[d] >= o->ndom[d] / 2;
+                    if (!outside) nested = pvalid(q3[0], q3[1], q3[2]);
+                  }
             }
-        if (!nested) return amr_fail(A, "patch %d of level %d is not properly nested in the cells of the level below (one coarse cell all around)", q, l);
+        if (!nested) return amr_fail(A, "patch %d of level %d is not properly nested in the cells of the level below (one coarse cell all around, diagonals included)", q, l);
       }
       // the nodes of one level must not touch: touching boxes belong into ONE node (mgic_op_create_patch_boxes: a union of
       // boxes in one masked array, where the fine-fine exchange is a neighbour read)
@@ -1946,7 +1949,13 @@ extern "C" int mgic_hier_node_info(const mgic_hier *H, int q, int *level, int lo
 extern "C" int mgic_hier_download(const mgic_hier *H, int q, int what, double *host) {
   MGIC_REQUIRE(H && host && q >= 0 && q < (int)H->nodes.size() && what >= 0 && what <= 10, "bad argument");
   const HierNode &nd = H->nodes[q];
-  if (what < 8) return mgic_vars_download(nd.vars, what, host);
+  if (what < 8) {
+    MGIC_TRY(mgic_vars_download(nd.vars, what, host));
+    if (nd.op && !nd.op->hmask.empty())   // the array also covers bounding-box cells outside the level's boxes: not data
+      for (size_t i = 0; i < nd.op->hmask.size(); i++)
+        if (!nd.op->hmask[i]) host[i] = 0.0;
+    return MGIC_OK;
+  }
   return mgic_field_download(what == 8 ? nd.dpsi : what == 9 ? nd.rhs : nd.a, host);
 }
 extern "C" int mgic_hier_get_mask(const mgic_hier *H, int q, unsigned char *host) {

@@ -158,6 +158,54 @@ __global__ void __launch_bounds__(128) k_rhs_acoef(SrcP P, const double *__restr
   if (rhs) rhs[o] = 0.125 * m * p5 - 0.125 * A2 * (1.0 / p7) - 2.0 * M_PI * P.G_Newton * rho * psi_0 - lap;  // :121-124
 }
 
+// set_regrid_condition (Source/SetLevelData.cpp:188-240) on the data set_grids evaluates it on (Source/SetGrids.cpp:86-95:
+// fresh set_initial_conditions -- psi = 1, phi and A_ij analytic, ghost cells included): a function of the cell position
+// alone, so it is evaluated analytically over any index box [lo, lo + n) of a level with spacing dx -- no multigrid_vars
+// array, no dependence on how the level is cut into boxes.  mode 1: set_constant_K_integrand (:128-186) on the same data.
+__device__ __forceinline__ double phi_at(const SrcP &P, int i, int j, int k) {
+  double loc[3];
+  cell_loc(P, i, j, k, loc);
+  const double r2 = loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2];
+  return P.phi_amplitude * exp(-r2 / P.phi_wavelength);   // MyPhiFunction.H:11-16
+}
+__global__ void __launch_bounds__(128) k_condition(SrcP P, int mode, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= P.nx || j >= P.ny) return;
+  const int gi = i + P.i0, gj = j + P.j0, gk = k + P.k0;
+  // GETRHOGRADPHIF on the analytic phi (SetLevelDataF.ChF:65-103)
+  double rho = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double g = 0.5 / P.dx * (phi_at(P, gi + (d == 0), gj + (d == 1), gk + (d == 2)) - phi_at(P, gi - (d == 0), gj - (d == 1), gk - (d == 2)));
+    rho = rho + 0.5 * g * g;
+  }
+  double loc[3];
+  cell_loc(P, gi, gj, gk, loc);
+  const double m = (2.0 / 3.0) * (0.0 * 0.0) - 16.0 * M_PI * P.G_Newton * (0.5 * 0.0 * 0.0 + 0.0);   // set_m_value(m, phi, params, 0.0)
+  double l1[3] = {loc[0] - P.off1, loc[1], loc[2]};
+  double l2[3] = {loc[0] - P.off2, loc[1], loc[2]};
+  const double r1 = sqrt(l1[0] * l1[0] + l1[1] * l1[1] + l1[2] * l1[2]);
+  const double rr2 = sqrt(l2[0] * l2[0] + l2[1] * l2[1] + l2[2] * l2[2]);
+  const double n1[3] = {l1[0] / r1, l1[1] / r1, l1[2] / r1};
+  const double n2[3] = {l2[0] / rr2, l2[1] / rr2, l2[2] / rr2};
+  const double J1[3] = {0.0, 0.0, P.spin1}, J2[3] = {0.0, 0.0, P.spin2};
+  const double P1[3] = {0.0, P.mom1, 0.0}, P2[3] = {0.0, P.mom2, 0.0};
+  const double a11 = get_Aij(0, 0, r1, rr2, n1, n2, J1, J2, P1, P2), a22 = get_Aij(1, 1, r1, rr2, n1, n2, J1, J2, P1, P2);
+  const double a33 = get_Aij(2, 2, r1, rr2, n1, n2, J1, J2, P1, P2), a12 = get_Aij(0, 1, r1, rr2, n1, n2, J1, J2, P1, P2);
+  const double a13 = get_Aij(0, 2, r1, rr2, n1, n2, J1, J2, P1, P2), a23 = get_Aij(1, 2, r1, rr2, n1, n2, J1, J2, P1, P2);
+  const double A2 = a11 * a11 + a22 * a22 + a33 * a33 + 2 * (a12 * a12) + 2 * (a13 * a13) + 2 * (a23 * a23);
+  const double psi_0 = 1.0 + (P.m1 / r1 + P.m2 / rr2);
+  const double p2 = psi_0 * psi_0, p4 = p2 * p2;
+  double v;
+  if (mode == 0)   // :233-236
+    v = 1.5 * fabs(m) + 1.5 * A2 * (1.0 / (p4 * p2 * psi_0)) + 24.0 * M_PI * P.G_Newton * fabs(rho) * psi_0 + log(psi_0);
+  else             // :180-183 with laplacian(psi = 1) = 0
+    v = -1.5 * m + 1.5 * A2 * (1.0 / (p4 * p4 * p4)) + 24.0 * M_PI * P.G_Newton * rho * (1.0 / p4) + 12.0 * 0.0 * (1.0 / (p4 * psi_0));
+  out[i + (long long)j * P.nx + (long long)k * P.nx * P.ny] = v;
+}
+
 // set_update_psi0 -- Source/SetLevelData.cpp:243-263: psi += dpsi over the GHOSTED box.  dpsi's domain-face
 // ghost is what the solver's last homogeneous BC fill left there: a*near (+0).
 __global__ void __launch_bounds__(128) k_update_psi(SrcP P, Geom g, BCk bc, double *__restrict__ mv,
@@ -254,6 +302,18 @@ int set_rhs_acoef(mgic_vars *v, double *rhs, double *acoef, double constant_K) {
   dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
   k_rhs_acoef<<<grd, blk, 0, v->ctx->stream>>>(s, v->d, rhs, acoef, constant_K);
   return post(v->ctx, "set_rhs_acoef");
+}
+
+// the regrid condition / constant-K integrand on the index box [lo, lo + n) of a level with spacing dx (device array `out`)
+int condition_box(mgic_ctx *c, const mgic_params &P, double dx, const int lo[3], const int n[3], int mode, double *out) {
+  mgic_vars v;
+  v.ctx = c; v.P = P;
+  for (int d = 0; d < 3; d++) { v.n[d] = n[d]; v.lo[d] = lo[d]; }
+  v.k0 = lo[2]; v.nzl = n[2]; v.dx = dx; v.isPatch = true;
+  SrcP s = make_srcp(&v);
+  dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
+  k_condition<<<grd, blk, 0, c->stream>>>(s, mode, out);
+  return post(c, "regrid_condition");
 }
 
 int update_psi_patch(mgic_vars *v, const BCk &bc, const double *dpsi) {

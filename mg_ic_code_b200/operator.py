@@ -479,6 +479,62 @@ class MultigridVars:
             self.h = None
 
 
+class Grids:
+    """set_grids (Source/SetGrids.cpp:31-148): the hierarchy of boxes from tagging + [Chombo] BRMeshRefine::regrid.
+    Grids.generate needs a GPU (the regrid condition is a device kernel); Grids.regrid is the clustering alone on
+    caller-supplied tags (host only)."""
+
+    def __init__(self, handle, L):
+        self.h, self.L = handle, L
+
+    @classmethod
+    def generate(cls, ctx, params, refine_threshold=0.1, fill_ratio=0.5):
+        p = params if not isinstance(params, dict) else make_params(params)
+        h = C.c_void_p()
+        check(ctx.L.mgic_grids_generate(ctx.h, C.byref(p), refine_threshold, fill_ratio, C.byref(h)))
+        return cls(h, ctx.L)
+
+    @classmethod
+    def regrid(cls, params, boxes_per_level, tags_per_level, fill_ratio=0.5):
+        """boxes_per_level[l] = [(lo, hi), ...], tags_per_level[l] = [(i, j, k), ...] for the existing levels 0 .. top"""
+        p = params if not isinstance(params, dict) else make_params(params)
+        L = lib()
+        mk = lambda v: (C.c_int * max(len(v), 1))(*v)
+        nb = [len(b) for b in boxes_per_level]
+        fb = [v for lv in boxes_per_level for lo, hi in lv for v in (list(lo) + list(hi))]
+        nt = [len(t) for t in tags_per_level]
+        ft = [int(v) for lv in tags_per_level for t in lv for v in t]
+        h = C.c_void_p()
+        check(L.mgic_grids_regrid(C.byref(p), fill_ratio, len(boxes_per_level) - 1, mk(nb), mk(fb), mk(nt), mk(ft), C.byref(h)))
+        return cls(h, L)
+
+    @property
+    def levels(self):
+        return self.L.mgic_grids_levels(self.h)
+
+    def boxes(self, level, parts=False):
+        n = self.L.mgic_grids_num_boxes(self.h, level)
+        b, part, np_ = (C.c_int * max(6 * n, 1))(), (C.c_int * max(n, 1))(), C.c_int()
+        check(self.L.mgic_grids_get_boxes(self.h, level, b, part, C.byref(np_)))
+        out = [(tuple(b[6 * q:6 * q + 3]), tuple(b[6 * q + 3:6 * q + 6])) for q in range(n)]
+        return (out, list(part[:n]), np_.value) if parts else out
+
+    def nodes(self, level):
+        """the level as its connected parts: [[(lo, hi), ...], ...] -- what Hierarchy takes"""
+        b, part, n = self.boxes(level, parts=True)
+        return [[b[q] for q in range(len(b)) if part[q] == c] for c in range(n)]
+
+    def stats(self, level):
+        mx, tg, cells = C.c_double(), C.c_longlong(), C.c_longlong()
+        check(self.L.mgic_grids_level_stats(self.h, level, C.byref(mx), C.byref(tg), C.byref(cells)))
+        return dict(max_condition=mx.value, tagged_cells=tg.value, cells=cells.value)
+
+    def close(self):
+        if self.h:
+            self.L.mgic_grids_destroy(self.h)
+            self.h = None
+
+
 class Hierarchy:
     """poissonSolve (Main_PoissonSolver.cpp:45-256) on an AMR hierarchy: levels = [[node, ...], ...] for levels 1, 2, ...;
     a node is a list of boxes (lo, hi) -- one connected component of its level, boxes may touch -- or a single (lo, hi)."""
@@ -501,6 +557,18 @@ class Hierarchy:
         check(self.L.mgic_hier_create(ctx.h, C.byref(self.params), len(levels), mk(nnodes), mk(nboxes), mk(flat), C.byref(h)))
         self.h = h
         self.nodes = self.L.mgic_hier_nodes(h)
+
+    @classmethod
+    def from_grids(cls, ctx, params, grids):
+        """the problem on the hierarchy set_grids produced (Main_PoissonSolver.cpp:278-284: set_grids, then poissonSolve)"""
+        self = cls.__new__(cls)
+        self.ctx, self.L = ctx, ctx.L
+        self.params = params if not isinstance(params, dict) else make_params(params)
+        h = C.c_void_p()
+        check(self.L.mgic_hier_create_from_grids(ctx.h, C.byref(self.params), grids.h, C.byref(h)))
+        self.h = h
+        self.nodes = self.L.mgic_hier_nodes(h)
+        return self
 
     def node_info(self, q):
         """(level, lo (i, j, k), n (nx, ny, nz), valid cells)"""

@@ -1522,6 +1522,42 @@ double orc_update_psi0(orc_problem *pb) {
   return std::sqrt(sum * dV);
 }
 
+// set_regrid_condition (Source/SetLevelData.cpp:188-240; mode 0) / set_constant_K_integrand (:128-186; mode 1) on freshly
+// initialised data (set_grids: Source/SetGrids.cpp:86-95) over the index box [lo, hi] of a level with spacing dx
+void orc_condition_box(const orc_params *Pp, double dx, const int lo[3], const int hi[3], int mode, double *out) {
+  const orc_params &P = *Pp;
+  Layout lay;
+  lay.domain = Box(lo, hi).grown(4);
+  lay.boxes.push_back(Box(lo, hi));
+  LevelData mgvars, dpsi;
+  mgvars.define(&lay, 8, 1); dpsi.define(&lay, 1, 1);
+  init_conditions_level(P, dx, mgvars, dpsi);
+  const FAB &mv = mgvars.fab[0];
+  const Box tb(lo, hi);
+  FAB rho, lap; rho.define(tb, 1); lap.define(tb, 1);
+  View psiV = fabview(mv); View phiV = fabview(mv); phiV.p += mv.sc * 7;
+  k_rho(fabview(rho), phiV, dx, tb);                                        // :205-208 / :151-154
+  k_lap(fabview(lap), psiV, dx, tb);                                        // :145-148 (mode 1)
+  const long nx = tb.size(0), ny = tb.size(1);
+  for (int k = tb.lo[2]; k <= tb.hi[2]; k++)
+    for (int j = tb.lo[1]; j <= tb.hi[1]; j++)
+      for (int i = tb.lo[0]; i <= tb.hi[0]; i++) {
+        Real loc[3]; cellLoc(P, dx, i, j, k, loc);
+        Real m = m_value(P, 0.0);                                           // set_m_value(m, phi, params, 0.0)
+        Real A2 = A2_of(mv, i, j, k);
+        Real psi_bh = set_binary_bh_psi(loc, P);
+        Real psi_0 = mv(i, j, k, 0) + psi_bh;
+        Real v;
+        if (mode == 0)
+          v = 1.5 * std::abs(m) + 1.5 * A2 * std::pow(psi_0, -7.0) + 24.0 * M_PI * P.G_Newton * std::abs(rho(i, j, k)) * std::pow(psi_0, 1.0) +
+              std::log(psi_0);                                              // :233-236
+        else
+          v = -1.5 * m + 1.5 * A2 * std::pow(psi_0, -12.0) + 24.0 * M_PI * P.G_Newton * rho(i, j, k) * std::pow(psi_0, -4.0) +
+              12.0 * lap(i, j, k) * std::pow(psi_0, -5.0);                  // :180-183
+        out[(i - tb.lo[0]) + nx * ((j - tb.lo[1]) + ny * (long)(k - tb.lo[2]))] = v;
+      }
+}
+
 // dpsi := the given valid cells, ghost layer 1 = the inhomogeneous ParseBC fill (what [Chombo] BiCGStab leaves there: the
 // initial residual's inhomogeneous fill + the homogeneous ghosts of the accumulated correction).  For callers whose solver
 // ran outside this library (the hierarchy twin of tests/amr_twin.py) before orc_update_psi0.

@@ -149,6 +149,8 @@ int orc_outer_solve(orc_problem *, int *exit_status, double *final_norm, double 
 /* Main_PoissonSolver.cpp:189-205 + computeNorm :208 ; returns dpsi_norm */
 double orc_update_psi0(orc_problem *);
 /* full NL loop (Main_PoissonSolver.cpp:131-216); dpsi_norms[NL_iter]; returns #NL iterations */
+/* set_regrid_condition (mode 0) / set_constant_K_integrand (mode 1) on fresh initial data over the index box [lo, hi] */
+void orc_condition_box(const orc_params *, double dx, const int lo[3], const int hi[3], int mode, double *out);
 void orc_set_dpsi_with_bc(orc_problem *, const double *valid_cells);   /* then orc_update_psi0 */
 int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
 

@@ -106,6 +106,7 @@ def lib():
         L.orc_outer_solve.restype = C.c_int
         L.orc_update_psi0.argtypes = [C.c_void_p]
         L.orc_set_dpsi_with_bc.argtypes = [C.c_void_p, dp]
+        L.orc_condition_box.argtypes = [C.POINTER(OrcParams), C.c_double, C.c_int * 3, C.c_int * 3, C.c_int, dp]
         L.orc_update_psi0.restype = C.c_double
         L.orc_nl_solve.argtypes = [C.c_void_p, dp, C.c_int]
         L.orc_nl_solve.restype = C.c_int
@@ -257,6 +258,15 @@ class Oracle:
     @property
     def num_threads(self):
         return self.L.orc_num_threads()
+
+
+def condition_box(params, dx, lo, hi, mode=0):
+    """set_regrid_condition (mode 0) / set_constant_K_integrand (mode 1) on fresh initial data over the index box [lo, hi] of a
+    level with spacing dx; [k, j, i]"""
+    p = to_struct(params)
+    out = np.zeros(tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0)))
+    lib().orc_condition_box(C.byref(p), dx, (C.c_int * 3)(*lo), (C.c_int * 3)(*hi), mode, out)
+    return out
 
 
 def use_all_host_cores():

@@ -70,6 +70,10 @@ def lib(cuda=False):
         nd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
         L.ref_set_level_data.argtypes = [C.POINTER(RefParams), C.c_int * 3, C.c_double, C.c_double, C.c_void_p, nd, nd, nd, nd]
         L.ref_set_level_data.restype = C.c_int
+        L.ref_condition.argtypes = [C.POINTER(RefParams), C.c_int * 3, C.c_double, C.c_int, nd]
+        L.ref_condition.restype = C.c_int
+        L.ref_output_data.argtypes = [C.POINTER(RefParams), C.c_int * 3, C.c_double, C.c_double, C.c_void_p, nd]
+        L.ref_output_data.restype = C.c_int
         L.ref_point_values.argtypes = [C.POINTER(RefParams), C.c_double * 3, C.c_double * 6, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_point_values.restype = None
         L.ref_m_value.argtypes = [C.POINTER(RefParams), C.c_double, C.c_double]
@@ -131,6 +135,31 @@ def set_level_data(params, constant_K=0.0, dpsi_ghosted=None, cuda=False):
     p = to_struct(params)
     lib(cuda).ref_set_level_data(C.byref(p), (C.c_int * 3)(*N), dx, constant_K, None if d is None else d.ctypes.data, mg, rhs, a, b)
     return mg, rhs, a, b
+
+
+def condition(params, mode=0, dx=None):
+    """The reference's set_regrid_condition (mode 0) / set_constant_K_integrand (mode 1) on freshly initialised data, one
+    box of N cells at spacing dx (default L / N[0]): [nz, ny, nx]"""
+    N = tuple(params["N"])
+    out = np.zeros((N[2], N[1], N[0]))
+    p = to_struct(params)
+    lib().ref_condition(C.byref(p), (C.c_int * 3)(*N), params["L"] / N[0] if dx is None else dx, mode, out)
+    return out
+
+
+def output_data(params, constant_K=0.0, dpsi_ghosted=None):
+    """The reference's set_output_data after set_initial_conditions [+ set_update_psi0(dpsi)]: the 32 GRChombo variables with
+    three ghost layers, [32, nz+6, ny+6, nx+6]"""
+    N = tuple(params["N"])
+    g = (N[2] + 6, N[1] + 6, N[0] + 6)
+    out = np.zeros((32,) + g)
+    d = None
+    if dpsi_ghosted is not None:
+        d = np.ascontiguousarray(dpsi_ghosted, dtype=np.float64)
+        assert d.shape == g
+    p = to_struct(params)
+    lib().ref_output_data(C.byref(p), (C.c_int * 3)(*N), params["L"] / N[0], constant_K, None if d is None else d.ctypes.data, out)
+    return out
 
 
 def point_values(params, loc):

@@ -262,6 +262,46 @@ int ref_set_level_data(const ref_params *p, const int N[3], double dx, double co
   return 0;
 }
 
+// set_regrid_condition (mode 0, Source/SetLevelData.cpp:188-240) / set_constant_K_integrand (mode 1, :128-186) of the
+// reference on freshly initialised data (what set_grids does, Source/SetGrids.cpp:86-95); one box of N cells; out N^3
+int ref_condition(const ref_params *p, const int N[3], double dx, int mode, double *out) {
+  PoissonParameters params = to_params(p);
+  Box dom(IntVect(0, 0, 0), IntVect(N[0] - 1, N[1] - 1, N[2] - 1));
+  const IntVect g3(3, 3, 3);
+  LevelData<FArrayBox> vars(dom, NUM_MULTIGRID_VARS, g3), dpsi(dom, 1, g3), cond(dom, 1, IntVect::Zero);
+  RealVect vdx(dx, dx, dx);
+  set_initial_conditions(vars, dpsi, vdx, params);
+  if (mode == 0) set_regrid_condition(cond, vars, vdx, params);
+  else set_constant_K_integrand(cond, vars, vdx, params);
+  DataIterator dit = cond.dataIterator();
+  dit.begin();
+  copy_out(cond[dit()], 0, out);
+  return 0;
+}
+
+// set_output_data (Source/SetLevelData.cpp:343-396): the 32 GRChombo variables from multigrid_vars after psi += dpsi_ghosted
+// (may be NULL); one box of N cells with the checkpoint's three ghost layers (Source/WriteOutput.H:180); out 32 x (N+6)^3
+int ref_output_data(const ref_params *p, const int N[3], double dx, double constant_K, const double *dpsi_ghosted, double *out) {
+  PoissonParameters params = to_params(p);
+  Box dom(IntVect(0, 0, 0), IntVect(N[0] - 1, N[1] - 1, N[2] - 1));
+  const IntVect g3(3, 3, 3);
+  LevelData<FArrayBox> vars(dom, NUM_MULTIGRID_VARS, g3), dpsi(dom, 1, g3), gr(dom, NUM_GRCHOMBO_VARS, g3);
+  RealVect vdx(dx, dx, dx);
+  set_initial_conditions(vars, dpsi, vdx, params);
+  DataIterator dit = vars.dataIterator();
+  dit.begin();
+  if (dpsi_ghosted) {
+    FArrayBox &d = dpsi[dit()];
+    Real *dst = d.dataPtr(0);
+    for (long q = 0; q < d.box().numPts(); q++) dst[q] = dpsi_ghosted[q];
+    Copier none;
+    set_update_psi0(vars, dpsi, none);
+  }
+  set_output_data(gr, vars, params, vdx, constant_K);
+  for (int c = 0; c < NUM_GRCHOMBO_VARS; c++) copy_out(gr[dit()], c, out + (size_t)c * gr[dit()].box().numPts());
+  return 0;
+}
+
 // the point functions of Source/SetBinaryBH.H and MyPhiFunction.H at one location (relative to the domain centre)
 void ref_point_values(const ref_params *p, const double loc[3], double Aij[6], double *psi_bh, double *phi) {
   PoissonParameters params = to_params(p);

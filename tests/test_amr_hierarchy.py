@@ -15,7 +15,7 @@ C4_BOXES = {1: [((16, 24, 24), (47, 39, 39))],
 # the same three levels with levels made of TOUCHING boxes whose union is no rectangle (what BRMeshRefine produces): a node is
 # a list of boxes = one connected component of its level, held by the library in one masked array
 MASKED_BOXES = {1: [[((16, 24, 24), (31, 39, 39)), ((32, 24, 24), (47, 31, 39))]],
-                2: [[((36, 52, 52), (51, 67, 67)), ((52, 52, 52), (59, 59, 67))], ((68, 50, 52), (83, 59, 67))]}
+                2: [[((36, 52, 52), (51, 67, 67)), ((52, 52, 52), (59, 59, 67))], ((68, 52, 52), (83, 59, 67))]}
 
 
 def c4_hierarchy(N=32, L=100.0, smooth=2, mg_iterations=2, box=16, boxes=None):
