@@ -135,6 +135,32 @@ def host_mirror_params(path, overrides, tmp_path_factory):
 
 
 @live
+@live
+@pytest.mark.parametrize("over", [
+    dict(N=(16, 16, 16), L=40.0), dict(N=(24, 16, 32), L=100.0),
+    dict(N=(16, 16, 16), L=6.0, phi_amplitude=0.7),          # rho_grad of order one: |rho| is not its integer part
+    dict(N=(16, 16, 16), L=64.0, bh1_bare_mass=0.7, bh1_spin=-0.2, bh1_momentum=0.11, bh1_offset=7.0, bh2_bare_mass=0.3,
+         bh2_spin=0.4, bh2_momentum=-0.02, bh2_offset=-13.0, phi_amplitude=0.02, phi_wavelength=90.0, G_Newton=0.5),
+], ids=["c16", "noncubic", "strong_field", "other_physics"])
+def test_regrid_condition_and_constant_K_integrand_equal_the_reference(over):
+    """set_regrid_condition (Source/SetLevelData.cpp:188-240, what set_grids tags on) and set_constant_K_integrand (:128-186)
+    on freshly initialised data: the oracle's restatement against the reference's own functions, bit for bit -- on the
+    whole level, and on sub-boxes / a refined level's index box (the values depend on the cell position alone)"""
+    from oracle import condition_box, default_params
+    P = default_params(**over)
+    N, dx = P["N"], P["L"] / P["N"][0]
+    for mode in (0, 1):
+        ref = pyref.condition(P, mode)
+        assert np.array_equal(condition_box(P, dx, (0, 0, 0), (N[0] - 1, N[1] - 1, N[2] - 1), mode), ref), mode
+        sub = condition_box(P, dx, (3, 2, 5), (10, 9, 12), mode)
+        assert np.array_equal(sub, ref[5:13, 2:10, 3:11]), mode
+    # the level-1 index space: the reference run on the refined grid (dx / 2, 2 N cells)
+    P2 = dict(P, N=tuple(2 * x for x in N))
+    ref2 = pyref.condition(P2, 0, dx=dx / 2)
+    fine = condition_box(P, dx / 2, (8, 4, 6), (19, 17, 15), 0)
+    assert np.allclose(fine, ref2[6:16, 4:18, 8:20], rtol=1e-13, atol=0)   # L / N[0] / 2 vs (L / 2N[0]): the same number
+
+
 @pytest.mark.skipif(not os.path.exists(REF_PARAMS), reason="needs the reference's params.txt")
 @pytest.mark.parametrize("case", list(PARAM_CASES))
 def test_parameter_readers_agree_with_the_reference(case, tmp_path_factory):
