@@ -318,6 +318,11 @@ int mgic_hier_get_mask(const mgic_hier *, int node, unsigned char *host);       
 int mgic_hier_set_initial_conditions(mgic_hier *);                                    /* Main_PoissonSolver.cpp:90-96 */
 int mgic_hier_nl_iteration(mgic_hier *, double *dpsi_norm, int *solver_iterations, int *solver_status);   /* :131-212 body */
 int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_iterations);                 /* :93 + the loop */
+/* replaces: output_final_data + set_output_data (Source/WriteOutput.H:127-227, Source/SetLevelData.cpp:343-396): the GRChombo
+ * checkpoint (32 variables, three ghost layers per box, header / per-level attributes as the reference sets them).  No HDF5
+ * in this build: a self-describing container ("MGICCHK1" + JSON header + the doubles in Chombo's dataset order) that
+ * tools/mgic2hdf5.py converts to vcPoissonFinal.3d.hdf5. */
+int mgic_hier_write_checkpoint(mgic_hier *, const char *path, double constant_K);
 /* what: 0..7 multigrid_vars component (0 = psi, MultigridUserVariables.hpp), 8 dpsi, 9 rhs, 10 aCoef; bounding-box shaped */
 int mgic_hier_download(const mgic_hier *, int node, int what, double *host);
 /* ----------------------------------------------------------------- grid generation

@@ -1867,6 +1867,7 @@ struct HierNode {
   mgic_op *op = nullptr;          // patch operator (owned); null for the base level (the MG hierarchy's, rebuilt per iteration)
   mgic_vars *vars = nullptr;
   mgic_field *dpsi = nullptr, *rhs = nullptr, *a = nullptr, *b = nullptr;
+  std::vector<int> boxes;         // the node's boxes, 6 ints each (the checkpoint is written box by box)
 };
 struct mgic_hier {
   mgic_ctx *ctx = nullptr;
@@ -1906,6 +1907,13 @@ extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, c
     HierNode n0;
     H->nodes.push_back(n0);
     HierNode &n = H->nodes.back();
+    for (int k = 0; k < P->N[2]; k += P->max_grid_size)          // the base level's boxes: domainSplit (SetGrids.cpp:54-58)
+      for (int j = 0; j < P->N[1]; j += P->max_grid_size)
+        for (int i = 0; i < P->N[0]; i += P->max_grid_size) {
+          const int b6[6] = {i, j, k, std::min(i + P->max_grid_size, P->N[0]) - 1, std::min(j + P->max_grid_size, P->N[1]) - 1,
+                             std::min(k + P->max_grid_size, P->N[2]) - 1};
+          n.boxes.insert(n.boxes.end(), b6, b6 + 6);
+        }
     H_TRY(mgic_vars_create(c, P, 0, P->N[2], &n.vars));
     H_TRY(mgic_field_create(H->lay0, &n.dpsi)); H_TRY(mgic_field_create(H->lay0, &n.rhs));
     H_TRY(mgic_field_create(H->lay0, &n.a)); H_TRY(mgic_field_create(H->lay0, &n.b));
@@ -1923,6 +1931,7 @@ extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, c
       HierNode &n = H->nodes.back();
       H_TRY(mgic_op_create_patch_boxes(c, ndom, nboxes[qn], boxes + 6 * (size_t)qb, dxl, 2.0 * dxl, P->alpha, P->beta, bclo, bchi,
                                        P->bc_value, &n.op));
+      n.boxes.assign(boxes + 6 * (size_t)qb, boxes + 6 * (size_t)(qb + nboxes[qn]));
       qb += nboxes[qn];
       H_TRY(mgic_vars_create_patch(c, P, n.op, &n.vars));
       H_TRY(mgic_field_create(n.op, &n.dpsi)); H_TRY(mgic_field_create(n.op, &n.rhs));
@@ -2016,6 +2025,95 @@ extern "C" int mgic_hier_nl_iteration(mgic_hier *H, double *dpsi_norm, int *solv
   if (solver_status) *solver_status = st;
   return rc;
 }
+// output_final_data (Source/WriteOutput.H:127-227): the GRChombo checkpoint -- header ints / reals / strings, per level a
+// group with ref_ratio, tag_buffer_size, dx, dt = dx / 4, time, prob_domain, is_periodic_*, the level's boxes and the 32
+// GRChombo variables (set_output_data, Source/SetLevelData.cpp:343-396) with three ghost layers per box, stored as Chombo's
+// write(handle, LevelData, "data") does: box after box, per box component after component, x fastest over the ghosted box.
+// There is no HDF5 library in this build: the file is a self-describing container -- "MGICCHK1", a uint64 header length,
+// a JSON header with everything above plus byte offsets, zero padding to 8 bytes, then the doubles -- that
+// tools/mgic2hdf5.py turns into vcPoissonFinal.3d.hdf5 (dataset for dataset) wherever h5py exists.
+extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double constant_K) {
+  MGIC_REQUIRE(H && path, "NULL argument");
+  mgic_ctx *c = H->ctx;
+  const int NV = 32, NG = 3;
+  static const char *names[32] = {"chi", "h11", "h12", "h13", "h22", "h23", "h33", "K", "A11", "A12", "A13", "A22", "A23", "A33", "Theta",
+                                  "Gamma1", "Gamma2", "Gamma3", "lapse", "shift1", "shift2", "shift3", "B1", "B2", "B3", "phi", "Pi", "Ham",
+                                  "Mom1", "Mom2", "Mom3", nullptr};
+  const int nlev = (int)H->perLevel.size() + 1;
+  // boxes per level in node order; data offsets in doubles
+  struct LB { int node; const int *b; long long off; };
+  std::vector<std::vector<LB>> lev(nlev);
+  long long total = 0;
+  for (size_t q = 0; q < H->nodes.size(); q++)
+    for (size_t b = 0; b + 5 < H->nodes[q].boxes.size(); b += 6) {
+      const int *bx = H->nodes[q].boxes.data() + b;
+      lev[H->nodes[q].level].push_back({(int)q, bx, total});
+      total += (long long)NV * (bx[3] - bx[0] + 1 + 2 * NG) * (bx[4] - bx[1] + 1 + 2 * NG) * (bx[5] - bx[2] + 1 + 2 * NG);
+    }
+  std::string js = "{\"format\": \"MGICCHK1: GRChombo checkpoint of MG_IC_code (Source/WriteOutput.H:127-227) without HDF5\", ";
+  char buf[512];
+  js += "\"filename\": \"vcPoissonFinal.3d.hdf5\", \"root\": {\"ints\": {";
+  snprintf(buf, sizeof buf, "\"max_level\": %d, \"num_levels\": %d, \"iteration\": 0, \"num_components\": %d", nlev - 1, nlev, NV);
+  js += buf;
+  for (int l = 0; l < nlev; l++) { snprintf(buf, sizeof buf, ", \"regrid_interval_%d\": 1, \"steps_since_regrid_%d\": 0", l, l); js += buf; }
+  js += "}, \"reals\": {\"time\": 0.0}, \"strings\": {";
+  for (int v = 0; v < NV - 1; v++) { snprintf(buf, sizeof buf, "%s\"component_%d\": \"%s\"", v ? ", " : "", v, names[v]); js += buf; }
+  js += "}}, \"note_components\": \"the reference declares 32 variables (NUM_GRCHOMBO_VARS) and names 31 (GRChomboUserVariables.hpp:55-78)\", ";
+  js += "\"ghost\": [3, 3, 3], \"dtype\": \"float64 little endian\", \"levels\": [";
+  const double dx0 = H->P.L / H->P.N[0];
+  for (int l = 0; l < nlev; l++) {
+    const double dx = dx0 / (double)(1 << l);
+    snprintf(buf, sizeof buf, "%s{\"group\": \"level_%d\", \"ints\": {\"ref_ratio\": 2, \"tag_buffer_size\": 3, \"is_periodic_0\": 1, \"is_periodic_1\": 1, "
+             "\"is_periodic_2\": 1}, \"reals\": {\"dx\": %.17g, \"dt\": %.17g, \"time\": 0.0}, \"prob_domain\": [0, 0, 0, %d, %d, %d], \"boxes\": [",
+             l ? ", " : "", l, dx, 0.25 * dx, (H->P.N[0] << l) - 1, (H->P.N[1] << l) - 1, (H->P.N[2] << l) - 1);
+    js += buf;
+    for (size_t b = 0; b < lev[l].size(); b++) {
+      const int *x = lev[l][b].b;
+      snprintf(buf, sizeof buf, "%s[%d, %d, %d, %d, %d, %d]", b ? ", " : "", x[0], x[1], x[2], x[3], x[4], x[5]);
+      js += buf;
+    }
+    js += "], \"offsets\": [";
+    for (size_t b = 0; b < lev[l].size(); b++) { snprintf(buf, sizeof buf, "%s%lld", b ? ", " : "", lev[l][b].off - (lev[l].empty() ? 0 : lev[l][0].off)); js += buf; }
+    long long end = (l + 1 < nlev && !lev[l + 1].empty()) ? lev[l + 1][0].off : total;
+    snprintf(buf, sizeof buf, "%s%lld], \"data_start_double\": %lld}", lev[l].empty() ? "" : ", ", end - (lev[l].empty() ? end : lev[l][0].off),
+             lev[l].empty() ? end : lev[l][0].off);
+    js += buf;
+  }
+  js += "]}";
+  FILE *fp = fopen(path, "wb");
+  if (!fp) { mgic_set_error("cannot open %s for writing", path); return MGIC_ERR_ARG; }
+  unsigned long long hl = js.size();
+  fwrite("MGICCHK1", 1, 8, fp);
+  fwrite(&hl, sizeof hl, 1, fp);
+  fwrite(js.data(), 1, js.size(), fp);
+  const char zeros[8] = {0};
+  fwrite(zeros, 1, (8 - js.size() % 8) % 8, fp);
+  int rc = MGIC_OK;
+  std::vector<double> hbuf;
+  double *dbuf = nullptr;
+  size_t dcap = 0;
+  for (int l = 0; l < nlev && rc == MGIC_OK; l++)
+    for (const LB &lb : lev[l]) {
+      const int lo[3] = {lb.b[0], lb.b[1], lb.b[2]}, n[3] = {lb.b[3] - lb.b[0] + 1, lb.b[4] - lb.b[1] + 1, lb.b[5] - lb.b[2] + 1};
+      const size_t cnt = (size_t)NV * (n[0] + 2 * NG) * (n[1] + 2 * NG) * (n[2] + 2 * NG);
+      if (cnt > dcap) {
+        cudaFree(dbuf);
+        dbuf = nullptr;
+        if (cudaMalloc(&dbuf, cnt * sizeof(double)) != cudaSuccess) { mgic_set_error("cudaMalloc failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }
+        dcap = cnt;
+      }
+      hbuf.resize(cnt);
+      rc = mgk::output_box(H->nodes[lb.node].vars, lo, n, NG, constant_K, dbuf);
+      if (rc != MGIC_OK) break;
+      if (cudaMemcpyAsync(hbuf.data(), dbuf, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+          cudaStreamSynchronize(c->stream) != cudaSuccess) { mgic_set_error("copy failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }
+      if (fwrite(hbuf.data(), sizeof(double), cnt, fp) != cnt) { mgic_set_error("short write to %s", path); rc = MGIC_ERR_ARG; break; }
+    }
+  cudaFree(dbuf);
+  fclose(fp);
+  return rc;
+}
+
 extern "C" int mgic_hier_nl_solve(mgic_hier *H, double *dpsi_norms, int max_out, int *nl_iterations) {
   MGIC_REQUIRE(H, "NULL argument");
   MGIC_TRY(mgic_hier_set_initial_conditions(H));                            // :93

@@ -237,6 +237,7 @@ int set_rhs_acoef(mgic_vars *, double *rhs, double *acoef, double constant_K);
 int update_psi(mgic_vars *, const Geom &, const BCk &, const double *dpsi);
 int update_psi_patch(mgic_vars *, const BCk &withCfFaces, const double *dpsi);
 int fill(mgic_ctx *, double *y, long long n, double value);
+int output_box(mgic_vars *, const int lo[3], const int n[3], int ng, double constant_K, double *out);
 int condition_box(mgic_ctx *, const mgic_params &P, double dx, const int lo[3], const int n[3], int mode, double *out);
 int bottom_bicgstab(mgic_op *, mgic_field *e, const mgic_field *r, mgic_field *const work[8], double *part, int partCap,
                     int *d_out);

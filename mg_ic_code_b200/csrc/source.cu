@@ -206,6 +206,79 @@ __global__ void __launch_bounds__(128) k_condition(SrcP P, int mode, double *__r
   out[i + (long long)j * P.nx + (long long)k * P.nx * P.ny] = v;
 }
 
+// set_output_data (Source/SetLevelData.cpp:343-396) for ONE box of a level with the checkpoint's ghost layers
+// (Source/WriteOutput.H:180: three): the 32 GRChombo variables (GRChomboUserVariables.hpp), component slowest, over the box
+// grown by `ng`.  psi of a ghost cell is what the reference's multigrid_vars holds there after the nonlinear loop: a cell of
+// the level -> that cell (the 3-ghost exchange of set_update_psi0); the first layer beyond a face of the box -> the physical
+// ghost of the padded array or the accumulated QuadCFInterp ghost psiG; anything else was never written: the initial 1.
+// phi and A_ij are the analytic initial data everywhere (set_initial_conditions fills ghost cells, nothing modifies them).
+struct OutBox { int lo[3], n[3], ng; };   // the box (level index space), its size, ghost width
+__global__ void __launch_bounds__(128) k_output_box(SrcP P, OutBox B, const double *__restrict__ mv, double constant_K, double *__restrict__ out) {
+  const int gnx = B.n[0] + 2 * B.ng, gny = B.n[1] + 2 * B.ng, gnz = B.n[2] + 2 * B.ng;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y, c = blockIdx.z;
+  if (a >= gnx || b >= gny) return;
+  const int g[3] = {B.lo[0] - B.ng + a, B.lo[1] - B.ng + b, B.lo[2] - B.ng + c};      // the cell in the level's index space
+  const int lo[3] = {P.i0, P.j0, P.k0}, n[3] = {P.nx, P.ny, P.nz};
+  const int l[3] = {g[0] - lo[0], g[1] - lo[1], g[2] - lo[2]};                         // in the node's array
+  const long long so[3] = {1, (long long)P.nx, (long long)P.nx * P.ny}, st[3] = {1, P.sy, P.sz};
+  auto level_cell = [&](const int *q) {
+    if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= n[0] || q[1] >= n[1] || q[2] >= n[2]) return false;
+    return !P.mask || P.mask[q[0] + q[1] * so[1] + q[2] * so[2]] != 0;
+  };
+  const double *psi = mv + c_psi * P.sc;
+  double psi_here = 1.0;
+  if (level_cell(l)) psi_here = psi[(l[0] + 1) + (l[1] + 1) * st[1] + (l[2] + 1) * st[2]];
+  else {
+    // one step beyond exactly one face of the BOX?
+    int out_dirs = 0, f = -1;
+    for (int d = 0; d < 3; d++) {
+      const int r = g[d] - B.lo[d];
+      if (r == -1) { out_dirs++; f = 2 * d; }
+      else if (r == B.n[d]) { out_dirs++; f = 2 * d + 1; }
+      else if (r < -1 || r > B.n[d]) out_dirs += 2;
+    }
+    if (out_dirs == 1) {
+      const int d = f >> 1;
+      if (g[d] < 0 || g[d] >= P.ndom[d]) psi_here = psi[(l[0] + 1) + (l[1] + 1) * st[1] + (l[2] + 1) * st[2]];   // physical ghost (padded array)
+      else if (P.patch) {
+        int q[3] = {l[0], l[1], l[2]};
+        q[d] += (f & 1) ? -1 : 1;                                                      // the box's cell inside the face
+        psi_here = P.psiG[f][q[0] + q[1] * so[1] + q[2] * so[2]];
+      }
+    }
+  }
+  double loc[3];
+  cell_loc(P, g[0], g[1], g[2], loc);
+  const double r2 = loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2];
+  const double phi = P.phi_amplitude * exp(-r2 / P.phi_wavelength);
+  double l1[3] = {loc[0] - P.off1, loc[1], loc[2]};
+  double l2[3] = {loc[0] - P.off2, loc[1], loc[2]};
+  const double r1 = sqrt(l1[0] * l1[0] + l1[1] * l1[1] + l1[2] * l1[2]);
+  const double rr2 = sqrt(l2[0] * l2[0] + l2[1] * l2[1] + l2[2] * l2[2]);
+  const double n1[3] = {l1[0] / r1, l1[1] / r1, l1[2] / r1};
+  const double n2[3] = {l2[0] / rr2, l2[1] / rr2, l2[2] / rr2};
+  const double J1[3] = {0.0, 0.0, P.spin1}, J2[3] = {0.0, 0.0, P.spin2};
+  const double P1[3] = {0.0, P.mom1, 0.0}, P2[3] = {0.0, P.mom2, 0.0};
+  const double psi_0 = psi_here + (P.m1 / r1 + P.m2 / rr2);
+  const double p2 = psi_0 * psi_0;
+  const double chi = 1.0 / (p2 * p2);                    // pow(psi_0, -4)   :381-383
+  const double factor = chi * sqrt(chi);                 // pow(chi, 1.5)    :384
+  const long long np = (long long)gnx * gny * gnz, q = a + (long long)gnx * (b + (long long)gny * c);
+  enum { o_chi = 0, o_h11 = 1, o_h22 = 4, o_h33 = 6, o_K = 7, o_A11 = 8, o_A12 = 9, o_A13 = 10, o_A22 = 11, o_A23 = 12, o_A33 = 13, o_lapse = 18,
+         o_phi = 25, NV = 32 };
+  for (int v = 0; v < NV; v++) out[v * np + q] = 0.0;    // :357-359
+  out[o_h11 * np + q] = 1.0; out[o_h22 * np + q] = 1.0; out[o_h33 * np + q] = 1.0; out[o_lapse * np + q] = 1.0;   // :363-366
+  out[o_K * np + q] = constant_K;                        // :369
+  out[o_chi * np + q] = chi;
+  out[o_phi * np + q] = phi;                             // :387
+  out[o_A11 * np + q] = get_Aij(0, 0, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;   // :388-393
+  out[o_A12 * np + q] = get_Aij(0, 1, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;
+  out[o_A13 * np + q] = get_Aij(0, 2, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;
+  out[o_A22 * np + q] = get_Aij(1, 1, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;
+  out[o_A23 * np + q] = get_Aij(1, 2, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;
+  out[o_A33 * np + q] = get_Aij(2, 2, r1, rr2, n1, n2, J1, J2, P1, P2) * factor;
+}
+
 // set_update_psi0 -- Source/SetLevelData.cpp:243-263: psi += dpsi over the GHOSTED box.  dpsi's domain-face
 // ghost is what the solver's last homogeneous BC fill left there: a*near (+0).
 __global__ void __launch_bounds__(128) k_update_psi(SrcP P, Geom g, BCk bc, double *__restrict__ mv,
@@ -273,7 +346,7 @@ SrcP make_srcp(const mgic_vars *v) {
   s.nx = v->n[0]; s.ny = v->n[1]; s.nz = v->nzl; s.k0 = v->k0;
   s.sy = v->sy; s.sz = v->sz; s.sc = v->sc;
   s.i0 = v->lo[0]; s.j0 = v->lo[1]; s.patch = v->isPatch ? 1 : 0;
-  for (int d = 0; d < 3; d++) s.ndom[d] = v->ndom[d];
+  for (int d = 0; d < 3; d++) s.ndom[d] = v->isPatch ? v->ndom[d] : P.N[d];
   s.mask = v->mask;
   for (int f = 0; f < 6; f++) s.psiG[f] = v->psiG[f];
   return s;
@@ -314,6 +387,17 @@ int condition_box(mgic_ctx *c, const mgic_params &P, double dx, const int lo[3],
   dim3 blk(32, 4, 1), grd((s.nx + 31) / 32, (s.ny + 3) / 4, s.nz);
   k_condition<<<grd, blk, 0, c->stream>>>(s, mode, out);
   return post(c, "regrid_condition");
+}
+
+// the 32 GRChombo variables of one box [lo, lo + n) of the level `v` lives on, grown by ng ghost layers, into the device array out
+int output_box(mgic_vars *v, const int lo[3], const int n[3], int ng, double constant_K, double *out) {
+  SrcP s = make_srcp(v);
+  OutBox B;
+  for (int d = 0; d < 3; d++) { B.lo[d] = lo[d]; B.n[d] = n[d]; }
+  B.ng = ng;
+  dim3 blk(32, 4, 1), grd((n[0] + 2 * ng + 31) / 32, (n[1] + 2 * ng + 3) / 4, n[2] + 2 * ng);
+  k_output_box<<<grd, blk, 0, v->ctx->stream>>>(s, B, v->d, constant_K, out);
+  return post(v->ctx, "output_box");
 }
 
 int update_psi_patch(mgic_vars *v, const BCk &bc, const double *dpsi) {

@@ -598,6 +598,10 @@ class Hierarchy:
         check(self.L.mgic_hier_nl_solve(self.h, norms, 64, C.byref(its)))
         return np.array(norms[: its.value])
 
+    def write_checkpoint(self, path, constant_K=0.0):
+        """output_final_data (Source/WriteOutput.H:127-227): the GRChombo checkpoint as an MGICCHK1 container"""
+        check(self.L.mgic_hier_write_checkpoint(self.h, str(path).encode(), constant_K))
+
     def download(self, q, what="psi"):
         _, _, n, _ = self.node_info(q)
         out = np.zeros((n[2], n[1], n[0]))

@@ -7,4 +7,4 @@ class, factory) and to a mechanical translation of its .ChF kernels (chf2c.py; n
 Fortran compiler); everything that is Chombo's is restated and UNPINNED (not vendored);
 see DESIGN.md.
 """
-from .pyoracle import Oracle, OraclePatch, OrcParams, lib, build, default_params, FIELD, interp_homo, use_all_host_cores, condition_box  # noqa: F401
+from .pyoracle import Oracle, OraclePatch, OrcParams, lib, build, default_params, FIELD, interp_homo, use_all_host_cores, condition_box, output_box  # noqa: F401

@@ -1558,6 +1558,45 @@ void orc_condition_box(const orc_params *Pp, double dx, const int lo[3], const i
       }
 }
 
+// set_output_data (Source/SetLevelData.cpp:343-396): the 32 GRChombo variables (GRChomboUserVariables.hpp) over the index
+// box [lo, hi] (the checkpoint's boxes carry three ghost layers, WriteOutput.H:180) of a level with spacing dx, from the
+// given psi (multigrid_vars component 0 over the same box); phi and A_ij are the analytic initial data, which nothing
+// modifies after set_initial_conditions.  out = 32 x box, component slowest.
+void orc_output_box(const orc_params *Pp, double dx, const int lo[3], const int hi[3], const double *psi, double constant_K, double *out) {
+  const orc_params &P = *Pp;
+  enum { c_chi = 0, c_h11 = 1, c_h22 = 4, c_h33 = 6, c_K = 7, c_A11 = 8, c_A12 = 9, c_A13 = 10, c_A22 = 11, c_A23 = 12, c_A33 = 13,
+         c_lapse = 18, c_phi = 25, NV = 32 };
+  const Box tb(lo, hi);
+  const long nx = tb.size(0), ny = tb.size(1), np = tb.numPts();
+  Layout lay; lay.domain = tb; lay.boxes.push_back(tb);
+  LevelData mgvars, dpsi;
+  mgvars.define(&lay, 8, 0); dpsi.define(&lay, 1, 0);
+  init_conditions_level(P, dx, mgvars, dpsi);
+  const FAB &mv = mgvars.fab[0];
+  for (long q = 0; q < NV * np; q++) out[q] = 0.0;                           // :357-359
+  for (long q = 0; q < np; q++) {
+    out[c_h11 * np + q] = 1.0; out[c_h22 * np + q] = 1.0; out[c_h33 * np + q] = 1.0; out[c_lapse * np + q] = 1.0;   // :363-366
+    out[c_K * np + q] = constant_K;                                          // :369
+  }
+  for (int k = tb.lo[2]; k <= tb.hi[2]; k++)
+    for (int j = tb.lo[1]; j <= tb.hi[1]; j++)
+      for (int i = tb.lo[0]; i <= tb.hi[0]; i++) {
+        const long q = (i - tb.lo[0]) + nx * ((j - tb.lo[1]) + ny * (long)(k - tb.lo[2]));
+        Real loc[3]; cellLoc(P, dx, i, j, k, loc);                           // :376-378
+        Real psi_bh = set_binary_bh_psi(loc, P);
+        Real chi = std::pow(psi[q] + psi_bh, -4.0);                          // :381-383
+        out[c_chi * np + q] = chi;
+        Real factor = std::pow(chi, 1.5);                                    // :384
+        out[c_phi * np + q] = mv(i, j, k, 7);                                // :387
+        out[c_A11 * np + q] = mv(i, j, k, 1) * factor;                       // :388-393
+        out[c_A12 * np + q] = mv(i, j, k, 2) * factor;
+        out[c_A13 * np + q] = mv(i, j, k, 3) * factor;
+        out[c_A22 * np + q] = mv(i, j, k, 4) * factor;
+        out[c_A23 * np + q] = mv(i, j, k, 5) * factor;
+        out[c_A33 * np + q] = mv(i, j, k, 6) * factor;
+      }
+}
+
 // dpsi := the given valid cells, ghost layer 1 = the inhomogeneous ParseBC fill (what [Chombo] BiCGStab leaves there: the
 // initial residual's inhomogeneous fill + the homogeneous ghosts of the accumulated correction).  For callers whose solver
 // ran outside this library (the hierarchy twin of tests/amr_twin.py) before orc_update_psi0.

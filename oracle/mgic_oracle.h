@@ -151,6 +151,8 @@ double orc_update_psi0(orc_problem *);
 /* full NL loop (Main_PoissonSolver.cpp:131-216); dpsi_norms[NL_iter]; returns #NL iterations */
 /* set_regrid_condition (mode 0) / set_constant_K_integrand (mode 1) on fresh initial data over the index box [lo, hi] */
 void orc_condition_box(const orc_params *, double dx, const int lo[3], const int hi[3], int mode, double *out);
+/* set_output_data: the 32 GRChombo variables over [lo, hi] from the given psi over the same box */
+void orc_output_box(const orc_params *, double dx, const int lo[3], const int hi[3], const double *psi, double constant_K, double *out);
 void orc_set_dpsi_with_bc(orc_problem *, const double *valid_cells);   /* then orc_update_psi0 */
 int orc_nl_solve(orc_problem *, double *dpsi_norms, int max_out);
 

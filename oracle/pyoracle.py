@@ -106,6 +106,7 @@ def lib():
         L.orc_outer_solve.restype = C.c_int
         L.orc_update_psi0.argtypes = [C.c_void_p]
         L.orc_set_dpsi_with_bc.argtypes = [C.c_void_p, dp]
+        L.orc_output_box.argtypes = [C.POINTER(OrcParams), C.c_double, C.c_int * 3, C.c_int * 3, dp, C.c_double, dp]
         L.orc_condition_box.argtypes = [C.POINTER(OrcParams), C.c_double, C.c_int * 3, C.c_int * 3, C.c_int, dp]
         L.orc_update_psi0.restype = C.c_double
         L.orc_nl_solve.argtypes = [C.c_void_p, dp, C.c_int]
@@ -266,6 +267,17 @@ def condition_box(params, dx, lo, hi, mode=0):
     p = to_struct(params)
     out = np.zeros(tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0)))
     lib().orc_condition_box(C.byref(p), dx, (C.c_int * 3)(*lo), (C.c_int * 3)(*hi), mode, out)
+    return out
+
+
+def output_box(params, dx, lo, hi, psi, constant_K=0.0):
+    """set_output_data: the 32 GRChombo variables over the index box [lo, hi] from psi [k, j, i] over the same box"""
+    p = to_struct(params)
+    shape = tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    assert psi.shape == shape
+    out = np.zeros((32,) + shape)
+    lib().orc_output_box(C.byref(p), dx, (C.c_int * 3)(*lo), (C.c_int * 3)(*hi), psi, constant_K, out)
     return out
 
 

@@ -107,3 +107,57 @@ def test_reference_run_set_grids_then_solve(ctx):
     fine = H.download(1, "psi")
     assert np.all(fine[H.mask(1) == 0] == 0) and np.abs(fine[H.mask(1) == 1] - 1).max() < 0.05
     H.close(); g.close()
+
+
+def test_grchombo_checkpoint(ctx, tmp_path):
+    """output_final_data (Source/WriteOutput.H:127-227): header and per-level attributes as the reference sets them, the level's
+    boxes, and per box the 32 GRChombo variables with three ghost layers -- set_output_data, whose oracle restatement is
+    pinned bit for bit to the reference's (tests/test_reference_pins.py) -- from the solved hierarchy."""
+    from mg_ic_code_b200 import checkpoint
+    from oracle import output_box
+    P = default_params(**dict(CASE, max_NL_iterations=2))
+    mp = m.make_params(P)
+    g = m.Grids.generate(ctx, mp, 0.1, 0.5)
+    H = m.Hierarchy.from_grids(ctx, mp, g)
+    H.nl_solve()
+    path = tmp_path / "vcPoissonFinal.3d.mgic"
+    H.write_checkpoint(path, constant_K=-0.25)
+    hdr, levels = checkpoint.read(path)
+    root = hdr["root"]
+    assert root["ints"]["max_level"] == g.levels - 1 and root["ints"]["num_levels"] == g.levels and root["ints"]["num_components"] == 32
+    assert root["ints"]["iteration"] == 0 and root["reals"]["time"] == 0.0 and root["ints"]["regrid_interval_1"] == 1
+    assert root["strings"]["component_0"] == "chi" and root["strings"]["component_25"] == "phi" and root["strings"]["component_30"] == "Mom3"
+    dx0 = P["L"] / P["N"][0]
+    for l, lv in enumerate(hdr["levels"]):
+        assert lv["group"] == f"level_{l}" and lv["ints"]["ref_ratio"] == 2 and lv["ints"]["tag_buffer_size"] == 3
+        assert lv["reals"]["dx"] == dx0 / 2 ** l and lv["reals"]["dt"] == 0.25 * dx0 / 2 ** l and lv["ints"]["is_periodic_2"] == 1
+        assert lv["prob_domain"] == [0, 0, 0] + [(x << l) - 1 for x in P["N"]]
+        assert sorted(map(tuple, lv["boxes"])) == sorted(lo + hi for lo, hi in g.boxes(l))
+        assert len(lv["offsets"]) == len(lv["boxes"]) + 1
+    # data: per box, psi of every cell reconstructed from the solver's own arrays -> the oracle's set_output_data
+    psi_nodes = [(H.node_info(q), H.download(q, "psi"), H.mask(q)) for q in range(H.nodes)]
+    checked = 0
+    for l, (lv, data) in enumerate(zip(hdr["levels"], levels)):
+        for b, arr in zip(lv["boxes"], data):
+            lo, hi = b[:3], b[3:]
+            node = next(q for q, ((lvl, nlo, nn, _), _, _) in enumerate(psi_nodes)
+                        if lvl == l and all(nlo[d] <= lo[d] and hi[d] < nlo[d] + nn[d] for d in range(3)))
+            (_, nlo, nn, _), psi, mask = psi_nodes[node]
+            sl = tuple(slice(lo[d] - nlo[d], hi[d] - nlo[d] + 1) for d in (2, 1, 0))
+            assert mask[sl].all()
+            # valid cells: chi, A_ij, phi, K, the constants
+            want = output_box(P, dx0 / 2 ** l, lo, hi, psi[sl], -0.25)
+            got = arr[:, 3:-3, 3:-3, 3:-3]
+            for v in range(32):
+                s = np.abs(want[v]).max()
+                assert np.abs(got[v] - want[v]).max() <= 1e-12 * max(s, 1e-300), (l, b, v)
+            # ghost cells never written by the reference keep psi = 1: the outermost layer away from other boxes of the level
+            ghosted_lo, ghosted_hi = [x - 3 for x in lo], [x + 3 for x in hi]
+            ones = output_box(P, dx0 / 2 ** l, ghosted_lo, ghosted_hi, np.ones(arr.shape[1:]), -0.25)
+            corner = (slice(None), 0, 0, 0)
+            if not any(0 <= ghosted_lo[d] - nlo[d] < nn[d] for d in range(3)):     # the corner cell lies outside the node's array
+                assert abs(arr[corner][0] - ones[corner][0]) <= 1e-12 * ones[corner][0]
+            assert np.all(arr[1] == 1.0) and np.all(arr[18] == 1.0) and np.all(arr[7] == -0.25) and not arr[14].any()
+            checked += 1
+    assert checked == sum(len(g.boxes(l)) for l in range(g.levels))
+    H.close(); g.close()

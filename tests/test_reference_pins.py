@@ -136,6 +136,23 @@ def host_mirror_params(path, overrides, tmp_path_factory):
 
 @live
 @live
+@pytest.mark.parametrize("over,K", [(dict(N=(12, 8, 10), L=30.0), -0.3), (dict(N=(16, 16, 16), L=100.0, phi_amplitude=0.3, bh1_spin=-0.4), 0.0)])
+def test_output_data_equals_the_reference(over, K):
+    """set_output_data (Source/SetLevelData.cpp:343-396; what output_final_data writes into the GRChombo checkpoint with three
+    ghost layers, Source/WriteOutput.H:180): chi = psi_0^-4, A~_ij = A-_ij chi^(3/2), phi, K, h_ii = lapse = 1, the rest 0 --
+    the oracle's restatement against the reference's own function, all 32 components, bit for bit, ghost cells included"""
+    from oracle import default_params, output_box
+    P = default_params(**over)
+    N = P["N"]
+    d = 0.01 * np.random.default_rng(2).standard_normal((N[2] + 6, N[1] + 6, N[0] + 6))
+    ref = pyref.output_data(P, constant_K=K, dpsi_ghosted=d)
+    got = output_box(P, P["L"] / N[0], (-3, -3, -3), (N[0] + 2, N[1] + 2, N[2] + 2), 1.0 + d, K)
+    assert np.array_equal(ref, got)
+    assert np.all(got[1] == 1) and np.all(got[4] == 1) and np.all(got[6] == 1) and np.all(got[18] == 1) and np.all(got[7] == K)
+    assert not got[[2, 3, 5, 14, 15, 16, 17, 19, 20, 21, 22, 23, 24, 26, 27, 28, 29, 30, 31]].any()
+
+
+@live
 @pytest.mark.parametrize("over", [
     dict(N=(16, 16, 16), L=40.0), dict(N=(24, 16, 32), L=100.0),
     dict(N=(16, 16, 16), L=6.0, phi_amplitude=0.7),          # rho_grad of order one: |rho| is not its integer part

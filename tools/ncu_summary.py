@@ -55,9 +55,10 @@ def main():
             if k in col:
                 rec[k] = {"value": r[col[k]], "unit": units[col[k]]}
         launches.append(rec)
-    grids = [int(float(l["launch__grid_size"]["value"].replace(",", ""))) for l in launches]
-    gmax = max(grids) if grids else 0
-    finest = [i for i, g in enumerate(grids) if g >= 0.9 * gmax] if grids else []
+    # the finest-level launches are the ones that write a whole finest-level array (grids differ between the variants)
+    written = [to_gbyte(l["dram__bytes_write.sum"]["value"], l["dram__bytes_write.sum"]["unit"]) for l in launches]
+    wmax = max(written) if written else 0.0
+    finest = [i for i, w in enumerate(written) if w >= 0.9 * wmax] if written else []
     rd = [to_gbyte(launches[i]["dram__bytes_read.sum"]["value"], launches[i]["dram__bytes_read.sum"]["unit"]) for i in finest]
     wr = [to_gbyte(launches[i]["dram__bytes_write.sum"]["value"], launches[i]["dram__bytes_write.sum"]["unit"]) for i in finest]
     import bench
