@@ -317,6 +317,15 @@ int mgic_hier_node_info(const mgic_hier *, int node, int *level, int lo[3], int 
 int mgic_hier_get_mask(const mgic_hier *, int node, unsigned char *host);            /* 1 = cell of the level, bounding-box shaped */
 int mgic_hier_set_initial_conditions(mgic_hier *);                                    /* Main_PoissonSolver.cpp:90-96 */
 int mgic_hier_nl_iteration(mgic_hier *, double *dpsi_norm, int *solver_iterations, int *solver_status);   /* :131-212 body */
+/* the same body step by step, as the reference's driver calls it (host/dropin maps Main_PoissonSolver.cpp's calls onto these) */
+int mgic_hier_set_solver_params(mgic_hier *, int numMGsmooth, int numMGIterations, int preCondSolverDepth, double tolerance,
+                                int max_iterations);                         /* :108-123 */
+int mgic_hier_set_sources(mgic_hier *, double constant_K);                   /* set_a_coef / set_b_coef / set_rhs, :154-160 */
+int mgic_hier_define_solver(mgic_hier *);                                    /* defineOperatorFactory + mlOp.define, :163-170 */
+int mgic_hier_solve(mgic_hier *, int *iterations, int *exit_status);         /* solver.solve(dpsi, rhs), :173-184 */
+int mgic_hier_update_psi(mgic_hier *);                                       /* QuadCFInterp + set_update_psi0 per level, :189-205 */
+int mgic_hier_dpsi_norm(mgic_hier *, double *out);                           /* computeNorm(dpsi), :208 */
+int mgic_hier_release_solver(mgic_hier *);
 int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_iterations);                 /* :93 + the loop */
 /* replaces: output_final_data + set_output_data (Source/WriteOutput.H:127-227, Source/SetLevelData.cpp:343-396): the GRChombo
  * checkpoint (32 variables, three ghost layers per box, header / per-level attributes as the reference sets them).  No HDF5

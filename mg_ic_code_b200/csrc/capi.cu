@@ -1876,9 +1876,13 @@ struct mgic_hier {
   std::vector<HierNode> nodes;
   std::vector<int> perLevel;   // nodes per finer level
   int lastIterations = 0, lastStatus = 0;
+  mgic_mg *mg = nullptr;       // the solver of the current nonlinear iteration (mgic_hier_define_solver .. _release_solver)
+  mgic_amr *amr = nullptr;
 };
+extern "C" int mgic_hier_release_solver(mgic_hier *H);
 extern "C" int mgic_hier_destroy(mgic_hier *H) {
   if (!H) return MGIC_OK;
+  mgic_hier_release_solver(H);
   for (HierNode &n : H->nodes) {
     mgic_field_destroy(n.dpsi); mgic_field_destroy(n.rhs); mgic_field_destroy(n.a); mgic_field_destroy(n.b);
     mgic_vars_destroy(n.vars);
@@ -1977,52 +1981,92 @@ extern "C" int mgic_hier_set_initial_conditions(mgic_hier *H) {   // Main_Poisso
   for (HierNode &n : H->nodes) MGIC_TRY(mgic_set_initial_conditions(n.vars, n.dpsi));
   return MGIC_OK;
 }
+// ---- the body of the nonlinear loop (Main_PoissonSolver.cpp:131-212) step by step, as the reference's driver calls it
+extern "C" int mgic_hier_set_solver_params(mgic_hier *H, int numMGsmooth, int numMGIterations, int preCondSolverDepth, double tolerance,
+                                           int max_iterations) {
+  MGIC_REQUIRE(H, "NULL argument");
+  H->P.numMGsmooth = numMGsmooth; H->P.numMGIterations = numMGIterations; H->P.preCondSolverDepth = preCondSolverDepth;   // :108-117
+  H->P.tolerance = tolerance; H->P.max_iterations = max_iterations;                                                       // :119-123
+  return MGIC_OK;
+}
+// set_a_coef / set_b_coef / set_rhs on every level (:154-160)
+extern "C" int mgic_hier_set_sources(mgic_hier *H, double constant_K) {
+  MGIC_REQUIRE(H, "NULL argument");
+  for (HierNode &n : H->nodes) {
+    MGIC_TRY(mgic_set_rhs_and_a_coef(n.vars, n.rhs, n.a, constant_K));
+    MGIC_TRY(mgic_set_b_coef(n.vars, n.b));
+  }
+  return MGIC_OK;
+}
+extern "C" int mgic_hier_release_solver(mgic_hier *H) {
+  if (!H) return MGIC_OK;
+  mgic_amr_destroy(H->amr); H->amr = nullptr;
+  mgic_mg_destroy(H->mg); H->mg = nullptr;
+  return MGIC_OK;
+}
+// defineOperatorFactory + MultilevelLinearOp::define (:163-170): rebuilt every nonlinear iteration, like the reference
+extern "C" int mgic_hier_define_solver(mgic_hier *H) {
+  MGIC_REQUIRE(H, "NULL argument");
+  MGIC_TRY(mgic_hier_release_solver(H));
+  mgic_params P0 = H->P;
+  P0.max_level = 0;                                                         // the base level's MG hierarchy
+  MGIC_TRY(mgic_mg_create(H->ctx, &P0, H->nodes[0].a, H->nodes[0].b, &H->mg));
+  std::vector<mgic_op *> patches;
+  for (size_t q = 1; q < H->nodes.size(); q++) {
+    HierNode &n = H->nodes[q];
+    // bCoef == 1 (set_b_coef, SetLevelData.cpp:330-340): b*x == x exactly, so the patch operators drop the stream like the
+    // base level does (mgic_mg_create detects it there)
+    MGIC_TRY(mgic_op_set_coefs(n.op, n.a, nullptr, H->P.alpha, H->P.beta));
+    patches.push_back(n.op);
+  }
+  return mgic_amr_create_levels(H->mg, (int)H->perLevel.size(), H->perLevel.data(), patches.data(), &H->amr);
+}
+// solver.solve(dpsi, rhs) (:173-184); dpsi keeps its previous value as the initial guess (:93 is its only zeroing)
+extern "C" int mgic_hier_solve(mgic_hier *H, int *iterations, int *exit_status) {
+  MGIC_REQUIRE(H && H->amr, "mgic_hier_define_solver first");
+  const size_t nn = H->nodes.size();
+  std::vector<mgic_field *> dpsi(nn), rhs(nn);
+  for (size_t q = 0; q < nn; q++) { dpsi[q] = H->nodes[q].dpsi; rhs[q] = H->nodes[q].rhs; }
+  // the hierarchy's solver parameters may have changed since the MG hierarchy was built
+  H->mg->P.tolerance = H->P.tolerance; H->mg->P.max_iterations = H->P.max_iterations; H->mg->P.numMGIterations = H->P.numMGIterations;
+  int it = 0, st = 0;
+  MGIC_TRY(mgic_amr_outer_solve(H->amr, dpsi.data(), rhs.data(), &it, &st, nullptr, 0));
+  H->lastIterations = it; H->lastStatus = st;
+  if (iterations) *iterations = it;
+  if (exit_status) *exit_status = st;
+  return MGIC_OK;
+}
+// :189-205, coarsest level first (the finer level's coarse-fine ghosts come from the coarser level's dpsi)
+extern "C" int mgic_hier_update_psi(mgic_hier *H) {
+  MGIC_REQUIRE(H && H->amr, "mgic_hier_define_solver first");
+  MGIC_TRY(mgic_update_psi0(H->nodes[0].vars, H->mg->ops[0], H->nodes[0].dpsi, nullptr));
+  for (size_t q = 1; q < H->nodes.size(); q++) {
+    int level = 0, parent = -1;
+    MGIC_TRY(mgic_amr_node_info(H->amr, (int)q, &level, &parent));
+    const HierNode &pn = H->nodes[parent];
+    const int zero[3] = {0, 0, 0};
+    MGIC_TRY(mgic_update_psi0_patch(H->nodes[q].vars, H->nodes[q].op, H->nodes[q].dpsi, pn.dpsi, pn.op ? pn.op->plo : zero));
+  }
+  return MGIC_OK;
+}
+// computeNorm(dpsi, refRatio, coarsestDx, Interval(0, 0)) (:208): p = 2 over the cells no finer level covers
+extern "C" int mgic_hier_dpsi_norm(mgic_hier *H, double *out) {
+  MGIC_REQUIRE(H && H->amr && out, "mgic_hier_define_solver first");
+  std::vector<mgic_field *> dpsi(H->nodes.size());
+  for (size_t q = 0; q < H->nodes.size(); q++) dpsi[q] = H->nodes[q].dpsi;
+  return mgic_amr_norm(H->amr, dpsi.data(), 2, out);
+}
 // one pass of the nonlinear loop's body (Main_PoissonSolver.cpp:131-212, non-periodic: constant_K = 0)
 extern "C" int mgic_hier_nl_iteration(mgic_hier *H, double *dpsi_norm, int *solver_iterations, int *solver_status) {
   MGIC_REQUIRE(H, "NULL argument");
-  mgic_ctx *c = H->ctx;
-  const size_t nn = H->nodes.size();
-  for (HierNode &n : H->nodes) {                                            // :154-160
-    MGIC_TRY(mgic_set_rhs_and_a_coef(n.vars, n.rhs, n.a, 0.0));
-    MGIC_TRY(mgic_set_b_coef(n.vars, n.b));
-  }
-  mgic_params P0 = H->P;
-  P0.max_level = 0;                                                         // the base level's MG hierarchy
-  mgic_mg *mg = nullptr;
-  mgic_amr *A = nullptr;
-  int rc = mgic_mg_create(c, &P0, H->nodes[0].a, H->nodes[0].b, &mg);      // :163-170 (rebuilt every NL iteration)
-  std::vector<mgic_op *> patches;
-  std::vector<mgic_field *> dpsi(nn), rhs(nn);
-  for (size_t q = 0; q < nn && rc == MGIC_OK; q++) {
-    HierNode &n = H->nodes[q];
-    dpsi[q] = n.dpsi; rhs[q] = n.rhs;
-    if (q == 0) continue;
-    // bCoef == 1 (set_b_coef, SetLevelData.cpp:330-340): b*x == x exactly, so the patch operators drop the stream like the
-    // base level does (mgic_mg_create detects it there)
-    rc = mgic_op_set_coefs(n.op, n.a, nullptr, H->P.alpha, H->P.beta);
-    patches.push_back(n.op);
-  }
-  if (rc == MGIC_OK) rc = mgic_amr_create_levels(mg, (int)H->perLevel.size(), H->perLevel.data(), patches.data(), &A);
-  int it = 0, st = 0;
-  if (rc == MGIC_OK) rc = mgic_amr_outer_solve(A, dpsi.data(), rhs.data(), &it, &st, nullptr, 0);   // :184
-  H->lastIterations = it; H->lastStatus = st;
-  // :189-205, coarsest level first (the finer level's coarse-fine ghosts come from the coarser level's dpsi)
-  if (rc == MGIC_OK) rc = mgic_update_psi0(H->nodes[0].vars, mg->ops[0], H->nodes[0].dpsi, nullptr);
-  for (size_t q = 1; q < nn && rc == MGIC_OK; q++) {
-    int level = 0, parent = -1;
-    rc = mgic_amr_node_info(A, (int)q, &level, &parent);
-    if (rc != MGIC_OK) break;
-    const HierNode &pn = H->nodes[parent];
-    const int zero[3] = {0, 0, 0};
-    rc = mgic_update_psi0_patch(H->nodes[q].vars, H->nodes[q].op, H->nodes[q].dpsi, pn.dpsi, pn.op ? pn.op->plo : zero);
-  }
+  MGIC_TRY(mgic_hier_set_sources(H, 0.0));
+  int rc = mgic_hier_define_solver(H);
+  if (rc == MGIC_OK) rc = mgic_hier_solve(H, solver_iterations, solver_status);
+  if (rc == MGIC_OK) rc = mgic_hier_update_psi(H);
   double nrm = 0.0;
-  if (rc == MGIC_OK) rc = mgic_amr_norm(A, dpsi.data(), 2, &nrm);            // :208 computeNorm(dpsi, ..., p = 2)
-  mgic_amr_destroy(A);
-  mgic_mg_destroy(mg);
+  if (rc == MGIC_OK) rc = mgic_hier_dpsi_norm(H, &nrm);
+  mgic_hier_release_solver(H);
   if (dpsi_norm) *dpsi_norm = nrm;
-  if (solver_iterations) *solver_iterations = it;
-  if (solver_status) *solver_status = st;
   return rc;
 }
 // output_final_data (Source/WriteOutput.H:127-227): the GRChombo checkpoint -- header ints / reals / strings, per level a

@@ -1,5 +1,6 @@
 // VariableCoeffPoissonOperatorFactory.cpp -- see the header.  Replaces Source/VariableCoeffPoissonOperatorFactory.cpp.
 #include "VariableCoeffPoissonOperatorFactory.H"
+#include "HierarchySession.H"
 
 #include <cstring>
 
@@ -22,7 +23,14 @@ void VariableCoeffPoissonOperatorFactory::define(const ProblemDomain &a_coarseDo
                                                  const Real &a_alpha, Vector<RefCountedPtr<LevelData<FArrayBox>>> &a_aCoef,
                                                  const Real &a_beta, Vector<RefCountedPtr<LevelData<FArrayBox>>> &a_bCoef) {
   setDefaultValues();
-  if (a_grids.size() != 1) MayDay::Error("VariableCoeffPoissonOperatorFactory (B200): one AMR level in this round (max_level = 0)");
+  m_hierarchyMode = false;
+  if (a_grids.size() != 1) {
+    // a hierarchy: the operators of every level live in the session's mgic_hier (HierarchySession.H); this factory is the
+    // token MultilevelLinearOp::define receives
+    if (!hierarchySession().active()) MayDay::Error("VariableCoeffPoissonOperatorFactory (B200): an AMR hierarchy needs the grids set_grids produced");
+    m_hierarchyMode = true;
+    return;
+  }
   m_boxes = a_grids;
   m_refRatios = a_refRatios;
   m_bc = a_bc;
