@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "_obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC",
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-diag-suppress", "177", "-Xcompiler", "-fPIC",
              "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
     if verbose:
         flags.insert(0, "-Xptxas=-v")

@@ -118,6 +118,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
   else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
   else if (!strcmp(name, "p2p_halo")) c->p2pHalo = (int)value;
+  else if (!strcmp(name, "fold_halo")) c->foldHalo = (int)value;
   else { mgic_set_error("unknown option %s", name); return MGIC_ERR_ARG; }
   c->cfgEpoch++;   // captured V-cycle graphs bake the options in: they are re-captured after any change
   return MGIC_OK;
@@ -132,6 +133,7 @@ extern "C" long long mgic_ctx_get_option(mgic_ctx *c, const char *name) {
   if (!strcmp(name, "agglo_cells")) return c->aggloCells;
   if (!strcmp(name, "overlap_halo")) return c->overlapHalo;
   if (!strcmp(name, "p2p_halo")) return c->p2pHalo;
+  if (!strcmp(name, "fold_halo")) return c->foldHalo;
   if (!strcmp(name, "last_bottom_kernel")) return c->lastBottomKernel;
   return -1;
 }
@@ -691,7 +693,15 @@ static int restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, cons
   REQ_SHAPE(o, phi); REQ_SHAPE(o, rhs);
   MGIC_REQUIRE(o->n[0] % 2 == 0 && o->n[1] % 2 == 0 && o->nzl % 2 == 0 && o->k0 % 2 == 0, "level is not coarsenable by 2");
   MGIC_REQUIRE(resC->nx == o->n[0] / 2 && resC->ny == o->n[1] / 2 && resC->nz == o->nzl / 2, "coarse residual has the wrong shape");
-  MGIC_TRY(halo(o, phi, haloPlanes));  // :163
+  if (haloPlanes < 0) {   // the last sweep pushed phi's boundary planes itself: no exchange, wait for the neighbours' planes
+    if (o->ctx->nranks > 1 && !o->isGlobal) {
+      MGIC_REQUIRE(o->ctx->sweep_wait, "folded halo without the communication hooks");
+      ProfScope ph(o->ctx, false, PROF_HALO);
+      MGIC_TRY(o->ctx->sweep_wait(o->ctx, phi));
+    }
+  } else {
+    MGIC_TRY(halo(o, phi, haloPlanes));  // :163
+  }
   ProfScope ps(o->ctx, false, PROF_RESTRICT);
   return mgk::restrict_res(o->ctx, o->geom(), o->bck(true), resC->p, resC->sy, resC->sz, phi->p, rhs->p, o->a->p, bptr(o),
                            o->alpha, o->beta, o->dx);
@@ -1171,12 +1181,22 @@ static mgic_field slab_view(const mgic_field *whole, const mgic_op *slab) {
 }
 
 // relax(e, r, S) where e is known to be zero: the first fused sweep reads nothing for it (and the zero fill is skipped)
-static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int S) {
+static int relax_from_zero(mgic_op *op, mgic_field *e, const mgic_field *r, int S, bool *pushed = nullptr) {
+  if (pushed) *pushed = false;
   if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op)) {
     MGIC_TRY(mgic_op_reset_lambda(op));
-    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_FROM_ZERO, nullptr);
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_FROM_ZERO, nullptr, false, false, pushed);
   }
   MGIC_TRY(mgic_op_set_to_zero(op, e));
+  return mgic_op_relax(op, e, r, S);
+}
+// relax(e, r, S) that reports whether the last sweep pushed e's ghost planes itself (multi-rank, halo folded into the sweep)
+static int relax_report(mgic_op *op, mgic_field *e, const mgic_field *r, int S, bool *pushed) {
+  *pushed = false;
+  if (S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op)) {
+    MGIC_TRY(mgic_op_reset_lambda(op));
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PLAIN, nullptr, false, false, pushed);
+  }
   return mgic_op_relax(op, e, r, S);
 }
 // prolongIncrement(e, eCoarse) followed by relax(e, r, S): the increment is folded into the first fused sweep
@@ -1184,32 +1204,42 @@ static bool prolong_relax_is_fused(const mgic_op *op, int S) {
   return S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op) && op->ctx->fusePR;
 }
 static int prolong_relax(mgic_op *op, mgic_field *e, const mgic_field *ec, const mgic_field *r, int S, bool rhsHaloValid,
-                         bool eHaloValid) {
+                         bool eHaloValid, bool coarseHaloValid, bool *pushed) {
+  *pushed = false;
   if (prolong_relax_is_fused(op, S)) {
     MGIC_TRY(mgic_op_reset_lambda(op));
-    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec, rhsHaloValid, eHaloValid);
+    return mgk::gsrb_fused(op, e, r, S, mgk::FUSED_PROLONG, ec, rhsHaloValid, eHaloValid, pushed, coarseHaloValid);
   }
   MGIC_TRY(mgic_op_prolong_increment(op, e, ec));
-  return mgic_op_relax(op, e, r, S);
+  return relax_report(op, e, r, S, pushed);
 }
 
 // [Chombo] MultiGrid::cycle, m_cycle = 1; pre = post = bottom = numMGsmooth (Main:111-113)
-static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, bool eIsZero) {
+// *ePushed: on return the ghost planes of e are those the neighbours' last sweep of this depth stored (multi-rank, folded
+// halo) -- the finer depth's prolonging sweep then needs no exchange of them
+static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, bool eIsZero, bool *ePushed = nullptr) {
   mgic_op *op = mg->ops[depth];
   const int S = mg->P.numMGsmooth;
   const bool z = eIsZero && mg->ctx->fusePR;
+  bool dummy = false;
+  if (!ePushed) ePushed = &dummy;
+  *ePushed = false;
   if (depth == mg->nd - 1) {
     const long long cells = (long long)op->n[0] * op->n[1] * op->n[2];
     if (cells == 1) return z ? relax_from_zero(op, e, r, 1) : mgic_op_relax(op, e, r, 1);
     MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
     return mgic_mg_bottom_solve(mg, e, r, nullptr);
   }
-  MGIC_TRY(z ? relax_from_zero(op, e, r, S) : mgic_op_relax(op, e, r, S));
+  bool pushedPre = false;
+  MGIC_TRY(z ? relax_from_zero(op, e, r, S, &pushedPre) : relax_report(op, e, r, S, &pushedPre));
   // the pre-smoothing fused relax exchanged the ghost planes of r; r is not written again on this depth
   const bool preFused = S >= 1 && op->smoother == 1 && mgk::gsrb_fused_applicable(op);
-  // e is not touched between the restriction and the fused prolong + relax: one two-plane exchange serves both
+  // e is not touched between the restriction and the fused prolong + relax: one two-plane exchange serves both -- or none at
+  // all when the last pre-smoothing sweep pushed its boundary planes itself (then the restriction only has to wait for them)
   const bool eOnce = prolong_relax_is_fused(op, S) && MGIC_GZ >= 2 && op->nzl >= 2;
-  const int rp = eOnce ? 2 : 1;
+  const int rp = pushedPre ? -1 : (eOnce ? 2 : 1);
+  const bool eValidAfter = pushedPre || eOnce;
+  bool coarsePushed = false;
   if (depth + 1 == mg->dA) {
     // slab-distributed -> agglomerated: restrict into this rank's slab of the whole-level residual, all-gather in
     // place, run the rest of the cycle on the whole level, prolong from the slab view of the whole-level correction
@@ -1224,12 +1254,12 @@ static int mg_cycle(mgic_mg *mg, int depth, mgic_field *e, const mgic_field *r, 
     if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));
     MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
     mgic_field ev = slab_view(mg->e[depth + 1], lo);
-    return prolong_relax(op, e, &ev, r, S, preFused, eOnce);
+    return prolong_relax(op, e, &ev, r, S, preFused, eValidAfter, false, ePushed);
   }
   MGIC_TRY(restrict_residual(op, mg->r[depth + 1], e, r, rp));
   if (!mg->ctx->fusePR) MGIC_TRY(mgic_op_set_to_zero(mg->ops[depth + 1], mg->e[depth + 1]));   // setToZero(e[depth+1])
-  MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true));
-  return prolong_relax(op, e, mg->e[depth + 1], r, S, preFused, eOnce);
+  MGIC_TRY(mg_cycle(mg, depth + 1, mg->e[depth + 1], mg->r[depth + 1], true, &coarsePushed));
+  return prolong_relax(op, e, mg->e[depth + 1], r, S, preFused, eValidAfter, coarsePushed, ePushed);
 }
 
 // One V-cycle, replayed as a CUDA graph when possible: the cycle is a fixed launch sequence (the bottom solve is a
@@ -2178,7 +2208,10 @@ extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_nor
                              double *psi_out) {
   MGIC_REQUIRE(c && P, "NULL argument");
   MGIC_REQUIRE(c->nranks == 1, "mgic_nl_solve drives a single GPU; multi-rank callers compose the pieces per rank");
-  MGIC_REQUIRE(P->max_level == 0, "mgic_nl_solve: single AMR level (max_level = 0); hierarchies go through mgic_amr_nl_solve");
+  MGIC_REQUIRE(P->max_level == 0, "mgic_nl_solve: single AMR level (max_level = 0); hierarchies go through mgic_hier_nl_solve");
+  // Main_PoissonSolver.cpp:137-150 recomputes constant_K from set_constant_K_integrand + computeSum every iteration on periodic
+  // domains; that branch is out of scope -- refuse instead of silently solving the singular K = 0 problem
+  MGIC_REQUIRE(!P->is_periodic, "mgic_nl_solve: the periodic constant-K branch (Main_PoissonSolver.cpp:137-150) is not implemented");
   mgic_vars *vars = nullptr;
   mgic_op *lay = nullptr;
   mgic_field *dpsi = nullptr, *rhs = nullptr, *aC = nullptr, *bC = nullptr;

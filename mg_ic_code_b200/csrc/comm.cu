@@ -60,6 +60,8 @@ typedef unsigned long long u64;
 enum { CTL_FREE_LO = 0, CTL_FREE_HI = 1,   // "my ghost planes may be overwritten", posted by the lo / hi neighbour
        CTL_DATA_LO = 2, CTL_DATA_HI = 3,   // "your ghost planes are filled", posted by the lo / hi neighbour
        CTL_EPOCH = 4, CTL_COUNT = 5, CTL_WORDS = 8 };
+// words 8.. belong to the fused sweep's own protocol (MGIC_SW_* in mgic_internal.h): the sweep kernel stores its boundary
+// planes into the neighbours' ghost planes itself
 constexpr size_t IPC_GRAIN = (size_t)2 << 20;  // cudaMalloc gives allocations of >= 2 MiB a block of their own
 
 struct PeerArr {
@@ -173,6 +175,40 @@ __global__ void __launch_bounds__(512, 2) k_halo_push(PushArgs A) {
   } while (0)
 
 int halo_hook(mgic_ctx *c, mgic_field *f, int planes) { return mgic_comm_halo_exchange(c, f, planes); }
+
+// the fused sweep pushes its boundary planes itself (gsrb_fused.cu): where do they go, and which control words synchronise it
+int sweep_peers_hook(mgic_ctx *c, const mgic_field *like, const double *outBase, SweepPeers *sp) {
+  memset(sp, 0, sizeof(*sp));
+  Comm *cm = (Comm *)c->comm;
+  if (!cm || !cm->p2p || !c->p2pHalo) return MGIC_OK;
+  auto it = cm->reg.find(outBase);
+  if (it == cm->reg.end() || !it->second.ok) return MGIC_OK;
+  const PeerArr &pa = it->second;
+  const bool hasLo = like->k0 > 0, hasHi = like->k0 + like->nz < like->gnz;
+  // my plane k (k = 0, 1) is the lo neighbour's upper ghost plane k; my plane nz-2+k is the hi neighbour's lower ghost plane k:
+  // both as "address of MY plane 0" in the neighbour's array, so that the kernel adds the same offset it uses for its own store
+  sp->peerLo = hasLo ? pa.lo + (long long)(MGIC_GZ + pa.nzLo) * like->sz : nullptr;
+  sp->peerHi = hasHi ? pa.hi - (long long)(like->nz - MGIC_GZ) * like->sz : nullptr;
+  sp->ctl = cm->ctl; sp->ctlLo = hasLo ? cm->ctlLo : nullptr; sp->ctlHi = hasHi ? cm->ctlHi : nullptr;
+  sp->ok = 1;
+  return MGIC_OK;
+}
+
+// a reader that is not a fused sweep (residual + restrict ...) of an array whose ghost planes the neighbours' last sweep
+// filled: wait until both neighbours have published that sweep
+__global__ void k_sweep_wait(u64 *ctl, int hasLo, int hasHi) {
+  const u64 ep = *(volatile u64 *)&ctl[MGIC_SW_EPOCH];
+  if (hasLo) wait_ge(&ctl[MGIC_SW_DATA_LO], ep);
+  if (hasHi) wait_ge(&ctl[MGIC_SW_DATA_HI], ep);
+}
+int sweep_wait_hook(mgic_ctx *c, const mgic_field *like) {
+  Comm *cm = (Comm *)c->comm;
+  if (!cm || !cm->p2p) { mgic_set_error("sweep_wait without peer mapping"); return MGIC_ERR_STATE; }
+  k_sweep_wait<<<1, 1, 0, c->haloStream ? c->haloStream : c->stream>>>(cm->ctl, like->k0 > 0, like->k0 + like->nz < like->gnz);
+  MGIC_CUDA(cudaGetLastError());
+  c->launches++;
+  return MGIC_OK;
+}
 
 int allreduce_hook(mgic_ctx *c, double *dev, int n, int op) {
   NcclApi *A = api();
@@ -371,6 +407,8 @@ extern "C" int mgic_comm_init(mgic_ctx *c, const unsigned char id[MGIC_NCCL_ID_B
   MGIC_TRY(p2p_setup(c, cm, A));
   c->array_release = release_hook;
   c->array_prepare = prepare_hook;
+  c->sweep_peers = sweep_peers_hook;
+  c->sweep_wait = sweep_wait_hook;
   return MGIC_OK;
 }
 
@@ -399,6 +437,7 @@ extern "C" int mgic_comm_destroy(mgic_ctx *c) {
   cudaFree(cm->d_stage);
   if (A && cm->comm) A->CommDestroy(cm->comm);
   delete cm;
+  c->sweep_peers = nullptr; c->sweep_wait = nullptr;
   c->comm = nullptr; c->halo_exchange = nullptr; c->allreduce = nullptr; c->allgather = nullptr; c->array_release = nullptr; c->array_prepare = nullptr;
   return MGIC_OK;
 }

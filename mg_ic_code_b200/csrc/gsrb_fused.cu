@@ -81,14 +81,38 @@ struct FusedArgs {
   double alpha, beta, dxinv;
   int zchunk, redLo, redHi;
   int zbeg, zend;         // output planes of this launch: [zbeg, zend) (interior / boundary launches of the overlapped sweep)
+  // multi-rank, halo folded into the sweep (mgic_internal.h MGIC_SW_*): the finished planes 0, 1 / nz-2, nz-1 also go into
+  // the lo / hi neighbour's ghost planes (NVLink peer stores); ctl == null: single rank or exchange by k_halo_push
+  SweepPeers sw;
+  int ctasPerChunk, ctasTotal;
 };
+
+typedef unsigned long long u64;
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p >= v; a neighbour that died must not leave this GPU spinning forever: trap after 60 s
+__device__ __forceinline__ void sweep_wait_ge(const u64 *p, u64 v) {
+  if (ld_acquire_sys(p) >= v) return;
+  u64 t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(p) < v) {
+    __nanosleep(64);
+    u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (t - t0 > 60000000000ull) { printf("mgic: fused sweep timed out waiting for a neighbour rank's boundary planes\n"); __trap(); }
+  }
+}
 
 // All input streams arrive by TMA: per z plane one slot = the halo'd phi plane plus the (TY+2)-row planes of aCoef,
 // lambda, rhs (and bCoef) -- and, in MODE_PROLONG, the 34 x (TY+4)/2 tile of the coarse correction under the region --
 // completed through ONE mbarrier.  Threads never form a global load address.  (The coarse values used to be plain
 // global loads: three dependent-latency loads per lane and plane made that sweep 36 % slower than the plain one,
 // 1138 vs 835 us on 512^3, profiles/r1b_launches_bench_512.csv.)
-template <int TY, bool HAS_B, int MODE>
+template <int TY, bool HAS_B, int MODE, bool FOLD = false>
 struct Fused {
   static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, CPLANE = RW * NW, NT = 32 * NW, NCOEF = HAS_B ? 4 : 3;
   // coarse tile: TMA wants the innermost start coordinate on a 16-byte boundary, i.e. an even coarse x; (x0-2)/2 is odd, so
@@ -201,6 +225,10 @@ struct Fused {
         const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, sa, HAS_B ? sb : 1.0, sl, sr, A.alpha, A.beta, A.dxinv);
         const double2 o = E ? make_double2(pm1.x, nv) : make_double2(nv, pm1.y);
         *reinterpret_cast<double2 *>(outp) = o;
+        if (FOLD) {   // the planes the z-neighbours need go straight into their ghost planes (warp-uniform tests)
+          if (kb < MGIC_GZ && A.sw.peerLo) *reinterpret_cast<double2 *>(A.sw.peerLo + (outp - A.out)) = o;
+          if (kb >= A.g.nz - MGIC_GZ && A.sw.peerHi) *reinterpret_cast<double2 *>(A.sw.peerHi + (outp - A.out)) = o;
+        }
       }
     }
     outp += A.g.sz;
@@ -235,11 +263,25 @@ struct Fused {
     full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSLOT * SLOT * sizeof(double) + 2 * NW * 32 * sizeof(double));
     tid = threadIdx.x;
     x0 = blockIdx.x * TX; y0 = blockIdx.y * TY;
-    zs = A.zbeg + blockIdx.z * A.zchunk; ze = min(zs + A.zchunk, A.zend);
+    // folded halo: the two chunks whose planes the neighbours wait for are scheduled first (blocks start in z order): chunk
+    // order 0, last, 1, 2, ... -- their planes are across NVLink long before the grid drains
+    int chunk = blockIdx.z;
+    if (FOLD && gridDim.z > 2) chunk = (blockIdx.z == 0) ? 0 : (blockIdx.z == 1 ? (int)gridDim.z - 1 : (int)blockIdx.z - 1);
+    zs = A.zbeg + chunk * A.zchunk; ze = min(zs + A.zchunk, A.zend);
     pfirst = zs - 2; plast = ze + 1;
+    u64 epoch = 0;
     if (tid == 0) {
       for (int q = 0; q < NSLOT; q++) mbar_init(&full[q], 1);
       fence_mbar_init();
+      if (FOLD) {
+        // sweep number `epoch` of this rank.  The CTAs of the first / last z chunk read the lower / upper ghost planes and will
+        // overwrite the neighbour's: the neighbour must have published its previous sweep (which filled the ghost planes read
+        // here, and has finished reading the ones written here)
+        epoch = *(volatile u64 *)&A.sw.ctl[MGIC_SW_EPOCH] + 1;
+        if (zs == A.zbeg && A.sw.ctlLo) sweep_wait_ge(&A.sw.ctl[MGIC_SW_DATA_LO], epoch - 1);
+        if (ze == A.zend && A.sw.ctlHi) sweep_wait_ge(&A.sw.ctl[MGIC_SW_DATA_HI], epoch - 1);
+        asm volatile("fence.proxy.async;" ::: "memory");   // the TMA loads below read what the acquire made visible
+      }
     }
     __syncthreads();
     if (tid == 0)
@@ -267,15 +309,39 @@ struct Fused {
     const int e0 = ((y & 1) + zs - 1 + A.g.k0) & 1;  // warp-uniform: element of the pair that is red in plane zs-1
     if (e0) march<1>(p1, p2);
     else march<0>(p1, p2);
+    if (FOLD) {
+      if ((zs == A.zbeg && A.sw.ctlLo) || (ze == A.zend && A.sw.ctlHi)) {   // block-uniform: this CTA stored into a neighbour
+        __threadfence_system();   // this thread's peer stores are visible before the CTA reports in
+        __syncthreads();
+      }
+      if (tid == 0) {
+        // the last CTA of the first / last chunk publishes the sweep to the lo / hi neighbour (I am its hi / lo neighbour)
+        if (zs == A.zbeg && A.sw.ctlLo && atomicAdd(&A.sw.ctl[MGIC_SW_CNT_LO], 1ull) == (u64)A.ctasPerChunk - 1) {
+          A.sw.ctl[MGIC_SW_CNT_LO] = 0;
+          __threadfence_system();
+          st_release_sys(&A.sw.ctlLo[MGIC_SW_DATA_HI], epoch);
+        }
+        if (ze == A.zend && A.sw.ctlHi && atomicAdd(&A.sw.ctl[MGIC_SW_CNT_HI], 1ull) == (u64)A.ctasPerChunk - 1) {
+          A.sw.ctl[MGIC_SW_CNT_HI] = 0;
+          __threadfence_system();
+          st_release_sys(&A.sw.ctlHi[MGIC_SW_DATA_LO], epoch);
+        }
+        if (atomicAdd(&A.sw.ctl[MGIC_SW_CNT_ALL], 1ull) == (u64)A.ctasTotal - 1) {   // the whole grid has read the epoch: advance it
+          A.sw.ctl[MGIC_SW_CNT_ALL] = 0;
+          A.sw.ctl[MGIC_SW_EPOCH] = epoch;
+          __threadfence();
+        }
+      }
+    }
   }
 };
 
-template <int TY, bool HAS_B, int MODE, int MINB>
+template <int TY, bool HAS_B, int MODE, int MINB, bool FOLD>
 __global__ void __launch_bounds__(32 * (TY + 2), MINB)
 k_gsrb_fused(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_l,
              const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
              const FusedArgs A) {
-  using F = Fused<TY, HAS_B, MODE>;
+  using F = Fused<TY, HAS_B, MODE, FOLD>;
   static_assert(F::PLANE_BYTES % 128 == 0 && F::CPLANE_BYTES % 128 == 0 && F::CTILE_BYTES % 128 == 0,
                 "TMA destinations must stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -334,10 +400,13 @@ Plan plan_chunks(int tiles, int nz, int resident) {
 }
 
 template <int TY, bool HAS_B, int MODE, int MINB>
-int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
+int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend,
+               const SweepPeers &sw) {
   using F = Fused<TY, HAS_B, MODE>;
   mgic_ctx *c = o->ctx;
-  auto kern = k_gsrb_fused<TY, HAS_B, MODE, MINB>;
+  // two builds of the kernel: the plain one (one rank, or halos exchanged by k_halo_push) and the one that stores its
+  // boundary planes into the neighbours' ghost planes itself -- the plain one carries none of the other's instructions
+  auto kern = sw.ctl ? k_gsrb_fused<TY, HAS_B, MODE, MINB, true> : k_gsrb_fused<TY, HAS_B, MODE, MINB, false>;
   int &resident = *mgic_dev_cache(c->device, (const void *)kern, 0, 0);   // per device: the opt-in and the occupancy
   if (!resident) {
     MGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM));
@@ -370,6 +439,8 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   A.redLo = (A.bc.type[4] == MGIC_FACE_INTERIOR) ? -1 : 0;
   A.redHi = (A.bc.type[5] == MGIC_FACE_INTERIOR) ? A.g.nz : A.g.nz - 1;
   dim3 grd(tilesX, tilesY, pl.nch);
+  A.sw = sw;
+  A.ctasPerChunk = tilesX * tilesY; A.ctasTotal = tilesX * tilesY * pl.nch;
   kern<<<grd, F::NT, F::SMEM, c->stream>>>(tp, ta, tl, tr, tb, tc, A);
   c->launches++;
   cudaError_t e = cudaGetLastError();
@@ -378,29 +449,31 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
 }
 
 template <bool HAS_B, int MODE>
-int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
+int launch_mode(mgic_op *o, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend,
+                const SweepPeers &sw) {
   switch (o->ctx->fusedCfg) {
-    case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
-    case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend);
+    case 0: return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend, sw);
+    case 1: return launch_cfg<16, HAS_B, MODE, 1>(o, in, outp, r, coarse, zbeg, zend, sw);
     default:
       // two CTAs per SM need a slot ring of <= ~110 KB: 10 rows with three coefficient streams, 8 rows with four or with
       // the coarse tile of the prolonging sweep
       // (6 rows when both apply)
-      if (HAS_B && MODE == MODE_PROLONG) return launch_cfg<6, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
-      if (HAS_B || MODE == MODE_PROLONG) return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
-      return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend);
+      if (HAS_B && MODE == MODE_PROLONG) return launch_cfg<6, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend, sw);
+      if (HAS_B || MODE == MODE_PROLONG) return launch_cfg<8, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend, sw);
+      return launch_cfg<10, HAS_B, MODE, 2>(o, in, outp, r, coarse, zbeg, zend, sw);
   }
 }
 
-int launch(mgic_op *o, int mode, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend) {
+int launch(mgic_op *o, int mode, const double *in, double *outp, const mgic_field *r, const mgic_field *coarse, int zbeg, int zend,
+           const SweepPeers &sw = SweepPeers()) {
   if (o->b) {
-    if (mode == MODE_ZERO) return launch_mode<true, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend);
-    if (mode == MODE_PROLONG) return launch_mode<true, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend);
-    return launch_mode<true, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend);
+    if (mode == MODE_ZERO) return launch_mode<true, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend, sw);
+    if (mode == MODE_PROLONG) return launch_mode<true, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend, sw);
+    return launch_mode<true, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend, sw);
   }
-  if (mode == MODE_ZERO) return launch_mode<false, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend);
-  if (mode == MODE_PROLONG) return launch_mode<false, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend);
-  return launch_mode<false, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend);
+  if (mode == MODE_ZERO) return launch_mode<false, MODE_ZERO>(o, in, outp, r, coarse, zbeg, zend, sw);
+  if (mode == MODE_PROLONG) return launch_mode<false, MODE_PROLONG>(o, in, outp, r, coarse, zbeg, zend, sw);
+  return launch_mode<false, MODE_PLAIN>(o, in, outp, r, coarse, zbeg, zend, sw);
 }
 
 }  // namespace
@@ -426,7 +499,8 @@ bool gsrb_fused_applicable(const mgic_op *o) {
 // first = FUSED_FROM_ZERO: e is known to be zero (setToZero + relax of [Chombo] MultiGrid::cycle); first =
 // FUSED_PROLONG: e += prolong(coarse) is applied on the fly by the first sweep (prolongIncrement + relax).
 int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, int first, const mgic_field *coarse,
-               bool rhsHaloValid, bool eHaloValid) {
+               bool rhsHaloValid, bool eHaloValid, bool *pushed, bool coarseHaloValid) {
+  if (pushed) *pushed = false;
   constexpr int OVL = 8;
   mgic_ctx *c = o->ctx;
   if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
@@ -438,11 +512,32 @@ int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, i
     first = FUSED_PLAIN; coarse = nullptr; eHaloValid = false;
   }
   const bool overlap = multi && c->overlapHalo && !c->profiling && c->commStream && g.nz >= 4 * OVL;
+  // halo folded into the sweep: every sweep stores its boundary planes into the neighbours' ghost planes of the array it writes
+  // and synchronises through the MGIC_SW_* words, so only the FIRST sweep of a call may still need an exchange of e (when the
+  // caller cannot vouch for its ghost planes).  Needs both ping-pong arrays mapped by the neighbours (collective, not while
+  // capturing: vcycle_run prepares them before it captures).
+  bool fold = multi && c->foldHalo && !overlap && c->sweep_peers && c->p2pHalo && g.nz >= 2 * MGIC_GZ;
+  if (fold && c->array_prepare) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    MGIC_CUDA(cudaStreamIsCapturing(c->stream, &cs));
+    if (cs == cudaStreamCaptureStatusNone) {
+      MGIC_TRY(c->array_prepare(c, e));
+      MGIC_TRY(c->array_prepare(c, o->scratch));
+    }
+  }
   for (int it = 0; it < iterations; it++) {
     const int mode = (it == 0) ? first : FUSED_PLAIN;
-    const bool needE = multi && mode != FUSED_FROM_ZERO && !(it == 0 && eHaloValid);  // eHaloValid: two ghost planes of e are current
+    SweepPeers sw = SweepPeers();
+    if (fold) {
+      SweepPeers in;   // the input array must be mapped too: the neighbours write its ghost planes in their next sweep
+      MGIC_TRY(c->sweep_peers(c, e, o->scratch->base, &sw));
+      MGIC_TRY(c->sweep_peers(c, e, e->base, &in));
+      if (!sw.ok || !in.ok) { fold = false; sw = SweepPeers(); }
+    }
+    // the previous sweep of this call pushed the ghost planes of e (folded mode)
+    const bool needE = multi && mode != FUSED_FROM_ZERO && !(it == 0 && eHaloValid) && !(fold && it > 0);
     const bool needR = multi && it == 0 && !rhsHaloValid;
-    const bool needC = multi && mode == FUSED_PROLONG;
+    const bool needC = multi && mode == FUSED_PROLONG && !(fold && coarseHaloValid);   // (pushed by the coarser level's last sweep)
     if (overlap && (needE || needR || needC)) {
       // fork: the exchange depends on everything issued so far (the previous sweep wrote the planes being sent)
       MGIC_CUDA(cudaEventRecord(c->evFork, c->stream));
@@ -464,10 +559,11 @@ int gsrb_fused(mgic_op *o, mgic_field *e, const mgic_field *r, int iterations, i
       if (needC) MGIC_TRY(mgic_halo_shape(c, const_cast<mgic_field *>(coarse), 1));
       if (needE) MGIC_TRY(mgic_halo(o, e, 2));
       ProfScope ps(c, o->profTag);
-      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, 0, g.nz));
+      MGIC_TRY(launch(o, mode, e->p, o->scratch->p, r, coarse, 0, g.nz, sw));
     }
     std::swap(e->base, o->scratch->base);  // ping-pong: the field handle now owns the freshly written array
     std::swap(e->p, o->scratch->p);
+    if (pushed) *pushed = fold;   // the ghost planes of e are on their way from the neighbours' same sweep (sweep_wait before other readers)
   }
   return MGIC_OK;
 }

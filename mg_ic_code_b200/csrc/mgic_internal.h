@@ -72,6 +72,21 @@ struct Geom {
   int gnz;            // global nz
 };
 
+// ---- the fused sweep's own halo protocol (multi-rank, NVLink peer memory) ------------------------------------------
+// Sweep number E of a context (all ranks launch the same sequence): the CTAs of the first / last z chunk store the planes
+// they finish into the lo / hi neighbour's ghost planes of ITS output array, and the last of them to finish publishes E to
+// that neighbour; before they touch a ghost plane they wait until the neighbour has published E-1 (its previous sweep has
+// filled the ghost planes this sweep reads, and has stopped reading the ones this sweep overwrites -- the arrays ping-pong).
+// Control words of a rank's IPC-exported block (comm.cu), written by the neighbours / by its own kernels:
+enum { MGIC_SW_DATA_LO = 8, MGIC_SW_DATA_HI = 9,   // the lo / hi neighbour has published sweep ...
+       MGIC_SW_EPOCH = 10,                         // sweeps this rank has finished
+       MGIC_SW_CNT_LO = 11, MGIC_SW_CNT_HI = 12, MGIC_SW_CNT_ALL = 13 };   // CTAs done: first chunk, last chunk, grid
+struct SweepPeers {
+  double *peerLo, *peerHi;                       // the neighbours' arrays, offset so that "my plane 0" has my own offset arithmetic
+  unsigned long long *ctl, *ctlLo, *ctlHi;
+  int ok;
+};
+
 // ---- host-side objects ------------------------------------------------------
 struct mgic_ctx {
   int device = 0;
@@ -91,6 +106,11 @@ struct mgic_ctx {
   int (*allgather)(mgic_ctx *, const double *send, double *recv, size_t count) = nullptr;  // equal counts per rank
   int (*array_prepare)(mgic_ctx *, mgic_field *) = nullptr;  // collective: make the field's array exchangeable by peer stores (never inside a capture)
   int (*array_release)(mgic_ctx *, void *base) = nullptr;  // field array about to be freed; 1 = the hook frees it later
+  int (*sweep_peers)(mgic_ctx *, const mgic_field *like, const double *outBase, SweepPeers *) = nullptr;  // fused sweep: where its boundary planes go
+  int (*sweep_wait)(mgic_ctx *, const mgic_field *like) = nullptr;   // wait (on the stream) for the neighbours' last sweep
+  int foldHalo = 0;      // 1: the fused sweep stores its boundary planes into the neighbours' ghost planes itself (measured at 2 GPUs,
+                         // 512^3 per GPU: 6.38 vs 6.27 ms per V-cycle -- the exchanges cost waiting for the neighbour, not launches
+                         // or data, and the wait moves into the sweep; off by default)
   void *comm = nullptr;
   int p2pHalo = 1;       // halo planes by NVLink peer stores (comm.cu k_halo_push) when the ranks could map each other
   // halo exchange overlapped with interior work: a second stream + fork/join events (capturable into a CUDA graph)
@@ -251,8 +271,11 @@ int mgic_halo(mgic_op *, mgic_field *, int planes);
 bool gsrb_fused_applicable(const mgic_op *);
 // relax(e, r, iterations) with the fused red+black sweep (gsrb_fused.cu); ping-pongs e with op->scratch
 enum { FUSED_PLAIN = 0, FUSED_FROM_ZERO = 1, FUSED_PROLONG = 2 };
+// *pushed (optional) = the last sweep stored e's boundary planes into the neighbours' ghost planes itself (halo folded into
+// the sweep): a following non-sweep reader of e's ghost planes needs ctx->sweep_wait instead of an exchange
 int gsrb_fused(mgic_op *, mgic_field *e, const mgic_field *r, int iterations, int first = FUSED_PLAIN,
-               const mgic_field *coarse = nullptr, bool rhsHaloValid = false, bool eHaloValid = false);
+               const mgic_field *coarse = nullptr, bool rhsHaloValid = false, bool eHaloValid = false, bool *pushed = nullptr,
+               bool coarseHaloValid = false);
 int mgic_halo_shape(mgic_ctx *, mgic_field *, int planes);  // halo exchange of a field of any level
 // a ghosted FArrayBox staged in HBM (chf_abi.cu)
 struct FabView { double *p; int lo[3]; long long s1, s2, sc; };

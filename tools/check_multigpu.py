@@ -86,6 +86,19 @@ for _ in range(3):
 results["vcycle_e_nccl"] = gather(D3["e"])
 ctx.set_option("p2p_halo", 1)
 stats_all = comm.halo_stats(ctx)
+# and with the halo folded into the sweep: every sweep stores its boundary planes into the neighbours' ghost planes itself
+# (fold_halo = 1; off by default) instead of a k_halo_push exchange before every sweep
+ctx.set_option("fold_halo", 1)
+D4 = build(ctx, k0, nzl)
+D4["op"].setToZero(D4["e"])
+for _ in range(3):
+    D4["f"].vcycle(D4["e"], D4["rhs"])
+results["vcycle_e_unfolded"] = gather(D4["e"])
+D4["e"].upload(e0)
+D4["op"].relax(D4["e"], D4["rhs"], 3)
+results["relax_unfolded"] = gather(D4["e"])
+stats_unfolded = comm.halo_stats(ctx)
+ctx.set_option("fold_halo", 0)
 ok = True
 if rank == 0:
     c1 = m.Context(local)
@@ -123,6 +136,10 @@ if rank == 0:
     ok &= same
     same = np.array_equal(results["vcycle_e_nccl"], results["vcycle_e"])
     print("vcycle with ncclSend/ncclRecv halos: bitwise", "OK" if same else "MISMATCH")
+    ok &= same
+    same = np.array_equal(results["vcycle_e_unfolded"], results["vcycle_e"]) and np.array_equal(results["relax_unfolded"], results["relax_fused"])
+    print("vcycle / sweeps with the halo stored by the sweep itself vs exchanged before every sweep: bitwise", "OK" if same else "MISMATCH",
+          "(exchange kernels left in the folded pass:", stats_unfolded[0] - stats_all[0], ")")
     ok &= same
     print("halo exchanges (peer stores, nccl, peer mapping available): before the nccl pass", stats_p2p, "after", stats_all)
     ok &= stats_all[1] > 0 and (not stats_all[2] or (stats_p2p[0] > 0 and stats_p2p[1] == 0))
