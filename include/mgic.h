@@ -325,7 +325,7 @@ int mgic_hier_define_solver(mgic_hier *);                                    /* 
 int mgic_hier_solve(mgic_hier *, int *iterations, int *exit_status);         /* solver.solve(dpsi, rhs), :173-184 */
 int mgic_hier_update_psi(mgic_hier *);                                       /* QuadCFInterp + set_update_psi0 per level, :189-205 */
 int mgic_hier_dpsi_norm(mgic_hier *, double *out);                           /* computeNorm(dpsi), :208 */
-int mgic_hier_release_solver(mgic_hier *);
+int mgic_hier_release_solver(mgic_hier *);                                   /* no-op: the solver objects are reused, coefficients refreshed in place */
 int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_iterations);                 /* :93 + the loop */
 /* replaces: output_final_data + set_output_data (Source/WriteOutput.H:127-227, Source/SetLevelData.cpp:343-396): the GRChombo
  * checkpoint (32 variables, three ghost layers per box, header / per-level attributes as the reference sets them).  No HDF5

@@ -100,6 +100,9 @@ def lib():
         "mgic_hier_get_mask": [vp, C.c_int, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")],
         "mgic_hier_set_initial_conditions": [vp], "mgic_hier_nl_iteration": [vp, dp, ip, ip],
         "mgic_hier_nl_solve": [vp, dp, C.c_int, ip], "mgic_hier_write_checkpoint": [vp, C.c_char_p, C.c_double], "mgic_hier_download": [vp, C.c_int, C.c_int, nd],
+        "mgic_hier_set_solver_params": [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int], "mgic_hier_set_sources": [vp, C.c_double],
+        "mgic_hier_define_solver": [vp], "mgic_hier_solve": [vp, ip, ip], "mgic_hier_update_psi": [vp], "mgic_hier_dpsi_norm": [vp, dp],
+        "mgic_hier_release_solver": [vp],
         "mgic_vars_create_patch": [vp, C.POINTER(MgicParams), vp, pvp],
         "mgic_grids_generate": [vp, C.POINTER(MgicParams), C.c_double, C.c_double, pvp],
         "mgic_grids_regrid": [C.POINTER(MgicParams), C.c_double, C.c_int, ip, ip, ip, ip, pvp],

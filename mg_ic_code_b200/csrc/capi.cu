@@ -166,8 +166,8 @@ extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *t
 }
 
 // read back `n` device scalars starting at slot (one sync); multi-rank: all-reduced on the device first (op 0 sum, 1 max)
-static int fetch_scalars(mgic_ctx *c, int slot, int n, int op, double *out) {
-  if (c->nranks > 1) {
+static int fetch_scalars(mgic_ctx *c, int slot, int n, int op, double *out, bool collective = true) {
+  if (c->nranks > 1 && collective) {
     MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm_init)");
     MGIC_TRY(c->allreduce(c, c->d_scal + slot, n, op));
   }
@@ -265,7 +265,6 @@ extern "C" int mgic_op_create(mgic_ctx *c, const int n[3], int k0, int nz_local,
 extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const int lo[3], const int hi[3], double dx, double dx_coarse,
                                     double alpha, double beta, const int bc_lo[3], const int bc_hi[3], double bc_value, mgic_op **out) {
   MGIC_REQUIRE(c && n_domain && lo && hi && out && bc_lo && bc_hi, "NULL argument");
-  MGIC_REQUIRE(c->nranks == 1, "AMR patches on a multi-rank context are not supported");
   int n[3];
   for (int d = 0; d < 3; d++) {
     MGIC_REQUIRE(lo[d] >= 0 && hi[d] < n_domain[d] && hi[d] - lo[d] + 1 >= 2, "patch box outside the domain or thinner than two cells");
@@ -276,6 +275,9 @@ extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const in
   MGIC_TRY(mgic_op_create(c, n, 0, n[2], dx, alpha, beta, bc_lo, bc_hi, bc_value, out));
   mgic_op *o = *out;
   o->isPatch = true;
+  // multi-rank context: the base level is cut into z-slabs, the (small) refined levels are REPLICATED -- every rank holds and
+  // updates the whole patch, like the agglomerated coarse MG levels: no halo planes, no all-reduce of its reductions
+  o->isGlobal = c->nranks > 1;
   o->dxCrse = dx_coarse;
   o->cshift = (lo[0] + lo[1] + lo[2]) & 1;
   o->smoother = 0;  // the fused sweep stages planes by TMA and has no coarse-fine ghost variant: per-colour kernel
@@ -729,7 +731,7 @@ extern "C" int mgic_op_precond(mgic_op *o, mgic_field *phi, const mgic_field *rh
 // BLAS-1 [Chombo AMRPoissonOp]
 static int local_reduce(mgic_op *o, const mgic_field *x, const mgic_field *y, int kind, double *out) {
   MGIC_TRY(mgk::reduce(o->ctx, o->geom(), x->p, y ? y->p : nullptr, kind, 0));
-  return fetch_scalars(o->ctx, 0, 1, kind == 0 ? 1 : 0, out);
+  return fetch_scalars(o->ctx, 0, 1, kind == 0 ? 1 : 0, out, !o->isGlobal);   // replicated level: every rank already has the whole sum
 }
 extern "C" int mgic_op_norm(mgic_op *o, const mgic_field *x, int ord, double *out) {
   MGIC_REQUIRE(o && x && out, "NULL argument");
@@ -1376,6 +1378,11 @@ struct AmrNode {
   int lo[3] = {0, 0, 0};           // origin of the node's array in its level's index space
   int off[3] = {0, 0, 0};          // coarsened patch origin inside the parent's array
   mgic_field *corr = nullptr, *res = nullptr, *tmp = nullptr;   // owned
+  // multi-rank: the parent is the z-slab-distributed base level, this patch is replicated.  What the patch reads of the
+  // parent (QuadCFInterp's stencils, the prolongation) is gathered into a replicated staging box = the coarsened patch grown
+  // by two cells, clipped to the coarse domain (owned); stageLo = its origin in the parent level's index space
+  mgic_field *stage = nullptr;
+  int stageLo[3] = {0, 0, 0};
 };
 struct mgic_amr {
   mgic_ctx *ctx = nullptr;
@@ -1394,7 +1401,6 @@ static int amr_fail(mgic_amr *A, const char *fmt, int a, int b) {
 
 extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npatches, mgic_op *const *patches, mgic_amr **out) {
   MGIC_REQUIRE(base && out && nfiner >= 0 && (nfiner == 0 || (patches && npatches)), "bad argument");
-  MGIC_REQUIRE(base->ctx->nranks == 1, "AMR levels on a multi-rank context are not supported");
   mgic_amr *A = new mgic_amr;
   A->ctx = base->ctx; A->base = base;
   AmrNode root;
@@ -1489,6 +1495,14 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
       mgic_amr_destroy(A);
       return MGIC_ERR_CUDA;
     }
+    if (A->ctx->nranks > 1 && nd.parent == 0) {   // staging box for what this patch reads of the distributed base level
+      int ns[3];
+      for (int d = 0; d < 3; d++) {
+        const int clo = std::max(0, (nd.op->plo[d] >> 1) - 2), chi = std::min(nd.op->ndom[d] / 2 - 1, ((nd.op->plo[d] + nd.op->n[d] - 1) >> 1) + 2);
+        nd.stageLo[d] = clo; ns[d] = chi - clo + 1;
+      }
+      if (field_alloc(A->ctx, ns[0], ns[1], ns[2], 0, ns[2], &nd.stage) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
+    }
   }
   *out = A;
   return MGIC_OK;
@@ -1501,7 +1515,7 @@ extern "C" int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patche
 }
 extern "C" int mgic_amr_destroy(mgic_amr *A) {
   if (!A) return MGIC_OK;
-  for (AmrNode &nd : A->nodes) { mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); }
+  for (AmrNode &nd : A->nodes) { mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); mgic_field_destroy(nd.stage); }
   for (auto *f : A->work) mgic_field_destroy(f);
   delete A;
   return MGIC_OK;
@@ -1516,13 +1530,69 @@ extern "C" int mgic_amr_node_info(const mgic_amr *A, int node, int *level, int *
 }
 
 // the cells of the parent's array `below` that lie under node q's patch, and that sub-box as a geometry
-static double *under_patch(const AmrNode &q, mgic_field *below) {
-  return below->p + q.off[0] + (long long)q.off[1] * below->sy + (long long)q.off[2] * below->sz;
+// ---- what a patch READS of its parent level (QuadCFInterp's stencils, the prolongation): the parent's array, or -- multi-rank,
+// parent = the z-slab-distributed base level -- the patch's replicated staging box, gathered here: every rank copies the part
+// of the box that lies in its slab into the zeroed box, one all-reduce (sum; exactly one rank contributes to each cell, so
+// the values arrive bit for bit) replicates it.  zero = the parent field is known to be identically zero.
+struct CoarseSrc { const mgic_field *f; int lo[3]; };
+static int amr_coarse_source(mgic_amr *A, const AmrNode &n, mgic_field *parentField, CoarseSrc *out, bool zero = false) {
+  const AmrNode &pn = A->nodes[n.parent];
+  if (!n.stage) {
+    out->f = parentField;
+    for (int d = 0; d < 3; d++) out->lo[d] = pn.lo[d];
+    return MGIC_OK;
+  }
+  mgic_ctx *c = A->ctx;
+  mgic_field *st = n.stage;
+  MGIC_CUDA(cudaMemsetAsync(st->base, 0, st->bytes, c->stream));
+  if (!zero) {
+    const int za = std::max(n.stageLo[2], parentField->k0), zb = std::min(n.stageLo[2] + st->nz, parentField->k0 + parentField->nz);
+    if (zb > za)
+      MGIC_TRY(mgk::copy_box(c, st->nx, st->ny, zb - za,
+                             parentField->p + n.stageLo[0] + (long long)n.stageLo[1] * parentField->sy + (long long)(za - parentField->k0) * parentField->sz,
+                             parentField->sy, parentField->sz, st->p + (long long)(za - n.stageLo[2]) * st->sz, st->sy, st->sz));
+    MGIC_REQUIRE(c->allreduce, "multi-rank hierarchy without the communication hooks (mgic_comm_init)");
+    ProfScope ps(c, false, PROF_GATHER);
+    MGIC_TRY(c->allreduce(c, st->p, (int)((long long)st->sz * st->nz), 0));
+  }
+  out->f = st;
+  for (int d = 0; d < 3; d++) out->lo[d] = n.stageLo[d];
+  return MGIC_OK;
 }
-static Geom under_geom(const AmrNode &q, const mgic_field *below) {
-  Geom gc = q.op->geom();
-  gc.nx /= 2; gc.ny /= 2; gc.nz /= 2; gc.sy = below->sy; gc.sz = below->sz;
-  return gc;
+// the cells under the patch inside a coarse source (its array starts at src.lo in the parent level's index space)
+static const double *under_in(const CoarseSrc &src, const AmrNode &n) {
+  const int o[3] = {(n.op->plo[0] >> 1) - src.lo[0], (n.op->plo[1] >> 1) - src.lo[1], (n.op->plo[2] >> 1) - src.lo[2]};
+  return src.f->p + o[0] + (long long)o[1] * src.f->sy + (long long)o[2] * src.f->sz;
+}
+// ---- what a patch WRITES into its parent level (the averaged residual, zeroCovered, averageDown): the cells of `below` under
+// the patch -- on a multi-rank context only the planes of this rank's slab (the patch is replicated, so every rank has the
+// fine data for its own part).  fineOff = first fine plane that maps into the local part.
+struct UnderLocal { Geom g; double *ptr; long long fineOff; bool empty; };
+static UnderLocal under_local(const AmrNode &q, mgic_field *below) {
+  UnderLocal u;
+  u.g = q.op->geom();
+  u.g.nx /= 2; u.g.ny /= 2; u.g.sy = below->sy; u.g.sz = below->sz;
+  const int zA = q.off[2], zB = q.off[2] + q.op->n[2] / 2;                 // in the parent array's (global) plane index
+  const int la = std::max(zA, below->k0), lb = std::min(zB, below->k0 + below->nz);
+  u.empty = lb <= la;
+  u.g.nz = u.empty ? 0 : lb - la;
+  u.ptr = below->p + q.off[0] + (long long)q.off[1] * below->sy + (long long)((u.empty ? zA : la) - below->k0) * below->sz;
+  u.fineOff = u.empty ? 0 : 2LL * (la - zA);
+  return u;
+}
+static inline const unsigned char *mask_at(const mgic_op *o, long long plane) {
+  return o->mask ? o->mask + plane * (long long)o->n[0] * o->n[1] : nullptr;
+}
+// the 8-cell average of a patch field into the parent's cells under it ([Chombo] CoarseAverage, AMRRestrictS' second half)
+static int average_under(mgic_amr *A, const AmrNode &n, mgic_field *below, const mgic_field *fine) {
+  const UnderLocal u = under_local(n, below);
+  if (u.empty) return MGIC_OK;
+  return mgk::coarse_average(A->ctx, u.g, u.ptr, fine->p + u.fineOff * fine->sz, fine->sy, fine->sz, 2, 0, mask_at(n.op, u.fineOff));
+}
+static int zero_under(mgic_amr *A, const AmrNode &n, mgic_field *below) {
+  const UnderLocal u = under_local(n, below);
+  if (u.empty) return MGIC_OK;
+  return mgk::box_set_val(A->ctx, u.g, u.ptr, 0.0, mask_at(n.op, u.fineOff), n.op->n[0], (long long)n.op->n[0] * n.op->n[1]);
 }
 
 static int amr_cycle(mgic_amr *A, int l) {
@@ -1539,16 +1609,20 @@ static int amr_cycle(mgic_amr *A, int l) {
   for (int q = q0; q < q1; q++) {
     AmrNode &n = A->nodes[q];
     AmrNode &pn = A->nodes[n.parent];
-    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
-    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, pn.res), under_patch(n, pn.res), n.tmp->p, n.tmp->sy, n.tmp->sz, 2, 0, n.op->mask));
+    CoarseSrc cs;
+    MGIC_TRY(amr_coarse_source(A, n, pn.corr, &cs, true));          // the coarser correction was just zeroed
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, cs.f, cs.lo, n.res, 1));
+    MGIC_TRY(average_under(A, n, pn.res, n.tmp));
   }
   MGIC_TRY(amr_cycle(A, l - 1));
   // ---- up
   for (int q = q0; q < q1; q++) {
     AmrNode &n = A->nodes[q];
     AmrNode &pn = A->nodes[n.parent];
-    MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_patch(n, pn.corr), pn.corr->sy, pn.corr->sz, n.op->mask));
-    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, pn.corr, pn.lo, n.res, 1));
+    CoarseSrc cs;
+    MGIC_TRY(amr_coarse_source(A, n, pn.corr, &cs));
+    MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_in(cs, n), cs.f->sy, cs.f->sz, n.op->mask));
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, cs.f, cs.lo, n.res, 1));
     MGIC_TRY(mgic_op_assign(n.op, n.res, n.tmp));
     MGIC_TRY(mgic_op_set_to_zero(n.op, n.tmp));
     MGIC_TRY(mgic_op_relax(n.op, n.tmp, n.res, S));
@@ -1584,7 +1658,9 @@ extern "C" int mgic_amr_apply(mgic_amr *A, mgic_field *const *lhs, mgic_field *c
   MGIC_TRY(mgic_op_apply(A->nodes[0].op, lhs[0], phi[0], homogeneous));
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgic_op_amr_operator_nf(n.op, lhs[q], phi[q], phi[n.parent], A->nodes[n.parent].lo, homogeneous));
+    CoarseSrc cs;
+    MGIC_TRY(amr_coarse_source(A, n, phi[n.parent], &cs));
+    MGIC_TRY(mgic_op_amr_operator_nf(n.op, lhs[q], phi[q], cs.f, cs.lo, homogeneous));
   }
   return MGIC_OK;
 }
@@ -1593,7 +1669,9 @@ extern "C" int mgic_amr_residual(mgic_amr *A, mgic_field *const *res, mgic_field
   MGIC_TRY(mgic_op_residual(A->nodes[0].op, res[0], phi[0], rhs[0], homogeneous));
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgic_op_amr_residual_nf(n.op, res[q], phi[q], phi[n.parent], A->nodes[n.parent].lo, rhs[q], homogeneous));
+    CoarseSrc cs;
+    MGIC_TRY(amr_coarse_source(A, n, phi[n.parent], &cs));
+    MGIC_TRY(mgic_op_amr_residual_nf(n.op, res[q], phi[q], cs.f, cs.lo, rhs[q], homogeneous));
   }
   return MGIC_OK;
 }
@@ -1602,8 +1680,7 @@ extern "C" int mgic_amr_zero_covered(mgic_amr *A, mgic_field *const *x) {
   MGIC_TRY(amr_check_vec(A, x));
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), 0.0, n.op->mask, n.op->n[0],
-                              (long long)n.op->n[0] * n.op->n[1]));
+    MGIC_TRY(zero_under(A, n, x[n.parent]));
   }
   return MGIC_OK;
 }
@@ -1613,7 +1690,7 @@ extern "C" int mgic_amr_average_down(mgic_amr *A, mgic_field *const *x) {
   MGIC_TRY(amr_check_vec(A, x));
   for (size_t q = A->nodes.size() - 1; q >= 1; q--) {
     const AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgk::coarse_average(A->ctx, under_geom(n, x[n.parent]), under_patch(n, x[n.parent]), x[q]->p, x[q]->sy, x[q]->sz, 2, 0, n.op->mask));
+    MGIC_TRY(average_under(A, n, x[n.parent], x[q]));
   }
   return MGIC_OK;
 }
@@ -1623,7 +1700,7 @@ static int amr_masked_copy(mgic_amr *A, mgic_field *const *x) {
   for (size_t q = 1; q < A->nodes.size(); q++) {
     const AmrNode &n = A->nodes[q];
     mgic_field *pt = A->nodes[n.parent].tmp;
-    MGIC_TRY(mgk::box_set_val(A->ctx, under_geom(n, pt), under_patch(n, pt), 0.0, n.op->mask, n.op->n[0], (long long)n.op->n[0] * n.op->n[1]));
+    MGIC_TRY(zero_under(A, n, pt));
   }
   return MGIC_OK;
 }
@@ -1909,10 +1986,10 @@ struct mgic_hier {
   mgic_mg *mg = nullptr;       // the solver of the current nonlinear iteration (mgic_hier_define_solver .. _release_solver)
   mgic_amr *amr = nullptr;
 };
-extern "C" int mgic_hier_release_solver(mgic_hier *H);
+static void hier_drop_solver(mgic_hier *H);
 extern "C" int mgic_hier_destroy(mgic_hier *H) {
   if (!H) return MGIC_OK;
-  mgic_hier_release_solver(H);
+  hier_drop_solver(H);
   for (HierNode &n : H->nodes) {
     mgic_field_destroy(n.dpsi); mgic_field_destroy(n.rhs); mgic_field_destroy(n.a); mgic_field_destroy(n.b);
     mgic_vars_destroy(n.vars);
@@ -1927,7 +2004,10 @@ extern "C" int mgic_hier_destroy(mgic_hier *H) {
 extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, const int *nnodes, const int *nboxes, const int *boxes,
                                 mgic_hier **out) {
   MGIC_REQUIRE(c && P && out && nfiner >= 0 && (nfiner == 0 || (nnodes && nboxes && boxes)), "bad argument");
-  MGIC_REQUIRE(c->nranks == 1, "mgic_hier drives one GPU");
+  // multi-rank context: the base level is cut into equal z-slabs (one per rank, multiples of max_grid_size), the refined
+  // levels are replicated on every rank (mgic_op_create_patch); every rank makes the same calls
+  MGIC_REQUIRE(P->N[2] % c->nranks == 0 && (P->N[2] / c->nranks) % P->max_grid_size == 0,
+               "the base level's z extent must split into equal slabs that are multiples of max_grid_size");
   MGIC_REQUIRE(!P->is_periodic, "the periodic constant-K branch (Main_PoissonSolver.cpp:137-150) is not implemented on hierarchies");
   mgic_hier *H = new mgic_hier;
   H->ctx = c; H->P = *P; H->P.max_level = nfiner;
@@ -1936,7 +2016,8 @@ extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, c
   for (int d = 0; d < 3; d++) { bclo[d] = P->bc_lo[d]; bchi[d] = P->bc_hi[d]; }
   const double dx0 = P->L / P->N[0];
 #define H_TRY(x) do { rc = (x); if (rc != MGIC_OK) { mgic_hier_destroy(H); return rc; } } while (0)
-  H_TRY(mgic_op_create(c, P->N, 0, P->N[2], dx0, P->alpha, P->beta, bclo, bchi, P->bc_value, &H->lay0));
+  const int nzl = P->N[2] / c->nranks, k0 = c->rank * nzl;
+  H_TRY(mgic_op_create(c, P->N, k0, nzl, dx0, P->alpha, P->beta, bclo, bchi, P->bc_value, &H->lay0));
   {
     HierNode n0;
     H->nodes.push_back(n0);
@@ -1948,7 +2029,7 @@ extern "C" int mgic_hier_create(mgic_ctx *c, const mgic_params *P, int nfiner, c
                              std::min(k + P->max_grid_size, P->N[2]) - 1};
           n.boxes.insert(n.boxes.end(), b6, b6 + 6);
         }
-    H_TRY(mgic_vars_create(c, P, 0, P->N[2], &n.vars));
+    H_TRY(mgic_vars_create(c, P, k0, nzl, &n.vars));
     H_TRY(mgic_field_create(H->lay0, &n.dpsi)); H_TRY(mgic_field_create(H->lay0, &n.rhs));
     H_TRY(mgic_field_create(H->lay0, &n.a)); H_TRY(mgic_field_create(H->lay0, &n.b));
   }
@@ -2028,27 +2109,37 @@ extern "C" int mgic_hier_set_sources(mgic_hier *H, double constant_K) {
   }
   return MGIC_OK;
 }
-extern "C" int mgic_hier_release_solver(mgic_hier *H) {
-  if (!H) return MGIC_OK;
+// The reference rebuilds factory, MultilevelLinearOp and every MG operator each nonlinear iteration (:163-170) because aCoef
+// changed.  Here the objects survive: the coefficient ARRAYS are the same ones, so re-deriving the coarsened coefficients and
+// lambda in place (mgic_mg_refresh_coefs, the patches' lambda) gives the operators a rebuild would give -- without freeing and
+// re-allocating ~3 GB of fields and re-capturing the V-cycle graph per iteration.  They go when the hierarchy goes, or when a
+// parameter that shapes them changes.
+static void hier_drop_solver(mgic_hier *H) {
   mgic_amr_destroy(H->amr); H->amr = nullptr;
   mgic_mg_destroy(H->mg); H->mg = nullptr;
+}
+extern "C" int mgic_hier_release_solver(mgic_hier *H) {
+  (void)H;
   return MGIC_OK;
 }
 // defineOperatorFactory + MultilevelLinearOp::define (:163-170): rebuilt every nonlinear iteration, like the reference
 extern "C" int mgic_hier_define_solver(mgic_hier *H) {
   MGIC_REQUIRE(H, "NULL argument");
-  MGIC_TRY(mgic_hier_release_solver(H));
-  mgic_params P0 = H->P;
-  P0.max_level = 0;                                                         // the base level's MG hierarchy
-  MGIC_TRY(mgic_mg_create(H->ctx, &P0, H->nodes[0].a, H->nodes[0].b, &H->mg));
   std::vector<mgic_op *> patches;
   for (size_t q = 1; q < H->nodes.size(); q++) {
     HierNode &n = H->nodes[q];
     // bCoef == 1 (set_b_coef, SetLevelData.cpp:330-340): b*x == x exactly, so the patch operators drop the stream like the
-    // base level does (mgic_mg_create detects it there)
+    // base level does (mgic_mg_create detects it there); set_coefs marks lambda for recomputation
     MGIC_TRY(mgic_op_set_coefs(n.op, n.a, nullptr, H->P.alpha, H->P.beta));
     patches.push_back(n.op);
   }
+  if (H->mg && H->amr && H->mg->P.numMGsmooth == H->P.numMGsmooth && H->mg->P.preCondSolverDepth == H->P.preCondSolverDepth &&
+      H->mg->P.coefficient_average_type == H->P.coefficient_average_type)
+    return mgic_mg_refresh_coefs(H->mg);                                    // same arrays, new values: coarsen + lambda in place
+  hier_drop_solver(H);
+  mgic_params P0 = H->P;
+  P0.max_level = 0;                                                         // the base level's MG hierarchy
+  MGIC_TRY(mgic_mg_create(H->ctx, &P0, H->nodes[0].a, H->nodes[0].b, &H->mg));
   return mgic_amr_create_levels(H->mg, (int)H->perLevel.size(), H->perLevel.data(), patches.data(), &H->amr);
 }
 // solver.solve(dpsi, rhs) (:173-184); dpsi keeps its previous value as the initial guess (:93 is its only zeroing)
@@ -2073,9 +2164,9 @@ extern "C" int mgic_hier_update_psi(mgic_hier *H) {
   for (size_t q = 1; q < H->nodes.size(); q++) {
     int level = 0, parent = -1;
     MGIC_TRY(mgic_amr_node_info(H->amr, (int)q, &level, &parent));
-    const HierNode &pn = H->nodes[parent];
-    const int zero[3] = {0, 0, 0};
-    MGIC_TRY(mgic_update_psi0_patch(H->nodes[q].vars, H->nodes[q].op, H->nodes[q].dpsi, pn.dpsi, pn.op ? pn.op->plo : zero));
+    CoarseSrc cs;   // the coarser level's dpsi around the patch (gathered when that level is the distributed base level)
+    MGIC_TRY(amr_coarse_source(H->amr, H->amr->nodes[q], H->nodes[parent].dpsi, &cs));
+    MGIC_TRY(mgic_update_psi0_patch(H->nodes[q].vars, H->nodes[q].op, H->nodes[q].dpsi, cs.f, cs.lo));
   }
   return MGIC_OK;
 }
@@ -2108,6 +2199,7 @@ extern "C" int mgic_hier_nl_iteration(mgic_hier *H, double *dpsi_norm, int *solv
 // tools/mgic2hdf5.py turns into vcPoissonFinal.3d.hdf5 (dataset for dataset) wherever h5py exists.
 extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double constant_K) {
   MGIC_REQUIRE(H && path, "NULL argument");
+  MGIC_REQUIRE(H->ctx->nranks == 1, "the checkpoint writer runs on a single-rank context");
   mgic_ctx *c = H->ctx;
   const int NV = 32, NG = 3;
   static const char *names[32] = {"chi", "h11", "h12", "h13", "h22", "h23", "h33", "K", "A11", "A12", "A13", "A22", "A23", "A33", "Theta",

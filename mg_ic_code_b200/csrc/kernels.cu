@@ -414,6 +414,17 @@ __global__ void __launch_bounds__(128) k_box_set(Geom g, double *__restrict__ y,
   y[I + J * g.sy + K * g.sz] = v;
 }
 
+// dst box := src box (nx x ny x nz cells, each array with its own strides): the cells of a z-slab-distributed coarser level
+// that lie under / around a replicated finer patch, on their way into the patch's staging array (capi.cu amr_coarse_source)
+__global__ void __launch_bounds__(128) k_copy_box(int nx, int ny, const double *__restrict__ src, long long ssy, long long ssz,
+                                                  double *__restrict__ dst, long long dsy, long long dsz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= nx || j >= ny) return;
+  dst[i + j * dsy + k * dsz] = src[i + j * ssy + k * ssz];
+}
+
 // y = 0 outside the mask (uploads and constant fills of a masked AMR level: cells outside its boxes stay zero)
 __global__ void __launch_bounds__(256) k_apply_mask(long long n, double *__restrict__ y, const unsigned char *__restrict__ mask) {
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
@@ -568,6 +579,14 @@ int box_set_val(mgic_ctx *c, const Geom &g, double *y, double v, const unsigned 
   dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
   k_box_set<<<grd, blk, 0, c->stream>>>(g, y, v, fineMask, msy, msz);
   return post_launch(c, "box_set_val");
+}
+
+int copy_box(mgic_ctx *c, int nx, int ny, int nz, const double *src, long long ssy, long long ssz, double *dst, long long dsy, long long dsz) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) return MGIC_OK;
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(nx, ny, nz, blk);
+  k_copy_box<<<grd, blk, 0, c->stream>>>(nx, ny, src, ssy, ssz, dst, dsy, dsz);
+  return post_launch(c, "copy_box");
 }
 
 int apply_mask(mgic_ctx *c, const Geom &g, double *y, const unsigned char *mask) {

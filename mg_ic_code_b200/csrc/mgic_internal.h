@@ -230,6 +230,7 @@ int restrict_res(mgic_ctx *, const Geom &fine, const BCk &, double *resC, long l
 int prolong(mgic_ctx *, const Geom &fine, double *phi, const double *coarse, long long csy, long long csz,
             const unsigned char *fineMask = nullptr);
 int apply_mask(mgic_ctx *, const Geom &, double *y, const unsigned char *mask);   // y = 0 outside the mask
+int copy_box(mgic_ctx *, int nx, int ny, int nz, const double *src, long long ssy, long long ssz, double *dst, long long dsy, long long dsz);
 // QuadCFInterp for every coarse-fine ghost of a masked level: face[f][cell] for the cells whose neighbour beyond face f is one
 int quad_cf_masked(mgic_ctx *, const Geom &g, const unsigned char *mask, const int plo[3], const int ndom[3], double h, const double *phi,
                    const double *coarse, long long csy, long long csz, const int clo[3], double *const face[6]);

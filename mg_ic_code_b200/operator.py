@@ -592,6 +592,20 @@ class Hierarchy:
         check(self.L.mgic_hier_nl_iteration(self.h, C.byref(nrm), C.byref(it), C.byref(st)))
         return nrm.value, it.value, st.value
 
+    def nl_iteration_steps(self, constant_K=0.0, timer=None):
+        """the same pass step by step, as the reference's driver calls it (Main_PoissonSolver.cpp:154-208); timer(name) is called
+        before each step and once ("end") after the last"""
+        t = timer or (lambda name: None)
+        it, st, nrm = C.c_int(), C.c_int(), C.c_double()
+        t("set_sources"); check(self.L.mgic_hier_set_sources(self.h, constant_K))
+        t("define_solver"); check(self.L.mgic_hier_define_solver(self.h))
+        t("solve"); check(self.L.mgic_hier_solve(self.h, C.byref(it), C.byref(st)))
+        t("update_psi"); check(self.L.mgic_hier_update_psi(self.h))
+        t("dpsi_norm"); check(self.L.mgic_hier_dpsi_norm(self.h, C.byref(nrm)))
+        t("release_solver"); check(self.L.mgic_hier_release_solver(self.h))
+        t("end")
+        return nrm.value, it.value, st.value
+
     def nl_solve(self):
         norms = (C.c_double * 64)()
         its = C.c_int()

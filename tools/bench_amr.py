@@ -58,7 +58,16 @@ def main():
     import torch
     import mg_ic_code_b200 as m
     n, L = args.n, 100.0
-    ctx = m.Context(0)
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:      # torchrun: the base level in z-slabs over the ranks, the refined levels replicated
+        import torch.distributed as dist
+        from mg_ic_code_b200 import comm
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = m.Context(local, rank=rank, nranks=world)
+    if world > 1:
+        comm.attach(ctx, dist)
     base = dict(m.DEFAULTS, N=(n, n, n), L=L, numMGsmooth=args.smooth, numMGIterations=2, max_NL_iterations=args.nl)
     t_grids = None
     if args.generated:
@@ -85,11 +94,21 @@ def main():
         l0 = ctx.launch_count
         w0 = time.perf_counter()
         ev0.record(stream)
-        nrm, its, st = H.nl_iteration()
+        marks = []
+
+        def timer(name):
+            ctx.sync()
+            marks.append((name, time.perf_counter()))
+        nrm, its, st = H.nl_iteration_steps(timer=timer)
         ev1.record(stream)
         ctx.sync()
+        steps = {a[0]: round((b[1] - a[1]) * 1e3, 3) for a, b in zip(marks, marks[1:])}
         rows.append({"dpsi_norm": nrm, "bicgstab_iterations": its, "status": st, "ms": ev0.elapsed_time(ev1),
-                     "wall_ms": (time.perf_counter() - w0) * 1e3, "launches": ctx.launch_count - l0})
+                     "wall_ms": (time.perf_counter() - w0) * 1e3, "launches": ctx.launch_count - l0, "steps_ms": steps})
+        if dist is not None:      # the slowest rank's time
+            t = torch.tensor([rows[-1]["ms"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rows[-1]["ms"] = float(t.item())
         if nrm < P.tolerance:
             break
     vc = [4 * r["bicgstab_iterations"] for r in rows]                     # 2 preCond per BiCGStab iteration x numMGIterations = 2
@@ -98,11 +117,17 @@ def main():
         covered[lvl - 1] = covered.get(lvl - 1, 0) + c // 8
     composite = sum(cells) - sum(covered.values())
     ms_vc = [r["ms"] / max(v, 1) for r, v in zip(rows, vc)]
-    print(json.dumps({"tool": "bench_amr", "config": "C4: 3-level hierarchy (ratio 2) refined around both punctures, base %d^3, one B200" % n,
+    if rank != 0:
+        dist.barrier(); dist.destroy_process_group()
+        return
+    print(json.dumps({"tool": "bench_amr", "config": "C4: 3-level hierarchy (ratio 2) refined around both punctures, base %d^3, %d B200" % (n, world),
+                      "decomposition": "one GPU" if world == 1 else "base level in %d z-slabs, refined levels replicated on every rank" % world,
                       "hierarchy": desc, "nodes": [{"level": lv, "lo": lo, "n": nn, "cells": c} for lv, lo, nn, c in info],
                       "composite_cells": composite, "smooth": args.smooth, "set_grids_s": t_grids, "nonlinear_iterations": rows,
                       "ms_per_amr_vcycle_upper_bound": float(np.median(ms_vc)),
                       "gdof_per_s_composite_per_vcycle": composite / float(np.median(ms_vc)) / 1e6}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
     norms = [r["dpsi_norm"] for r in rows]
     # quadratic-looking decay for the first iterations (5e-2, 2e-5, 1e-8 on one level), then a floor around
     # 1e-7: with the reference's reflux a no-op (VariableCoeffPoissonOperator.cpp:264-271) the coarse cells a finer level covers
