@@ -250,7 +250,6 @@ extern "C" int mgic_op_create(mgic_ctx *c, const int n[3], int k0, int nz_local,
     if (bc_hi[d] < 0 || bc_hi[d] > 2) { mgic_set_error("bogus bc flag high side %d", bc_hi[d]); return MGIC_ERR_ARG; }   // SetBCs.cpp:123
     MGIC_REQUIRE((bc_lo[d] == MGIC_BC_PERIODIC) == (bc_hi[d] == MGIC_BC_PERIODIC), "periodic must be set on both sides");
   }
-  MGIC_REQUIRE(c->nranks == 1 || bc_lo[2] != MGIC_BC_PERIODIC, "periodic z across ranks is not supported");
   MGIC_CUDA(cudaSetDevice(c->device));
   mgic_op *o = new mgic_op;
   o->ctx = c;
@@ -385,7 +384,10 @@ extern "C" int mgic_op_set_alpha_beta(mgic_op *o, double alpha, double beta) {
 }
 extern "C" int mgic_op_reset_lambda(mgic_op *o) {
   MGIC_REQUIRE(o && o->a, "operator has no coefficients (setCoefs)");
-  if (!o->lambda) MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
+  if (!o->lambda) {
+    MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
+    o->lambda->zWrap = o->ctx->nranks > 1 && !o->isGlobal && o->bc_lo[2] == MGIC_BC_PERIODIC;
+  }
   if (!o->lambdaDirty) return MGIC_OK;
   MGIC_TRY(mgk::compute_lambda(o->ctx, o->geom(), o->lambda->p, o->a->p, o->alpha, o->beta, o->dx));
   if (o->ctx->nranks > 1 && !o->isGlobal) {  // the fused sweep updates the neighbour's first plane redundantly: it needs its coefficients
@@ -414,6 +416,7 @@ extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
   MGIC_CUDA(cudaSetDevice(like->ctx->device));
   MGIC_TRY(field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out));
   (*out)->mask = like->mask;
+  (*out)->zWrap = like->ctx->nranks > 1 && !like->isGlobal && like->bc_lo[2] == MGIC_BC_PERIODIC;
   return MGIC_OK;
 }
 extern "C" int mgic_field_destroy(mgic_field *f) {

@@ -83,6 +83,10 @@ struct Comm {
   long long p2pExchanges = 0, ncclExchanges = 0;
 };
 
+// z-neighbours of a field's slab: the ranks below / above, on a ring when the level is periodic in z
+inline bool has_lo(const mgic_field *f) { return f->zWrap || f->k0 > 0; }
+inline bool has_hi(const mgic_field *f) { return f->zWrap || f->k0 + f->nz < f->gnz; }
+
 struct PushArgs {
   const double *srcLo, *srcHi;  // this rank's lowest / highest `planes` valid planes
   double *dstLo, *dstHi;        // the lo neighbour's upper ghost planes, the hi neighbour's lower ghost planes (null: none)
@@ -184,7 +188,7 @@ int sweep_peers_hook(mgic_ctx *c, const mgic_field *like, const double *outBase,
   auto it = cm->reg.find(outBase);
   if (it == cm->reg.end() || !it->second.ok) return MGIC_OK;
   const PeerArr &pa = it->second;
-  const bool hasLo = like->k0 > 0, hasHi = like->k0 + like->nz < like->gnz;
+  const bool hasLo = has_lo(like), hasHi = has_hi(like);
   // my plane k (k = 0, 1) is the lo neighbour's upper ghost plane k; my plane nz-2+k is the hi neighbour's lower ghost plane k:
   // both as "address of MY plane 0" in the neighbour's array, so that the kernel adds the same offset it uses for its own store
   sp->peerLo = hasLo ? pa.lo + (long long)(MGIC_GZ + pa.nzLo) * like->sz : nullptr;
@@ -204,7 +208,7 @@ __global__ void k_sweep_wait(u64 *ctl, int hasLo, int hasHi) {
 int sweep_wait_hook(mgic_ctx *c, const mgic_field *like) {
   Comm *cm = (Comm *)c->comm;
   if (!cm || !cm->p2p) { mgic_set_error("sweep_wait without peer mapping"); return MGIC_ERR_STATE; }
-  k_sweep_wait<<<1, 1, 0, c->haloStream ? c->haloStream : c->stream>>>(cm->ctl, like->k0 > 0, like->k0 + like->nz < like->gnz);
+  k_sweep_wait<<<1, 1, 0, c->haloStream ? c->haloStream : c->stream>>>(cm->ctl, has_lo(like), has_hi(like));
   MGIC_CUDA(cudaGetLastError());
   c->launches++;
   return MGIC_OK;
@@ -280,14 +284,16 @@ int map_neighbours(mgic_ctx *c, Comm *cm, NcclApi *A, void *base, int nz, long l
   for (const IpcRec &r : all) allOk = allOk && r.ok;
   *lo = *hi = nullptr;
   int opened = allOk ? 1 : 0;
+  const int loRank = (cm->rank - 1 + cm->nranks) % cm->nranks, hiRank = (cm->rank + 1) % cm->nranks;   // a ring when z is periodic
   if (allOk && hasLo) {
-    const IpcRec &r = all[cm->rank - 1];
+    const IpcRec &r = all[loRank];
     if (r.sz != sz || cudaIpcOpenMemHandle(lo, r.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; *lo = nullptr; }
     *nzLo = r.nz;
   }
   if (allOk && hasHi) {
-    const IpcRec &r = all[cm->rank + 1];
-    if (r.sz != sz || cudaIpcOpenMemHandle(hi, r.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; *hi = nullptr; }
+    const IpcRec &r = all[hiRank];
+    if (hasLo && hiRank == loRank) *hi = *lo;   // two ranks on a ring: one peer, one mapping
+    else if (r.sz != sz || cudaIpcOpenMemHandle(hi, r.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0; *hi = nullptr; }
     *nzHi = r.nz;
   }
   cudaGetLastError();
@@ -300,7 +306,7 @@ int map_neighbours(mgic_ctx *c, Comm *cm, NcclApi *A, void *base, int nz, long l
   for (const IpcRec &r : all) good = good && r.ok;
   if (!good) {
     if (*lo) cudaIpcCloseMemHandle(*lo);
-    if (*hi) cudaIpcCloseMemHandle(*hi);
+    if (*hi && *hi != *lo) cudaIpcCloseMemHandle(*hi);
     *lo = *hi = nullptr;
     cudaGetLastError();
   }
@@ -318,7 +324,8 @@ int p2p_setup(mgic_ctx *c, Comm *cm, NcclApi *A) {
   void *lo = nullptr, *hi = nullptr;
   int a = 0, b = 0;
   bool ok = false;
-  MGIC_TRY(map_neighbours(c, cm, A, cm->ctl, 0, 0, cm->rank > 0, cm->rank + 1 < cm->nranks, want, &lo, &hi, &a, &b, &ok));
+  // both ring neighbours (rank 0's lo neighbour is the last rank): levels that are periodic in z exchange around the ring
+  MGIC_TRY(map_neighbours(c, cm, A, cm->ctl, 0, 0, true, true, want, &lo, &hi, &a, &b, &ok));
   cm->p2p = ok;
   cm->ctlLo = (u64 *)lo; cm->ctlHi = (u64 *)hi;
   if (!ok && want && cm->rank == 0)
@@ -329,7 +336,7 @@ int p2p_setup(mgic_ctx *c, Comm *cm, NcclApi *A) {
 // collective: called by every rank for the same array (same call sequence on every rank)
 int register_array(mgic_ctx *c, Comm *cm, NcclApi *A, mgic_field *f) {
   const size_t buried = cm->graveyard.size();
-  const bool hasLo = f->k0 > 0, hasHi = f->k0 + f->nz < f->gnz;
+  const bool hasLo = has_lo(f), hasHi = has_hi(f);
   PeerArr pa;
   void *lo = nullptr, *hi = nullptr;
   MGIC_TRY(map_neighbours(c, cm, A, f->base, f->nz, f->sz, hasLo, hasHi, true, &lo, &hi, &pa.nzLo, &pa.nzHi, &pa.ok));
@@ -362,7 +369,7 @@ int release_hook(mgic_ctx *c, void *base) {
   cudaStreamSynchronize(c->stream);
   if (c->commStream) cudaStreamSynchronize(c->commStream);
   if (pa.lo) cudaIpcCloseMemHandle(pa.lo);
-  if (pa.hi) cudaIpcCloseMemHandle(pa.hi);
+  if (pa.hi && pa.hi != pa.lo) cudaIpcCloseMemHandle(pa.hi);
   cudaGetLastError();
   cm->graveyard.push_back(base);
   return 1;
@@ -422,11 +429,11 @@ extern "C" int mgic_comm_destroy(mgic_ctx *c) {
   // unmap everything this rank imported; once every rank has done so (barrier) the exported blocks may be freed
   for (auto &kv : cm->reg) {
     if (kv.second.lo) cudaIpcCloseMemHandle(kv.second.lo);
-    if (kv.second.hi) cudaIpcCloseMemHandle(kv.second.hi);
+    if (kv.second.hi && kv.second.hi != kv.second.lo) cudaIpcCloseMemHandle(kv.second.hi);
   }
   cm->reg.clear();
   if (cm->ctlLo) cudaIpcCloseMemHandle(cm->ctlLo);
-  if (cm->ctlHi) cudaIpcCloseMemHandle(cm->ctlHi);
+  if (cm->ctlHi && cm->ctlHi != cm->ctlLo) cudaIpcCloseMemHandle(cm->ctlHi);
   cudaGetLastError();
   if (A && cm->comm && cm->d_stage) {
     A->AllReduce(cm->d_stage, cm->d_stage, 1, ncclChar, ncclSum, cm->comm, c->stream);
@@ -451,7 +458,8 @@ extern "C" int mgic_comm_halo_exchange(mgic_ctx *c, mgic_field *f, int planes) {
   NcclApi *A = api();
   Comm *cm = (Comm *)c->comm;
   if (!A || !cm) { mgic_set_error("NCCL communicator not initialised"); return MGIC_ERR_STATE; }
-  const bool hasLo = f->k0 > 0, hasHi = f->k0 + f->nz < f->gnz;
+  const bool hasLo = has_lo(f), hasHi = has_hi(f);
+  const int loRank = (c->rank - 1 + c->nranks) % c->nranks, hiRank = (c->rank + 1) % c->nranks;
   const size_t cnt = (size_t)planes * f->sz;
   cudaStream_t st = c->haloStream ? c->haloStream : c->stream;
   if (cm->p2p && c->p2pHalo) {
@@ -488,16 +496,12 @@ extern "C" int mgic_comm_halo_exchange(mgic_ctx *c, mgic_field *f, int planes) {
   }
   cm->ncclExchanges++;
   NCCL_TRY(A->GroupStart());
-  if (hasLo) {
-    NCCL_TRY(A->Send(f->p, cnt, ncclDouble, c->rank - 1, cm->comm, st));
-    NCCL_TRY(A->Recv(f->p - (long long)planes * f->sz, cnt, ncclDouble, c->rank - 1, cm->comm, st));
-    cm->haloBytes += (long long)cnt * 8;
-  }
-  if (hasHi) {
-    NCCL_TRY(A->Send(f->p + (long long)(f->nz - planes) * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, st));
-    NCCL_TRY(A->Recv(f->p + (long long)f->nz * f->sz, cnt, ncclDouble, c->rank + 1, cm->comm, st));
-    cm->haloBytes += (long long)cnt * 8;
-  }
+  // issue order matters when both neighbours are the same rank (two ranks on a ring): NCCL pairs the sends and receives of
+  // one peer in order, and my low planes must land in its UPPER ghost planes
+  if (hasLo) { NCCL_TRY(A->Send(f->p, cnt, ncclDouble, loRank, cm->comm, st)); cm->haloBytes += (long long)cnt * 8; }
+  if (hasHi) NCCL_TRY(A->Recv(f->p + (long long)f->nz * f->sz, cnt, ncclDouble, hiRank, cm->comm, st));
+  if (hasHi) { NCCL_TRY(A->Send(f->p + (long long)(f->nz - planes) * f->sz, cnt, ncclDouble, hiRank, cm->comm, st)); cm->haloBytes += (long long)cnt * 8; }
+  if (hasLo) NCCL_TRY(A->Recv(f->p - (long long)planes * f->sz, cnt, ncclDouble, loRank, cm->comm, st));
   NCCL_TRY(A->GroupEnd());
   return MGIC_OK;
 }

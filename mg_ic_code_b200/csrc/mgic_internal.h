@@ -165,6 +165,7 @@ struct mgic_field {
   size_t bytes = 0;
   int k0 = 0, gnz = 0;
   bool noHalo = false;     // slab view into a whole-level array: its ghost planes are real neighbour planes
+  bool zWrap = false;      // periodic in z on a multi-rank context: the slabs form a ring (rank 0's lo neighbour is the last rank)
   const unsigned char *mask = nullptr;  // masked AMR level (see BCk): cells outside the level's boxes are kept at zero
   cudaEvent_t evPending = nullptr;  // completion of the field's last prefetch / writeback (mgic_field_wait)
 };
