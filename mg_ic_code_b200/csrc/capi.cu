@@ -191,7 +191,9 @@ BCk mgic_op::bck(bool homogeneous) const {
   }
   if (k0 > 0) k.type[4] = MGIC_FACE_INTERIOR;
   if (k0 + nzl < n[2]) k.type[5] = MGIC_FACE_INTERIOR;
-  if (ctx->nranks > 1 && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
+  // periodic in z across ranks: the slabs form a ring, the wrap-around planes arrive by the halo exchange -- but a whole-level
+  // (agglomerated / replicated) operator on a multi-rank context wraps its own indices like a single-GPU one
+  if (ctx->nranks > 1 && !isGlobal && bc_lo[2] == MGIC_BC_PERIODIC) { k.type[4] = MGIC_FACE_INTERIOR; k.type[5] = MGIC_FACE_INTERIOR; }
   for (int q = 0; q < 7; q++) k.cf[q] = 0.0;
   for (int f = 0; f < 6; f++) k.face[f] = nullptr;
   k.mask = mask;

@@ -1,4 +1,4 @@
-"""python tools/bench_amr.py [--n 256] [--smooth 2] [--generated]: config C4 (BASELINE.json configs[3]) on one GPU --
+"""python tools/bench_amr.py [--size 256] [--smooth 2] [--generated]   (torchrun --nproc-per-node N tools/bench_amr.py --size 256 on N GPUs): config C4 (BASELINE.json configs[3]) on one GPU --
 base level n^3, level 1 = the union of the two 64^3-coarse-cell cubes around the punctures, level 2 = two 32^3-level-1-cell
 cubes -- as the reference runs it: poissonSolve's nonlinear loop on the hierarchy (Main_PoissonSolver.cpp:131-216) through
 mgic_hier_*: level-resolution Bowen-York sources on every level, BiCGStab over MultilevelLinearOp preconditioned by AMR
@@ -47,7 +47,7 @@ def c4_boxes(n, L=100.0, offset=10.0, block=8):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="base level cells per side (--size under torchrun, whose own parser claims --n)")
     ap.add_argument("--smooth", type=int, default=2)
     ap.add_argument("--box", type=int, default=32)
     ap.add_argument("--max-level", type=int, default=2)
