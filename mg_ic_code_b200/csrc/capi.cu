@@ -2312,6 +2312,7 @@ extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_nor
   mgic_vars *vars = nullptr;
   mgic_op *lay = nullptr;
   mgic_field *dpsi = nullptr, *rhs = nullptr, *aC = nullptr, *bC = nullptr;
+  mgic_mg *mg = nullptr;
   int rc = MGIC_OK, its = 0;
   int bclo[3], bchi[3];
   for (int d = 0; d < 3; d++) {
@@ -2329,14 +2330,15 @@ extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_nor
   for (int NL_iter = 0; NL_iter < P->max_NL_iterations; NL_iter++) {     // :131
     NL_TRY(mgic_set_rhs_and_a_coef(vars, rhs, aC, 0.0));                 // :154-160 (non-periodic: constant_K = 0)
     NL_TRY(mgic_set_b_coef(vars, bC));
-    mgic_mg *mg = nullptr;
-    NL_TRY(mgic_mg_create(c, P, aC, bC, &mg));                           // :163-170 (rebuilt every NL iteration)
+    // :163-170 rebuilds factory, MultilevelLinearOp and every MG operator per iteration; here the objects survive and the
+    // coarsened coefficients / lambda are re-derived in place from the same coefficient arrays (identical operators, no
+    // re-allocation, the V-cycle graph stays valid)
+    if (!mg) NL_TRY(mgic_mg_create(c, P, aC, bC, &mg));
+    else NL_TRY(mgic_mg_refresh_coefs(mg));
     int it = 0, st = 0;
-    rc = mgic_mg_outer_solve(mg, dpsi, rhs, &it, &st, nullptr, 0);       // :184
+    NL_TRY(mgic_mg_outer_solve(mg, dpsi, rhs, &it, &st, nullptr, 0));    // :184
     double nrm = 0.0;
-    if (rc == MGIC_OK) rc = mgic_update_psi0(vars, mg->ops[0], dpsi, &nrm);  // :189-208
-    mgic_mg_destroy(mg);
-    if (rc != MGIC_OK) goto done;
+    NL_TRY(mgic_update_psi0(vars, mg->ops[0], dpsi, &nrm));              // :189-208
     if (dpsi_norms && NL_iter < max_out) dpsi_norms[NL_iter] = nrm;
     its = NL_iter + 1;
     if (nrm < P->tolerance || nrm > 1e5) break;                          // :212
@@ -2345,6 +2347,7 @@ extern "C" int mgic_nl_solve(mgic_ctx *c, const mgic_params *P, double *dpsi_nor
 done:
 #undef NL_TRY
   if (nl_iterations) *nl_iterations = its;
+  mgic_mg_destroy(mg);
   mgic_field_destroy(dpsi); mgic_field_destroy(rhs); mgic_field_destroy(aC); mgic_field_destroy(bC);
   mgic_op_destroy(lay);
   mgic_vars_destroy(vars);
