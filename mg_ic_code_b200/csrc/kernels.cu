@@ -25,7 +25,7 @@ inline int post_launch(mgic_ctx *c, const char *what) {
 
 // ---- GSRB colour pass: GSRBHELMHOLTZVC3D (VariableCoeffPoissonOperatorF.ChF:56-139) ------------------------
 // One thread per cell of the colour: i = 2t + parity so that (i + j + k_global + color) is even (:98-106).
-template <bool HAS_B>
+template <bool HAS_B, bool MASKED>
 __global__ void __launch_bounds__(256) k_gsrb_color(Geom g, BCk bc, double *__restrict__ phi, const double *__restrict__ rhs,
                                                     const double *__restrict__ a, const double *__restrict__ b,
                                                     const double *__restrict__ lam, double alpha, double beta,
@@ -37,16 +37,16 @@ __global__ void __launch_bounds__(256) k_gsrb_color(Geom g, BCk bc, double *__re
   const int i = 2 * t + ((j + k + g.k0 + color) & 1);
   if (i >= g.nx) return;
   const long long idx = i + j * g.sy + k * g.sz;
-  if (bc.mask && !bc.mask[idx]) return;   // masked AMR level: not a cell of the level's boxes
+  if (MASKED && !bc.mask[idx]) return;   // masked AMR level: not a cell of the level's boxes
   const double c = phi[idx];
-  const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+  const Nb n = neighbours<MASKED>(phi, idx, i, j, k, g, bc, c);
   phi[idx] = gsrb_point<HAS_B>(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp, a[idx], HAS_B ? b[idx] : 1.0, lam[idx], rhs[idx], alpha, beta,
                                dxinv);
 }
 
 // ---- applyOp / residual: VCCOMPUTEOP3D (:181-237), VCCOMPUTERES3D (:283-339) --------------------------------
 // MODE 0: lhs = alpha*a*phi - S*dxinv*beta*b ; MODE 1: lhs = (rhs - alpha*a*phi) + S*dxinv*beta*b
-template <int MODE, bool HAS_B>
+template <int MODE, bool HAS_B, bool MASKED>
 __global__ void __launch_bounds__(256) k_op(Geom g, BCk bc, double *__restrict__ lhs, const double *__restrict__ phi,
                                             const double *__restrict__ rhs, const double *__restrict__ a,
                                             const double *__restrict__ b, double alpha, double beta, double dxinv) {
@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(256) k_op(Geom g, BCk bc, double *__restrict__
   const int k = blockIdx.z;
   if (i >= g.nx || j >= g.ny) return;
   const long long idx = i + j * g.sy + k * g.sz;
-  if (bc.mask && !bc.mask[idx]) return;
+  if (MASKED && !bc.mask[idx]) return;
   const double c = phi[idx];
-  const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+  const Nb n = neighbours<MASKED>(phi, idx, i, j, k, g, bc, c);
   double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);
   l = l * dxinv * beta;                                  // :227 / :331  ((ldpsi*dxinv)*beta)*bCoef
   if (HAS_B) l = l * b[idx];
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_op(Geom g, BCk bc, double *__restrict__
 // zero the caller stored (VariableCoeffPoissonOperator.cpp:177).
 // (Measured alternative: 16-byte loads of the x-pairs with the outer x-neighbours by warp shuffle, 20 vector loads per
 // coarse cell instead of 72 scalar ones -- bit-identical, but slower: 0.80 vs 0.75 ms per V-cycle at 512^3.)
-template <bool HAS_B>
+template <bool HAS_B, bool MASKED>
 __global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__restrict__ resC, long long csy, long long csz,
                                                   const double *__restrict__ phi, const double *__restrict__ rhs,
                                                   const double *__restrict__ a, const double *__restrict__ b, double alpha,
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__rest
   const int J = blockIdx.y * blockDim.y + threadIdx.y;
   const int K = blockIdx.z;
   if (2 * I >= g.nx || 2 * J >= g.ny) return;
-  if (bc.mask && !bc.mask[2 * I + 2 * J * g.sy + 2 * K * g.sz]) return;   // boxes are coarsenable: all eight cells or none
+  if (MASKED && !bc.mask[2 * I + 2 * J * g.sy + 2 * K * g.sz]) return;   // boxes are coarsenable: all eight cells or none
   double acc = 0.0;
 #pragma unroll
   for (int dk = 0; dk < 2; dk++)
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) k_restrict(Geom g, BCk bc, double *__rest
         const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
         const long long idx = i + j * g.sy + k * g.sz;
         const double c = phi[idx];
-        const Nb n = neighbours(phi, idx, i, j, k, g, bc, c);
+        const Nb n = neighbours<MASKED>(phi, idx, i, j, k, g, bc, c);
         double lof = alpha * a[idx] * c;                       // :411-412
         double l = lap7(c, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp);
         l = l * dxinv * beta;                                  // :427
@@ -448,10 +448,19 @@ int gsrb_color(mgic_ctx *c, const Geom &g, const BCk &bc, double *phi, const dou
   const double dxinv = 1.0 / (dx * dx);  // :89
   dim3 blk(64, 4, 1);
   dim3 grd = grid3((g.nx + 1) / 2, g.ny, g.nz, blk);
-  if (b)
-    k_gsrb_color<true><<<grd, blk, 0, c->stream>>>(g, bc, phi, rhs, a, b, lam, alpha, beta, dxinv, color);
-  else
-    k_gsrb_color<false><<<grd, blk, 0, c->stream>>>(g, bc, phi, rhs, a, b, lam, alpha, beta, dxinv, color);
+// K<PRE..., HAS_B, MASKED><<<...>>>ARGS: the four builds of a stencil kernel (bCoef stream or not, masked AMR level or not)
+#define MGIC_UNPAREN(...) __VA_ARGS__
+#define MGIC_STENCIL_LAUNCH(K, PRE, ARGS)                                                    \
+  do {                                                                                       \
+    if (bc.mask) {                                                                           \
+      if (b) K<MGIC_UNPAREN PRE true, true><<<grd, blk, 0, c->stream>>> ARGS;                 \
+      else K<MGIC_UNPAREN PRE false, true><<<grd, blk, 0, c->stream>>> ARGS;                  \
+    } else {                                                                                 \
+      if (b) K<MGIC_UNPAREN PRE true, false><<<grd, blk, 0, c->stream>>> ARGS;                \
+      else K<MGIC_UNPAREN PRE false, false><<<grd, blk, 0, c->stream>>> ARGS;                 \
+    }                                                                                        \
+  } while (0)
+  MGIC_STENCIL_LAUNCH(k_gsrb_color, (), (g, bc, phi, rhs, a, b, lam, alpha, beta, dxinv, color));
   return post_launch(c, "gsrb_color");
 }
 
@@ -460,8 +469,7 @@ int apply_op(mgic_ctx *c, const Geom &g, const BCk &bc, double *lhs, const doubl
   const double dxinv = 1.0 / (dx * dx);
   dim3 blk(64, 4, 1);
   dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
-  if (b) k_op<0, true><<<grd, blk, 0, c->stream>>>(g, bc, lhs, phi, nullptr, a, b, alpha, beta, dxinv);
-  else k_op<0, false><<<grd, blk, 0, c->stream>>>(g, bc, lhs, phi, nullptr, a, b, alpha, beta, dxinv);
+  MGIC_STENCIL_LAUNCH(k_op, (0,), (g, bc, lhs, phi, nullptr, a, b, alpha, beta, dxinv));
   return post_launch(c, "apply_op");
 }
 
@@ -470,8 +478,7 @@ int residual(mgic_ctx *c, const Geom &g, const BCk &bc, double *res, const doubl
   const double dxinv = 1.0 / (dx * dx);
   dim3 blk(64, 4, 1);
   dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
-  if (b) k_op<1, true><<<grd, blk, 0, c->stream>>>(g, bc, res, phi, rhs, a, b, alpha, beta, dxinv);
-  else k_op<1, false><<<grd, blk, 0, c->stream>>>(g, bc, res, phi, rhs, a, b, alpha, beta, dxinv);
+  MGIC_STENCIL_LAUNCH(k_op, (1,), (g, bc, res, phi, rhs, a, b, alpha, beta, dxinv));
   return post_launch(c, "residual");
 }
 
@@ -480,8 +487,7 @@ int restrict_res(mgic_ctx *c, const Geom &g, const BCk &bc, double *resC, long l
   const double dxinv = 1.0 / (dx * dx);
   dim3 blk(32, 4, 1);
   dim3 grd = grid3(g.nx / 2, g.ny / 2, g.nz / 2, blk);
-  if (b) k_restrict<true><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
-  else k_restrict<false><<<grd, blk, 0, c->stream>>>(g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv);
+  MGIC_STENCIL_LAUNCH(k_restrict, (), (g, bc, resC, csy, csz, phi, rhs, a, b, alpha, beta, dxinv));
   return post_launch(c, "restrict");
 }
 

@@ -53,10 +53,13 @@ __device__ __forceinline__ double nb_masked(const BCk &bc, int f, bool inside, l
   return cf_homog(bc.cf, p[farIdx], c);                      // homogeneousCFInterp
 }
 
+// MASKED is a compile-time switch: the kernels of plain levels carry none of the masked branch (with a run-time test on
+// bc.mask instead, k_restrict at 512^3 went from 0.62 to 0.84 ms: profiles/r1b_ vs r2m_launches_bench_512.csv)
+template <bool MASKED = false>
 __device__ __forceinline__ Nb neighbours(const double *p, long long idx, int i, int j, int k, const Geom &g,
                                          const BCk &bc, double c) {
   Nb n;
-  if (bc.mask) {
+  if (MASKED) {
     n.xm = nb_masked(bc, 0, i > 0, idx - 1, bc.plo[0] + i == 0, c, p, idx + 1, idx);
     n.xp = nb_masked(bc, 1, i < g.nx - 1, idx + 1, bc.plo[0] + i == bc.ndom[0] - 1, c, p, idx - 1, idx);
     n.ym = nb_masked(bc, 2, j > 0, idx - g.sy, bc.plo[1] + j == 0, c, p, idx + g.sy, idx);
