@@ -621,16 +621,18 @@ static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *p
     *out = k;
     return MGIC_OK;
   }
+  double *faces[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int f = 0; f < 6; f++) {
     k.face[f] = nullptr;
     const int dir = f / 2, side = (f % 2) ? +1 : -1;
     if (!(side < 0 ? o->cfLo[dir] : o->cfHi[dir])) continue;
     const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
     if (!o->cfFace[f]) MGIC_CUDA(cudaMalloc(&o->cfFace[f], (size_t)n[ta] * n[tb] * sizeof(double)));
-    MGIC_TRY(mgk::quad_cf_face(o->ctx, o->geom(), o->plo, o->ndom, o->dx, dir, side, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfFace[f]));
     k.type[f] = MGIC_FACE_GHOST;
     k.face[f] = o->cfFace[f];
+    faces[f] = o->cfFace[f];
   }
+  MGIC_TRY(mgk::quad_cf_faces(o->ctx, o->geom(), o->plo, o->ndom, o->dx, phi->p, pc->p, pc->sy, pc->sz, clo, faces));   // all faces, one launch
   *out = k;
   return MGIC_OK;
 }
@@ -1388,6 +1390,9 @@ struct AmrNode {
   // by two cells, clipped to the coarse domain (owned); stageLo = its origin in the parent level's index space
   mgic_field *stage = nullptr;
   int stageLo[3] = {0, 0, 0};
+  // one byte per cell of this node's (local) array: 1 = a finer node covers the cell ([Chombo] zeroCovered's set) -- what the
+  // composite norms and dot products skip; null: nothing finer (owned)
+  unsigned char *covered = nullptr;
 };
 struct mgic_amr {
   mgic_ctx *ctx = nullptr;
@@ -1398,6 +1403,7 @@ struct mgic_amr {
   int nlevels() const { return (int)levelStart.size() - 1; }
 };
 
+static int amr_build_covered(mgic_amr *A);
 static int amr_fail(mgic_amr *A, const char *fmt, int a, int b) {
   mgic_set_error(fmt, a, b);
   delete A;
@@ -1509,6 +1515,7 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
       if (field_alloc(A->ctx, ns[0], ns[1], ns[2], 0, ns[2], &nd.stage) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
     }
   }
+  if (amr_build_covered(A) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
   *out = A;
   return MGIC_OK;
 }
@@ -1520,7 +1527,10 @@ extern "C" int mgic_amr_create(mgic_mg *base, int nfiner, mgic_op *const *patche
 }
 extern "C" int mgic_amr_destroy(mgic_amr *A) {
   if (!A) return MGIC_OK;
-  for (AmrNode &nd : A->nodes) { mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); mgic_field_destroy(nd.stage); }
+  for (AmrNode &nd : A->nodes) {
+    mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); mgic_field_destroy(nd.stage);
+    if (nd.covered) cudaFree(nd.covered);
+  }
   for (auto *f : A->work) mgic_field_destroy(f);
   delete A;
   return MGIC_OK;
@@ -1598,6 +1608,24 @@ static int zero_under(mgic_amr *A, const AmrNode &n, mgic_field *below) {
   const UnderLocal u = under_local(n, below);
   if (u.empty) return MGIC_OK;
   return mgk::box_set_val(A->ctx, u.g, u.ptr, 0.0, mask_at(n.op, u.fineOff), n.op->n[0], (long long)n.op->n[0] * n.op->n[1]);
+}
+
+// the `covered` marks of every node that has finer nodes above it (the cells zero_under would zero)
+static int amr_build_covered(mgic_amr *A) {
+  for (size_t q = 1; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    AmrNode &pn = A->nodes[n.parent];
+    const mgic_field *ref = pn.corr;   // any field of the parent: the geometry of its (local) array
+    if (!pn.covered) {
+      const size_t cells = (size_t)ref->sz * ref->nz;
+      MGIC_CUDA(cudaMalloc(&pn.covered, cells));
+      MGIC_CUDA(cudaMemsetAsync(pn.covered, 0, cells, A->ctx->stream));
+    }
+    const UnderLocal u = under_local(n, pn.corr);
+    if (u.empty) continue;
+    MGIC_TRY(mgk::box_set_u8(A->ctx, u.g, pn.covered + (u.ptr - ref->p), 1, mask_at(n.op, u.fineOff), n.op->n[0], (long long)n.op->n[0] * n.op->n[1]));
+  }
+  return MGIC_OK;
 }
 
 static int amr_cycle(mgic_amr *A, int l) {
@@ -1699,13 +1727,24 @@ extern "C" int mgic_amr_average_down(mgic_amr *A, mgic_field *const *x) {
   }
   return MGIC_OK;
 }
-// copy of x with the covered cells zeroed, in the nodes' tmp fields
-static int amr_masked_copy(mgic_amr *A, mgic_field *const *x) {
-  for (size_t q = 0; q < A->nodes.size(); q++) MGIC_TRY(mgic_op_assign(A->nodes[q].op, A->nodes[q].tmp, x[q]));
-  for (size_t q = 1; q < A->nodes.size(); q++) {
-    const AmrNode &n = A->nodes[q];
-    mgic_field *pt = A->nodes[n.parent].tmp;
-    MGIC_TRY(zero_under(A, n, pt));
+// kind-reduction of every node of a level vector, the cells a finer node covers counting as zero ([Chombo]
+// MultilevelLinearOp::norm / dotProduct zero them on temporaries: same bits), one launch per node into the scalar slots and
+// ONE readback for the whole hierarchy.  A z-slab-distributed node is summed over the ranks; replicated nodes are not.
+static int amr_reduce(mgic_amr *A, mgic_field *const *x, mgic_field *const *y, int kind, std::vector<double> *out) {
+  mgic_ctx *c = A->ctx;
+  const int nn = (int)A->nodes.size(), SLOTS = 64;
+  out->assign((size_t)nn, 0.0);
+  for (int q0 = 0; q0 < nn; q0 += SLOTS) {
+    const int cnt = std::min(SLOTS, nn - q0);
+    for (int q = q0; q < q0 + cnt; q++) {
+      const AmrNode &n = A->nodes[q];
+      MGIC_TRY(mgk::reduce(c, n.op->geom(), x[q]->p, y ? y[q]->p : nullptr, kind, q - q0, n.covered));
+      if (c->nranks > 1 && !n.op->isGlobal) {
+        MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm_init)");
+        MGIC_TRY(c->allreduce(c, c->d_scal + (q - q0), 1, kind == 0 ? 1 : 0));
+      }
+    }
+    MGIC_TRY(fetch_scalars(c, 0, cnt, 0, out->data() + q0, false));
   }
   return MGIC_OK;
 }
@@ -1714,13 +1753,13 @@ static int amr_masked_copy(mgic_amr *A, mgic_field *const *x) {
 extern "C" int mgic_amr_norm(mgic_amr *A, mgic_field *const *x, int ord, double *out) {
   MGIC_TRY(amr_check_vec(A, x));
   MGIC_REQUIRE(out && ord >= 0 && ord <= 2, "norm order must be 0, 1 or 2");
-  MGIC_TRY(amr_masked_copy(A, x));
+  std::vector<double> v;
+  MGIC_TRY(amr_reduce(A, x, nullptr, ord, &v));
   double acc = 0.0;
-  for (AmrNode &n : A->nodes) {
-    double v;
-    MGIC_TRY(local_reduce(n.op, n.tmp, nullptr, ord, &v));
-    if (ord == 0) acc = std::max(acc, v);
-    else acc += v * (n.op->dx * n.op->dx * n.op->dx);
+  for (size_t q = 0; q < A->nodes.size(); q++) {
+    const AmrNode &n = A->nodes[q];
+    if (ord == 0) acc = std::max(acc, v[q]);
+    else acc += v[q] * (n.op->dx * n.op->dx * n.op->dx);
   }
   *out = ord == 2 ? sqrt(acc) : acc;
   return MGIC_OK;
@@ -1730,13 +1769,12 @@ extern "C" int mgic_amr_norm(mgic_amr *A, mgic_field *const *x, int ord, double 
 extern "C" int mgic_amr_dot(mgic_amr *A, mgic_field *const *x, mgic_field *const *y, double *out) {
   MGIC_TRY(amr_check_vec(A, x)); MGIC_TRY(amr_check_vec(A, y));
   MGIC_REQUIRE(out, "NULL argument");
-  MGIC_TRY(amr_masked_copy(A, x));
+  std::vector<double> v;
+  MGIC_TRY(amr_reduce(A, x, y, 3, &v));
   double acc = 0.0;
   for (size_t q = 0; q < A->nodes.size(); q++) {
-    AmrNode &n = A->nodes[q];
-    double v;
-    MGIC_TRY(local_reduce(n.op, n.tmp, y[q], 3, &v));
-    acc += v * (n.op->dx * n.op->dx * n.op->dx);
+    const AmrNode &n = A->nodes[q];
+    acc += v[q] * (n.op->dx * n.op->dx * n.op->dx);
   }
   *out = acc;
   return MGIC_OK;

@@ -139,9 +139,8 @@ struct QcfArgs {
   int dir, side, ta, tb;  // tangential directions ta < tb
   double h;
 };
-__global__ void __launch_bounds__(256) k_quad_cf_face(QcfArgs A, const double *__restrict__ phi, const double *__restrict__ coarse,
-                                                      double *__restrict__ face) {
-  const int qa = blockIdx.x * blockDim.x + threadIdx.x, qb = blockIdx.y * blockDim.y + threadIdx.y;   // local tangential indices
+__device__ __forceinline__ void quad_cf_face_cell(const QcfArgs &A, int qa, int qb, const double *__restrict__ phi,
+                                                  const double *__restrict__ coarse, double *__restrict__ face) {
   // geometry per direction without dynamically indexed local arrays: (value for x, y, z) selected by compile-time-simple tests
   const int dir = A.dir, ta = A.ta, tb = A.tb;
   const int nA = ta == 0 ? A.g.nx : A.g.ny;                  // ta is 0 or 1
@@ -210,6 +209,20 @@ __global__ void __launch_bounds__(256) k_quad_cf_face(QcfArgs A, const double *_
   const double a = (2.0 / h / h) * ((2.0 * phistar + pa * (nref + 1.0)) - pb * (nref + 3.0)) / (nref * nref + 4.0 * nref + 3.0);
   const double b = (pb - pa) / h - a * h;
   face[qa + (long long)nA * qb] = (pa + b * x) + a * x * x;
+}
+__global__ void __launch_bounds__(256) k_quad_cf_face(QcfArgs A, const double *__restrict__ phi, const double *__restrict__ coarse,
+                                                      double *__restrict__ face) {
+  quad_cf_face_cell(A, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y, phi, coarse, face);   // local tangential indices
+}
+// every coarse-fine face of a rectangular patch in ONE launch: blockIdx.z = face (0 x-lo ... 5 z-hi), faces without a
+// coarse-fine boundary have a null array.  (Config C4 spent 2.5 of 22 ms per nonlinear iteration in 450 one-face launches.)
+struct QcfFaces { double *face[6]; };
+__global__ void __launch_bounds__(256) k_quad_cf_faces(QcfArgs A, QcfFaces F, const double *__restrict__ phi, const double *__restrict__ coarse) {
+  const int f = blockIdx.z;
+  if (!F.face[f]) return;
+  A.dir = f >> 1; A.side = (f & 1) ? +1 : -1;
+  A.ta = A.dir == 0 ? 1 : 0; A.tb = A.dir == 2 ? 1 : 2;
+  quad_cf_face_cell(A, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y, phi, coarse, F.face[f]);
 }
 
 // ---- the same interpolation for a masked AMR level (a union of boxes in one bounding-box array): one thread per cell of
@@ -355,12 +368,14 @@ __device__ __forceinline__ double block_reduce(double v, double *sh) {
 template <int KIND>
 __global__ void __launch_bounds__(256) k_reduce(long long n, const double *__restrict__ x, const double *__restrict__ y, double s,
                                                 double *__restrict__ part, unsigned int *__restrict__ count,
-                                                double *__restrict__ out) {
+                                                double *__restrict__ out, const unsigned char *__restrict__ skip) {
   __shared__ double sh[32];
   __shared__ bool last;
   double v = 0.0;
+  // skip[q] != 0: the cell counts as x = 0 (a cell a finer AMR level covers: the composite norms / dot products) -- the same
+  // bits as reducing a copy with those cells zeroed
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
-    v = red_comb<KIND>(v, red_elem<KIND>(x[q], KIND == 3 ? y[q] : 0.0, s));
+    v = red_comb<KIND>(v, red_elem<KIND>((skip && skip[q]) ? 0.0 : x[q], KIND == 3 ? y[q] : 0.0, s));
   v = block_reduce<KIND>(v, sh);
   if (threadIdx.x == 0) {
     part[blockIdx.x] = v;
@@ -411,6 +426,17 @@ __global__ void __launch_bounds__(128) k_box_set(Geom g, double *__restrict__ y,
   const int K = blockIdx.z;
   if (I >= g.nx || J >= g.ny) return;
   if (fineMask && !fineMask[2 * I + 2 * J * msy + 2 * K * msz]) return;   // ratio 2: the coarse cell is not under the fine level
+  y[I + J * g.sy + K * g.sz] = v;
+}
+
+// the same on a byte array: the "covered by a finer level" marks the composite reductions skip
+__global__ void __launch_bounds__(128) k_box_set_u8(Geom g, unsigned char *__restrict__ y, unsigned char v,
+                                                    const unsigned char *__restrict__ fineMask, long long msy, long long msz) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J = blockIdx.y * blockDim.y + threadIdx.y;
+  const int K = blockIdx.z;
+  if (I >= g.nx || J >= g.ny) return;
+  if (fineMask && !fineMask[2 * I + 2 * J * msy + 2 * K * msz]) return;
   y[I + J * g.sy + K * g.sz] = v;
 }
 
@@ -507,6 +533,25 @@ int quad_cf_face(mgic_ctx *c, const Geom &g, const int plo[3], const int ndom[3]
   return post_launch(c, "quad_cf_face");
 }
 
+int quad_cf_faces(mgic_ctx *c, const Geom &g, const int plo[3], const int ndom[3], double h, const double *phi, const double *coarse,
+                  long long csy, long long csz, const int clo[3], double *const face[6]) {
+  QcfArgs A;
+  A.g = g;
+  for (int d = 0; d < 3; d++) { A.plo[d] = plo[d]; A.cdom[d] = ndom[d] / 2; A.clo[d] = clo[d]; }
+  A.csy = csy; A.csz = csz;
+  A.dir = 0; A.side = -1; A.ta = 1; A.tb = 2;
+  A.h = h;
+  QcfFaces F;
+  bool any = false;
+  for (int f = 0; f < 6; f++) { F.face[f] = face[f]; any = any || face[f]; }
+  if (!any) return MGIC_OK;
+  const int na = g.nx > g.ny ? g.nx : g.ny, nb = g.ny > g.nz ? g.ny : g.nz;   // ta in {x, y}, tb in {y, z}
+  dim3 blk(32, 8, 1);
+  dim3 grd((na + blk.x - 1) / blk.x, (nb + blk.y - 1) / blk.y, 6);
+  k_quad_cf_faces<<<grd, blk, 0, c->stream>>>(A, F, phi, coarse);
+  return post_launch(c, "quad_cf_faces");
+}
+
 int quad_cf_masked(mgic_ctx *c, const Geom &g, const unsigned char *mask, const int plo[3], const int ndom[3], double h, const double *phi,
                    const double *coarse, long long csy, long long csz, const int clo[3], double *const face[6]) {
   QcfmArgs A;
@@ -553,7 +598,7 @@ int jacobi_update(mgic_ctx *c, const Geom &g, double *phi, const double *res, co
   EW_LAUNCH(EW_JACOBI, phi, res, lam, w, 0.0);
 }
 
-int reduce(mgic_ctx *c, const Geom &g, const double *x, const double *y, int kind, int slot) {
+int reduce(mgic_ctx *c, const Geom &g, const double *x, const double *y, int kind, int slot, const unsigned char *skip) {
   const long long n = ncells(g);
   // grid depends only on n -> summation tree (and result bits) are a function of the level size alone
   long long nb = (n + 256 * 8 - 1) / (256 * 8);
@@ -562,10 +607,10 @@ int reduce(mgic_ctx *c, const Geom &g, const double *x, const double *y, int kin
   const int grd = (int)nb;
   double *out = c->d_scal + slot;
   switch (kind) {
-    case 0: k_reduce<0><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
-    case 1: k_reduce<1><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
-    case 2: k_reduce<2><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
-    case 3: k_reduce<3><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out); break;
+    case 0: k_reduce<0><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out, skip); break;
+    case 1: k_reduce<1><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out, skip); break;
+    case 2: k_reduce<2><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out, skip); break;
+    case 3: k_reduce<3><<<grd, 256, 0, c->stream>>>(n, x, y, 0.0, c->d_part, c->d_count, out, skip); break;
     default: mgic_set_error("reduce: bad kind %d", kind); return MGIC_ERR_ARG;
   }
   return post_launch(c, "reduce");
@@ -576,7 +621,7 @@ int is_constant(mgic_ctx *c, const Geom &g, const double *x, double value, int s
   long long nb = (n + 256 * 8 - 1) / (256 * 8);
   if (nb < 1) nb = 1;
   if (nb > (long long)c->partCap) nb = (long long)c->partCap;
-  k_reduce<4><<<(int)nb, 256, 0, c->stream>>>(n, x, nullptr, value, c->d_part, c->d_count, c->d_scal + slot);
+  k_reduce<4><<<(int)nb, 256, 0, c->stream>>>(n, x, nullptr, value, c->d_part, c->d_count, c->d_scal + slot, nullptr);
   return post_launch(c, "is_constant");
 }
 
@@ -585,6 +630,13 @@ int box_set_val(mgic_ctx *c, const Geom &g, double *y, double v, const unsigned 
   dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
   k_box_set<<<grd, blk, 0, c->stream>>>(g, y, v, fineMask, msy, msz);
   return post_launch(c, "box_set_val");
+}
+
+int box_set_u8(mgic_ctx *c, const Geom &g, unsigned char *y, unsigned char v, const unsigned char *fineMask, long long msy, long long msz) {
+  dim3 blk(32, 4, 1);
+  dim3 grd = grid3(g.nx, g.ny, g.nz, blk);
+  k_box_set_u8<<<grd, blk, 0, c->stream>>>(g, y, v, fineMask, msy, msz);
+  return post_launch(c, "box_set_u8");
 }
 
 int copy_box(mgic_ctx *c, int nx, int ny, int nz, const double *src, long long ssy, long long ssz, double *dst, long long dsy, long long dsz) {

@@ -244,9 +244,13 @@ int assign(mgic_ctx *, const Geom &, double *y, const double *x);
 int set_val(mgic_ctx *, const Geom &, double *y, double v);
 int box_set_val(mgic_ctx *, const Geom &box, double *y, double v, const unsigned char *fineMask = nullptr, long long msy = 0,
                 long long msz = 0);   // sub-box of a larger array (strides box.sy / box.sz); fineMask: only under masked-in fine cells
+int box_set_u8(mgic_ctx *, const Geom &box, unsigned char *y, unsigned char v, const unsigned char *fineMask, long long msy, long long msz);
+// QuadCFInterp on every coarse-fine face of a rectangular patch in one launch (face[f] null: no coarse-fine boundary there)
+int quad_cf_faces(mgic_ctx *, const Geom &g, const int plo[3], const int ndom[3], double h, const double *phi, const double *coarse,
+                  long long csy, long long csz, const int clo[3], double *const face[6]);
 int jacobi_update(mgic_ctx *, const Geom &, double *phi, const double *res, const double *lam, double w);
 // reductions: result left in ctx->d_scal[slot]; kind 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y
-int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot);
+int reduce(mgic_ctx *, const Geom &, const double *x, const double *y, int kind, int slot, const unsigned char *skip = nullptr);
 // QuadCFInterp on one coarse-fine face (dir, side) of a patch: ghost values into `face`
 int quad_cf_face(mgic_ctx *, const Geom &g, const int plo[3], const int ndom[3], double h, int dir, int side, const double *phi,
                  const double *coarse, long long csy, long long csz, const int clo[3], double *face);
