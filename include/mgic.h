@@ -106,6 +106,13 @@ int mgic_ctx_profile(mgic_ctx *, int enable);
 int mgic_ctx_profile_read(mgic_ctx *, long long *launches, double *total_ms);
 /* same per category: 0 finest GSRB, 1 halo exchange, 2 all-gather, 3 bottom solve, 4 restrict, 5 coarser GSRB, 6 prolong */
 int mgic_ctx_profile_read_tag(mgic_ctx *, int tag, long long *launches, double *total_ms);
+/* driver allocations the library has made so far in this process (calls, seconds spent inside cudaMalloc / cudaFree).
+ * Arrays below 256 MiB are ranges of a few large chunks per device (kept until the process ends; MGIC_ARENA=0 in the
+ * environment: one cudaMalloc per array), because a B200 box pays milliseconds per cudaMalloc and a hierarchy of many small
+ * levels needs hundreds of arrays (tools/time_to_solution.py) */
+int mgic_alloc_stats(long long *alloc_calls, double *alloc_seconds, long long *free_calls, double *free_seconds);
+/* the sub-allocator's bookkeeping checked on the host alone (no device): `ops` random allocations / frees; 0 = consistent */
+int mgic_arena_selftest(unsigned seed, int ops);
 /* multi-GPU z-slab decomposition: this context is rank `rank` of `nranks` (one process per GPU);
  * peers are wired with mgic_ctx_set_peer_halo(); see mgic_comm.h */
 int mgic_ctx_set_rank(mgic_ctx *, int rank, int nranks);

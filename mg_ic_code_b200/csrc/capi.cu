@@ -4,14 +4,18 @@
 //
 // Host code here only sequences kernel launches; all field data stays in HBM.  There is no CPU compute path.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
 
 #include "mgic_internal.h"
+#include "arena.h"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -53,11 +57,11 @@ extern "C" int mgic_ctx_create(int device, mgic_ctx **out) {
   MGIC_CUDA(cudaGetDeviceProperties(&prop, device));
   c->numSMs = prop.multiProcessorCount;
   c->partCap = 4096;
-  MGIC_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+  MGIC_CUDA(mgic_dev_malloc(&c->d_scal, 64 * sizeof(double)));
   MGIC_CUDA(cudaMemset(c->d_scal, 0, 64 * sizeof(double)));
   MGIC_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
-  MGIC_CUDA(cudaMalloc(&c->d_part, c->partCap * sizeof(double)));
-  MGIC_CUDA(cudaMalloc(&c->d_count, sizeof(unsigned int)));
+  MGIC_CUDA(mgic_dev_malloc(&c->d_part, c->partCap * sizeof(double)));
+  MGIC_CUDA(mgic_dev_malloc(&c->d_count, sizeof(unsigned int)));
   MGIC_CUDA(cudaMemset(c->d_count, 0, sizeof(unsigned int)));
   *out = c;
   return MGIC_OK;
@@ -67,10 +71,10 @@ extern "C" int mgic_ctx_destroy(mgic_ctx *c) {
   if (!c) return MGIC_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_scal);
+  mgic_dev_free(c->d_scal);
   cudaFreeHost(c->h_scal);
-  cudaFree(c->d_part);
-  cudaFree(c->d_count);
+  mgic_dev_free(c->d_part);
+  mgic_dev_free(c->d_count);
   if (c->commStream) { cudaStreamDestroy(c->commStream); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin); }
   if (c->h2dStream) { cudaStreamSynchronize(c->h2dStream); cudaStreamSynchronize(c->d2hStream); cudaStreamDestroy(c->h2dStream); cudaStreamDestroy(c->d2hStream); cudaEventDestroy(c->evXfer); }
   if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -166,6 +170,127 @@ extern "C" int mgic_ctx_profile_read(mgic_ctx *c, long long *launches, double *t
 }
 
 // read back `n` device scalars starting at slot (one sync); multi-rank: all-reduced on the device first (op 0 sum, 1 max)
+// ---- device allocations of the library.  cudaMalloc / cudaFree synchronise the device and map memory: 2-9 ms per call on
+// a B200 box, and the reference's default hierarchy (7 levels, 11 arrays-of-boxes) needs about 450 arrays -- 3 of the 4.3 s
+// from set_grids to the converged nonlinear loop were spent there (tools/time_to_solution.py).  Requests below
+// ARENA_DIRECT are ranges of a few large chunks per device (arena.h; chunks are kept until the process ends), larger ones
+// and arrays that CUDA IPC has to name (multi-rank fields: `plain`) are blocks of their own.  MGIC_ARENA=0 turns it off.
+// mgic_alloc_stats counts the driver calls and the time inside them.
+static std::atomic<long long> g_allocCalls{0}, g_allocNs{0}, g_freeCalls{0}, g_freeNs{0};
+static cudaError_t timed_cuda_malloc(void **p, size_t bytes) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const cudaError_t e = cudaMalloc(p, bytes);
+  g_allocNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  g_allocCalls++;
+  return e;
+}
+static cudaError_t timed_cuda_free(void *p) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const cudaError_t e = cudaFree(p);
+  g_freeNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  g_freeCalls++;
+  return e;
+}
+namespace {
+constexpr size_t ARENA_ALIGN = 512, ARENA_DIRECT = (size_t)256 << 20, ARENA_FIRST = (size_t)256 << 20, ARENA_MAX_CHUNK = (size_t)4 << 30;
+struct DevChunk {
+  char *base;
+  RangeAllocator ra;
+  DevChunk(char *b, size_t n) : base(b), ra(n, ARENA_ALIGN) {}
+};
+struct DevArena {
+  std::vector<DevChunk *> chunks;
+  size_t next = ARENA_FIRST;
+};
+std::mutex g_arenaMu;
+std::map<int, DevArena> g_arenas;   // by device
+bool arena_on() {
+  static const bool on = [] { const char *e = getenv("MGIC_ARENA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+}  // namespace
+cudaError_t mgic_dev_malloc_(void **p, size_t bytes, bool plain) {
+  if (plain || !arena_on() || bytes >= ARENA_DIRECT) return timed_cuda_malloc(p, bytes);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_arenaMu);
+  DevArena &A = g_arenas[dev];
+  for (DevChunk *c : A.chunks) {
+    const size_t off = c->ra.take(bytes);
+    if (off != (size_t)-1) { *p = c->base + off; return cudaSuccess; }
+  }
+  size_t want = std::max(A.next, (bytes + ARENA_ALIGN) * 2);
+  want = (want + (((size_t)2 << 20) - 1)) / ((size_t)2 << 20) * ((size_t)2 << 20);
+  void *base = nullptr;
+  e = timed_cuda_malloc(&base, want);
+  if (e != cudaSuccess) {   // no room for a chunk: the request alone
+    cudaGetLastError();
+    return timed_cuda_malloc(p, bytes);
+  }
+  A.next = std::min(A.next * 2, ARENA_MAX_CHUNK);
+  DevChunk *c = new DevChunk((char *)base, want);
+  A.chunks.push_back(c);
+  c->ra.take(1);   // no array starts at the chunk's own address: CUDA IPC would take it for a block of its own (comm.cu owns_its_block)
+  *p = c->base + c->ra.take(bytes);
+  return cudaSuccess;
+}
+cudaError_t mgic_dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lk(g_arenaMu);
+    for (auto &da : g_arenas)
+      for (DevChunk *c : da.second.chunks)
+        if ((char *)p >= c->base && (char *)p < c->base + c->ra.size()) {
+          // like cudaFree: nothing in flight may still use the range when it is handed out again
+          const cudaError_t e = cudaDeviceSynchronize();
+          if (!c->ra.give((size_t)((char *)p - c->base))) return cudaErrorInvalidDevicePointer;
+          return e;
+        }
+  }
+  return timed_cuda_free(p);
+}
+// bookkeeping self-test without a device: `ops` random takes / gives on a 1 MiB range, checked against a byte map
+extern "C" int mgic_arena_selftest(unsigned seed, int ops) {
+  const size_t N = (size_t)1 << 20, AL = 512;
+  RangeAllocator ra(N, AL);
+  std::vector<unsigned char> owner(N / AL, 0);
+  std::vector<std::pair<size_t, size_t>> live;   // offset, bytes
+  unsigned long long st = seed * 2654435761ull + 12345;
+  auto rnd = [&st]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(st >> 33); };
+  for (int it = 0; it < ops; it++) {
+    if (live.empty() || rnd() % 3) {
+      const size_t bytes = 1 + rnd() % (64 * 1024);
+      const size_t off = ra.take(bytes);
+      if (off == (size_t)-1) continue;
+      if (off % AL || off + bytes > N) return 1;
+      for (size_t b = off / AL; b < (off + bytes + AL - 1) / AL; b++) {
+        if (owner[b]) return 2;   // overlap with a live range
+        owner[b] = 1;
+      }
+      live.push_back({off, bytes});
+    } else {
+      const size_t k = rnd() % live.size();
+      const size_t off = live[k].first, bytes = live[k].second;
+      if (!ra.give(off)) return 3;
+      if (ra.give(off)) return 4;   // double free must be refused
+      for (size_t b = off / AL; b < (off + bytes + AL - 1) / AL; b++) owner[b] = 0;
+      live[k] = live.back(); live.pop_back();
+    }
+  }
+  for (auto &l : live) if (!ra.give(l.first)) return 5;
+  if (ra.in_use() != 0 || ra.free_ranges() != 1) return 6;   // everything coalesced back into one range
+  if (ra.take(N) != 0) return 7;
+  return 0;
+}
+extern "C" int mgic_alloc_stats(long long *alloc_calls, double *alloc_seconds, long long *free_calls, double *free_seconds) {
+  if (alloc_calls) *alloc_calls = g_allocCalls.load();
+  if (alloc_seconds) *alloc_seconds = 1e-9 * (double)g_allocNs.load();
+  if (free_calls) *free_calls = g_freeCalls.load();
+  if (free_seconds) *free_seconds = 1e-9 * (double)g_freeNs.load();
+  return MGIC_OK;
+}
+
 static int fetch_scalars(mgic_ctx *c, int slot, int n, int op, double *out, bool collective = true) {
   if (c->nranks > 1 && collective) {
     MGIC_REQUIRE(c->allreduce, "multi-rank context without an allreduce hook (mgic_comm_init)");
@@ -219,7 +344,7 @@ BCk mgic_op::bck(bool homogeneous) const {
   return k;
 }
 
-static int field_alloc(mgic_ctx *c, int nx, int ny, int nz, int k0, int gnz, mgic_field **out) {
+static int field_alloc(mgic_ctx *c, int nx, int ny, int nz, int k0, int gnz, mgic_field **out, bool exported = true) {
   mgic_field *f = new mgic_field;
   f->ctx = c;
   f->nx = nx; f->ny = ny; f->nz = nz;
@@ -227,10 +352,12 @@ static int field_alloc(mgic_ctx *c, int nx, int ny, int nz, int k0, int gnz, mgi
   f->k0 = k0; f->gnz = gnz;
   f->bytes = (size_t)f->sz * (nz + 2 * MGIC_GZ) * sizeof(double);
   size_t alloc = f->bytes;
-  // multi-rank: arrays are exported to the z-neighbours by CUDA IPC, which names whole cudaMalloc blocks; allocations
-  // of at least 2 MiB get a block of their own
-  if (c->nranks > 1) alloc = (std::max(alloc, (size_t)1) + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
-  cudaError_t e = cudaMalloc(&f->base, alloc);
+  // multi-rank: the arrays of a z-slab level are exported to the z-neighbours by CUDA IPC, which names whole cudaMalloc
+  // blocks; allocations of at least 2 MiB get a block of their own.  Whole-level arrays (agglomerated MG depths, replicated
+  // AMR patches, staging boxes) are never exported.
+  const bool plain = c->nranks > 1 && exported;
+  if (plain) alloc = (std::max(alloc, (size_t)1) + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+  cudaError_t e = mgic_dev_malloc(&f->base, alloc, plain);
   if (e != cudaSuccess) {
     mgic_set_error("cudaMalloc(%zu bytes) failed: %s", f->bytes, cudaGetErrorString(e));
     delete f;
@@ -328,7 +455,7 @@ extern "C" int mgic_op_create_patch_boxes(mgic_ctx *c, const int n_domain[3], in
   if ((size_t)o->validCells == nx * ny * nz) { o->hmask.clear(); return MGIC_OK; }   // the union IS the bounding box: the rectangular patch
   // every masked-in cell must have a second masked-in cell inwards of each coarse-fine face (homogeneousCFInterp / QUADINTERP
   // read two interior cells): guaranteed by boxes >= 2 cells thick, checked here for unions
-  MGIC_CUDA(cudaMalloc(&o->mask, o->hmask.size()));
+  MGIC_CUDA(mgic_dev_malloc(&o->mask, o->hmask.size()));
   MGIC_CUDA(cudaMemcpyAsync(o->mask, o->hmask.data(), o->hmask.size(), cudaMemcpyHostToDevice, c->stream));
   MGIC_CUDA(cudaStreamSynchronize(c->stream));
   return MGIC_OK;
@@ -350,8 +477,8 @@ extern "C" int mgic_op_destroy(mgic_op *o) {
   if (!o) return MGIC_OK;
   mgic_field_destroy(o->lambda);
   mgic_field_destroy(o->scratch);
-  for (int f = 0; f < 6; f++) { cudaFree(o->cfFace[f]); cudaFree(o->cfCell[f]); }
-  cudaFree(o->mask);
+  for (int f = 0; f < 6; f++) { mgic_dev_free(o->cfFace[f]); mgic_dev_free(o->cfCell[f]); }
+  mgic_dev_free(o->mask);
   delete o;
   return MGIC_OK;
 }
@@ -387,7 +514,7 @@ extern "C" int mgic_op_set_alpha_beta(mgic_op *o, double alpha, double beta) {
 extern "C" int mgic_op_reset_lambda(mgic_op *o) {
   MGIC_REQUIRE(o && o->a, "operator has no coefficients (setCoefs)");
   if (!o->lambda) {
-    MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda));
+    MGIC_TRY(field_alloc(o->ctx, o->n[0], o->n[1], o->nzl, o->k0, o->n[2], &o->lambda, !o->isGlobal));
     o->lambda->zWrap = o->ctx->nranks > 1 && !o->isGlobal && o->bc_lo[2] == MGIC_BC_PERIODIC;
   }
   if (!o->lambdaDirty) return MGIC_OK;
@@ -416,7 +543,7 @@ extern "C" int mgic_op_get_lambda(mgic_op *o, mgic_field **l) {
 extern "C" int mgic_field_create(mgic_op *like, mgic_field **out) {
   MGIC_REQUIRE(like && out, "NULL argument");
   MGIC_CUDA(cudaSetDevice(like->ctx->device));
-  MGIC_TRY(field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out));
+  MGIC_TRY(field_alloc(like->ctx, like->n[0], like->n[1], like->nzl, like->k0, like->n[2], out, !like->isGlobal));
   (*out)->mask = like->mask;
   (*out)->zWrap = like->ctx->nranks > 1 && !like->isGlobal && like->bc_lo[2] == MGIC_BC_PERIODIC;
   return MGIC_OK;
@@ -425,7 +552,7 @@ extern "C" int mgic_field_destroy(mgic_field *f) {
   if (!f) return MGIC_OK;
   mgic_ctx *c = f->ctx;
   if (f->evPending) { cudaEventSynchronize(f->evPending); cudaEventDestroy(f->evPending); }
-  if (!(c && c->array_release && c->array_release(c, f->base))) cudaFree(f->base);
+  if (!(c && c->array_release && c->array_release(c, f->base))) mgic_dev_free(f->base);
   delete f;
   return MGIC_OK;
 }
@@ -614,7 +741,7 @@ static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *p
   if (o->mask) {
     const size_t cells = (size_t)n[0] * n[1] * n[2];
     for (int f = 0; f < 6; f++) {
-      if (!o->cfFace[f]) MGIC_CUDA(cudaMalloc(&o->cfFace[f], cells * sizeof(double)));
+      if (!o->cfFace[f]) MGIC_CUDA(mgic_dev_malloc(&o->cfFace[f], cells * sizeof(double)));
       k.face[f] = o->cfFace[f];
     }
     MGIC_TRY(mgk::quad_cf_masked(o->ctx, o->geom(), o->mask, o->plo, o->ndom, o->dx, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfFace));
@@ -627,7 +754,7 @@ static int quad_cf_interp(mgic_op *o, const mgic_field *phi, const mgic_field *p
     const int dir = f / 2, side = (f % 2) ? +1 : -1;
     if (!(side < 0 ? o->cfLo[dir] : o->cfHi[dir])) continue;
     const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
-    if (!o->cfFace[f]) MGIC_CUDA(cudaMalloc(&o->cfFace[f], (size_t)n[ta] * n[tb] * sizeof(double)));
+    if (!o->cfFace[f]) MGIC_CUDA(mgic_dev_malloc(&o->cfFace[f], (size_t)n[ta] * n[tb] * sizeof(double)));
     k.type[f] = MGIC_FACE_GHOST;
     k.face[f] = o->cfFace[f];
     faces[f] = o->cfFace[f];
@@ -643,7 +770,7 @@ static int quad_cf_cells(mgic_op *o, const mgic_field *phi, const mgic_field *pc
   const size_t cells = (size_t)o->n[0] * o->n[1] * o->n[2];
   BCk k = o->bck(homogeneous);
   for (int f = 0; f < 6; f++) {
-    if (!o->cfCell[f]) MGIC_CUDA(cudaMalloc(&o->cfCell[f], cells * sizeof(double)));
+    if (!o->cfCell[f]) MGIC_CUDA(mgic_dev_malloc(&o->cfCell[f], cells * sizeof(double)));
     k.face[f] = o->cfCell[f];
   }
   MGIC_TRY(mgk::quad_cf_masked(o->ctx, o->geom(), o->mask, o->plo, o->ndom, o->dx, phi->p, pc->p, pc->sy, pc->sz, clo, o->cfCell));
@@ -1098,7 +1225,7 @@ extern "C" int mgic_mg_destroy(mgic_mg *mg) {
     mgic_op_destroy(mg->locOps[d]);
   }
   for (auto &g : mg->graphs) cudaGraphExecDestroy(g.exec);
-  cudaFree(mg->d_bottomOut);
+  mgic_dev_free(mg->d_bottomOut);
   for (int d = 0; d < mg->nd; d++) {
     mgic_field_destroy(mg->e[d]); mgic_field_destroy(mg->r[d]);
     mgic_field_destroy(mg->aOwn[d]); mgic_field_destroy(mg->bOwn[d]);
@@ -1143,7 +1270,7 @@ extern "C" int mgic_mg_bottom_solve(mgic_mg *mg, mgic_field *e, const mgic_field
     // one persistent cooperative kernel (bottom.cu); iteration count stays on the device until asked for
     MGIC_TRY(mg->bottomWork.alloc(op));
     MGIC_TRY(mgic_op_reset_lambda(op));
-    if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
+    if (!mg->d_bottomOut) MGIC_CUDA(mgic_dev_malloc(&mg->d_bottomOut, 2 * sizeof(int)));
     {
       ProfScope ps(mg->ctx, false, PROF_BOTTOM);
       MGIC_TRY(mgk::bottom_bicgstab(op, e, r, mg->bottomWork.v, mg->ctx->d_part, (int)mg->ctx->partCap, mg->d_bottomOut));
@@ -1295,7 +1422,7 @@ static int vcycle_run(mgic_mg *mg, mgic_field *e, const mgic_field *r, bool eIsZ
     }
   // everything the cycle allocates lazily must exist before capture
   MGIC_TRY(mg->bottomWork.alloc(mg->ops.back()));
-  if (!mg->d_bottomOut) MGIC_CUDA(cudaMalloc(&mg->d_bottomOut, 2 * sizeof(int)));
+  if (!mg->d_bottomOut) MGIC_CUDA(mgic_dev_malloc(&mg->d_bottomOut, 2 * sizeof(int)));
   for (auto *o : mg->ops) {
     MGIC_TRY(mgic_op_reset_lambda(o));
     if (!o->scratch) MGIC_TRY(mgic_field_create(o, &o->scratch));
@@ -1512,7 +1639,7 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
         const int clo = std::max(0, (nd.op->plo[d] >> 1) - 2), chi = std::min(nd.op->ndom[d] / 2 - 1, ((nd.op->plo[d] + nd.op->n[d] - 1) >> 1) + 2);
         nd.stageLo[d] = clo; ns[d] = chi - clo + 1;
       }
-      if (field_alloc(A->ctx, ns[0], ns[1], ns[2], 0, ns[2], &nd.stage) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
+      if (field_alloc(A->ctx, ns[0], ns[1], ns[2], 0, ns[2], &nd.stage, false) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
     }
   }
   if (amr_build_covered(A) != MGIC_OK) { mgic_amr_destroy(A); return MGIC_ERR_CUDA; }
@@ -1529,7 +1656,7 @@ extern "C" int mgic_amr_destroy(mgic_amr *A) {
   if (!A) return MGIC_OK;
   for (AmrNode &nd : A->nodes) {
     mgic_field_destroy(nd.corr); mgic_field_destroy(nd.res); mgic_field_destroy(nd.tmp); mgic_field_destroy(nd.stage);
-    if (nd.covered) cudaFree(nd.covered);
+    if (nd.covered) mgic_dev_free(nd.covered);
   }
   for (auto *f : A->work) mgic_field_destroy(f);
   delete A;
@@ -1618,7 +1745,7 @@ static int amr_build_covered(mgic_amr *A) {
     const mgic_field *ref = pn.corr;   // any field of the parent: the geometry of its (local) array
     if (!pn.covered) {
       const size_t cells = (size_t)ref->sz * ref->nz;
-      MGIC_CUDA(cudaMalloc(&pn.covered, cells));
+      MGIC_CUDA(mgic_dev_malloc(&pn.covered, cells));
       MGIC_CUDA(cudaMemsetAsync(pn.covered, 0, cells, A->ctx->stream));
     }
     const UnderLocal u = under_local(n, pn.corr);
@@ -1891,7 +2018,7 @@ extern "C" int mgic_vars_create(mgic_ctx *c, const mgic_params *P, int k0, int n
   for (int d = 0; d < 3; d++) v->n[d] = P->N[d];
   v->k0 = k0; v->nzl = nzl; v->dx = P->L / P->N[0];
   v->sy = P->N[0] + 2; v->sz = v->sy * (P->N[1] + 2); v->sc = v->sz * (nzl + 2);
-  MGIC_CUDA(cudaMalloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
+  MGIC_CUDA(mgic_dev_malloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
   MGIC_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->sc * 8 * sizeof(double), c->stream));
   *out = v;
   return MGIC_OK;
@@ -1908,11 +2035,11 @@ extern "C" int mgic_vars_create_patch(mgic_ctx *c, const mgic_params *P, const m
   v->isPatch = true; v->mask = patch->mask;
   v->k0 = patch->plo[2]; v->nzl = patch->n[2]; v->dx = patch->dx;
   v->sy = v->n[0] + 2; v->sz = v->sy * (v->n[1] + 2); v->sc = v->sz * (v->nzl + 2);
-  MGIC_CUDA(cudaMalloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
+  MGIC_CUDA(mgic_dev_malloc(&v->d, (size_t)v->sc * 8 * sizeof(double)));
   MGIC_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->sc * 8 * sizeof(double), c->stream));
   const long long cells = (long long)v->n[0] * v->n[1] * v->nzl;
   for (int f = 0; f < 6; f++) {
-    MGIC_CUDA(cudaMalloc(&v->psiG[f], (size_t)cells * sizeof(double)));
+    MGIC_CUDA(mgic_dev_malloc(&v->psiG[f], (size_t)cells * sizeof(double)));
     MGIC_TRY(mgk::fill(c, v->psiG[f], cells, 1.0));
   }
   *out = v;
@@ -1920,8 +2047,8 @@ extern "C" int mgic_vars_create_patch(mgic_ctx *c, const mgic_params *P, const m
 }
 extern "C" int mgic_vars_destroy(mgic_vars *v) {
   if (!v) return MGIC_OK;
-  for (int f = 0; f < 6; f++) cudaFree(v->psiG[f]);
-  cudaFree(v->d);
+  for (int f = 0; f < 6; f++) mgic_dev_free(v->psiG[f]);
+  mgic_dev_free(v->d);
   delete v;
   return MGIC_OK;
 }
@@ -2306,9 +2433,9 @@ extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double
       const int lo[3] = {lb.b[0], lb.b[1], lb.b[2]}, n[3] = {lb.b[3] - lb.b[0] + 1, lb.b[4] - lb.b[1] + 1, lb.b[5] - lb.b[2] + 1};
       const size_t cnt = (size_t)NV * (n[0] + 2 * NG) * (n[1] + 2 * NG) * (n[2] + 2 * NG);
       if (cnt > dcap) {
-        cudaFree(dbuf);
+        mgic_dev_free(dbuf);
         dbuf = nullptr;
-        if (cudaMalloc(&dbuf, cnt * sizeof(double)) != cudaSuccess) { mgic_set_error("cudaMalloc failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }
+        if (mgic_dev_malloc(&dbuf, cnt * sizeof(double)) != cudaSuccess) { mgic_set_error("cudaMalloc failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }
         dcap = cnt;
       }
       hbuf.resize(cnt);
@@ -2318,7 +2445,7 @@ extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double
           cudaStreamSynchronize(c->stream) != cudaSuccess) { mgic_set_error("copy failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }
       if (fwrite(hbuf.data(), sizeof(double), cnt, fp) != cnt) { mgic_set_error("short write to %s", path); rc = MGIC_ERR_ARG; break; }
     }
-  cudaFree(dbuf);
+  mgic_dev_free(dbuf);
   fclose(fp);
   return rc;
 }

@@ -344,7 +344,7 @@ int register_array(mgic_ctx *c, Comm *cm, NcclApi *A, mgic_field *f) {
   cm->reg[f->base] = pa;
   // every rank has passed the destroy calls that precede this registration in program order, i.e. has unmapped the
   // arrays buried before it: their memory can go now
-  for (size_t i = 0; i < buried; i++) cudaFree(cm->graveyard[i]);
+  for (size_t i = 0; i < buried; i++) mgic_dev_free(cm->graveyard[i]);
   cm->graveyard.erase(cm->graveyard.begin(), cm->graveyard.begin() + buried);
   return MGIC_OK;
 }
@@ -439,7 +439,7 @@ extern "C" int mgic_comm_destroy(mgic_ctx *c) {
     A->AllReduce(cm->d_stage, cm->d_stage, 1, ncclChar, ncclSum, cm->comm, c->stream);
     cudaStreamSynchronize(c->stream);
   }
-  for (void *q : cm->graveyard) cudaFree(q);
+  for (void *q : cm->graveyard) mgic_dev_free(q);
   cudaFree(cm->ctl);
   cudaFree(cm->d_stage);
   if (A && cm->comm) A->CommDestroy(cm->comm);

@@ -62,6 +62,42 @@ struct Bits {
 
 inline int floordiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
 
+// One axis of a box filter over a Bits array, in place, O(cells): with grow = true a cell becomes set when a set cell lies
+// within `radius` along the axis (dilation; nothing outside the array is set); with grow = false a cell stays set only
+// if every position within `radius` along the axis is set, where positions outside the array count as set when they are
+// outside the domain [0, ndom) and as clear otherwise (erosion with "beyond the domain boundary is inside").  A cube filter
+// is the three axes one after the other.
+void filter_axis(Bits &u, int axis, int radius, bool grow, const int *ndom) {
+  const size_t st[3] = {1, (size_t)u.n[0], (size_t)u.n[0] * u.n[1]};
+  const int len = u.n[axis], a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+  if (len == 0 || radius <= 0) return;
+  std::vector<int> dist(len);
+  const int FAR = 1 << 29;
+  for (int q2 = 0; q2 < u.n[a2]; q2++)
+    for (int q1 = 0; q1 < u.n[a1]; q1++) {
+      unsigned char *row = u.v.data() + q1 * st[a1] + q2 * st[a2];
+      // distance along the row to the nearest "hit": a set cell (grow) / a clear position (shrink)
+      int last = -FAR;
+      if (!grow && u.b.lo[axis] - 1 >= 0) last = -1;                         // the position just before the array is a clear one
+      for (int x = 0; x < len; x++) {
+        const bool hit = grow ? row[x * st[axis]] != 0 : row[x * st[axis]] == 0;
+        if (hit) last = x;
+        dist[x] = x - last;
+      }
+      last = FAR;
+      if (!grow && u.b.hi[axis] + 1 <= ndom[axis] - 1) last = len;            // ... and the one just after it
+      for (int x = len - 1; x >= 0; x--) {
+        const bool hit = grow ? row[x * st[axis]] != 0 : row[x * st[axis]] == 0;
+        if (hit) last = x;
+        dist[x] = std::min(dist[x], last - x);
+      }
+      for (int x = 0; x < len; x++) {
+        if (grow) { if (dist[x] <= radius) row[x * st[axis]] = 1; }
+        else if (dist[x] <= radius) row[x * st[axis]] = 0;
+      }
+    }
+}
+
 IBox bounding(const std::vector<IBox> &boxes) {
   IBox bb = {{1 << 30, 1 << 30, 1 << 30}, {-(1 << 30), -(1 << 30), -(1 << 30)}};
   for (const IBox &q : boxes)
@@ -83,24 +119,8 @@ Bits nesting_domain(const std::vector<IBox> &boxes, const int ndom[3], int radiu
   if (boxes.empty()) { u.define({{0, 0, 0}, {-1, -1, -1}}); return u; }
   u.define(bounding(boxes));
   for (const IBox &q : boxes) u.fill(q);
-  for (int r = 0; r < radius; r++) {   // one erosion per cell of radius; outside the domain counts as inside
-    Bits e = u;
-    for (int k = u.b.lo[2]; k <= u.b.hi[2]; k++)
-      for (int j = u.b.lo[1]; j <= u.b.hi[1]; j++)
-        for (int i = u.b.lo[0]; i <= u.b.hi[0]; i++) {
-          if (!u.v[u.at(i, j, k)]) continue;
-          bool keep = true;
-          for (int dk = -1; dk <= 1 && keep; dk++)
-            for (int dj = -1; dj <= 1 && keep; dj++)
-              for (int di = -1; di <= 1 && keep; di++) {
-                const int a = i + di, bq = j + dj, c = k + dk;
-                if (a < 0 || bq < 0 || c < 0 || a >= ndom[0] || bq >= ndom[1] || c >= ndom[2]) continue;
-                keep = u.get(a, bq, c);
-              }
-          if (!keep) e.v[e.at(i, j, k)] = 0;
-        }
-    u = e;
-  }
+  // erosion by the (2 radius + 1)^3 cube, beyond the domain boundary counting as inside (= `radius` erosions by 3^3)
+  for (int axis = 0; axis < 3; axis++) filter_axis(u, axis, radius, false, ndom);
   return u;
 }
 
@@ -111,12 +131,30 @@ struct Cluster {
   int maxSize;
   std::vector<IBox> out;
 
-  bool nested(const IBox &q) const {
-    for (int k = q.lo[2]; k <= q.hi[2]; k++)
-      for (int j = q.lo[1]; j <= q.hi[1]; j++)
-        for (int i = q.lo[0]; i <= q.hi[0]; i++)
-          if (!ok->get(i, j, k)) return false;
-    return true;
+  // every cell of q is an allowed one: a box query on the summed-area table of `ok`
+  std::vector<int> sat;
+  bool nested(const IBox &q) {
+    const int n0 = ok->n[0], n1 = ok->n[1], n2 = ok->n[2];
+    for (int d = 0; d < 3; d++)
+      if (q.lo[d] < ok->b.lo[d] || q.hi[d] > ok->b.hi[d]) return false;   // cells outside the array are not allowed ones
+    const size_t s1 = (size_t)n0 + 1, s2 = s1 * ((size_t)n1 + 1);
+    if (sat.empty()) {
+      sat.assign(s2 * ((size_t)n2 + 1), 0);
+      for (int k = 0; k < n2; k++)
+        for (int j = 0; j < n1; j++) {
+          int row = 0;
+          for (int i = 0; i < n0; i++) {
+            row += ok->v[(size_t)i + (size_t)n0 * ((size_t)j + (size_t)n1 * k)] ? 1 : 0;
+            sat[(i + 1) + s1 * (j + 1) + s2 * (k + 1)] = row + sat[(i + 1) + s1 * j + s2 * (k + 1)] + sat[(i + 1) + s1 * (j + 1) + s2 * k] -
+                                                         sat[(i + 1) + s1 * j + s2 * k];
+          }
+        }
+    }
+    const int a0 = q.lo[0] - ok->b.lo[0], a1 = q.lo[1] - ok->b.lo[1], a2 = q.lo[2] - ok->b.lo[2];
+    const int b0 = q.hi[0] - ok->b.lo[0] + 1, b1 = q.hi[1] - ok->b.lo[1] + 1, b2 = q.hi[2] - ok->b.lo[2] + 1;
+    auto S = [&](int i, int j, int k) { return (long long)sat[i + s1 * j + s2 * k]; };
+    const long long cnt = S(b0, b1, b2) - S(a0, b1, b2) - S(b0, a1, b2) - S(b0, b1, a2) + S(a0, a1, b2) + S(a0, b1, a2) + S(b0, a1, a2) - S(a0, a1, a2);
+    return cnt == q.vol();
   }
   void accept(const IBox &q) {   // break up to maxSize, pieces as equal as possible
     int np[3];
@@ -332,12 +370,12 @@ int tag_level(mgic_ctx *c, mgic_grids *G, int level, std::vector<Pt> &pts) {
     const int n[3] = {pt.cells.n[0], pt.cells.n[1], pt.cells.n[2]};
     const size_t cells = pt.cells.v.size();
     double *d = nullptr;
-    MGIC_CUDA(cudaMalloc(&d, cells * sizeof(double)));
+    MGIC_CUDA(mgic_dev_malloc(&d, cells * sizeof(double)));
     int rc = mgk::condition_box(c, G->P, dx, pt.bb.lo, n, 0, d);
     pt.val.resize(cells);
     if (rc == MGIC_OK && cudaMemcpyAsync(pt.val.data(), d, cells * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = MGIC_ERR_CUDA;
     if (rc == MGIC_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = MGIC_ERR_CUDA;
-    cudaFree(d);
+    mgic_dev_free(d);
     if (rc != MGIC_OK) { mgic_set_error("regrid condition on level %d failed", level); return rc; }
     for (size_t i = 0; i < cells; i++)
       if (pt.cells.v[i]) vmax = std::max(vmax, std::fabs(pt.val[i]));   // norm(levelRhs, interval, 0), SetGrids.cpp:184
@@ -356,8 +394,9 @@ int tag_level(mgic_ctx *c, mgic_grids *G, int level, std::vector<Pt> &pts) {
         for (int i = pt.bb.lo[0]; i <= pt.bb.hi[0]; i++) {
           const size_t a = pt.cells.at(i, j, k);
           if (!pt.cells.v[a] || !(std::fabs(pt.val[a]) >= tagVal)) continue;
-          tg.fill({{i - g, j - g, k - g}, {i + g, j + g, k + g}});
+          tg.v[tg.at(i, j, k)] = 1;
         }
+  for (int axis = 0; axis < 3; axis++) filter_axis(tg, axis, g, true, ndom);   // tags.grow(tagsGrow), clipped to the domain by `all`
   pts.clear();
   for (int k = all.lo[2]; k <= all.hi[2]; k++)
     for (int j = all.lo[1]; j <= all.hi[1]; j++)

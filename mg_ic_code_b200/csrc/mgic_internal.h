@@ -219,6 +219,12 @@ struct mgic_vars {
 };
 
 // ---- kernel launchers (kernels.cu) -------------------------------------------
+// device allocations (capi.cu): ranges of a few large chunks per device unless `plain` (a cudaMalloc block of its own: what
+// CUDA IPC can name) or large; counted and timed, see mgic_alloc_stats
+cudaError_t mgic_dev_malloc_(void **p, size_t bytes, bool plain);
+template <class T> inline cudaError_t mgic_dev_malloc(T **p, size_t bytes, bool plain = false) { return mgic_dev_malloc_((void **)p, bytes, plain); }
+cudaError_t mgic_dev_free(void *p);
+
 namespace mgk {
 int gsrb_color(mgic_ctx *, const Geom &, const BCk &, double *phi, const double *rhs, const double *a, const double *b,
                const double *lam, double alpha, double beta, double dx, int color);

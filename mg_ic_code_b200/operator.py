@@ -65,6 +65,13 @@ class Context:
     def stream(self):
         return self.L.mgic_ctx_stream(self.h)
 
+    @staticmethod
+    def alloc_stats():
+        """(cudaMalloc calls, seconds inside them, cudaFree calls, seconds inside them) of the library in this process"""
+        a, f, sa, sf = C.c_longlong(), C.c_longlong(), C.c_double(), C.c_double()
+        check(lib().mgic_alloc_stats(C.byref(a), C.byref(sa), C.byref(f), C.byref(sf)))
+        return a.value, sa.value, f.value, sf.value
+
     @property
     def launch_count(self):
         return self.L.mgic_ctx_launch_count(self.h)

@@ -113,3 +113,14 @@ bh1_offset = 12.5
     p.write_text(txt.replace("harmonic", "geometric"))
     with pytest.raises(m.MgicError, match="bad coefficient_average_type"):
         m.read_params(str(p))
+
+
+def test_device_arena_bookkeeping():
+    """the sub-allocator that replaces one cudaMalloc per array (csrc/arena.h): random allocations and frees on the host alone --
+    no overlap between live ranges, double frees refused, everything coalesces back into one free range"""
+    import ctypes as C
+    from mg_ic_code_b200._capi import lib
+    L = lib()
+    L.mgic_arena_selftest.argtypes = [C.c_uint, C.c_int]
+    for seed in range(8):
+        assert L.mgic_arena_selftest(seed, 20000) == 0

@@ -108,6 +108,26 @@ def test_tags_next_to_the_level_boundary_are_clipped_to_the_nesting_domain():
     g.close()
 
 
+def test_nesting_domain_of_a_level_that_is_not_a_box():
+    """level 1 = an L-shaped union of boxes that touches two domain faces, every level-1 cell tagged, fill ratio 1: level 2 must
+    cover exactly the blocks of 4 level-1 cells that lie wholly in level 1 eroded by the 5^3 cube (nesting radius 2, beyond the
+    domain boundary counting as inside) -- the erosion is done axis by axis in grids.cu, here by scipy in one go"""
+    from scipy import ndimage
+    lvl1 = [((0, 0, 16), (31, 15, 47)), ((0, 16, 16), (15, 47, 47)), ((16, 16, 32), (31, 31, 47)), ((32, 48, 0), (63, 63, 15))]
+    l1 = raster(lvl1, 64).astype(bool)
+    t0 = l1.reshape(32, 2, 32, 2, 32, 2).any(axis=(1, 3, 5))
+    g = m.Grids.regrid(P, [lattice(32, 16), lvl1], [points(t0), points(l1)], fill_ratio=1.0)
+    assert g.levels == 3
+    assert np.array_equal(check_level(g.boxes(1), 64, 8, 16), l1)          # level 1 reproduced (its tags are its own cells)
+    l2 = check_level(g.boxes(2), 128, 8, 16)
+    under = l2.reshape(64, 2, 64, 2, 64, 2).any(axis=(1, 3, 5))
+    eroded = ndimage.binary_erosion(l1, structure=np.ones((5, 5, 5), dtype=bool), border_value=1)
+    blocks = eroded.reshape(16, 4, 16, 4, 16, 4).all(axis=(1, 3, 5))
+    expect = np.repeat(np.repeat(np.repeat(blocks, 4, axis=0), 4, axis=1), 4, axis=2)
+    assert expect.any() and np.array_equal(under, expect)
+    g.close()
+
+
 def test_finer_level_forces_its_coarser_level_to_hold_it():
     """tags only on level 1 (none on level 0 around them) still keep the new level 1 under the new level 2"""
     lvl1 = [((16, 16, 16), (47, 47, 47))]

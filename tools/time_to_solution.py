@@ -32,16 +32,21 @@ def main():
     runs = []
     for rep in range(args.repeat):
         w = {}
+        st0 = m.Context.alloc_stats()
         a = time.perf_counter()
         g = m.Grids.generate(ctx, P, 0.1, 0.5)
         ctx.sync()
         b = time.perf_counter()
         w["set_grids_s"] = b - a
+        st1 = m.Context.alloc_stats()
+        w["set_grids_alloc"] = {"mallocs": st1[0] - st0[0], "malloc_s": st1[1] - st0[1], "frees": st1[2] - st0[2], "free_s": st1[3] - st0[3]}
         H = m.Hierarchy.from_grids(ctx, P, g)
         H.set_initial_conditions()
         ctx.sync()
         c = time.perf_counter()
         w["hierarchy_and_initial_conditions_s"] = c - b
+        st2 = m.Context.alloc_stats()
+        w["hierarchy_alloc"] = {"mallocs": st2[0] - st1[0], "malloc_s": st2[1] - st1[1], "frees": st2[2] - st1[2], "free_s": st2[3] - st1[3]}
         its = []
         for it in range(args.nl):
             marks = []
@@ -50,10 +55,13 @@ def main():
                 ctx.sync()
                 marks.append((name, time.perf_counter()))
             s = time.perf_counter()
+            sa = m.Context.alloc_stats()
             nrm, nit, st = H.nl_iteration_steps(timer=timer)
             ctx.sync()
             e = time.perf_counter()
+            sb = m.Context.alloc_stats()
             its.append({"s": e - s, "dpsi_norm": nrm, "bicgstab_iterations": nit,
+                        "alloc": {"mallocs": sb[0] - sa[0], "malloc_s": round(sb[1] - sa[1], 4), "frees": sb[2] - sa[2], "free_s": round(sb[3] - sa[3], 4)},
                         "steps_ms": {x[0]: round((y[1] - x[1]) * 1e3, 3) for x, y in zip(marks, marks[1:])}})
             if nrm < P.tolerance:
                 break
