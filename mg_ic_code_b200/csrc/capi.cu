@@ -119,6 +119,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "bottom_kernel")) c->bottomKernel = (int)value;
   else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
   else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
+  else if (!strcmp(name, "fused_patch")) c->fusedPatch = (int)value;
   else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
   else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
   else if (!strcmp(name, "p2p_halo")) c->p2pHalo = (int)value;
@@ -134,6 +135,7 @@ extern "C" long long mgic_ctx_get_option(mgic_ctx *c, const char *name) {
   if (!strcmp(name, "bottom_kernel")) return c->bottomKernel;
   if (!strcmp(name, "use_graph")) return c->useGraph;
   if (!strcmp(name, "fuse_transfers")) return c->fusePR;
+  if (!strcmp(name, "fused_patch")) return c->fusedPatch;
   if (!strcmp(name, "agglo_cells")) return c->aggloCells;
   if (!strcmp(name, "overlap_halo")) return c->overlapHalo;
   if (!strcmp(name, "p2p_halo")) return c->p2pHalo;
@@ -408,7 +410,7 @@ extern "C" int mgic_op_create_patch(mgic_ctx *c, const int n_domain[3], const in
   o->isGlobal = c->nranks > 1;
   o->dxCrse = dx_coarse;
   o->cshift = (lo[0] + lo[1] + lo[2]) & 1;
-  o->smoother = 0;  // the fused sweep stages planes by TMA and has no coarse-fine ghost variant: per-colour kernel
+  o->smoother = 1;  // (the fused sweep takes rectangular patches; unions of boxes fall back to the per-colour kernel: gsrb_fused_applicable)
   for (int d = 0; d < 3; d++) {
     o->cfLo[d] = lo[d] > 0;
     o->cfHi[d] = hi[d] < n_domain[d] - 1;
@@ -1578,22 +1580,33 @@ extern "C" int mgic_amr_create_levels(mgic_mg *base, int nfiner, const int *npat
           if (li < 0 || lj < 0 || lk < 0 || li >= po->n[0] || lj >= po->n[1] || lk >= po->n[2]) return false;
           return po->hmask.empty() || po->hmask[(size_t)li + (size_t)po->n[0] * ((size_t)lj + (size_t)po->n[1] * lk)] != 0;
         };
+        // QuadCFInterp reads, around every coarse cell next to the patch, its tangential and diagonal neighbours: the whole
+        // 3 x 3 x 3 neighbourhood of the cells under the patch must be cells of the parent level (or outside the domain).
+        // The coarse footprint of the patch, grown by one cell axis by axis, is checked cell by cell.
+        const int fn[3] = {o->n[0] / 2 + 2, o->n[1] / 2 + 2, o->n[2] / 2 + 2};   // footprint array with a margin of one
+        const size_t f1 = (size_t)fn[0], f2 = (size_t)fn[0] * fn[1];
+        std::vector<unsigned char> fp(f2 * fn[2], 0), tmpv;
+        for (int k = 0; k < o->n[2]; k += 2)
+          for (int j = 0; j < o->n[1]; j += 2)
+            for (int i = 0; i < o->n[0]; i += 2)
+              if (o->hmask.empty() || o->hmask[(size_t)i + (size_t)o->n[0] * ((size_t)j + (size_t)o->n[1] * k)])
+                fp[(size_t)(i / 2 + 1) + f1 * (j / 2 + 1) + f2 * (k / 2 + 1)] = 1;
+        const size_t fst[3] = {1, f1, f2};
+        for (int ax = 0; ax < 3; ax++) {
+          tmpv = fp;
+          for (size_t q = fst[ax]; q + fst[ax] < fp.size(); q++)
+            if (tmpv[q - fst[ax]] | tmpv[q + fst[ax]]) fp[q] = 1;   // (rows do not wrap: the margin cells of a row are never set before their own axis is grown)
+        }
         bool nested = true;
-        for (int k = 0; k < o->n[2] && nested; k += 2)
-          for (int j = 0; j < o->n[1] && nested; j += 2)
-            for (int i = 0; i < o->n[0] && nested; i += 2) {
-              if (!o->hmask.empty() && !o->hmask[(size_t)i + (size_t)o->n[0] * ((size_t)j + (size_t)o->n[1] * k)]) continue;
-              const int c[3] = {(o->plo[0] + i) >> 1, (o->plo[1] + j) >> 1, (o->plo[2] + k) >> 1};
-              // QuadCFInterp reads, around every coarse cell next to the patch, its tangential and diagonal neighbours: the
-              // whole 3 x 3 x 3 neighbourhood of the cells under the patch must be cells of the parent level (or outside the domain)
-              for (int dk = -1; dk <= 1 && nested; dk++)
-                for (int dj = -1; dj <= 1 && nested; dj++)
-                  for (int di = -1; di <= 1 && nested; di++) {
-                    const int q3[3] = {c[0] + di, c[1] + dj, c[2] + dk};
-                    bool outside = false;
-                    for (int d = 0; d < 3; d++) outside = outside || q3[d] < 0 || q3[d] >= o->ndom[d] / 2;
-                    if (!outside) nested = pvalid(q3[0], q3[1], q3[2]);
-                  }
+        const int c0[3] = {(o->plo[0] >> 1) - 1, (o->plo[1] >> 1) - 1, (o->plo[2] >> 1) - 1};   // coarse index of footprint cell (0, 0, 0)
+        for (int k = 0; k < fn[2] && nested; k++)
+          for (int j = 0; j < fn[1] && nested; j++)
+            for (int i = 0; i < fn[0] && nested; i++) {
+              if (!fp[(size_t)i + f1 * j + f2 * k]) continue;
+              const int q3[3] = {c0[0] + i, c0[1] + j, c0[2] + k};
+              bool outside = false;
+              for (int d = 0; d < 3; d++) outside = outside || q3[d] < 0 || q3[d] >= o->ndom[d] / 2;
+              if (!outside) nested = pvalid(q3[0], q3[1], q3[2]);
             }
         if (!nested) return amr_fail(A, "patch %d of level %d is not properly nested in the cells of the level below (one coarse cell all around, diagonals included)", q, l);
       }
@@ -1762,8 +1775,7 @@ static int amr_cycle(mgic_amr *A, int l) {
   // ---- down
   for (int q = q0; q < q1; q++) {
     AmrNode &n = A->nodes[q];
-    MGIC_TRY(mgic_op_set_to_zero(n.op, n.corr));
-    MGIC_TRY(mgic_op_relax(n.op, n.corr, n.res, S));
+    MGIC_TRY(relax_from_zero(n.op, n.corr, n.res, S));
   }
   for (int P = A->levelStart[l - 1]; P < A->levelStart[l]; P++) MGIC_TRY(mgic_op_set_to_zero(A->nodes[P].op, A->nodes[P].corr));
   for (int q = q0; q < q1; q++) {
@@ -1784,8 +1796,7 @@ static int amr_cycle(mgic_amr *A, int l) {
     MGIC_TRY(mgk::prolong(A->ctx, n.op->geom(), n.corr->p, under_in(cs, n), cs.f->sy, cs.f->sz, n.op->mask));
     MGIC_TRY(mgic_op_amr_residual_nf(n.op, n.tmp, n.corr, cs.f, cs.lo, n.res, 1));
     MGIC_TRY(mgic_op_assign(n.op, n.res, n.tmp));
-    MGIC_TRY(mgic_op_set_to_zero(n.op, n.tmp));
-    MGIC_TRY(mgic_op_relax(n.op, n.tmp, n.res, S));
+    MGIC_TRY(relax_from_zero(n.op, n.tmp, n.res, S));
     MGIC_TRY(mgic_op_incr(n.op, n.corr, n.tmp, 1.0));
   }
   return MGIC_OK;

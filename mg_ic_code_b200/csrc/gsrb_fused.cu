@@ -112,7 +112,7 @@ __device__ __forceinline__ void sweep_wait_ge(const u64 *p, u64 v) {
 // completed through ONE mbarrier.  Threads never form a global load address.  (The coarse values used to be plain
 // global loads: three dependent-latency loads per lane and plane made that sweep 36 % slower than the plain one,
 // 1138 vs 835 us on 512^3, profiles/r1b_launches_bench_512.csv.)
-template <int TY, bool HAS_B, int MODE, bool FOLD = false>
+template <int TY, bool HAS_B, int MODE, bool FOLD = false, bool PATCH = false>
 struct Fused {
   static constexpr int RR = TY + 4, NW = TY + 2, PLANE = RW * RR, CPLANE = RW * NW, NT = 32 * NW, NCOEF = HAS_B ? 4 : 3;
   // coarse tile: TMA wants the innermost start coordinate on a 16-byte boundary, i.e. an even coarse x; (x0-2)/2 is odd, so
@@ -161,6 +161,14 @@ struct Fused {
     return v;
   }
 
+  // the ghost value beyond face f of a cell with value c whose neighbour on the opposite side is `far`: ParseBC's a*c + b, or --
+  // PATCH: a rectangular AMR patch, [Chombo] homogeneousCFInterp on a coarse-fine face -- the parabola through far, c and a
+  // zero coarse value (cf_homog, as the per-colour kernel evaluates it: `far` is of the other colour, i.e. its current value)
+  __device__ __forceinline__ double face_ghost(int f, double c, double far) const {
+    if (PATCH && A.bc.type[f] == MGIC_FACE_CF) return cf_homog(A.bc.cf, far, c);
+    return A.bc.a[f] * c + A.bc.b[f];
+  }
+
   // one plane step: red update of plane kr (pc), black update + output of plane kr-1 (pm1)
   template <int E, int U>
   __device__ __forceinline__ void step(int kr, int it, const double2 &pm2, const double2 &pm1, double2 &pc, double2 &pn) {
@@ -174,7 +182,6 @@ struct Fused {
     const double *dense = slots + SC * SLOT;
     double *redw = redbuf + (kr & 1) * NW * 32;
     const double *redr = redbuf + ((kr - 1) & 1) * NW * 32;
-    const BCk &bc = A.bc;
     double2 ca, cl, cr, cb;
     if (doRed) {
       ca = *reinterpret_cast<const double2 *>(dense + PLANE + cidx);
@@ -193,13 +200,13 @@ struct Fused {
       }
       double zm = E ? pm1.y : pm1.x, zp = E ? pn.y : pn.x;
       if (anyxy) {
-        if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
-        if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
-        if (by0) ym = bc.a[2] * c + bc.b[2];
-        if (byn) yp = bc.a[3] * c + bc.b[3];
+        if (E == 0 && bx0) xm = face_ghost(0, c, xp);
+        if (E == 1 && bxn) xp = face_ghost(1, c, xm);
+        if (by0) ym = face_ghost(2, c, yp);
+        if (byn) yp = face_ghost(3, c, ym);
       }
-      if (kr == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-      if (kr == A.g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+      if (kr == 0 && zloPhys) zm = face_ghost(4, c, zp);
+      if (kr == A.g.nz - 1 && zhiPhys) zp = face_ghost(5, c, zm);
       // lanes outside the red region / the domain compute a value nobody reads (their coefficients are zero-filled)
       const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, E ? ca.y : ca.x, HAS_B ? (E ? cb.y : cb.x) : 1.0,
                                           E ? cl.y : cl.x, E ? cr.y : cr.x, A.alpha, A.beta, A.dxinv);
@@ -215,13 +222,13 @@ struct Fused {
         double ym = redr[(w - 1) * 32 + lane], yp = redr[(w + 1) * 32 + lane];
         double zm = E ? pm2.y : pm2.x, zp = E ? pc.y : pc.x;
         if (anyxy) {
-          if (E == 0 && bx0) xm = bc.a[0] * c + bc.b[0];
-          if (E == 1 && bxn) xp = bc.a[1] * c + bc.b[1];
-          if (by0) ym = bc.a[2] * c + bc.b[2];
-          if (byn) yp = bc.a[3] * c + bc.b[3];
+          if (E == 0 && bx0) xm = face_ghost(0, c, xp);
+          if (E == 1 && bxn) xp = face_ghost(1, c, xm);
+          if (by0) ym = face_ghost(2, c, yp);
+          if (byn) yp = face_ghost(3, c, ym);
         }
-        if (kb == 0 && zloPhys) zm = bc.a[4] * c + bc.b[4];
-        if (kb == A.g.nz - 1 && zhiPhys) zp = bc.a[5] * c + bc.b[5];
+        if (kb == 0 && zloPhys) zm = face_ghost(4, c, zp);
+        if (kb == A.g.nz - 1 && zhiPhys) zp = face_ghost(5, c, zm);
         const double nv = gsrb_point<HAS_B>(c, xm, xp, ym, yp, zm, zp, sa, HAS_B ? sb : 1.0, sl, sr, A.alpha, A.beta, A.dxinv);
         const double2 o = E ? make_double2(pm1.x, nv) : make_double2(nv, pm1.y);
         *reinterpret_cast<double2 *>(outp) = o;
@@ -336,12 +343,12 @@ struct Fused {
   }
 };
 
-template <int TY, bool HAS_B, int MODE, int MINB, bool FOLD>
+template <int TY, bool HAS_B, int MODE, int MINB, bool FOLD, bool PATCH>
 __global__ void __launch_bounds__(32 * (TY + 2), MINB)
 k_gsrb_fused(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_l,
              const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
              const FusedArgs A) {
-  using F = Fused<TY, HAS_B, MODE, FOLD>;
+  using F = Fused<TY, HAS_B, MODE, FOLD, PATCH>;
   static_assert(F::PLANE_BYTES % 128 == 0 && F::CPLANE_BYTES % 128 == 0 && F::CTILE_BYTES % 128 == 0,
                 "TMA destinations must stay 128-byte aligned");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -406,7 +413,9 @@ int launch_cfg(mgic_op *o, const double *in, double *outp, const mgic_field *r, 
   mgic_ctx *c = o->ctx;
   // two builds of the kernel: the plain one (one rank, or halos exchanged by k_halo_push) and the one that stores its
   // boundary planes into the neighbours' ghost planes itself -- the plain one carries none of the other's instructions
-  auto kern = sw.ctl ? k_gsrb_fused<TY, HAS_B, MODE, MINB, true> : k_gsrb_fused<TY, HAS_B, MODE, MINB, false>;
+  // ... and a third for rectangular AMR patches (coarse-fine faces by homogeneousCFInterp; patches are never z-slabs)
+  auto kern = o->isPatch ? k_gsrb_fused<TY, HAS_B, MODE, MINB, false, true>
+                         : (sw.ctl ? k_gsrb_fused<TY, HAS_B, MODE, MINB, true, false> : k_gsrb_fused<TY, HAS_B, MODE, MINB, false, false>);
   int &resident = *mgic_dev_cache(c->device, (const void *)kern, 0, 0);   // per device: the opt-in and the occupancy
   if (!resident) {
     MGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM));
@@ -483,7 +492,9 @@ namespace mgk {
 // Periodic faces (TMA cannot wrap), odd nx and small (launch-latency bound) levels use the per-colour kernel, which
 // computes the same bits.
 bool gsrb_fused_applicable(const mgic_op *o) {
-  if (o->isPatch) return false;  // coarse-fine ghosts need the second interior cell: per-colour kernel
+  // an AMR level that is one box: its coarse-fine ghosts are a function of the two cells inside the face, which the sweep has at
+  // hand (the opposite neighbour); a union of boxes (masked level) has such faces anywhere inside its array: per-colour kernel
+  if (o->isPatch && (o->mask || !o->ctx->fusedPatch)) return false;
   for (int d = 0; d < 3; d++)
     if (o->bc_lo[d] == MGIC_BC_PERIODIC) return false;
   const long long cells = (long long)o->n[0] * o->n[1] * o->nzl;

@@ -131,6 +131,7 @@ struct mgic_ctx {
                                           // 2 one kernel in a thread-block cluster, 3 same as a cooperative grid (bottom.cu);
                                           // 0 host-driven launches
   int lastBottomKernel = -1;               // which bottom solver ran last: 0 host, 1 dsmem, 2 cluster, 3 coop, 4 brick, 5 cluster bricks
+  int fusedPatch = 1;                     // 1: rectangular AMR patches are swept by the fused kernel too (coarse-fine faces by homogeneousCFInterp in the sweep)
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph

@@ -115,6 +115,36 @@ class C4:
         return [a if f is None else a * f for a, f in zip(out, self.ob.fmask)]   # nothing outside a level's boxes
 
 
+def test_proper_nesting_is_enforced(ctx):
+    """a finer node needs one cell of its parent level all around the cells under it, diagonals included (QuadCFInterp's
+    stencils): a level-2 patch flush with a face of level 1, or with only an edge neighbour missing, is refused"""
+    base = C4(ctx)
+    N, L = 32, 100.0
+
+    def patch(dims, lo, hi, dx):
+        op = m.VariableCoeffPoissonOperator.patch(ctx, (dims,) * 3, lo, hi, dx)
+        a = op.create()
+        a.upload(np.ones(a.shape))
+        op.setCoefs(a, a, 1.0, -1.0)
+        return op, a
+    l1, keep1 = patch(2 * N, (16, 16, 16), (47, 47, 47), L / N / 2)
+    ok, keep2 = patch(4 * N, (34, 40, 40), (65, 71, 71), L / N / 4)               # level-1 cells 17..32: one cell inside the face x = 16
+    assert m.AMRHierarchy(base.f, [[l1], [ok]]).nodes == 3
+    flush, keep3 = patch(4 * N, (32, 40, 40), (63, 71, 71), L / N / 4)            # level-1 cells 16..31: flush with the face
+    with pytest.raises(m.MgicError, match="properly nested"):
+        m.AMRHierarchy(base.f, [[l1], [flush]])
+    # an L-shaped level 1 (two boxes in one node) and a level-2 patch in the corner of the L whose diagonal neighbour is missing
+    lshape = m.VariableCoeffPoissonOperator.patch_boxes(ctx, (2 * N,) * 3, [((16, 16, 16), (47, 31, 47)), ((16, 32, 16), (31, 47, 47))], L / N / 2)
+    al = lshape.create()
+    al.upload(np.ones(al.shape))
+    lshape.setCoefs(al, al, 1.0, -1.0)
+    corner, keep4 = patch(4 * N, (34, 34, 40), (61, 61, 71), L / N / 4)           # level-1 cells 17..30 in x and y: the cell (31, 31) is there, (32, 32) is not
+    edge, keep5 = patch(4 * N, (34, 34, 40), (63, 63, 71), L / N / 4)             # level-1 cells 17..31: needs (32, 32), the hole of the L
+    assert m.AMRHierarchy(base.f, [[lshape], [corner]]).nodes == 3
+    with pytest.raises(m.MgicError, match="properly nested"):
+        m.AMRHierarchy(base.f, [[lshape], [edge]])
+
+
 @pytest.fixture(scope="module", params=["c4", "touching_boxes"])
 def c4(ctx, request):
     """config C4's shape with rectangular nodes, and the same three levels with nodes that are unions of touching boxes"""

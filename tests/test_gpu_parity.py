@@ -568,6 +568,25 @@ def test_amr_patch_level_homogeneous_cf(ctx, name, with_b):
     assert np.array_equal(RC.download(), P.restrict())
     P.precond(); op.preCond(E, R)
     assert np.array_equal(E.download(), P.get("E"))
+    # the same sweeps by the fused red+black kernel (rectangular patches: homogeneousCFInterp inside the sweep; by default
+    # only levels of >= fused_min_cells cells take it)
+    launches = ctx.launch_count
+    keep = ctx.get_option("fused_min_cells")
+    ctx.set_option("fused_min_cells", 0)
+    try:
+        P.relax(3); op.relax(E, R, 3)
+        assert ctx.launch_count - launches == 3, "three fused sweeps expected"
+        assert np.array_equal(E.download(), P.get("E"))
+        P.precond(); op.preCond(E, R)
+        assert np.array_equal(E.download(), P.get("E"))
+        ctx.set_option("fused_patch", 0)
+        launches = ctx.launch_count
+        P.relax(1); op.relax(E, R, 1)
+        assert ctx.launch_count - launches == 2, "fused_patch = 0: one launch per colour"
+        assert np.array_equal(E.download(), P.get("E"))
+    finally:
+        ctx.set_option("fused_min_cells", keep)
+        ctx.set_option("fused_patch", 1)
     with pytest.raises(m.MgicError, match="QuadCFInterp"):
         op.residual(A, E, R, True)
     with pytest.raises(m.MgicError, match="QuadCFInterp"):
