@@ -337,7 +337,9 @@ int mgic_hier_nl_solve(mgic_hier *, double *dpsi_norms, int max_out, int *nl_ite
 /* replaces: output_final_data + set_output_data (Source/WriteOutput.H:127-227, Source/SetLevelData.cpp:343-396): the GRChombo
  * checkpoint (32 variables, three ghost layers per box, header / per-level attributes as the reference sets them).  No HDF5
  * in this build: a self-describing container ("MGICCHK1" + JSON header + the doubles in Chombo's dataset order) that
- * tools/mgic2hdf5.py converts to vcPoissonFinal.3d.hdf5. */
+ * tools/mgic2hdf5.py converts to vcPoissonFinal.3d.hdf5.  Multi-rank context: collective -- psi of the z-slab-distributed
+ * base level is gathered (the boxes' ghost layers reach into the neighbours' planes), rank 0 writes `path`, the others write
+ * nothing. */
 int mgic_hier_write_checkpoint(mgic_hier *, const char *path, double constant_K);
 /* what: 0..7 multigrid_vars component (0 = psi, MultigridUserVariables.hpp), 8 dpsi, 9 rhs, 10 aCoef; bounding-box shaped */
 int mgic_hier_download(const mgic_hier *, int node, int what, double *host);

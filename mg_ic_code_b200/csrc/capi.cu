@@ -2380,9 +2380,38 @@ extern "C" int mgic_hier_nl_iteration(mgic_hier *H, double *dpsi_norm, int *solv
 // tools/mgic2hdf5.py turns into vcPoissonFinal.3d.hdf5 (dataset for dataset) wherever h5py exists.
 extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double constant_K) {
   MGIC_REQUIRE(H && path, "NULL argument");
-  MGIC_REQUIRE(H->ctx->nranks == 1, "the checkpoint writer runs on a single-rank context");
   mgic_ctx *c = H->ctx;
   const int NV = 32, NG = 3;
+  // multi-rank: the base level lives in z-slabs, its boxes' three ghost layers reach into the neighbours' planes.  psi of the
+  // whole base level is gathered on every rank (interior planes by one all-gather, the two physical z-ghost planes from the
+  // first / last rank) into a whole-level multigrid_vars whose other components are the analytic initial data; rank 0 writes
+  // the file, the refined levels are replicated anyway.  Collective: every rank calls, only rank 0 touches `path`.
+  mgic_vars *whole = nullptr;
+  struct WholeGuard { mgic_vars *&v; ~WholeGuard() { mgic_vars_destroy(v); } } wholeGuard{whole};
+  if (c->nranks > 1) {
+    MGIC_REQUIRE(c->allgather, "multi-rank hierarchy without the communication hooks (mgic_comm_init)");
+    const mgic_vars *v0 = H->nodes[0].vars;
+    MGIC_REQUIRE(v0->nzl * c->nranks == H->P.N[2] && v0->k0 == c->rank * v0->nzl, "the base level is not cut into equal z-slabs");
+    MGIC_TRY(mgic_vars_create(c, &H->P, 0, H->P.N[2], &whole));
+    MGIC_TRY(mgk::init_conditions(whole));
+    const size_t plane = (size_t)v0->sz;
+    MGIC_TRY(c->allgather(c, v0->d + plane, whole->d + plane, plane * v0->nzl));          // psi is component 0; padded planes 1 .. nzl
+    double *ends = nullptr;
+    MGIC_CUDA(mgic_dev_malloc(&ends, (size_t)(c->nranks + 1) * 2 * plane * sizeof(double)));
+    cudaError_t e1 = cudaMemcpyAsync(ends, v0->d, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    cudaError_t e2 = cudaMemcpyAsync(ends + plane, v0->d + plane * (v0->nzl + 1), plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? c->allgather(c, ends, ends + 2 * plane, 2 * plane) : MGIC_ERR_CUDA;
+    if (rc == MGIC_OK) {
+      const double *all = ends + 2 * plane;
+      e1 = cudaMemcpyAsync(whole->d, all, plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);                                 // rank 0's plane below the domain
+      e2 = cudaMemcpyAsync(whole->d + plane * (H->P.N[2] + 1), all + (size_t)(c->nranks - 1) * 2 * plane + plane, plane * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream);                                                                       // the last rank's plane above it
+      if (e1 != cudaSuccess || e2 != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = MGIC_ERR_CUDA;
+    }
+    mgic_dev_free(ends);
+    if (rc != MGIC_OK) { mgic_set_error("gathering the base level for the checkpoint failed"); return rc; }
+    if (c->rank != 0) return MGIC_OK;
+  }
   static const char *names[32] = {"chi", "h11", "h12", "h13", "h22", "h23", "h33", "K", "A11", "A12", "A13", "A22", "A23", "A33", "Theta",
                                   "Gamma1", "Gamma2", "Gamma3", "lapse", "shift1", "shift2", "shift3", "B1", "B2", "B3", "phi", "Pi", "Ham",
                                   "Mom1", "Mom2", "Mom3", nullptr};
@@ -2450,7 +2479,7 @@ extern "C" int mgic_hier_write_checkpoint(mgic_hier *H, const char *path, double
         dcap = cnt;
       }
       hbuf.resize(cnt);
-      rc = mgk::output_box(H->nodes[lb.node].vars, lo, n, NG, constant_K, dbuf);
+      rc = mgk::output_box((lb.node == 0 && whole) ? whole : H->nodes[lb.node].vars, lo, n, NG, constant_K, dbuf);
       if (rc != MGIC_OK) break;
       if (cudaMemcpyAsync(hbuf.data(), dbuf, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
           cudaStreamSynchronize(c->stream) != cudaSuccess) { mgic_set_error("copy failed in the checkpoint writer"); rc = MGIC_ERR_CUDA; break; }

@@ -3,9 +3,12 @@ base level cut into z-slabs over the ranks and the refined levels replicated, ag
 
 Every rank also runs the whole problem on its own GPU with a single-rank context.  Checked: dpsi norms of three nonlinear
 iterations, BiCGStab iteration counts, psi on every node to 1e-10 relative in max-norm (the base level's reductions are summed in
-a different order across ranks; everything else is the same arithmetic)."""
+a different order across ranks; everything else is the same arithmetic), and the GRChombo checkpoint rank 0 writes from the
+distributed hierarchy (the base level gathered for it) against the one-GPU file: same header, data to 1e-10."""
+import json
 import os
 import sys
+import tempfile
 
 import numpy as np
 import torch
@@ -28,27 +31,38 @@ l1, l2 = c4_boxes(n)
 levels = [[l1], [b for b in l2]]
 
 
-def run(c):
+tmp = tempfile.mkdtemp(prefix="mgic_chk_")
+
+
+def run(c, chk):
     H = m.Hierarchy(c, P, levels)
     H.set_initial_conditions()
     rows = [H.nl_iteration() for _ in range(3)]
     psi = [H.download(q, "psi") for q in range(H.nodes)]
+    H.write_checkpoint(chk)          # collective on a multi-rank context; rank 0 writes
     H.close()
     return rows, psi
 
 
-rows_m, psi_m = run(ctx)
+rows_m, psi_m = run(ctx, os.path.join(tmp, "ranks.mgic"))
 t = torch.from_numpy(psi_m[0]).cuda()          # node 0: each rank filled its own planes of the global array
 dist.all_reduce(t)
 psi_m[0] = t.cpu().numpy()
 c1 = m.Context(local)
-rows_1, psi_1 = run(c1)
+rows_1, psi_1 = run(c1, os.path.join(tmp, f"one_{rank}.mgic"))
 ok = True
 for a, b in zip(rows_m, rows_1):
     ok &= a[1:] == b[1:] and abs(a[0] - b[0]) <= 1e-9 * b[0]
 errs = [float(np.abs(x - y).max() / np.abs(y).max()) for x, y in zip(psi_m, psi_1)]
 ok &= all(e < 1e-10 for e in errs)
 if rank == 0:
+    from mg_ic_code_b200 import checkpoint
+    ha, da = checkpoint.read(os.path.join(tmp, "ranks.mgic"))
+    hb, db = checkpoint.read(os.path.join(tmp, "one_0.mgic"))
+    same_header = json.dumps(ha, sort_keys=True) == json.dumps(hb, sort_keys=True)
+    chk_err = max(float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)) for la, lb in zip(da, db) for x, y in zip(la, lb))
+    print("checkpoint written from the ranks vs one GPU: header", "equal" if same_header else "DIFFERENT", "data rel err", chk_err)
+    ok &= same_header and chk_err < 1e-10
     print("nonlinear iterations (dpsi norm, BiCGStab iterations, status):", rows_m, "one GPU:", rows_1)
     print("psi per node, relative max-norm difference to one GPU:", errs)
 flag = torch.tensor([int(ok)], device="cuda")
