@@ -113,6 +113,13 @@ int mgic_ctx_profile_read_tag(mgic_ctx *, int tag, long long *launches, double *
  * environment: one cudaMalloc per array), because a B200 box pays milliseconds per cudaMalloc and a hierarchy of many small
  * levels needs hundreds of arrays (tools/time_to_solution.py) */
 int mgic_alloc_stats(long long *alloc_calls, double *alloc_seconds, long long *free_calls, double *free_seconds);
+/* MGIC_ARENA_GUARD=<bytes> in the environment puts that many bytes of 0xA5 in front of and behind every array (except the
+ * IPC-exported fields of multi-rank z-slab levels); they are checked when an array is freed and here, for every live array.
+ * *violations = arrays found with a damaged band so far in this process (each is also reported on stderr). */
+int mgic_arena_guard_check(long long *violations, long long *arrays_checked);
+/* overruns and underruns a scratch array by one byte on purpose: 0 = both were detected (and taken off the count again),
+ * 1 = no bands configured, 2 = missed */
+int mgic_arena_guard_selftest(int device);
 /* the sub-allocator's bookkeeping checked on the host alone (no device): `ops` random allocations / frees; 0 = consistent */
 int mgic_arena_selftest(unsigned seed, int ops);
 /* multi-GPU z-slab decomposition: this context is rank `rank` of `nranks` (one process per GPU);

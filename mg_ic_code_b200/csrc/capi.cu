@@ -211,7 +211,7 @@ bool arena_on() {
   return on;
 }
 }  // namespace
-cudaError_t mgic_dev_malloc_(void **p, size_t bytes, bool plain) {
+static cudaError_t raw_dev_malloc(void **p, size_t bytes, bool plain) {
   if (plain || !arena_on() || bytes >= ARENA_DIRECT) return timed_cuda_malloc(p, bytes);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -237,7 +237,7 @@ cudaError_t mgic_dev_malloc_(void **p, size_t bytes, bool plain) {
   *p = c->base + c->ra.take(bytes);
   return cudaSuccess;
 }
-cudaError_t mgic_dev_free(void *p) {
+static cudaError_t raw_dev_free(void *p) {
   if (!p) return cudaSuccess;
   {
     std::lock_guard<std::mutex> lk(g_arenaMu);
@@ -251,6 +251,100 @@ cudaError_t mgic_dev_free(void *p) {
         }
   }
   return timed_cuda_free(p);
+}
+// ---- guard bands (MGIC_ARENA_GUARD=<bytes> in the environment; the GPU test suite sets it): every array gets that many bytes
+// of 0xA5 in front of it and behind it, checked when the array is freed and by mgic_arena_guard_check -- a write past either
+// end of an array shows up as a violation instead of as a wrong number in some other array.  (compute-sanitizer is not
+// available on the GPU pool.)  Arrays exported by CUDA IPC keep their own block and carry no bands.
+namespace {
+size_t guard_bytes() {
+  static const size_t g = [] {
+    const char *e = getenv("MGIC_ARENA_GUARD");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (size_t)((v + 511) / 512 * 512) : (size_t)0;
+  }();
+  return g;
+}
+std::mutex g_guardMu;
+std::map<void *, size_t> g_guarded;   // user pointer -> bytes
+std::atomic<long long> g_guardViolations{0};
+bool guard_intact(char *user, size_t bytes, const char *when) {
+  const size_t G = guard_bytes();
+  std::vector<unsigned char> h(2 * G);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(h.data(), user - G, G, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(h.data() + G, user + bytes, G, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return true;   // cannot tell (the device is in an error state: the caller sees that elsewhere)
+  }
+  for (size_t i = 0; i < 2 * G; i++)
+    if (h[i] != 0xA5) {
+      g_guardViolations++;
+      fprintf(stderr, "mgic: guard band violated (%s): array of %zu bytes, byte %lld %s it\n", when, bytes,
+              i < G ? (long long)(G - i) : (long long)(i - G), i < G ? "before" : "after the end of");
+      return false;
+    }
+  return true;
+}
+}  // namespace
+cudaError_t mgic_dev_malloc_(void **p, size_t bytes, bool plain) {
+  const size_t G = guard_bytes();
+  if (!G || plain) return raw_dev_malloc(p, bytes, plain);
+  void *raw = nullptr;
+  cudaError_t e = raw_dev_malloc(&raw, bytes + 2 * G, false);
+  if (e != cudaSuccess) return e;
+  char *user = (char *)raw + G;
+  if ((e = cudaMemset(raw, 0xA5, G)) != cudaSuccess || (e = cudaMemset(user + bytes, 0xA5, G)) != cudaSuccess) return e;
+  cudaDeviceSynchronize();
+  {
+    std::lock_guard<std::mutex> lk(g_guardMu);
+    g_guarded[user] = bytes;
+  }
+  *p = user;
+  return cudaSuccess;
+}
+cudaError_t mgic_dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  size_t bytes = 0;
+  bool guarded = false;
+  {
+    std::lock_guard<std::mutex> lk(g_guardMu);
+    auto it = g_guarded.find(p);
+    if (it != g_guarded.end()) { guarded = true; bytes = it->second; g_guarded.erase(it); }
+  }
+  if (!guarded) return raw_dev_free(p);
+  guard_intact((char *)p, bytes, "at free");
+  return raw_dev_free((char *)p - guard_bytes());
+}
+// checks the bands of every live array now; *violations = all violations seen so far in this process (0 bands: always 0)
+extern "C" int mgic_arena_guard_check(long long *violations, long long *arrays_checked) {
+  std::vector<std::pair<void *, size_t>> live;
+  {
+    std::lock_guard<std::mutex> lk(g_guardMu);
+    live.assign(g_guarded.begin(), g_guarded.end());
+  }
+  for (auto &l : live) guard_intact((char *)l.first, l.second, "mgic_arena_guard_check");
+  if (violations) *violations = g_guardViolations.load();
+  if (arrays_checked) *arrays_checked = (long long)live.size();
+  return MGIC_OK;
+}
+// the bands do their job: an array is overrun by one byte on purpose (and underrun), both must be seen; the two violations are
+// taken off the process's count again.  0 = detected; 1 = no bands configured; 2 = missed
+extern "C" int mgic_arena_guard_selftest(int device) {
+  if (!guard_bytes()) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) { mgic_set_error("no CUDA device"); return MGIC_ERR_NO_DEVICE; }
+  int seen = 0;
+  for (int side = 0; side < 2; side++) {
+    char *a = nullptr;
+    const size_t bytes = 1000;
+    if (mgic_dev_malloc(&a, bytes) != cudaSuccess) return MGIC_ERR_CUDA;
+    cudaMemset(side ? a - 1 : a + bytes, 0, 1);
+    const long long before = g_guardViolations.load();
+    fprintf(stderr, "mgic: (self-test: the next guard-band report is provoked)\n");
+    mgic_dev_free(a);
+    if (g_guardViolations.load() == before + 1) { seen++; g_guardViolations--; }
+  }
+  return seen == 2 ? 0 : 2;
 }
 // bookkeeping self-test without a device: `ops` random takes / gives on a 1 MiB range, checked against a byte map
 extern "C" int mgic_arena_selftest(unsigned seed, int ops) {

@@ -72,6 +72,14 @@ class Context:
         check(lib().mgic_alloc_stats(C.byref(a), C.byref(sa), C.byref(f), C.byref(sf)))
         return a.value, sa.value, f.value, sf.value
 
+    @staticmethod
+    def guard_check():
+        """(arrays found with a damaged guard band so far in this process, live arrays checked now); bands exist when
+        MGIC_ARENA_GUARD=<bytes> is in the environment (the GPU test suite sets it)"""
+        v, n = C.c_longlong(), C.c_longlong()
+        check(lib().mgic_arena_guard_check(C.byref(v), C.byref(n)))
+        return v.value, n.value
+
     @property
     def launch_count(self):
         return self.L.mgic_ctx_launch_count(self.h)

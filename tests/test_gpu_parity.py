@@ -849,3 +849,16 @@ def test_amr_vcycle_library_entry_three_levels(ctx):
     for l in range(3):
         assert np.array_equal(Cout[l].download(), want[l]), l
     amr.close()
+
+
+@pytest.mark.gpu
+def test_guard_bands_detect_an_overrun(ctx):
+    """the device arrays of this test session carry guard bands (tests/conftest.py: MGIC_ARENA_GUARD); a one-byte overrun and a
+    one-byte underrun provoked on a scratch array are both reported, and nothing else has been so far"""
+    import ctypes as C
+    from mg_ic_code_b200._capi import lib
+    L = lib()
+    L.mgic_arena_guard_selftest.argtypes = [C.c_int]
+    assert L.mgic_arena_guard_selftest(0) == 0
+    violations, live = m.Context.guard_check()
+    assert violations == 0 and live > 0

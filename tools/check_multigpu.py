@@ -143,9 +143,14 @@ if rank == 0:
     ok &= same
     print("halo exchanges (peer stores, nccl, peer mapping available): before the nccl pass", stats_p2p, "after", stats_all)
     ok &= stats_all[1] > 0 and (not stats_all[2] or (stats_p2p[0] > 0 and stats_p2p[1] == 0))
-    print("MULTIGPU CHECK", "PASSED" if ok else "FAILED", f"({world} ranks, {n}^3, halo bytes sent by rank 0: {comm.halo_bytes(ctx)})")
+viol, _ = m.Context.guard_check()   # guard bands around the device arrays (MGIC_ARENA_GUARD, set by the test suite): none damaged
+if viol:
+    print(f"rank {rank}: {viol} arrays with damaged guard bands")
+ok = bool(ok) and viol == 0
 flag = torch.tensor([int(ok)], device="cuda")
-dist.broadcast(flag, 0)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTIGPU CHECK", "PASSED" if flag.item() else "FAILED", f"({world} ranks, {n}^3, halo bytes sent by rank 0: {comm.halo_bytes(ctx)})")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

@@ -65,6 +65,10 @@ if rank == 0:
     ok &= same_header and chk_err < 1e-10
     print("nonlinear iterations (dpsi norm, BiCGStab iterations, status):", rows_m, "one GPU:", rows_1)
     print("psi per node, relative max-norm difference to one GPU:", errs)
+viol, _ = m.Context.guard_check()   # guard bands around the device arrays (MGIC_ARENA_GUARD, set by the test suite): none damaged
+if viol:
+    print(f"rank {rank}: {viol} arrays with damaged guard bands")
+ok = bool(ok) and viol == 0
 flag = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -84,9 +84,14 @@ if rank == 0:
         ok &= err < 1e-6
     print("halo exchanges (peer stores, nccl, peer mapping available):", stats)
     ok &= stats[1] > 0 and (not stats[2] or stats[0] > 0)
-    print("MULTIGPU PERIODIC CHECK", "PASSED" if ok else "FAILED", f"({world} ranks, {n}^3)")
+viol, _ = m.Context.guard_check()   # guard bands around the device arrays (MGIC_ARENA_GUARD, set by the test suite): none damaged
+if viol:
+    print(f"rank {rank}: {viol} arrays with damaged guard bands")
+ok = bool(ok) and viol == 0
 flag = torch.tensor([int(ok)], device="cuda")
-dist.broadcast(flag, 0)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTIGPU PERIODIC CHECK", "PASSED" if flag.item() else "FAILED", f"({world} ranks, {n}^3)")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
