@@ -84,8 +84,12 @@ static cudaError_t raw_dev_free(void *p) {
     for (auto &da : g_arenas)
       for (DevChunk *c : da.second.chunks)
         if ((char *)p >= c->base && (char *)p < c->base + c->ra.size()) {
-          // like cudaFree: nothing in flight may still use the range when it is handed out again
+          // like cudaFree: nothing in flight on the chunk's device may still use the range when it is handed out again
+          int cur = da.first;
+          cudaGetDevice(&cur);
+          if (cur != da.first) cudaSetDevice(da.first);
           const cudaError_t e = cudaDeviceSynchronize();
+          if (cur != da.first) cudaSetDevice(cur);
           if (!c->ra.give((size_t)((char *)p - c->base))) return cudaErrorInvalidDevicePointer;
           return e;
         }
