@@ -286,3 +286,46 @@ def test_nonlinear_solve_on_a_hierarchy(ctx, boxes):
     H2 = m.Hierarchy(ctx, P, levels)
     assert np.allclose(H2.nl_solve(), got, rtol=1e-12)
     H.close(); H2.close()
+
+
+def test_config_c4_at_its_full_size(ctx):
+    """BASELINE config C4 as named -- 256^3 base, level 1 = 224 x 128 x 128 around both punctures, two 64^3 level-2 boxes
+    (tools/bench_amr.py's hierarchy, 20.4 M composite cells) -- two nonlinear iterations against the oracle-backed twin at the
+    same size: BiCGStab iteration counts, dpsi norms to 1e-7, psi on every node to 1e-10.  At this size level 1 is swept by the
+    fused kernel's PATCH build and the base level by its plain build (>= fused_min_cells cells), which the small hierarchies
+    above never reach.  About a minute of CPU for the twin."""
+    from oracle import use_all_host_cores
+    from tools.bench_amr import c4_boxes
+    use_all_host_cores()
+    n = 256
+    l1, l2 = c4_boxes(n)
+    boxes = {1: [l1], 2: [b for b in l2]}
+    o, patches = bare_hierarchy(boxes, N=n, box=32)
+    log = []
+    norms_o, psi_o = hierarchy_nl_solve(o, patches, max_nl=2, log=log)
+    P = m.make_params(dict(o.params, max_NL_iterations=2))
+    H = m.Hierarchy(ctx, P, [[l1], [b for b in l2]])
+    assert [H.node_info(q)[3] for q in range(H.nodes)] == [256 ** 3, 224 * 128 * 128, 64 ** 3, 64 ** 3]
+    H.set_initial_conditions()
+    got = []
+    for it in range(2):
+        nrm, its, st = H.nl_iteration()
+        got.append(nrm)
+        assert (its, st) == (log[it][0], log[it][1]), (it, its, st, log[it])
+    assert np.allclose(got, norms_o, rtol=1e-7), (got, norms_o)
+    psi = [H.download(q, "psi") for q in range(H.nodes)]
+    for q in range(H.nodes):
+        assert relerr(psi[q], psi_o[q]) < 1e-10, q
+    H.close()
+    o.close()
+    # the same with level 1 swept by the per-colour kernel: identical bits
+    ctx.set_option("fused_patch", 0)
+    try:
+        H = m.Hierarchy(ctx, P, [[l1], [b for b in l2]])
+        H.set_initial_conditions()
+        assert [H.nl_iteration()[0] for _ in range(2)] == got
+        for q in range(H.nodes):
+            assert np.array_equal(H.download(q, "psi"), psi[q]), q
+        H.close()
+    finally:
+        ctx.set_option("fused_patch", 1)
