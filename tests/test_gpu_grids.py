@@ -109,15 +109,16 @@ def test_reference_run_set_grids_then_solve(ctx):
     H.close(); g.close()
 
 
-def test_solve_on_the_generated_hierarchy_matches_the_twin(ctx):
+@pytest.mark.parametrize("max_level", [2, 3])
+def test_solve_on_the_generated_hierarchy_matches_the_twin(ctx, max_level):
     """set_grids' own hierarchy (BRMeshRefine's boxes, every connected part of a level one masked array) through three nonlinear
     iterations against the oracle-backed twin on the same boxes: BiCGStab counts, dpsi norms, psi on every node to 1e-10"""
     from amr_twin import hierarchy_nl_solve
     from test_amr_hierarchy import bare_hierarchy
-    P = default_params(**CASE)
+    P = default_params(**dict(CASE, max_level=max_level))
     mp = m.make_params(dict(P, max_NL_iterations=3))
     g = m.Grids.generate(ctx, mp, 0.1, 0.5)
-    assert g.levels == 3
+    assert g.levels == max_level + 1
     boxes = {l: [[(tuple(lo), tuple(hi)) for lo, hi in part] for part in g.nodes(l)] for l in range(1, g.levels)}
     assert max(len(part) for l in boxes for part in boxes[l]) > 1, "the case is meant to have parts made of several touching boxes"
     o, patches = bare_hierarchy(boxes, N=32, L=P["L"], box=16)
