@@ -340,7 +340,7 @@ def kernel_fingerprint():
     build it was captured on."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("gsrb_fused.cu", "mgic_device.cuh"):     # the kernel and the point update it inlines
+    for f in ("gsrb_fused.cu", "mgic_device.cuh", "tma.cuh"):     # the kernel, the point update and the TMA wrappers it inlines
         h.update(open(os.path.join(ROOT, "mg_ic_code_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -12,8 +12,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libmgic_b200.so")
-SOURCES = ["alloc.cu", "kernels.cu", "gsrb_fused.cu", "bottom.cu", "bottom_brick.cu", "bottom_dsmem.cu", "bottom_cbrick.cu", "source.cu", "grids.cu", "capi.cu", "chf_abi.cu", "comm.cu"]
-HEADERS = [os.path.join(CSRC, "mgic_internal.h"), os.path.join(CSRC, "mgic_device.cuh"), os.path.join(CSRC, "arena.h"), os.path.join(ROOT, "include", "mgic.h"),
+SOURCES = ["alloc.cu", "kernels.cu", "gsrb_fused.cu", "restrict_tma.cu", "bottom.cu", "bottom_brick.cu", "bottom_dsmem.cu", "bottom_cbrick.cu", "source.cu", "grids.cu", "capi.cu", "chf_abi.cu", "comm.cu"]
+HEADERS = [os.path.join(CSRC, "mgic_internal.h"), os.path.join(CSRC, "mgic_device.cuh"), os.path.join(CSRC, "arena.h"), os.path.join(CSRC, "tma.cuh"), os.path.join(ROOT, "include", "mgic.h"),
            os.path.join(ROOT, "include", "mgic_chf.h"), os.path.join(ROOT, "include", "mgic_comm.h")]
 
 

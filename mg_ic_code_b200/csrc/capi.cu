@@ -119,6 +119,7 @@ extern "C" int mgic_ctx_set_option(mgic_ctx *c, const char *name, long long valu
   else if (!strcmp(name, "use_graph")) c->useGraph = (int)value;
   else if (!strcmp(name, "fuse_transfers")) c->fusePR = (int)value;
   else if (!strcmp(name, "fused_patch")) c->fusedPatch = (int)value;
+  else if (!strcmp(name, "restrict_tma")) c->restrictTma = (int)value;
   else if (!strcmp(name, "agglo_cells")) c->aggloCells = value;
   else if (!strcmp(name, "overlap_halo")) c->overlapHalo = (int)value;
   else if (!strcmp(name, "p2p_halo")) c->p2pHalo = (int)value;
@@ -135,6 +136,7 @@ extern "C" long long mgic_ctx_get_option(mgic_ctx *c, const char *name) {
   if (!strcmp(name, "use_graph")) return c->useGraph;
   if (!strcmp(name, "fuse_transfers")) return c->fusePR;
   if (!strcmp(name, "fused_patch")) return c->fusedPatch;
+  if (!strcmp(name, "restrict_tma")) return c->restrictTma;
   if (!strcmp(name, "agglo_cells")) return c->aggloCells;
   if (!strcmp(name, "overlap_halo")) return c->overlapHalo;
   if (!strcmp(name, "p2p_halo")) return c->p2pHalo;
@@ -719,6 +721,7 @@ static int restrict_residual(mgic_op *o, mgic_field *resC, mgic_field *phi, cons
     MGIC_TRY(halo(o, phi, haloPlanes));  // :163
   }
   ProfScope ps(o->ctx, false, PROF_RESTRICT);
+  if (mgk::restrict_tma_applicable(o)) return mgk::restrict_tma(o, o->bck(true), resC, phi, rhs);
   return mgk::restrict_res(o->ctx, o->geom(), o->bck(true), resC->p, resC->sy, resC->sz, phi->p, rhs->p, o->a->p, bptr(o),
                            o->alpha, o->beta, o->dx);
 }

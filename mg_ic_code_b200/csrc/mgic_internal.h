@@ -132,6 +132,7 @@ struct mgic_ctx {
                                           // 0 host-driven launches
   int lastBottomKernel = -1;               // which bottom solver ran last: 0 host, 1 dsmem, 2 cluster, 3 coop, 4 brick, 5 cluster bricks
   int fusedPatch = 1;                     // 1: rectangular AMR patches are swept by the fused kernel too (coarse-fine faces by homogeneousCFInterp in the sweep)
+  int restrictTma = 1;                    // 1: restrictResidual of large rectangular levels by the plane-streaming kernel (restrict_tma.cu)
   int fusePR = 1;                         // 1: fold setToZero / prolongIncrement into the first fused sweep that follows
   long long aggloCells = 262144;          // multi-rank: depths whose slab has at most this many cells are agglomerated
   int useGraph = 1;                       // 1: replay each V-cycle as a CUDA graph
@@ -233,6 +234,9 @@ int apply_op(mgic_ctx *, const Geom &, const BCk &, double *lhs, const double *p
              double alpha, double beta, double dx);
 int residual(mgic_ctx *, const Geom &, const BCk &, double *res, const double *phi, const double *rhs, const double *a,
              const double *b, double alpha, double beta, double dx);
+// the same by the plane-streaming kernel (restrict_tma.cu): rectangular, non-periodic levels of at least fused_min_cells cells
+bool restrict_tma_applicable(const mgic_op *);
+int restrict_tma(mgic_op *, const BCk &, mgic_field *resC, const mgic_field *phi, const mgic_field *rhs);
 int restrict_res(mgic_ctx *, const Geom &fine, const BCk &, double *resC, long long csy, long long csz, const double *phi,
                  const double *rhs, const double *a, const double *b, double alpha, double beta, double dx);
 int prolong(mgic_ctx *, const Geom &fine, double *phi, const double *coarse, long long csy, long long csz,

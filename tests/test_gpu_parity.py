@@ -131,6 +131,40 @@ def test_fused_smoother_bit_exact(ctx, case, cfg):
         ctx.set_option("fused_cfg", 4)
 
 
+@pytest.mark.parametrize("keep_b", [False, True])
+@pytest.mark.parametrize("case", ["c16", "neumann", "c64", "c8", "wide"])
+def test_plane_streaming_restriction_bit_exact(ctx, case, keep_b):
+    """restrictResidual by the TMA-staged kernel (restrict_tma.cu: planes marched like the fused sweep, the eight contributions
+    of a coarse cell accumulated in the Fortran loop's order) == the oracle == the one-thread-per-coarse-cell kernel, on every
+    MG depth that can be coarsened (tiles larger than the level, ragged tiles, several z chunks, Neumann / inhomogeneous
+    boundary values, bCoef streamed or dropped).  By default only levels of >= fused_min_cells cells take it."""
+    ctx.set_option("fused_min_cells", 0)
+    try:
+        p = Pair(ctx, keep_b=keep_b, **CASES[case])
+        for d in range(p.nd - 1):
+            opd = p.f.MGnewOp(d)
+            ed, rd = (p.e, p.r) if d == 0 else p.f.scratch(d)
+            _, rc = p.f.scratch(d + 1)
+            rng = np.random.default_rng(20 + d)
+            ev, rv = rng.standard_normal(ed.shape), rng.standard_normal(ed.shape)
+            ed.upload(ev); rd.upload(rv)
+            p.o.set("E", ev, d); p.o.set("R", rv, d)
+            launches = ctx.launch_count
+            opd.restrictResidual(rc, ed, rd)
+            assert ctx.launch_count - launches == 1
+            got = rc.download()
+            p.o.restrict(d)
+            assert np.array_equal(got, p.o.get("R", d + 1)), d
+            ctx.set_option("restrict_tma", 0)                       # the same by k_restrict
+            rc.upload(np.zeros(rc.shape))
+            opd.restrictResidual(rc, ed, rd)
+            ctx.set_option("restrict_tma", 1)
+            assert np.array_equal(rc.download(), got), d
+    finally:
+        ctx.set_option("fused_min_cells", 2097152)
+        ctx.set_option("restrict_tma", 1)
+
+
 def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
     ctx.set_option("fused_min_cells", 0)
     try:
