@@ -81,6 +81,7 @@ k_restrict_tma(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant
   const bool inDom = x >= 0 && x + 1 < A.g.nx && y < A.g.ny;
   const bool out = inDom && lane >= 1 && lane <= 30;
   const bool bx0 = (x == 0), bxn = (x == A.g.nx - 2), by0 = (y == 0), byn = (y == A.g.ny - 1);
+  const bool anyxy = bx0 || bxn || by0 || byn;
   const bool zloPhys = A.bc.type[4] != MGIC_FACE_INTERIOR, zhiPhys = A.bc.type[5] != MGIC_FACE_INTERIOR;
   const int s = (w + 1) * RRW + 2 * lane, cidx = w * RRW + 2 * lane;
   const BCk &bc = A.bc;
@@ -89,8 +90,10 @@ k_restrict_tma(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant
   for (int k = zs; k < ze; k++) {
     const int rel = k - pfirst;                                             // >= 1
     const int sm = (rel - 1) % RNS, sc = rel % RNS, sp = (rel + 1) % RNS;
-    mbar_wait(&full[sm], ((rel - 1) / RNS) & 1);
-    mbar_wait(&full[sc], (rel / RNS) & 1);
+    if (k == zs) {   // the two older planes were waited for in the previous steps
+      mbar_wait(&full[sm], ((rel - 1) / RNS) & 1);
+      mbar_wait(&full[sc], (rel / RNS) & 1);
+    }
     mbar_wait(&full[sp], ((rel + 1) / RNS) & 1);
     const double *pm = slots + (size_t)sm * R::SLOT, *pc = slots + (size_t)sc * R::SLOT, *pp = slots + (size_t)sp * R::SLOT;
     const double2 c = *reinterpret_cast<const double2 *>(pc + s);
@@ -99,10 +102,12 @@ k_restrict_tma(const __grid_constant__ CUtensorMap tm_phi, const __grid_constant
     // x neighbours: inside the pair, and the neighbouring lanes' near elements
     double xm0 = __shfl_up_sync(FULL, c.y, 1), xp1 = __shfl_down_sync(FULL, c.x, 1);
     double xp0 = c.y, xm1 = c.x;
-    if (bx0) xm0 = bc.a[0] * c.x + bc.b[0];
-    if (bxn) xp1 = bc.a[1] * c.y + bc.b[1];
-    if (by0) { ym.x = bc.a[2] * c.x + bc.b[2]; ym.y = bc.a[2] * c.y + bc.b[2]; }
-    if (byn) { yp.x = bc.a[3] * c.x + bc.b[3]; yp.y = bc.a[3] * c.y + bc.b[3]; }
+    if (anyxy) {
+      if (bx0) xm0 = bc.a[0] * c.x + bc.b[0];
+      if (bxn) xp1 = bc.a[1] * c.y + bc.b[1];
+      if (by0) { ym.x = bc.a[2] * c.x + bc.b[2]; ym.y = bc.a[2] * c.y + bc.b[2]; }
+      if (byn) { yp.x = bc.a[3] * c.x + bc.b[3]; yp.y = bc.a[3] * c.y + bc.b[3]; }
+    }
     if (k == 0 && zloPhys) { zm.x = bc.a[4] * c.x + bc.b[4]; zm.y = bc.a[4] * c.y + bc.b[4]; }
     if (k == A.g.nz - 1 && zhiPhys) { zp.x = bc.a[5] * c.x + bc.b[5]; zp.y = bc.a[5] * c.y + bc.b[5]; }
     const double2 av = *reinterpret_cast<const double2 *>(pc + R::PLANE + cidx);
