@@ -165,6 +165,42 @@ def test_plane_streaming_restriction_bit_exact(ctx, case, keep_b):
         ctx.set_option("restrict_tma", 1)
 
 
+TILE_EDGE_SHAPES = [   # (N, max_grid_size): x sizes around the 60-cell tile / 64-cell staged row, y around the 8- / 10- / 12-row tiles, short z
+    ((60, 12, 8), 4), ((64, 12, 8), 4), ((68, 28, 36), 4), ((120, 24, 16), 8), ((124, 20, 12), 4), ((56, 16, 8), 8), ((128, 24, 24), 8),
+    ((62, 14, 18), 2), ((66, 26, 34), 2), ((122, 10, 8), 2), ((58, 22, 18), 2),
+]
+
+
+@pytest.mark.parametrize("shape", TILE_EDGE_SHAPES, ids=lambda s: "x".join(map(str, s[0])))
+def test_tile_edges_of_the_plane_streaming_kernels(ctx, shape):
+    """level sizes that put domain edges just inside, on and just outside tile edges of the two TMA kernels (fused sweep: 60 x
+    {8, 10} output cells of a 64-wide staged row; restriction: 60 x 12), with Dirichlet / Neumann faces mixed and a non-zero
+    boundary value: sweeps and restriction bit-exact against the oracle on every depth"""
+    N, box = shape
+    rng = np.random.default_rng(sum(N))
+    bc_lo, bc_hi = tuple(int(v) for v in rng.integers(0, 2, 3)), tuple(int(v) for v in rng.integers(0, 2, 3))
+    ctx.set_option("fused_min_cells", 0)
+    try:
+        p = Pair(ctx, smoother=1, N=N, max_grid_size=box, L=50.0, bc_lo=bc_lo, bc_hi=bc_hi, bc_value=0.125)
+        for d in range(p.nd):
+            opd = p.f.MGnewOp(d)
+            ed, rd = (p.e, p.r) if d == 0 else p.f.scratch(d)
+            ev, rv = rng.standard_normal(ed.shape), rng.standard_normal(ed.shape)
+            ed.upload(ev); rd.upload(rv)
+            p.o.set("E", ev, d); p.o.set("R", rv, d)
+            for its in (1, 2):
+                opd.relax(ed, rd, its)
+                p.o.relax(d, its)
+                assert np.array_equal(ed.download(), p.o.get("E", d)), (d, its)
+            if d + 1 < p.nd:
+                _, rc = p.f.scratch(d + 1)
+                opd.restrictResidual(rc, ed, rd)
+                p.o.restrict(d)
+                assert np.array_equal(rc.download(), p.o.get("R", d + 1)), d
+    finally:
+        ctx.set_option("fused_min_cells", 2097152)
+
+
 def test_fused_smoother_keep_b_and_inhomogeneous_value(ctx):
     ctx.set_option("fused_min_cells", 0)
     try:
