@@ -564,6 +564,29 @@ def run_gpu(args):
             pb.close()
             pb = None
         parity = multirank_parity(m, ctx, args, dist, rank, world, local)
+    # ---- the same weak-scaling V-cycle with the reference's max_grid_size at 64 (params.txt key; it sets the MG depth,
+    # Factory.cpp:168-172): one level more, so the coarsest -- at N > 1 agglomerated -- level is 8x smaller.  Reported
+    # next to the headline configuration because that level is what costs the headline its parallel efficiency.
+    alt = None
+    if args.box != 64 and not args.no_alt and args.scaling == "weak":
+        import types
+        a2 = types.SimpleNamespace(**dict(vars(args), box=64))
+        if world > 1 and pb is not None:
+            pb.close()
+            pb = None
+        pa = Problem(m, ctx, a2, N, 100.0 * mult[0], k0, nzl)
+        for _ in range(max(args.warmup, 3)):
+            pa.step()
+        ms_a, _, _ = time_steps(pa, args.steps, barrier, stream, torch)
+        alt_iters, alt_depths = pa.f.last_bottom_iterations, pa.f.depths
+        pa.close()
+        if dist is not None:
+            t = torch.tensor([ms_a], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_a = t.item()
+        alt = {"what": "the same V-cycle with max_grid_size = 64 instead of %d (the reference's params.txt key; one MG level more)" % args.box,
+               "ms_per_step": ms_a / args.steps, "value": cells_total / (ms_a / args.steps * 1e-3) / 1e9, "unit": UNIT,
+               "mg_depths": alt_depths, "bottom_bicgstab_iterations": alt_iters}
     if rank == 0:
         ms_step = ms / args.steps
         value = cells_total / (ms_step * 1e-3) / 1e9
@@ -617,6 +640,8 @@ def run_gpu(args):
             line["details"]["halo"] = halo_info
         if strong:
             line["strong"] = strong
+        if alt:
+            line["max_grid_size_64"] = alt
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"], parity = cpu_baseline_and_parity(args, pb, ms_step)
         if parity:
@@ -643,6 +668,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=0, help="side of the CPU problem (default: the workload's own n)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling (config C3) sub-record")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the multi-rank vs one-GPU bit comparison")
+    ap.add_argument("--no-alt", action="store_true", help="skip the max_grid_size = 64 sub-record")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (mgic_ctx_set_option), repeatable")
     ap.add_argument("--smooth", type=int, default=2, help="numMGsmooth (pre = post = bottom)")
     ap.add_argument("--box", type=int, default=32, help="max_grid_size (sets the MG depth, Factory.cpp:168-172)")
