@@ -95,7 +95,7 @@ long long mgic_ctx_launch_count(mgic_ctx *);
  * this many cells are gathered onto every rank), "overlap_halo" (multi-rank: exchange on a second stream while the
  * interior planes are swept), "p2p_halo" (multi-rank: 1 halo planes by NVLink peer stores, 0 ncclSend/ncclRecv; same
  * value on every rank), "fold_halo" (multi-rank: 1 the fused sweep stores its boundary planes into the neighbours' ghost planes
- * itself instead of an exchange kernel before every sweep; measured slower, default 0), "restrict_tma" (1: restrictResidual of rectangular, non-periodic levels of at least 16 x fused_min_cells cells by the
+ * itself instead of an exchange kernel before every sweep; measured slower, default 0), "restrict_tma" (1: restrictResidual of rectangular, non-periodic levels of at least 8 x fused_min_cells cells (256^3) by the
  * plane-streaming kernel; 0: one thread per coarse cell everywhere; same bits), "fused_patch" (1: AMR levels that are
  * one box are swept by the fused kernel too, homogeneousCFInterp evaluated in the sweep; 0: per-colour kernel).  Fields do not depend on fused_* / use_graph / *_halo; bottom_kernel changes only the
  * summation order of the bottom solver's dot products. */

@@ -234,7 +234,7 @@ int apply_op(mgic_ctx *, const Geom &, const BCk &, double *lhs, const double *p
              double alpha, double beta, double dx);
 int residual(mgic_ctx *, const Geom &, const BCk &, double *res, const double *phi, const double *rhs, const double *a,
              const double *b, double alpha, double beta, double dx);
-// the same by the plane-streaming kernel (restrict_tma.cu): rectangular, non-periodic levels of at least 16 x fused_min_cells cells
+// the same by the plane-streaming kernel (restrict_tma.cu): rectangular, non-periodic levels of at least 8 x fused_min_cells cells
 bool restrict_tma_applicable(const mgic_op *);
 int restrict_tma(mgic_op *, const BCk &, mgic_field *resC, const mgic_field *phi, const mgic_field *rhs);
 int restrict_res(mgic_ctx *, const Geom &fine, const BCk &, double *resC, long long csy, long long csz, const double *phi,

@@ -189,10 +189,10 @@ bool restrict_tma_applicable(const mgic_op *o) {
   if (!o->ctx->restrictTma || o->isPatch || o->mask) return false;
   for (int d = 0; d < 3; d++)
     if (o->bc_lo[d] == MGIC_BC_PERIODIC) return false;
-  // measured per level under ncu (first version of this kernel vs k_restrict): 512^3 613 vs 688 us (now 525), 256^3 96 vs 94 us,
-  // 128^3 21 vs 18 us -- the streaming kernel pays from a few tens of millions of cells on
+  // measured per level: 512^3 525 vs 688 us under ncu; 256^3: the level's restrictions 123 vs 135 us per V-cycle
+  // (bench.py --n 256, profiles/r3s_*); 128^3 no gain (21 vs 18 us with the kernel's first version) -- from 256^3 on
   const long long cells = (long long)o->n[0] * o->n[1] * o->nzl;
-  return !(o->n[0] & 1) && !(o->n[1] & 1) && !(o->nzl & 1) && o->n[0] >= 8 && cells >= 16 * o->ctx->fusedMinCells;
+  return !(o->n[0] & 1) && !(o->n[1] & 1) && !(o->nzl & 1) && o->n[0] >= 8 && cells >= 8 * o->ctx->fusedMinCells;
 }
 
 // resC = restriction of rhs - L(phi) (homogeneous boundary values: bc), phi's z ghost planes already exchanged

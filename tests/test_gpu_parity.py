@@ -137,7 +137,7 @@ def test_plane_streaming_restriction_bit_exact(ctx, case, keep_b):
     """restrictResidual by the TMA-staged kernel (restrict_tma.cu: planes marched like the fused sweep, the eight contributions
     of a coarse cell accumulated in the Fortran loop's order) == the oracle == the one-thread-per-coarse-cell kernel, on every
     MG depth that can be coarsened (tiles larger than the level, ragged tiles, several z chunks, Neumann / inhomogeneous
-    boundary values, bCoef streamed or dropped).  By default only levels of >= 16 x fused_min_cells cells take it."""
+    boundary values, bCoef streamed or dropped).  By default only levels of >= 8 x fused_min_cells cells (256^3) take it."""
     ctx.set_option("fused_min_cells", 0)
     try:
         p = Pair(ctx, keep_b=keep_b, **CASES[case])
